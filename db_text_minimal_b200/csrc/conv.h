@@ -1,0 +1,77 @@
+// conv.h -- host-side interface of the tcgen05 implicit-GEMM kernels (conv_tcgen05.cu), used by net.cu
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace dbb {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int IGEMM_MAX_TAPS = 16;
+
+// One implicit-GEMM launch:  Y[pixel, co] = sum_{tap, ci} X[pixel @ tap, ci] * Wp[co, tap*cin + ci]  (+ bias[co])
+//
+// "pixel" runs over an M-space grid (mn, mh, mw); row (n,h,w) reads X at (n, h*in_sh + dh[tap], w*in_sw + dw[tap])
+// (zero outside the tensor) and writes Y at (n, h*out_sh + out_oh, w*out_sw + out_ow).  This one form covers Conv2d
+// fprop (any stride), Conv2d dgrad (stride-1 directly; stride-2 as parity classes), ConvTranspose2d(k2,s2) fprop
+// (4 classes) and dgrad.
+struct IgemmPlan {
+  CUtensorMap tmap_x;      // 4-D {C, W, H, N} bf16 NHWC, box {64, bw*in_sw, bh*in_sh, bn}, 128B swizzle
+  CUtensorMap tmap_w;      // 2-D {K, Cout} bf16 K-major, box {64, block_n}, 128B swizzle
+  int mn, mh, mw;          // M-space extent
+  int bn, bh, bw;          // tile box, bn*bh*bw <= 128
+  int tiles_n, tiles_h, tiles_w;
+  int in_sh, in_sw;
+  int ntaps;
+  int8_t dh[IGEMM_MAX_TAPS], dw[IGEMM_MAX_TAPS];
+  uint8_t wtap[IGEMM_MAX_TAPS];   // index of tap t inside the packed weight matrix (K offset = wtap[t]*cin)
+  int cin;                 // channels reduced per tap (multiple of 64)
+  int cout;                // valid output channels (GEMM N)
+  int block_n;             // 64 / 128 / 256
+  // output
+  bf16* y;
+  int out_h, out_w, out_c; // Y tensor extent (NHWC), out_c = channel stride
+  int out_sh, out_sw, out_oh, out_ow;
+  int out_coff;            // channel offset inside Y's channel dimension
+  const float* bias;       // may be null
+};
+
+// weight packing: fp32 parameter -> bf16 GEMM B matrix [rows][K] (K-major)
+//   mode 0: Conv2d OIHW (co,ci,kh,kw)       -> [co][(kh*KW+kw)*ci_n + ci]                 (fprop)
+//   mode 1: Conv2d OIHW                      -> [ci][(kh*KW+kw)*co_n + co]                 (dgrad)
+//   mode 2: ConvT   (ci,co,2,2)              -> [cls=(a*2+b)][co][ci]   4 matrices         (fprop, one per class)
+//   mode 3: ConvT   (ci,co,2,2)              -> [ci][(a*2+b)*co_n + co]                    (dgrad)
+//   mode 4: conv1 7x7/2 OIHW (64,3,7,7)      -> [co][kh2(4)][kw2(4)][16]  space-to-depth form, K = 256
+int pack_weights(int mode, const float* w, bf16* out, int co_n, int ci_n, int kh, int kw, cudaStream_t s);
+
+int igemm_plan_init(IgemmPlan* p, const bf16* x, int n, int h, int w, int c_total, int c_off, int cin,
+                    const bf16* wp, int k_total, int w_rows, int block_n);
+int igemm_launch(const IgemmPlan& p, cudaStream_t s);
+
+// weight gradient:  dW[m][n][tap] (+)= sum_pixel A[pixel @ (a-side map)][m] * B[pixel @ tap][n]
+struct WgradPlan {
+  CUtensorMap tmap_a;      // M-side operand (dy for Conv2d, x for ConvT): 4-D NHWC, box {64, bw*a_sw, bh*a_sh, bn}
+  CUtensorMap tmap_b;      // N-side operand
+  int mn, mh, mw;          // pixel grid reduced over
+  int bn, bh, bw;          // 64-pixel box
+  int tiles_n, tiles_h, tiles_w;
+  int a_sh, a_sw, b_sh, b_sw;
+  int ntaps;
+  int8_t a_dh[IGEMM_MAX_TAPS], a_dw[IGEMM_MAX_TAPS], b_dh[IGEMM_MAX_TAPS], b_dw[IGEMM_MAX_TAPS];
+  int m_total, n_total;    // GEMM M (rows of dW), N
+  int m_tile, n_tile;      // 64|128, 64|128|256
+  int split_k;
+  float* dw;               // fp32, layout [m][n][tap] (== OIHW for Conv2d, (ci,co,a,b) for ConvT); atomically accumulated
+  int tap_stride;          // ntaps of the destination layout
+};
+int wgrad_launch(const WgradPlan& p, cudaStream_t s);
+
+int encode_tmap_raw4(CUtensorMap* m, const bf16* base, const cuuint64_t dims[4], const cuuint64_t strides_bytes[3],
+                     const cuuint32_t box[4]);
+int encode_tmap_nhwc(CUtensorMap* m, const bf16* base, int n, int h, int w, int c_total, int c_off, int c_extent,
+                     int box_n, int box_h, int box_w, int stride_h, int stride_w);
+void choose_box(int rows, int mn, int mh, int mw, int* bn, int* bh, int* bw);
+
+}  // namespace dbb

@@ -1,0 +1,244 @@
+// conv_ops.cu -- builds igemm / wgrad plans for the convolution flavours of the DB network and exposes the
+// single-operator C ABI (dbb_conv2d, dbb_conv2d_wgrad) used by the parity tests and the module drop-ins.
+#include "common.cuh"
+#include "conv.h"
+#include "conv_ops.h"
+
+namespace dbb {
+
+static int pick_block_n(int cout, int64_t m_tiles) {
+  // wide N tiles amortise the A-tile fetch; fall back to narrower tiles when there are too few CTAs to fill the GPU
+  if (cout >= 256 && m_tiles >= 2 * DBB_NUM_SMS) return 256;
+  if (cout >= 128) return 128;
+  return 64;
+}
+
+static void finish_tiles(IgemmPlan* p) {
+  (void)p;
+}
+
+int conv_fprop(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const bf16* wp, const float* bias, bf16* y,
+               int y_ctotal, int y_coff, cudaStream_t s) {
+  const int ho = g.out_h(), wo = g.out_w();
+  IgemmPlan p;
+  memset(&p, 0, sizeof(p));
+  p.mn = g.n; p.mh = ho; p.mw = wo;
+  p.in_sh = p.in_sw = g.stride;
+  p.ntaps = g.ks * g.ks;
+  for (int kh = 0; kh < g.ks; ++kh)
+    for (int kw = 0; kw < g.ks; ++kw) {
+      const int t = kh * g.ks + kw;
+      p.dh[t] = (int8_t)(kh - g.pad); p.dw[t] = (int8_t)(kw - g.pad); p.wtap[t] = (uint8_t)t;
+    }
+  p.cout = g.cout;
+  p.y = y; p.out_h = ho; p.out_w = wo; p.out_c = y_ctotal; p.out_coff = y_coff;
+  p.out_sh = p.out_sw = 1; p.out_oh = p.out_ow = 0;
+  p.bias = bias;
+  const int64_t m_tiles = ((int64_t)g.n * ho * wo + 127) / 128;
+  int rc = igemm_plan_init(&p, x, g.n, g.h, g.w, x_ctotal, x_coff, g.cin, wp, p.ntaps * g.cin, g.cout, pick_block_n(g.cout, m_tiles));
+  if (rc) return rc;
+  return igemm_launch(p, s);
+}
+
+int conv_dgrad(const ConvGeom& g, const bf16* dy, const bf16* wp_t, bf16* dx, cudaStream_t s) {
+  // dx[n,h,w,ci] = sum_{kh,kw,co} dy[n,(h+pad-kh)/s,(w+pad-kw)/s,co] * W[co,ci,kh,kw]   (where divisible)
+  const int ho = g.out_h(), wo = g.out_w();
+  const int st = g.stride;
+  if (st != 1 && st != 2) return set_error(DBB_EUNSUPPORTED, "conv_dgrad: stride must be 1 or 2");
+  bool need_zero = false;
+  for (int a = 0; a < st; ++a)
+    for (int b = 0; b < st; ++b) {
+      int nt = 0;
+      for (int kh = 0; kh < g.ks; ++kh) for (int kw = 0; kw < g.ks; ++kw)
+        if ((a + g.pad - kh) % st == 0 && (b + g.pad - kw) % st == 0) ++nt;
+      if (nt == 0) need_zero = true;
+    }
+  if (need_zero) DBB_CUDA(cudaMemsetAsync(dx, 0, sizeof(bf16) * (size_t)g.n * g.h * g.w * g.cin, s));
+  for (int a = 0; a < st; ++a)
+    for (int b = 0; b < st; ++b) {
+      IgemmPlan p;
+      memset(&p, 0, sizeof(p));
+      p.mn = g.n; p.mh = (g.h - a + st - 1) / st; p.mw = (g.w - b + st - 1) / st;
+      if (p.mh <= 0 || p.mw <= 0) continue;
+      p.in_sh = p.in_sw = 1;
+      int nt = 0;
+      for (int kh = 0; kh < g.ks; ++kh)
+        for (int kw = 0; kw < g.ks; ++kw) {
+          const int eh = a + g.pad - kh, ew = b + g.pad - kw;
+          if (eh % st != 0 || ew % st != 0) continue;
+          p.dh[nt] = (int8_t)(eh / st); p.dw[nt] = (int8_t)(ew / st); p.wtap[nt] = (uint8_t)(kh * g.ks + kw);
+          ++nt;
+        }
+      if (nt == 0) continue;
+      p.ntaps = nt;
+      p.cout = g.cin;
+      p.y = dx; p.out_h = g.h; p.out_w = g.w; p.out_c = g.cin; p.out_coff = 0;
+      p.out_sh = p.out_sw = st; p.out_oh = a; p.out_ow = b;
+      p.bias = nullptr;
+      const int64_t m_tiles = ((int64_t)p.mn * p.mh * p.mw + 127) / 128;
+      int rc = igemm_plan_init(&p, dy, g.n, ho, wo, g.cout, 0, g.cout, wp_t, g.ks * g.ks * g.cout, g.cin, pick_block_n(g.cin, m_tiles));
+      if (rc) return rc;
+      rc = igemm_launch(p, s);
+      if (rc) return rc;
+    }
+  return DBB_OK;
+}
+
+int convt_fprop(const ConvGeom& g, const bf16* x, const bf16* wp_cls, const float* bias, bf16* y, cudaStream_t s) {
+  // ConvTranspose2d(k=2, s=2): y[n,2i+a,2j+b,co] = sum_ci x[n,i,j,ci] * W[ci,co,a,b] + bias[co]
+  for (int cls = 0; cls < 4; ++cls) {
+    IgemmPlan p;
+    memset(&p, 0, sizeof(p));
+    p.mn = g.n; p.mh = g.h; p.mw = g.w;
+    p.in_sh = p.in_sw = 1;
+    p.ntaps = 1; p.dh[0] = 0; p.dw[0] = 0; p.wtap[0] = 0;
+    p.cout = g.cout;
+    p.y = y; p.out_h = 2 * g.h; p.out_w = 2 * g.w; p.out_c = g.cout; p.out_coff = 0;
+    p.out_sh = p.out_sw = 2; p.out_oh = cls >> 1; p.out_ow = cls & 1;
+    p.bias = bias;
+    const int64_t m_tiles = ((int64_t)g.n * g.h * g.w + 127) / 128;
+    int rc = igemm_plan_init(&p, x, g.n, g.h, g.w, g.cin, 0, g.cin, wp_cls + (size_t)cls * g.cout * g.cin, g.cin, g.cout,
+                             pick_block_n(g.cout, m_tiles));
+    if (rc) return rc;
+    rc = igemm_launch(p, s);
+    if (rc) return rc;
+  }
+  return DBB_OK;
+}
+
+int convt_dgrad(const ConvGeom& g, const bf16* dy, const bf16* wp_t, bf16* dx, cudaStream_t s) {
+  // dx[n,i,j,ci] = sum_{a,b,co} dy[n,2i+a,2j+b,co] * W[ci,co,a,b]
+  IgemmPlan p;
+  memset(&p, 0, sizeof(p));
+  p.mn = g.n; p.mh = g.h; p.mw = g.w;
+  p.in_sh = p.in_sw = 2;
+  p.ntaps = 4;
+  for (int t = 0; t < 4; ++t) { p.dh[t] = (int8_t)(t >> 1); p.dw[t] = (int8_t)(t & 1); p.wtap[t] = (uint8_t)t; }
+  p.cout = g.cin;
+  p.y = dx; p.out_h = g.h; p.out_w = g.w; p.out_c = g.cin; p.out_coff = 0;
+  p.out_sh = p.out_sw = 1; p.out_oh = p.out_ow = 0;
+  const int64_t m_tiles = ((int64_t)g.n * g.h * g.w + 127) / 128;
+  int rc = igemm_plan_init(&p, dy, g.n, 2 * g.h, 2 * g.w, g.cout, 0, g.cout, wp_t, 4 * g.cout, g.cin, pick_block_n(g.cin, m_tiles));
+  if (rc) return rc;
+  return igemm_launch(p, s);
+}
+
+static int pick_split_k(int64_t out_tiles, int total_pixel_tiles) {
+  int64_t want = (2 * DBB_NUM_SMS + out_tiles - 1) / out_tiles;
+  if (want < 1) want = 1;
+  if (want > total_pixel_tiles) want = total_pixel_tiles;
+  return (int)want;
+}
+
+static int wgrad_common(WgradPlan& p, const bf16* a, int a_n, int a_h, int a_w, int a_c, const bf16* b, int b_n, int b_h,
+                        int b_w, int b_c, cudaStream_t s) {
+  choose_box(64, p.mn, p.mh, p.mw, &p.bn, &p.bh, &p.bw);
+  p.tiles_n = (p.mn + p.bn - 1) / p.bn;
+  p.tiles_h = (p.mh + p.bh - 1) / p.bh;
+  p.tiles_w = (p.mw + p.bw - 1) / p.bw;
+  p.m_tile = 128;
+  p.n_tile = p.n_total >= 256 ? 256 : (p.n_total >= 128 ? 128 : 64);
+  const int m_tiles = (p.m_total + 127) / 128, n_tiles = (p.n_total + p.n_tile - 1) / p.n_tile;
+  p.split_k = pick_split_k((int64_t)p.ntaps * m_tiles * n_tiles, p.tiles_n * p.tiles_h * p.tiles_w);
+  int rc = encode_tmap_nhwc(&p.tmap_a, a, a_n, a_h, a_w, a_c, 0, a_c, p.bn, p.bh, p.bw, p.a_sh, p.a_sw);
+  if (rc) return rc;
+  rc = encode_tmap_nhwc(&p.tmap_b, b, b_n, b_h, b_w, b_c, 0, b_c, p.bn, p.bh, p.bw, p.b_sh, p.b_sw);
+  if (rc) return rc;
+  return wgrad_launch(p, s);
+}
+
+int conv_wgrad(const ConvGeom& g, const bf16* x, const bf16* dy, float* dw, cudaStream_t s) {
+  // dW[co,ci,kh,kw] = sum_{n,i,j} dy[n,i,j,co] * x[n, i*s+kh-pad, j*s+kw-pad, ci]
+  const int ho = g.out_h(), wo = g.out_w();
+  DBB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g.cout * g.cin * g.ks * g.ks, s));
+  WgradPlan p;
+  memset(&p, 0, sizeof(p));
+  p.mn = g.n; p.mh = ho; p.mw = wo;
+  p.a_sh = p.a_sw = 1; p.b_sh = p.b_sw = g.stride;
+  p.ntaps = g.ks * g.ks;
+  for (int kh = 0; kh < g.ks; ++kh)
+    for (int kw = 0; kw < g.ks; ++kw) {
+      const int t = kh * g.ks + kw;
+      p.a_dh[t] = 0; p.a_dw[t] = 0; p.b_dh[t] = (int8_t)(kh - g.pad); p.b_dw[t] = (int8_t)(kw - g.pad);
+    }
+  p.m_total = g.cout; p.n_total = g.cin;
+  p.dw = dw; p.tap_stride = p.ntaps;
+  return wgrad_common(p, dy, g.n, ho, wo, g.cout, x, g.n, g.h, g.w, g.cin, s);
+}
+
+int convt_wgrad(const ConvGeom& g, const bf16* x, const bf16* dy, float* dw, cudaStream_t s) {
+  // dW[ci,co,a,b] = sum_{n,i,j} x[n,i,j,ci] * dy[n,2i+a,2j+b,co]
+  DBB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g.cout * g.cin * 4, s));
+  WgradPlan p;
+  memset(&p, 0, sizeof(p));
+  p.mn = g.n; p.mh = g.h; p.mw = g.w;
+  p.a_sh = p.a_sw = 1; p.b_sh = p.b_sw = 2;
+  p.ntaps = 4;
+  for (int t = 0; t < 4; ++t) { p.a_dh[t] = 0; p.a_dw[t] = 0; p.b_dh[t] = (int8_t)(t >> 1); p.b_dw[t] = (int8_t)(t & 1); }
+  p.m_total = g.cin; p.n_total = g.cout;
+  p.dw = dw; p.tap_stride = 4;
+  return wgrad_common(p, x, g.n, g.h, g.w, g.cin, dy, g.n, 2 * g.h, 2 * g.w, g.cout, s);
+}
+
+}  // namespace dbb
+
+using namespace dbb;
+
+// workspace of the single-operator entry: packed bf16 weights
+extern "C" size_t dbb_conv2d_workspace(int kind, int64_t n, int64_t h, int64_t wdt, int cin, int cout, int ksize, int stride, int pad) {
+  (void)kind; (void)n; (void)h; (void)wdt; (void)stride; (void)pad;
+  return ((size_t)cin * cout * ksize * ksize * sizeof(bf16) + 255) / 256 * 256;
+}
+
+static int check_geom(const char* who, int64_t n, int64_t h, int64_t w, int cin, int cout, int ks, int stride) {
+  if (n <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0) return set_error(DBB_EINVAL, who);
+  if (cin % 64 || cout % 64) return set_error(DBB_EUNSUPPORTED, "conv: channel counts must be multiples of 64");
+  if (ks != 1 && ks != 2 && ks != 3) return set_error(DBB_EUNSUPPORTED, "conv: kernel size must be 1, 2 (ConvT) or 3");
+  if (stride != 1 && stride != 2) return set_error(DBB_EUNSUPPORTED, "conv: stride must be 1 or 2");
+  return DBB_OK;
+}
+
+extern "C" int dbb_conv2d(int kind, const void* x, const float* w, const float* bias, void* y, int64_t n, int64_t h, int64_t wdt,
+                          int cin, int cout, int ksize, int stride, int pad, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x || !w || !y || !workspace) return set_error(DBB_EINVAL, "conv2d: null pointer");
+  int rc = check_geom("conv2d: bad shape", n, h, wdt, cin, cout, ksize, stride);
+  if (rc) return rc;
+  if (workspace_bytes < dbb_conv2d_workspace(kind, n, h, wdt, cin, cout, ksize, stride, pad)) return set_error(DBB_EWORKSPACE, "conv2d: workspace too small");
+  if (!aligned16(x) || !aligned16(y) || !aligned16(workspace)) return set_error(DBB_EALIGN, "conv2d: pointer not 16B aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  ConvGeom g{(int)n, (int)h, (int)wdt, cin, cout, ksize, stride, pad};
+  bf16* wp = (bf16*)workspace;
+  switch (kind) {
+    case 0:
+      if ((rc = pack_weights(0, w, wp, cout, cin, ksize, ksize, s))) return rc;
+      return conv_fprop(g, (const bf16*)x, cin, 0, wp, bias, (bf16*)y, cout, 0, s);
+    case 1:   // x := dy (n, ho, wo, cout), y := dx (n, h, w, cin)
+      if ((rc = pack_weights(1, w, wp, cout, cin, ksize, ksize, s))) return rc;
+      return conv_dgrad(g, (const bf16*)x, wp, (bf16*)y, s);
+    case 2:
+      if (ksize != 2 || stride != 2) return set_error(DBB_EUNSUPPORTED, "convT: only k=2, s=2");
+      if ((rc = pack_weights(2, w, wp, cout, cin, 2, 2, s))) return rc;
+      return convt_fprop(g, (const bf16*)x, wp, bias, (bf16*)y, s);
+    case 3:
+      if (ksize != 2 || stride != 2) return set_error(DBB_EUNSUPPORTED, "convT: only k=2, s=2");
+      if ((rc = pack_weights(3, w, wp, cout, cin, 2, 2, s))) return rc;
+      return convt_dgrad(g, (const bf16*)x, wp, (bf16*)y, s);
+    default: return set_error(DBB_EINVAL, "conv2d: kind must be 0..3");
+  }
+}
+
+extern "C" int dbb_conv2d_wgrad(int kind, const void* x, const void* dy, float* dw, int64_t n, int64_t h, int64_t wdt, int cin,
+                                int cout, int ksize, int stride, int pad, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  if (!x || !dy || !dw) return set_error(DBB_EINVAL, "conv2d_wgrad: null pointer");
+  int rc = check_geom("conv2d_wgrad: bad shape", n, h, wdt, cin, cout, ksize, stride);
+  if (rc) return rc;
+  if (!aligned16(x) || !aligned16(dy) || !aligned16(dw)) return set_error(DBB_EALIGN, "conv2d_wgrad: pointer not 16B aligned");
+  ConvGeom g{(int)n, (int)h, (int)wdt, cin, cout, ksize, stride, pad};
+  if (kind == 0) return conv_wgrad(g, (const bf16*)x, (const bf16*)dy, dw, (cudaStream_t)stream);
+  if (kind == 2) {
+    if (ksize != 2 || stride != 2) return set_error(DBB_EUNSUPPORTED, "convT: only k=2, s=2");
+    return convt_wgrad(g, (const bf16*)x, (const bf16*)dy, dw, (cudaStream_t)stream);
+  }
+  return set_error(DBB_EINVAL, "conv2d_wgrad: kind must be 0 (Conv2d) or 2 (ConvTranspose2d)");
+}

@@ -1,0 +1,26 @@
+// conv_ops.h -- convolution flavours of the DB network expressed as igemm / wgrad plans
+#pragma once
+#include "conv.h"
+#include <string.h>
+
+namespace dbb {
+
+// h, w are the spatial extent of the (forward) INPUT; for ConvTranspose2d(k2,s2) the output is (2h, 2w)
+struct ConvGeom {
+  int n, h, w, cin, cout, ks, stride, pad;
+  int out_h() const { return (h + 2 * pad - ks) / stride + 1; }
+  int out_w() const { return (w + 2 * pad - ks) / stride + 1; }
+};
+
+// wp: packed by pack_weights mode 0 ; x may be a channel slice [x_coff, x_coff+cin) of a wider NHWC tensor
+int conv_fprop(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const bf16* wp, const float* bias, bf16* y,
+               int y_ctotal, int y_coff, cudaStream_t s);
+// wp_t: packed by pack_weights mode 1
+int conv_dgrad(const ConvGeom& g, const bf16* dy, const bf16* wp_t, bf16* dx, cudaStream_t s);
+int conv_wgrad(const ConvGeom& g, const bf16* x, const bf16* dy, float* dw, cudaStream_t s);
+// ConvTranspose2d(k=2, s=2); wp_cls: mode 2, wp_t: mode 3
+int convt_fprop(const ConvGeom& g, const bf16* x, const bf16* wp_cls, const float* bias, bf16* y, cudaStream_t s);
+int convt_dgrad(const ConvGeom& g, const bf16* dy, const bf16* wp_t, bf16* dx, cudaStream_t s);
+int convt_wgrad(const ConvGeom& g, const bf16* x, const bf16* dy, float* dw, cudaStream_t s);
+
+}  // namespace dbb

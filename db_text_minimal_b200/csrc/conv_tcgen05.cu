@@ -1,0 +1,453 @@
+// conv_tcgen05.cu -- implicit-GEMM convolutions on the 5th-generation tensor cores (sm_100a).
+//
+// Replaces the cuDNN/oneDNN calls under nn.Conv2d / nn.ConvTranspose2d on the reference's hot path
+// (src/modules/resnet.py:73-86,232; segmentation_body.py:67-76; segmentation_head.py:25-29,64-76):
+//   * igemm_kernel  : forward / data-gradient.  A = activation tile fetched by TMA straight from the NHWC tensor
+//                     (one 4-D box per filter tap; padding = TMA out-of-bounds zero fill; stride = TMA element
+//                     stride), B = packed bf16 weights (2-D TMA), 128-byte swizzle, tcgen05.mma kind::f16 with the
+//                     fp32 accumulator in TMEM, epilogue tcgen05.ld -> +bias -> bf16 NHWC store.  No im2col buffer.
+//   * wgrad_kernel  : weight gradient.  Both operands MN-major (pixels are the GEMM K), split-K over pixel tiles,
+//                     fp32 red.global.add into the OIHW gradient.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (one TMEM lane quadrant each).  smem ring of STAGES {A,B} tiles with full/empty mbarriers.
+#include "common.cuh"
+#include "conv.h"
+#include "tcgen05.cuh"
+#include <mutex>
+
+namespace dbb {
+
+using namespace ptx;
+
+constexpr int IG_THREADS = 192;
+constexpr int A_TILE_BYTES = 128 * 128;   // 128 rows x 64 bf16
+
+template <int BLOCK_N, int STAGES>
+struct IgemmSmem {
+  static constexpr int B_TILE_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // + barriers + alignment slack
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(IG_THREADS)
+igemm_kernel(const __grid_constant__ IgemmPlan p) {
+  using SM = IgemmSmem<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_blocks = (p.cout + BLOCK_N - 1) / BLOCK_N;
+  const int nblk = blockIdx.x % n_blocks;
+  int tile = blockIdx.x / n_blocks;
+  const int tw = tile % p.tiles_w; tile /= p.tiles_w;
+  const int th = tile % p.tiles_h; tile /= p.tiles_h;
+  const int tn = tile;
+  const int n0 = tn * p.bn, h0 = th * p.bh, w0 = tw * p.bw;
+  const int cin_chunks = p.cin >> 6;
+  const int kiters = p.ntaps * cin_chunks;
+  const uint32_t a_bytes = (uint32_t)(p.bn * p.bh * p.bw) * 128u;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmap_x);
+    prefetch_tmap(&p.tmap_w);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BLOCK_N>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        const int tap = it / cin_chunks, cc = it - tap * cin_chunks;
+        uint8_t* sa = smem + s * SM::STAGE_BYTES;
+        uint8_t* sb = sa + A_TILE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], a_bytes + (uint32_t)SM::B_TILE_BYTES);
+        tma_load_4d(sa, &p.tmap_x, &full_bar[s], cc * 64, w0 * p.in_sw + p.dw[tap], h0 * p.in_sh + p.dh[tap], n0);
+        tma_load_2d(sb, &p.tmap_w, &full_bar[s], (int)p.wtap[tap] * p.cin + cc * 64, nblk * BLOCK_N);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
+        const uint64_t da = make_desc_sw128(sa, 16, 1024);
+        const uint64_t db = make_desc_sw128(sa + A_TILE_BYTES, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // 4 x K=16 per 64-wide chunk: +32 B inside the 128 B swizzle row
+          mma_bf16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
+        mma_commit(&empty_bar[s]);
+      }
+      mma_commit(tmem_full);
+    }
+  } else {
+    // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 ; one output pixel (GEMM row) per thread
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int dw_ = r % p.bw, dh_ = (r / p.bw) % p.bh, dn_ = r / (p.bw * p.bh);
+    const int n = n0 + dn_, h = h0 + dh_, w = w0 + dw_;
+    const bool row_ok = (dn_ < p.bn) && n < p.mn && h < p.mh && w < p.mw;
+    const int64_t opix = ((int64_t)n * p.out_h + (h * p.out_sh + p.out_oh)) * p.out_w + (w * p.out_sw + p.out_ow);
+    bf16* yrow = p.y + opix * p.out_c + p.out_coff + nblk * BLOCK_N;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 16) {
+      uint32_t v[16];
+      tmem_ld_x16(taddr + (uint32_t)c, v);
+      tmem_ld_wait();
+      const int col0 = nblk * BLOCK_N + c;
+      if (row_ok && col0 < p.cout) {
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + col0 + j);
+        }
+        uint4 o0, o1;
+        o0.x = pack_bf16(f[0], f[1]);   o0.y = pack_bf16(f[2], f[3]);   o0.z = pack_bf16(f[4], f[5]);   o0.w = pack_bf16(f[6], f[7]);
+        o1.x = pack_bf16(f[8], f[9]);   o1.y = pack_bf16(f[10], f[11]); o1.z = pack_bf16(f[12], f[13]); o1.w = pack_bf16(f[14], f[15]);
+        uint4* dst = reinterpret_cast<uint4*>(yrow + c);
+        dst[0] = o0; dst[1] = o1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<BLOCK_N>(tmem_d);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight gradient
+// ---------------------------------------------------------------------------------------------
+constexpr int WG_BOX_BYTES = 64 * 128;   // 64 pixels x 64 channels bf16
+
+template <int N_TILE, int STAGES>
+struct WgradSmem {
+  static constexpr int A_BYTES = 2 * WG_BOX_BYTES;              // M tile is always 128 channels (2 boxes)
+  static constexpr int B_BYTES = (N_TILE / 64) * WG_BOX_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+template <int N_TILE, int STAGES>
+__global__ void __launch_bounds__(IG_THREADS)
+wgrad_kernel(const __grid_constant__ WgradPlan p) {
+  using SM = WgradSmem<N_TILE, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (p.m_total + 127) / 128, n_tiles = (p.n_total + N_TILE - 1) / N_TILE;
+  int b = blockIdx.x;
+  const int split = b % p.split_k; b /= p.split_k;
+  const int nt = b % n_tiles; b /= n_tiles;
+  const int mt = b % m_tiles; b /= m_tiles;
+  const int tap = b;
+  const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
+  const int t_begin = (int)((int64_t)total_tiles * split / p.split_k);
+  const int t_end = (int)((int64_t)total_tiles * (split + 1) / p.split_k);
+  const int kiters = t_end - t_begin;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmap_a);
+    prefetch_tmap(&p.tmap_b);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<N_TILE>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (kiters > 0) {
+    if (warp == 0) {
+      if (elect_one()) {
+        for (int it = 0; it < kiters; ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          int t = t_begin + it;
+          const int tw = t % p.tiles_w; t /= p.tiles_w;
+          const int th = t % p.tiles_h; t /= p.tiles_h;
+          const int n0 = t * p.bn, h0 = th * p.bh, w0 = tw * p.bw;
+          uint8_t* sa = smem + s * SM::STAGE_BYTES;
+          uint8_t* sb = sa + SM::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)SM::STAGE_BYTES);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            tma_load_4d(sa + j * WG_BOX_BYTES, &p.tmap_a, &full_bar[s], mt * 128 + j * 64,
+                        w0 * p.a_sw + p.a_dw[tap], h0 * p.a_sh + p.a_dh[tap], n0);
+#pragma unroll
+          for (int j = 0; j < N_TILE / 64; ++j)
+            tma_load_4d(sb + j * WG_BOX_BYTES, &p.tmap_b, &full_bar[s], nt * N_TILE + j * 64,
+                        w0 * p.b_sw + p.b_dw[tap], h0 * p.b_sh + p.b_dh[tap], n0);
+        }
+      }
+    } else if (warp == 1) {
+      if (elect_one()) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, N_TILE, 1, 1);
+        for (int it = 0; it < kiters; ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
+          // MN-major: 64-channel blocks LBO = 8192 B apart, 8-pixel K groups SBO = 1024 B apart
+          const uint64_t da = make_desc_sw128(sa, WG_BOX_BYTES, 1024);
+          const uint64_t db = make_desc_sw128(sa + SM::A_BYTES, WG_BOX_BYTES, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // 16 pixels per MMA = 2 K groups = 2048 B
+            mma_bf16_ss(tmem_d, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, (it | k) != 0);
+          mma_commit(&empty_bar[s]);
+        }
+        mma_commit(tmem_full);
+      }
+    } else {
+      const int q = warp & 3;
+      const int m = mt * 128 + q * 32 + lane;
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < N_TILE; c += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(taddr + (uint32_t)c, v);
+        tmem_ld_wait();
+        const int n0c = nt * N_TILE + c;
+        if (m < p.m_total && n0c < p.n_total) {
+          float* dst = p.dw + ((int64_t)m * p.n_total + n0c) * p.tap_stride + tap;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0c + j < p.n_total) atomicAdd(dst + (int64_t)j * p.tap_stride, __uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<N_TILE>(tmem_d);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing (fp32 parameters -> bf16 GEMM operand)
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(int mode, const float* __restrict__ w, bf16* __restrict__ out, int co_n, int ci_n, int kh, int kw) {
+  const int taps = kh * kw;
+  const int64_t total = (mode == 4) ? (int64_t)co_n * 256 : (int64_t)co_n * ci_n * taps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float v;
+    if (mode == 0) {          // out[co][tap][ci] <- w[co][ci][tap]
+      const int ci = i % ci_n; const int tap = (i / ci_n) % taps; const int co = i / ((int64_t)ci_n * taps);
+      v = w[((int64_t)co * ci_n + ci) * taps + tap];
+    } else if (mode == 1) {   // out[ci][tap][co] <- w[co][ci][tap]
+      const int co = i % co_n; const int tap = (i / co_n) % taps; const int ci = i / ((int64_t)co_n * taps);
+      v = w[((int64_t)co * ci_n + ci) * taps + tap];
+    } else if (mode == 2) {   // out[cls][co][ci] <- w[ci][co][cls]   (ConvT weight is (ci, co, 2, 2))
+      const int ci = i % ci_n; const int co = (i / ci_n) % co_n; const int cls = i / ((int64_t)ci_n * co_n);
+      v = w[((int64_t)ci * co_n + co) * 4 + cls];
+    } else if (mode == 3) {   // out[ci][cls][co] <- w[ci][co][cls]
+      const int co = i % co_n; const int cls = (i / co_n) % 4; const int ci = i / ((int64_t)co_n * 4);
+      v = w[((int64_t)ci * co_n + co) * 4 + cls];
+    } else {                  // conv1 7x7/2 in space-to-depth form: out[co][kh2][kw2][16], ch = (py*2+px)*3 + c (12 used)
+      const int ch = i % 16; const int kw2 = (i / 16) % 4; const int kh2 = (i / 64) % 4; const int co = i / 256;
+      v = 0.f;
+      if (ch < 12) {
+        const int c = ch % 3, px = (ch / 3) % 2, py = ch / 6;
+        // s2d pixel (i+kh2-2, j+kw2-2), sub-pixel (py,px) <-> original row 2(i+kh2-2)+py = 2i + (2*kh2+py-4) = 2i - 3 + kh
+        const int kh_ = 2 * kh2 + py - 1, kw_ = 2 * kw2 + px - 1;
+        if (kh_ >= 0 && kh_ < 7 && kw_ >= 0 && kw_ < 7) v = w[(((int64_t)co * 3 + c) * 7 + kh_) * 7 + kw_];
+      }
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+int pack_weights(int mode, const float* w, bf16* out, int co_n, int ci_n, int kh, int kw, cudaStream_t s) {
+  const int64_t total = (mode == 4) ? (int64_t)co_n * 256 : (int64_t)co_n * ci_n * kh * kw;
+  int grid = (int)((total + 255) / 256);
+  if (grid > DBB_NUM_SMS * 8) grid = DBB_NUM_SMS * 8;
+  pack_weights_kernel<<<grid, 256, 0, s>>>(mode, w, out, co_n, ci_n, kh, kw);
+  DBB_CHECK_LAUNCH("pack_weights");
+  return DBB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tensor maps
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static EncodeTiledFn get_encode() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      g_encode = (EncodeTiledFn)fn;
+  });
+  return g_encode;
+}
+
+int encode_tmap_nhwc(CUtensorMap* m, const bf16* base, int n, int h, int w, int c_total, int c_off, int c_extent,
+                     int box_n, int box_h, int box_w, int stride_h, int stride_w) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(DBB_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)c_extent, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c_total * 2, (cuuint64_t)w * c_total * 2, (cuuint64_t)h * w * c_total * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(box_w * stride_w), (cuuint32_t)(box_h * stride_h), (cuuint32_t)box_n};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride_w, (cuuint32_t)stride_h, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)(base + c_off), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled(nhwc n=%d h=%d w=%d c=%d box=%d,%d,%d stride=%d,%d) failed: %d",
+             n, h, w, c_total, box_n, box_h, box_w, stride_h, stride_w, (int)r);
+    return DBB_ECUDA;
+  }
+  return DBB_OK;
+}
+
+// generic 4-D map with explicit strides (used for the overlapping conv1 space-to-depth view)
+int encode_tmap_raw4(CUtensorMap* m, const bf16* base, const cuuint64_t dims[4], const cuuint64_t strides_bytes[3],
+                     const cuuint32_t box[4]) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(DBB_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled(raw4) failed: %d", (int)r);
+    return DBB_ECUDA;
+  }
+  return DBB_OK;
+}
+
+static int encode_tmap_weights(CUtensorMap* m, const bf16* wp, int k_total, int rows, int block_n) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(DBB_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)block_n};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)wp, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled(weights k=%d rows=%d) failed: %d", k_total, rows, (int)r);
+    return DBB_ECUDA;
+  }
+  return DBB_OK;
+}
+
+// pick a (bn, bh, bw) box of exactly `rows` pixels (power-of-two factors) with the least overhang
+void choose_box(int rows, int mn, int mh, int mw, int* bn, int* bh, int* bw) {
+  double best = 1e30; int bbn = 1, bbh = 1, bbw = rows;
+  for (int w = rows; w >= 1; w >>= 1) {
+    for (int h = rows / w; h >= 1; h >>= 1) {
+      const int n = rows / (w * h);
+      const double cover = (double)((mw + w - 1) / w * w) * ((mh + h - 1) / h * h) * ((mn + n - 1) / n * n);
+      // tie-break towards wide boxes (longer contiguous runs per TMA row)
+      const double score = cover * (1.0 + 1e-6 * (rows / w));
+      if (score < best) { best = score; bbn = n; bbh = h; bbw = w; }
+    }
+  }
+  *bn = bbn; *bh = bbh; *bw = bbw;
+}
+
+int igemm_plan_init(IgemmPlan* p, const bf16* x, int n, int h, int w, int c_total, int c_off, int cin,
+                    const bf16* wp, int k_total, int w_rows, int block_n) {
+  // caller has filled: mn, mh, mw, in_sh, in_sw, ntaps, dh, dw, cout, out_*; y, bias
+  p->cin = cin;
+  p->block_n = block_n;
+  choose_box(128, p->mn, p->mh, p->mw, &p->bn, &p->bh, &p->bw);
+  p->tiles_n = (p->mn + p->bn - 1) / p->bn;
+  p->tiles_h = (p->mh + p->bh - 1) / p->bh;
+  p->tiles_w = (p->mw + p->bw - 1) / p->bw;
+  int rc = encode_tmap_nhwc(&p->tmap_x, x, n, h, w, c_total, c_off, cin, p->bn, p->bh, p->bw, p->in_sh, p->in_sw);
+  if (rc) return rc;
+  return encode_tmap_weights(&p->tmap_w, wp, k_total, w_rows, block_n);
+}
+
+template <int BLOCK_N, int STAGES>
+static int igemm_launch_t(const IgemmPlan& p, cudaStream_t s) {
+  using SM = IgemmSmem<BLOCK_N, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DBB_CUDA(cudaFuncSetAttribute(igemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    attr_done = true;
+  }
+  const int n_blocks = (p.cout + BLOCK_N - 1) / BLOCK_N;
+  const int64_t grid = (int64_t)p.tiles_n * p.tiles_h * p.tiles_w * n_blocks;
+  if (grid <= 0 || grid > 0x7fffffff) return set_error(DBB_EINVAL, "igemm: bad grid");
+  igemm_kernel<BLOCK_N, STAGES><<<(unsigned)grid, IG_THREADS, SM::TOTAL, s>>>(p);
+  DBB_CHECK_LAUNCH("igemm_kernel");
+  return DBB_OK;
+}
+
+int igemm_launch(const IgemmPlan& p, cudaStream_t s) {
+  if (p.cin % 64 != 0 || p.ntaps < 1 || p.ntaps > IGEMM_MAX_TAPS) return set_error(DBB_EUNSUPPORTED, "igemm: cin must be a multiple of 64, taps <= 16");
+  switch (p.block_n) {
+    case 64: return igemm_launch_t<64, 4>(p, s);     // 24 KB/stage -> 96 KB, 2 CTAs/SM
+    case 128: return igemm_launch_t<128, 3>(p, s);   // 32 KB/stage -> 96 KB, 2 CTAs/SM
+    case 256: return igemm_launch_t<256, 4>(p, s);   // 48 KB/stage -> 192 KB, 1 CTA/SM
+    default: return set_error(DBB_EUNSUPPORTED, "igemm: block_n must be 64, 128 or 256");
+  }
+}
+
+template <int N_TILE, int STAGES>
+static int wgrad_launch_t(const WgradPlan& p, cudaStream_t s) {
+  using SM = WgradSmem<N_TILE, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DBB_CUDA(cudaFuncSetAttribute(wgrad_kernel<N_TILE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    attr_done = true;
+  }
+  const int m_tiles = (p.m_total + 127) / 128, n_tiles = (p.n_total + N_TILE - 1) / N_TILE;
+  const int64_t grid = (int64_t)p.ntaps * m_tiles * n_tiles * p.split_k;
+  if (grid <= 0 || grid > 0x7fffffff) return set_error(DBB_EINVAL, "wgrad: bad grid");
+  wgrad_kernel<N_TILE, STAGES><<<(unsigned)grid, IG_THREADS, SM::TOTAL, s>>>(p);
+  DBB_CHECK_LAUNCH("wgrad_kernel");
+  return DBB_OK;
+}
+
+int wgrad_launch(const WgradPlan& p, cudaStream_t s) {
+  switch (p.n_tile) {
+    case 64: return wgrad_launch_t<64, 4>(p, s);     // 24 KB/stage
+    case 128: return wgrad_launch_t<128, 3>(p, s);   // 32 KB/stage
+    case 256: return wgrad_launch_t<256, 4>(p, s);   // 48 KB/stage
+    default: return set_error(DBB_EUNSUPPORTED, "wgrad: n_tile must be 64, 128 or 256");
+  }
+}
+
+}  // namespace dbb

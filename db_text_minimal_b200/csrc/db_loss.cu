@@ -1,0 +1,567 @@
+// db_loss.cu -- fused three-term DB loss (balanced BCE with OHEM top-k, Dice, masked L1), forward + backward.
+//
+// Replaces src/losses.py:18-40 (OHEMBalanceCrossEntropyLoss), :48-66 (DiceLoss), :75-82 (L1Loss) and
+// :105-139 (DBLoss.forward) of the reference.  HBM-bound: one read of the 7 maps in the forward
+// (28 B/px), one more read of P/gt/mask (12 B/px) for the exact radix select in 'none' mode, and
+// 28 B/px read + 12 B/px write in the backward.  No host synchronisation anywhere: the three
+// blocking syncs of the reference (losses.py:25,27,65) become device scalars in DbbLossState.
+//
+// Semantics restated from the reference:
+//   pos = gt*mask, neg = (1-gt)*mask, n_pos = int(sum pos), n_neg = min(int(n_pos*ratio), int(sum neg))
+//   bce_i = -(g*max(log p,-100) + (1-g)*max(log1p(-p),-100));  bce'_i = (p-g)/max(p(1-p),1e-12)
+//   'mean': prob = mean(bce) * (sum pos + n_neg) / (n_pos + n_neg + eps)      (degenerate OHEM)
+//   'none': prob = (sum pos*bce + sum of the n_neg largest neg*bce) / (n_pos + n_neg + eps)
+//   thr  = sum |T-tg|*tm / (sum tm + eps);   bin = 1 - 2 sum(B g m) / (sum B m + sum g m + eps)
+#include "common.cuh"
+
+namespace dbb {
+
+enum { S_POS = 0, S_NEG, S_BCE_ALL, S_BCE_POS, S_L1, S_TM, S_I, S_BM, S_NEGL, S_TOP_ABOVE, S_TOP_CAND, S_SPARE, NSUM };
+static_assert(NSUM == 12, "DbbLossState.sums has 12 slots");
+
+constexpr int LOSS_THREADS = 256;
+constexpr int HIST1_BITS = 11;               // bits 30..20 of the (non-negative) float
+constexpr int HIST1_BINS = 1 << HIST1_BITS;  // 2048
+constexpr int HIST2_BINS = 2048;             // bits 19..9
+constexpr int HIST3_BINS = 512;              // bits 8..0
+
+// workspace layout (bytes): [partials double grid*NSUM][hist1 u32 2048][cand_count u32 (padded to 16)][taubin i32 ...][cands float px]
+struct LossWs {
+  double* partials;
+  unsigned* hist1;
+  unsigned* cand_count;   // [0] = count, [1] = taubin (as int), [2] = cnt_above_bin lo, [3] hi
+  float* cands;
+};
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int loss_grid(int64_t px) {
+  int64_t want = (px / 4 + LOSS_THREADS * 4 - 1) / (LOSS_THREADS * 4);   // ~4 float4 per thread minimum
+  int64_t g = DBB_NUM_SMS * 4;
+  if (want < g) g = want < 1 ? 1 : want;
+  return (int)g;
+}
+
+static LossWs carve(void* ws, int grid, int64_t px) {
+  LossWs w;
+  char* p = (char*)ws;
+  w.partials = (double*)p;            p += align_up(sizeof(double) * NSUM * (size_t)grid, 256);
+  w.hist1 = (unsigned*)p;             p += sizeof(unsigned) * HIST1_BINS;
+  w.cand_count = (unsigned*)p;        p += 256;
+  w.cands = (float*)p;
+  return w;
+}
+
+__device__ __forceinline__ float bce_fwd(float p, float g) {
+  // ATen binary_cross_entropy: (t-1)*max(log1p(-x),-100) - t*max(log(x),-100)
+  // explicit _rn ops: no FMA contraction, so every kernel (and the CPU oracle) rounds identically
+  float l1 = fmaxf(log1pf(-p), -100.f);
+  float l0 = fmaxf(logf(p), -100.f);
+  return __fsub_rn(__fmul_rn(__fsub_rn(g, 1.f), l1), __fmul_rn(g, l0));
+}
+__device__ __forceinline__ float bce_bwd(float p, float g) {
+  return (p - g) / fmaxf(p * (1.f - p), 1e-12f);
+}
+__device__ __forceinline__ float negl_of(float p, float g, float m) {
+  float v = __fmul_rn(bce_fwd(p, g), __fmul_rn(__fsub_rn(1.f, g), m));   // loss * negative, fp32 like the reference
+  return v > 0.f ? v : 0.f;                    // folds -0.0 into +0.0 so the bit pattern is monotone
+}
+
+template <int N>
+__device__ __forceinline__ void block_reduce_store(float (&acc)[N], double* out) {
+  __shared__ float red[LOSS_THREADS / 32][N];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < N; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) red[wid][i] = acc[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < LOSS_THREADS / 32; ++w) s += (double)red[w][threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+}
+
+struct Vec4 { float v[4]; };
+template <int VEC> struct Loader;
+template <> struct Loader<4> {
+  static __device__ __forceinline__ Vec4 ld(const float* p) {
+    float4 t = ldg_stream(reinterpret_cast<const float4*>(p));
+    return Vec4{{t.x, t.y, t.z, t.w}};
+  }
+  static __device__ __forceinline__ void st(float* p, const Vec4& a) {
+    stg_stream(reinterpret_cast<float4*>(p), make_float4(a.v[0], a.v[1], a.v[2], a.v[3]));
+  }
+};
+template <> struct Loader<1> {
+  static __device__ __forceinline__ Vec4 ld(const float* p) { return Vec4{{__ldg(p), 0.f, 0.f, 0.f}}; }
+  static __device__ __forceinline__ void st(float* p, const Vec4& a) { *p = a.v[0]; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// pass 1: every reduction of the three losses in one read of the 7 maps (+ level-1 histogram)
+// ---------------------------------------------------------------------------------------------
+template <int VEC, bool HAS_B, bool SELECT>
+__global__ void __launch_bounds__(LOSS_THREADS)
+dbloss_reduce_kernel(const float* __restrict__ preds, const float* __restrict__ gts, int64_t n_img, int64_t hw, int cch,
+                     double* __restrict__ partials, unsigned* __restrict__ hist1) {
+  __shared__ unsigned sh_hist[SELECT ? HIST1_BINS : 1];
+  if (SELECT) {
+    for (int i = threadIdx.x; i < HIST1_BINS; i += LOSS_THREADS) sh_hist[i] = 0;
+    __syncthreads();
+  }
+  const int64_t px = n_img * hw;
+  const int64_t hwv = hw / VEC, nvec = n_img * hwv;
+  float acc[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) acc[i] = 0.f;
+
+  for (int64_t v = (int64_t)blockIdx.x * LOSS_THREADS + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * LOSS_THREADS) {
+    const int64_t n = v / hwv, r = (v - n * hwv) * VEC;
+    const float* pp = preds + (n * cch) * hw + r;
+    const int64_t go = n * hw + r;
+    Vec4 P = Loader<VEC>::ld(pp), T = Loader<VEC>::ld(pp + hw);
+    Vec4 B; if (HAS_B) B = Loader<VEC>::ld(pp + 2 * hw);
+    Vec4 G = Loader<VEC>::ld(gts + go), M = Loader<VEC>::ld(gts + px + go);
+    Vec4 TG = Loader<VEC>::ld(gts + 2 * px + go), TM = Loader<VEC>::ld(gts + 3 * px + go);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float p = P.v[j], g = G.v[j], m = M.v[j];
+      const float pos = __fmul_rn(g, m), neg = __fmul_rn(__fsub_rn(1.f, g), m);
+      const float bce = bce_fwd(p, g);
+      acc[S_POS] += pos;
+      acc[S_NEG] += neg;
+      acc[S_BCE_ALL] += bce;
+      acc[S_BCE_POS] += bce * pos;
+      acc[S_L1] += fabsf(T.v[j] - TG.v[j]) * TM.v[j];
+      acc[S_TM] += TM.v[j];
+      if (HAS_B) {
+        acc[S_I] += B.v[j] * g * m;
+        acc[S_BM] += B.v[j] * m;
+      }
+      if (SELECT) {
+        float nl = __fmul_rn(bce, neg);
+        if (nl > 0.f) {
+          acc[S_NEGL] += nl;
+          atomicAdd(&sh_hist[__float_as_uint(nl) >> 20], 1u);
+        }
+      }
+    }
+  }
+  block_reduce_store<9>(acc, partials + (size_t)blockIdx.x * NSUM);
+  if (SELECT) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < HIST1_BINS; i += LOSS_THREADS) {
+      unsigned c = sh_hist[i];
+      if (c) atomicAdd(&hist1[i], c);
+    }
+  }
+}
+
+// deterministic sum of per-block partials: thread j (< NSUM*?) ...
+__device__ void sum_partials(const double* partials, int nblk, double* sums /*smem NSUM*/, int first, int last) {
+  // each warp handles one component at a time; fixed order -> bitwise reproducible
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c = first + wid; c < last; c += nw) {
+    double s = 0.0;
+    for (int b = lane; b < nblk; b += 32) s += partials[(size_t)b * NSUM + c];
+    s = warp_sum(s);
+    if (lane == 0) sums[c] = s;
+  }
+}
+
+struct LossParams {
+  float alpha, beta, ratio, eps;
+  int64_t px;
+  int has_b;
+};
+
+__device__ void write_losses(const double* S, double prob, const LossParams& lp, float* losses5, DbbLossState* st,
+                             double coef0) {
+  const double thr = S[S_L1] / (S[S_TM] + (double)lp.eps);
+  double bin = 0.0, U = 1.0, I = 0.0;
+  if (lp.has_b) {
+    I = S[S_I];
+    U = S[S_BM] + S[S_POS] + (double)lp.eps;
+    bin = 1.0 - 2.0 * I / U;
+  }
+  const double pt = prob + (double)lp.beta * thr;
+  const double total = lp.has_b ? (double)lp.alpha * bin + pt : pt;
+  losses5[0] = (float)prob; losses5[1] = (float)thr; losses5[2] = (float)bin; losses5[3] = (float)pt; losses5[4] = (float)total;
+  st->coef[0] = (float)coef0;
+  st->coef[1] = (float)(1.0 / (S[S_TM] + (double)lp.eps));
+  st->coef[2] = lp.has_b ? (float)(2.0 / U) : 0.f;
+  st->coef[3] = lp.has_b ? (float)(2.0 * I / (U * U)) : 0.f;
+  for (int i = 0; i < NSUM; ++i) st->sums[i] = S[i];
+  st->tie_ticket = 0;
+}
+
+// finalize for 'mean', and level-1 bin search for 'none'
+template <bool SELECT>
+__global__ void __launch_bounds__(256)
+dbloss_finalize1_kernel(const double* __restrict__ partials, int nblk, unsigned* __restrict__ hist1,
+                        unsigned* __restrict__ cand_ctl, LossParams lp, float* losses5, DbbLossState* st) {
+  __shared__ double S[NSUM];
+  __shared__ unsigned sh[SELECT ? HIST1_BINS : 1];
+  if (threadIdx.x < NSUM) S[threadIdx.x] = 0.0;
+  __syncthreads();
+  sum_partials(partials, nblk, S, 0, 9);
+  if (SELECT) for (int i = threadIdx.x; i < HIST1_BINS; i += blockDim.x) sh[i] = hist1[i];
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const long long n_pos = (long long)S[S_POS];                       // int(positive.sum())
+  long long n_neg = (long long)((double)n_pos * (double)lp.ratio);   // int(no_positive * ratio)
+  const long long n_neg_cur = (long long)S[S_NEG];
+  if (n_neg_cur < n_neg) n_neg = n_neg_cur;
+  const double D = (double)n_pos + (double)n_neg + (double)lp.eps;
+  st->n_pos = n_pos; st->n_neg = n_neg; st->reduction = SELECT ? 1 : 0;
+  if (!SELECT) {
+    const double mean_bce = S[S_BCE_ALL] / (double)lp.px;
+    const double prob = mean_bce * (S[S_POS] + (double)n_neg) / D;
+    st->tau = (float)mean_bce; st->tau_bits = __float_as_uint((float)mean_bce);
+    st->n_above = 0; st->n_tie = n_neg;
+    write_losses(S, prob, lp, losses5, st, (S[S_POS] + (double)n_neg) / D / (double)lp.px);
+    return;
+  }
+  // level-1: walk the histogram from the top bin down until k entries are covered
+  long long above = 0; int tb = -1;
+  if (n_neg > 0) {
+    for (int b = HIST1_BINS - 1; b >= 0; --b) {
+      const long long c = sh[b];
+      if (above + c >= n_neg) { tb = b; break; }
+      above += c;
+    }
+  }
+  // tb == -1: k == 0, or k exceeds the number of strictly positive entries -> tau = 0
+  cand_ctl[0] = 0u;
+  cand_ctl[1] = (unsigned)tb;
+  cand_ctl[2] = (unsigned)(above & 0xffffffffll);
+  cand_ctl[3] = (unsigned)(above >> 32);
+  for (int i = 0; i < NSUM; ++i) st->sums[i] = S[i];
+}
+
+// pass 2 ('none'): sum of everything above the tau bin + compaction of the tau bin
+template <int VEC>
+__global__ void __launch_bounds__(LOSS_THREADS)
+dbloss_select_pass2_kernel(const float* __restrict__ preds, const float* __restrict__ gts, int64_t n_img, int64_t hw, int cch,
+                           double* __restrict__ partials, unsigned* __restrict__ cand_ctl, float* __restrict__ cands) {
+  const int tb = (int)cand_ctl[1];
+  const int64_t px = n_img * hw;
+  const int64_t hwv = hw / VEC, nvec = n_img * hwv;
+  float acc[1] = {0.f};
+  if (tb >= 0) {
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * LOSS_THREADS;
+    const int64_t start = (int64_t)blockIdx.x * LOSS_THREADS + threadIdx.x;
+    // all lanes of a warp iterate the same number of times (ballot below needs convergence)
+    const int64_t iters = (nvec + stride - 1) / stride;
+    for (int64_t it = 0; it < iters; ++it) {
+      const int64_t v = start + it * stride;
+      const bool valid = v < nvec;
+      Vec4 NL;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) NL.v[j] = 0.f;
+      if (valid) {
+        const int64_t n = v / hwv, r = (v - n * hwv) * VEC;
+        Vec4 P = Loader<VEC>::ld(preds + (n * cch) * hw + r);
+        Vec4 G = Loader<VEC>::ld(gts + n * hw + r), M = Loader<VEC>::ld(gts + px + n * hw + r);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) NL.v[j] = negl_of(P.v[j], G.v[j], M.v[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const float nl = NL.v[j];
+        const int b = (nl > 0.f) ? (int)(__float_as_uint(nl) >> 20) : -1;
+        if (b > tb) acc[0] += nl;
+        const bool hit = (b == tb);
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (mask) {
+          unsigned base = 0;
+          if (lane == (__ffs(mask) - 1)) base = atomicAdd(&cand_ctl[0], (unsigned)__popc(mask));
+          base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+          if (hit) cands[base + __popc(mask & ((1u << lane) - 1u))] = nl;
+        }
+      }
+    }
+  }
+  // reuse slot S_TOP_ABOVE of this block's partial row
+  __shared__ float red[LOSS_THREADS / 32];
+  float s = warp_sum(acc[0]);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < LOSS_THREADS / 32; ++w) t += (double)red[w];
+    partials[(size_t)blockIdx.x * NSUM + S_TOP_ABOVE] = t;
+  }
+}
+
+// exact select inside the tau bin (one CTA) + final losses for 'none'
+__global__ void __launch_bounds__(1024)
+dbloss_select_final_kernel(double* __restrict__ partials, int nblk, const unsigned* __restrict__ cand_ctl,
+                           const float* __restrict__ cands, LossParams lp, float* losses5, DbbLossState* st) {
+  __shared__ unsigned hist[HIST2_BINS];
+  __shared__ double S[NSUM];
+  __shared__ double redd[32];
+  __shared__ long long sh_above;
+  __shared__ unsigned sh_prefix;     // resolved low 20 bits so far
+  __shared__ long long sh_krem;
+  const int tid = threadIdx.x;
+  const unsigned ncand = cand_ctl[0];
+  const int tb = (int)cand_ctl[1];
+  if (tid < NSUM) S[tid] = st->sums[tid];
+  __syncthreads();
+  sum_partials(partials, nblk, S, S_TOP_ABOVE, S_TOP_ABOVE + 1);
+  const long long n_pos = st->n_pos, n_neg = st->n_neg;
+  const double D = (double)n_pos + (double)n_neg + (double)lp.eps;
+  if (tb < 0) {
+    __syncthreads();
+    if (tid == 0) {
+      // tau = 0: every strictly positive entry is taken, the rest of the picks are zeros
+      long long nz = 0;   // number of strictly positive entries = cnt walked in finalize1
+      nz = ((long long)cand_ctl[3] << 32) | cand_ctl[2];
+      st->tau = 0.f; st->tau_bits = 0u;
+      st->n_above = n_neg > 0 ? nz : 0; st->n_tie = n_neg > 0 ? n_neg - nz : 0;
+      const double top = n_neg > 0 ? S[S_NEGL] : 0.0;
+      S[S_TOP_CAND] = 0.0; S[S_TOP_ABOVE] = top;
+      write_losses(S, (S[S_BCE_POS] + top) / D, lp, losses5, st, 1.0 / D);
+    }
+    return;
+  }
+  if (tid == 0) {
+    sh_above = ((long long)cand_ctl[3] << 32) | cand_ctl[2];
+    sh_krem = n_neg - sh_above;      // 1 <= k_rem <= ncand
+    sh_prefix = 0u;
+  }
+  // ---- level 2: bits 19..9
+  for (int i = tid; i < HIST2_BINS; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (unsigned i = tid; i < ncand; i += blockDim.x) atomicAdd(&hist[(__float_as_uint(cands[i]) >> 9) & 0x7ffu], 1u);
+  __syncthreads();
+  if (tid == 0) {
+    long long acc = 0, kr = sh_krem; int b2 = 0;
+    for (int b = HIST2_BINS - 1; b >= 0; --b) {
+      const long long c = hist[b];
+      if (acc + c >= kr) { b2 = b; break; }
+      acc += c;
+    }
+    sh_above += acc; sh_krem = kr - acc; sh_prefix = (unsigned)b2 << 9;
+  }
+  __syncthreads();
+  const unsigned p2 = sh_prefix >> 9;
+  // ---- level 3: bits 8..0
+  for (int i = tid; i < HIST3_BINS; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (unsigned i = tid; i < ncand; i += blockDim.x) {
+    const unsigned u = __float_as_uint(cands[i]);
+    if (((u >> 9) & 0x7ffu) == p2) atomicAdd(&hist[u & 0x1ffu], 1u);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    long long acc = 0, kr = sh_krem; int b3 = 0;
+    for (int b = HIST3_BINS - 1; b >= 0; --b) {
+      const long long c = hist[b];
+      if (acc + c >= kr) { b3 = b; break; }
+      acc += c;
+    }
+    sh_above += acc; sh_krem = kr - acc; sh_prefix |= (unsigned)b3;
+  }
+  __syncthreads();
+  const unsigned tau_bits = ((unsigned)tb << 20) | sh_prefix;
+  const float tau = __uint_as_float(tau_bits);
+  // ---- sum of candidates strictly above tau
+  double s = 0.0;
+  for (unsigned i = tid; i < ncand; i += blockDim.x) {
+    const float c = cands[i];
+    if (c > tau) s += (double)c;
+  }
+  s = warp_sum(s);
+  if ((tid & 31) == 0) redd[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += redd[w];
+    S[S_TOP_CAND] = t;
+    const long long n_above = sh_above, n_tie = n_neg - n_above;
+    st->tau = tau; st->tau_bits = tau_bits; st->n_above = n_above; st->n_tie = n_tie;
+    const double top = S[S_TOP_ABOVE] + t + (double)tau * (double)n_tie;
+    write_losses(S, (S[S_BCE_POS] + top) / D, lp, losses5, st, 1.0 / D);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward: per-pixel gradient of sum_j grad_out[j] * loss[j]
+// ---------------------------------------------------------------------------------------------
+template <int VEC, bool HAS_B, bool SELECT>
+__global__ void __launch_bounds__(LOSS_THREADS)
+dbloss_bwd_kernel(const float* __restrict__ preds, const float* __restrict__ gts, int64_t n_img, int64_t hw, int cch,
+                  float alpha, float beta, const float* __restrict__ grad_out5, DbbLossState* __restrict__ st,
+                  float* __restrict__ dpreds) {
+  const int64_t px = n_img * hw;
+  const int64_t hwv = hw / VEC, nvec = n_img * hwv;
+  const float go0 = grad_out5[0], go1 = grad_out5[1], go2 = grad_out5[2], go3 = grad_out5[3], go4 = grad_out5[4];
+  const float c_prob = (go0 + go3 + go4) * st->coef[0];
+  const float c_thr = (go1 + beta * (go3 + go4)) * st->coef[1];
+  const float c_bin = HAS_B ? (go2 + alpha * go4) : 0.f;
+  const float dice_a = st->coef[2], dice_b = st->coef[3];
+  const float tau = st->tau;
+  const int n_tie = (int)(st->n_tie > 0x7fffffffll ? 0x7fffffffll : st->n_tie);
+  const bool any_neg = st->n_neg > 0;
+
+  for (int64_t v = (int64_t)blockIdx.x * LOSS_THREADS + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * LOSS_THREADS) {
+    const int64_t n = v / hwv, r = (v - n * hwv) * VEC;
+    const int64_t po = (n * cch) * hw + r, go = n * hw + r;
+    Vec4 P = Loader<VEC>::ld(preds + po), T = Loader<VEC>::ld(preds + po + hw);
+    Vec4 G = Loader<VEC>::ld(gts + go), M = Loader<VEC>::ld(gts + px + go);
+    Vec4 TG = Loader<VEC>::ld(gts + 2 * px + go), TM = Loader<VEC>::ld(gts + 3 * px + go);
+    Vec4 dP, dT, dB;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float p = P.v[j], g = G.v[j], m = M.v[j];
+      float w = 1.f;
+      if (SELECT) {
+        const float pos = g * m, neg = (1.f - g) * m;
+        float sel = 0.f;
+        if (any_neg) {
+          const float nl = negl_of(p, g, m);
+          if (nl > tau) sel = 1.f;
+          else if (nl == tau && neg != 0.f && n_tie > 0) {
+            // torch.topk leaves the order among equal values unspecified; take n_tie of them by ticket
+            if (atomicAdd(&st->tie_ticket, 1) < n_tie) sel = 1.f;
+          }
+        }
+        w = pos + sel * neg;
+      }
+      dP.v[j] = c_prob * w * bce_bwd(p, g);
+      const float d = T.v[j] - TG.v[j];
+      dT.v[j] = c_thr * TM.v[j] * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+      if (HAS_B) dB.v[j] = c_bin * m * (dice_b - g * dice_a);
+    }
+    Loader<VEC>::st(dpreds + po, dP);
+    Loader<VEC>::st(dpreds + po + hw, dT);
+    if (HAS_B) Loader<VEC>::st(dpreds + po + 2 * hw, dB);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// step function, standalone (DBHead.step_function drop-in; the fused head tail has its own copy)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) step_fwd_kernel(const float* __restrict__ p, const float* __restrict__ t,
+                                                       float* __restrict__ b, int64_t n, float k) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    b[i] = 1.f / (1.f + expf(-k * (p[i] - t[i])));
+}
+__global__ void __launch_bounds__(256) step_bwd_kernel(const float* __restrict__ p, const float* __restrict__ t,
+                                                       const float* __restrict__ db, float* __restrict__ dp,
+                                                       float* __restrict__ dt, int64_t n, float k) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float e = expf(-k * (p[i] - t[i]));
+    const float bb = 1.f / (1.f + e);
+    const float d = db[i] * k * bb * bb * e;     // k B^2 e, not k B (1-B): SURVEY.md section 9
+    dp[i] = d; dt[i] = -d;
+  }
+}
+
+}  // namespace dbb
+
+using namespace dbb;
+
+extern "C" size_t dbb_dbloss_workspace(int64_t n, int c, int64_t h, int64_t w, int reduction) {
+  (void)c;
+  const int64_t px = n * h * w;
+  const int grid = loss_grid(px);
+  size_t b = align_up(sizeof(double) * NSUM * (size_t)grid, 256) + sizeof(unsigned) * HIST1_BINS + 256;
+  if (reduction == 1) b += sizeof(float) * (size_t)px;
+  return align_up(b, 256);
+}
+
+template <int VEC, bool HAS_B, bool SELECT>
+static int loss_fwd_impl(const float* preds, const float* gts, int64_t n, int c, int64_t hw, LossParams lp, float* losses5,
+                         DbbLossState* state, void* workspace, cudaStream_t s) {
+  const int64_t px = n * hw;
+  const int grid = loss_grid(px);
+  LossWs ws = carve(workspace, grid, px);
+  if (SELECT) DBB_CUDA(cudaMemsetAsync(ws.hist1, 0, sizeof(unsigned) * HIST1_BINS + 256, s));
+  dbloss_reduce_kernel<VEC, HAS_B, SELECT><<<grid, LOSS_THREADS, 0, s>>>(preds, gts, n, hw, c, ws.partials, ws.hist1);
+  DBB_CHECK_LAUNCH("dbloss_reduce");
+  dbloss_finalize1_kernel<SELECT><<<1, 256, 0, s>>>(ws.partials, grid, ws.hist1, ws.cand_count, lp, losses5, state);
+  DBB_CHECK_LAUNCH("dbloss_finalize1");
+  if (SELECT) {
+    dbloss_select_pass2_kernel<VEC><<<grid, LOSS_THREADS, 0, s>>>(preds, gts, n, hw, c, ws.partials, ws.cand_count, ws.cands);
+    DBB_CHECK_LAUNCH("dbloss_select_pass2");
+    dbloss_select_final_kernel<<<1, 1024, 0, s>>>(ws.partials, grid, ws.cand_count, ws.cands, lp, losses5, state);
+    DBB_CHECK_LAUNCH("dbloss_select_final");
+  }
+  return DBB_OK;
+}
+
+extern "C" int dbb_dbloss_fwd(const float* preds, const float* gts, int64_t n, int c, int64_t h, int64_t w, float alpha,
+                              float beta, int reduction, float negative_ratio, float eps, float* losses5,
+                              DbbLossState* state, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!preds || !gts || !losses5 || !state || !workspace) return set_error(DBB_EINVAL, "dbloss_fwd: null pointer");
+  if (n <= 0 || h <= 0 || w <= 0 || (c != 2 && c != 3) || (reduction != 0 && reduction != 1))
+    return set_error(DBB_EINVAL, "dbloss_fwd: bad shape or reduction");
+  if (!aligned16(preds) || !aligned16(gts) || !aligned16(workspace)) return set_error(DBB_EALIGN, "dbloss_fwd: pointer not 16B aligned");
+  if (workspace_bytes < dbb_dbloss_workspace(n, c, h, w, reduction)) return set_error(DBB_EWORKSPACE, "dbloss_fwd: workspace too small");
+  const int64_t hw = h * w;
+  LossParams lp{alpha, beta, negative_ratio, eps, n * hw, c == 3};
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool v4 = (hw % 4) == 0;
+#define DISPATCH(V, B, S) return loss_fwd_impl<V, B, S>(preds, gts, n, c, hw, lp, losses5, state, workspace, s)
+  if (v4) {
+    if (c == 3) { if (reduction) DISPATCH(4, true, true); else DISPATCH(4, true, false); }
+    else        { if (reduction) DISPATCH(4, false, true); else DISPATCH(4, false, false); }
+  } else {
+    if (c == 3) { if (reduction) DISPATCH(1, true, true); else DISPATCH(1, true, false); }
+    else        { if (reduction) DISPATCH(1, false, true); else DISPATCH(1, false, false); }
+  }
+#undef DISPATCH
+}
+
+extern "C" int dbb_dbloss_bwd(const float* preds, const float* gts, int64_t n, int c, int64_t h, int64_t w, float alpha,
+                              float beta, int reduction, float eps, const float* grad_out5, DbbLossState* state,
+                              float* dpreds, void* stream) {
+  (void)eps;
+  if (!preds || !gts || !grad_out5 || !state || !dpreds) return set_error(DBB_EINVAL, "dbloss_bwd: null pointer");
+  if (n <= 0 || h <= 0 || w <= 0 || (c != 2 && c != 3) || (reduction != 0 && reduction != 1))
+    return set_error(DBB_EINVAL, "dbloss_bwd: bad shape or reduction");
+  if (!aligned16(preds) || !aligned16(gts) || !aligned16(dpreds)) return set_error(DBB_EALIGN, "dbloss_bwd: pointer not 16B aligned");
+  const int64_t hw = h * w;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = loss_grid(n * hw);
+  const bool v4 = (hw % 4) == 0;
+  if (reduction) DBB_CUDA(cudaMemsetAsync(&state->tie_ticket, 0, sizeof(int), s));
+#define LAUNCH(V, B, S) dbloss_bwd_kernel<V, B, S><<<grid, LOSS_THREADS, 0, s>>>(preds, gts, n, hw, c, alpha, beta, grad_out5, state, dpreds)
+  if (v4) {
+    if (c == 3) { if (reduction) LAUNCH(4, true, true); else LAUNCH(4, true, false); }
+    else        { if (reduction) LAUNCH(4, false, true); else LAUNCH(4, false, false); }
+  } else {
+    if (c == 3) { if (reduction) LAUNCH(1, true, true); else LAUNCH(1, true, false); }
+    else        { if (reduction) LAUNCH(1, false, true); else LAUNCH(1, false, false); }
+  }
+#undef LAUNCH
+  DBB_CHECK_LAUNCH("dbloss_bwd");
+  return DBB_OK;
+}
+
+extern "C" int dbb_step_fwd(const float* p, const float* t, float* b, int64_t numel, float k, void* stream) {
+  if (!p || !t || !b || numel < 0) return set_error(DBB_EINVAL, "step_fwd: bad argument");
+  if (numel == 0) return DBB_OK;
+  int64_t g = (numel + 255) / 256; if (g > DBB_NUM_SMS * 8) g = DBB_NUM_SMS * 8;
+  step_fwd_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(p, t, b, numel, k);
+  DBB_CHECK_LAUNCH("step_fwd");
+  return DBB_OK;
+}
+extern "C" int dbb_step_bwd(const float* p, const float* t, const float* db, float* dp, float* dt, int64_t numel, float k,
+                            void* stream) {
+  if (!p || !t || !db || !dp || !dt || numel < 0) return set_error(DBB_EINVAL, "step_bwd: bad argument");
+  if (numel == 0) return DBB_OK;
+  int64_t g = (numel + 255) / 256; if (g > DBB_NUM_SMS * 8) g = DBB_NUM_SMS * 8;
+  step_bwd_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(p, t, db, dp, dt, numel, k);
+  DBB_CHECK_LAUNCH("step_bwd");
+  return DBB_OK;
+}

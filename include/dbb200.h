@@ -1,0 +1,175 @@
+/*
+ * dbb200.h -- C ABI of libdbb200.so: the B200 (sm_100a) kernels behind the DB_text_minimal hot path.
+ *
+ * The reference (huyhoang17/DB_text_minimal) is pure Python/PyTorch and has no FFI layer; its
+ * boundary for this path is three Python callables:
+ *     DBTextModel.forward          src/models.py:34-48
+ *     DBLoss.forward               src/losses.py:105-139
+ *     SegDetectorRepresenter.__call__ / binarize / box_score_fast   src/postprocess.py:19-52,186-198
+ * Each entry point below names the reference code it replaces.  The Python host side
+ * (db_text_minimal_b200/*.py) mirrors those classes and reaches this library through ctypes;
+ * INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions (all entries):
+ *   - plain pointers + sizes, no torch types; every pointer is DEVICE memory unless named host_*;
+ *   - the caller owns all memory (inputs, outputs, workspaces); the library never allocates
+ *     device memory and never synchronises the stream;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); entries are CUDA-graph capturable;
+ *   - return 0 on success or a negative DBB_E* code; dbb_strerror() names it;
+ *   - float tensors are contiguous, 16-byte aligned.
+ */
+#ifndef DBB200_H_
+#define DBB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBB_VERSION 100
+
+enum {
+  DBB_OK = 0,
+  DBB_EINVAL = -1,      /* bad shape / argument */
+  DBB_EALIGN = -2,      /* pointer not 16-byte aligned */
+  DBB_EWORKSPACE = -3,  /* workspace too small */
+  DBB_ECUDA = -4,       /* CUDA runtime/driver error (see dbb_last_cuda_error) */
+  DBB_EUNSUPPORTED = -5 /* configuration not supported by the sm_100a kernels */
+};
+
+int dbb_version(void);
+const char* dbb_strerror(int code);
+const char* dbb_last_cuda_error(void);
+/* number of kernels this library has launched in this process (bench.py: "gpu_launches") */
+uint64_t dbb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * DBLoss  (replaces src/losses.py:18-40 OHEM BCE, :48-66 Dice, :75-82 masked L1, :105-139)
+ *
+ * preds (N, C, H, W) float32, C = 3 (train: P, T, B) or 2 (eval: P, T)
+ * gts   (4, N, H, W) float32: prob_map, supervision_mask, thresh_map, text_area_map  (src/train.py:163-166)
+ * reduction: 0 = 'mean' (reference default; degenerate OHEM), 1 = 'none' (true top-k OHEM)
+ * losses5: device float[5] = prob, threshold, binary, prob+beta*thr, alpha*binary+prob+beta*thr
+ *          (C == 2: binary = 0 and [4] == [3], the single tensor the reference returns)
+ * state:   device DbbLossState, consumed by dbb_dbloss_bwd and readable by tests.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct DbbLossState {
+  double sums[12];      /* see db_loss.cu: S_* indices */
+  long long n_pos;      /* int(sum(gt*mask))                       src/losses.py:25 */
+  long long n_neg;      /* min(int(n_pos*ratio), int(sum((1-gt)*mask)))   :26-28 */
+  long long n_above;    /* 'none': #negatives with loss strictly above tau */
+  long long n_tie;      /* 'none': #picks taken among entries equal to tau */
+  float tau;            /* 'none': k-th largest of (bce * negative); 'mean': mean bce */
+  unsigned int tau_bits;
+  int tie_ticket;       /* bwd: running ticket for tie picks */
+  int reduction;
+  float coef[8];        /* precomputed gradient coefficients, see db_loss.cu */
+} DbbLossState;
+
+size_t dbb_dbloss_workspace(int64_t n, int c, int64_t h, int64_t w, int reduction);
+int dbb_dbloss_fwd(const float* preds, const float* gts, int64_t n, int c, int64_t h, int64_t w,
+                   float alpha, float beta, int reduction, float negative_ratio, float eps,
+                   float* losses5, DbbLossState* state, void* workspace, size_t workspace_bytes, void* stream);
+/* grad_out5: device float[5] upstream gradients of the five returned scalars (autograd);
+ * dpreds (N, C, H, W) float32 = d(sum_j grad_out[j]*loss[j]) / d preds. */
+int dbb_dbloss_bwd(const float* preds, const float* gts, int64_t n, int c, int64_t h, int64_t w,
+                   float alpha, float beta, int reduction, float eps, const float* grad_out5,
+                   DbbLossState* state, float* dpreds, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Step function  B = 1/(1+exp(-k(P-T)))   (replaces src/modules/segmentation_head.py:106-108)
+ * ------------------------------------------------------------------------------------------ */
+int dbb_step_fwd(const float* p, const float* t, float* b, int64_t numel, float k, void* stream);
+int dbb_step_bwd(const float* p, const float* t, const float* db, float* dp, float* dt, int64_t numel, float k,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Post-processing front  (replaces src/postprocess.py:51-52 binarize, :116-118 findContours
+ * candidate extraction, :186-198 box_score_fast, and the score/size filters at :124-130)
+ *
+ * pred (N, C, H, W) float32, channel 0 is used (postprocess.py:33).  Per image the kernel
+ * binarises (P > thresh, strict), labels foreground 8-connected and background 4-connected,
+ * builds the containment tree and emits one candidate per foreground component ("outer") and
+ * one per enclosed background region ("hole"), i.e. exactly the cv2.RETR_LIST contour set,
+ * with the float64 sum / count of P over the contour's fillPoly set.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct DbbCandidate {
+  int kind;             /* 0 = outer border of a foreground component, 1 = hole border */
+  int first_y, first_x; /* raster-first pixel of the component/region (discovery order key) */
+  int x0, y0, x1, y1;   /* bounding box of the fill set == bounding box of the contour */
+  int count;            /* pixels in the fill set */
+  double sum;           /* float64 sum of P over the fill set; score = sum / count (cv2.mean) */
+  int keep;             /* 1 if not (box_thresh > score)  (postprocess.py:129) */
+  int pad_;
+} DbbCandidate;
+
+size_t dbb_postprocess_workspace(int64_t n, int64_t h, int64_t w);
+/* bitmap: (N, H, W) uint8 out; labels: (N, H, W) int32 out (fg: 1+root index, bg: -(1+root index));
+ * cands: (N, max_cands) DbbCandidate out, sorted by (first_y, first_x) descending (cv2 order);
+ * n_cands: (N) int32 out (total found, may exceed max_cands). */
+int dbb_binarize_ccl_score(const float* pred, int64_t n, int c, int64_t h, int64_t w, float thresh, double box_thresh,
+                           uint8_t* bitmap, int32_t* labels, DbbCandidate* cands, int32_t* n_cands, int max_cands,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole-network executor: DBTextModel forward / backward  (replaces src/models.py:34-48 with
+ * src/modules/resnet.py:231-242, segmentation_body.py:64-87, segmentation_head.py:35-45)
+ *
+ * The network is a fixed graph of sm_100a kernels (tcgen05 implicit-GEMM convolutions, fused
+ * BN/ReLU/residual passes, FPN glue, fused head tail).  Parameters are passed as an array of
+ * device pointers in the order returned by dbb_net_param_name(i) (the reference state_dict
+ * keys), gradients likewise.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct DbbNet DbbNet;
+
+int dbb_net_num_params(void);                 /* trainable tensors incl. the unused fc / smooth */
+const char* dbb_net_param_name(int i);        /* reference state_dict key */
+int dbb_net_param_numel(int i);
+int dbb_net_num_buffers(void);                /* BN running_mean / running_var, in pairs */
+const char* dbb_net_buffer_name(int i);
+int dbb_net_buffer_numel(int i);
+
+/* Plans one (N, H, W, training) configuration.  Returns NULL on error (see dbb_last_cuda_error). */
+DbbNet* dbb_net_create(int64_t n, int64_t h, int64_t w, int training);
+void dbb_net_destroy(DbbNet* net);
+size_t dbb_net_workspace_bytes(const DbbNet* net);
+int64_t dbb_net_out_channels(const DbbNet* net);   /* 3 train, 2 eval */
+uint64_t dbb_net_flops_fwd(const DbbNet* net);     /* 2*MACs of the convolutions, forward */
+
+/* x (N,3,H,W) float32; params[i] float32 device pointers; buffers[i] BN running stats (updated in
+ * training mode, momentum 0.1, src/modules/basic.py:34); out (N, 3|2, H, W) float32. */
+int dbb_net_forward(DbbNet* net, const float* x, const float* const* params, float* const* buffers,
+                    float* out, void* workspace, size_t workspace_bytes, void* stream);
+/* dout (N,3,H,W) float32 -> grads[i] (float32, same shapes as params; OVERWRITTEN, not accumulated;
+ * entries for the unused tensors are left untouched).  Must follow dbb_net_forward on the same workspace.
+ * segment: -1 = whole backward; 0..dbb_net_num_segments()-1 = one slice (head+FPN first), so the host can
+ * overlap the NCCL all-reduce of finished gradient buckets with the rest of the backward. */
+int dbb_net_num_segments(void);
+int dbb_net_backward(DbbNet* net, const float* dout, const float* const* params, float* const* grads,
+                     void* workspace, size_t workspace_bytes, int segment, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Single operators (used by the FPN / DBHead module drop-ins and by the parity tests)
+ * ------------------------------------------------------------------------------------------ */
+/* Implicit-GEMM convolution on tcgen05: x NHWC bf16 (N,H,W,Cin), w OIHW float32 -> y NHWC bf16 raw output
+ * (+bias), fp32 accumulate.  kind: 0 = Conv2d fprop, 1 = Conv2d dgrad (x := dy, y := dx), 2 = ConvTranspose2d(k=2,s=2)
+ * fprop, 3 = ConvTranspose2d dgrad. */
+int dbb_conv2d(int kind, const void* x_nhwc_bf16, const float* w, const float* bias, void* y_nhwc_bf16,
+               int64_t n, int64_t h, int64_t wdt, int cin, int cout, int ksize, int stride, int pad,
+               void* workspace, size_t workspace_bytes, void* stream);
+size_t dbb_conv2d_workspace(int kind, int64_t n, int64_t h, int64_t wdt, int cin, int cout, int ksize, int stride, int pad);
+/* wgrad: dw OIHW float32 (overwritten) = sum_px dy[px, co] * x[px @ tap, ci] */
+int dbb_conv2d_wgrad(int kind, const void* x_nhwc_bf16, const void* dy_nhwc_bf16, float* dw,
+                     int64_t n, int64_t h, int64_t wdt, int cin, int cout, int ksize, int stride, int pad,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* layout helpers: NCHW float32 <-> NHWC bf16 */
+int dbb_nchw_f32_to_nhwc_bf16(const float* x, void* y, int64_t n, int c, int64_t h, int64_t w, void* stream);
+int dbb_nhwc_bf16_to_nchw_f32(const void* x, float* y, int64_t n, int c, int64_t h, int64_t w, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBB200_H_ */

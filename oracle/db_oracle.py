@@ -230,12 +230,14 @@ def bf16_round(t: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 
 def bce_elementwise(p: np.ndarray, g: np.ndarray) -> np.ndarray:
-    """F.binary_cross_entropy(reduction='none'), src/losses.py:30-32; logs clamped at -100."""
+    """F.binary_cross_entropy(reduction='none'), src/losses.py:30-32.  ATen evaluates
+    (t-1)*max(log1p(-x),-100) - t*max(log(x),-100) in float32."""
     p = p.astype(np.float32)
+    g = g.astype(np.float32)
     with np.errstate(divide="ignore"):
-        lp = np.maximum(np.log(p, dtype=np.float32), np.float32(-100.0))
-        l1p = np.maximum(np.log((np.float32(1.0) - p), dtype=np.float32), np.float32(-100.0))
-    return -(g * lp + (np.float32(1.0) - g) * l1p).astype(np.float32)
+        l0 = np.maximum(np.log(p, dtype=np.float32), np.float32(-100.0))
+        l1 = np.maximum(np.log1p(-p, dtype=np.float32), np.float32(-100.0))
+    return ((g - np.float32(1.0)) * l1 - g * l0).astype(np.float32)
 
 
 def bce_grad(p: np.ndarray, g: np.ndarray) -> np.ndarray:
