@@ -67,7 +67,9 @@ def lib():
     sig("dbb_net_flops_fwd", C.c_uint64, [vp])
     sig("dbb_net_forward", i32, [vp, vp, vp, vp, vp, vp, sz, vp])
     sig("dbb_net_num_segments", i32, [])
-    sig("dbb_net_backward", i32, [vp, vp, vp, vp, vp, sz, i32, vp])
+    sig("dbb_net_backward", i32, [vp, vp, vp, vp, vp, vp, sz, i32, vp])
+    sig("dbb_net_debug_shape", i32, [vp, C.c_char_p, vp])
+    sig("dbb_net_debug_read", i32, [vp, C.c_char_p, vp, vp, vp])
     sig("dbb_conv2d", i32, [i32, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, i32, vp, sz, vp])
     sig("dbb_conv2d_workspace", sz, [i32, i64, i64, i64, i32, i32, i32, i32, i32])
     sig("dbb_conv2d_wgrad", i32, [i32, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, i32, vp, sz, vp])

@@ -36,6 +36,7 @@ struct IgemmPlan {
   int out_sh, out_sw, out_oh, out_ow;
   int out_coff;            // channel offset inside Y's channel dimension
   const float* bias;       // may be null
+  int accumulate;          // 1: Y += result (gradient fan-in), 0: overwrite
 };
 
 // weight packing: fp32 parameter -> bf16 GEMM B matrix [rows][K] (K-major)
@@ -44,7 +45,8 @@ struct IgemmPlan {
 //   mode 2: ConvT   (ci,co,2,2)              -> [cls=(a*2+b)][co][ci]   4 matrices         (fprop, one per class)
 //   mode 3: ConvT   (ci,co,2,2)              -> [ci][(a*2+b)*co_n + co]                    (dgrad)
 //   mode 4: conv1 7x7/2 OIHW (64,3,7,7)      -> [co][kh2(4)][kw2(4)][16]  space-to-depth form, K = 256
-int pack_weights(int mode, const float* w, bf16* out, int co_n, int ci_n, int kh, int kw, cudaStream_t s);
+// co_total / co_off: (modes 1 and 3) the packed matrix is co_total wide and this tensor fills columns [co_off, co_off+co_n)
+int pack_weights(int mode, const float* w, bf16* out, int co_n, int ci_n, int kh, int kw, cudaStream_t s, int co_total = 0, int co_off = 0);
 
 int igemm_plan_init(IgemmPlan* p, const bf16* x, int n, int h, int w, int c_total, int c_off, int cin,
                     const bf16* wp, int k_total, int w_rows, int block_n);
@@ -72,6 +74,7 @@ int encode_tmap_raw4(CUtensorMap* m, const bf16* base, const cuuint64_t dims[4],
                      const cuuint32_t box[4]);
 int encode_tmap_nhwc(CUtensorMap* m, const bf16* base, int n, int h, int w, int c_total, int c_off, int c_extent,
                      int box_n, int box_h, int box_w, int stride_h, int stride_w);
+int encode_weights_public(CUtensorMap* m, const bf16* wp, int k_total, int rows, int block_n);
 void choose_box(int rows, int mn, int mh, int mw, int* bn, int* bh, int* bw);
 
 }  // namespace dbb

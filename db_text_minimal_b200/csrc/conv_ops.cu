@@ -13,10 +13,6 @@ static int pick_block_n(int cout, int64_t m_tiles) {
   return 64;
 }
 
-static void finish_tiles(IgemmPlan* p) {
-  (void)p;
-}
-
 int conv_fprop(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const bf16* wp, const float* bias, bf16* y,
                int y_ctotal, int y_coff, cudaStream_t s) {
   const int ho = g.out_h(), wo = g.out_w();
@@ -40,7 +36,7 @@ int conv_fprop(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const
   return igemm_launch(p, s);
 }
 
-int conv_dgrad(const ConvGeom& g, const bf16* dy, const bf16* wp_t, bf16* dx, cudaStream_t s) {
+int conv_dgrad(const ConvGeom& g, const bf16* dy, const bf16* wp_t, bf16* dx, cudaStream_t s, int accumulate) {
   // dx[n,h,w,ci] = sum_{kh,kw,co} dy[n,(h+pad-kh)/s,(w+pad-kw)/s,co] * W[co,ci,kh,kw]   (where divisible)
   const int ho = g.out_h(), wo = g.out_w();
   const int st = g.stride;
@@ -53,7 +49,7 @@ int conv_dgrad(const ConvGeom& g, const bf16* dy, const bf16* wp_t, bf16* dx, cu
         if ((a + g.pad - kh) % st == 0 && (b + g.pad - kw) % st == 0) ++nt;
       if (nt == 0) need_zero = true;
     }
-  if (need_zero) DBB_CUDA(cudaMemsetAsync(dx, 0, sizeof(bf16) * (size_t)g.n * g.h * g.w * g.cin, s));
+  if (need_zero && !accumulate) DBB_CUDA(cudaMemsetAsync(dx, 0, sizeof(bf16) * (size_t)g.n * g.h * g.w * g.cin, s));
   for (int a = 0; a < st; ++a)
     for (int b = 0; b < st; ++b) {
       IgemmPlan p;
@@ -75,6 +71,7 @@ int conv_dgrad(const ConvGeom& g, const bf16* dy, const bf16* wp_t, bf16* dx, cu
       p.y = dx; p.out_h = g.h; p.out_w = g.w; p.out_c = g.cin; p.out_coff = 0;
       p.out_sh = p.out_sw = st; p.out_oh = a; p.out_ow = b;
       p.bias = nullptr;
+      p.accumulate = accumulate;
       const int64_t m_tiles = ((int64_t)p.mn * p.mh * p.mw + 127) / 128;
       int rc = igemm_plan_init(&p, dy, g.n, ho, wo, g.cout, 0, g.cout, wp_t, g.ks * g.ks * g.cout, g.cin, pick_block_n(g.cin, m_tiles));
       if (rc) return rc;
@@ -84,7 +81,8 @@ int conv_dgrad(const ConvGeom& g, const bf16* dy, const bf16* wp_t, bf16* dx, cu
   return DBB_OK;
 }
 
-int convt_fprop(const ConvGeom& g, const bf16* x, const bf16* wp_cls, const float* bias, bf16* y, cudaStream_t s) {
+int convt_fprop(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const bf16* wp_cls, const float* bias, bf16* y,
+                int y_ctotal, int y_coff, cudaStream_t s) {
   // ConvTranspose2d(k=2, s=2): y[n,2i+a,2j+b,co] = sum_ci x[n,i,j,ci] * W[ci,co,a,b] + bias[co]
   for (int cls = 0; cls < 4; ++cls) {
     IgemmPlan p;
@@ -93,11 +91,11 @@ int convt_fprop(const ConvGeom& g, const bf16* x, const bf16* wp_cls, const floa
     p.in_sh = p.in_sw = 1;
     p.ntaps = 1; p.dh[0] = 0; p.dw[0] = 0; p.wtap[0] = 0;
     p.cout = g.cout;
-    p.y = y; p.out_h = 2 * g.h; p.out_w = 2 * g.w; p.out_c = g.cout; p.out_coff = 0;
+    p.y = y; p.out_h = 2 * g.h; p.out_w = 2 * g.w; p.out_c = y_ctotal; p.out_coff = y_coff;
     p.out_sh = p.out_sw = 2; p.out_oh = cls >> 1; p.out_ow = cls & 1;
     p.bias = bias;
     const int64_t m_tiles = ((int64_t)g.n * g.h * g.w + 127) / 128;
-    int rc = igemm_plan_init(&p, x, g.n, g.h, g.w, g.cin, 0, g.cin, wp_cls + (size_t)cls * g.cout * g.cin, g.cin, g.cout,
+    int rc = igemm_plan_init(&p, x, g.n, g.h, g.w, x_ctotal, x_coff, g.cin, wp_cls + (size_t)cls * g.cout * g.cin, g.cin, g.cout,
                              pick_block_n(g.cout, m_tiles));
     if (rc) return rc;
     rc = igemm_launch(p, s);
@@ -106,7 +104,8 @@ int convt_fprop(const ConvGeom& g, const bf16* x, const bf16* wp_cls, const floa
   return DBB_OK;
 }
 
-int convt_dgrad(const ConvGeom& g, const bf16* dy, const bf16* wp_t, bf16* dx, cudaStream_t s) {
+int convt_dgrad(const ConvGeom& g, const bf16* dy, int dy_ctotal, int dy_coff, const bf16* wp_t, bf16* dx, int dx_ctotal,
+                int dx_coff, cudaStream_t s) {
   // dx[n,i,j,ci] = sum_{a,b,co} dy[n,2i+a,2j+b,co] * W[ci,co,a,b]
   IgemmPlan p;
   memset(&p, 0, sizeof(p));
@@ -115,10 +114,10 @@ int convt_dgrad(const ConvGeom& g, const bf16* dy, const bf16* wp_t, bf16* dx, c
   p.ntaps = 4;
   for (int t = 0; t < 4; ++t) { p.dh[t] = (int8_t)(t >> 1); p.dw[t] = (int8_t)(t & 1); p.wtap[t] = (uint8_t)t; }
   p.cout = g.cin;
-  p.y = dx; p.out_h = g.h; p.out_w = g.w; p.out_c = g.cin; p.out_coff = 0;
+  p.y = dx; p.out_h = g.h; p.out_w = g.w; p.out_c = dx_ctotal; p.out_coff = dx_coff;
   p.out_sh = p.out_sw = 1; p.out_oh = p.out_ow = 0;
   const int64_t m_tiles = ((int64_t)g.n * g.h * g.w + 127) / 128;
-  int rc = igemm_plan_init(&p, dy, g.n, 2 * g.h, 2 * g.w, g.cout, 0, g.cout, wp_t, 4 * g.cout, g.cin, pick_block_n(g.cin, m_tiles));
+  int rc = igemm_plan_init(&p, dy, g.n, 2 * g.h, 2 * g.w, dy_ctotal, dy_coff, g.cout, wp_t, 4 * g.cout, g.cin, pick_block_n(g.cin, m_tiles));
   if (rc) return rc;
   return igemm_launch(p, s);
 }
@@ -130,8 +129,8 @@ static int pick_split_k(int64_t out_tiles, int total_pixel_tiles) {
   return (int)want;
 }
 
-static int wgrad_common(WgradPlan& p, const bf16* a, int a_n, int a_h, int a_w, int a_c, const bf16* b, int b_n, int b_h,
-                        int b_w, int b_c, cudaStream_t s) {
+static int wgrad_common(WgradPlan& p, const bf16* a, int a_n, int a_h, int a_w, int a_ctotal, int a_coff, int a_c,
+                        const bf16* b, int b_n, int b_h, int b_w, int b_ctotal, int b_coff, int b_c, cudaStream_t s) {
   choose_box(64, p.mn, p.mh, p.mw, &p.bn, &p.bh, &p.bw);
   p.tiles_n = (p.mn + p.bn - 1) / p.bn;
   p.tiles_h = (p.mh + p.bh - 1) / p.bh;
@@ -140,14 +139,15 @@ static int wgrad_common(WgradPlan& p, const bf16* a, int a_n, int a_h, int a_w, 
   p.n_tile = p.n_total >= 256 ? 256 : (p.n_total >= 128 ? 128 : 64);
   const int m_tiles = (p.m_total + 127) / 128, n_tiles = (p.n_total + p.n_tile - 1) / p.n_tile;
   p.split_k = pick_split_k((int64_t)p.ntaps * m_tiles * n_tiles, p.tiles_n * p.tiles_h * p.tiles_w);
-  int rc = encode_tmap_nhwc(&p.tmap_a, a, a_n, a_h, a_w, a_c, 0, a_c, p.bn, p.bh, p.bw, p.a_sh, p.a_sw);
+  int rc = encode_tmap_nhwc(&p.tmap_a, a, a_n, a_h, a_w, a_ctotal, a_coff, a_c, p.bn, p.bh, p.bw, p.a_sh, p.a_sw);
   if (rc) return rc;
-  rc = encode_tmap_nhwc(&p.tmap_b, b, b_n, b_h, b_w, b_c, 0, b_c, p.bn, p.bh, p.bw, p.b_sh, p.b_sw);
+  rc = encode_tmap_nhwc(&p.tmap_b, b, b_n, b_h, b_w, b_ctotal, b_coff, b_c, p.bn, p.bh, p.bw, p.b_sh, p.b_sw);
   if (rc) return rc;
   return wgrad_launch(p, s);
 }
 
-int conv_wgrad(const ConvGeom& g, const bf16* x, const bf16* dy, float* dw, cudaStream_t s) {
+int conv_wgrad(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const bf16* dy, int dy_ctotal, int dy_coff, float* dw,
+               cudaStream_t s) {
   // dW[co,ci,kh,kw] = sum_{n,i,j} dy[n,i,j,co] * x[n, i*s+kh-pad, j*s+kw-pad, ci]
   const int ho = g.out_h(), wo = g.out_w();
   DBB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g.cout * g.cin * g.ks * g.ks, s));
@@ -163,10 +163,11 @@ int conv_wgrad(const ConvGeom& g, const bf16* x, const bf16* dy, float* dw, cuda
     }
   p.m_total = g.cout; p.n_total = g.cin;
   p.dw = dw; p.tap_stride = p.ntaps;
-  return wgrad_common(p, dy, g.n, ho, wo, g.cout, x, g.n, g.h, g.w, g.cin, s);
+  return wgrad_common(p, dy, g.n, ho, wo, dy_ctotal, dy_coff, g.cout, x, g.n, g.h, g.w, x_ctotal, x_coff, g.cin, s);
 }
 
-int convt_wgrad(const ConvGeom& g, const bf16* x, const bf16* dy, float* dw, cudaStream_t s) {
+int convt_wgrad(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const bf16* dy, int dy_ctotal, int dy_coff, float* dw,
+                cudaStream_t s) {
   // dW[ci,co,a,b] = sum_{n,i,j} x[n,i,j,ci] * dy[n,2i+a,2j+b,co]
   DBB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g.cout * g.cin * 4, s));
   WgradPlan p;
@@ -177,7 +178,60 @@ int convt_wgrad(const ConvGeom& g, const bf16* x, const bf16* dy, float* dw, cud
   for (int t = 0; t < 4; ++t) { p.a_dh[t] = 0; p.a_dw[t] = 0; p.b_dh[t] = (int8_t)(t >> 1); p.b_dw[t] = (int8_t)(t & 1); }
   p.m_total = g.cin; p.n_total = g.cout;
   p.dw = dw; p.tap_stride = 4;
-  return wgrad_common(p, x, g.n, g.h, g.w, g.cin, dy, g.n, 2 * g.h, 2 * g.w, g.cout, s);
+  return wgrad_common(p, x, g.n, g.h, g.w, x_ctotal, x_coff, g.cin, dy, g.n, 2 * g.h, 2 * g.w, dy_ctotal, dy_coff, g.cout, s);
+}
+
+// ---- conv1: Conv2d(3, 64, 7, stride 2, pad 3) as a 4x4 stride-1 convolution over the space-to-depth image.
+// The staging buffer [n][hs+3][ws+3][16] is viewed through an OVERLAPPING tensor map {64, ws, hs+3, n} with a 32-byte
+// stride along W: one 128-byte "row" is 4 consecutive s2d pixels x 16 channels = the kw2 taps of one kh2 row.
+static int conv1_tmap(CUtensorMap* m, const bf16* s2d, int n, int hs, int ws, int bn, int bh, int bw) {
+  const cuuint64_t dims[4] = {64, (cuuint64_t)ws, (cuuint64_t)(hs + 3), (cuuint64_t)n};
+  const cuuint64_t strides[3] = {32, (cuuint64_t)(ws + 3) * 32, (cuuint64_t)(hs + 3) * (ws + 3) * 32};
+  const cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  return encode_tmap_raw4(m, s2d, dims, strides, box);
+}
+
+int conv1_fprop(int n, int h, int w, const bf16* s2d, const bf16* wp, bf16* y, cudaStream_t s) {
+  const int hs = (h + 1) / 2, ws = (w + 1) / 2;
+  IgemmPlan p;
+  memset(&p, 0, sizeof(p));
+  p.mn = n; p.mh = hs; p.mw = ws;
+  p.in_sh = p.in_sw = 1;
+  p.ntaps = 4;
+  for (int t = 0; t < 4; ++t) { p.dh[t] = (int8_t)t; p.dw[t] = 0; p.wtap[t] = (uint8_t)t; }
+  p.cout = 64;
+  p.y = y; p.out_h = hs; p.out_w = ws; p.out_c = 64; p.out_coff = 0;
+  p.out_sh = p.out_sw = 1;
+  p.cin = 64; p.block_n = 64;
+  choose_box(128, p.mn, p.mh, p.mw, &p.bn, &p.bh, &p.bw);
+  p.tiles_n = (p.mn + p.bn - 1) / p.bn; p.tiles_h = (p.mh + p.bh - 1) / p.bh; p.tiles_w = (p.mw + p.bw - 1) / p.bw;
+  int rc = conv1_tmap(&p.tmap_x, s2d, n, hs, ws, p.bn, p.bh, p.bw);
+  if (rc) return rc;
+  rc = encode_weights_public(&p.tmap_w, wp, 256, 64, 64);   // 2-D weight map: [64 rows][256 K]
+  if (rc) return rc;
+  return igemm_launch(p, s);
+}
+
+int conv1_wgrad(int n, int h, int w, const bf16* s2d, const bf16* dy, float* dw_s2d, cudaStream_t s) {
+  const int hs = (h + 1) / 2, ws = (w + 1) / 2;
+  DBB_CUDA(cudaMemsetAsync(dw_s2d, 0, sizeof(float) * 64 * 64 * 4, s));
+  WgradPlan p;
+  memset(&p, 0, sizeof(p));
+  p.mn = n; p.mh = hs; p.mw = ws;
+  p.a_sh = p.a_sw = 1; p.b_sh = p.b_sw = 1;
+  p.ntaps = 4;
+  for (int t = 0; t < 4; ++t) { p.b_dh[t] = (int8_t)t; p.b_dw[t] = 0; }
+  p.m_total = 64; p.n_total = 64;
+  p.dw = dw_s2d; p.tap_stride = 4;
+  choose_box(64, p.mn, p.mh, p.mw, &p.bn, &p.bh, &p.bw);
+  p.tiles_n = (p.mn + p.bn - 1) / p.bn; p.tiles_h = (p.mh + p.bh - 1) / p.bh; p.tiles_w = (p.mw + p.bw - 1) / p.bw;
+  p.m_tile = 128; p.n_tile = 64;
+  p.split_k = pick_split_k(4, p.tiles_n * p.tiles_h * p.tiles_w);
+  int rc = encode_tmap_nhwc(&p.tmap_a, dy, n, hs, ws, 64, 0, 64, p.bn, p.bh, p.bw, 1, 1);
+  if (rc) return rc;
+  rc = conv1_tmap(&p.tmap_b, s2d, n, hs, ws, p.bn, p.bh, p.bw);
+  if (rc) return rc;
+  return wgrad_launch(p, s);
 }
 
 }  // namespace dbb
@@ -218,11 +272,11 @@ extern "C" int dbb_conv2d(int kind, const void* x, const float* w, const float* 
     case 2:
       if (ksize != 2 || stride != 2) return set_error(DBB_EUNSUPPORTED, "convT: only k=2, s=2");
       if ((rc = pack_weights(2, w, wp, cout, cin, 2, 2, s))) return rc;
-      return convt_fprop(g, (const bf16*)x, wp, bias, (bf16*)y, s);
+      return convt_fprop(g, (const bf16*)x, cin, 0, wp, bias, (bf16*)y, cout, 0, s);
     case 3:
       if (ksize != 2 || stride != 2) return set_error(DBB_EUNSUPPORTED, "convT: only k=2, s=2");
       if ((rc = pack_weights(3, w, wp, cout, cin, 2, 2, s))) return rc;
-      return convt_dgrad(g, (const bf16*)x, wp, (bf16*)y, s);
+      return convt_dgrad(g, (const bf16*)x, cout, 0, wp, (bf16*)y, cin, 0, s);
     default: return set_error(DBB_EINVAL, "conv2d: kind must be 0..3");
   }
 }
@@ -235,10 +289,10 @@ extern "C" int dbb_conv2d_wgrad(int kind, const void* x, const void* dy, float* 
   if (rc) return rc;
   if (!aligned16(x) || !aligned16(dy) || !aligned16(dw)) return set_error(DBB_EALIGN, "conv2d_wgrad: pointer not 16B aligned");
   ConvGeom g{(int)n, (int)h, (int)wdt, cin, cout, ksize, stride, pad};
-  if (kind == 0) return conv_wgrad(g, (const bf16*)x, (const bf16*)dy, dw, (cudaStream_t)stream);
+  if (kind == 0) return conv_wgrad(g, (const bf16*)x, cin, 0, (const bf16*)dy, cout, 0, dw, (cudaStream_t)stream);
   if (kind == 2) {
     if (ksize != 2 || stride != 2) return set_error(DBB_EUNSUPPORTED, "convT: only k=2, s=2");
-    return convt_wgrad(g, (const bf16*)x, (const bf16*)dy, dw, (cudaStream_t)stream);
+    return convt_wgrad(g, (const bf16*)x, cin, 0, (const bf16*)dy, cout, 0, dw, (cudaStream_t)stream);
   }
   return set_error(DBB_EINVAL, "conv2d_wgrad: kind must be 0 (Conv2d) or 2 (ConvTranspose2d)");
 }

@@ -124,10 +124,17 @@ igemm_kernel(const __grid_constant__ IgemmPlan p) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + col0 + j);
         }
+        uint4* dst = reinterpret_cast<uint4*>(yrow + c);
+        if (p.accumulate) {
+          const uint4 e0 = dst[0], e1 = dst[1];
+          f[0] += bf16lo(e0.x); f[1] += bf16hi(e0.x); f[2] += bf16lo(e0.y); f[3] += bf16hi(e0.y);
+          f[4] += bf16lo(e0.z); f[5] += bf16hi(e0.z); f[6] += bf16lo(e0.w); f[7] += bf16hi(e0.w);
+          f[8] += bf16lo(e1.x); f[9] += bf16hi(e1.x); f[10] += bf16lo(e1.y); f[11] += bf16hi(e1.y);
+          f[12] += bf16lo(e1.z); f[13] += bf16hi(e1.z); f[14] += bf16lo(e1.w); f[15] += bf16hi(e1.w);
+        }
         uint4 o0, o1;
         o0.x = pack_bf16(f[0], f[1]);   o0.y = pack_bf16(f[2], f[3]);   o0.z = pack_bf16(f[4], f[5]);   o0.w = pack_bf16(f[6], f[7]);
         o1.x = pack_bf16(f[8], f[9]);   o1.y = pack_bf16(f[10], f[11]); o1.z = pack_bf16(f[12], f[13]); o1.w = pack_bf16(f[14], f[15]);
-        uint4* dst = reinterpret_cast<uint4*>(yrow + c);
         dst[0] = o0; dst[1] = o1;
       }
     }
@@ -259,7 +266,8 @@ wgrad_kernel(const __grid_constant__ WgradPlan p) {
 // ---------------------------------------------------------------------------------------------
 // weight packing (fp32 parameters -> bf16 GEMM operand)
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_weights_kernel(int mode, const float* __restrict__ w, bf16* __restrict__ out, int co_n, int ci_n, int kh, int kw) {
+__global__ void pack_weights_kernel(int mode, const float* __restrict__ w, bf16* __restrict__ out, int co_n, int ci_n, int kh, int kw,
+                                    int co_total, int co_off) {
   const int taps = kh * kw;
   const int64_t total = (mode == 4) ? (int64_t)co_n * 256 : (int64_t)co_n * ci_n * taps;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -270,12 +278,16 @@ __global__ void pack_weights_kernel(int mode, const float* __restrict__ w, bf16*
     } else if (mode == 1) {   // out[ci][tap][co] <- w[co][ci][tap]
       const int co = i % co_n; const int tap = (i / co_n) % taps; const int ci = i / ((int64_t)co_n * taps);
       v = w[((int64_t)co * ci_n + ci) * taps + tap];
+      out[((int64_t)ci * taps + tap) * co_total + co_off + co] = __float2bfloat16_rn(v);
+      continue;
     } else if (mode == 2) {   // out[cls][co][ci] <- w[ci][co][cls]   (ConvT weight is (ci, co, 2, 2))
       const int ci = i % ci_n; const int co = (i / ci_n) % co_n; const int cls = i / ((int64_t)ci_n * co_n);
       v = w[((int64_t)ci * co_n + co) * 4 + cls];
     } else if (mode == 3) {   // out[ci][cls][co] <- w[ci][co][cls]
       const int co = i % co_n; const int cls = (i / co_n) % 4; const int ci = i / ((int64_t)co_n * 4);
       v = w[((int64_t)ci * co_n + co) * 4 + cls];
+      out[((int64_t)ci * 4 + cls) * co_total + co_off + co] = __float2bfloat16_rn(v);
+      continue;
     } else {                  // conv1 7x7/2 in space-to-depth form: out[co][kh2][kw2][16], ch = (py*2+px)*3 + c (12 used)
       const int ch = i % 16; const int kw2 = (i / 16) % 4; const int kh2 = (i / 64) % 4; const int co = i / 256;
       v = 0.f;
@@ -290,11 +302,12 @@ __global__ void pack_weights_kernel(int mode, const float* __restrict__ w, bf16*
   }
 }
 
-int pack_weights(int mode, const float* w, bf16* out, int co_n, int ci_n, int kh, int kw, cudaStream_t s) {
+int pack_weights(int mode, const float* w, bf16* out, int co_n, int ci_n, int kh, int kw, cudaStream_t s, int co_total, int co_off) {
+  if (co_total <= 0) { co_total = co_n; co_off = 0; }
   const int64_t total = (mode == 4) ? (int64_t)co_n * 256 : (int64_t)co_n * ci_n * kh * kw;
   int grid = (int)((total + 255) / 256);
   if (grid > DBB_NUM_SMS * 8) grid = DBB_NUM_SMS * 8;
-  pack_weights_kernel<<<grid, 256, 0, s>>>(mode, w, out, co_n, ci_n, kh, kw);
+  pack_weights_kernel<<<grid, 256, 0, s>>>(mode, w, out, co_n, ci_n, kh, kw, co_total, co_off);
   DBB_CHECK_LAUNCH("pack_weights");
   return DBB_OK;
 }
@@ -368,6 +381,10 @@ static int encode_tmap_weights(CUtensorMap* m, const bf16* wp, int k_total, int 
     return DBB_ECUDA;
   }
   return DBB_OK;
+}
+
+int encode_weights_public(CUtensorMap* m, const bf16* wp, int k_total, int rows, int block_n) {
+  return encode_tmap_weights(m, wp, k_total, rows, block_n);
 }
 
 // pick a (bn, bh, bw) box of exactly `rows` pixels (power-of-two factors) with the least overhang

@@ -60,6 +60,556 @@ int nhwc_bf16_to_nchw_f32(const bf16* x, float* y, int n, int c, int64_t hw, cud
   return DBB_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// per-channel machinery: a thread owns one 8-channel group (16 B) and walks pixels
+// ---------------------------------------------------------------------------------------------
+constexpr int EW_THREADS = 256;
+
+struct F8 { float v[8]; };
+__device__ __forceinline__ F8 ld8(const bf16* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  F8 r;
+  r.v[0] = bf16lo(u.x); r.v[1] = bf16hi(u.x); r.v[2] = bf16lo(u.y); r.v[3] = bf16hi(u.y);
+  r.v[4] = bf16lo(u.z); r.v[5] = bf16hi(u.z); r.v[6] = bf16lo(u.w); r.v[7] = bf16hi(u.w);
+  return r;
+}
+__device__ __forceinline__ F8 ld8s(const bf16* p) {   // streaming variant (touched once)
+  const uint4 u = ldg_stream(reinterpret_cast<const uint4*>(p));
+  F8 r;
+  r.v[0] = bf16lo(u.x); r.v[1] = bf16hi(u.x); r.v[2] = bf16lo(u.y); r.v[3] = bf16hi(u.y);
+  r.v[4] = bf16lo(u.z); r.v[5] = bf16hi(u.z); r.v[6] = bf16lo(u.w); r.v[7] = bf16hi(u.w);
+  return r;
+}
+__device__ __forceinline__ void st8(bf16* p, const F8& a) {
+  uint4 u;
+  u.x = pack_bf16(a.v[0], a.v[1]); u.y = pack_bf16(a.v[2], a.v[3]); u.z = pack_bf16(a.v[4], a.v[5]); u.w = pack_bf16(a.v[6], a.v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ F8 ldf8(const float* p) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  return F8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+
+static int ew_blocks(int64_t P, int c) {
+  const int ppi = EW_THREADS / (c / 8);              // pixels per block iteration
+  int64_t want = (P + (int64_t)ppi * 4 - 1) / ((int64_t)ppi * 4);
+  if (want < 1) want = 1;
+  if (want > BN_MAX_BLOCKS) want = BN_MAX_BLOCKS;
+  return (int)want;
+}
+
+// block-level reduction of per-thread 8-channel accumulators over the pixel lanes; writes [2][C] (or [1][C])
+template <int NACC>
+__device__ __forceinline__ void reduce_groups_store(float (&acc)[NACC][8], int c, float* out /* [NACC][c] */) {
+  __shared__ float sh[EW_THREADS * 8];
+  const int groups = c / 8;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
+  const int lanes = EW_THREADS / groups;
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[(pl * groups + g) * 8 + j] = acc[a][j];
+    __syncthreads();
+    // thread t < c sums channel t over the pixel lanes
+    for (int ch = threadIdx.x; ch < c; ch += EW_THREADS) {
+      const int gg = ch / 8, jj = ch % 8;
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += sh[(l * groups + gg) * 8 + jj];
+      out[a * c + ch] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS) bn_stats_kernel(const bf16* __restrict__ z, int64_t P, int c, float* __restrict__ partials) {
+  const int groups = c / 8;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups, lanes = EW_THREADS / groups;
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+  for (int64_t p = (int64_t)blockIdx.x * lanes + pl; p < P; p += (int64_t)gridDim.x * lanes) {
+    const F8 x = ld8(z + p * c + g * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[0][j] += x.v[j]; acc[1][j] += x.v[j] * x.v[j]; }
+  }
+  reduce_groups_store<2>(acc, c, partials + (size_t)blockIdx.x * 2 * c);
+}
+
+__global__ void bn_finalize_train_kernel(const float* __restrict__ partials, int nblk, int c, int coff, int cn, double count,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         float* __restrict__ rmean, float* __restrict__ rvar, float momentum, float eps,
+                                         float* __restrict__ stats4) {
+  int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= cn) return;
+  gamma += ch; beta += ch; if (rmean) { rmean += ch; rvar += ch; }
+  ch += coff;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < nblk; ++b) { s += (double)partials[(size_t)b * 2 * c + ch]; q += (double)partials[(size_t)b * 2 * c + c + ch]; }
+  const double mean = s / count;
+  double var = q / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double invstd = 1.0 / sqrt(var + (double)eps);
+  const float sc = (float)((double)gamma[0] * invstd);
+  stats4[ch] = sc;
+  stats4[c + ch] = (float)((double)beta[0] - mean * (double)gamma[0] * invstd);
+  stats4[2 * c + ch] = (float)mean;
+  stats4[3 * c + ch] = (float)invstd;
+  if (rmean) {   // running stats: unbiased variance, momentum 0.1 (torch.nn.BatchNorm2d)
+    const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+    rmean[0] = (float)((1.0 - momentum) * (double)rmean[0] + momentum * mean);
+    rvar[0] = (float)((1.0 - momentum) * (double)rvar[0] + momentum * unb);
+  }
+}
+
+__global__ void bn_finalize_eval_kernel(int c, int coff, int cn, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                        const float* __restrict__ rmean, const float* __restrict__ rvar, float eps,
+                                        float* __restrict__ stats4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cn) return;
+  const int ch = coff + i;
+  const float invstd = 1.f / sqrtf(rvar[i] + eps);
+  stats4[ch] = gamma[i] * invstd;
+  stats4[c + ch] = beta[i] - rmean[i] * gamma[i] * invstd;
+  stats4[2 * c + ch] = rmean[i];
+  stats4[3 * c + ch] = invstd;
+}
+
+__global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const bf16* __restrict__ z, int64_t P, int c, const float* __restrict__ stats4,
+                                                              const bf16* __restrict__ res, int relu, bf16* __restrict__ out,
+                                                              int out_ctotal, int out_coff) {
+  const int groups = c / 8;
+  const int64_t total = P * groups;
+  for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
+    const int64_t p = i / groups; const int g = (int)(i - p * groups);
+    const F8 x = ld8s(z + p * c + g * 8);
+    const F8 sc = ldf8(stats4 + g * 8), sh = ldf8(stats4 + c + g * 8);
+    F8 y;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y.v[j] = fmaf(x.v[j], sc.v[j], sh.v[j]);
+    if (res) {
+      const F8 r = ld8s(res + p * c + g * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y.v[j] += r.v[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y.v[j] = fmaxf(y.v[j], 0.f);
+    }
+    st8(out + p * out_ctotal + out_coff + g * 8, y);
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+bn_bwd_reduce_kernel(const bf16* __restrict__ dout, int dout_ctotal, int dout_coff, const bf16* __restrict__ mask_src,
+                     int mask_ctotal, int mask_coff, const bf16* __restrict__ z, int64_t P, int c,
+                     const float* __restrict__ stats4, float* __restrict__ partials) {
+  const int groups = c / 8;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups, lanes = EW_THREADS / groups;
+  const F8 mean = ldf8(stats4 + 2 * c + g * 8), inv = ldf8(stats4 + 3 * c + g * 8);
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+  for (int64_t p = (int64_t)blockIdx.x * lanes + pl; p < P; p += (int64_t)gridDim.x * lanes) {
+    F8 dy = ld8(dout + p * dout_ctotal + dout_coff + g * 8);
+    if (mask_src) {
+      const F8 m = ld8(mask_src + p * mask_ctotal + mask_coff + g * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dy.v[j] = m.v[j] > 0.f ? dy.v[j] : 0.f;
+    }
+    const F8 x = ld8(z + p * c + g * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[0][j] += dy.v[j]; acc[1][j] += dy.v[j] * (x.v[j] - mean.v[j]) * inv.v[j]; }
+  }
+  reduce_groups_store<2>(acc, c, partials + (size_t)blockIdx.x * 2 * c);
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nblk, int c, int coff, int cn, double count,
+                                       const float* __restrict__ gamma, const float* __restrict__ stats4,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cn) return;
+  const int ch = coff + i;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < nblk; ++b) { s += (double)partials[(size_t)b * 2 * c + ch]; q += (double)partials[(size_t)b * 2 * c + c + ch]; }
+  if (dgamma) dgamma[i] = (float)q;
+  if (dbeta) dbeta[i] = (float)s;
+  coef3[ch] = gamma[i] * stats4[3 * c + ch];
+  coef3[c + ch] = (float)(s / count);
+  coef3[2 * c + ch] = (float)(q / count);
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+bn_bwd_apply_kernel(const bf16* __restrict__ dout, int dout_ctotal, int dout_coff, const bf16* __restrict__ mask_src,
+                    int mask_ctotal, int mask_coff, const bf16* __restrict__ z, int64_t P, int c,
+                    const float* __restrict__ stats4, const float* __restrict__ coef3, bf16* __restrict__ dz,
+                    bf16* __restrict__ dsum) {
+  const int groups = c / 8;
+  const int64_t total = P * groups;
+  for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
+    const int64_t p = i / groups; const int g = (int)(i - p * groups);
+    F8 dy = ld8s(dout + p * dout_ctotal + dout_coff + g * 8);
+    if (mask_src) {
+      const F8 m = ld8s(mask_src + p * mask_ctotal + mask_coff + g * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dy.v[j] = m.v[j] > 0.f ? dy.v[j] : 0.f;
+    }
+    const F8 x = ld8s(z + p * c + g * 8);
+    const F8 mean = ldf8(stats4 + 2 * c + g * 8), inv = ldf8(stats4 + 3 * c + g * 8);
+    const F8 a = ldf8(coef3 + g * 8), c1 = ldf8(coef3 + c + g * 8), c2 = ldf8(coef3 + 2 * c + g * 8);
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = a.v[j] * (dy.v[j] - c1.v[j] - (x.v[j] - mean.v[j]) * inv.v[j] * c2.v[j]);
+    st8(dz + p * c + g * 8, o);
+    if (dsum) st8(dsum + p * c + g * 8, dy);
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS) colsum_kernel(const bf16* __restrict__ x, int64_t P, int c, float* __restrict__ partials) {
+  const int groups = c / 8;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups, lanes = EW_THREADS / groups;
+  float acc[1][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
+  for (int64_t p = (int64_t)blockIdx.x * lanes + pl; p < P; p += (int64_t)gridDim.x * lanes) {
+    const F8 v = ld8(x + p * c + g * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] += v.v[j];
+  }
+  reduce_groups_store<1>(acc, c, partials + (size_t)blockIdx.x * c);
+}
+__global__ void colsum_finalize_kernel(const float* __restrict__ partials, int nblk, int c, float* __restrict__ out) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += (double)partials[(size_t)b * c + ch];
+  out[ch] = (float)s;
+}
+
+static int check_c(int c) { return (c % 8 == 0 && c >= 8 && c <= 2048 && EW_THREADS % (c / 8) == 0) ? 0 : 1; }
+
+int bn_stats(const bf16* z, int64_t P, int c, float* partials, int* nblk, cudaStream_t s) {
+  if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_stats: channel count");
+  *nblk = ew_blocks(P, c);
+  bn_stats_kernel<<<*nblk, EW_THREADS, 0, s>>>(z, P, c, partials);
+  DBB_CHECK_LAUNCH("bn_stats");
+  return DBB_OK;
+}
+int bn_finalize_train(const float* partials, int nblk, int c, int coff, int cn, int64_t count, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, float momentum, float eps, float* stats4, cudaStream_t s) {
+  bn_finalize_train_kernel<<<(cn + 127) / 128, 128, 0, s>>>(partials, nblk, c, coff, cn, (double)count, gamma, beta, running_mean, running_var, momentum, eps, stats4);
+  DBB_CHECK_LAUNCH("bn_finalize_train");
+  return DBB_OK;
+}
+int bn_finalize_eval(int c, int coff, int cn, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                     float eps, float* stats4, cudaStream_t s) {
+  bn_finalize_eval_kernel<<<(cn + 127) / 128, 128, 0, s>>>(c, coff, cn, gamma, beta, running_mean, running_var, eps, stats4);
+  DBB_CHECK_LAUNCH("bn_finalize_eval");
+  return DBB_OK;
+}
+static int stream_grid(int64_t total) {
+  int64_t g = (total + EW_THREADS - 1) / EW_THREADS;
+  if (g > DBB_NUM_SMS * 16) g = DBB_NUM_SMS * 16;
+  return (int)(g < 1 ? 1 : g);
+}
+int bn_apply(const bf16* z, int64_t P, int c, const float* stats4, const bf16* res, int relu, bf16* out, int out_ctotal,
+             int out_coff, cudaStream_t s) {
+  if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_apply: channel count");
+  bn_apply_kernel<<<stream_grid(P * (c / 8)), EW_THREADS, 0, s>>>(z, P, c, stats4, res, relu, out, out_ctotal, out_coff);
+  DBB_CHECK_LAUNCH("bn_apply");
+  return DBB_OK;
+}
+int bn_bwd_reduce(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
+                  const bf16* z, int64_t P, int c, const float* stats4, float* partials, int* nblk, cudaStream_t s) {
+  if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_bwd_reduce: channel count");
+  *nblk = ew_blocks(P, c);
+  bn_bwd_reduce_kernel<<<*nblk, EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, partials);
+  DBB_CHECK_LAUNCH("bn_bwd_reduce");
+  return DBB_OK;
+}
+int bn_bwd_finalize(const float* partials, int nblk, int c, int coff, int cn, int64_t count, const float* gamma, const float* stats4,
+                    float* dgamma, float* dbeta, float* coef3, cudaStream_t s) {
+  bn_bwd_finalize_kernel<<<(cn + 127) / 128, 128, 0, s>>>(partials, nblk, c, coff, cn, (double)count, gamma, stats4, dgamma, dbeta, coef3);
+  DBB_CHECK_LAUNCH("bn_bwd_finalize");
+  return DBB_OK;
+}
+int bn_bwd_apply(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
+                 const bf16* z, int64_t P, int c, const float* stats4, const float* coef3, bf16* dz, bf16* dsum,
+                 cudaStream_t s) {
+  if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_bwd_apply: channel count");
+  bn_bwd_apply_kernel<<<stream_grid(P * (c / 8)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, coef3, dz, dsum);
+  DBB_CHECK_LAUNCH("bn_bwd_apply");
+  return DBB_OK;
+}
+int bias_grad(const bf16* dz, int64_t P, int c, float* partials, float* dbias, cudaStream_t s) {
+  if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bias_grad: channel count");
+  const int nblk = ew_blocks(P, c);
+  colsum_kernel<<<nblk, EW_THREADS, 0, s>>>(dz, P, c, partials);
+  DBB_CHECK_LAUNCH("colsum");
+  colsum_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(partials, nblk, c, dbias);
+  DBB_CHECK_LAUNCH("colsum_finalize");
+  return DBB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MaxPool2d(kernel 3, stride 2, padding 1); argmax = first maximum in (kh, kw) scan order (ATen semantics)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS) maxpool_fwd_kernel(const bf16* __restrict__ x, int n, int h, int w, int c, int oh, int ow,
+                                                                 bf16* __restrict__ y, uint8_t* __restrict__ argmax) {
+  const int groups = c / 8;
+  const int64_t total = (int64_t)n * oh * ow * groups;
+  for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
+    const int g = (int)(i % groups); int64_t t = i / groups;
+    const int x0 = (int)(t % ow); t /= ow; const int y0 = (int)(t % oh); const int b = (int)(t / oh);
+    F8 best; uint8_t bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best.v[j] = -INFINITY; bi[j] = 0; }
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int yy = 2 * y0 - 1 + kh;
+      if (yy < 0 || yy >= h) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int xx = 2 * x0 - 1 + kw;
+        if (xx < 0 || xx >= w) continue;
+        const F8 v = ld8(x + (((int64_t)b * h + yy) * w + xx) * c + g * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (v.v[j] > best.v[j]) { best.v[j] = v.v[j]; bi[j] = (uint8_t)(kh * 3 + kw); }
+      }
+    }
+    const int64_t o = (((int64_t)b * oh + y0) * ow + x0) * c + g * 8;
+    st8(y + o, best);
+    if (argmax) {
+      uint2 pk;
+      pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+      pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+      *reinterpret_cast<uint2*>(argmax + o) = pk;
+    }
+  }
+}
+__global__ void __launch_bounds__(EW_THREADS) maxpool_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* __restrict__ argmax, int n, int h,
+                                                                 int w, int c, int oh, int ow, bf16* __restrict__ dx) {
+  const int groups = c / 8;
+  const int64_t total = (int64_t)n * h * w * groups;
+  for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
+    const int g = (int)(i % groups); int64_t t = i / groups;
+    const int xx = (int)(t % w); t /= w; const int yy = (int)(t % h); const int b = (int)(t / h);
+    F8 acc;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
+    // windows (y0, x0) with 2*y0-1 <= yy <= 2*y0+1
+    const int y_lo = yy / 2, y_hi = (yy + 1) / 2, x_lo = xx / 2, x_hi = (xx + 1) / 2;
+    for (int y0 = y_lo; y0 <= y_hi; ++y0) {
+      if (y0 >= oh) continue;
+      const int kh = yy - (2 * y0 - 1);
+      for (int x0 = x_lo; x0 <= x_hi; ++x0) {
+        if (x0 >= ow) continue;
+        const int k = kh * 3 + (xx - (2 * x0 - 1));
+        const int64_t o = (((int64_t)b * oh + y0) * ow + x0) * c + g * 8;
+        const uint2 pk = *reinterpret_cast<const uint2*>(argmax + o);
+        const F8 d = ld8(dy + o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const unsigned idx = ((j < 4 ? pk.x : pk.y) >> ((j & 3) * 8)) & 0xffu;
+          if ((int)idx == k) acc.v[j] += d.v[j];
+        }
+      }
+    }
+    st8(dx + (((int64_t)b * h + yy) * w + xx) * c + g * 8, acc);
+  }
+}
+int maxpool_fwd(const bf16* x, int n, int h, int w, int c, bf16* y, uint8_t* argmax, cudaStream_t s) {
+  const int oh = (h + 2 - 3) / 2 + 1, ow = (w + 2 - 3) / 2 + 1;
+  maxpool_fwd_kernel<<<stream_grid((int64_t)n * oh * ow * (c / 8)), EW_THREADS, 0, s>>>(x, n, h, w, c, oh, ow, y, argmax);
+  DBB_CHECK_LAUNCH("maxpool_fwd");
+  return DBB_OK;
+}
+int maxpool_bwd(const bf16* dy, const uint8_t* argmax, int n, int h, int w, int c, bf16* dx, cudaStream_t s) {
+  const int oh = (h + 2 - 3) / 2 + 1, ow = (w + 2 - 3) / 2 + 1;
+  maxpool_bwd_kernel<<<stream_grid((int64_t)n * h * w * (c / 8)), EW_THREADS, 0, s>>>(dy, argmax, n, h, w, c, oh, ow, dx);
+  DBB_CHECK_LAUNCH("maxpool_bwd");
+  return DBB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// nearest-neighbour upsampling, F.interpolate(mode='nearest'): src = min(floor(dst * fp32(in/out)), in-1)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
+  const int s = (int)floorf((float)dst * scale);
+  return s < in_size - 1 ? s : in_size - 1;
+}
+__global__ void __launch_bounds__(EW_THREADS) upsample_fwd_kernel(const bf16* __restrict__ xs, int hs, int ws, float sch, float scw,
+                                                                  const bf16* __restrict__ addend, int n, int h, int w, int c,
+                                                                  bf16* __restrict__ dst, int dst_ctotal, int dst_coff) {
+  const int groups = c / 8;
+  const int64_t total = (int64_t)n * h * w * groups;
+  for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
+    const int g = (int)(i % groups); int64_t t = i / groups;
+    const int xx = (int)(t % w); t /= w; const int yy = (int)(t % h); const int b = (int)(t / h);
+    const int sy = nearest_src(yy, sch, hs), sx = nearest_src(xx, scw, ws);
+    F8 v = ld8(xs + (((int64_t)b * hs + sy) * ws + sx) * c + g * 8);
+    const int64_t pix = ((int64_t)b * h + yy) * w + xx;
+    if (addend) {
+      const F8 a = ld8s(addend + pix * c + g * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v.v[j] += a.v[j];
+    }
+    st8(dst + pix * dst_ctotal + dst_coff + g * 8, v);
+  }
+}
+__global__ void __launch_bounds__(EW_THREADS) upsample_bwd_kernel(const bf16* __restrict__ d_big, int big_ctotal, int big_coff, int n, int h,
+                                                                  int w, int c, float sch, float scw, bf16* __restrict__ d_xs,
+                                                                  int hs, int ws, int accumulate) {
+  const int groups = c / 8;
+  const int64_t total = (int64_t)n * hs * ws * groups;
+  for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
+    const int g = (int)(i % groups); int64_t t = i / groups;
+    const int sx = (int)(t % ws); t /= ws; const int sy = (int)(t % hs); const int b = (int)(t / hs);
+    // destination rows/cols that read (sy, sx): a contiguous range (the map is monotone)
+    int y0 = (int)ceilf((float)sy / sch) - 2; if (y0 < 0) y0 = 0;
+    while (y0 < h && nearest_src(y0, sch, hs) < sy) ++y0;
+    int y1 = y0; while (y1 < h && nearest_src(y1, sch, hs) == sy) ++y1;
+    int x0 = (int)ceilf((float)sx / scw) - 2; if (x0 < 0) x0 = 0;
+    while (x0 < w && nearest_src(x0, scw, ws) < sx) ++x0;
+    int x1 = x0; while (x1 < w && nearest_src(x1, scw, ws) == sx) ++x1;
+    F8 acc;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
+    for (int yy = y0; yy < y1; ++yy)
+      for (int xx = x0; xx < x1; ++xx) {
+        const F8 d = ld8(d_big + (((int64_t)b * h + yy) * w + xx) * big_ctotal + big_coff + g * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc.v[j] += d.v[j];
+      }
+    bf16* o = d_xs + (((int64_t)b * hs + sy) * ws + sx) * c + g * 8;
+    if (accumulate) {
+      const F8 old = ld8(o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc.v[j] += old.v[j];
+    }
+    st8(o, acc);
+  }
+}
+int upsample_add_fwd(const bf16* xs, int hs, int ws, const bf16* y, int n, int h, int w, int c, bf16* out, cudaStream_t s) {
+  upsample_fwd_kernel<<<stream_grid((int64_t)n * h * w * (c / 8)), EW_THREADS, 0, s>>>(xs, hs, ws, (float)hs / (float)h, (float)ws / (float)w, y, n, h, w, c, out, c, 0);
+  DBB_CHECK_LAUNCH("upsample_add_fwd");
+  return DBB_OK;
+}
+int upsample_into(const bf16* xs, int hs, int ws, int n, int h, int w, int c, bf16* dst, int dst_ctotal, int dst_coff, cudaStream_t s) {
+  upsample_fwd_kernel<<<stream_grid((int64_t)n * h * w * (c / 8)), EW_THREADS, 0, s>>>(xs, hs, ws, (float)hs / (float)h, (float)ws / (float)w, nullptr, n, h, w, c, dst, dst_ctotal, dst_coff);
+  DBB_CHECK_LAUNCH("upsample_into");
+  return DBB_OK;
+}
+int upsample_bwd(const bf16* d_big, int big_ctotal, int big_coff, int n, int h, int w, int c, bf16* d_xs, int hs, int ws,
+                 int accumulate, cudaStream_t s) {
+  upsample_bwd_kernel<<<stream_grid((int64_t)n * hs * ws * (c / 8)), EW_THREADS, 0, s>>>(d_big, big_ctotal, big_coff, n, h, w, c, (float)hs / (float)h, (float)ws / (float)w, d_xs, hs, ws, accumulate);
+  DBB_CHECK_LAUNCH("upsample_bwd");
+  return DBB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv1 staging: NCHW float32 image -> zero-padded space-to-depth bf16 [n][hs+3][ws+3][16]
+// channel = (py*2+px)*3 + c for the 2x2 sub-pixel (py,px); channels 12..15 are zero
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS) image_to_s2d_kernel(const float* __restrict__ img, int n, int h, int w, int hs, int ws,
+                                                                  bf16* __restrict__ out) {
+  const int ph = hs + 3, pw = ws + 3;
+  const int64_t total = (int64_t)n * ph * pw;
+  for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
+    const int q = (int)(i % pw); int64_t t = i / pw; const int r = (int)(t % ph); const int b = (int)(t / ph);
+    const int si = r - 2, sj = q - 2;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+    if (si >= 0 && si < hs && sj >= 0 && sj < ws) {
+#pragma unroll
+      for (int py = 0; py < 2; ++py)
+#pragma unroll
+        for (int px = 0; px < 2; ++px) {
+          const int yy = 2 * si + py, xx = 2 * sj + px;
+          if (yy < h && xx < w) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[(py * 2 + px) * 3 + c] = __ldg(img + (((int64_t)b * 3 + c) * h + yy) * w + xx);
+          }
+        }
+    }
+    uint4 o0, o1;
+    o0.x = pack_bf16(v[0], v[1]); o0.y = pack_bf16(v[2], v[3]); o0.z = pack_bf16(v[4], v[5]); o0.w = pack_bf16(v[6], v[7]);
+    o1.x = pack_bf16(v[8], v[9]); o1.y = pack_bf16(v[10], v[11]); o1.z = pack_bf16(v[12], v[13]); o1.w = pack_bf16(v[14], v[15]);
+    uint4* dst = reinterpret_cast<uint4*>(out + i * 16);
+    dst[0] = o0; dst[1] = o1;
+  }
+}
+int image_to_s2d(const float* img, int n, int h, int w, bf16* s2d, cudaStream_t s) {
+  const int hs = (h + 1) / 2, ws = (w + 1) / 2;
+  image_to_s2d_kernel<<<stream_grid((int64_t)n * (hs + 3) * (ws + 3)), EW_THREADS, 0, s>>>(img, n, h, w, hs, ws, s2d);
+  DBB_CHECK_LAUNCH("image_to_s2d");
+  return DBB_OK;
+}
+__global__ void conv1_wgrad_unpack_kernel(const float* __restrict__ dw_s2d, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over 64*3*7*7
+  if (i >= 64 * 147) return;
+  const int kw = i % 7, kh = (i / 7) % 7, c = (i / 49) % 3, co = i / 147;
+  // kh = 2*kh2 + py - 1  ->  py = (kh+1)&1, kh2 = (kh+1)>>1
+  const int py = (kh + 1) & 1, kh2 = (kh + 1) >> 1, px = (kw + 1) & 1, kw2 = (kw + 1) >> 1;
+  const int nidx = kw2 * 16 + (py * 2 + px) * 3 + c;
+  dw[i] = dw_s2d[((int64_t)co * 64 + nidx) * 4 + kh2];
+}
+int conv1_wgrad_unpack(const float* dw_s2d, float* dw, cudaStream_t s) {
+  conv1_wgrad_unpack_kernel<<<(64 * 147 + 255) / 256, 256, 0, s>>>(dw_s2d, dw);
+  DBB_CHECK_LAUNCH("conv1_wgrad_unpack");
+  return DBB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bilinear resize, align_corners=True (src/models.py:43-46).  Identity when sizes match (multiples of 4).
+// ATen: src = dst * (in-1)/(out-1); lambda in float32
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bilin_coord(int d, int in, int out, int& i0, int& i1, float& l1) {
+  const float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+  const float src = scale * (float)d;
+  i0 = (int)src;
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+}
+__global__ void __launch_bounds__(256) bilinear_fwd_kernel(const float* __restrict__ x, int nc, int hi, int wi, float* __restrict__ y, int ho, int wo) {
+  const int64_t total = (int64_t)nc * ho * wo;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int ox = (int)(i % wo); int64_t t = i / wo; const int oy = (int)(t % ho); const int m = (int)(t / ho);
+    int y0, y1, x0, x1; float ly, lx;
+    bilin_coord(oy, hi, ho, y0, y1, ly);
+    bilin_coord(ox, wi, wo, x0, x1, lx);
+    const float* p = x + (int64_t)m * hi * wi;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    y[i] = hy * (hx * p[y0 * wi + x0] + lx * p[y0 * wi + x1]) + ly * (hx * p[y1 * wi + x0] + lx * p[y1 * wi + x1]);
+  }
+}
+__global__ void __launch_bounds__(256) bilinear_bwd_kernel(const float* __restrict__ dy, int nc, int hi, int wi, float* __restrict__ dx, int ho, int wo) {
+  const int64_t total = (int64_t)nc * ho * wo;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int ox = (int)(i % wo); int64_t t = i / wo; const int oy = (int)(t % ho); const int m = (int)(t / ho);
+    int y0, y1, x0, x1; float ly, lx;
+    bilin_coord(oy, hi, ho, y0, y1, ly);
+    bilin_coord(ox, wi, wo, x0, x1, lx);
+    float* p = dx + (int64_t)m * hi * wi;
+    const float hy = 1.f - ly, hx = 1.f - lx, g = dy[i];
+    atomicAdd(p + y0 * wi + x0, hy * hx * g); atomicAdd(p + y0 * wi + x1, hy * lx * g);
+    atomicAdd(p + y1 * wi + x0, ly * hx * g); atomicAdd(p + y1 * wi + x1, ly * lx * g);
+  }
+}
+int bilinear_fwd(const float* x, int nc, int hi, int wi, float* y, int ho, int wo, cudaStream_t s) {
+  bilinear_fwd_kernel<<<stream_grid((int64_t)nc * ho * wo), 256, 0, s>>>(x, nc, hi, wi, y, ho, wo);
+  DBB_CHECK_LAUNCH("bilinear_fwd");
+  return DBB_OK;
+}
+int bilinear_bwd(const float* dy, int nc, int hi, int wi, float* dx, int ho, int wo, cudaStream_t s) {
+  DBB_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)nc * hi * wi, s));
+  bilinear_bwd_kernel<<<stream_grid((int64_t)nc * ho * wo), 256, 0, s>>>(dy, nc, hi, wi, dx, ho, wo);
+  DBB_CHECK_LAUNCH("bilinear_bwd");
+  return DBB_OK;
+}
+
 }  // namespace dbb
 
 using namespace dbb;

@@ -1,0 +1,351 @@
+// head_tail.cu -- the memory-bound tail of DBHead, fused:  BN-apply + ReLU -> ConvTranspose2d(64->1, k2, s2) x 2
+// branches -> Sigmoid -> differentiable step B = 1/(1+exp(-k(P-T))) -> packed NCHW float32 store, and its backward.
+//
+// Replaces src/modules/segmentation_head.py:28-29 (BatchNorm2d, ReLU, ConvTranspose2d(64,1,2,2), Sigmoid of the
+// `binarize` branch), :72-76 (same for `thresh`), :39-44 and :106-108 (step_function + cat) of the reference.
+//
+// Input  zt  : raw output of the two ConvTranspose2d(64,64,2,2) layers, NHWC bf16 (N, H2, W2, 128);
+//              channels 0..63 = binarize branch, 64..127 = thresh branch (256 B per pixel).
+// Output out : (N, 3|2, 2*H2, 2*W2) float32 = [P, T, (B)].
+// HBM traffic per OUTPUT pixel: 64 B read (bf16) + 12 B written forward; the 64x320^2 ReLU activations and the
+// pre-sigmoid logits never touch memory.  A CTA owns a run of 64 input pixels of one row: phase 1 gives 16 lanes to
+// each pixel (one 16-byte vector per lane, warp-shuffle dot products), phase 2 re-maps threads to output columns so
+// the P/T/B rows leave as fully coalesced 512-byte stores.
+#include "common.cuh"
+#include "head_tail.h"
+
+namespace dbb {
+
+constexpr int HT_THREADS = 256;
+constexpr int HT_TILE = 64;   // input pixels per tile
+
+struct HtF8 { float v[8]; };
+__device__ __forceinline__ HtF8 ht_ld8(const bf16* p) {
+  const uint4 u = ldg_stream(reinterpret_cast<const uint4*>(p));
+  HtF8 r;
+  r.v[0] = bf16lo(u.x); r.v[1] = bf16hi(u.x); r.v[2] = bf16lo(u.y); r.v[3] = bf16hi(u.y);
+  r.v[4] = bf16lo(u.z); r.v[5] = bf16hi(u.z); r.v[6] = bf16lo(u.w); r.v[7] = bf16hi(u.w);
+  return r;
+}
+
+// per-lane constants: lane l = (branch = l>>3, channel group = l&7) owns channels ch0 = branch*64 + 8*(l&7) ..
+struct LaneConst {
+  float sc[8], sh[8], w[8][4];
+};
+__device__ __forceinline__ void load_lane_const(LaneConst& L, int l16, const float* __restrict__ stats4,
+                                                const float* __restrict__ w2b, const float* __restrict__ w2t) {
+  const int branch = l16 >> 3, cg = l16 & 7, ch0 = branch * 64 + cg * 8;
+  const float* w2 = branch ? w2t : w2b;   // ConvTranspose2d weight (64, 1, 2, 2): [c][a*2+b]
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    L.sc[j] = stats4[ch0 + j];
+    L.sh[j] = stats4[128 + ch0 + j];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) L.w[j][t] = w2[(cg * 8 + j) * 4 + t];
+  }
+}
+
+__device__ __forceinline__ void tile_coords(int64_t tile, int tiles_per_row, int h2, int& n, int& i, int& j0) {
+  const int tr = (int)(tile % tiles_per_row);
+  const int64_t row = tile / tiles_per_row;
+  i = (int)(row % h2); n = (int)(row / h2); j0 = tr * HT_TILE;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HT_THREADS)
+head_tail_fwd_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w2, const float* __restrict__ stats4,
+                     const float* __restrict__ w2b, const float* __restrict__ w2t, const float* __restrict__ b2b,
+                     const float* __restrict__ b2t, float k, int out_c, float* __restrict__ out) {
+  __shared__ float zs[2][4][HT_TILE];   // [branch][tap][pixel] pre-sigmoid logits
+  const int l16 = threadIdx.x & 15, pslot = threadIdx.x >> 4;   // 16 pixel slots per pass
+  LaneConst L;
+  load_lane_const(L, l16, stats4, w2b, w2t);
+  const float bias_b = b2b[0], bias_t = b2t[0];
+  const int tiles_per_row = (w2 + HT_TILE - 1) / HT_TILE;
+  const int64_t ntiles = (int64_t)n_img * h2 * tiles_per_row;
+  const int H = 2 * h2, W = 2 * w2;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int n, i, j0;
+    tile_coords(tile, tiles_per_row, h2, n, i, j0);
+    const bf16* zrow = zt + (((int64_t)n * h2 + i) * w2) * 128;
+    // ---- phase 1: BN + ReLU + 4 dot products per branch
+#pragma unroll
+    for (int pass = 0; pass < HT_TILE / 16; ++pass) {
+      const int px = pass * 16 + pslot;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      if (j0 + px < w2) {
+        const HtF8 z = ht_ld8(zrow + (int64_t)(j0 + px) * 128 + l16 * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float a = fmaxf(fmaf(z.v[j], L.sc[j], L.sh[j]), 0.f);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) acc[t] = fmaf(a, L.w[j][t], acc[t]);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], 1);
+        acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], 2);
+        acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], 4);
+      }
+      if ((l16 & 7) == 0) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) zs[l16 >> 3][t][px] = acc[t];
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: sigmoid, step, coalesced store.  thread -> (a = row parity, col = output column in the tile)
+    {
+      const int a = threadIdx.x >> 7, col = threadIdx.x & 127;
+      const int px = col >> 1, tap = a * 2 + (col & 1);
+      if (j0 + px < w2) {
+        const float zb = zs[0][tap][px] + bias_b, ztv = zs[1][tap][px] + bias_t;
+        const float P = 1.f / (1.f + expf(-zb));
+        const float T = 1.f / (1.f + expf(-ztv));
+        const int64_t plane = (int64_t)H * W;
+        float* o = out + ((int64_t)n * out_c) * plane + (int64_t)(2 * i + a) * W + 2 * j0 + col;
+        o[0] = P;
+        o[plane] = T;
+        if (out_c == 3) o[2 * plane] = 1.f / (1.f + expf(-k * (P - T)));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+//   dz_b[tap] = (dP + s) P (1-P),  dz_t[tap] = (dT - s) T (1-T),  s = dB k B^2 e,  e = exp(-k (P - T))
+//   da[c] = sum_tap dz[tap] w2[c][tap];  dy[c] = da[c] [a[c] > 0]   (gradient entering the BatchNorm of ConvT1)
+// pass "reduce": per-channel sums for BN backward (sum dy, sum dy*xhat), dW2[c][tap] = sum a[c] dz[tap], db2 = sum dz
+// pass "apply" : d_zt = gamma*invstd*(dy - mean(dy) - xhat*mean(dy*xhat))  -> NHWC bf16
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bwd_phase_a(float (&dzs)[2][4][HT_TILE], const float* __restrict__ out, const float* __restrict__ dout,
+                                            int n, int i, int j0, int w2, int H, int W, float k) {
+  const int a = threadIdx.x >> 7, col = threadIdx.x & 127;
+  const int px = col >> 1, tap = a * 2 + (col & 1);
+  float dzb = 0.f, dzt = 0.f;
+  if (j0 + px < w2) {
+    const int64_t plane = (int64_t)H * W;
+    const int64_t o = ((int64_t)n * 3) * plane + (int64_t)(2 * i + a) * W + 2 * j0 + col;
+    const float P = __ldg(out + o), T = __ldg(out + o + plane), B = __ldg(out + o + 2 * plane);
+    const float dP = __ldg(dout + o), dT = __ldg(dout + o + plane), dB = __ldg(dout + o + 2 * plane);
+    const float e = expf(-k * (P - T));
+    const float s = dB * k * B * B * e;
+    dzb = (dP + s) * P * (1.f - P);
+    dzt = (dT - s) * T * (1.f - T);
+  }
+  dzs[0][tap][px] = dzb;
+  dzs[1][tap][px] = dzt;
+}
+
+constexpr int HT_NACC = 6;   // per channel: dW2[4 taps], sum dy, sum dy*xhat
+
+__global__ void __launch_bounds__(HT_THREADS)
+head_tail_bwd_reduce_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w2, const float* __restrict__ stats4,
+                            const float* __restrict__ w2b, const float* __restrict__ w2t, const float* __restrict__ out,
+                            const float* __restrict__ dout, float k, float* __restrict__ partials /* [grid][128*6 + 2] */) {
+  __shared__ float dzs[2][4][HT_TILE];
+  __shared__ float red[HT_THREADS][9];   // padded rows
+  const int l16 = threadIdx.x & 15, pslot = threadIdx.x >> 4;
+  LaneConst L;
+  load_lane_const(L, l16, stats4, w2b, w2t);
+  float mean[8], inv[8];
+  {
+    const int ch0 = (l16 >> 3) * 64 + (l16 & 7) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { mean[j] = stats4[256 + ch0 + j]; inv[j] = stats4[384 + ch0 + j]; }
+  }
+  float accW[8][4], accS[8], accQ[8], accB = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { accS[j] = 0.f; accQ[j] = 0.f; for (int t = 0; t < 4; ++t) accW[j][t] = 0.f; }
+  const int tiles_per_row = (w2 + HT_TILE - 1) / HT_TILE;
+  const int64_t ntiles = (int64_t)n_img * h2 * tiles_per_row;
+  const int H = 2 * h2, W = 2 * w2;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int n, i, j0;
+    tile_coords(tile, tiles_per_row, h2, n, i, j0);
+    bwd_phase_a(dzs, out, dout, n, i, j0, w2, H, W, k);
+    __syncthreads();
+    const bf16* zrow = zt + (((int64_t)n * h2 + i) * w2) * 128;
+    const int br = l16 >> 3;
+#pragma unroll
+    for (int pass = 0; pass < HT_TILE / 16; ++pass) {
+      const int px = pass * 16 + pslot;
+      if (j0 + px < w2) {
+        const HtF8 z = ht_ld8(zrow + (int64_t)(j0 + px) * 128 + l16 * 8);
+        float dz[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) dz[t] = dzs[br][t][px];
+        if ((l16 & 7) == 0) accB += dz[0] + dz[1] + dz[2] + dz[3];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float a = fmaxf(fmaf(z.v[j], L.sc[j], L.sh[j]), 0.f);
+          float da = 0.f;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) { accW[j][t] = fmaf(a, dz[t], accW[j][t]); da = fmaf(dz[t], L.w[j][t], da); }
+          const float dy = a > 0.f ? da : 0.f;
+          accS[j] += dy;
+          accQ[j] = fmaf(dy, (z.v[j] - mean[j]) * inv[j], accQ[j]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- reduce over the 16 pixel slots that share a lane role; thread (l16, pslot)
+  float* my = partials + (size_t)blockIdx.x * (128 * HT_NACC + 2);
+  const int ch0 = (l16 >> 3) * 64 + (l16 & 7) * 8;
+#pragma unroll
+  for (int q = 0; q < HT_NACC; ++q) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = (q < 4) ? accW[j][q] : (q == 4 ? accS[j] : accQ[j]);
+    __syncthreads();
+    if (threadIdx.x < 128) {      // thread -> channel (l = t/8, j = t%8)
+      const int l = threadIdx.x >> 3, j = threadIdx.x & 7;
+      float s = 0.f;
+#pragma unroll
+      for (int ps = 0; ps < 16; ++ps) s += red[ps * 16 + l][j];
+      const int ch = (l >> 3) * 64 + (l & 7) * 8 + j;
+      my[ch * HT_NACC + q] = s;
+    }
+  }
+  (void)ch0;
+  __syncthreads();
+  red[threadIdx.x][0] = accB;
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float s = 0.f;
+    for (int ps = 0; ps < 16; ++ps) s += red[ps * 16 + threadIdx.x * 8][0];
+    my[128 * HT_NACC + threadIdx.x] = s;
+  }
+}
+
+__global__ void head_tail_bwd_finalize_kernel(const float* __restrict__ partials, int nblk, double count,
+                                              const float* __restrict__ gamma_b, const float* __restrict__ gamma_t,
+                                              const float* __restrict__ stats4, float* __restrict__ dgamma_b,
+                                              float* __restrict__ dbeta_b, float* __restrict__ dgamma_t,
+                                              float* __restrict__ dbeta_t, float* __restrict__ coef3,
+                                              float* __restrict__ dw2b, float* __restrict__ dw2t, float* __restrict__ db2b,
+                                              float* __restrict__ db2t) {
+  const int ch = threadIdx.x;   // 128 threads
+  const size_t stride = 128 * HT_NACC + 2;
+  double acc[HT_NACC];
+  for (int q = 0; q < HT_NACC; ++q) acc[q] = 0.0;
+  for (int b = 0; b < nblk; ++b)
+    for (int q = 0; q < HT_NACC; ++q) acc[q] += (double)partials[(size_t)b * stride + ch * HT_NACC + q];
+  const int br = ch >> 6, c = ch & 63;
+  float* dw2 = br ? dw2t : dw2b;
+  for (int t = 0; t < 4; ++t) dw2[c * 4 + t] = (float)acc[t];
+  (br ? dbeta_t : dbeta_b)[c] = (float)acc[4];
+  (br ? dgamma_t : dgamma_b)[c] = (float)acc[5];
+  const float g = (br ? gamma_t : gamma_b)[c];
+  coef3[ch] = g * stats4[384 + ch];
+  coef3[128 + ch] = (float)(acc[4] / count);
+  coef3[256 + ch] = (float)(acc[5] / count);
+  if (ch < 2) {
+    double s = 0.0;
+    for (int b = 0; b < nblk; ++b) s += (double)partials[(size_t)b * stride + 128 * HT_NACC + ch];
+    (ch ? db2t : db2b)[0] = (float)s;
+  }
+}
+
+__global__ void __launch_bounds__(HT_THREADS)
+head_tail_bwd_apply_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w2, const float* __restrict__ stats4,
+                           const float* __restrict__ coef3, const float* __restrict__ w2b, const float* __restrict__ w2t,
+                           const float* __restrict__ out, const float* __restrict__ dout, float k, bf16* __restrict__ d_zt) {
+  __shared__ float dzs[2][4][HT_TILE];
+  const int l16 = threadIdx.x & 15, pslot = threadIdx.x >> 4;
+  LaneConst L;
+  load_lane_const(L, l16, stats4, w2b, w2t);
+  float mean[8], inv[8], ca[8], c1[8], c2[8];
+  {
+    const int ch0 = (l16 >> 3) * 64 + (l16 & 7) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mean[j] = stats4[256 + ch0 + j]; inv[j] = stats4[384 + ch0 + j];
+      ca[j] = coef3[ch0 + j]; c1[j] = coef3[128 + ch0 + j]; c2[j] = coef3[256 + ch0 + j];
+    }
+  }
+  const int tiles_per_row = (w2 + HT_TILE - 1) / HT_TILE;
+  const int64_t ntiles = (int64_t)n_img * h2 * tiles_per_row;
+  const int H = 2 * h2, W = 2 * w2;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int n, i, j0;
+    tile_coords(tile, tiles_per_row, h2, n, i, j0);
+    bwd_phase_a(dzs, out, dout, n, i, j0, w2, H, W, k);
+    __syncthreads();
+    const int64_t rowoff = (((int64_t)n * h2 + i) * w2) * 128;
+    const int br = l16 >> 3;
+#pragma unroll
+    for (int pass = 0; pass < HT_TILE / 16; ++pass) {
+      const int px = pass * 16 + pslot;
+      if (j0 + px < w2) {
+        const int64_t off = rowoff + (int64_t)(j0 + px) * 128 + l16 * 8;
+        const HtF8 z = ht_ld8(zt + off);
+        float dz[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) dz[t] = dzs[br][t][px];
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float a = fmaf(z.v[j], L.sc[j], L.sh[j]);
+          float da = 0.f;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) da = fmaf(dz[t], L.w[j][t], da);
+          const float dy = a > 0.f ? da : 0.f;
+          o[j] = ca[j] * (dy - c1[j] - (z.v[j] - mean[j]) * inv[j] * c2[j]);
+        }
+        uint4 u;
+        u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+        stg_stream(reinterpret_cast<uint4*>(d_zt + off), u);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static int ht_grid(int n, int h2, int w2) {
+  const int64_t ntiles = (int64_t)n * h2 * ((w2 + HT_TILE - 1) / HT_TILE);
+  int64_t g = DBB_NUM_SMS * 8;
+  if (ntiles < g) g = ntiles;
+  return (int)(g < 1 ? 1 : g);
+}
+static int ht_reduce_grid(int n, int h2, int w2) {
+  const int64_t ntiles = (int64_t)n * h2 * ((w2 + HT_TILE - 1) / HT_TILE);
+  int64_t g = HT_MAX_BLOCKS;
+  if (ntiles < g) g = ntiles;
+  return (int)(g < 1 ? 1 : g);
+}
+
+int head_tail_fwd(const bf16* zt, int n, int h2, int w2, const float* stats4, const float* w2b, const float* w2t,
+                  const float* b2b, const float* b2t, float k, int out_c, float* out, cudaStream_t s) {
+  head_tail_fwd_kernel<<<ht_grid(n, h2, w2), HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, w2b, w2t, b2b, b2t, k, out_c, out);
+  DBB_CHECK_LAUNCH("head_tail_fwd");
+  return DBB_OK;
+}
+int head_tail_bwd_reduce(const bf16* zt, int n, int h2, int w2, const float* stats4, const float* w2b, const float* w2t,
+                         const float* out, const float* dout, float k, float* partials, int* nblk, cudaStream_t s) {
+  *nblk = ht_reduce_grid(n, h2, w2);
+  head_tail_bwd_reduce_kernel<<<*nblk, HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, w2b, w2t, out, dout, k, partials);
+  DBB_CHECK_LAUNCH("head_tail_bwd_reduce");
+  return DBB_OK;
+}
+int head_tail_bwd_finalize(const float* partials, int nblk, int64_t count, const float* gamma_b, const float* gamma_t,
+                           const float* stats4, float* dgamma_b, float* dbeta_b, float* dgamma_t, float* dbeta_t,
+                           float* coef3, float* dw2b, float* dw2t, float* db2b, float* db2t, cudaStream_t s) {
+  head_tail_bwd_finalize_kernel<<<1, 128, 0, s>>>(partials, nblk, (double)count, gamma_b, gamma_t, stats4, dgamma_b, dbeta_b,
+                                                  dgamma_t, dbeta_t, coef3, dw2b, dw2t, db2b, db2t);
+  DBB_CHECK_LAUNCH("head_tail_bwd_finalize");
+  return DBB_OK;
+}
+int head_tail_bwd_apply(const bf16* zt, int n, int h2, int w2, const float* stats4, const float* coef3, const float* w2b,
+                        const float* w2t, const float* out, const float* dout, float k, bf16* d_zt, cudaStream_t s) {
+  head_tail_bwd_apply_kernel<<<ht_grid(n, h2, w2), HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, coef3, w2b, w2t, out, dout, k, d_zt);
+  DBB_CHECK_LAUNCH("head_tail_bwd_apply");
+  return DBB_OK;
+}
+
+}  // namespace dbb

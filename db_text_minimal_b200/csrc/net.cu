@@ -1,0 +1,617 @@
+// net.cu -- whole-network executor: DBTextModel forward / backward as one fixed graph of sm_100a kernels.
+//
+// Replaces src/models.py:34-48 (DBTextModel.forward) together with src/modules/resnet.py:231-242 (ResNet-18),
+// src/modules/segmentation_body.py:64-87 (FPN) and src/modules/segmentation_head.py:35-45 (DBHead), and the
+// autograd backward PyTorch would derive for them.  One C call enqueues the whole pass on the caller's stream:
+// no per-op Python dispatch, no host synchronisation, CUDA-graph capturable.
+//
+// Data layout in HBM: module boundary tensors keep the reference's layout (x NCHW float32, out NCHW float32,
+// parameters float32 in state_dict shapes); every internal activation is NHWC bf16 so that a pixel's channels are one
+// contiguous TMA row.  All buffers live in a caller-owned workspace (bump-allocated at dbb_net_create).
+// BatchNorm (training): raw conv output z (bf16) -> bn_stats -> finalize (scale/shift, running stats) -> bn_apply
+// (+residual)(+ReLU) -> activation; backward mirrors it (reduce, finalize, apply).
+#include "common.cuh"
+#include "conv_ops.h"
+#include "elementwise.h"
+#include "head_tail.h"
+#include <string>
+#include <vector>
+#include <map>
+
+namespace dbb {
+
+struct PInfo { std::string name; int numel; };
+static std::vector<PInfo> g_params, g_buffers;
+static std::map<std::string, int> g_pidx, g_bidx;
+
+static void add_p(const std::string& n, int numel) { g_pidx[n] = (int)g_params.size(); g_params.push_back({n, numel}); }
+static void add_bn(const std::string& n, int c) {
+  add_p(n + ".weight", c); add_p(n + ".bias", c);
+  g_bidx[n + ".running_mean"] = (int)g_buffers.size(); g_buffers.push_back({n + ".running_mean", c});
+  g_bidx[n + ".running_var"] = (int)g_buffers.size(); g_buffers.push_back({n + ".running_var", c});
+}
+static void build_tables() {
+  if (!g_params.empty()) return;
+  add_p("backbone.conv1.weight", 64 * 3 * 49);
+  add_bn("backbone.bn1", 64);
+  int inpl = 64;
+  const int planes[4] = {64, 128, 256, 512};
+  for (int li = 1; li <= 4; ++li)
+    for (int bi = 0; bi < 2; ++bi) {
+      const std::string pre = "backbone.layer" + std::to_string(li) + "." + std::to_string(bi);
+      const int pl = planes[li - 1];
+      const bool ds = (bi == 0 && li > 1);
+      add_p(pre + ".conv1.weight", pl * inpl * 9); add_bn(pre + ".bn1", pl);
+      add_p(pre + ".conv2.weight", pl * pl * 9); add_bn(pre + ".bn2", pl);
+      if (ds) { add_p(pre + ".downsample.0.weight", pl * inpl); add_bn(pre + ".downsample.1", pl); }
+      inpl = pl;
+    }
+  // present in the state dict, never used in forward: no gradient
+  add_p("backbone.fc.weight", 1000 * 512); add_p("backbone.fc.bias", 1000);
+  add_p("backbone.smooth.weight", 256 * 2048); add_p("backbone.smooth.bias", 256);
+  const char* cn[4] = {"c2", "c3", "c4", "c5"};
+  for (int i = 0; i < 4; ++i) {
+    const std::string pre = std::string("segmentation_body.reduce_conv_") + cn[i];
+    add_p(pre + ".conv.weight", 64 * planes[i]); add_p(pre + ".conv.bias", 64); add_bn(pre + ".bn", 64);
+  }
+  const char* pn[3] = {"p4", "p3", "p2"};
+  for (int i = 0; i < 3; ++i) {
+    const std::string pre = std::string("segmentation_body.smooth_") + pn[i];
+    add_p(pre + ".conv.weight", 64 * 64 * 9); add_p(pre + ".conv.bias", 64); add_bn(pre + ".bn", 64);
+  }
+  add_p("segmentation_body.conv.0.weight", 256 * 256 * 9); add_p("segmentation_body.conv.0.bias", 256);
+  add_bn("segmentation_body.conv.1", 256);
+  for (int br = 0; br < 2; ++br) {
+    const std::string pre = std::string("segmentation_head.") + (br ? "thresh" : "binarize");
+    add_p(pre + ".0.weight", 64 * 256 * 9);
+    if (br == 0) add_p(pre + ".0.bias", 64);      // thresh.0 has no bias (segmentation_head.py:64-68)
+    add_bn(pre + ".1", 64);
+    add_p(pre + ".3.weight", 64 * 64 * 4); add_p(pre + ".3.bias", 64);
+    add_bn(pre + ".4", 64);
+    add_p(pre + ".6.weight", 64 * 4); add_p(pre + ".6.bias", 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct Buf { size_t off = 0; size_t bytes = 0; };
+
+struct ConvBN {          // Conv2d (+bias) -> BatchNorm2d (-> ReLU handled by the caller's bn_apply flags)
+  ConvGeom g{};
+  int w = -1, b = -1, gamma = -1, beta = -1, rm = -1, rv = -1;   // param / buffer indices
+  Buf wp, wpt;           // packed bf16 weights: fprop, dgrad
+  Buf z, stats, coef, dz;
+  int64_t P() const { return (int64_t)g.n * g.out_h() * g.out_w(); }
+};
+
+struct Block {
+  ConvBN c1, c2, ds;
+  bool has_ds = false;
+  Buf a1, rd, out, d_a1, d_out;   // d_out: gradient w.r.t. the block output (allocated by the consumer side)
+  int h_in, w_in, c_in;
+};
+
+}  // namespace dbb
+
+using namespace dbb;
+
+struct DbbNet {
+  int n, h, w, training;
+  int h1, w1, h2, w2, hh[4], ww[4];      // conv1 out, pool out (= c2), c2..c5 extents
+  int ho, wo;                            // head output extent (4*h2, 4*w2)
+  size_t ws_bytes = 0;
+  uint64_t flops_fwd = 0;
+  // stem
+  Buf s2d, wp_conv1, z0, stats0, coef0, a0, x1, argmax, d_x1, d_a0, d_z0, dw_s2d;
+  Block blocks[8];
+  // FPN
+  ConvBN lat[4];          // reduce_conv_c2..c5
+  ConvBN smooth[3];       // smooth_p4, p3, p2   (index 0 -> p4)
+  Buf l_act[4];           // lateral activations (l2, l3, l4, p5)
+  Buf s_sum[3];           // s4, s3, s2 (inputs of the smooth convs)
+  Buf p_act[2];           // p4, p3 (p2 lives in cat[..., 0:64])
+  Buf cat, d_cat;
+  ConvBN fconv;           // segmentation_body.conv
+  Buf af, d_af;
+  Buf d_p[3];             // d_p5, d_p4, d_p3
+  Buf d_s[3];             // d_s4, d_s3, d_s2
+  Buf d_c[4];             // gradients w.r.t. c2..c5
+  // head
+  ConvGeom hconv_g{}, tconv_g{};
+  Buf wp_h, wpt_h, bias_h, zh, stats_h, coef_h, ah, d_ah, d_zh, dw_h, dbias_h;
+  Buf wp_t[2], wpt_t[2], zt, stats_t, coef_t, d_zt, dbias_t;
+  Buf head_out;           // fp32 (N, C, ho, wo) when a final bilinear resize is needed
+  Buf d_head_out;
+  Buf partials;           // shared reduction scratch
+  int out_c;
+  // bump allocator
+  size_t cur = 0;
+  Buf alloc(size_t bytes) {
+    Buf b; b.off = cur; b.bytes = bytes;
+    cur += (bytes + 1023) / 1024 * 1024;   // 1 KB alignment (TMA needs 16 B; swizzled smem is unaffected)
+    return b;
+  }
+};
+
+static int P(const char* name) {
+  auto it = g_pidx.find(name);
+  return it == g_pidx.end() ? -1 : it->second;
+}
+static int P(const std::string& name) { return P(name.c_str()); }
+static int B(const std::string& name) {
+  auto it = g_bidx.find(name);
+  return it == g_bidx.end() ? -1 : it->second;
+}
+
+static void setup_convbn(DbbNet* net, ConvBN& L, const std::string& conv, const std::string& bn, int n, int h, int w, int cin,
+                         int cout, int ks, int stride, int pad, bool has_bias, bool need_dgrad) {
+  L.g = ConvGeom{n, h, w, cin, cout, ks, stride, pad};
+  L.w = P(conv + ".weight");
+  L.b = has_bias ? P(conv + ".bias") : -1;
+  L.gamma = P(bn + ".weight"); L.beta = P(bn + ".bias");
+  L.rm = B(bn + ".running_mean"); L.rv = B(bn + ".running_var");
+  const size_t wbytes = (size_t)cin * cout * ks * ks * sizeof(bf16);
+  L.wp = net->alloc(wbytes);
+  if (net->training && need_dgrad) L.wpt = net->alloc(wbytes);
+  L.z = net->alloc((size_t)L.P() * cout * sizeof(bf16));
+  L.stats = net->alloc(4 * cout * sizeof(float));
+  if (net->training) {
+    L.coef = net->alloc(3 * cout * sizeof(float));
+    L.dz = net->alloc((size_t)L.P() * cout * sizeof(bf16));
+  }
+  net->flops_fwd += 2ull * (uint64_t)L.P() * cout * cin * ks * ks;
+}
+
+extern "C" DbbNet* dbb_net_create(int64_t n, int64_t h, int64_t w, int training) {
+  build_tables();
+  if (n <= 0 || h < 32 || w < 32) { set_error(DBB_EINVAL, "net_create: need n >= 1 and h, w >= 32"); return nullptr; }
+  DbbNet* net = new DbbNet();
+  net->n = (int)n; net->h = (int)h; net->w = (int)w; net->training = training ? 1 : 0;
+  net->out_c = training ? 3 : 2;
+  const int N = (int)n;
+  const bool T = net->training;
+  auto act_bytes = [&](int hh, int ww, int c) { return (size_t)N * hh * ww * c * sizeof(bf16); };
+  // ---- stem
+  net->h1 = ((int)h + 1) / 2; net->w1 = ((int)w + 1) / 2;                 // conv 7x7/2 pad 3
+  net->h2 = (net->h1 + 2 - 3) / 2 + 1; net->w2 = (net->w1 + 2 - 3) / 2 + 1;   // maxpool 3/2 pad 1
+  net->s2d = net->alloc((size_t)N * (net->h1 + 3) * (net->w1 + 3) * 16 * sizeof(bf16));
+  net->wp_conv1 = net->alloc(64 * 256 * sizeof(bf16));
+  net->z0 = net->alloc(act_bytes(net->h1, net->w1, 64));
+  net->stats0 = net->alloc(4 * 64 * sizeof(float));
+  net->a0 = net->alloc(act_bytes(net->h1, net->w1, 64));
+  net->x1 = net->alloc(act_bytes(net->h2, net->w2, 64));
+  net->flops_fwd += 2ull * N * net->h1 * net->w1 * 64 * 147;
+  if (T) {
+    net->coef0 = net->alloc(3 * 64 * sizeof(float));
+    net->argmax = net->alloc((size_t)N * net->h2 * net->w2 * 64);
+    net->d_x1 = net->alloc(act_bytes(net->h2, net->w2, 64));
+    net->d_a0 = net->alloc(act_bytes(net->h1, net->w1, 64));
+    net->d_z0 = net->alloc(act_bytes(net->h1, net->w1, 64));
+    net->dw_s2d = net->alloc(64 * 64 * 4 * sizeof(float));
+  }
+  // ---- residual stages
+  int hin = net->h2, win = net->w2, cin = 64;
+  const int planes[4] = {64, 128, 256, 512};
+  for (int li = 0; li < 4; ++li)
+    for (int bi = 0; bi < 2; ++bi) {
+      Block& bk = net->blocks[li * 2 + bi];
+      const std::string pre = "backbone.layer" + std::to_string(li + 1) + "." + std::to_string(bi);
+      const int pl = planes[li];
+      const int stride = (li > 0 && bi == 0) ? 2 : 1;
+      bk.h_in = hin; bk.w_in = win; bk.c_in = cin;
+      bk.has_ds = (stride != 1 || cin != pl);
+      // the very first block's input (pool output) needs a data gradient too (it flows on into conv1's BN)
+      setup_convbn(net, bk.c1, pre + ".conv1", pre + ".bn1", N, hin, win, cin, pl, 3, stride, 1, false, true);
+      const int ho = bk.c1.g.out_h(), wo = bk.c1.g.out_w();
+      setup_convbn(net, bk.c2, pre + ".conv2", pre + ".bn2", N, ho, wo, pl, pl, 3, 1, 1, false, true);
+      if (bk.has_ds) setup_convbn(net, bk.ds, pre + ".downsample.0", pre + ".downsample.1", N, hin, win, cin, pl, 1, stride, 0, false, true);
+      bk.a1 = net->alloc(act_bytes(ho, wo, pl));
+      if (bk.has_ds) bk.rd = net->alloc(act_bytes(ho, wo, pl));
+      bk.out = net->alloc(act_bytes(ho, wo, pl));
+      if (T) { bk.d_a1 = net->alloc(act_bytes(ho, wo, pl)); bk.d_out = net->alloc(act_bytes(ho, wo, pl)); }
+      hin = ho; win = wo; cin = pl;
+      if (bi == 1) { net->hh[li] = ho; net->ww[li] = wo; }
+    }
+  // ---- FPN
+  const char* cn[4] = {"c2", "c3", "c4", "c5"};
+  for (int i = 0; i < 4; ++i) {
+    const std::string pre = std::string("segmentation_body.reduce_conv_") + cn[i];
+    setup_convbn(net, net->lat[i], pre + ".conv", pre + ".bn", N, net->hh[i], net->ww[i], planes[i], 64, 1, 1, 0, true, true);
+    net->l_act[i] = net->alloc(act_bytes(net->hh[i], net->ww[i], 64));
+  }
+  const char* pn[3] = {"p4", "p3", "p2"};
+  for (int i = 0; i < 3; ++i) {
+    const int lvl = 2 - i;   // p4 -> level index 2 (c4), p3 -> 1, p2 -> 0
+    const std::string pre = std::string("segmentation_body.smooth_") + pn[i];
+    setup_convbn(net, net->smooth[i], pre + ".conv", pre + ".bn", N, net->hh[lvl], net->ww[lvl], 64, 64, 3, 1, 1, true, true);
+    net->s_sum[i] = net->alloc(act_bytes(net->hh[lvl], net->ww[lvl], 64));
+    if (i < 2) net->p_act[i] = net->alloc(act_bytes(net->hh[lvl], net->ww[lvl], 64));
+    if (T) net->d_s[i] = net->alloc(act_bytes(net->hh[lvl], net->ww[lvl], 64));
+  }
+  const int hf = net->hh[0], wf = net->ww[0];
+  net->cat = net->alloc(act_bytes(hf, wf, 256));
+  setup_convbn(net, net->fconv, "segmentation_body.conv.0", "segmentation_body.conv.1", N, hf, wf, 256, 256, 3, 1, 1, true, true);
+  net->af = net->alloc(act_bytes(hf, wf, 256));
+  if (T) {
+    net->d_cat = net->alloc(act_bytes(hf, wf, 256));
+    net->d_af = net->alloc(act_bytes(hf, wf, 256));
+    net->d_p[0] = net->alloc(act_bytes(net->hh[3], net->ww[3], 64));   // d_p5
+    net->d_p[1] = net->alloc(act_bytes(net->hh[2], net->ww[2], 64));   // d_p4
+    net->d_p[2] = net->alloc(act_bytes(net->hh[1], net->ww[1], 64));   // d_p3
+    for (int i = 0; i < 4; ++i) net->d_c[i] = net->blocks[i * 2 + 1].d_out;   // gradient of c2..c5 = d_out of the stage's last block
+  }
+  // ---- head: the two 3x3 convs share their input -> one 256->128 GEMM; the two ConvT(64,64,2,2) write one 128-wide tensor
+  net->hconv_g = ConvGeom{N, hf, wf, 256, 128, 3, 1, 1};
+  net->tconv_g = ConvGeom{N, hf, wf, 64, 64, 2, 2, 0};
+  net->wp_h = net->alloc(128 * 256 * 9 * sizeof(bf16));
+  net->bias_h = net->alloc(128 * sizeof(float));
+  net->zh = net->alloc(act_bytes(hf, wf, 128));
+  net->stats_h = net->alloc(4 * 128 * sizeof(float));
+  net->ah = net->alloc(act_bytes(hf, wf, 128));
+  for (int br = 0; br < 2; ++br) net->wp_t[br] = net->alloc(4 * 64 * 64 * sizeof(bf16));
+  net->zt = net->alloc(act_bytes(2 * hf, 2 * wf, 128));
+  net->stats_t = net->alloc(4 * 128 * sizeof(float));
+  net->flops_fwd += 2ull * N * hf * wf * 128 * 256 * 9 + 2ull * 2 * N * hf * wf * 64 * 256 + 2ull * 2 * N * 4 * hf * wf * 64 * 4;
+  net->ho = 4 * hf; net->wo = 4 * wf;
+  if (net->ho != net->h || net->wo != net->w) net->head_out = net->alloc((size_t)N * net->out_c * net->ho * net->wo * sizeof(float));
+  if (T) {
+    net->wpt_h = net->alloc(128 * 256 * 9 * sizeof(bf16));
+    net->coef_h = net->alloc(3 * 128 * sizeof(float));
+    net->d_ah = net->alloc(act_bytes(hf, wf, 128));
+    net->d_zh = net->alloc(act_bytes(hf, wf, 128));
+    net->dw_h = net->alloc(128 * 256 * 9 * sizeof(float));
+    net->dbias_h = net->alloc(128 * sizeof(float));
+    for (int br = 0; br < 2; ++br) net->wpt_t[br] = net->alloc(4 * 64 * 64 * sizeof(bf16));
+    net->coef_t = net->alloc(3 * 128 * sizeof(float));
+    net->d_zt = net->alloc(act_bytes(2 * hf, 2 * wf, 128));
+    net->dbias_t = net->alloc(128 * sizeof(float));
+    if (net->head_out.bytes) net->d_head_out = net->alloc((size_t)N * 3 * net->ho * net->wo * sizeof(float));
+  }
+  size_t pf = bn_partials_floats(512);
+  if (head_tail_partials_floats() > pf) pf = head_tail_partials_floats();
+  net->partials = net->alloc(pf * sizeof(float));
+  net->ws_bytes = net->cur;
+  return net;
+}
+
+extern "C" void dbb_net_destroy(DbbNet* net) { delete net; }
+extern "C" size_t dbb_net_workspace_bytes(const DbbNet* net) { return net ? net->ws_bytes : 0; }
+extern "C" int64_t dbb_net_out_channels(const DbbNet* net) { return net ? net->out_c : 0; }
+extern "C" uint64_t dbb_net_flops_fwd(const DbbNet* net) { return net ? net->flops_fwd : 0; }
+extern "C" int dbb_net_num_params(void) { build_tables(); return (int)g_params.size(); }
+extern "C" const char* dbb_net_param_name(int i) { build_tables(); return (i >= 0 && i < (int)g_params.size()) ? g_params[i].name.c_str() : nullptr; }
+extern "C" int dbb_net_param_numel(int i) { build_tables(); return (i >= 0 && i < (int)g_params.size()) ? g_params[i].numel : -1; }
+extern "C" int dbb_net_num_buffers(void) { build_tables(); return (int)g_buffers.size(); }
+extern "C" const char* dbb_net_buffer_name(int i) { build_tables(); return (i >= 0 && i < (int)g_buffers.size()) ? g_buffers[i].name.c_str() : nullptr; }
+extern "C" int dbb_net_buffer_numel(int i) { build_tables(); return (i >= 0 && i < (int)g_buffers.size()) ? g_buffers[i].numel : -1; }
+extern "C" int dbb_net_num_segments(void) { return 3; }
+
+namespace {
+
+constexpr float BN_EPS = 1e-5f, BN_MOM = 0.1f, STEP_K = 50.f;
+
+struct Ctx {
+  DbbNet* net;
+  char* base;
+  const float* const* params;
+  float* const* buffers;
+  float* const* grads;
+  cudaStream_t s;
+  template <typename T = bf16> T* p(const Buf& b) const { return reinterpret_cast<T*>(base + b.off); }
+  const float* par(int i) const { return i >= 0 ? params[i] : nullptr; }
+  float* buf(int i) const { return (i >= 0 && buffers) ? buffers[i] : nullptr; }
+  float* grad(int i) const { return (i >= 0 && grads) ? grads[i] : nullptr; }
+  float* partials() const { return p<float>(net->partials); }
+};
+
+#define RC(call) do { int rc__ = (call); if (rc__) return rc__; } while (0)
+
+// BatchNorm statistics of a raw conv output (training) or running statistics (eval) -> stats4
+int bn_prepare(const Ctx& c, const bf16* z, int64_t Pn, int ch, int gamma, int beta, int rm, int rv, float* stats4, int coff = 0,
+               int cn = -1, bool do_stats = true) {
+  if (cn < 0) cn = ch;
+  if (c.net->training) {
+    static thread_local int nblk = 0;
+    if (do_stats) RC(bn_stats(z, Pn, ch, c.partials(), &nblk, c.s));
+    RC(bn_finalize_train(c.partials(), nblk, ch, coff, cn, Pn, c.par(gamma), c.par(beta), c.buf(rm), c.buf(rv), BN_MOM, BN_EPS, stats4, c.s));
+  } else {
+    RC(bn_finalize_eval(ch, coff, cn, c.par(gamma), c.par(beta), c.buf(rm), c.buf(rv), BN_EPS, stats4, c.s));
+  }
+  return 0;
+}
+
+int convbn_fwd(const Ctx& c, ConvBN& L, const bf16* x, int x_ctotal, int x_coff) {
+  RC(pack_weights(0, c.par(L.w), c.p(L.wp), L.g.cout, L.g.cin, L.g.ks, L.g.ks, c.s));
+  RC(conv_fprop(L.g, x, x_ctotal, x_coff, c.p(L.wp), c.par(L.b), c.p(L.z), L.g.cout, 0, c.s));
+  RC(bn_prepare(c, c.p(L.z), L.P(), L.g.cout, L.gamma, L.beta, L.rm, L.rv, c.p<float>(L.stats)));
+  return 0;
+}
+
+// backward through BN (+ReLU mask) and the conv: dout -> dz -> (dW, dbias, dx)
+int convbn_bwd(const Ctx& c, ConvBN& L, const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask, int mask_ctotal,
+               int mask_coff, const bf16* x, int x_ctotal, int x_coff, bf16* dx, int dx_accumulate, bf16* dsum) {
+  int nblk = 0;
+  const int64_t Pn = L.P();
+  const int ch = L.g.cout;
+  RC(bn_bwd_reduce(dout, dout_ctotal, dout_coff, mask, mask_ctotal, mask_coff, c.p(L.z), Pn, ch, c.p<float>(L.stats), c.partials(), &nblk, c.s));
+  RC(bn_bwd_finalize(c.partials(), nblk, ch, 0, ch, Pn, c.par(L.gamma), c.p<float>(L.stats), c.grad(L.gamma), c.grad(L.beta), c.p<float>(L.coef), c.s));
+  RC(bn_bwd_apply(dout, dout_ctotal, dout_coff, mask, mask_ctotal, mask_coff, c.p(L.z), Pn, ch, c.p<float>(L.stats), c.p<float>(L.coef), c.p(L.dz), dsum, c.s));
+  RC(conv_wgrad(L.g, x, x_ctotal, x_coff, c.p(L.dz), ch, 0, c.grad(L.w), c.s));
+  if (L.b >= 0) RC(bias_grad(c.p(L.dz), Pn, ch, c.partials(), c.grad(L.b), c.s));
+  if (dx) {
+    RC(pack_weights(1, c.par(L.w), c.p(L.wpt), L.g.cout, L.g.cin, L.g.ks, L.g.ks, c.s));
+    RC(conv_dgrad(L.g, c.p(L.dz), c.p(L.wpt), dx, c.s, dx_accumulate));
+  }
+  return 0;
+}
+
+int block_fwd(const Ctx& c, Block& bk, const bf16* x) {
+  RC(convbn_fwd(c, bk.c1, x, bk.c_in, 0));
+  RC(bn_apply(c.p(bk.c1.z), bk.c1.P(), bk.c1.g.cout, c.p<float>(bk.c1.stats), nullptr, 1, c.p(bk.a1), bk.c1.g.cout, 0, c.s));
+  RC(convbn_fwd(c, bk.c2, c.p(bk.a1), bk.c1.g.cout, 0));
+  const bf16* res = x;
+  if (bk.has_ds) {
+    RC(convbn_fwd(c, bk.ds, x, bk.c_in, 0));
+    RC(bn_apply(c.p(bk.ds.z), bk.ds.P(), bk.ds.g.cout, c.p<float>(bk.ds.stats), nullptr, 0, c.p(bk.rd), bk.ds.g.cout, 0, c.s));
+    res = c.p(bk.rd);
+  }
+  RC(bn_apply(c.p(bk.c2.z), bk.c2.P(), bk.c2.g.cout, c.p<float>(bk.c2.stats), res, 1, c.p(bk.out), bk.c2.g.cout, 0, c.s));
+  return 0;
+}
+
+// dx: gradient buffer of the block input; dx_has_content: it already holds another consumer's contribution
+int block_bwd(const Ctx& c, Block& bk, const bf16* x, bf16* dx, int dx_has_content) {
+  const int pl = bk.c2.g.cout;
+  const bf16* dout = c.p(bk.d_out);
+  const bf16* out = c.p(bk.out);
+  // bn2 + conv2 ; identity skip: the ReLU-masked gradient goes straight to dx
+  bf16* dsum = nullptr;
+  if (!bk.has_ds) {
+    if (dx_has_content) return set_error(DBB_EUNSUPPORTED, "block_bwd: identity-skip block with pre-filled dx");
+    dsum = dx;
+  }
+  RC(convbn_bwd(c, bk.c2, dout, pl, 0, out, pl, 0, c.p(bk.a1), pl, 0, c.p(bk.d_a1), 0, dsum));
+  int acc = (dsum != nullptr) || dx_has_content;
+  if (bk.has_ds) {
+    RC(convbn_bwd(c, bk.ds, dout, pl, 0, out, pl, 0, x, bk.c_in, 0, dx, acc, nullptr));
+    acc = 1;
+  }
+  RC(convbn_bwd(c, bk.c1, c.p(bk.d_a1), pl, 0, c.p(bk.a1), pl, 0, x, bk.c_in, 0, dx, acc, nullptr));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* params, float* const* buffers, float* out,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  if (!net || !x || !params || !out || !workspace) return set_error(DBB_EINVAL, "net_forward: null pointer");
+  if (workspace_bytes < net->ws_bytes) return set_error(DBB_EWORKSPACE, "net_forward: workspace too small");
+  if (!aligned16(x) || !aligned16(out) || (reinterpret_cast<uintptr_t>(workspace) & 1023)) return set_error(DBB_EALIGN, "net_forward: x/out need 16 B, workspace 1024 B alignment");
+  Ctx c{net, (char*)workspace, params, buffers, nullptr, (cudaStream_t)stream};
+  const int N = net->n;
+  // ---- stem: conv 7x7/2 (space-to-depth form) -> BN -> ReLU -> maxpool
+  RC(image_to_s2d(x, N, net->h, net->w, c.p(net->s2d), c.s));
+  RC(pack_weights(4, c.par(P("backbone.conv1.weight")), c.p(net->wp_conv1), 64, 3, 7, 7, c.s));
+  RC(conv1_fprop(N, net->h, net->w, c.p(net->s2d), c.p(net->wp_conv1), c.p(net->z0), c.s));
+  const int64_t P0 = (int64_t)N * net->h1 * net->w1;
+  RC(bn_prepare(c, c.p(net->z0), P0, 64, P("backbone.bn1.weight"), P("backbone.bn1.bias"), B("backbone.bn1.running_mean"),
+                B("backbone.bn1.running_var"), c.p<float>(net->stats0)));
+  RC(bn_apply(c.p(net->z0), P0, 64, c.p<float>(net->stats0), nullptr, 1, c.p(net->a0), 64, 0, c.s));
+  RC(maxpool_fwd(c.p(net->a0), N, net->h1, net->w1, 64, c.p(net->x1), net->training ? c.p<uint8_t>(net->argmax) : nullptr, c.s));
+  // ---- residual stages
+  const bf16* cur = c.p(net->x1);
+  for (int i = 0; i < 8; ++i) { RC(block_fwd(c, net->blocks[i], cur)); cur = c.p(net->blocks[i].out); }
+  const bf16* feat[4];
+  for (int i = 0; i < 4; ++i) feat[i] = c.p(net->blocks[i * 2 + 1].out);
+  const int planes[4] = {64, 128, 256, 512};
+  // ---- FPN top-down (segmentation_body.py:64-77)
+  for (int i = 3; i >= 0; --i) {
+    RC(convbn_fwd(c, net->lat[i], feat[i], planes[i], 0));
+    RC(bn_apply(c.p(net->lat[i].z), net->lat[i].P(), 64, c.p<float>(net->lat[i].stats), nullptr, 1, c.p(net->l_act[i]), 64, 0, c.s));
+  }
+  const int hf = net->hh[0], wf = net->ww[0];
+  const bf16* upper = c.p(net->l_act[3]);   // p5
+  int uh = net->hh[3], uw = net->ww[3];
+  for (int i = 0; i < 3; ++i) {             // p4, p3, p2
+    const int lvl = 2 - i;
+    RC(upsample_add_fwd(upper, uh, uw, c.p(net->l_act[lvl]), N, net->hh[lvl], net->ww[lvl], 64, c.p(net->s_sum[i]), c.s));
+    RC(convbn_fwd(c, net->smooth[i], c.p(net->s_sum[i]), 64, 0));
+    bf16* dst = (i < 2) ? c.p(net->p_act[i]) : c.p(net->cat);
+    RC(bn_apply(c.p(net->smooth[i].z), net->smooth[i].P(), 64, c.p<float>(net->smooth[i].stats), nullptr, 1, dst, i < 2 ? 64 : 256, 0, c.s));
+    upper = dst; uh = net->hh[lvl]; uw = net->ww[lvl];
+    if (i == 2) break;
+  }
+  // concat [p2, up(p3), up(p4), up(p5)] (segmentation_body.py:82-87); p2 is already in channels 0..63
+  RC(upsample_into(c.p(net->p_act[1]), net->hh[1], net->ww[1], N, hf, wf, 64, c.p(net->cat), 256, 64, c.s));
+  RC(upsample_into(c.p(net->p_act[0]), net->hh[2], net->ww[2], N, hf, wf, 64, c.p(net->cat), 256, 128, c.s));
+  RC(upsample_into(c.p(net->l_act[3]), net->hh[3], net->ww[3], N, hf, wf, 64, c.p(net->cat), 256, 192, c.s));
+  RC(convbn_fwd(c, net->fconv, c.p(net->cat), 256, 0));
+  RC(bn_apply(c.p(net->fconv.z), net->fconv.P(), 256, c.p<float>(net->fconv.stats), nullptr, 1, c.p(net->af), 256, 0, c.s));
+  // ---- head (segmentation_head.py:35-45)
+  const int ib = P("segmentation_head.binarize.0.weight"), it = P("segmentation_head.thresh.0.weight");
+  RC(pack_weights(0, c.par(ib), c.p(net->wp_h), 64, 256, 3, 3, c.s));
+  RC(pack_weights(0, c.par(it), c.p(net->wp_h) + (size_t)64 * 256 * 9, 64, 256, 3, 3, c.s));
+  DBB_CUDA(cudaMemsetAsync(c.p<float>(net->bias_h), 0, 128 * sizeof(float), c.s));
+  DBB_CUDA(cudaMemcpyAsync(c.p<float>(net->bias_h), c.par(P("segmentation_head.binarize.0.bias")), 64 * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
+  RC(conv_fprop(net->hconv_g, c.p(net->af), 256, 0, c.p(net->wp_h), c.p<float>(net->bias_h), c.p(net->zh), 128, 0, c.s));
+  const int64_t Ph = (int64_t)N * hf * wf;
+  for (int br = 0; br < 2; ++br) {
+    const std::string pre = std::string("segmentation_head.") + (br ? "thresh" : "binarize");
+    RC(bn_prepare(c, c.p(net->zh), Ph, 128, P(pre + ".1.weight"), P(pre + ".1.bias"), B(pre + ".1.running_mean"), B(pre + ".1.running_var"),
+                  c.p<float>(net->stats_h), br * 64, 64, br == 0));
+  }
+  RC(bn_apply(c.p(net->zh), Ph, 128, c.p<float>(net->stats_h), nullptr, 1, c.p(net->ah), 128, 0, c.s));
+  for (int br = 0; br < 2; ++br) {
+    const std::string pre = std::string("segmentation_head.") + (br ? "thresh" : "binarize");
+    RC(pack_weights(2, c.par(P(pre + ".3.weight")), c.p(net->wp_t[br]), 64, 64, 2, 2, c.s));
+    RC(convt_fprop(net->tconv_g, c.p(net->ah), 128, br * 64, c.p(net->wp_t[br]), c.par(P(pre + ".3.bias")), c.p(net->zt), 128, br * 64, c.s));
+  }
+  const int64_t Pt = Ph * 4;
+  for (int br = 0; br < 2; ++br) {
+    const std::string pre = std::string("segmentation_head.") + (br ? "thresh" : "binarize");
+    RC(bn_prepare(c, c.p(net->zt), Pt, 128, P(pre + ".4.weight"), P(pre + ".4.bias"), B(pre + ".4.running_mean"), B(pre + ".4.running_var"),
+                  c.p<float>(net->stats_t), br * 64, 64, br == 0));
+  }
+  float* hout = net->head_out.bytes ? c.p<float>(net->head_out) : out;
+  RC(head_tail_fwd(c.p(net->zt), N, 2 * hf, 2 * wf, c.p<float>(net->stats_t), c.par(P("segmentation_head.binarize.6.weight")),
+                   c.par(P("segmentation_head.thresh.6.weight")), c.par(P("segmentation_head.binarize.6.bias")),
+                   c.par(P("segmentation_head.thresh.6.bias")), STEP_K, net->out_c, hout, c.s));
+  if (net->head_out.bytes) RC(bilinear_fwd(hout, N * net->out_c, net->ho, net->wo, out, net->h, net->w, c.s));
+  return DBB_OK;
+}
+
+extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout, const float* const* params,
+                                float* const* grads, void* workspace, size_t workspace_bytes, int segment, void* stream) {
+  if (!net || !out || !dout || !params || !grads || !workspace) return set_error(DBB_EINVAL, "net_backward: null pointer");
+  if (!net->training) return set_error(DBB_EINVAL, "net_backward: network was planned in eval mode");
+  if (workspace_bytes < net->ws_bytes) return set_error(DBB_EWORKSPACE, "net_backward: workspace too small");
+  if (segment < -1 || segment > 2) return set_error(DBB_EINVAL, "net_backward: segment must be -1..2");
+  Ctx c{net, (char*)workspace, params, nullptr, grads, (cudaStream_t)stream};
+  const int N = net->n;
+  const int hf = net->hh[0], wf = net->ww[0];
+  const int planes[4] = {64, 128, 256, 512};
+  const bf16* feat[4];
+  for (int i = 0; i < 4; ++i) feat[i] = c.p(net->blocks[i * 2 + 1].out);
+  const bool all = segment < 0;
+  int nblk = 0;
+
+  if (all || segment == 0) {
+    // ---- fused head tail (ConvT2 + sigmoid + step, and the BatchNorm in front of them)
+    const float* hout = out;
+    const float* dhout = dout;
+    if (net->head_out.bytes) {
+      RC(bilinear_bwd(dout, N * 3, net->ho, net->wo, c.p<float>(net->d_head_out), net->h, net->w, c.s));
+      hout = c.p<float>(net->head_out); dhout = c.p<float>(net->d_head_out);
+    }
+    const std::string hb = "segmentation_head.binarize", ht = "segmentation_head.thresh";
+    const int64_t Ph = (int64_t)N * hf * wf, Pt = Ph * 4;
+    RC(head_tail_bwd_reduce(c.p(net->zt), N, 2 * hf, 2 * wf, c.p<float>(net->stats_t), c.par(P(hb + ".6.weight")), c.par(P(ht + ".6.weight")),
+                            hout, dhout, STEP_K, c.partials(), &nblk, c.s));
+    RC(head_tail_bwd_finalize(c.partials(), nblk, Pt, c.par(P(hb + ".4.weight")), c.par(P(ht + ".4.weight")), c.p<float>(net->stats_t),
+                              c.grad(P(hb + ".4.weight")), c.grad(P(hb + ".4.bias")), c.grad(P(ht + ".4.weight")), c.grad(P(ht + ".4.bias")),
+                              c.p<float>(net->coef_t), c.grad(P(hb + ".6.weight")), c.grad(P(ht + ".6.weight")), c.grad(P(hb + ".6.bias")),
+                              c.grad(P(ht + ".6.bias")), c.s));
+    RC(head_tail_bwd_apply(c.p(net->zt), N, 2 * hf, 2 * wf, c.p<float>(net->stats_t), c.p<float>(net->coef_t), c.par(P(hb + ".6.weight")),
+                           c.par(P(ht + ".6.weight")), hout, dhout, STEP_K, c.p(net->d_zt), c.s));
+    // ---- ConvTranspose2d(64,64,2,2) x 2
+    RC(bias_grad(c.p(net->d_zt), Pt, 128, c.partials(), c.p<float>(net->dbias_t), c.s));
+    for (int br = 0; br < 2; ++br) {
+      const std::string pre = br ? ht : hb;
+      DBB_CUDA(cudaMemcpyAsync(c.grad(P(pre + ".3.bias")), c.p<float>(net->dbias_t) + br * 64, 64 * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
+      RC(pack_weights(3, c.par(P(pre + ".3.weight")), c.p(net->wpt_t[br]), 64, 64, 2, 2, c.s));
+      RC(convt_dgrad(net->tconv_g, c.p(net->d_zt), 128, br * 64, c.p(net->wpt_t[br]), c.p(net->d_ah), 128, br * 64, c.s));
+      RC(convt_wgrad(net->tconv_g, c.p(net->ah), 128, br * 64, c.p(net->d_zt), 128, br * 64, c.grad(P(pre + ".3.weight")), c.s));
+    }
+    // ---- BN(2 x 64) + ReLU + the fused 256->128 3x3 conv of the two branches
+    RC(bn_bwd_reduce(c.p(net->d_ah), 128, 0, c.p(net->ah), 128, 0, c.p(net->zh), Ph, 128, c.p<float>(net->stats_h), c.partials(), &nblk, c.s));
+    for (int br = 0; br < 2; ++br) {
+      const std::string pre = br ? ht : hb;
+      RC(bn_bwd_finalize(c.partials(), nblk, 128, br * 64, 64, Ph, c.par(P(pre + ".1.weight")), c.p<float>(net->stats_h),
+                         c.grad(P(pre + ".1.weight")), c.grad(P(pre + ".1.bias")), c.p<float>(net->coef_h), c.s));
+    }
+    RC(bn_bwd_apply(c.p(net->d_ah), 128, 0, c.p(net->ah), 128, 0, c.p(net->zh), Ph, 128, c.p<float>(net->stats_h), c.p<float>(net->coef_h),
+                    c.p(net->d_zh), nullptr, c.s));
+    RC(conv_wgrad(net->hconv_g, c.p(net->af), 256, 0, c.p(net->d_zh), 128, 0, c.p<float>(net->dw_h), c.s));
+    const size_t half = (size_t)64 * 256 * 9;
+    DBB_CUDA(cudaMemcpyAsync(c.grad(P(hb + ".0.weight")), c.p<float>(net->dw_h), half * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
+    DBB_CUDA(cudaMemcpyAsync(c.grad(P(ht + ".0.weight")), c.p<float>(net->dw_h) + half, half * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
+    RC(bias_grad(c.p(net->d_zh), Ph, 128, c.partials(), c.p<float>(net->dbias_h), c.s));
+    DBB_CUDA(cudaMemcpyAsync(c.grad(P(hb + ".0.bias")), c.p<float>(net->dbias_h), 64 * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
+    RC(pack_weights(1, c.par(P(hb + ".0.weight")), c.p(net->wpt_h), 64, 256, 3, 3, c.s, 128, 0));
+    RC(pack_weights(1, c.par(P(ht + ".0.weight")), c.p(net->wpt_h), 64, 256, 3, 3, c.s, 128, 64));
+    RC(conv_dgrad(net->hconv_g, c.p(net->d_zh), c.p(net->wpt_h), c.p(net->d_af), c.s, 0));
+    // ---- FPN output conv
+    RC(convbn_bwd(c, net->fconv, c.p(net->d_af), 256, 0, c.p(net->af), 256, 0, c.p(net->cat), 256, 0, c.p(net->d_cat), 0, nullptr));
+    // ---- top-down path, bottom level first: smooth_p2, p3, p4 then the c5 lateral
+    //      d_p[k]: gradient of p5 (k=0), p4 (1), p3 (2); d_s[i]: gradient of the sum feeding smooth[i]
+    const bf16* dlevel = c.p(net->d_cat);   // gradient w.r.t. p2 = channels 0..63 of d_cat
+    int dl_ct = 256;
+    const bf16* mlevel = c.p(net->cat);     // p2 activation = channels 0..63 of cat
+    int ml_ct = 256;
+    for (int i = 2; i >= 0; --i) {
+      const int lvl = 2 - i;               // smooth[2] -> level 0 (c2 resolution)
+      const int up = lvl + 1;              // the level that was upsampled into this one
+      RC(convbn_bwd(c, net->smooth[i], dlevel, dl_ct, 0, mlevel, ml_ct, 0, c.p(net->s_sum[i]), 64, 0, c.p(net->d_s[i]), 0, nullptr));
+      // gradient of the upsampled operand: concat slice (channels 64*up ..) + the upsample-add path
+      bf16* dpu = c.p(net->d_p[3 - up]);   // up=1 -> d_p[2] (p3), up=2 -> d_p[1] (p4), up=3 -> d_p[0] (p5)
+      RC(upsample_bwd(c.p(net->d_cat), 256, 64 * up, N, hf, wf, 64, dpu, net->hh[up], net->ww[up], 0, c.s));
+      RC(upsample_bwd(c.p(net->d_s[i]), 64, 0, N, net->hh[lvl], net->ww[lvl], 64, dpu, net->hh[up], net->ww[up], 1, c.s));
+      // lateral conv of this level: its output was the other operand of the sum
+      RC(convbn_bwd(c, net->lat[lvl], c.p(net->d_s[i]), 64, 0, c.p(net->l_act[lvl]), 64, 0, feat[lvl], planes[lvl], 0, c.p(net->d_c[lvl]), 0, nullptr));
+      dlevel = dpu; dl_ct = 64;
+      mlevel = (up < 3) ? c.p(net->p_act[2 - up]) : c.p(net->l_act[3]);   // p3 = p_act[1], p4 = p_act[0], p5 = l_act[3]
+      ml_ct = 64;
+    }
+    RC(convbn_bwd(c, net->lat[3], dlevel, 64, 0, mlevel, 64, 0, feat[3], 512, 0, c.p(net->d_c[3]), 0, nullptr));
+  }
+  auto run_block = [&](int i) -> int {
+    const bf16* x = (i == 0) ? c.p(net->x1) : c.p(net->blocks[i - 1].out);
+    bf16* dx = (i == 0) ? c.p(net->d_x1) : c.p(net->blocks[i - 1].d_out);
+    const int has_content = (i >= 2 && (i % 2) == 0) ? 1 : 0;   // input is c2/c3/c4: the FPN lateral already wrote its share
+    return block_bwd(c, net->blocks[i], x, dx, has_content);
+  };
+  if (all || segment == 1) for (int i = 7; i >= 4; --i) RC(run_block(i));
+  if (all || segment == 2) {
+    for (int i = 3; i >= 0; --i) RC(run_block(i));
+    // ---- stem: maxpool -> ReLU/BN -> conv1 (no data gradient: the image needs none)
+    RC(maxpool_bwd(c.p(net->d_x1), c.p<uint8_t>(net->argmax), N, net->h1, net->w1, 64, c.p(net->d_a0), c.s));
+    const int64_t P0 = (int64_t)N * net->h1 * net->w1;
+    const int g1 = P("backbone.bn1.weight"), b1 = P("backbone.bn1.bias");
+    RC(bn_bwd_reduce(c.p(net->d_a0), 64, 0, c.p(net->a0), 64, 0, c.p(net->z0), P0, 64, c.p<float>(net->stats0), c.partials(), &nblk, c.s));
+    RC(bn_bwd_finalize(c.partials(), nblk, 64, 0, 64, P0, c.par(g1), c.p<float>(net->stats0), c.grad(g1), c.grad(b1), c.p<float>(net->coef0), c.s));
+    RC(bn_bwd_apply(c.p(net->d_a0), 64, 0, c.p(net->a0), 64, 0, c.p(net->z0), P0, 64, c.p<float>(net->stats0), c.p<float>(net->coef0),
+                    c.p(net->d_z0), nullptr, c.s));
+    RC(conv1_wgrad(N, net->h, net->w, c.p(net->s2d), c.p(net->d_z0), c.p<float>(net->dw_s2d), c.s));
+    RC(conv1_wgrad_unpack(c.p<float>(net->dw_s2d), c.grad(P("backbone.conv1.weight")), c.s));
+  }
+  return DBB_OK;
+}
+
+// ---- debugging / parity aid: copy a named internal NHWC bf16 tensor out as NCHW float32 (tests only)
+static bool find_tensor(DbbNet* net, const std::string& name, Buf* b, int* h, int* w, int* ch) {
+  auto blk = [&](int i, const char* what) -> bool {
+    Block& k = net->blocks[i];
+    const int ho = k.c1.g.out_h(), wo = k.c1.g.out_w(), pl = k.c2.g.cout;
+    *h = ho; *w = wo; *ch = pl;
+    std::string wname = what;
+    if (wname == "out") *b = k.out; else if (wname == "a1") *b = k.a1; else if (wname == "z1") *b = k.c1.z;
+    else if (wname == "z2") *b = k.c2.z; else if (wname == "d_out") *b = k.d_out; else if (wname == "d_a1") *b = k.d_a1;
+    else if (wname == "dz1") *b = k.c1.dz; else if (wname == "dz2") *b = k.c2.dz; else return false;
+    return b->bytes != 0;
+  };
+  if (name.rfind("block", 0) == 0) {
+    const int i = name[5] - '0';
+    if (i < 0 || i > 7 || name.size() < 8) return false;
+    return blk(i, name.c_str() + 7);
+  }
+  const int hf = net->hh[0], wf = net->ww[0];
+  struct E { const char* n; Buf b; int h, w, c; };
+  const E table[] = {
+      {"z0", net->z0, net->h1, net->w1, 64}, {"a0", net->a0, net->h1, net->w1, 64}, {"x1", net->x1, net->h2, net->w2, 64},
+      {"d_x1", net->d_x1, net->h2, net->w2, 64}, {"d_a0", net->d_a0, net->h1, net->w1, 64}, {"d_z0", net->d_z0, net->h1, net->w1, 64},
+      {"l2", net->l_act[0], net->hh[0], net->ww[0], 64}, {"l3", net->l_act[1], net->hh[1], net->ww[1], 64},
+      {"l4", net->l_act[2], net->hh[2], net->ww[2], 64}, {"p5", net->l_act[3], net->hh[3], net->ww[3], 64},
+      {"p4", net->p_act[0], net->hh[2], net->ww[2], 64}, {"p3", net->p_act[1], net->hh[1], net->ww[1], 64},
+      {"s4", net->s_sum[0], net->hh[2], net->ww[2], 64}, {"s3", net->s_sum[1], net->hh[1], net->ww[1], 64}, {"s2", net->s_sum[2], hf, wf, 64},
+      {"cat", net->cat, hf, wf, 256}, {"zf", net->fconv.z, hf, wf, 256}, {"af", net->af, hf, wf, 256},
+      {"zh", net->zh, hf, wf, 128}, {"ah", net->ah, hf, wf, 128}, {"zt", net->zt, 2 * hf, 2 * wf, 128},
+      {"d_zt", net->d_zt, 2 * hf, 2 * wf, 128}, {"d_ah", net->d_ah, hf, wf, 128}, {"d_zh", net->d_zh, hf, wf, 128},
+      {"d_af", net->d_af, hf, wf, 256}, {"d_cat", net->d_cat, hf, wf, 256},
+      {"d_p5", net->d_p[0], net->hh[3], net->ww[3], 64}, {"d_p4", net->d_p[1], net->hh[2], net->ww[2], 64}, {"d_p3", net->d_p[2], net->hh[1], net->ww[1], 64},
+      {"d_s4", net->d_s[0], net->hh[2], net->ww[2], 64}, {"d_s3", net->d_s[1], net->hh[1], net->ww[1], 64}, {"d_s2", net->d_s[2], hf, wf, 64},
+  };
+  for (const E& e : table)
+    if (name == e.n) { *b = e.b; *h = e.h; *w = e.w; *ch = e.c; return e.b.bytes != 0; }
+  return false;
+}
+
+extern "C" int dbb_net_debug_shape(DbbNet* net, const char* name, int64_t* shape4) {
+  Buf b; int h, w, ch;
+  if (!net || !name || !find_tensor(net, name, &b, &h, &w, &ch)) return set_error(DBB_EINVAL, "net_debug: unknown tensor");
+  shape4[0] = net->n; shape4[1] = ch; shape4[2] = h; shape4[3] = w;
+  return DBB_OK;
+}
+extern "C" int dbb_net_debug_read(DbbNet* net, const char* name, const void* workspace, float* out_nchw, void* stream) {
+  Buf b; int h, w, ch;
+  if (!net || !name || !find_tensor(net, name, &b, &h, &w, &ch)) return set_error(DBB_EINVAL, "net_debug: unknown tensor");
+  return nhwc_bf16_to_nchw_f32(reinterpret_cast<const bf16*>((const char*)workspace + b.off), out_nchw, net->n, ch, (int64_t)h * w, (cudaStream_t)stream);
+}

@@ -1,0 +1,20 @@
+"""ConvBnRelu -- mirror of src/modules/basic.py:7-36 (Conv2d(bias=True) + BatchNorm2d + ReLU)."""
+from torch import nn
+
+
+class ConvBnRelu(nn.Module):
+    """Holds ``conv`` and ``bn`` exactly like the reference so state_dict keys match.  The arithmetic of the
+    DB network runs in the fused executor (csrc/net.cu); calling this block on its own is not part of the hot path."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 padding_mode='zeros', inplace=True):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, padding=padding, dilation=dilation,
+                              groups=groups, bias=bias, padding_mode=padding_mode)
+        self.bn = nn.BatchNorm2d(out_channels)
+        self.relu = nn.ReLU(inplace=inplace)
+
+    def forward(self, x):
+        from .._lib import DbbError
+        raise DbbError("ConvBnRelu is executed inside the fused DBTextModel graph (csrc/net.cu); "
+                       "there is no stand-alone eager path")

@@ -1,0 +1,70 @@
+"""ResNet-18 parameter tree -- mirror of src/modules/resnet.py:37-91,162-255 (only what 'resnet18' needs).
+
+Same attribute names => same state_dict keys (conv1, bn1, layer{1-4}.{0,1}.{conv1,bn1,conv2,bn2[,downsample.{0,1}]},
+plus the never-used ``fc`` and ``smooth`` members the reference carries).  Initialisation follows
+src/modules/resnet.py:197-203.  ``pretrained=True`` cannot download anything here (no network): it is accepted and
+ignored, and a checkpoint is loaded through load_state_dict like the reference does (src/test.py:16)."""
+import math
+
+import torch.nn as nn
+
+__all__ = ['ResNet', 'BasicBlock', 'resnet18']
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, dcn=None):
+        super().__init__()
+        if dcn is not None:
+            raise NotImplementedError("deformable convolutions are outside the resnet18-FPN-DBHead hot path")
+        self.conv1 = nn.Conv2d(inplanes, planes, 3, stride=stride, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(planes, planes, 3, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.downsample = downsample
+        self.stride = stride
+
+
+class ResNet(nn.Module):
+    def __init__(self, block, layers, num_classes=1000, dcn=None):
+        super().__init__()
+        self.inplanes = 64
+        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
+        self.layer1 = self._make_layer(block, 64, layers[0])
+        self.layer2 = self._make_layer(block, 128, layers[1], stride=2)
+        self.layer3 = self._make_layer(block, 256, layers[2], stride=2)
+        self.layer4 = self._make_layer(block, 512, layers[3], stride=2)
+        self.avgpool = nn.AvgPool2d(7, stride=1)
+        self.fc = nn.Linear(512 * block.expansion, num_classes)          # unused in forward, kept for the state dict
+        self.smooth = nn.Conv2d(2048, 256, kernel_size=1, stride=1, padding=1)   # idem
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+                m.weight.data.normal_(0, math.sqrt(2. / n))
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+
+    def _make_layer(self, block, planes, blocks, stride=1):
+        downsample = None
+        if stride != 1 or self.inplanes != planes * block.expansion:
+            downsample = nn.Sequential(
+                nn.Conv2d(self.inplanes, planes * block.expansion, 1, stride=stride, bias=False),
+                nn.BatchNorm2d(planes * block.expansion))
+        layers = [block(self.inplanes, planes, stride, downsample)]
+        self.inplanes = planes * block.expansion
+        layers += [block(self.inplanes, planes) for _ in range(1, blocks)]
+        return nn.Sequential(*layers)
+
+    def forward(self, x):
+        from .._lib import DbbError
+        raise DbbError("the backbone runs inside the fused DBTextModel graph (csrc/net.cu)")
+
+
+def resnet18(pretrained=True, **kwargs):
+    return ResNet(BasicBlock, [2, 2, 2, 2], **kwargs)

@@ -142,13 +142,17 @@ uint64_t dbb_net_flops_fwd(const DbbNet* net);     /* 2*MACs of the convolutions
  * training mode, momentum 0.1, src/modules/basic.py:34); out (N, 3|2, H, W) float32. */
 int dbb_net_forward(DbbNet* net, const float* x, const float* const* params, float* const* buffers,
                     float* out, void* workspace, size_t workspace_bytes, void* stream);
-/* dout (N,3,H,W) float32 -> grads[i] (float32, same shapes as params; OVERWRITTEN, not accumulated;
+/* out: the (N,3,H,W) tensor dbb_net_forward produced; dout (N,3,H,W) float32 -> grads[i] (float32, same shapes as params; OVERWRITTEN, not accumulated;
  * entries for the unused tensors are left untouched).  Must follow dbb_net_forward on the same workspace.
  * segment: -1 = whole backward; 0..dbb_net_num_segments()-1 = one slice (head+FPN first), so the host can
  * overlap the NCCL all-reduce of finished gradient buckets with the rest of the backward. */
 int dbb_net_num_segments(void);
-int dbb_net_backward(DbbNet* net, const float* dout, const float* const* params, float* const* grads,
+int dbb_net_backward(DbbNet* net, const float* out, const float* dout, const float* const* params, float* const* grads,
                      void* workspace, size_t workspace_bytes, int segment, void* stream);
+
+/* parity aid (tests): shape of / NCHW float32 copy of a named internal NHWC bf16 activation or gradient, e.g. "af", "block3.out" */
+int dbb_net_debug_shape(DbbNet* net, const char* name, int64_t* shape4);
+int dbb_net_debug_read(DbbNet* net, const char* name, const void* workspace, float* out_nchw, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Single operators (used by the FPN / DBHead module drop-ins and by the parity tests)

@@ -58,7 +58,8 @@ def test_loss_golden(case, red):
         assert st.n_above + st.n_tie == st.n_neg
         near = near_tau_mask(preds, gts, orc["tau"])
         assert abs(int(st.n_above) - orc["n_above"]) <= int(near.sum())
-        assert ulp_dist(st.tau, orc["tau"]) <= 2                      # k-th largest (logf vs numpy log: <= 1 ulp each)
+        if orc["n_neg"] > 0:
+            assert ulp_dist(st.tau, orc["tau"]) <= 2                  # k-th largest (logf vs numpy log: <= 1 ulp each)
         diff[:, 0][near] = 0                                          # topk tie order is unspecified
     assert diff.max() <= 1e-5 * scale
 
@@ -80,7 +81,8 @@ def test_loss_random_vs_oracle(red, shape):
     if red == "none":
         near = near_tau_mask(preds, gts, orc["tau"])
         assert abs(int(st.n_above) - orc["n_above"]) <= int(near.sum())
-        assert ulp_dist(st.tau, orc["tau"]) <= 2
+        if orc["n_neg"] > 0:
+            assert ulp_dist(st.tau, orc["tau"]) <= 2
         # selected set: gradient non-zero exactly on pos U selected (away from values within 4 ulp of tau)
         sel_gpu = (grad[:, 0] != 0)
         sel_orc = (g[:, 0] != 0)
