@@ -68,6 +68,16 @@ def lib():
     sig("dbb_net_forward", i32, [vp, vp, vp, vp, vp, vp, sz, vp])
     sig("dbb_net_num_segments", i32, [])
     sig("dbb_net_backward", i32, [vp, vp, vp, vp, vp, vp, sz, i32, vp])
+    sig("dbb_ops_workspace", sz, [])
+    sig("dbb_bn_fwd", i32, [vp, i64, i32, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp, sz, vp])
+    sig("dbb_bn_bwd", i32, [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp])
+    sig("dbb_maxpool_fwd", i32, [vp, i64, i64, i64, i32, vp, vp, vp])
+    sig("dbb_maxpool_bwd", i32, [vp, vp, i64, i64, i64, i32, vp, vp])
+    sig("dbb_upsample_add_fwd", i32, [vp, i64, i64, vp, i64, i64, i64, i32, vp, vp])
+    sig("dbb_upsample_into", i32, [vp, i64, i64, i64, i64, i64, i32, vp, i32, i32, vp])
+    sig("dbb_upsample_bwd", i32, [vp, i32, i32, i64, i64, i64, i32, vp, i64, i64, i32, vp])
+    sig("dbb_head_tail_fwd", i32, [vp, i64, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, f32, i32, vp, vp, vp, sz, vp])
+    sig("dbb_head_tail_bwd", i32, [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp])
     sig("dbb_net_debug_shape", i32, [vp, C.c_char_p, vp])
     sig("dbb_net_debug_read", i32, [vp, C.c_char_p, vp, vp, vp])
     sig("dbb_conv2d", i32, [i32, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, i32, vp, sz, vp])

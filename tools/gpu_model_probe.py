@@ -40,7 +40,21 @@ def oracle_intermediates(params, x, training, quant):
             i += 1
         feats.append(xx)
     f = O.fpn_forward(c, tuple(feats)); inter["af"] = f
-    y = O.dbhead_forward(c, f)
+    # head, step by step (segmentation_head.py:35-45)
+    zh, ah, zt = [], [], []
+    outs = []
+    for br in ("binarize", "thresh"):
+        pre = "segmentation_head." + br
+        z = c.conv(f, pre + ".0", 1, 1); zh.append(z)
+        a = F.relu(c.bn(z, pre + ".1")); ah.append(a)
+        t = c.q(c.convT(a, pre + ".3")); zt.append(t)
+        yb = F.relu(c.bn(t, pre + ".4"))
+        outs.append(torch.sigmoid(F.conv_transpose2d(yb, c.p[pre + ".6.weight"], c.p[pre + ".6.bias"], stride=2)))
+    for nm, lst in (("zh", zh), ("ah", ah), ("zt", zt)):
+        inter[nm + "0"], inter[nm + "1"] = lst
+    if training:
+        outs.append(O.step_function(outs[0], outs[1]))
+    y = torch.cat(outs, 1)
     return y, inter
 
 
@@ -78,16 +92,38 @@ def main():
     model.train(True)
     model.zero_grad()
     y = model(x.cuda())
-    crit = DBLoss(reduction="mean")
-    ls = crit(y, torch.from_numpy(gts).cuda())
-    ls[-1].backward()
+    plan = model._plan(n, h, w, True)
+    ws_ptr = y.grad_fn.ws_ptr
+    ws_keep = y.grad_fn.ws_raw      # keep the workspace alive past backward()
+    USE_LOSS = os.environ.get("PROBE_LOSS", "0") == "1"
+    g = torch.Generator().manual_seed(5)
+    dout_fixed = torch.randn(y.shape, generator=g) * 1e-3
+    dout_fixed[:, 2] = 0      # the step function amplifies forward differences by k=50: keep B out of this check
+    if USE_LOSS:
+        crit = DBLoss(reduction="mean")
+        ls = crit(y, torch.from_numpy(gts).cuda())
+        ls[-1].backward()
+        print("losses gpu", [float(v) for v in ls])
+    else:
+        y.backward(dout_fixed.cuda())
     torch.cuda.synchronize()
-    print("losses gpu", [float(v) for v in ls])
     po = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in params.items()}
-    yo = O.dbnet_forward(po, x, True, quant=O.bf16_round)
-    res = O.db_loss(yo.detach().numpy(), gts, reduction="mean")
-    print("losses oracle(bf16-emulated fwd)", res["losses"])
-    yo.backward(torch.from_numpy(res["grad"]).float())
+    yo, inter = oracle_intermediates(po, x, True, O.bf16_round)
+    for t in inter.values():
+        t.retain_grad()
+    if USE_LOSS:
+        res = O.db_loss(yo.detach().numpy(), gts, reduction="mean")
+        print("losses oracle(bf16-emulated fwd)", res["losses"])
+        yo.backward(torch.from_numpy(res["grad"]).float())
+    else:
+        yo.backward(dout_fixed)
+    # NOTE: the workspace was released by backward(); it is still intact until the next allocation
+    pairs = [("d_zt", "zt"), ("d_ah", "ah"), ("d_zh", "zh"), ("d_af", "af")] + [(f"block{i}.d_out", f"block{i}.out") for i in range(7, -1, -1)] + \
+            [("d_x1", "x1"), ("d_a0", "a0"), ("d_z0", "z0")]
+    for mine, theirs in pairs:
+        t = debug_read(model, plan, ws_ptr, mine)
+        og = torch.cat([inter[theirs + "0"].grad, inter[theirs + "1"].grad], 1) if theirs in ("zt", "ah", "zh") else inter[theirs].grad
+        print(f"  {mine:14s} vs oracle grad max/l2 rel = %.3e %.3e" % rel(t, og))
     named = dict(model.named_parameters())
     worst = []
     for k, p in named.items():
