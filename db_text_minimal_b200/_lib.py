@@ -68,6 +68,8 @@ def lib():
     sig("dbb_net_forward", i32, [vp, vp, vp, vp, vp, vp, sz, vp])
     sig("dbb_net_num_segments", i32, [])
     sig("dbb_net_backward", i32, [vp, vp, vp, vp, vp, vp, sz, i32, vp])
+    sig("dbb_profile_enable", None, [i32])
+    sig("dbb_profile_report", sz, [C.c_char_p, sz])
     sig("dbb_ops_workspace", sz, [])
     sig("dbb_bn_fwd", i32, [vp, i64, i32, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp, sz, vp])
     sig("dbb_bn_bwd", i32, [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp])
@@ -105,3 +107,15 @@ def require_cuda(*tensors):
 def stream_ptr():
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def profile_enable(on=True):
+    lib().dbb_profile_enable(1 if on else 0)
+
+
+def profile_report():
+    """[{name, launches, ms}] of the launches recorded since profile_enable(); synchronises the device."""
+    import json
+    buf = C.create_string_buffer(1 << 20)
+    n = lib().dbb_profile_report(buf, len(buf))
+    return json.loads(buf.value.decode())["kernels"] if n else []

@@ -16,6 +16,14 @@ extern thread_local char g_last_error[512];
 extern uint64_t g_launch_count;
 
 int set_cuda_error(cudaError_t e, const char* where);
+// per-kernel CUDA-event timing (off by default; bench.py turns it on for the roofline figure)
+int prof_begin(const char* name, cudaStream_t s);   // returns slot or -1 when profiling is off
+void prof_end(int slot, cudaStream_t s);
+}  // namespace dbb
+#include <string>
+namespace dbb {
+const char* prof_label(const std::string& s);
+bool prof_enabled();   // interned label (stable pointer)
 int set_error(int code, const char* msg);
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -26,6 +34,15 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
     ++::dbb::g_launch_count;                                                \
     cudaError_t e__ = cudaGetLastError();                                   \
     if (e__ != cudaSuccess) return ::dbb::set_cuda_error(e__, where);       \
+  } while (0)
+
+// launch + account + (optionally) time one kernel:  DBB_LAUNCH("name", stream, kernel<<<g, b, smem, stream>>>(args...));
+#define DBB_LAUNCH(name, stream, ...)                                       \
+  do {                                                                      \
+    const int prof__ = ::dbb::prof_begin(name, stream);                     \
+    __VA_ARGS__;                                                            \
+    if (prof__ >= 0) ::dbb::prof_end(prof__, stream);                       \
+    DBB_CHECK_LAUNCH(name);                                                 \
   } while (0)
 
 #define DBB_CUDA(call)                                                      \

@@ -307,8 +307,7 @@ int pack_weights(int mode, const float* w, bf16* out, int co_n, int ci_n, int kh
   const int64_t total = (mode == 4) ? (int64_t)co_n * 256 : (int64_t)co_n * ci_n * kh * kw;
   int grid = (int)((total + 255) / 256);
   if (grid > DBB_NUM_SMS * 8) grid = DBB_NUM_SMS * 8;
-  pack_weights_kernel<<<grid, 256, 0, s>>>(mode, w, out, co_n, ci_n, kh, kw, co_total, co_off);
-  DBB_CHECK_LAUNCH("pack_weights");
+  DBB_LAUNCH("pack_weights", s, pack_weights_kernel<<<grid, 256, 0, s>>>(mode, w, out, co_n, ci_n, kh, kw, co_total, co_off));
   return DBB_OK;
 }
 
@@ -427,8 +426,13 @@ static int igemm_launch_t(const IgemmPlan& p, cudaStream_t s) {
   const int n_blocks = (p.cout + BLOCK_N - 1) / BLOCK_N;
   const int64_t grid = (int64_t)p.tiles_n * p.tiles_h * p.tiles_w * n_blocks;
   if (grid <= 0 || grid > 0x7fffffff) return set_error(DBB_EINVAL, "igemm: bad grid");
-  igemm_kernel<BLOCK_N, STAGES><<<(unsigned)grid, IG_THREADS, SM::TOTAL, s>>>(p);
-  DBB_CHECK_LAUNCH("igemm_kernel");
+  const char* label = "igemm";
+  if (prof_enabled()) {
+    char tmp[96];   // label carries the GEMM shape: M pixels, N channels, K = taps*cin
+    snprintf(tmp, sizeof(tmp), "igemm_bn%d_m%lld_n%d_k%d", BLOCK_N, (long long)p.mn * p.mh * p.mw, p.cout, p.ntaps * p.cin);
+    label = prof_label(tmp);
+  }
+  DBB_LAUNCH(label, s, igemm_kernel<BLOCK_N, STAGES><<<(unsigned)grid, IG_THREADS, SM::TOTAL, s>>>(p));
   return DBB_OK;
 }
 
@@ -453,8 +457,13 @@ static int wgrad_launch_t(const WgradPlan& p, cudaStream_t s) {
   const int m_tiles = (p.m_total + 127) / 128, n_tiles = (p.n_total + N_TILE - 1) / N_TILE;
   const int64_t grid = (int64_t)p.ntaps * m_tiles * n_tiles * p.split_k;
   if (grid <= 0 || grid > 0x7fffffff) return set_error(DBB_EINVAL, "wgrad: bad grid");
-  wgrad_kernel<N_TILE, STAGES><<<(unsigned)grid, IG_THREADS, SM::TOTAL, s>>>(p);
-  DBB_CHECK_LAUNCH("wgrad_kernel");
+  const char* label = "wgrad";
+  if (prof_enabled()) {
+    char tmp[96];   // M x N per tap, K = pixels reduced
+    snprintf(tmp, sizeof(tmp), "wgrad_nt%d_m%d_n%d_t%d_k%lld", N_TILE, p.m_total, p.n_total, p.ntaps, (long long)p.mn * p.mh * p.mw);
+    label = prof_label(tmp);
+  }
+  DBB_LAUNCH(label, s, wgrad_kernel<N_TILE, STAGES><<<(unsigned)grid, IG_THREADS, SM::TOTAL, s>>>(p));
   return DBB_OK;
 }
 

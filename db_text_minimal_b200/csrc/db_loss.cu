@@ -486,15 +486,11 @@ static int loss_fwd_impl(const float* preds, const float* gts, int64_t n, int c,
   const int grid = loss_grid(px);
   LossWs ws = carve(workspace, grid, px);
   if (SELECT) DBB_CUDA(cudaMemsetAsync(ws.hist1, 0, sizeof(unsigned) * HIST1_BINS + 256, s));
-  dbloss_reduce_kernel<VEC, HAS_B, SELECT><<<grid, LOSS_THREADS, 0, s>>>(preds, gts, n, hw, c, ws.partials, ws.hist1);
-  DBB_CHECK_LAUNCH("dbloss_reduce");
-  dbloss_finalize1_kernel<SELECT><<<1, 256, 0, s>>>(ws.partials, grid, ws.hist1, ws.cand_count, lp, losses5, state);
-  DBB_CHECK_LAUNCH("dbloss_finalize1");
+  DBB_LAUNCH("dbloss_reduce", s, dbloss_reduce_kernel<VEC, HAS_B, SELECT><<<grid, LOSS_THREADS, 0, s>>>(preds, gts, n, hw, c, ws.partials, ws.hist1));
+  DBB_LAUNCH("dbloss_finalize1", s, dbloss_finalize1_kernel<SELECT><<<1, 256, 0, s>>>(ws.partials, grid, ws.hist1, ws.cand_count, lp, losses5, state));
   if (SELECT) {
-    dbloss_select_pass2_kernel<VEC><<<grid, LOSS_THREADS, 0, s>>>(preds, gts, n, hw, c, ws.partials, ws.cand_count, ws.cands);
-    DBB_CHECK_LAUNCH("dbloss_select_pass2");
-    dbloss_select_final_kernel<<<1, 1024, 0, s>>>(ws.partials, grid, ws.cand_count, ws.cands, lp, losses5, state);
-    DBB_CHECK_LAUNCH("dbloss_select_final");
+    DBB_LAUNCH("dbloss_select_pass2", s, dbloss_select_pass2_kernel<VEC><<<grid, LOSS_THREADS, 0, s>>>(preds, gts, n, hw, c, ws.partials, ws.cand_count, ws.cands));
+    DBB_LAUNCH("dbloss_select_final", s, dbloss_select_final_kernel<<<1, 1024, 0, s>>>(ws.partials, grid, ws.cand_count, ws.cands, lp, losses5, state));
   }
   return DBB_OK;
 }
@@ -535,7 +531,7 @@ extern "C" int dbb_dbloss_bwd(const float* preds, const float* gts, int64_t n, i
   const int grid = loss_grid(n * hw);
   const bool v4 = (hw % 4) == 0;
   if (reduction) DBB_CUDA(cudaMemsetAsync(&state->tie_ticket, 0, sizeof(int), s));
-#define LAUNCH(V, B, S) dbloss_bwd_kernel<V, B, S><<<grid, LOSS_THREADS, 0, s>>>(preds, gts, n, hw, c, alpha, beta, grad_out5, state, dpreds)
+#define LAUNCH(V, B, S) DBB_LAUNCH("dbloss_bwd", s, dbloss_bwd_kernel<V, B, S><<<grid, LOSS_THREADS, 0, s>>>(preds, gts, n, hw, c, alpha, beta, grad_out5, state, dpreds))
   if (v4) {
     if (c == 3) { if (reduction) LAUNCH(4, true, true); else LAUNCH(4, true, false); }
     else        { if (reduction) LAUNCH(4, false, true); else LAUNCH(4, false, false); }
@@ -544,7 +540,6 @@ extern "C" int dbb_dbloss_bwd(const float* preds, const float* gts, int64_t n, i
     else        { if (reduction) LAUNCH(1, false, true); else LAUNCH(1, false, false); }
   }
 #undef LAUNCH
-  DBB_CHECK_LAUNCH("dbloss_bwd");
   return DBB_OK;
 }
 
@@ -552,8 +547,7 @@ extern "C" int dbb_step_fwd(const float* p, const float* t, float* b, int64_t nu
   if (!p || !t || !b || numel < 0) return set_error(DBB_EINVAL, "step_fwd: bad argument");
   if (numel == 0) return DBB_OK;
   int64_t g = (numel + 255) / 256; if (g > DBB_NUM_SMS * 8) g = DBB_NUM_SMS * 8;
-  step_fwd_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(p, t, b, numel, k);
-  DBB_CHECK_LAUNCH("step_fwd");
+  DBB_LAUNCH("step_fwd", (cudaStream_t)stream, step_fwd_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(p, t, b, numel, k));
   return DBB_OK;
 }
 extern "C" int dbb_step_bwd(const float* p, const float* t, const float* db, float* dp, float* dt, int64_t numel, float k,
@@ -561,7 +555,6 @@ extern "C" int dbb_step_bwd(const float* p, const float* t, const float* db, flo
   if (!p || !t || !db || !dp || !dt || numel < 0) return set_error(DBB_EINVAL, "step_bwd: bad argument");
   if (numel == 0) return DBB_OK;
   int64_t g = (numel + 255) / 256; if (g > DBB_NUM_SMS * 8) g = DBB_NUM_SMS * 8;
-  step_bwd_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(p, t, db, dp, dt, numel, k);
-  DBB_CHECK_LAUNCH("step_bwd");
+  DBB_LAUNCH("step_bwd", (cudaStream_t)stream, step_bwd_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(p, t, db, dp, dt, numel, k));
   return DBB_OK;
 }

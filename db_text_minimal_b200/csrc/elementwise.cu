@@ -49,14 +49,12 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const bf16* __restric
 
 int nchw_f32_to_nhwc_bf16(const float* x, bf16* y, int n, int c, int64_t hw, cudaStream_t s) {
   dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n);
-  nchw_to_nhwc_kernel<<<grid, 256, 0, s>>>(x, y, c, hw);
-  DBB_CHECK_LAUNCH("nchw_to_nhwc");
+  DBB_LAUNCH("nchw_to_nhwc", s, nchw_to_nhwc_kernel<<<grid, 256, 0, s>>>(x, y, c, hw));
   return DBB_OK;
 }
 int nhwc_bf16_to_nchw_f32(const bf16* x, float* y, int n, int c, int64_t hw, cudaStream_t s) {
   dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n);
-  nhwc_to_nchw_kernel<<<grid, 256, 0, s>>>(x, y, c, hw);
-  DBB_CHECK_LAUNCH("nhwc_to_nchw");
+  DBB_LAUNCH("nhwc_to_nchw", s, nhwc_to_nchw_kernel<<<grid, 256, 0, s>>>(x, y, c, hw));
   return DBB_OK;
 }
 
@@ -291,20 +289,17 @@ static int check_c(int c) { return (c % 8 == 0 && c >= 8 && c <= 2048 && EW_THRE
 int bn_stats(const bf16* z, int64_t P, int c, float* partials, int* nblk, cudaStream_t s) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_stats: channel count");
   *nblk = ew_blocks(P, c);
-  bn_stats_kernel<<<*nblk, EW_THREADS, 0, s>>>(z, P, c, partials);
-  DBB_CHECK_LAUNCH("bn_stats");
+  DBB_LAUNCH("bn_stats", s, bn_stats_kernel<<<*nblk, EW_THREADS, 0, s>>>(z, P, c, partials));
   return DBB_OK;
 }
 int bn_finalize_train(const float* partials, int nblk, int c, int coff, int cn, int64_t count, const float* gamma, const float* beta,
                       float* running_mean, float* running_var, float momentum, float eps, float* stats4, cudaStream_t s) {
-  bn_finalize_train_kernel<<<(cn + 127) / 128, 128, 0, s>>>(partials, nblk, c, coff, cn, (double)count, gamma, beta, running_mean, running_var, momentum, eps, stats4);
-  DBB_CHECK_LAUNCH("bn_finalize_train");
+  DBB_LAUNCH("bn_finalize_train", s, bn_finalize_train_kernel<<<(cn + 127) / 128, 128, 0, s>>>(partials, nblk, c, coff, cn, (double)count, gamma, beta, running_mean, running_var, momentum, eps, stats4));
   return DBB_OK;
 }
 int bn_finalize_eval(int c, int coff, int cn, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                      float eps, float* stats4, cudaStream_t s) {
-  bn_finalize_eval_kernel<<<(cn + 127) / 128, 128, 0, s>>>(c, coff, cn, gamma, beta, running_mean, running_var, eps, stats4);
-  DBB_CHECK_LAUNCH("bn_finalize_eval");
+  DBB_LAUNCH("bn_finalize_eval", s, bn_finalize_eval_kernel<<<(cn + 127) / 128, 128, 0, s>>>(c, coff, cn, gamma, beta, running_mean, running_var, eps, stats4));
   return DBB_OK;
 }
 static int stream_grid(int64_t total) {
@@ -315,39 +310,33 @@ static int stream_grid(int64_t total) {
 int bn_apply(const bf16* z, int64_t P, int c, const float* stats4, const bf16* res, int relu, bf16* out, int out_ctotal,
              int out_coff, cudaStream_t s) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_apply: channel count");
-  bn_apply_kernel<<<stream_grid(P * (c / 8)), EW_THREADS, 0, s>>>(z, P, c, stats4, res, relu, out, out_ctotal, out_coff);
-  DBB_CHECK_LAUNCH("bn_apply");
+  DBB_LAUNCH("bn_apply", s, bn_apply_kernel<<<stream_grid(P * (c / 8)), EW_THREADS, 0, s>>>(z, P, c, stats4, res, relu, out, out_ctotal, out_coff));
   return DBB_OK;
 }
 int bn_bwd_reduce(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
                   const bf16* z, int64_t P, int c, const float* stats4, float* partials, int* nblk, cudaStream_t s) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_bwd_reduce: channel count");
   *nblk = ew_blocks(P, c);
-  bn_bwd_reduce_kernel<<<*nblk, EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, partials);
-  DBB_CHECK_LAUNCH("bn_bwd_reduce");
+  DBB_LAUNCH("bn_bwd_reduce", s, bn_bwd_reduce_kernel<<<*nblk, EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, partials));
   return DBB_OK;
 }
 int bn_bwd_finalize(const float* partials, int nblk, int c, int coff, int cn, int64_t count, const float* gamma, const float* stats4,
                     float* dgamma, float* dbeta, float* coef3, cudaStream_t s) {
-  bn_bwd_finalize_kernel<<<(cn + 127) / 128, 128, 0, s>>>(partials, nblk, c, coff, cn, (double)count, gamma, stats4, dgamma, dbeta, coef3);
-  DBB_CHECK_LAUNCH("bn_bwd_finalize");
+  DBB_LAUNCH("bn_bwd_finalize", s, bn_bwd_finalize_kernel<<<(cn + 127) / 128, 128, 0, s>>>(partials, nblk, c, coff, cn, (double)count, gamma, stats4, dgamma, dbeta, coef3));
   return DBB_OK;
 }
 int bn_bwd_apply(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
                  const bf16* z, int64_t P, int c, const float* stats4, const float* coef3, bf16* dz, bf16* dsum,
                  cudaStream_t s) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_bwd_apply: channel count");
-  bn_bwd_apply_kernel<<<stream_grid(P * (c / 8)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, coef3, dz, dsum);
-  DBB_CHECK_LAUNCH("bn_bwd_apply");
+  DBB_LAUNCH("bn_bwd_apply", s, bn_bwd_apply_kernel<<<stream_grid(P * (c / 8)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, coef3, dz, dsum));
   return DBB_OK;
 }
 int bias_grad(const bf16* dz, int64_t P, int c, float* partials, float* dbias, cudaStream_t s) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bias_grad: channel count");
   const int nblk = ew_blocks(P, c);
-  colsum_kernel<<<nblk, EW_THREADS, 0, s>>>(dz, P, c, partials);
-  DBB_CHECK_LAUNCH("colsum");
-  colsum_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(partials, nblk, c, dbias);
-  DBB_CHECK_LAUNCH("colsum_finalize");
+  DBB_LAUNCH("colsum", s, colsum_kernel<<<nblk, EW_THREADS, 0, s>>>(dz, P, c, partials));
+  DBB_LAUNCH("colsum_finalize", s, colsum_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(partials, nblk, c, dbias));
   return DBB_OK;
 }
 
@@ -420,14 +409,12 @@ __global__ void __launch_bounds__(EW_THREADS) maxpool_bwd_kernel(const bf16* __r
 }
 int maxpool_fwd(const bf16* x, int n, int h, int w, int c, bf16* y, uint8_t* argmax, cudaStream_t s) {
   const int oh = (h + 2 - 3) / 2 + 1, ow = (w + 2 - 3) / 2 + 1;
-  maxpool_fwd_kernel<<<stream_grid((int64_t)n * oh * ow * (c / 8)), EW_THREADS, 0, s>>>(x, n, h, w, c, oh, ow, y, argmax);
-  DBB_CHECK_LAUNCH("maxpool_fwd");
+  DBB_LAUNCH("maxpool_fwd", s, maxpool_fwd_kernel<<<stream_grid((int64_t)n * oh * ow * (c / 8)), EW_THREADS, 0, s>>>(x, n, h, w, c, oh, ow, y, argmax));
   return DBB_OK;
 }
 int maxpool_bwd(const bf16* dy, const uint8_t* argmax, int n, int h, int w, int c, bf16* dx, cudaStream_t s) {
   const int oh = (h + 2 - 3) / 2 + 1, ow = (w + 2 - 3) / 2 + 1;
-  maxpool_bwd_kernel<<<stream_grid((int64_t)n * h * w * (c / 8)), EW_THREADS, 0, s>>>(dy, argmax, n, h, w, c, oh, ow, dx);
-  DBB_CHECK_LAUNCH("maxpool_bwd");
+  DBB_LAUNCH("maxpool_bwd", s, maxpool_bwd_kernel<<<stream_grid((int64_t)n * h * w * (c / 8)), EW_THREADS, 0, s>>>(dy, argmax, n, h, w, c, oh, ow, dx));
   return DBB_OK;
 }
 
@@ -491,19 +478,16 @@ __global__ void __launch_bounds__(EW_THREADS) upsample_bwd_kernel(const bf16* __
   }
 }
 int upsample_add_fwd(const bf16* xs, int hs, int ws, const bf16* y, int n, int h, int w, int c, bf16* out, cudaStream_t s) {
-  upsample_fwd_kernel<<<stream_grid((int64_t)n * h * w * (c / 8)), EW_THREADS, 0, s>>>(xs, hs, ws, (float)hs / (float)h, (float)ws / (float)w, y, n, h, w, c, out, c, 0);
-  DBB_CHECK_LAUNCH("upsample_add_fwd");
+  DBB_LAUNCH("upsample_add_fwd", s, upsample_fwd_kernel<<<stream_grid((int64_t)n * h * w * (c / 8)), EW_THREADS, 0, s>>>(xs, hs, ws, (float)hs / (float)h, (float)ws / (float)w, y, n, h, w, c, out, c, 0));
   return DBB_OK;
 }
 int upsample_into(const bf16* xs, int hs, int ws, int n, int h, int w, int c, bf16* dst, int dst_ctotal, int dst_coff, cudaStream_t s) {
-  upsample_fwd_kernel<<<stream_grid((int64_t)n * h * w * (c / 8)), EW_THREADS, 0, s>>>(xs, hs, ws, (float)hs / (float)h, (float)ws / (float)w, nullptr, n, h, w, c, dst, dst_ctotal, dst_coff);
-  DBB_CHECK_LAUNCH("upsample_into");
+  DBB_LAUNCH("upsample_into", s, upsample_fwd_kernel<<<stream_grid((int64_t)n * h * w * (c / 8)), EW_THREADS, 0, s>>>(xs, hs, ws, (float)hs / (float)h, (float)ws / (float)w, nullptr, n, h, w, c, dst, dst_ctotal, dst_coff));
   return DBB_OK;
 }
 int upsample_bwd(const bf16* d_big, int big_ctotal, int big_coff, int n, int h, int w, int c, bf16* d_xs, int hs, int ws,
                  int accumulate, cudaStream_t s) {
-  upsample_bwd_kernel<<<stream_grid((int64_t)n * hs * ws * (c / 8)), EW_THREADS, 0, s>>>(d_big, big_ctotal, big_coff, n, h, w, c, (float)hs / (float)h, (float)ws / (float)w, d_xs, hs, ws, accumulate);
-  DBB_CHECK_LAUNCH("upsample_bwd");
+  DBB_LAUNCH("upsample_bwd", s, upsample_bwd_kernel<<<stream_grid((int64_t)n * hs * ws * (c / 8)), EW_THREADS, 0, s>>>(d_big, big_ctotal, big_coff, n, h, w, c, (float)hs / (float)h, (float)ws / (float)w, d_xs, hs, ws, accumulate));
   return DBB_OK;
 }
 
@@ -542,8 +526,7 @@ __global__ void __launch_bounds__(EW_THREADS) image_to_s2d_kernel(const float* _
 }
 int image_to_s2d(const float* img, int n, int h, int w, bf16* s2d, cudaStream_t s) {
   const int hs = (h + 1) / 2, ws = (w + 1) / 2;
-  image_to_s2d_kernel<<<stream_grid((int64_t)n * (hs + 3) * (ws + 3)), EW_THREADS, 0, s>>>(img, n, h, w, hs, ws, s2d);
-  DBB_CHECK_LAUNCH("image_to_s2d");
+  DBB_LAUNCH("image_to_s2d", s, image_to_s2d_kernel<<<stream_grid((int64_t)n * (hs + 3) * (ws + 3)), EW_THREADS, 0, s>>>(img, n, h, w, hs, ws, s2d));
   return DBB_OK;
 }
 __global__ void conv1_wgrad_unpack_kernel(const float* __restrict__ dw_s2d, float* __restrict__ dw) {
@@ -556,8 +539,7 @@ __global__ void conv1_wgrad_unpack_kernel(const float* __restrict__ dw_s2d, floa
   dw[i] = dw_s2d[((int64_t)co * 64 + nidx) * 4 + kh2];
 }
 int conv1_wgrad_unpack(const float* dw_s2d, float* dw, cudaStream_t s) {
-  conv1_wgrad_unpack_kernel<<<(64 * 147 + 255) / 256, 256, 0, s>>>(dw_s2d, dw);
-  DBB_CHECK_LAUNCH("conv1_wgrad_unpack");
+  DBB_LAUNCH("conv1_wgrad_unpack", s, conv1_wgrad_unpack_kernel<<<(64 * 147 + 255) / 256, 256, 0, s>>>(dw_s2d, dw));
   return DBB_OK;
 }
 
@@ -599,14 +581,12 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const float* __restri
   }
 }
 int bilinear_fwd(const float* x, int nc, int hi, int wi, float* y, int ho, int wo, cudaStream_t s) {
-  bilinear_fwd_kernel<<<stream_grid((int64_t)nc * ho * wo), 256, 0, s>>>(x, nc, hi, wi, y, ho, wo);
-  DBB_CHECK_LAUNCH("bilinear_fwd");
+  DBB_LAUNCH("bilinear_fwd", s, bilinear_fwd_kernel<<<stream_grid((int64_t)nc * ho * wo), 256, 0, s>>>(x, nc, hi, wi, y, ho, wo));
   return DBB_OK;
 }
 int bilinear_bwd(const float* dy, int nc, int hi, int wi, float* dx, int ho, int wo, cudaStream_t s) {
   DBB_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)nc * hi * wi, s));
-  bilinear_bwd_kernel<<<stream_grid((int64_t)nc * ho * wo), 256, 0, s>>>(dy, nc, hi, wi, dx, ho, wo);
-  DBB_CHECK_LAUNCH("bilinear_bwd");
+  DBB_LAUNCH("bilinear_bwd", s, bilinear_bwd_kernel<<<stream_grid((int64_t)nc * ho * wo), 256, 0, s>>>(dy, nc, hi, wi, dx, ho, wo));
   return DBB_OK;
 }
 

@@ -322,29 +322,25 @@ static int ht_reduce_grid(int n, int h2, int w2) {
 
 int head_tail_fwd(const bf16* zt, int n, int h2, int w2, const float* stats4, const float* w2b, const float* w2t,
                   const float* b2b, const float* b2t, float k, int out_c, float* out, cudaStream_t s) {
-  head_tail_fwd_kernel<<<ht_grid(n, h2, w2), HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, w2b, w2t, b2b, b2t, k, out_c, out);
-  DBB_CHECK_LAUNCH("head_tail_fwd");
+  DBB_LAUNCH("head_tail_fwd", s, head_tail_fwd_kernel<<<ht_grid(n, h2, w2), HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, w2b, w2t, b2b, b2t, k, out_c, out));
   return DBB_OK;
 }
 int head_tail_bwd_reduce(const bf16* zt, int n, int h2, int w2, const float* stats4, const float* w2b, const float* w2t,
                          const float* out, const float* dout, float k, float* partials, int* nblk, cudaStream_t s) {
   *nblk = ht_reduce_grid(n, h2, w2);
-  head_tail_bwd_reduce_kernel<<<*nblk, HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, w2b, w2t, out, dout, k, partials);
-  DBB_CHECK_LAUNCH("head_tail_bwd_reduce");
+  DBB_LAUNCH("head_tail_bwd_reduce", s, head_tail_bwd_reduce_kernel<<<*nblk, HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, w2b, w2t, out, dout, k, partials));
   return DBB_OK;
 }
 int head_tail_bwd_finalize(const float* partials, int nblk, int64_t count, const float* gamma_b, const float* gamma_t,
                            const float* stats4, float* dgamma_b, float* dbeta_b, float* dgamma_t, float* dbeta_t,
                            float* coef3, float* dw2b, float* dw2t, float* db2b, float* db2t, cudaStream_t s) {
-  head_tail_bwd_finalize_kernel<<<1, 128, 0, s>>>(partials, nblk, (double)count, gamma_b, gamma_t, stats4, dgamma_b, dbeta_b,
-                                                  dgamma_t, dbeta_t, coef3, dw2b, dw2t, db2b, db2t);
-  DBB_CHECK_LAUNCH("head_tail_bwd_finalize");
+  DBB_LAUNCH("head_tail_bwd_finalize", s, head_tail_bwd_finalize_kernel<<<1, 128, 0, s>>>(partials, nblk, (double)count, gamma_b, gamma_t, stats4, dgamma_b, dbeta_b,
+                                                  dgamma_t, dbeta_t, coef3, dw2b, dw2t, db2b, db2t));
   return DBB_OK;
 }
 int head_tail_bwd_apply(const bf16* zt, int n, int h2, int w2, const float* stats4, const float* coef3, const float* w2b,
                         const float* w2t, const float* out, const float* dout, float k, bf16* d_zt, cudaStream_t s) {
-  head_tail_bwd_apply_kernel<<<ht_grid(n, h2, w2), HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, coef3, w2b, w2t, out, dout, k, d_zt);
-  DBB_CHECK_LAUNCH("head_tail_bwd_apply");
+  DBB_LAUNCH("head_tail_bwd_apply", s, head_tail_bwd_apply_kernel<<<ht_grid(n, h2, w2), HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, coef3, w2b, w2t, out, dout, k, d_zt));
   return DBB_OK;
 }
 

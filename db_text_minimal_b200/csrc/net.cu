@@ -575,13 +575,33 @@ static bool find_tensor(DbbNet* net, const std::string& name, Buf* b, int* h, in
     std::string wname = what;
     if (wname == "out") *b = k.out; else if (wname == "a1") *b = k.a1; else if (wname == "z1") *b = k.c1.z;
     else if (wname == "z2") *b = k.c2.z; else if (wname == "d_out") *b = k.d_out; else if (wname == "d_a1") *b = k.d_a1;
-    else if (wname == "dz1") *b = k.c1.dz; else if (wname == "dz2") *b = k.c2.dz; else return false;
+    else if (wname == "dz1") *b = k.c1.dz; else if (wname == "dz2") *b = k.c2.dz;
+    else if (wname == "zd" && k.has_ds) *b = k.ds.z; else if (wname == "dzd" && k.has_ds) *b = k.ds.dz; else return false;
     return b->bytes != 0;
   };
   if (name.rfind("block", 0) == 0) {
     const int i = name[5] - '0';
     if (i < 0 || i > 7 || name.size() < 8) return false;
     return blk(i, name.c_str() + 7);
+  }
+  {
+    // "<unit>.z" / "<unit>.dz" for lat0..3, smooth0..2, fconv, blockK.ds
+    auto unit = [&](const std::string& u) -> ConvBN* {
+      if (u.rfind("lat", 0) == 0 && u.size() == 4) return &net->lat[u[3] - '0'];
+      if (u.rfind("smooth", 0) == 0 && u.size() == 7) return &net->smooth[u[6] - '0'];
+      if (u == "fconv") return &net->fconv;
+      return nullptr;
+    };
+    const size_t dot = name.rfind('.');
+    if (dot != std::string::npos) {
+      ConvBN* L = unit(name.substr(0, dot));
+      const std::string what = name.substr(dot + 1);
+      if (L && (what == "z" || what == "dz")) {
+        *b = (what == "z") ? L->z : L->dz;
+        *h = L->g.out_h(); *w = L->g.out_w(); *ch = L->g.cout;
+        return b->bytes != 0;
+      }
+    }
   }
   const int hf = net->hh[0], wf = net->ww[0];
   struct E { const char* n; Buf b; int h, w, c; };
