@@ -53,6 +53,7 @@ def lib():
     sig("dbb_step_fwd", i32, [vp, vp, vp, i64, f32, vp])
     sig("dbb_step_bwd", i32, [vp, vp, vp, vp, vp, i64, f32, vp])
     sig("dbb_postprocess_workspace", sz, [i64, i64, i64])
+    sig("dbb_binarize", i32, [vp, i64, i32, i64, i64, f32, vp, vp])
     sig("dbb_binarize_ccl_score", i32, [vp, i64, i32, i64, i64, f32, f64, vp, vp, vp, vp, i32, vp, sz, vp])
     sig("dbb_net_num_params", i32, [])
     sig("dbb_net_param_name", C.c_char_p, [i32])

@@ -30,8 +30,12 @@ struct LossWs {
   double* partials;
   unsigned* hist1;
   unsigned* cand_count;   // [0] = count, [1] = taubin (as int), [2] = cnt_above_bin lo, [3] hi
+  unsigned* hist2;
+  unsigned* hist3;
+  unsigned* sel_ctl;
   float* cands;
 };
+constexpr size_t LOSS_CTL_BYTES = sizeof(unsigned) * (HIST1_BINS + HIST2_BINS + HIST3_BINS) + 512;
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -48,6 +52,9 @@ static LossWs carve(void* ws, int grid, int64_t px) {
   w.partials = (double*)p;            p += align_up(sizeof(double) * NSUM * (size_t)grid, 256);
   w.hist1 = (unsigned*)p;             p += sizeof(unsigned) * HIST1_BINS;
   w.cand_count = (unsigned*)p;        p += 256;
+  w.hist2 = (unsigned*)p;             p += sizeof(unsigned) * HIST2_BINS;
+  w.hist3 = (unsigned*)p;             p += sizeof(unsigned) * HIST3_BINS;
+  w.sel_ctl = (unsigned*)p;           p += 256;
   w.cands = (float*)p;
   return w;
 }
@@ -244,7 +251,7 @@ dbloss_finalize1_kernel(const double* __restrict__ partials, int nblk, unsigned*
   for (int i = 0; i < NSUM; ++i) st->sums[i] = S[i];
 }
 
-// pass 2 ('none'): sum of everything above the tau bin + compaction of the tau bin
+// pass 2 ('none'): sum of everything above the tau bin + compaction of the tau bin (one atomic per warp iteration)
 template <int VEC>
 __global__ void __launch_bounds__(LOSS_THREADS)
 dbloss_select_pass2_kernel(const float* __restrict__ preds, const float* __restrict__ gts, int64_t n_img, int64_t hw, int cch,
@@ -252,45 +259,46 @@ dbloss_select_pass2_kernel(const float* __restrict__ preds, const float* __restr
   const int tb = (int)cand_ctl[1];
   const int64_t px = n_img * hw;
   const int64_t hwv = hw / VEC, nvec = n_img * hwv;
-  float acc[1] = {0.f};
+  float acc = 0.f;
   if (tb >= 0) {
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * LOSS_THREADS;
     const int64_t start = (int64_t)blockIdx.x * LOSS_THREADS + threadIdx.x;
-    // all lanes of a warp iterate the same number of times (ballot below needs convergence)
-    const int64_t iters = (nvec + stride - 1) / stride;
+    const int64_t iters = (nvec + stride - 1) / stride;     // same trip count for every lane (shuffles below)
     for (int64_t it = 0; it < iters; ++it) {
       const int64_t v = start + it * stride;
-      const bool valid = v < nvec;
-      Vec4 NL;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) NL.v[j] = 0.f;
-      if (valid) {
+      float hit[4];
+      int cnt = 0;
+      if (v < nvec) {
         const int64_t n = v / hwv, r = (v - n * hwv) * VEC;
         Vec4 P = Loader<VEC>::ld(preds + (n * cch) * hw + r);
         Vec4 G = Loader<VEC>::ld(gts + n * hw + r), M = Loader<VEC>::ld(gts + px + n * hw + r);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) NL.v[j] = negl_of(P.v[j], G.v[j], M.v[j]);
-      }
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        const float nl = NL.v[j];
-        const int b = (nl > 0.f) ? (int)(__float_as_uint(nl) >> 20) : -1;
-        if (b > tb) acc[0] += nl;
-        const bool hit = (b == tb);
-        const unsigned mask = __ballot_sync(0xffffffffu, hit);
-        if (mask) {
-          unsigned base = 0;
-          if (lane == (__ffs(mask) - 1)) base = atomicAdd(&cand_ctl[0], (unsigned)__popc(mask));
-          base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
-          if (hit) cands[base + __popc(mask & ((1u << lane) - 1u))] = nl;
+        for (int j = 0; j < VEC; ++j) {
+          const float nl = negl_of(P.v[j], G.v[j], M.v[j]);
+          const int bin = (nl > 0.f) ? (int)(__float_as_uint(nl) >> 20) : -1;
+          if (bin > tb) acc += nl;
+          if (bin == tb) hit[cnt++] = nl;
         }
+      }
+      // warp exclusive scan of the hit counts -> one atomicAdd per warp
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (total) {
+        unsigned base = 0;
+        if (lane == 31) base = atomicAdd(&cand_ctl[0], (unsigned)total);
+        base = __shfl_sync(0xffffffffu, base, 31) + (unsigned)(incl - cnt);
+        for (int j = 0; j < cnt; ++j) cands[base + j] = hit[j];
       }
     }
   }
-  // reuse slot S_TOP_ABOVE of this block's partial row
   __shared__ float red[LOSS_THREADS / 32];
-  float s = warp_sum(acc[0]);
+  const float s = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -300,97 +308,122 @@ dbloss_select_pass2_kernel(const float* __restrict__ preds, const float* __restr
   }
 }
 
-// exact select inside the tau bin (one CTA) + final losses for 'none'
-__global__ void __launch_bounds__(1024)
+// exact select inside the tau bin, grid-wide over the compacted candidates:
+//   level 2 histogram (bits 19..9) -> pick -> level 3 histogram (bits 8..0 of the matching prefix) + sum above -> pick.
+// hist2 / hist3 live behind hist1 in the workspace; sel_ctl: [0] = bin2, [1] = k_rem after level 2 (lo), [2] hi, [3] above lo, [4] above hi
+__global__ void __launch_bounds__(LOSS_THREADS)
+dbloss_l2hist_kernel(const unsigned* __restrict__ cand_ctl, const float* __restrict__ cands, unsigned* __restrict__ hist2) {
+  __shared__ unsigned sh[HIST2_BINS];
+  for (int i = threadIdx.x; i < HIST2_BINS; i += LOSS_THREADS) sh[i] = 0;
+  __syncthreads();
+  const unsigned n = ((int)cand_ctl[1] >= 0) ? cand_ctl[0] : 0u;
+  for (unsigned i = blockIdx.x * LOSS_THREADS + threadIdx.x; i < n; i += gridDim.x * LOSS_THREADS)
+    atomicAdd(&sh[(__float_as_uint(cands[i]) >> 9) & 0x7ffu], 1u);
+  __syncthreads();
+  for (int i = threadIdx.x; i < HIST2_BINS; i += LOSS_THREADS) { const unsigned c = sh[i]; if (c) atomicAdd(&hist2[i], c); }
+}
+
+// walk a histogram (in shared memory) from the top until k entries are covered; one warp, 64-bin chunks per step
+__device__ void pick_bin(const unsigned* sh, int nbins, long long k, int& bin, long long& above) {
+  long long acc = 0; int b = nbins - 1;
+  for (; b >= 0; --b) {
+    const long long c = sh[b];
+    if (acc + c >= k) break;
+    acc += c;
+  }
+  bin = b < 0 ? 0 : b; above = acc;
+}
+
+__global__ void __launch_bounds__(256)
+dbloss_pick2_kernel(const unsigned* __restrict__ cand_ctl, const unsigned* __restrict__ hist2, const DbbLossState* __restrict__ st,
+                    unsigned* __restrict__ sel_ctl) {
+  __shared__ unsigned sh[HIST2_BINS];
+  for (int i = threadIdx.x; i < HIST2_BINS; i += blockDim.x) sh[i] = hist2[i];
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const int tb = (int)cand_ctl[1];
+  if (tb < 0) { sel_ctl[0] = 0; sel_ctl[1] = sel_ctl[2] = sel_ctl[3] = sel_ctl[4] = 0; return; }
+  const long long above1 = ((long long)cand_ctl[3] << 32) | cand_ctl[2];
+  const long long krem = st->n_neg - above1;
+  int b2; long long a2;
+  pick_bin(sh, HIST2_BINS, krem, b2, a2);
+  const long long k3 = krem - a2, ab = above1 + a2;
+  sel_ctl[0] = (unsigned)b2;
+  sel_ctl[1] = (unsigned)(k3 & 0xffffffffll); sel_ctl[2] = (unsigned)(k3 >> 32);
+  sel_ctl[3] = (unsigned)(ab & 0xffffffffll); sel_ctl[4] = (unsigned)(ab >> 32);
+}
+
+__global__ void __launch_bounds__(LOSS_THREADS)
+dbloss_l3hist_kernel(const unsigned* __restrict__ cand_ctl, const float* __restrict__ cands, const unsigned* __restrict__ sel_ctl,
+                     unsigned* __restrict__ hist3, double* __restrict__ partials) {
+  __shared__ unsigned sh[HIST3_BINS];
+  __shared__ double red[LOSS_THREADS / 32];
+  for (int i = threadIdx.x; i < HIST3_BINS; i += LOSS_THREADS) sh[i] = 0;
+  __syncthreads();
+  const unsigned n = ((int)cand_ctl[1] >= 0) ? cand_ctl[0] : 0u;
+  const unsigned b2 = sel_ctl[0];
+  double acc = 0.0;   // candidates whose level-2 prefix is above the picked bin (all strictly above tau)
+  for (unsigned i = blockIdx.x * LOSS_THREADS + threadIdx.x; i < n; i += gridDim.x * LOSS_THREADS) {
+    const float c = cands[i];
+    const unsigned u = __float_as_uint(c), p2 = (u >> 9) & 0x7ffu;
+    if (p2 > b2) acc += (double)c;
+    else if (p2 == b2) atomicAdd(&sh[u & 0x1ffu], 1u);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  for (int i = threadIdx.x; i < HIST3_BINS; i += LOSS_THREADS) { const unsigned c = sh[i]; if (c) atomicAdd(&hist3[i], c); }
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < LOSS_THREADS / 32; ++w) t += red[w];
+    partials[(size_t)blockIdx.x * NSUM + S_TOP_CAND] = t;
+  }
+}
+
+// final pick (bits 8..0) + the five losses for 'none'
+__global__ void __launch_bounds__(512)
 dbloss_select_final_kernel(double* __restrict__ partials, int nblk, const unsigned* __restrict__ cand_ctl,
-                           const float* __restrict__ cands, LossParams lp, float* losses5, DbbLossState* st) {
-  __shared__ unsigned hist[HIST2_BINS];
+                           const unsigned* __restrict__ sel_ctl, const unsigned* __restrict__ hist3, LossParams lp,
+                           float* losses5, DbbLossState* st) {
+  __shared__ unsigned sh[HIST3_BINS];
   __shared__ double S[NSUM];
-  __shared__ double redd[32];
-  __shared__ long long sh_above;
-  __shared__ unsigned sh_prefix;     // resolved low 20 bits so far
-  __shared__ long long sh_krem;
   const int tid = threadIdx.x;
-  const unsigned ncand = cand_ctl[0];
   const int tb = (int)cand_ctl[1];
   if (tid < NSUM) S[tid] = st->sums[tid];
+  for (int i = tid; i < HIST3_BINS; i += blockDim.x) sh[i] = hist3[i];
   __syncthreads();
-  sum_partials(partials, nblk, S, S_TOP_ABOVE, S_TOP_ABOVE + 1);
+  sum_partials(partials, nblk, S, S_TOP_ABOVE, S_TOP_CAND + 1);
+  __syncthreads();
+  if (tid != 0) return;
   const long long n_pos = st->n_pos, n_neg = st->n_neg;
   const double D = (double)n_pos + (double)n_neg + (double)lp.eps;
   if (tb < 0) {
-    __syncthreads();
-    if (tid == 0) {
-      // tau = 0: every strictly positive entry is taken, the rest of the picks are zeros
-      long long nz = 0;   // number of strictly positive entries = cnt walked in finalize1
-      nz = ((long long)cand_ctl[3] << 32) | cand_ctl[2];
-      st->tau = 0.f; st->tau_bits = 0u;
-      st->n_above = n_neg > 0 ? nz : 0; st->n_tie = n_neg > 0 ? n_neg - nz : 0;
-      const double top = n_neg > 0 ? S[S_NEGL] : 0.0;
-      S[S_TOP_CAND] = 0.0; S[S_TOP_ABOVE] = top;
-      write_losses(S, (S[S_BCE_POS] + top) / D, lp, losses5, st, 1.0 / D);
-    }
+    // tau = 0: every strictly positive entry is taken, the rest of the picks are zeros
+    const long long nz = ((long long)cand_ctl[3] << 32) | cand_ctl[2];
+    st->tau = 0.f; st->tau_bits = 0u;
+    st->n_above = n_neg > 0 ? nz : 0; st->n_tie = n_neg > 0 ? n_neg - nz : 0;
+    const double top = n_neg > 0 ? S[S_NEGL] : 0.0;
+    S[S_TOP_CAND] = 0.0; S[S_TOP_ABOVE] = top;
+    write_losses(S, (S[S_BCE_POS] + top) / D, lp, losses5, st, 1.0 / D);
     return;
   }
-  if (tid == 0) {
-    sh_above = ((long long)cand_ctl[3] << 32) | cand_ctl[2];
-    sh_krem = n_neg - sh_above;      // 1 <= k_rem <= ncand
-    sh_prefix = 0u;
-  }
-  // ---- level 2: bits 19..9
-  for (int i = tid; i < HIST2_BINS; i += blockDim.x) hist[i] = 0;
-  __syncthreads();
-  for (unsigned i = tid; i < ncand; i += blockDim.x) atomicAdd(&hist[(__float_as_uint(cands[i]) >> 9) & 0x7ffu], 1u);
-  __syncthreads();
-  if (tid == 0) {
-    long long acc = 0, kr = sh_krem; int b2 = 0;
-    for (int b = HIST2_BINS - 1; b >= 0; --b) {
-      const long long c = hist[b];
-      if (acc + c >= kr) { b2 = b; break; }
-      acc += c;
-    }
-    sh_above += acc; sh_krem = kr - acc; sh_prefix = (unsigned)b2 << 9;
-  }
-  __syncthreads();
-  const unsigned p2 = sh_prefix >> 9;
-  // ---- level 3: bits 8..0
-  for (int i = tid; i < HIST3_BINS; i += blockDim.x) hist[i] = 0;
-  __syncthreads();
-  for (unsigned i = tid; i < ncand; i += blockDim.x) {
-    const unsigned u = __float_as_uint(cands[i]);
-    if (((u >> 9) & 0x7ffu) == p2) atomicAdd(&hist[u & 0x1ffu], 1u);
-  }
-  __syncthreads();
-  if (tid == 0) {
-    long long acc = 0, kr = sh_krem; int b3 = 0;
-    for (int b = HIST3_BINS - 1; b >= 0; --b) {
-      const long long c = hist[b];
-      if (acc + c >= kr) { b3 = b; break; }
-      acc += c;
-    }
-    sh_above += acc; sh_krem = kr - acc; sh_prefix |= (unsigned)b3;
-  }
-  __syncthreads();
-  const unsigned tau_bits = ((unsigned)tb << 20) | sh_prefix;
+  const unsigned b2 = sel_ctl[0];
+  const long long k3 = ((long long)sel_ctl[2] << 32) | sel_ctl[1];
+  long long above = ((long long)sel_ctl[4] << 32) | sel_ctl[3];
+  int b3; long long a3;
+  pick_bin(sh, HIST3_BINS, k3, b3, a3);
+  above += a3;
+  const unsigned prefix = ((unsigned)tb << 20) | (b2 << 9);
+  const unsigned tau_bits = prefix | (unsigned)b3;
   const float tau = __uint_as_float(tau_bits);
-  // ---- sum of candidates strictly above tau
-  double s = 0.0;
-  for (unsigned i = tid; i < ncand; i += blockDim.x) {
-    const float c = cands[i];
-    if (c > tau) s += (double)c;
-  }
-  s = warp_sum(s);
-  if ((tid & 31) == 0) redd[tid >> 5] = s;
-  __syncthreads();
-  if (tid == 0) {
-    double t = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += redd[w];
-    S[S_TOP_CAND] = t;
-    const long long n_above = sh_above, n_tie = n_neg - n_above;
-    st->tau = tau; st->tau_bits = tau_bits; st->n_above = n_above; st->n_tie = n_tie;
-    const double top = S[S_TOP_ABOVE] + t + (double)tau * (double)n_tie;
-    write_losses(S, (S[S_BCE_POS] + top) / D, lp, losses5, st, 1.0 / D);
-  }
+  // candidates sharing the 23-bit prefix and a larger low field are single values: count x value is exact
+  double same_prefix = 0.0;
+  for (int b = HIST3_BINS - 1; b > b3; --b) same_prefix += (double)sh[b] * (double)__uint_as_float(prefix | (unsigned)b);
+  const long long n_tie = n_neg - above;
+  st->tau = tau; st->tau_bits = tau_bits; st->n_above = above; st->n_tie = n_tie;
+  S[S_TOP_CAND] += same_prefix;
+  const double top = S[S_TOP_ABOVE] + S[S_TOP_CAND] + (double)tau * (double)n_tie;
+  write_losses(S, (S[S_BCE_POS] + top) / D, lp, losses5, st, 1.0 / D);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -474,7 +507,7 @@ extern "C" size_t dbb_dbloss_workspace(int64_t n, int c, int64_t h, int64_t w, i
   (void)c;
   const int64_t px = n * h * w;
   const int grid = loss_grid(px);
-  size_t b = align_up(sizeof(double) * NSUM * (size_t)grid, 256) + sizeof(unsigned) * HIST1_BINS + 256;
+  size_t b = align_up(sizeof(double) * NSUM * (size_t)grid, 256) + LOSS_CTL_BYTES;
   if (reduction == 1) b += sizeof(float) * (size_t)px;
   return align_up(b, 256);
 }
@@ -485,12 +518,15 @@ static int loss_fwd_impl(const float* preds, const float* gts, int64_t n, int c,
   const int64_t px = n * hw;
   const int grid = loss_grid(px);
   LossWs ws = carve(workspace, grid, px);
-  if (SELECT) DBB_CUDA(cudaMemsetAsync(ws.hist1, 0, sizeof(unsigned) * HIST1_BINS + 256, s));
+  if (SELECT) DBB_CUDA(cudaMemsetAsync(ws.hist1, 0, LOSS_CTL_BYTES, s));
   DBB_LAUNCH("dbloss_reduce", s, dbloss_reduce_kernel<VEC, HAS_B, SELECT><<<grid, LOSS_THREADS, 0, s>>>(preds, gts, n, hw, c, ws.partials, ws.hist1));
   DBB_LAUNCH("dbloss_finalize1", s, dbloss_finalize1_kernel<SELECT><<<1, 256, 0, s>>>(ws.partials, grid, ws.hist1, ws.cand_count, lp, losses5, state));
   if (SELECT) {
     DBB_LAUNCH("dbloss_select_pass2", s, dbloss_select_pass2_kernel<VEC><<<grid, LOSS_THREADS, 0, s>>>(preds, gts, n, hw, c, ws.partials, ws.cand_count, ws.cands));
-    DBB_LAUNCH("dbloss_select_final", s, dbloss_select_final_kernel<<<1, 1024, 0, s>>>(ws.partials, grid, ws.cand_count, ws.cands, lp, losses5, state));
+    DBB_LAUNCH("dbloss_l2hist", s, dbloss_l2hist_kernel<<<grid, LOSS_THREADS, 0, s>>>(ws.cand_count, ws.cands, ws.hist2));
+    DBB_LAUNCH("dbloss_pick2", s, dbloss_pick2_kernel<<<1, 256, 0, s>>>(ws.cand_count, ws.hist2, state, ws.sel_ctl));
+    DBB_LAUNCH("dbloss_l3hist", s, dbloss_l3hist_kernel<<<grid, LOSS_THREADS, 0, s>>>(ws.cand_count, ws.cands, ws.sel_ctl, ws.hist3, ws.partials));
+    DBB_LAUNCH("dbloss_select_final", s, dbloss_select_final_kernel<<<1, 512, 0, s>>>(ws.partials, grid, ws.cand_count, ws.sel_ctl, ws.hist3, lp, losses5, state));
   }
   return DBB_OK;
 }

@@ -134,29 +134,39 @@ __global__ void __launch_bounds__(EW_THREADS) bn_stats_kernel(const bf16* __rest
   reduce_groups_store<2>(acc, c, partials + (size_t)blockIdx.x * 2 * c);
 }
 
+// one warp per channel: lanes stride over the per-block partials (fixed order -> bitwise reproducible)
+__device__ __forceinline__ void warp_sum_partials(const float* __restrict__ partials, int nblk, int c, int ch, double& s, double& q) {
+  const int lane = threadIdx.x & 31;
+  s = 0.0; q = 0.0;
+  for (int b = lane; b < nblk; b += 32) {
+    s += (double)partials[(size_t)b * 2 * c + ch];
+    q += (double)partials[(size_t)b * 2 * c + c + ch];
+  }
+  s = warp_sum(s); q = warp_sum(q);
+}
+
 __global__ void bn_finalize_train_kernel(const float* __restrict__ partials, int nblk, int c, int coff, int cn, double count,
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          float* __restrict__ rmean, float* __restrict__ rvar, float momentum, float eps,
                                          float* __restrict__ stats4) {
-  int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= cn) return;
-  gamma += ch; beta += ch; if (rmean) { rmean += ch; rvar += ch; }
-  ch += coff;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblk; ++b) { s += (double)partials[(size_t)b * 2 * c + ch]; q += (double)partials[(size_t)b * 2 * c + c + ch]; }
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= cn) return;
+  const int ch = coff + i;
+  double s, q;
+  warp_sum_partials(partials, nblk, c, ch, s, q);
+  if ((threadIdx.x & 31) != 0) return;
   const double mean = s / count;
   double var = q / count - mean * mean;
   if (var < 0.0) var = 0.0;
   const double invstd = 1.0 / sqrt(var + (double)eps);
-  const float sc = (float)((double)gamma[0] * invstd);
-  stats4[ch] = sc;
-  stats4[c + ch] = (float)((double)beta[0] - mean * (double)gamma[0] * invstd);
+  stats4[ch] = (float)((double)gamma[i] * invstd);
+  stats4[c + ch] = (float)((double)beta[i] - mean * (double)gamma[i] * invstd);
   stats4[2 * c + ch] = (float)mean;
   stats4[3 * c + ch] = (float)invstd;
   if (rmean) {   // running stats: unbiased variance, momentum 0.1 (torch.nn.BatchNorm2d)
     const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
-    rmean[0] = (float)((1.0 - momentum) * (double)rmean[0] + momentum * mean);
-    rvar[0] = (float)((1.0 - momentum) * (double)rvar[0] + momentum * unb);
+    rmean[i] = (float)((1.0 - momentum) * (double)rmean[i] + momentum * mean);
+    rvar[i] = (float)((1.0 - momentum) * (double)rvar[i] + momentum * unb);
   }
 }
 
@@ -225,11 +235,12 @@ bn_bwd_reduce_kernel(const bf16* __restrict__ dout, int dout_ctotal, int dout_co
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nblk, int c, int coff, int cn, double count,
                                        const float* __restrict__ gamma, const float* __restrict__ stats4,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef3) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= cn) return;
   const int ch = coff + i;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblk; ++b) { s += (double)partials[(size_t)b * 2 * c + ch]; q += (double)partials[(size_t)b * 2 * c + c + ch]; }
+  double s, q;
+  warp_sum_partials(partials, nblk, c, ch, s, q);
+  if ((threadIdx.x & 31) != 0) return;
   if (dgamma) dgamma[i] = (float)q;
   if (dbeta) dbeta[i] = (float)s;
   coef3[ch] = gamma[i] * stats4[3 * c + ch];
@@ -277,11 +288,12 @@ __global__ void __launch_bounds__(EW_THREADS) colsum_kernel(const bf16* __restri
   reduce_groups_store<1>(acc, c, partials + (size_t)blockIdx.x * c);
 }
 __global__ void colsum_finalize_kernel(const float* __restrict__ partials, int nblk, int c, float* __restrict__ out) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (ch >= c) return;
   double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += (double)partials[(size_t)b * c + ch];
-  out[ch] = (float)s;
+  for (int b = threadIdx.x & 31; b < nblk; b += 32) s += (double)partials[(size_t)b * c + ch];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) out[ch] = (float)s;
 }
 
 static int check_c(int c) { return (c % 8 == 0 && c >= 8 && c <= 2048 && EW_THREADS % (c / 8) == 0) ? 0 : 1; }
@@ -294,7 +306,7 @@ int bn_stats(const bf16* z, int64_t P, int c, float* partials, int* nblk, cudaSt
 }
 int bn_finalize_train(const float* partials, int nblk, int c, int coff, int cn, int64_t count, const float* gamma, const float* beta,
                       float* running_mean, float* running_var, float momentum, float eps, float* stats4, cudaStream_t s) {
-  DBB_LAUNCH("bn_finalize_train", s, bn_finalize_train_kernel<<<(cn + 127) / 128, 128, 0, s>>>(partials, nblk, c, coff, cn, (double)count, gamma, beta, running_mean, running_var, momentum, eps, stats4));
+  DBB_LAUNCH("bn_finalize_train", s, bn_finalize_train_kernel<<<(cn + 7) / 8, 256, 0, s>>>(partials, nblk, c, coff, cn, (double)count, gamma, beta, running_mean, running_var, momentum, eps, stats4));
   return DBB_OK;
 }
 int bn_finalize_eval(int c, int coff, int cn, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
@@ -322,7 +334,7 @@ int bn_bwd_reduce(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* 
 }
 int bn_bwd_finalize(const float* partials, int nblk, int c, int coff, int cn, int64_t count, const float* gamma, const float* stats4,
                     float* dgamma, float* dbeta, float* coef3, cudaStream_t s) {
-  DBB_LAUNCH("bn_bwd_finalize", s, bn_bwd_finalize_kernel<<<(cn + 127) / 128, 128, 0, s>>>(partials, nblk, c, coff, cn, (double)count, gamma, stats4, dgamma, dbeta, coef3));
+  DBB_LAUNCH("bn_bwd_finalize", s, bn_bwd_finalize_kernel<<<(cn + 7) / 8, 256, 0, s>>>(partials, nblk, c, coff, cn, (double)count, gamma, stats4, dgamma, dbeta, coef3));
   return DBB_OK;
 }
 int bn_bwd_apply(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
@@ -336,7 +348,7 @@ int bias_grad(const bf16* dz, int64_t P, int c, float* partials, float* dbias, c
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bias_grad: channel count");
   const int nblk = ew_blocks(P, c);
   DBB_LAUNCH("colsum", s, colsum_kernel<<<nblk, EW_THREADS, 0, s>>>(dz, P, c, partials));
-  DBB_LAUNCH("colsum_finalize", s, colsum_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(partials, nblk, c, dbias));
+  DBB_LAUNCH("colsum_finalize", s, colsum_finalize_kernel<<<(c + 7) / 8, 256, 0, s>>>(partials, nblk, c, dbias));
   return DBB_OK;
 }
 

@@ -223,6 +223,7 @@ head_tail_bwd_reduce_kernel(const bf16* __restrict__ zt, int n_img, int h2, int 
   }
 }
 
+// one warp per channel (128 warps) + one warp per bias; lanes stride over the per-block partials in a fixed order
 __global__ void head_tail_bwd_finalize_kernel(const float* __restrict__ partials, int nblk, double count,
                                               const float* __restrict__ gamma_b, const float* __restrict__ gamma_t,
                                               const float* __restrict__ stats4, float* __restrict__ dgamma_b,
@@ -230,12 +231,27 @@ __global__ void head_tail_bwd_finalize_kernel(const float* __restrict__ partials
                                               float* __restrict__ dbeta_t, float* __restrict__ coef3,
                                               float* __restrict__ dw2b, float* __restrict__ dw2t, float* __restrict__ db2b,
                                               float* __restrict__ db2t) {
-  const int ch = threadIdx.x;   // 128 threads
+  const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // 0..129
+  const int lane = threadIdx.x & 31;
   const size_t stride = 128 * HT_NACC + 2;
+  if (ch >= 130) return;
+  if (ch >= 128) {
+    double s = 0.0;
+    for (int b = lane; b < nblk; b += 32) s += (double)partials[(size_t)b * stride + 128 * HT_NACC + (ch - 128)];
+    s = warp_sum(s);
+    if (lane == 0) ((ch - 128) ? db2t : db2b)[0] = (float)s;
+    return;
+  }
   double acc[HT_NACC];
+#pragma unroll
   for (int q = 0; q < HT_NACC; ++q) acc[q] = 0.0;
-  for (int b = 0; b < nblk; ++b)
+  for (int b = lane; b < nblk; b += 32) {
+#pragma unroll
     for (int q = 0; q < HT_NACC; ++q) acc[q] += (double)partials[(size_t)b * stride + ch * HT_NACC + q];
+  }
+#pragma unroll
+  for (int q = 0; q < HT_NACC; ++q) acc[q] = warp_sum(acc[q]);
+  if (lane != 0) return;
   const int br = ch >> 6, c = ch & 63;
   float* dw2 = br ? dw2t : dw2b;
   for (int t = 0; t < 4; ++t) dw2[c * 4 + t] = (float)acc[t];
@@ -245,11 +261,6 @@ __global__ void head_tail_bwd_finalize_kernel(const float* __restrict__ partials
   coef3[ch] = g * stats4[384 + ch];
   coef3[128 + ch] = (float)(acc[4] / count);
   coef3[256 + ch] = (float)(acc[5] / count);
-  if (ch < 2) {
-    double s = 0.0;
-    for (int b = 0; b < nblk; ++b) s += (double)partials[(size_t)b * stride + 128 * HT_NACC + ch];
-    (ch ? db2t : db2b)[0] = (float)s;
-  }
 }
 
 __global__ void __launch_bounds__(HT_THREADS)
@@ -334,7 +345,7 @@ int head_tail_bwd_reduce(const bf16* zt, int n, int h2, int w2, const float* sta
 int head_tail_bwd_finalize(const float* partials, int nblk, int64_t count, const float* gamma_b, const float* gamma_t,
                            const float* stats4, float* dgamma_b, float* dbeta_b, float* dgamma_t, float* dbeta_t,
                            float* coef3, float* dw2b, float* dw2t, float* db2b, float* db2t, cudaStream_t s) {
-  DBB_LAUNCH("head_tail_bwd_finalize", s, head_tail_bwd_finalize_kernel<<<1, 128, 0, s>>>(partials, nblk, (double)count, gamma_b, gamma_t, stats4, dgamma_b, dbeta_b,
+  DBB_LAUNCH("head_tail_bwd_finalize", s, head_tail_bwd_finalize_kernel<<<(130 + 7) / 8, 256, 0, s>>>(partials, nblk, (double)count, gamma_b, gamma_t, stats4, dgamma_b, dbeta_b,
                                                   dgamma_t, dbeta_t, coef3, dw2b, dw2t, db2b, db2t));
   return DBB_OK;
 }
