@@ -113,6 +113,10 @@ int dbb_binarize_ccl_score(const float* pred, int64_t n, int c, int64_t h, int64
                            uint8_t* bitmap, int32_t* labels, DbbCandidate* cands, int32_t* n_cands, int max_cands,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+
+/* bitmap = pred[:, 0] > thresh on its own (src/postprocess.py:51-52) */
+int dbb_binarize(const float* pred, int64_t n, int c, int64_t h, int64_t w, float thresh, uint8_t* bitmap, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Whole-network executor: DBTextModel forward / backward  (replaces src/models.py:34-48 with
  * src/modules/resnet.py:231-242, segmentation_body.py:64-87, segmentation_head.py:35-45)
@@ -168,6 +172,42 @@ size_t dbb_conv2d_workspace(int kind, int64_t n, int64_t h, int64_t wdt, int cin
 int dbb_conv2d_wgrad(int kind, const void* x_nhwc_bf16, const void* dy_nhwc_bf16, float* dw,
                      int64_t n, int64_t h, int64_t wdt, int cin, int cout, int ksize, int stride, int pad,
                      void* workspace, size_t workspace_bytes, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------
+ * Memory-bound operators on NHWC bf16 activations (parity-tested in isolation; also the building blocks of the executor)
+ * ------------------------------------------------------------------------------------------ */
+size_t dbb_ops_workspace(void);
+/* BatchNorm2d [+ residual] [+ ReLU]  (src/modules/basic.py:34-35, resnet.py:74-90).  stats4 out: [scale|shift|mean|invstd] */
+int dbb_bn_fwd(const void* z, int64_t pixels, int c, const float* gamma, const float* beta, float* running_mean,
+               float* running_var, int training, const void* residual, int relu, void* out, float* stats4,
+               void* workspace, size_t workspace_bytes, void* stream);
+int dbb_bn_bwd(const void* dout, const void* act, const void* z, int64_t pixels, int c, const float* gamma,
+               const float* stats4, void* dz, void* dres, float* dgamma, float* dbeta, void* workspace,
+               size_t workspace_bytes, void* stream);
+/* MaxPool2d(3, 2, 1)  (src/modules/resnet.py:175) */
+int dbb_maxpool_fwd(const void* x, int64_t n, int64_t h, int64_t w, int c, void* y, uint8_t* argmax, void* stream);
+int dbb_maxpool_bwd(const void* dy, const uint8_t* argmax, int64_t n, int64_t h, int64_t w, int c, void* dx, void* stream);
+/* FPN._upsample_add / _upsample_cat: F.interpolate(mode='nearest')  (src/modules/segmentation_body.py:79-87) */
+int dbb_upsample_add_fwd(const void* xs, int64_t hs, int64_t ws, const void* y, int64_t n, int64_t h, int64_t w, int c,
+                         void* out, void* stream);
+int dbb_upsample_into(const void* xs, int64_t hs, int64_t ws, int64_t n, int64_t h, int64_t w, int c, void* dst,
+                      int dst_ctotal, int dst_coff, void* stream);
+int dbb_upsample_bwd(const void* d_big, int big_ctotal, int big_coff, int64_t n, int64_t h, int64_t w, int c, void* d_xs,
+                     int64_t hs, int64_t ws, int accumulate, void* stream);
+/* fused DBHead tail: BN+ReLU -> ConvTranspose2d(64,1,2,2) x2 -> Sigmoid -> step  (src/modules/segmentation_head.py:28-29,39-44,72-76,106-108) */
+int dbb_head_tail_fwd(const void* zt, int64_t n, int64_t h2, int64_t w2, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, int training, const float* w2b, const float* w2t,
+                      const float* b2b, const float* b2t, float k, int out_c, float* out, float* stats4,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int dbb_head_tail_bwd(const void* zt, int64_t n, int64_t h2, int64_t w2, const float* gamma, const float* stats4,
+                      const float* w2b, const float* w2t, const float* out, const float* dout, float k, void* d_zt,
+                      float* dgamma, float* dbeta, float* dw2b, float* dw2t, float* db2b, float* db2t,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* per-kernel CUDA-event timing on the launching stream (bench.py roofline); report is JSON text */
+void dbb_profile_enable(int on);
+size_t dbb_profile_report(char* buf, size_t cap);
 
 /* layout helpers: NCHW float32 <-> NHWC bf16 */
 int dbb_nchw_f32_to_nhwc_bf16(const float* x, void* y, int64_t n, int c, int64_t h, int64_t w, void* stream);
