@@ -31,6 +31,7 @@ def parse():
     ap.add_argument("--reduction", default="none", choices=["none", "mean"],
                     help="'none' = true top-k OHEM (BASELINE config 2); 'mean' = the reference's shipped (degenerate) default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-kernels", default=None, help="write the full per-kernel timing table (JSON) to this path")
     ap.add_argument("--cpu-batch", type=int, default=2, help="images in the bounded CPU sample")
     return ap.parse_args()
 
@@ -278,6 +279,9 @@ def run_ours(args):
             table.append({"name": k["name"], "launches_per_step": k["launches"] / nprof, "ms_per_step": k["ms"] / nprof,
                           "share": k["ms"] / tot, "tflops": (fl / avg / 1e9) if fl else None})
         table.sort(key=lambda r: -r["ms_per_step"])
+        if args.dump_kernels:
+            with open(args.dump_kernels, "w") as f:
+                json.dump(table, f, indent=1)
         dom = next(r for r in table if r["tflops"] is not None)
         roofline = {"bound": "tensor", "kernel": dom["name"], "achieved": dom["tflops"], "peak": peaks["tflops_sustained"],
                     "unit": "TFLOP/s", "frac": dom["tflops"] / peaks["tflops_sustained"], "traffic": None,

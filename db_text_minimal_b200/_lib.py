@@ -85,6 +85,7 @@ def lib():
     sig("dbb_net_debug_read", i32, [vp, C.c_char_p, vp, vp, vp])
     sig("dbb_conv2d", i32, [i32, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, i32, vp, sz, vp])
     sig("dbb_conv2d_workspace", sz, [i32, i64, i64, i64, i32, i32, i32, i32, i32])
+    sig("dbb_conv2d_wgrad_workspace", sz, [])
     sig("dbb_conv2d_wgrad", i32, [i32, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, i32, vp, sz, vp])
     sig("dbb_nchw_f32_to_nhwc_bf16", i32, [vp, vp, i64, i32, i64, i64, vp])
     sig("dbb_nhwc_bf16_to_nchw_f32", i32, [vp, vp, i64, i32, i64, i64, vp])

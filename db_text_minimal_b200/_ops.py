@@ -46,9 +46,11 @@ def conv2d_wgrad_raw(kind, x_nhwc, dy_nhwc, n, h, w, cin, cout, ks, stride, pad)
     _lib.require_cuda(x_nhwc, dy_nhwc)
     shape = (cout, cin, ks, ks) if kind == 0 else (cin, cout, 2, 2)
     dw = torch.empty(shape, dtype=torch.float32, device=x_nhwc.device)
+    wsb = L.dbb_conv2d_wgrad_workspace()
+    ws = torch.empty(wsb, dtype=torch.uint8, device=x_nhwc.device)
     with torch.cuda.device(x_nhwc.device):
         _lib.check(L.dbb_conv2d_wgrad(kind, x_nhwc.data_ptr(), dy_nhwc.data_ptr(), dw.data_ptr(), n, h, w, cin, cout, ks,
-                                      stride, pad, None, 0, _lib.stream_ptr()), "dbb_conv2d_wgrad")
+                                      stride, pad, ws.data_ptr(), wsb, _lib.stream_ptr()), "dbb_conv2d_wgrad")
     return dw
 
 

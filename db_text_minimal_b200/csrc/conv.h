@@ -37,6 +37,7 @@ struct IgemmPlan {
   int out_coff;            // channel offset inside Y's channel dimension
   const float* bias;       // may be null
   int accumulate;          // 1: Y += result (gradient fan-in), 0: overwrite
+  int cls_cols;            // > 0: pixel-shuffle epilogue, GEMM column = class*cls_cols + channel (ConvTranspose2d k2 s2)
 };
 
 // weight packing: fp32 parameter -> bf16 GEMM B matrix [rows][K] (K-major)
@@ -47,6 +48,12 @@ struct IgemmPlan {
 //   mode 4: conv1 7x7/2 OIHW (64,3,7,7)      -> [co][kh2(4)][kw2(4)][16]  space-to-depth form, K = 256
 // co_total / co_off: (modes 1 and 3) the packed matrix is co_total wide and this tensor fills columns [co_off, co_off+co_n)
 int pack_weights(int mode, const float* w, bf16* out, int co_n, int ci_n, int kh, int kw, cudaStream_t s, int co_total = 0, int co_off = 0);
+
+// batched packing: all weight tensors of the network in one or two launches
+struct PackJob { const float* w; bf16* out; int mode, co_n, ci_n, kh, kw, co_total, co_off; };
+constexpr int PACK_BATCH = 48;
+struct PackBatch { int njobs; PackJob jobs[PACK_BATCH]; };
+int pack_weights_batch(const PackBatch& b, cudaStream_t s);
 
 int igemm_plan_init(IgemmPlan* p, const bf16* x, int n, int h, int w, int c_total, int c_off, int cin,
                     const bf16* wp, int k_total, int w_rows, int block_n);
@@ -65,10 +72,14 @@ struct WgradPlan {
   int m_total, n_total;    // GEMM M (rows of dW), N
   int m_tile, n_tile;      // 64|128, 64|128|256
   int split_k;
-  float* dw;               // fp32, layout [m][n][tap] (== OIHW for Conv2d, (ci,co,a,b) for ConvT); atomically accumulated
+  float* dw;               // fp32, layout [m][n][tap] (== OIHW for Conv2d, (ci,co,a,b) for ConvT); overwritten
+  float* ws;               // split-K partials [split][tap][m_pad][n_pad] fp32
+  int m_pad, n_pad;
   int tap_stride;          // ntaps of the destination layout
 };
 int wgrad_launch(const WgradPlan& p, cudaStream_t s);
+size_t wgrad_scratch_bytes(const WgradPlan& p);
+constexpr size_t WGRAD_SCRATCH_BYTES = 96ull << 20;   // shared split-K scratch the executor reserves
 
 int encode_tmap_raw4(CUtensorMap* m, const bf16* base, const cuuint64_t dims[4], const cuuint64_t strides_bytes[3],
                      const cuuint32_t box[4]);

@@ -83,25 +83,22 @@ int conv_dgrad(const ConvGeom& g, const bf16* dy, const bf16* wp_t, bf16* dx, cu
 
 int convt_fprop(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const bf16* wp_cls, const float* bias, bf16* y,
                 int y_ctotal, int y_coff, cudaStream_t s) {
-  // ConvTranspose2d(k=2, s=2): y[n,2i+a,2j+b,co] = sum_ci x[n,i,j,ci] * W[ci,co,a,b] + bias[co]
-  for (int cls = 0; cls < 4; ++cls) {
-    IgemmPlan p;
-    memset(&p, 0, sizeof(p));
-    p.mn = g.n; p.mh = g.h; p.mw = g.w;
-    p.in_sh = p.in_sw = 1;
-    p.ntaps = 1; p.dh[0] = 0; p.dw[0] = 0; p.wtap[0] = 0;
-    p.cout = g.cout;
-    p.y = y; p.out_h = 2 * g.h; p.out_w = 2 * g.w; p.out_c = y_ctotal; p.out_coff = y_coff;
-    p.out_sh = p.out_sw = 2; p.out_oh = cls >> 1; p.out_ow = cls & 1;
-    p.bias = bias;
-    const int64_t m_tiles = ((int64_t)g.n * g.h * g.w + 127) / 128;
-    int rc = igemm_plan_init(&p, x, g.n, g.h, g.w, x_ctotal, x_coff, g.cin, wp_cls + (size_t)cls * g.cout * g.cin, g.cin, g.cout,
-                             pick_block_n(g.cout, m_tiles));
-    if (rc) return rc;
-    rc = igemm_launch(p, s);
-    if (rc) return rc;
-  }
-  return DBB_OK;
+  // ConvTranspose2d(k=2, s=2): y[n,2i+a,2j+b,co] = sum_ci x[n,i,j,ci] * W[ci,co,a,b] + bias[co].
+  // ONE GEMM [pixels, cin] x [cin, 4*cout] (packed weights are [class][co][ci] = 4*cout rows) with a pixel-shuffle epilogue.
+  IgemmPlan p;
+  memset(&p, 0, sizeof(p));
+  p.mn = g.n; p.mh = g.h; p.mw = g.w;
+  p.in_sh = p.in_sw = 1;
+  p.ntaps = 1; p.dh[0] = 0; p.dw[0] = 0; p.wtap[0] = 0;
+  p.cout = 4 * g.cout;
+  p.cls_cols = g.cout;
+  p.y = y; p.out_h = 2 * g.h; p.out_w = 2 * g.w; p.out_c = y_ctotal; p.out_coff = y_coff;
+  p.out_sh = p.out_sw = 2; p.out_oh = p.out_ow = 0;
+  p.bias = bias;
+  const int64_t m_tiles = ((int64_t)g.n * g.h * g.w + 127) / 128;
+  int rc = igemm_plan_init(&p, x, g.n, g.h, g.w, x_ctotal, x_coff, g.cin, wp_cls, g.cin, 4 * g.cout, pick_block_n(4 * g.cout, m_tiles));
+  if (rc) return rc;
+  return igemm_launch(p, s);
 }
 
 int convt_dgrad(const ConvGeom& g, const bf16* dy, int dy_ctotal, int dy_coff, const bf16* wp_t, bf16* dx, int dx_ctotal,
@@ -122,24 +119,40 @@ int convt_dgrad(const ConvGeom& g, const bf16* dy, int dy_ctotal, int dy_coff, c
   return igemm_launch(p, s);
 }
 
-static int pick_split_k(int64_t out_tiles, int total_pixel_tiles) {
+// split-K policy: enough CTAs to fill the GPU, but at least 8 k-iterations per CTA and partials that fit the scratch
+static int pick_split_k(int64_t out_tiles, int total_pixel_tiles, size_t tile_bytes_all, size_t scratch_bytes) {
   int64_t want = (2 * DBB_NUM_SMS + out_tiles - 1) / out_tiles;
-  if (want < 1) want = 1;
+  const int64_t cap_k = total_pixel_tiles / 8 > 1 ? total_pixel_tiles / 8 : 1;
+  const int64_t cap_ws = tile_bytes_all ? (int64_t)(scratch_bytes / tile_bytes_all) : 1;
+  if (want > cap_k) want = cap_k;
+  if (want > cap_ws) want = cap_ws;
   if (want > total_pixel_tiles) want = total_pixel_tiles;
+  if (want < 1) want = 1;
   return (int)want;
 }
 
+static int wgrad_finish_plan(WgradPlan& p, float* scratch, size_t scratch_bytes) {
+  const int m_tiles = (p.m_total + 127) / 128, n_tiles = (p.n_total + p.n_tile - 1) / p.n_tile;
+  p.m_pad = m_tiles * 128; p.n_pad = n_tiles * p.n_tile;
+  const size_t one = (size_t)p.ntaps * p.m_pad * p.n_pad * sizeof(float);
+  if (!scratch || scratch_bytes < one) return set_error(DBB_EWORKSPACE, "wgrad: split-K scratch too small");
+  p.split_k = pick_split_k((int64_t)p.ntaps * m_tiles * n_tiles, p.tiles_n * p.tiles_h * p.tiles_w, one, scratch_bytes);
+  p.ws = scratch;
+  return DBB_OK;
+}
+
 static int wgrad_common(WgradPlan& p, const bf16* a, int a_n, int a_h, int a_w, int a_ctotal, int a_coff, int a_c,
-                        const bf16* b, int b_n, int b_h, int b_w, int b_ctotal, int b_coff, int b_c, cudaStream_t s) {
+                        const bf16* b, int b_n, int b_h, int b_w, int b_ctotal, int b_coff, int b_c, float* scratch,
+                        size_t scratch_bytes, cudaStream_t s) {
   choose_box(64, p.mn, p.mh, p.mw, &p.bn, &p.bh, &p.bw);
   p.tiles_n = (p.mn + p.bn - 1) / p.bn;
   p.tiles_h = (p.mh + p.bh - 1) / p.bh;
   p.tiles_w = (p.mw + p.bw - 1) / p.bw;
   p.m_tile = 128;
   p.n_tile = p.n_total >= 256 ? 256 : (p.n_total >= 128 ? 128 : 64);
-  const int m_tiles = (p.m_total + 127) / 128, n_tiles = (p.n_total + p.n_tile - 1) / p.n_tile;
-  p.split_k = pick_split_k((int64_t)p.ntaps * m_tiles * n_tiles, p.tiles_n * p.tiles_h * p.tiles_w);
-  int rc = encode_tmap_nhwc(&p.tmap_a, a, a_n, a_h, a_w, a_ctotal, a_coff, a_c, p.bn, p.bh, p.bw, p.a_sh, p.a_sw);
+  int rc = wgrad_finish_plan(p, scratch, scratch_bytes);
+  if (rc) return rc;
+  rc = encode_tmap_nhwc(&p.tmap_a, a, a_n, a_h, a_w, a_ctotal, a_coff, a_c, p.bn, p.bh, p.bw, p.a_sh, p.a_sw);
   if (rc) return rc;
   rc = encode_tmap_nhwc(&p.tmap_b, b, b_n, b_h, b_w, b_ctotal, b_coff, b_c, p.bn, p.bh, p.bw, p.b_sh, p.b_sw);
   if (rc) return rc;
@@ -147,10 +160,9 @@ static int wgrad_common(WgradPlan& p, const bf16* a, int a_n, int a_h, int a_w, 
 }
 
 int conv_wgrad(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const bf16* dy, int dy_ctotal, int dy_coff, float* dw,
-               cudaStream_t s) {
+               float* scratch, size_t scratch_bytes, cudaStream_t s) {
   // dW[co,ci,kh,kw] = sum_{n,i,j} dy[n,i,j,co] * x[n, i*s+kh-pad, j*s+kw-pad, ci]
   const int ho = g.out_h(), wo = g.out_w();
-  DBB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g.cout * g.cin * g.ks * g.ks, s));
   WgradPlan p;
   memset(&p, 0, sizeof(p));
   p.mn = g.n; p.mh = ho; p.mw = wo;
@@ -163,13 +175,12 @@ int conv_wgrad(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const
     }
   p.m_total = g.cout; p.n_total = g.cin;
   p.dw = dw; p.tap_stride = p.ntaps;
-  return wgrad_common(p, dy, g.n, ho, wo, dy_ctotal, dy_coff, g.cout, x, g.n, g.h, g.w, x_ctotal, x_coff, g.cin, s);
+  return wgrad_common(p, dy, g.n, ho, wo, dy_ctotal, dy_coff, g.cout, x, g.n, g.h, g.w, x_ctotal, x_coff, g.cin, scratch, scratch_bytes, s);
 }
 
 int convt_wgrad(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const bf16* dy, int dy_ctotal, int dy_coff, float* dw,
-                cudaStream_t s) {
+                float* scratch, size_t scratch_bytes, cudaStream_t s) {
   // dW[ci,co,a,b] = sum_{n,i,j} x[n,i,j,ci] * dy[n,2i+a,2j+b,co]
-  DBB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g.cout * g.cin * 4, s));
   WgradPlan p;
   memset(&p, 0, sizeof(p));
   p.mn = g.n; p.mh = g.h; p.mw = g.w;
@@ -178,7 +189,7 @@ int convt_wgrad(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, cons
   for (int t = 0; t < 4; ++t) { p.a_dh[t] = 0; p.a_dw[t] = 0; p.b_dh[t] = (int8_t)(t >> 1); p.b_dw[t] = (int8_t)(t & 1); }
   p.m_total = g.cin; p.n_total = g.cout;
   p.dw = dw; p.tap_stride = 4;
-  return wgrad_common(p, x, g.n, g.h, g.w, x_ctotal, x_coff, g.cin, dy, g.n, 2 * g.h, 2 * g.w, dy_ctotal, dy_coff, g.cout, s);
+  return wgrad_common(p, x, g.n, g.h, g.w, x_ctotal, x_coff, g.cin, dy, g.n, 2 * g.h, 2 * g.w, dy_ctotal, dy_coff, g.cout, scratch, scratch_bytes, s);
 }
 
 // ---- conv1: Conv2d(3, 64, 7, stride 2, pad 3) as a 4x4 stride-1 convolution over the space-to-depth image.
@@ -212,9 +223,8 @@ int conv1_fprop(int n, int h, int w, const bf16* s2d, const bf16* wp, bf16* y, c
   return igemm_launch(p, s);
 }
 
-int conv1_wgrad(int n, int h, int w, const bf16* s2d, const bf16* dy, float* dw_s2d, cudaStream_t s) {
+int conv1_wgrad(int n, int h, int w, const bf16* s2d, const bf16* dy, float* dw_s2d, float* scratch, size_t scratch_bytes, cudaStream_t s) {
   const int hs = (h + 1) / 2, ws = (w + 1) / 2;
-  DBB_CUDA(cudaMemsetAsync(dw_s2d, 0, sizeof(float) * 64 * 64 * 4, s));
   WgradPlan p;
   memset(&p, 0, sizeof(p));
   p.mn = n; p.mh = hs; p.mw = ws;
@@ -226,8 +236,9 @@ int conv1_wgrad(int n, int h, int w, const bf16* s2d, const bf16* dy, float* dw_
   choose_box(64, p.mn, p.mh, p.mw, &p.bn, &p.bh, &p.bw);
   p.tiles_n = (p.mn + p.bn - 1) / p.bn; p.tiles_h = (p.mh + p.bh - 1) / p.bh; p.tiles_w = (p.mw + p.bw - 1) / p.bw;
   p.m_tile = 128; p.n_tile = 64;
-  p.split_k = pick_split_k(4, p.tiles_n * p.tiles_h * p.tiles_w);
-  int rc = encode_tmap_nhwc(&p.tmap_a, dy, n, hs, ws, 64, 0, 64, p.bn, p.bh, p.bw, 1, 1);
+  int rc = wgrad_finish_plan(p, scratch, scratch_bytes);
+  if (rc) return rc;
+  rc = encode_tmap_nhwc(&p.tmap_a, dy, n, hs, ws, 64, 0, 64, p.bn, p.bh, p.bw, 1, 1);
   if (rc) return rc;
   rc = conv1_tmap(&p.tmap_b, s2d, n, hs, ws, p.bn, p.bh, p.bw);
   if (rc) return rc;
@@ -281,18 +292,20 @@ extern "C" int dbb_conv2d(int kind, const void* x, const float* w, const float* 
   }
 }
 
+extern "C" size_t dbb_conv2d_wgrad_workspace(void) { return WGRAD_SCRATCH_BYTES; }
+
 extern "C" int dbb_conv2d_wgrad(int kind, const void* x, const void* dy, float* dw, int64_t n, int64_t h, int64_t wdt, int cin,
                                 int cout, int ksize, int stride, int pad, void* workspace, size_t workspace_bytes, void* stream) {
-  (void)workspace; (void)workspace_bytes;
+  if (!workspace) return set_error(DBB_EINVAL, "conv2d_wgrad: null workspace (see dbb_conv2d_wgrad_workspace)");
   if (!x || !dy || !dw) return set_error(DBB_EINVAL, "conv2d_wgrad: null pointer");
   int rc = check_geom("conv2d_wgrad: bad shape", n, h, wdt, cin, cout, ksize, stride);
   if (rc) return rc;
   if (!aligned16(x) || !aligned16(dy) || !aligned16(dw)) return set_error(DBB_EALIGN, "conv2d_wgrad: pointer not 16B aligned");
   ConvGeom g{(int)n, (int)h, (int)wdt, cin, cout, ksize, stride, pad};
-  if (kind == 0) return conv_wgrad(g, (const bf16*)x, cin, 0, (const bf16*)dy, cout, 0, dw, (cudaStream_t)stream);
+  if (kind == 0) return conv_wgrad(g, (const bf16*)x, cin, 0, (const bf16*)dy, cout, 0, dw, (float*)workspace, workspace_bytes, (cudaStream_t)stream);
   if (kind == 2) {
     if (ksize != 2 || stride != 2) return set_error(DBB_EUNSUPPORTED, "convT: only k=2, s=2");
-    return convt_wgrad(g, (const bf16*)x, cin, 0, (const bf16*)dy, cout, 0, dw, (cudaStream_t)stream);
+    return convt_wgrad(g, (const bf16*)x, cin, 0, (const bf16*)dy, cout, 0, dw, (float*)workspace, workspace_bytes, (cudaStream_t)stream);
   }
   return set_error(DBB_EINVAL, "conv2d_wgrad: kind must be 0 (Conv2d) or 2 (ConvTranspose2d)");
 }

@@ -105,8 +105,6 @@ igemm_kernel(const __grid_constant__ IgemmPlan p) {
     const int dw_ = r % p.bw, dh_ = (r / p.bw) % p.bh, dn_ = r / (p.bw * p.bh);
     const int n = n0 + dn_, h = h0 + dh_, w = w0 + dw_;
     const bool row_ok = (dn_ < p.bn) && n < p.mn && h < p.mh && w < p.mw;
-    const int64_t opix = ((int64_t)n * p.out_h + (h * p.out_sh + p.out_oh)) * p.out_w + (w * p.out_sw + p.out_ow);
-    bf16* yrow = p.y + opix * p.out_c + p.out_coff + nblk * BLOCK_N;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
@@ -117,14 +115,20 @@ igemm_kernel(const __grid_constant__ IgemmPlan p) {
       tmem_ld_wait();
       const int col0 = nblk * BLOCK_N + c;
       if (row_ok && col0 < p.cout) {
+        // pixel-shuffle epilogue (ConvTranspose2d k2 s2 as ONE GEMM): column = class * cls_cols + channel,
+        // class (a, b) lands on output pixel (2h + a, 2w + b)
+        int ch0 = col0, oh = p.out_oh, ow = p.out_ow;
+        if (p.cls_cols > 0) { const int cls = col0 / p.cls_cols; ch0 = col0 - cls * p.cls_cols; oh = cls >> 1; ow = cls & 1; }
+        const int64_t opix = ((int64_t)n * p.out_h + (h * p.out_sh + oh)) * p.out_w + (w * p.out_sw + ow);
+        bf16* ydst = p.y + opix * p.out_c + p.out_coff + ch0;
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
         if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + col0 + j);
+          for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + ch0 + j);
         }
-        uint4* dst = reinterpret_cast<uint4*>(yrow + c);
+        uint4* dst = reinterpret_cast<uint4*>(ydst);
         if (p.accumulate) {
           const uint4 e0 = dst[0], e1 = dst[1];
           f[0] += bf16lo(e0.x); f[1] += bf16hi(e0.x); f[2] += bf16lo(e0.y); f[3] += bf16hi(e0.y);
@@ -239,7 +243,6 @@ wgrad_kernel(const __grid_constant__ WgradPlan p) {
       }
     } else {
       const int q = warp & 3;
-      const int m = mt * 128 + q * 32 + lane;
       mbar_wait(tmem_full, 0);
       tc_fence_after();
       const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
@@ -248,13 +251,13 @@ wgrad_kernel(const __grid_constant__ WgradPlan p) {
         uint32_t v[16];
         tmem_ld_x16(taddr + (uint32_t)c, v);
         tmem_ld_wait();
-        const int n0c = nt * N_TILE + c;
-        if (m < p.m_total && n0c < p.n_total) {
-          float* dst = p.dw + ((int64_t)m * p.n_total + n0c) * p.tap_stride + tap;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (n0c + j < p.n_total) atomicAdd(dst + (int64_t)j * p.tap_stride, __uint_as_float(v[j]));
-        }
+        // deterministic split-K: every CTA stores its partial tile, wgrad_reduce_kernel sums the splits in a fixed order
+        float* dst = p.ws + (((int64_t)split * p.ntaps + tap) * p.m_pad + (mt * 128 + q * 32 + lane)) * p.n_pad + nt * N_TILE + c;
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        d4[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+        d4[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+        d4[2] = make_float4(__uint_as_float(v[8]), __uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
+        d4[3] = make_float4(__uint_as_float(v[12]), __uint_as_float(v[13]), __uint_as_float(v[14]), __uint_as_float(v[15]));
       }
     }
   }
@@ -266,11 +269,11 @@ wgrad_kernel(const __grid_constant__ WgradPlan p) {
 // ---------------------------------------------------------------------------------------------
 // weight packing (fp32 parameters -> bf16 GEMM operand)
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_weights_kernel(int mode, const float* __restrict__ w, bf16* __restrict__ out, int co_n, int ci_n, int kh, int kw,
-                                    int co_total, int co_off) {
+__device__ __forceinline__ void pack_one(int mode, const float* __restrict__ w, bf16* __restrict__ out, int co_n, int ci_n, int kh, int kw,
+                                         int co_total, int co_off, int64_t start, int64_t stride) {
   const int taps = kh * kw;
   const int64_t total = (mode == 4) ? (int64_t)co_n * 256 : (int64_t)co_n * ci_n * taps;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = start; i < total; i += stride) {
     float v;
     if (mode == 0) {          // out[co][tap][ci] <- w[co][ci][tap]
       const int ci = i % ci_n; const int tap = (i / ci_n) % taps; const int co = i / ((int64_t)ci_n * taps);
@@ -300,6 +303,19 @@ __global__ void pack_weights_kernel(int mode, const float* __restrict__ w, bf16*
     }
     out[i] = __float2bfloat16_rn(v);
   }
+}
+__global__ void pack_weights_kernel(int mode, const float* __restrict__ w, bf16* __restrict__ out, int co_n, int ci_n, int kh, int kw,
+                                    int co_total, int co_off) {
+  pack_one(mode, w, out, co_n, ci_n, kh, kw, co_total, co_off, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+}
+__global__ void __launch_bounds__(256) pack_weights_batch_kernel(const __grid_constant__ PackBatch b) {
+  const PackJob& j = b.jobs[blockIdx.y];
+  pack_one(j.mode, j.w, j.out, j.co_n, j.ci_n, j.kh, j.kw, j.co_total, j.co_off, (int64_t)blockIdx.x * 256 + threadIdx.x, (int64_t)gridDim.x * 256);
+}
+int pack_weights_batch(const PackBatch& b, cudaStream_t s) {
+  if (b.njobs <= 0) return DBB_OK;
+  DBB_LAUNCH("pack_weights_batch", s, pack_weights_batch_kernel<<<dim3(64, (unsigned)b.njobs), 256, 0, s>>>(b));
+  return DBB_OK;
 }
 
 int pack_weights(int mode, const float* w, bf16* out, int co_n, int ci_n, int kh, int kw, cudaStream_t s, int co_total, int co_off) {
@@ -446,6 +462,25 @@ int igemm_launch(const IgemmPlan& p, cudaStream_t s) {
   }
 }
 
+// dw[m][n][tap] = sum_split ws[split][tap][m][n]   (fixed summation order -> bitwise reproducible gradients)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int split_k, int ntaps, int m_pad, int n_pad,
+                                                           int m_total, int n_total, int tap_stride, float* __restrict__ dw) {
+  const int64_t total = (int64_t)ntaps * m_total * n_total;
+  const int64_t plane = (int64_t)ntaps * m_pad * n_pad;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int n = (int)(i % n_total); int64_t t = i / n_total;
+    const int m = (int)(t % m_total); const int tap = (int)(t / m_total);
+    const float* src = ws + ((int64_t)tap * m_pad + m) * n_pad + n;
+    float acc = 0.f;
+    for (int sp = 0; sp < split_k; ++sp) acc += src[(int64_t)sp * plane];
+    dw[((int64_t)m * n_total + n) * tap_stride + tap] = acc;
+  }
+}
+
+size_t wgrad_scratch_bytes(const WgradPlan& p) {
+  return (size_t)p.split_k * p.ntaps * p.m_pad * p.n_pad * sizeof(float);
+}
+
 template <int N_TILE, int STAGES>
 static int wgrad_launch_t(const WgradPlan& p, cudaStream_t s) {
   using SM = WgradSmem<N_TILE, STAGES>;
@@ -464,6 +499,10 @@ static int wgrad_launch_t(const WgradPlan& p, cudaStream_t s) {
     label = prof_label(tmp);
   }
   DBB_LAUNCH(label, s, wgrad_kernel<N_TILE, STAGES><<<(unsigned)grid, IG_THREADS, SM::TOTAL, s>>>(p));
+  const int64_t total = (int64_t)p.ntaps * p.m_total * p.n_total;
+  int rgrid = (int)((total + 255) / 256);
+  if (rgrid > DBB_NUM_SMS * 8) rgrid = DBB_NUM_SMS * 8;
+  DBB_LAUNCH("wgrad_reduce", s, wgrad_reduce_kernel<<<rgrid, 256, 0, s>>>(p.ws, p.split_k, p.ntaps, p.m_pad, p.n_pad, p.m_total, p.n_total, p.tap_stride, p.dw));
   return DBB_OK;
 }
 

@@ -122,6 +122,7 @@ struct DbbNet {
   Buf head_out;           // fp32 (N, C, ho, wo) when a final bilinear resize is needed
   Buf d_head_out;
   Buf partials;           // shared reduction scratch
+  Buf wg_scratch;         // split-K partials of the weight-gradient GEMMs
   int out_c;
   // bump allocator
   size_t cur = 0;
@@ -269,6 +270,7 @@ extern "C" DbbNet* dbb_net_create(int64_t n, int64_t h, int64_t w, int training)
   size_t pf = bn_partials_floats(512);
   if (head_tail_partials_floats() > pf) pf = head_tail_partials_floats();
   net->partials = net->alloc(pf * sizeof(float));
+  if (T) net->wg_scratch = net->alloc(WGRAD_SCRATCH_BYTES);
   net->ws_bytes = net->cur;
   return net;
 }
@@ -301,6 +303,7 @@ struct Ctx {
   float* buf(int i) const { return (i >= 0 && buffers) ? buffers[i] : nullptr; }
   float* grad(int i) const { return (i >= 0 && grads) ? grads[i] : nullptr; }
   float* partials() const { return p<float>(net->partials); }
+  float* wgs() const { return p<float>(net->wg_scratch); }
 };
 
 #define RC(call) do { int rc__ = (call); if (rc__) return rc__; } while (0)
@@ -319,8 +322,44 @@ int bn_prepare(const Ctx& c, const bf16* z, int64_t Pn, int ch, int gamma, int b
   return 0;
 }
 
+// every weight tensor -> its bf16 GEMM operand(s), in one or two launches at the start of the forward pass
+// (fprop layout always; the transposed dgrad layout too in training mode, so backward launches no packing at all)
+int pack_all(const Ctx& c) {
+  DbbNet* net = c.net;
+  PackBatch b;
+  b.njobs = 0;
+  auto flush = [&]() -> int { int rc = pack_weights_batch(b, c.s); b.njobs = 0; return rc; };
+  auto add = [&](int mode, const float* w, bf16* out, int co, int ci, int ks, int co_total, int co_off) -> int {
+    if (b.njobs == PACK_BATCH) RC(flush());
+    b.jobs[b.njobs++] = PackJob{w, out, mode, co, ci, ks, ks, co_total > 0 ? co_total : co, co_off};
+    return 0;
+  };
+  auto unit = [&](ConvBN& L) -> int {
+    RC(add(0, c.par(L.w), c.p(L.wp), L.g.cout, L.g.cin, L.g.ks, 0, 0));
+    if (net->training && L.wpt.bytes) RC(add(1, c.par(L.w), c.p(L.wpt), L.g.cout, L.g.cin, L.g.ks, 0, 0));
+    return 0;
+  };
+  RC(add(4, c.par(P("backbone.conv1.weight")), c.p(net->wp_conv1), 64, 3, 7, 0, 0));
+  for (int i = 0; i < 8; ++i) {
+    RC(unit(net->blocks[i].c1)); RC(unit(net->blocks[i].c2));
+    if (net->blocks[i].has_ds) RC(unit(net->blocks[i].ds));
+  }
+  for (int i = 0; i < 4; ++i) RC(unit(net->lat[i]));
+  for (int i = 0; i < 3; ++i) RC(unit(net->smooth[i]));
+  RC(unit(net->fconv));
+  for (int br = 0; br < 2; ++br) {
+    const std::string pre = std::string("segmentation_head.") + (br ? "thresh" : "binarize");
+    RC(add(0, c.par(P(pre + ".0.weight")), c.p(net->wp_h) + (size_t)br * 64 * 256 * 9, 64, 256, 3, 0, 0));
+    RC(add(2, c.par(P(pre + ".3.weight")), c.p(net->wp_t[br]), 64, 64, 2, 0, 0));
+    if (net->training) {
+      RC(add(1, c.par(P(pre + ".0.weight")), c.p(net->wpt_h), 64, 256, 3, 128, br * 64));
+      RC(add(3, c.par(P(pre + ".3.weight")), c.p(net->wpt_t[br]), 64, 64, 2, 0, 0));
+    }
+  }
+  return flush();
+}
+
 int convbn_fwd(const Ctx& c, ConvBN& L, const bf16* x, int x_ctotal, int x_coff) {
-  RC(pack_weights(0, c.par(L.w), c.p(L.wp), L.g.cout, L.g.cin, L.g.ks, L.g.ks, c.s));
   RC(conv_fprop(L.g, x, x_ctotal, x_coff, c.p(L.wp), c.par(L.b), c.p(L.z), L.g.cout, 0, c.s));
   RC(bn_prepare(c, c.p(L.z), L.P(), L.g.cout, L.gamma, L.beta, L.rm, L.rv, c.p<float>(L.stats)));
   return 0;
@@ -335,10 +374,9 @@ int convbn_bwd(const Ctx& c, ConvBN& L, const bf16* dout, int dout_ctotal, int d
   RC(bn_bwd_reduce(dout, dout_ctotal, dout_coff, mask, mask_ctotal, mask_coff, c.p(L.z), Pn, ch, c.p<float>(L.stats), c.partials(), &nblk, c.s));
   RC(bn_bwd_finalize(c.partials(), nblk, ch, 0, ch, Pn, c.par(L.gamma), c.p<float>(L.stats), c.grad(L.gamma), c.grad(L.beta), c.p<float>(L.coef), c.s));
   RC(bn_bwd_apply(dout, dout_ctotal, dout_coff, mask, mask_ctotal, mask_coff, c.p(L.z), Pn, ch, c.p<float>(L.stats), c.p<float>(L.coef), c.p(L.dz), dsum, c.s));
-  RC(conv_wgrad(L.g, x, x_ctotal, x_coff, c.p(L.dz), ch, 0, c.grad(L.w), c.s));
+  RC(conv_wgrad(L.g, x, x_ctotal, x_coff, c.p(L.dz), ch, 0, c.grad(L.w), c.wgs(), WGRAD_SCRATCH_BYTES, c.s));
   if (L.b >= 0) RC(bias_grad(c.p(L.dz), Pn, ch, c.partials(), c.grad(L.b), c.s));
   if (dx) {
-    RC(pack_weights(1, c.par(L.w), c.p(L.wpt), L.g.cout, L.g.cin, L.g.ks, L.g.ks, c.s));
     RC(conv_dgrad(L.g, c.p(L.dz), c.p(L.wpt), dx, c.s, dx_accumulate));
   }
   return 0;
@@ -390,7 +428,7 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
   const int N = net->n;
   // ---- stem: conv 7x7/2 (space-to-depth form) -> BN -> ReLU -> maxpool
   RC(image_to_s2d(x, N, net->h, net->w, c.p(net->s2d), c.s));
-  RC(pack_weights(4, c.par(P("backbone.conv1.weight")), c.p(net->wp_conv1), 64, 3, 7, 7, c.s));
+  RC(pack_all(c));
   RC(conv1_fprop(N, net->h, net->w, c.p(net->s2d), c.p(net->wp_conv1), c.p(net->z0), c.s));
   const int64_t P0 = (int64_t)N * net->h1 * net->w1;
   RC(bn_prepare(c, c.p(net->z0), P0, 64, P("backbone.bn1.weight"), P("backbone.bn1.bias"), B("backbone.bn1.running_mean"),
@@ -427,9 +465,6 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
   RC(convbn_fwd(c, net->fconv, c.p(net->cat), 256, 0));
   RC(bn_apply(c.p(net->fconv.z), net->fconv.P(), 256, c.p<float>(net->fconv.stats), nullptr, 1, c.p(net->af), 256, 0, c.s));
   // ---- head (segmentation_head.py:35-45)
-  const int ib = P("segmentation_head.binarize.0.weight"), it = P("segmentation_head.thresh.0.weight");
-  RC(pack_weights(0, c.par(ib), c.p(net->wp_h), 64, 256, 3, 3, c.s));
-  RC(pack_weights(0, c.par(it), c.p(net->wp_h) + (size_t)64 * 256 * 9, 64, 256, 3, 3, c.s));
   DBB_CUDA(cudaMemsetAsync(c.p<float>(net->bias_h), 0, 128 * sizeof(float), c.s));
   DBB_CUDA(cudaMemcpyAsync(c.p<float>(net->bias_h), c.par(P("segmentation_head.binarize.0.bias")), 64 * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
   RC(conv_fprop(net->hconv_g, c.p(net->af), 256, 0, c.p(net->wp_h), c.p<float>(net->bias_h), c.p(net->zh), 128, 0, c.s));
@@ -442,7 +477,6 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
   RC(bn_apply(c.p(net->zh), Ph, 128, c.p<float>(net->stats_h), nullptr, 1, c.p(net->ah), 128, 0, c.s));
   for (int br = 0; br < 2; ++br) {
     const std::string pre = std::string("segmentation_head.") + (br ? "thresh" : "binarize");
-    RC(pack_weights(2, c.par(P(pre + ".3.weight")), c.p(net->wp_t[br]), 64, 64, 2, 2, c.s));
     RC(convt_fprop(net->tconv_g, c.p(net->ah), 128, br * 64, c.p(net->wp_t[br]), c.par(P(pre + ".3.bias")), c.p(net->zt), 128, br * 64, c.s));
   }
   const int64_t Pt = Ph * 4;
@@ -497,9 +531,8 @@ extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout
     for (int br = 0; br < 2; ++br) {
       const std::string pre = br ? ht : hb;
       DBB_CUDA(cudaMemcpyAsync(c.grad(P(pre + ".3.bias")), c.p<float>(net->dbias_t) + br * 64, 64 * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
-      RC(pack_weights(3, c.par(P(pre + ".3.weight")), c.p(net->wpt_t[br]), 64, 64, 2, 2, c.s));
       RC(convt_dgrad(net->tconv_g, c.p(net->d_zt), 128, br * 64, c.p(net->wpt_t[br]), c.p(net->d_ah), 128, br * 64, c.s));
-      RC(convt_wgrad(net->tconv_g, c.p(net->ah), 128, br * 64, c.p(net->d_zt), 128, br * 64, c.grad(P(pre + ".3.weight")), c.s));
+      RC(convt_wgrad(net->tconv_g, c.p(net->ah), 128, br * 64, c.p(net->d_zt), 128, br * 64, c.grad(P(pre + ".3.weight")), c.wgs(), WGRAD_SCRATCH_BYTES, c.s));
     }
     // ---- BN(2 x 64) + ReLU + the fused 256->128 3x3 conv of the two branches
     RC(bn_bwd_reduce(c.p(net->d_ah), 128, 0, c.p(net->ah), 128, 0, c.p(net->zh), Ph, 128, c.p<float>(net->stats_h), c.partials(), &nblk, c.s));
@@ -510,14 +543,12 @@ extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout
     }
     RC(bn_bwd_apply(c.p(net->d_ah), 128, 0, c.p(net->ah), 128, 0, c.p(net->zh), Ph, 128, c.p<float>(net->stats_h), c.p<float>(net->coef_h),
                     c.p(net->d_zh), nullptr, c.s));
-    RC(conv_wgrad(net->hconv_g, c.p(net->af), 256, 0, c.p(net->d_zh), 128, 0, c.p<float>(net->dw_h), c.s));
+    RC(conv_wgrad(net->hconv_g, c.p(net->af), 256, 0, c.p(net->d_zh), 128, 0, c.p<float>(net->dw_h), c.wgs(), WGRAD_SCRATCH_BYTES, c.s));
     const size_t half = (size_t)64 * 256 * 9;
     DBB_CUDA(cudaMemcpyAsync(c.grad(P(hb + ".0.weight")), c.p<float>(net->dw_h), half * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
     DBB_CUDA(cudaMemcpyAsync(c.grad(P(ht + ".0.weight")), c.p<float>(net->dw_h) + half, half * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
     RC(bias_grad(c.p(net->d_zh), Ph, 128, c.partials(), c.p<float>(net->dbias_h), c.s));
     DBB_CUDA(cudaMemcpyAsync(c.grad(P(hb + ".0.bias")), c.p<float>(net->dbias_h), 64 * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
-    RC(pack_weights(1, c.par(P(hb + ".0.weight")), c.p(net->wpt_h), 64, 256, 3, 3, c.s, 128, 0));
-    RC(pack_weights(1, c.par(P(ht + ".0.weight")), c.p(net->wpt_h), 64, 256, 3, 3, c.s, 128, 64));
     RC(conv_dgrad(net->hconv_g, c.p(net->d_zh), c.p(net->wpt_h), c.p(net->d_af), c.s, 0));
     // ---- FPN output conv
     RC(convbn_bwd(c, net->fconv, c.p(net->d_af), 256, 0, c.p(net->af), 256, 0, c.p(net->cat), 256, 0, c.p(net->d_cat), 0, nullptr));
@@ -560,7 +591,7 @@ extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout
     RC(bn_bwd_finalize(c.partials(), nblk, 64, 0, 64, P0, c.par(g1), c.p<float>(net->stats0), c.grad(g1), c.grad(b1), c.p<float>(net->coef0), c.s));
     RC(bn_bwd_apply(c.p(net->d_a0), 64, 0, c.p(net->a0), 64, 0, c.p(net->z0), P0, 64, c.p<float>(net->stats0), c.p<float>(net->coef0),
                     c.p(net->d_z0), nullptr, c.s));
-    RC(conv1_wgrad(N, net->h, net->w, c.p(net->s2d), c.p(net->d_z0), c.p<float>(net->dw_s2d), c.s));
+    RC(conv1_wgrad(N, net->h, net->w, c.p(net->s2d), c.p(net->d_z0), c.p<float>(net->dw_s2d), c.wgs(), WGRAD_SCRATCH_BYTES, c.s));
     RC(conv1_wgrad_unpack(c.p<float>(net->dw_s2d), c.grad(P("backbone.conv1.weight")), c.s));
   }
   return DBB_OK;

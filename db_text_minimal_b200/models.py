@@ -198,10 +198,9 @@ class DBTextModel(nn.Module):
                 raise _lib.DbbError("DBTextModel parameters must be float32 CUDA tensors (call .cuda())")
         if self.training:
             y = _DBNetFn.apply(self, plan, x, *params)
-            with torch.no_grad():
-                for m in self.modules():
-                    if isinstance(m, nn.BatchNorm2d) and m.num_batches_tracked is not None:
-                        m.num_batches_tracked += 1
+            with torch.no_grad():      # BatchNorm2d bookkeeping, one fused launch for the 32 counters
+                torch._foreach_add_([m.num_batches_tracked for m in self.modules()
+                                     if isinstance(m, nn.BatchNorm2d) and m.num_batches_tracked is not None], 1)
         else:
             with torch.no_grad():
                 y = _DBNetFn.apply(self, plan, x, *params)

@@ -168,7 +168,8 @@ int dbb_conv2d(int kind, const void* x_nhwc_bf16, const float* w, const float* b
                int64_t n, int64_t h, int64_t wdt, int cin, int cout, int ksize, int stride, int pad,
                void* workspace, size_t workspace_bytes, void* stream);
 size_t dbb_conv2d_workspace(int kind, int64_t n, int64_t h, int64_t wdt, int cin, int cout, int ksize, int stride, int pad);
-/* wgrad: dw OIHW float32 (overwritten) = sum_px dy[px, co] * x[px @ tap, ci] */
+size_t dbb_conv2d_wgrad_workspace(void);
+/* wgrad: dw OIHW float32 (overwritten; deterministic split-K through `workspace`) = sum_px dy[px, co] * x[px @ tap, ci] */
 int dbb_conv2d_wgrad(int kind, const void* x_nhwc_bf16, const void* dy_nhwc_bf16, float* dw,
                      int64_t n, int64_t h, int64_t wdt, int cin, int cout, int ksize, int stride, int pad,
                      void* workspace, size_t workspace_bytes, void* stream);
