@@ -266,9 +266,9 @@ def run_ours(args):
                     if p.startswith(key) and p[len(key):].isdigit():
                         d.setdefault(key, int(p[len(key):]))
                         break
-            if name.startswith("igemm"):
+            if name.startswith("igemm_bn"):
                 return 2.0 * d["m"] * d["n"] * d["k"]
-            if name.startswith("wgrad"):
+            if name.startswith("wgrad_nt"):
                 return 2.0 * d["m"] * d["n"] * d["t"] * d["k"]
             return None
 

@@ -13,8 +13,58 @@
 // the P/T/B rows leave as fully coalesced 512-byte stores.
 #include "common.cuh"
 #include "head_tail.h"
+#include "tcgen05.cuh"
 
 namespace dbb {
+
+using ptx::mbar_init; using ptx::mbar_wait; using ptx::mbar_arrive_expect_tx; using ptx::fence_barrier_init; using ptx::smem_u32;
+
+// Tile staging (PIPE kernels, used when W2 is a multiple of the 64-pixel tile so that a tile is 16 KB of contiguous
+// NHWC memory): a ring of HT_STAGES shared-memory buffers filled by the bulk-copy engine (cp.async.bulk, the 1-D TMA
+// path) and signalled through mbarriers, so that 64 KB per CTA are in flight while the warps compute on earlier tiles.
+constexpr int HT_STAGES = 4;
+constexpr int HT_TILE_BYTES = 64 * 256;
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+struct HtRing {
+  uint8_t* buf;
+  uint64_t* full;
+  const bf16* zt;
+  int tiles_per_row, h2, w2;
+  int64_t ntiles;
+  __device__ __forceinline__ void issue(int64_t tile, int stage) const {
+    const int tr = (int)(tile % tiles_per_row);
+    const int64_t row = tile / tiles_per_row;
+    const bf16* src = zt + (row * w2 + (int64_t)tr * 64) * 128;
+    mbar_arrive_expect_tx(&full[stage], HT_TILE_BYTES);
+    bulk_load(buf + stage * HT_TILE_BYTES, src, HT_TILE_BYTES, &full[stage]);
+  }
+  __device__ __forceinline__ void start() const {
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < HT_STAGES; ++s) mbar_init(&full[s], 1);
+      fence_barrier_init();
+      for (int s = 0; s < HT_STAGES; ++s) {
+        const int64_t t = blockIdx.x + (int64_t)s * gridDim.x;
+        if (t < ntiles) issue(t, s);
+      }
+    }
+    __syncthreads();
+  }
+  __device__ __forceinline__ const bf16* wait(int64_t k) const {
+    const int stage = (int)(k % HT_STAGES);
+    mbar_wait(&full[stage], (uint32_t)((k / HT_STAGES) & 1));
+    return reinterpret_cast<const bf16*>(buf + stage * HT_TILE_BYTES);
+  }
+  // call after a __syncthreads() that follows the last read of iteration k's stage
+  __device__ __forceinline__ void refill(int64_t k, int64_t tile) const {
+    if (threadIdx.x == 0) {
+      const int64_t nxt = tile + (int64_t)HT_STAGES * gridDim.x;
+      if (nxt < ntiles) issue(nxt, (int)(k % HT_STAGES));
+    }
+  }
+};
 
 constexpr int HT_THREADS = 256;
 constexpr int HT_TILE = 64;   // input pixels per tile
@@ -22,6 +72,14 @@ constexpr int HT_TILE = 64;   // input pixels per tile
 struct HtF8 { float v[8]; };
 __device__ __forceinline__ HtF8 ht_ld8(const bf16* p) {
   const uint4 u = ldg_stream(reinterpret_cast<const uint4*>(p));
+  HtF8 r;
+  r.v[0] = bf16lo(u.x); r.v[1] = bf16hi(u.x); r.v[2] = bf16lo(u.y); r.v[3] = bf16hi(u.y);
+  r.v[4] = bf16lo(u.z); r.v[5] = bf16hi(u.z); r.v[6] = bf16lo(u.w); r.v[7] = bf16hi(u.w);
+  return r;
+}
+
+__device__ __forceinline__ HtF8 ht_lds8(const bf16* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
   HtF8 r;
   r.v[0] = bf16lo(u.x); r.v[1] = bf16hi(u.x); r.v[2] = bf16lo(u.y); r.v[3] = bf16hi(u.y);
   r.v[4] = bf16lo(u.z); r.v[5] = bf16hi(u.z); r.v[6] = bf16lo(u.w); r.v[7] = bf16hi(u.w);
@@ -54,11 +112,14 @@ __device__ __forceinline__ void tile_coords(int64_t tile, int tiles_per_row, int
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
+template <bool PIPE>
 __global__ void __launch_bounds__(HT_THREADS)
 head_tail_fwd_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w2, const float* __restrict__ stats4,
                      const float* __restrict__ w2b, const float* __restrict__ w2t, const float* __restrict__ b2b,
                      const float* __restrict__ b2t, float k, int out_c, float* __restrict__ out) {
   __shared__ float zs[2][4][HT_TILE];   // [branch][tap][pixel] pre-sigmoid logits
+  __shared__ uint64_t full_bar[HT_STAGES];
+  extern __shared__ __align__(128) uint8_t ring_smem[];
   const int l16 = threadIdx.x & 15, pslot = threadIdx.x >> 4;   // 16 pixel slots per pass
   LaneConst L;
   load_lane_const(L, l16, stats4, w2b, w2t);
@@ -66,17 +127,21 @@ head_tail_fwd_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w2, con
   const int tiles_per_row = (w2 + HT_TILE - 1) / HT_TILE;
   const int64_t ntiles = (int64_t)n_img * h2 * tiles_per_row;
   const int H = 2 * h2, W = 2 * w2;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const HtRing ring{ring_smem, full_bar, zt, tiles_per_row, h2, w2, ntiles};
+  if (PIPE) ring.start();
+  int64_t kk = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++kk) {
     int n, i, j0;
     tile_coords(tile, tiles_per_row, h2, n, i, j0);
-    const bf16* zrow = zt + (((int64_t)n * h2 + i) * w2) * 128;
+    const bf16* zrow = PIPE ? ring.wait(kk) - (int64_t)j0 * 128 : zt + (((int64_t)n * h2 + i) * w2) * 128;
     // ---- phase 1: BN + ReLU + 4 dot products per branch
 #pragma unroll
     for (int pass = 0; pass < HT_TILE / 16; ++pass) {
       const int px = pass * 16 + pslot;
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       if (j0 + px < w2) {
-        const HtF8 z = ht_ld8(zrow + (int64_t)(j0 + px) * 128 + l16 * 8);
+        const bf16* zp = zrow + (int64_t)(j0 + px) * 128 + l16 * 8;
+        const HtF8 z = PIPE ? ht_lds8(zp) : ht_ld8(zp);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float a = fmaxf(fmaf(z.v[j], L.sc[j], L.sh[j]), 0.f);
@@ -96,6 +161,7 @@ head_tail_fwd_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w2, con
       }
     }
     __syncthreads();
+    if (PIPE) ring.refill(kk, tile);
     // ---- phase 2: sigmoid, step, coalesced store.  thread -> (a = row parity, col = output column in the tile)
     {
       const int a = threadIdx.x >> 7, col = threadIdx.x & 127;
@@ -143,12 +209,15 @@ __device__ __forceinline__ void bwd_phase_a(float (&dzs)[2][4][HT_TILE], const f
 
 constexpr int HT_NACC = 6;   // per channel: dW2[4 taps], sum dy, sum dy*xhat
 
+template <bool PIPE>
 __global__ void __launch_bounds__(HT_THREADS)
 head_tail_bwd_reduce_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w2, const float* __restrict__ stats4,
                             const float* __restrict__ w2b, const float* __restrict__ w2t, const float* __restrict__ out,
                             const float* __restrict__ dout, float k, float* __restrict__ partials /* [grid][128*6 + 2] */) {
   __shared__ float dzs[2][4][HT_TILE];
   __shared__ float red[HT_THREADS][9];   // padded rows
+  __shared__ uint64_t full_bar[HT_STAGES];
+  extern __shared__ __align__(128) uint8_t ring_smem[];
   const int l16 = threadIdx.x & 15, pslot = threadIdx.x >> 4;
   LaneConst L;
   load_lane_const(L, l16, stats4, w2b, w2t);
@@ -164,18 +233,22 @@ head_tail_bwd_reduce_kernel(const bf16* __restrict__ zt, int n_img, int h2, int 
   const int tiles_per_row = (w2 + HT_TILE - 1) / HT_TILE;
   const int64_t ntiles = (int64_t)n_img * h2 * tiles_per_row;
   const int H = 2 * h2, W = 2 * w2;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const HtRing ring{ring_smem, full_bar, zt, tiles_per_row, h2, w2, ntiles};
+  if (PIPE) ring.start();
+  int64_t kk = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++kk) {
     int n, i, j0;
     tile_coords(tile, tiles_per_row, h2, n, i, j0);
     bwd_phase_a(dzs, out, dout, n, i, j0, w2, H, W, k);
     __syncthreads();
-    const bf16* zrow = zt + (((int64_t)n * h2 + i) * w2) * 128;
+    const bf16* zrow = PIPE ? ring.wait(kk) - (int64_t)j0 * 128 : zt + (((int64_t)n * h2 + i) * w2) * 128;
     const int br = l16 >> 3;
 #pragma unroll
     for (int pass = 0; pass < HT_TILE / 16; ++pass) {
       const int px = pass * 16 + pslot;
       if (j0 + px < w2) {
-        const HtF8 z = ht_ld8(zrow + (int64_t)(j0 + px) * 128 + l16 * 8);
+        const bf16* zp = zrow + (int64_t)(j0 + px) * 128 + l16 * 8;
+        const HtF8 z = PIPE ? ht_lds8(zp) : ht_ld8(zp);
         float dz[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) dz[t] = dzs[br][t][px];
@@ -193,6 +266,7 @@ head_tail_bwd_reduce_kernel(const bf16* __restrict__ zt, int n_img, int h2, int 
       }
     }
     __syncthreads();
+    if (PIPE) ring.refill(kk, tile);
   }
   // ---- reduce over the 16 pixel slots that share a lane role; thread (l16, pslot)
   float* my = partials + (size_t)blockIdx.x * (128 * HT_NACC + 2);
@@ -263,11 +337,14 @@ __global__ void head_tail_bwd_finalize_kernel(const float* __restrict__ partials
   coef3[256 + ch] = (float)(acc[5] / count);
 }
 
+template <bool PIPE>
 __global__ void __launch_bounds__(HT_THREADS)
 head_tail_bwd_apply_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w2, const float* __restrict__ stats4,
                            const float* __restrict__ coef3, const float* __restrict__ w2b, const float* __restrict__ w2t,
                            const float* __restrict__ out, const float* __restrict__ dout, float k, bf16* __restrict__ d_zt) {
   __shared__ float dzs[2][4][HT_TILE];
+  __shared__ uint64_t full_bar[HT_STAGES];
+  extern __shared__ __align__(128) uint8_t ring_smem[];
   const int l16 = threadIdx.x & 15, pslot = threadIdx.x >> 4;
   LaneConst L;
   load_lane_const(L, l16, stats4, w2b, w2t);
@@ -283,19 +360,23 @@ head_tail_bwd_apply_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w
   const int tiles_per_row = (w2 + HT_TILE - 1) / HT_TILE;
   const int64_t ntiles = (int64_t)n_img * h2 * tiles_per_row;
   const int H = 2 * h2, W = 2 * w2;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const HtRing ring{ring_smem, full_bar, zt, tiles_per_row, h2, w2, ntiles};
+  if (PIPE) ring.start();
+  int64_t kk = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++kk) {
     int n, i, j0;
     tile_coords(tile, tiles_per_row, h2, n, i, j0);
     bwd_phase_a(dzs, out, dout, n, i, j0, w2, H, W, k);
     __syncthreads();
     const int64_t rowoff = (((int64_t)n * h2 + i) * w2) * 128;
+    const bf16* ztile = PIPE ? ring.wait(kk) : nullptr;
     const int br = l16 >> 3;
 #pragma unroll
     for (int pass = 0; pass < HT_TILE / 16; ++pass) {
       const int px = pass * 16 + pslot;
       if (j0 + px < w2) {
         const int64_t off = rowoff + (int64_t)(j0 + px) * 128 + l16 * 8;
-        const HtF8 z = ht_ld8(zt + off);
+        const HtF8 z = PIPE ? ht_lds8(ztile + px * 128 + l16 * 8) : ht_ld8(zt + off);
         float dz[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) dz[t] = dzs[br][t][px];
@@ -315,9 +396,18 @@ head_tail_bwd_apply_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w
       }
     }
     __syncthreads();
+    if (PIPE) ring.refill(kk, tile);
   }
 }
 
+constexpr int HT_RING_BYTES = HT_STAGES * HT_TILE_BYTES;
+// persistent grid of the staged kernels: ctas_per_sm CTAs on each of the 148 SMs (64 KB ring each)
+static int ht_pipe_grid(int n, int h2, int w2, int ctas_per_sm) {
+  const int64_t ntiles = (int64_t)n * h2 * (w2 / HT_TILE);
+  int64_t g = (int64_t)DBB_NUM_SMS * ctas_per_sm;
+  if (ntiles < g) g = ntiles;
+  return (int)(g < 1 ? 1 : g);
+}
 static int ht_grid(int n, int h2, int w2) {
   const int64_t ntiles = (int64_t)n * h2 * ((w2 + HT_TILE - 1) / HT_TILE);
   int64_t g = DBB_NUM_SMS * 8;
@@ -333,13 +423,27 @@ static int ht_reduce_grid(int n, int h2, int w2) {
 
 int head_tail_fwd(const bf16* zt, int n, int h2, int w2, const float* stats4, const float* w2b, const float* w2t,
                   const float* b2b, const float* b2t, float k, int out_c, float* out, cudaStream_t s) {
-  DBB_LAUNCH("head_tail_fwd", s, head_tail_fwd_kernel<<<ht_grid(n, h2, w2), HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, w2b, w2t, b2b, b2t, k, out_c, out));
+  if (w2 % HT_TILE == 0) {
+    static bool attr = false;
+    if (!attr) { DBB_CUDA(cudaFuncSetAttribute(head_tail_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_RING_BYTES)); attr = true; }
+    DBB_LAUNCH("head_tail_fwd", s, head_tail_fwd_kernel<true><<<ht_pipe_grid(n, h2, w2, 2), HT_THREADS, HT_RING_BYTES, s>>>(zt, n, h2, w2, stats4, w2b, w2t, b2b, b2t, k, out_c, out));
+    return DBB_OK;
+  }
+  DBB_LAUNCH("head_tail_fwd", s, head_tail_fwd_kernel<false><<<ht_grid(n, h2, w2), HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, w2b, w2t, b2b, b2t, k, out_c, out));
   return DBB_OK;
 }
 int head_tail_bwd_reduce(const bf16* zt, int n, int h2, int w2, const float* stats4, const float* w2b, const float* w2t,
                          const float* out, const float* dout, float k, float* partials, int* nblk, cudaStream_t s) {
   *nblk = ht_reduce_grid(n, h2, w2);
-  DBB_LAUNCH("head_tail_bwd_reduce", s, head_tail_bwd_reduce_kernel<<<*nblk, HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, w2b, w2t, out, dout, k, partials));
+  if (w2 % HT_TILE == 0) {
+    static bool attr = false;
+    if (!attr) { DBB_CUDA(cudaFuncSetAttribute(head_tail_bwd_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_RING_BYTES)); attr = true; }
+    const int g = ht_pipe_grid(n, h2, w2, 1);
+    *nblk = g < *nblk ? g : *nblk;
+    DBB_LAUNCH("head_tail_bwd_reduce", s, head_tail_bwd_reduce_kernel<true><<<*nblk, HT_THREADS, HT_RING_BYTES, s>>>(zt, n, h2, w2, stats4, w2b, w2t, out, dout, k, partials));
+    return DBB_OK;
+  }
+  DBB_LAUNCH("head_tail_bwd_reduce", s, head_tail_bwd_reduce_kernel<false><<<*nblk, HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, w2b, w2t, out, dout, k, partials));
   return DBB_OK;
 }
 int head_tail_bwd_finalize(const float* partials, int nblk, int64_t count, const float* gamma_b, const float* gamma_t,
@@ -351,7 +455,13 @@ int head_tail_bwd_finalize(const float* partials, int nblk, int64_t count, const
 }
 int head_tail_bwd_apply(const bf16* zt, int n, int h2, int w2, const float* stats4, const float* coef3, const float* w2b,
                         const float* w2t, const float* out, const float* dout, float k, bf16* d_zt, cudaStream_t s) {
-  DBB_LAUNCH("head_tail_bwd_apply", s, head_tail_bwd_apply_kernel<<<ht_grid(n, h2, w2), HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, coef3, w2b, w2t, out, dout, k, d_zt));
+  if (w2 % HT_TILE == 0) {
+    static bool attr = false;
+    if (!attr) { DBB_CUDA(cudaFuncSetAttribute(head_tail_bwd_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_RING_BYTES)); attr = true; }
+    DBB_LAUNCH("head_tail_bwd_apply", s, head_tail_bwd_apply_kernel<true><<<ht_pipe_grid(n, h2, w2, 2), HT_THREADS, HT_RING_BYTES, s>>>(zt, n, h2, w2, stats4, coef3, w2b, w2t, out, dout, k, d_zt));
+    return DBB_OK;
+  }
+  DBB_LAUNCH("head_tail_bwd_apply", s, head_tail_bwd_apply_kernel<false><<<ht_grid(n, h2, w2), HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, coef3, w2b, w2t, out, dout, k, d_zt));
   return DBB_OK;
 }
 

@@ -129,7 +129,7 @@ def _head_tail_ref(zt, gamma, beta, w2b, w2t, b2b, b2t, training, rm=None, rv=No
     return torch.cat(outs, 1)
 
 
-@pytest.mark.parametrize("shape", [(2, 16, 24), (1, 9, 70), (3, 5, 64), (2, 40, 130)])
+@pytest.mark.parametrize("shape", [(2, 16, 24), (1, 9, 70), (3, 5, 64), (2, 40, 130), (4, 104, 192)])   # last: staged ring wraps
 def test_head_tail_fwd_bwd(shape):
     """a-5 / a-6: BN+ReLU -> ConvT(64->1) x2 -> sigmoid -> step.  fp32 outputs: P, T within 1e-4 rel (north_star)."""
     from db_text_minimal_b200 import _ops

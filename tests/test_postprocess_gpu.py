@@ -101,7 +101,12 @@ def test_full_size_properties():
         assert (lab > 0).sum() == bm[i].sum()
         # idempotence
     _, _, rec2, nc2 = r.front(P)
-    assert np.array_equal(nc, nc2) and all(np.array_equal(rec[i][:int(nc[i])], rec2[i][:int(nc[i])]) for i in range(n))
+    assert np.array_equal(nc, nc2)
+    for i in range(n):          # integer fields bit-exact; the float64 sums come from atomics (order varies in the last bits)
+        a, b = rec[i][:int(nc[i])], rec2[i][:int(nc[i])]
+        for f in ("kind", "first_y", "first_x", "x0", "y0", "x1", "y1", "count", "keep"):
+            assert np.array_equal(a[f], b[f]), f
+        np.testing.assert_allclose(a["sum"], b["sum"], rtol=1e-13)
 
 
 def test_boxes_end_to_end_box_mode():

@@ -1,0 +1,89 @@
+"""Turns gpurun_out/{launches_TAG.csv, prof_*_TAG.ncu-rep} into the tracked summaries under profiles/."""
+import collections
+import csv
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
+OUT = os.path.join(ROOT, "profiles")
+os.makedirs(OUT, exist_ok=True)
+
+
+def short(name):
+    name = re.sub(r"^void ", "", name)
+    return re.sub(r"\(.*", "", name)
+
+
+def launches():
+    path = os.path.join(ROOT, "gpurun_out", f"launches_{TAG}.csv")
+    if not os.path.exists(path):
+        return
+    rows = list(csv.DictReader(l for l in open(path) if l.startswith('"')))
+    seq = [(short(r["Kernel Name"]), r["Grid Size"], float(r["Metric Value"]) / 1e3) for r in rows]
+    starts = [i for i, s in enumerate(seq) if "image_to_s2d" in s[0]]
+    if len(starts) >= 3:
+        step = seq[starts[1]:starts[2]]
+    elif len(starts) >= 2:
+        step = seq[starts[0]:starts[1]]
+    else:
+        step = seq
+    tot = sum(t for _, _, t in step)
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for n, g, t in step:
+        agg[n][0] += 1
+        agg[n][1] += t
+    with open(os.path.join(OUT, f"launches_{TAG}.md"), "w") as f:
+        f.write(f"# ncu launch list, one training step (bench.py config 2, 16x3x640x640) — {TAG}\n\n")
+        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised: compare shares).\n\n")
+        f.write(f"launches in the step: {len(step)}; sum of kernel durations: {tot / 1e3:.3f} ms\n\n| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
+        for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{n[:110]}` | {c} | {t:.1f} | {100 * t / tot:.1f}% |\n")
+    with open(os.path.join(OUT, f"launches_{TAG}.csv"), "w") as f:
+        f.write("idx,kernel,grid,us\n")
+        for i, (n, g, t) in enumerate(step):
+            f.write(f'{i},"{n}","{g}",{t:.3f}\n')
+    print("launch list:", len(step), "launches,", tot / 1e3, "ms")
+
+
+METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+           "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+           "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
+           "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+           "launch__block_size", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
+           "lts__t_bytes.sum", "l1tex__t_bytes.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.max"]
+
+
+def ncu_rep(stem):
+    path = os.path.join(ROOT, "gpurun_out", f"{stem}_{TAG}.ncu-rep")
+    if not os.path.exists(path):
+        return
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    cols = [(m, hdr.index(m)) for m in METRICS if m in hdr]
+    extra = [(h, i) for i, h in enumerate(hdr) if re.search(r"pipe_tensor.*pct|tensor_op.*pct_of_peak_sustained_elapsed", h)][:6]
+    with open(os.path.join(OUT, f"{stem}_{TAG}.md"), "w") as f:
+        f.write(f"# ncu --set full --clock-control none — {stem} {TAG}\n\n")
+        for r in rows[2:]:
+            name = short(r[hdr.index("Kernel Name")])
+            f.write(f"## `{name[:120]}`  grid {r[hdr.index('Grid Size')] if 'Grid Size' in hdr else ''}\n\n| metric | value | unit |\n|---|---:|---|\n")
+            for m, i in cols + extra:
+                f.write(f"| {m} | {r[i]} | {units[i]} |\n")
+            try:
+                rd = float(r[hdr.index("dram__bytes_read.sum")].replace(",", "")); wr = float(r[hdr.index("dram__bytes_write.sum")].replace(",", ""))
+                u = units[hdr.index("dram__bytes_read.sum")]
+                f.write(f"| **traffic (dram read + write)** | {rd + wr:.3f} | {u} |\n")
+            except Exception:
+                pass
+            f.write("\n")
+    print("wrote", stem)
+
+
+if __name__ == "__main__":
+    launches()
+    ncu_rep("prof_igemm")
+    ncu_rep("prof_mem")
+    ncu_rep("prof")
