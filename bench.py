@@ -247,11 +247,13 @@ def run_ours(args):
 
     # ---- per-kernel timing (CUDA events on the launching stream) for the roofline figures: 3 extra steps
     out = None
+    nprof = 3
     if rank == 0:
         _lib.profile_enable(True)
-        nprof = 3
-        for i in range(nprof):
-            step(*dev_batches[i % 3])
+    for i in range(nprof):          # every rank steps (the step contains the gradient all-reduce); only rank 0 records
+        step(*dev_batches[i % 3])
+    barrier()
+    if rank == 0:
         kern = _lib.profile_report()
         _lib.profile_enable(False)
         peaks = load_peaks()
