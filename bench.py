@@ -45,6 +45,25 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "which": "fallback"}
 
 
+def ncu_traffic(label):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, from the committed `ncu --set full`
+    capture (profiles/traffic_*.json, written by tools/summarize_profiles.py); None when it was not captured."""
+    import glob
+    import re
+    m = re.match(r"igemm_bn(\d+)_m(\d+)_n(\d+)_k(\d+)", label)
+    if not m:
+        return None
+    bn, mm, nn = int(m.group(1)), int(m.group(2)), int(m.group(3))
+    stages = {64: 4, 128: 3, 256: 4}[bn]
+    key = f"igemm_kernel<{bn}, {stages}> grid ({-(-mm // 128) * -(-nn // bn)}, 1, 1)"
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json")), reverse=True):
+        with open(path) as f:
+            d = json.load(f)
+        if key in d:
+            return d[key]
+    return None
+
+
 # ------------------------------------------------------------------------------------------ CPU baseline (oracle port)
 def cpu_train_step_rate(batch, size, reduction, steps, warmup):
     """Reference code path restated on the CPU (oracle/db_oracle.py; the reference itself is pure PyTorch and is not
@@ -286,7 +305,7 @@ def run_ours(args):
                 json.dump(table, f, indent=1)
         dom = next(r for r in table if r["tflops"] is not None)
         roofline = {"bound": "tensor", "kernel": dom["name"], "achieved": dom["tflops"], "peak": peaks["tflops_sustained"],
-                    "unit": "TFLOP/s", "frac": dom["tflops"] / peaks["tflops_sustained"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": dom["tflops"] / peaks["tflops_sustained"], "traffic": ncu_traffic(dom["name"]),
                     "peak_source": peaks["which"] + " (sustained: kernel timed inside a long step)",
                     "share_of_step": dom["share"]}
         conv_ms = sum(r["ms_per_step"] for r in table if r["tflops"] is not None)

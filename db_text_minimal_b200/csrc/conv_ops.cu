@@ -3,10 +3,13 @@
 #include "common.cuh"
 #include "conv.h"
 #include "conv_ops.h"
+#include <stdlib.h>
 
 namespace dbb {
 
 static int pick_block_n(int cout, int64_t m_tiles) {
+  static const int forced = getenv("DBB_FORCE_BN") ? atoi(getenv("DBB_FORCE_BN")) : 0;   // tuning aid
+  if (forced && cout >= forced) return forced;
   // wide N tiles amortise the A-tile fetch; fall back to narrower tiles when there are too few CTAs to fill the GPU
   if (cout >= 256 && m_tiles >= 2 * DBB_NUM_SMS) return 256;
   if (cout >= 128) return 128;

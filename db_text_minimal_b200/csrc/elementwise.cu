@@ -298,6 +298,134 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ partials, int n
 
 static int check_c(int c) { return (c % 8 == 0 && c >= 8 && c <= 2048 && EW_THREADS % (c / 8) == 0) ? 0 : 1; }
 
+
+// ---------------------------------------------------------------------------------------------
+// fused "reduce + finalize": blocks add their per-channel sums to global fp64 accumulators (atomics), the last block to
+// arrive (ticket counter) computes the per-channel results and leaves accumulators + counter zeroed for the next layer.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool last_block_arrives(unsigned* counter) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+template <int NACC>
+__device__ __forceinline__ void reduce_groups_atomic(float (&acc)[NACC][8], int c, double* gacc /* [NACC][c] */) {
+  __shared__ float sh[EW_THREADS * 8];
+  const int groups = c / 8;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
+  const int lanes = EW_THREADS / groups;
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[(pl * groups + g) * 8 + j] = acc[a][j];
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += EW_THREADS) {
+      const int gg = ch / 8, jj = ch % 8;
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += sh[(l * groups + gg) * 8 + jj];
+      atomicAdd(&gacc[a * c + ch], (double)s);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+bn_stats_fin_kernel(const bf16* __restrict__ z, int64_t P, int c, double* __restrict__ gacc, unsigned* __restrict__ counter, BnFin fin) {
+  const int groups = c / 8;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups, lanes = EW_THREADS / groups;
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+  for (int64_t p = (int64_t)blockIdx.x * lanes + pl; p < P; p += (int64_t)gridDim.x * lanes) {
+    const F8 x = ld8(z + p * c + g * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[0][j] += x.v[j]; acc[1][j] += x.v[j] * x.v[j]; }
+  }
+  reduce_groups_atomic<2>(acc, c, gacc);
+  if (!last_block_arrives(counter)) return;
+  const double count = (double)P;
+  for (int sg = 0; sg < fin.nseg; ++sg) {
+    const BnFinSeg& S = fin.seg[sg];
+    for (int i = threadIdx.x; i < S.cn; i += EW_THREADS) {
+      const int ch = S.coff + i;
+      const double s = __ldcg(&gacc[ch]), q = __ldcg(&gacc[c + ch]);
+      gacc[ch] = 0.0; gacc[c + ch] = 0.0;
+      const double mean = s / count;
+      double var = q / count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const double invstd = 1.0 / sqrt(var + (double)fin.eps);
+      fin.stats4[ch] = (float)((double)S.gamma[i] * invstd);
+      fin.stats4[c + ch] = (float)((double)S.beta[i] - mean * (double)S.gamma[i] * invstd);
+      fin.stats4[2 * c + ch] = (float)mean;
+      fin.stats4[3 * c + ch] = (float)invstd;
+      if (S.rmean) {   // running stats: unbiased variance, momentum 0.1 (torch.nn.BatchNorm2d)
+        const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+        S.rmean[i] = (float)((1.0 - fin.momentum) * (double)S.rmean[i] + fin.momentum * mean);
+        S.rvar[i] = (float)((1.0 - fin.momentum) * (double)S.rvar[i] + fin.momentum * unb);
+      }
+    }
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+bn_bwd_reduce_fin_kernel(const bf16* __restrict__ dout, int dout_ctotal, int dout_coff, const bf16* __restrict__ mask_src,
+                         int mask_ctotal, int mask_coff, const bf16* __restrict__ z, int64_t P, int c,
+                         const float* __restrict__ stats4, double* __restrict__ gacc, unsigned* __restrict__ counter, BnBwdFin fin) {
+  const int groups = c / 8;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups, lanes = EW_THREADS / groups;
+  const F8 mean = ldf8(stats4 + 2 * c + g * 8), inv = ldf8(stats4 + 3 * c + g * 8);
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+  for (int64_t p = (int64_t)blockIdx.x * lanes + pl; p < P; p += (int64_t)gridDim.x * lanes) {
+    F8 dy = ld8(dout + p * dout_ctotal + dout_coff + g * 8);
+    if (mask_src) {
+      const F8 m = ld8(mask_src + p * mask_ctotal + mask_coff + g * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dy.v[j] = m.v[j] > 0.f ? dy.v[j] : 0.f;
+    }
+    const F8 x = ld8(z + p * c + g * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[0][j] += dy.v[j]; acc[1][j] += dy.v[j] * (x.v[j] - mean.v[j]) * inv.v[j]; }
+  }
+  reduce_groups_atomic<2>(acc, c, gacc);
+  if (!last_block_arrives(counter)) return;
+  const double count = (double)P;
+  for (int sg = 0; sg < fin.nseg; ++sg) {
+    const BnBwdFinSeg& S = fin.seg[sg];
+    for (int i = threadIdx.x; i < S.cn; i += EW_THREADS) {
+      const int ch = S.coff + i;
+      const double s = __ldcg(&gacc[ch]), q = __ldcg(&gacc[c + ch]);
+      gacc[ch] = 0.0; gacc[c + ch] = 0.0;
+      if (S.dgamma) S.dgamma[i] = (float)q;
+      if (S.dbeta) S.dbeta[i] = (float)s;
+      fin.coef3[ch] = S.gamma[i] * stats4[3 * c + ch];
+      fin.coef3[c + ch] = (float)(s / count);
+      fin.coef3[2 * c + ch] = (float)(q / count);
+    }
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+
+int bn_stats_finalize(const bf16* z, int64_t P, int c, const BnFin& fin, double* gacc, unsigned* counter, cudaStream_t s) {
+  if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_stats: channel count");
+  DBB_LAUNCH("bn_stats_fin", s, bn_stats_fin_kernel<<<ew_blocks(P, c), EW_THREADS, 0, s>>>(z, P, c, gacc, counter, fin));
+  return DBB_OK;
+}
+int bn_bwd_reduce_finalize(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
+                           const bf16* z, int64_t P, int c, const float* stats4, const BnBwdFin& fin, double* gacc,
+                           unsigned* counter, cudaStream_t s) {
+  if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_bwd_reduce: channel count");
+  DBB_LAUNCH("bn_bwd_reduce_fin", s, bn_bwd_reduce_fin_kernel<<<ew_blocks(P, c), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, gacc, counter, fin));
+  return DBB_OK;
+}
+
 int bn_stats(const bf16* z, int64_t P, int c, float* partials, int* nblk, cudaStream_t s) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_stats: channel count");
   *nblk = ew_blocks(P, c);

@@ -20,6 +20,17 @@ int bn_finalize_train(const float* partials, int nblk, int c, int coff, int cn, 
                       float* running_mean, float* running_var, float momentum, float eps, float* stats4, cudaStream_t s);
 int bn_finalize_eval(int c, int coff, int cn, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                      float eps, float* stats4, cudaStream_t s);
+// fused statistics + finalize (one launch): fp64 atomics into `gacc` ([2][c] doubles, zero on entry, left zero) and a
+// last-block-done ticket in `counter` (zero on entry, left zero).  Up to two parameter segments (the two head branches).
+struct BnFinSeg { const float* gamma; const float* beta; float* rmean; float* rvar; int coff, cn; };
+struct BnFin { BnFinSeg seg[2]; int nseg; float momentum, eps; float* stats4; };
+struct BnBwdFinSeg { const float* gamma; float* dgamma; float* dbeta; int coff, cn; };
+struct BnBwdFin { BnBwdFinSeg seg[2]; int nseg; float* coef3; };
+constexpr size_t BN_ACC_BYTES = 2 * 2048 * sizeof(double) + 256;
+int bn_stats_finalize(const bf16* z, int64_t P, int c, const BnFin& fin, double* gacc, unsigned* counter, cudaStream_t s);
+int bn_bwd_reduce_finalize(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
+                           const bf16* z, int64_t P, int c, const float* stats4, const BnBwdFin& fin, double* gacc,
+                           unsigned* counter, cudaStream_t s);
 // out = [relu](z*scale + shift [+ res])
 int bn_apply(const bf16* z, int64_t P, int c, const float* stats4, const bf16* res, int relu, bf16* out, int out_ctotal,
              int out_coff, cudaStream_t s);

@@ -123,6 +123,7 @@ struct DbbNet {
   Buf d_head_out;
   Buf partials;           // shared reduction scratch
   Buf wg_scratch;         // split-K partials of the weight-gradient GEMMs
+  Buf bn_acc;             // fp64 accumulators + ticket of the fused reduce+finalize kernels (kept zero between uses)
   int out_c;
   // bump allocator
   size_t cur = 0;
@@ -270,6 +271,7 @@ extern "C" DbbNet* dbb_net_create(int64_t n, int64_t h, int64_t w, int training)
   size_t pf = bn_partials_floats(512);
   if (head_tail_partials_floats() > pf) pf = head_tail_partials_floats();
   net->partials = net->alloc(pf * sizeof(float));
+  net->bn_acc = net->alloc(BN_ACC_BYTES);
   if (T) net->wg_scratch = net->alloc(WGRAD_SCRATCH_BYTES);
   net->ws_bytes = net->cur;
   return net;
@@ -304,22 +306,32 @@ struct Ctx {
   float* grad(int i) const { return (i >= 0 && grads) ? grads[i] : nullptr; }
   float* partials() const { return p<float>(net->partials); }
   float* wgs() const { return p<float>(net->wg_scratch); }
+  double* acc() const { return p<double>(net->bn_acc); }
+  unsigned* ticket() const { return reinterpret_cast<unsigned*>(base + net->bn_acc.off + 2 * 2048 * sizeof(double)); }
 };
 
 #define RC(call) do { int rc__ = (call); if (rc__) return rc__; } while (0)
 
-// BatchNorm statistics of a raw conv output (training) or running statistics (eval) -> stats4
-int bn_prepare(const Ctx& c, const bf16* z, int64_t Pn, int ch, int gamma, int beta, int rm, int rv, float* stats4, int coff = 0,
-               int cn = -1, bool do_stats = true) {
-  if (cn < 0) cn = ch;
+// BatchNorm statistics of a raw conv output (training: one fused reduce+finalize launch) or running statistics (eval)
+// -> stats4.  nseg = 2 for the 128-channel head tensors that carry two BatchNorm layers side by side.
+struct BnIdx { int gamma, beta, rm, rv; };
+int bn_prepare(const Ctx& c, const bf16* z, int64_t Pn, int ch, int nseg, const BnIdx* ix, float* stats4) {
+  const int cn = ch / nseg;
   if (c.net->training) {
-    static thread_local int nblk = 0;
-    if (do_stats) RC(bn_stats(z, Pn, ch, c.partials(), &nblk, c.s));
-    RC(bn_finalize_train(c.partials(), nblk, ch, coff, cn, Pn, c.par(gamma), c.par(beta), c.buf(rm), c.buf(rv), BN_MOM, BN_EPS, stats4, c.s));
+    BnFin fin;
+    fin.nseg = nseg; fin.momentum = BN_MOM; fin.eps = BN_EPS; fin.stats4 = stats4;
+    for (int i = 0; i < nseg; ++i)
+      fin.seg[i] = BnFinSeg{c.par(ix[i].gamma), c.par(ix[i].beta), c.buf(ix[i].rm), c.buf(ix[i].rv), i * cn, cn};
+    RC(bn_stats_finalize(z, Pn, ch, fin, c.acc(), c.ticket(), c.s));
   } else {
-    RC(bn_finalize_eval(ch, coff, cn, c.par(gamma), c.par(beta), c.buf(rm), c.buf(rv), BN_EPS, stats4, c.s));
+    for (int i = 0; i < nseg; ++i)
+      RC(bn_finalize_eval(ch, i * cn, cn, c.par(ix[i].gamma), c.par(ix[i].beta), c.buf(ix[i].rm), c.buf(ix[i].rv), BN_EPS, stats4, c.s));
   }
   return 0;
+}
+int bn_prepare(const Ctx& c, const bf16* z, int64_t Pn, int ch, int gamma, int beta, int rm, int rv, float* stats4) {
+  const BnIdx ix{gamma, beta, rm, rv};
+  return bn_prepare(c, z, Pn, ch, 1, &ix, stats4);
 }
 
 // every weight tensor -> its bf16 GEMM operand(s), in one or two launches at the start of the forward pass
@@ -368,14 +380,17 @@ int convbn_fwd(const Ctx& c, ConvBN& L, const bf16* x, int x_ctotal, int x_coff)
 // backward through BN (+ReLU mask) and the conv: dout -> dz -> (dW, dbias, dx)
 int convbn_bwd(const Ctx& c, ConvBN& L, const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask, int mask_ctotal,
                int mask_coff, const bf16* x, int x_ctotal, int x_coff, bf16* dx, int dx_accumulate, bf16* dsum) {
-  int nblk = 0;
   const int64_t Pn = L.P();
   const int ch = L.g.cout;
-  RC(bn_bwd_reduce(dout, dout_ctotal, dout_coff, mask, mask_ctotal, mask_coff, c.p(L.z), Pn, ch, c.p<float>(L.stats), c.partials(), &nblk, c.s));
-  RC(bn_bwd_finalize(c.partials(), nblk, ch, 0, ch, Pn, c.par(L.gamma), c.p<float>(L.stats), c.grad(L.gamma), c.grad(L.beta), c.p<float>(L.coef), c.s));
+  BnBwdFin fin;
+  fin.nseg = 1; fin.coef3 = c.p<float>(L.coef);
+  fin.seg[0] = BnBwdFinSeg{c.par(L.gamma), c.grad(L.gamma), c.grad(L.beta), 0, ch};
+  RC(bn_bwd_reduce_finalize(dout, dout_ctotal, dout_coff, mask, mask_ctotal, mask_coff, c.p(L.z), Pn, ch, c.p<float>(L.stats), fin, c.acc(), c.ticket(), c.s));
   RC(bn_bwd_apply(dout, dout_ctotal, dout_coff, mask, mask_ctotal, mask_coff, c.p(L.z), Pn, ch, c.p<float>(L.stats), c.p<float>(L.coef), c.p(L.dz), dsum, c.s));
   RC(conv_wgrad(L.g, x, x_ctotal, x_coff, c.p(L.dz), ch, 0, c.grad(L.w), c.wgs(), WGRAD_SCRATCH_BYTES, c.s));
-  if (L.b >= 0) RC(bias_grad(c.p(L.dz), Pn, ch, c.partials(), c.grad(L.b), c.s));
+  // the bias of a convolution that feeds a training-mode BatchNorm has an identically zero gradient
+  // (sum_px dz = 0); the reference's value is float rounding noise.  Written as exact zeros.
+  if (L.b >= 0) DBB_CUDA(cudaMemsetAsync(c.grad(L.b), 0, sizeof(float) * ch, c.s));
   if (dx) {
     RC(conv_dgrad(L.g, c.p(L.dz), c.p(L.wpt), dx, c.s, dx_accumulate));
   }
@@ -426,6 +441,7 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
   if (!aligned16(x) || !aligned16(out) || (reinterpret_cast<uintptr_t>(workspace) & 1023)) return set_error(DBB_EALIGN, "net_forward: x/out need 16 B, workspace 1024 B alignment");
   Ctx c{net, (char*)workspace, params, buffers, nullptr, (cudaStream_t)stream};
   const int N = net->n;
+  DBB_CUDA(cudaMemsetAsync(c.p<uint8_t>(net->bn_acc), 0, BN_ACC_BYTES, c.s));
   // ---- stem: conv 7x7/2 (space-to-depth form) -> BN -> ReLU -> maxpool
   RC(image_to_s2d(x, N, net->h, net->w, c.p(net->s2d), c.s));
   RC(pack_all(c));
@@ -469,10 +485,17 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
   DBB_CUDA(cudaMemcpyAsync(c.p<float>(net->bias_h), c.par(P("segmentation_head.binarize.0.bias")), 64 * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
   RC(conv_fprop(net->hconv_g, c.p(net->af), 256, 0, c.p(net->wp_h), c.p<float>(net->bias_h), c.p(net->zh), 128, 0, c.s));
   const int64_t Ph = (int64_t)N * hf * wf;
-  for (int br = 0; br < 2; ++br) {
-    const std::string pre = std::string("segmentation_head.") + (br ? "thresh" : "binarize");
-    RC(bn_prepare(c, c.p(net->zh), Ph, 128, P(pre + ".1.weight"), P(pre + ".1.bias"), B(pre + ".1.running_mean"), B(pre + ".1.running_var"),
-                  c.p<float>(net->stats_h), br * 64, 64, br == 0));
+  auto head_bn = [&](const char* idx) {
+    std::vector<BnIdx> v;
+    for (int br = 0; br < 2; ++br) {
+      const std::string pre = std::string("segmentation_head.") + (br ? "thresh" : "binarize") + "." + idx;
+      v.push_back(BnIdx{P(pre + ".weight"), P(pre + ".bias"), B(pre + ".running_mean"), B(pre + ".running_var")});
+    }
+    return v;
+  };
+  {
+    const std::vector<BnIdx> ix = head_bn("1");
+    RC(bn_prepare(c, c.p(net->zh), Ph, 128, 2, ix.data(), c.p<float>(net->stats_h)));
   }
   RC(bn_apply(c.p(net->zh), Ph, 128, c.p<float>(net->stats_h), nullptr, 1, c.p(net->ah), 128, 0, c.s));
   for (int br = 0; br < 2; ++br) {
@@ -480,10 +503,9 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
     RC(convt_fprop(net->tconv_g, c.p(net->ah), 128, br * 64, c.p(net->wp_t[br]), c.par(P(pre + ".3.bias")), c.p(net->zt), 128, br * 64, c.s));
   }
   const int64_t Pt = Ph * 4;
-  for (int br = 0; br < 2; ++br) {
-    const std::string pre = std::string("segmentation_head.") + (br ? "thresh" : "binarize");
-    RC(bn_prepare(c, c.p(net->zt), Pt, 128, P(pre + ".4.weight"), P(pre + ".4.bias"), B(pre + ".4.running_mean"), B(pre + ".4.running_var"),
-                  c.p<float>(net->stats_t), br * 64, 64, br == 0));
+  {
+    const std::vector<BnIdx> ix = head_bn("4");
+    RC(bn_prepare(c, c.p(net->zt), Pt, 128, 2, ix.data(), c.p<float>(net->stats_t)));
   }
   float* hout = net->head_out.bytes ? c.p<float>(net->head_out) : out;
   RC(head_tail_fwd(c.p(net->zt), N, 2 * hf, 2 * wf, c.p<float>(net->stats_t), c.par(P("segmentation_head.binarize.6.weight")),
@@ -527,19 +549,22 @@ extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout
     RC(head_tail_bwd_apply(c.p(net->zt), N, 2 * hf, 2 * wf, c.p<float>(net->stats_t), c.p<float>(net->coef_t), c.par(P(hb + ".6.weight")),
                            c.par(P(ht + ".6.weight")), hout, dhout, STEP_K, c.p(net->d_zt), c.s));
     // ---- ConvTranspose2d(64,64,2,2) x 2
-    RC(bias_grad(c.p(net->d_zt), Pt, 128, c.partials(), c.p<float>(net->dbias_t), c.s));
     for (int br = 0; br < 2; ++br) {
       const std::string pre = br ? ht : hb;
-      DBB_CUDA(cudaMemcpyAsync(c.grad(P(pre + ".3.bias")), c.p<float>(net->dbias_t) + br * 64, 64 * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
+      // biases in front of a training-mode BatchNorm: identically zero gradient (see convbn_bwd)
+      DBB_CUDA(cudaMemsetAsync(c.grad(P(pre + ".3.bias")), 0, 64 * sizeof(float), c.s));
       RC(convt_dgrad(net->tconv_g, c.p(net->d_zt), 128, br * 64, c.p(net->wpt_t[br]), c.p(net->d_ah), 128, br * 64, c.s));
       RC(convt_wgrad(net->tconv_g, c.p(net->ah), 128, br * 64, c.p(net->d_zt), 128, br * 64, c.grad(P(pre + ".3.weight")), c.wgs(), WGRAD_SCRATCH_BYTES, c.s));
     }
     // ---- BN(2 x 64) + ReLU + the fused 256->128 3x3 conv of the two branches
-    RC(bn_bwd_reduce(c.p(net->d_ah), 128, 0, c.p(net->ah), 128, 0, c.p(net->zh), Ph, 128, c.p<float>(net->stats_h), c.partials(), &nblk, c.s));
-    for (int br = 0; br < 2; ++br) {
-      const std::string pre = br ? ht : hb;
-      RC(bn_bwd_finalize(c.partials(), nblk, 128, br * 64, 64, Ph, c.par(P(pre + ".1.weight")), c.p<float>(net->stats_h),
-                         c.grad(P(pre + ".1.weight")), c.grad(P(pre + ".1.bias")), c.p<float>(net->coef_h), c.s));
+    {
+      BnBwdFin fin;
+      fin.nseg = 2; fin.coef3 = c.p<float>(net->coef_h);
+      for (int br = 0; br < 2; ++br) {
+        const std::string pre = br ? ht : hb;
+        fin.seg[br] = BnBwdFinSeg{c.par(P(pre + ".1.weight")), c.grad(P(pre + ".1.weight")), c.grad(P(pre + ".1.bias")), br * 64, 64};
+      }
+      RC(bn_bwd_reduce_finalize(c.p(net->d_ah), 128, 0, c.p(net->ah), 128, 0, c.p(net->zh), Ph, 128, c.p<float>(net->stats_h), fin, c.acc(), c.ticket(), c.s));
     }
     RC(bn_bwd_apply(c.p(net->d_ah), 128, 0, c.p(net->ah), 128, 0, c.p(net->zh), Ph, 128, c.p<float>(net->stats_h), c.p<float>(net->coef_h),
                     c.p(net->d_zh), nullptr, c.s));
@@ -547,8 +572,7 @@ extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout
     const size_t half = (size_t)64 * 256 * 9;
     DBB_CUDA(cudaMemcpyAsync(c.grad(P(hb + ".0.weight")), c.p<float>(net->dw_h), half * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
     DBB_CUDA(cudaMemcpyAsync(c.grad(P(ht + ".0.weight")), c.p<float>(net->dw_h) + half, half * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
-    RC(bias_grad(c.p(net->d_zh), Ph, 128, c.partials(), c.p<float>(net->dbias_h), c.s));
-    DBB_CUDA(cudaMemcpyAsync(c.grad(P(hb + ".0.bias")), c.p<float>(net->dbias_h), 64 * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
+    DBB_CUDA(cudaMemsetAsync(c.grad(P(hb + ".0.bias")), 0, 64 * sizeof(float), c.s));
     RC(conv_dgrad(net->hconv_g, c.p(net->d_zh), c.p(net->wpt_h), c.p(net->d_af), c.s, 0));
     // ---- FPN output conv
     RC(convbn_bwd(c, net->fconv, c.p(net->d_af), 256, 0, c.p(net->af), 256, 0, c.p(net->cat), 256, 0, c.p(net->d_cat), 0, nullptr));
@@ -587,8 +611,12 @@ extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout
     RC(maxpool_bwd(c.p(net->d_x1), c.p<uint8_t>(net->argmax), N, net->h1, net->w1, 64, c.p(net->d_a0), c.s));
     const int64_t P0 = (int64_t)N * net->h1 * net->w1;
     const int g1 = P("backbone.bn1.weight"), b1 = P("backbone.bn1.bias");
-    RC(bn_bwd_reduce(c.p(net->d_a0), 64, 0, c.p(net->a0), 64, 0, c.p(net->z0), P0, 64, c.p<float>(net->stats0), c.partials(), &nblk, c.s));
-    RC(bn_bwd_finalize(c.partials(), nblk, 64, 0, 64, P0, c.par(g1), c.p<float>(net->stats0), c.grad(g1), c.grad(b1), c.p<float>(net->coef0), c.s));
+    {
+      BnBwdFin fin;
+      fin.nseg = 1; fin.coef3 = c.p<float>(net->coef0);
+      fin.seg[0] = BnBwdFinSeg{c.par(g1), c.grad(g1), c.grad(b1), 0, 64};
+      RC(bn_bwd_reduce_finalize(c.p(net->d_a0), 64, 0, c.p(net->a0), 64, 0, c.p(net->z0), P0, 64, c.p<float>(net->stats0), fin, c.acc(), c.ticket(), c.s));
+    }
     RC(bn_bwd_apply(c.p(net->d_a0), 64, 0, c.p(net->a0), 64, 0, c.p(net->z0), P0, 64, c.p<float>(net->stats0), c.p<float>(net->coef0),
                     c.p(net->d_z0), nullptr, c.s));
     RC(conv1_wgrad(N, net->h, net->w, c.p(net->s2d), c.p(net->d_z0), c.p<float>(net->dw_s2d), c.wgs(), WGRAD_SCRATCH_BYTES, c.s));

@@ -232,7 +232,10 @@ def test_backward_wiring_against_own_tensors():
     assert_f32(G["segmentation_body.conv.1.weight"], dgf, "fpn conv.1.weight")
     wf = bf(P["segmentation_body.conv.0.weight"])
     assert_f32(G["segmentation_body.conv.0.weight"], torch.nn.grad.conv2d_weight(cat, wf.shape, dzf, padding=1), "fpn conv.0.weight")
-    assert_f32(G["segmentation_body.conv.0.bias"], dzf.sum((0, 2, 3)), "fpn conv.0.bias", tol=5e-3)
+    # a bias in front of a training-mode BatchNorm has an identically zero gradient (sum_px dz = 0): the executor writes
+    # exact zeros; the reference's autograd value is rounding noise around zero
+    assert float(G["segmentation_body.conv.0.bias"].abs().max()) == 0.0
+    assert float(dzf.sum((0, 2, 3)).abs().max()) <= 2e-3 * float(dzf.abs().sum((0, 2, 3)).max())
     d_cat = rd("d_cat")
     assert_bf16(d_cat, torch.nn.grad.conv2d_input(cat.shape, wf, dzf, padding=1), "d_cat")
     # p2 level
@@ -290,7 +293,8 @@ def test_backward_wiring_against_own_tensors():
         F.conv_transpose2d(ar, wr, None, stride=2).backward(d_zt[:, sl])
         assert_bf16(d_ah[:, sl], ar.grad, f"{pre} d_ah")
         assert_f32(G[pre + ".3.weight"], wr.grad, f"{pre}.3.weight")
-        assert_f32(G[pre + ".3.bias"], d_zt[:, sl].sum((0, 2, 3)), f"{pre}.3.bias", tol=5e-3)
+        assert float(G[pre + ".3.bias"].abs().max()) == 0.0          # feeds BatchNorm .4: zero gradient
+        assert float(d_zt[:, sl].sum((0, 2, 3)).abs().max()) <= 2e-3 * float(d_zt[:, sl].abs().sum((0, 2, 3)).max())
         dzh_ref, dgh, dbh, _ = bn_bwd_ref(d_ah[:, sl], ah[:, sl], zh[:, sl], P[pre + ".1.weight"])
         assert_bf16(d_zh[:, sl], dzh_ref, f"{pre} d_zh")
         assert_f32(G[pre + ".1.weight"], dgh, f"{pre}.1.weight")

@@ -73,16 +73,40 @@ def ncu_rep(stem):
             for m, i in cols + extra:
                 f.write(f"| {m} | {r[i]} | {units[i]} |\n")
             try:
-                rd = float(r[hdr.index("dram__bytes_read.sum")].replace(",", "")); wr = float(r[hdr.index("dram__bytes_write.sum")].replace(",", ""))
-                u = units[hdr.index("dram__bytes_read.sum")]
-                f.write(f"| **traffic (dram read + write)** | {rd + wr:.3f} | {u} |\n")
+                U = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+                ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+                tot = float(r[ir].replace(",", "")) * U[units[ir]] + float(r[iw].replace(",", "")) * U[units[iw]]
+                f.write(f"| **traffic (dram read + write)** | {tot / 1e6:.3f} | Mbyte |\n")
             except Exception:
                 pass
             f.write("\n")
     print("wrote", stem)
 
 
+def traffic_json():
+    """dram read+write bytes per launch of the kernels bench.py reports a roofline for (read back by bench.py)."""
+    import json
+    out = {}
+    for stem in ("prof_igemm", "prof_mem"):
+        path = os.path.join(ROOT, "gpurun_out", f"{stem}_{TAG}.ncu-rep")
+        if not os.path.exists(path):
+            continue
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        hdr, units = rows[0], rows[1]
+        ir, iw, ik, ig = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name"), hdr.index("Grid Size")
+        U = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+        for r in rows[2:]:
+            name = short(r[ik])
+            key = f"{name} grid {r[ig]}"
+            out.setdefault(key, float(r[ir]) * U[units[ir]] + float(r[iw]) * U[units[iw]])
+    with open(os.path.join(OUT, f"traffic_{TAG}.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print(out)
+
+
 if __name__ == "__main__":
+    traffic_json()
     launches()
     ncu_rep("prof_igemm")
     ncu_rep("prof_mem")
