@@ -59,6 +59,26 @@ int igemm_plan_init(IgemmPlan* p, const bf16* x, int n, int h, int w, int c_tota
                     const bf16* wp, int k_total, int w_rows, int block_n);
 int igemm_launch(const IgemmPlan& p, cudaStream_t s);
 
+// 3x3 / stride 1 / 64 -> 64 channels: persistent, weights-stationary, shifted-window ("halo") implicit GEMM.
+// One (R+2) x (bw+2) activation box per tile feeds all nine taps through descriptor start offsets; the 72 KB of packed
+// weights stay in shared memory for the life of the CTA; TMEM accumulators are double buffered.
+struct HaloPlan {
+  CUtensorMap tmap_x;      // 4-D NHWC, box {64, bw+2, R+2, 1}
+  CUtensorMap tmap_w;      // 2-D {K = 576, 64 rows}, box {64, 64}
+  int n, h, w;             // output (= input) extent
+  int R, bw, pitch;        // tile rows / cols, pitch = bw + 2
+  int tiles_h, tiles_w, total_tiles;
+  int16_t off[9];          // smem row offset of tap t inside the halo box
+  uint8_t wtap[9];         // weight tile used with tap t
+  bf16* y; int out_c, out_coff;
+  const float* bias;
+  int accumulate;
+  int base_offset_mode;    // descriptor base_offset: 1 = (addr >> 7) & 7, 0 = always 0 (tuning / bring-up)
+};
+int halo64_supported(int h, int w);
+int halo64_plan(HaloPlan* p, const bf16* x, int n, int h, int w, int x_ctotal, int x_coff, const bf16* wp, int dgrad);
+int halo64_launch(const HaloPlan& p, cudaStream_t s);
+
 // weight gradient:  dW[m][n][tap] (+)= sum_pixel A[pixel @ (a-side map)][m] * B[pixel @ tap][n]
 struct WgradPlan {
   CUtensorMap tmap_a;      // M-side operand (dy for Conv2d, x for ConvT): 4-D NHWC, box {64, bw*a_sw, bh*a_sh, bn}

@@ -16,9 +16,22 @@ static int pick_block_n(int cout, int64_t m_tiles) {
   return 64;
 }
 
+static bool use_halo(const ConvGeom& g) {
+  static const bool off = getenv("DBB_NO_HALO") != nullptr;    // A/B switch for benchmarking
+  return !off && g.ks == 3 && g.stride == 1 && g.pad == 1 && g.cin == 64 && g.cout == 64 && halo64_supported(g.h, g.w);
+}
+
 int conv_fprop(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const bf16* wp, const float* bias, bf16* y,
                int y_ctotal, int y_coff, cudaStream_t s) {
   const int ho = g.out_h(), wo = g.out_w();
+  if (use_halo(g)) {
+    HaloPlan hp;
+    memset(&hp, 0, sizeof(hp));
+    int rc = halo64_plan(&hp, x, g.n, g.h, g.w, x_ctotal, x_coff, wp, 0);
+    if (rc) return rc;
+    hp.y = y; hp.out_c = y_ctotal; hp.out_coff = y_coff; hp.bias = bias; hp.accumulate = 0;
+    return halo64_launch(hp, s);
+  }
   IgemmPlan p;
   memset(&p, 0, sizeof(p));
   p.mn = g.n; p.mh = ho; p.mw = wo;
@@ -44,6 +57,14 @@ int conv_dgrad(const ConvGeom& g, const bf16* dy, const bf16* wp_t, bf16* dx, cu
   const int ho = g.out_h(), wo = g.out_w();
   const int st = g.stride;
   if (st != 1 && st != 2) return set_error(DBB_EUNSUPPORTED, "conv_dgrad: stride must be 1 or 2");
+  if (use_halo(g)) {      // dx = conv(dy, W^T flipped): same kernel, mirrored tap offsets, weights packed by mode 1
+    HaloPlan hp;
+    memset(&hp, 0, sizeof(hp));
+    int rc = halo64_plan(&hp, dy, g.n, g.h, g.w, g.cout, 0, wp_t, 1);
+    if (rc) return rc;
+    hp.y = dx; hp.out_c = g.cin; hp.out_coff = 0; hp.bias = nullptr; hp.accumulate = accumulate;
+    return halo64_launch(hp, s);
+  }
   bool need_zero = false;
   for (int a = 0; a < st; ++a)
     for (int b = 0; b < st; ++b) {

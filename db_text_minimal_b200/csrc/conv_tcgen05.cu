@@ -14,6 +14,7 @@
 #include "conv.h"
 #include "tcgen05.cuh"
 #include <mutex>
+#include <stdlib.h>
 
 namespace dbb {
 
@@ -146,6 +147,199 @@ igemm_kernel(const __grid_constant__ IgemmPlan p) {
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<BLOCK_N>(tmem_d);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// halo64: 3x3 stride-1 64->64 convolution (fprop and dgrad), persistent + weights-stationary + shifted windows
+// ---------------------------------------------------------------------------------------------
+constexpr int HALO_B_BYTES = 9 * 64 * 128;      // nine 64x64 bf16 weight tiles
+constexpr int HALO_A_STAGE = 224 * 128;         // up to 224 pixel rows of 128 B
+constexpr int HALO_STAGES = 3;
+constexpr int HALO_SMEM = HALO_B_BYTES + HALO_STAGES * HALO_A_STAGE + 256 + 1024;
+
+// Shifted-window operands start at 128 B granularity, not on the 1024 B swizzle repeat.  Measured on B200: tcgen05 applies the
+// 128 B swizzle to the ABSOLUTE shared-memory address bits (the same function TMA used when writing the tile), so the
+// descriptor's base_offset field must stay 0; setting it to (addr >> 7) & 7 gives wrong products (kept as a bring-up switch).
+__device__ __forceinline__ uint64_t make_desc_sw128_off(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, int base_mode) {
+  uint64_t d = make_desc_sw128(smem_addr, lbo_bytes, sbo_bytes);
+  if (base_mode) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
+  return d;
+}
+
+__global__ void __launch_bounds__(IG_THREADS)
+halo64_kernel(const __grid_constant__ HaloPlan p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + HALO_B_BYTES;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sA + HALO_STAGES * HALO_A_STAGE);
+  uint64_t* a_empty = a_full + HALO_STAGES;
+  uint64_t* b_full = a_empty + HALO_STAGES;
+  uint64_t* t_full = b_full + 1;       // [2]
+  uint64_t* t_empty = t_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = (uint32_t)((p.R + 2) * p.pitch) * 128u;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmap_x);
+    prefetch_tmap(&p.tmap_w);
+    for (int s = 0; s < HALO_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    mbar_init(b_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  // (shared memory beyond the box is stale: it only feeds GEMM rows that are discarded, rows are independent in M)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(b_full, (uint32_t)HALO_B_BYTES);
+      for (int t = 0; t < 9; ++t) tma_load_2d(sB + t * 8192, &p.tmap_w, b_full, t * 64, 0);
+      int k = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++k) {
+        const int s = k % HALO_STAGES;
+        mbar_wait(&a_empty[s], ((uint32_t)(k / HALO_STAGES) & 1u) ^ 1u);
+        int t = tile;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h; const int n = t / p.tiles_h;
+        mbar_arrive_expect_tx(&a_full[s], a_bytes);
+        tma_load_4d(sA + s * HALO_A_STAGE, &p.tmap_x, &a_full[s], 0, tw * p.bw - 1, th * p.R - 1, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+      mbar_wait(b_full, 0);
+      int k = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++k) {
+        const int s = k % HALO_STAGES, buf = k & 1;
+        mbar_wait(&t_empty[buf], ((uint32_t)(k >> 1) & 1u) ^ 1u);
+        mbar_wait(&a_full[s], (uint32_t)(k / HALO_STAGES) & 1u);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sA + s * HALO_A_STAGE), b0 = smem_u32(sB);
+        const uint32_t dcol = tmem_d + (uint32_t)(buf * 64);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const uint32_t aa = a0 + (uint32_t)p.off[t] * 128u;
+          const uint32_t bb = b0 + (uint32_t)p.wtap[t] * 8192u;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            mma_bf16_ss(dcol, make_desc_sw128_off(aa + k4 * 32, 16, 1024, p.base_offset_mode), make_desc_sw128(bb + k4 * 32, 16, 1024),
+                        idesc, (t | k4) != 0);
+        }
+        mma_commit(&a_empty[s]);
+        mma_commit(&t_full[buf]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int dr = r / p.pitch, dc = r - dr * p.pitch;
+    int k = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++k) {
+      const int buf = k & 1;
+      int t = tile;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; const int n = t / p.tiles_h;
+      const int hh = th * p.R + dr, ww = tw * p.bw + dc;
+      const bool ok = dr < p.R && dc < p.bw && hh < p.h && ww < p.w;
+      mbar_wait(&t_full[buf], (uint32_t)(k >> 1) & 1u);
+      tc_fence_after();
+      uint32_t v[4][16];
+      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 64);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_x16(taddr + (uint32_t)(c * 16), v[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[buf]);       // accumulator drained: the MMA warp may reuse this buffer
+      if (ok) {
+        bf16* yrow = p.y + (((int64_t)n * p.h + hh) * p.w + ww) * p.out_c + p.out_coff;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[c][j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + c * 16 + j);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(yrow + c * 16);
+          if (p.accumulate) {
+            const uint4 e0 = dst[0], e1 = dst[1];
+            f[0] += bf16lo(e0.x); f[1] += bf16hi(e0.x); f[2] += bf16lo(e0.y); f[3] += bf16hi(e0.y);
+            f[4] += bf16lo(e0.z); f[5] += bf16hi(e0.z); f[6] += bf16lo(e0.w); f[7] += bf16hi(e0.w);
+            f[8] += bf16lo(e1.x); f[9] += bf16hi(e1.x); f[10] += bf16lo(e1.y); f[11] += bf16hi(e1.y);
+            f[12] += bf16lo(e1.z); f[13] += bf16hi(e1.z); f[14] += bf16lo(e1.w); f[15] += bf16hi(e1.w);
+          }
+          uint4 o0, o1;
+          o0.x = pack_bf16(f[0], f[1]);   o0.y = pack_bf16(f[2], f[3]);   o0.z = pack_bf16(f[4], f[5]);   o0.w = pack_bf16(f[6], f[7]);
+          o1.x = pack_bf16(f[8], f[9]);   o1.y = pack_bf16(f[10], f[11]); o1.z = pack_bf16(f[12], f[13]); o1.w = pack_bf16(f[14], f[15]);
+          dst[0] = o0; dst[1] = o1;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<128>(tmem_d);
+}
+
+static void halo_pick(int h, int w, int* R, int* bw) {
+  double best = -1; *R = 1; *bw = 16;
+  for (int b = 8; b <= 45; ++b)
+    for (int r = 1; r * (b + 2) <= 128; ++r) {
+      if ((r + 2) * (b + 2) > 224) continue;
+      const int tw = (w + b - 1) / b, th = (h + r - 1) / r;
+      const double eff = (double)h * w / ((double)tw * th * 128.0);
+      if (eff > best + 1e-9) { best = eff; *R = r; *bw = b; }
+    }
+}
+int halo64_supported(int h, int w) { return h >= 1 && w >= 1; }
+
+int halo64_plan(HaloPlan* p, const bf16* x, int n, int h, int w, int x_ctotal, int x_coff, const bf16* wp, int dgrad) {
+  static const int base_mode = getenv("DBB_HALO_BASE1") ? 1 : 0;
+  p->n = n; p->h = h; p->w = w;
+  halo_pick(h, w, &p->R, &p->bw);
+  p->pitch = p->bw + 2;
+  p->tiles_h = (h + p->R - 1) / p->R; p->tiles_w = (w + p->bw - 1) / p->bw;
+  p->total_tiles = n * p->tiles_h * p->tiles_w;
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw) {
+      const int t = kh * 3 + kw;
+      // box origin is (h0-1, w0-1): fprop reads x[h+kh-1, w+kw-1] -> offset (kh, kw); dgrad reads dy[h+1-kh, w+1-kw] -> (2-kh, 2-kw)
+      const int oh = dgrad ? 2 - kh : kh, ow = dgrad ? 2 - kw : kw;
+      p->off[t] = (int16_t)(oh * p->pitch + ow);
+      p->wtap[t] = (uint8_t)t;
+    }
+  p->base_offset_mode = base_mode;
+  int rc = encode_tmap_nhwc(&p->tmap_x, x, n, h, w, x_ctotal, x_coff, 64, 1, p->R + 2, p->pitch, 1, 1);
+  if (rc) return rc;
+  return encode_weights_public(&p->tmap_w, wp, 576, 64, 64);
+}
+
+int halo64_launch(const HaloPlan& p, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    DBB_CUDA(cudaFuncSetAttribute(halo64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM));
+    attr_done = true;
+  }
+  int grid = p.total_tiles < DBB_NUM_SMS ? p.total_tiles : DBB_NUM_SMS;
+  const char* label = "halo64";
+  if (prof_enabled()) {
+    char tmp[96];
+    snprintf(tmp, sizeof(tmp), "igemm_bn64_m%lld_n64_k576_halo", (long long)p.n * p.h * p.w);
+    label = prof_label(tmp);
+  }
+  DBB_LAUNCH(label, s, halo64_kernel<<<grid, IG_THREADS, HALO_SMEM, s>>>(p));
+  return DBB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
