@@ -34,6 +34,7 @@ struct CompStat {          // one slot per pixel index, touched only at roots
 };
 
 struct CclWs {
+  unsigned* bits;          // [n][h][wq]    packed bitmap, 32 pixels per word
   int* label;              // [n][hw + 1]   (+1: virtual outside node)
   CompStat* stat;          // [n][hw]
   int* blk_count;          // [n][nblk]
@@ -44,9 +45,10 @@ __host__ __device__ inline size_t ccl_align(size_t v) { return (v + 255) / 256 *
 
 static int ccl_nblk(int64_t hw) { return (int)((hw + CCL_THREADS - 1) / CCL_THREADS); }
 
-static CclWs ccl_carve(void* ws, int64_t n, int64_t hw) {
+static CclWs ccl_carve(void* ws, int64_t n, int64_t hw, int64_t h, int64_t wq) {
   CclWs w;
   char* p = (char*)ws;
+  w.bits = (unsigned*)p;    p += ccl_align(sizeof(unsigned) * (size_t)n * h * wq);
   w.label = (int*)p;        p += ccl_align(sizeof(int) * (size_t)n * (hw + 1));
   w.stat = (CompStat*)p;    p += ccl_align(sizeof(CompStat) * (size_t)n * hw);
   w.blk_count = (int*)p;    p += ccl_align(sizeof(int) * (size_t)n * ccl_nblk(hw));
@@ -71,132 +73,203 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Run-based labelling.  A warp owns one 32-pixel segment of a row; the segment's bits come from a packed bitmap
+// (1 bit / pixel), so every neighbourhood test is a few word operations and unions are issued once per pair of
+// touching runs instead of once per pixel.
+// ---------------------------------------------------------------------------------------------
+struct Seg { int img, y, s, x0, nvalid; };
+__device__ __forceinline__ bool seg_of(int64_t widx, int h, int wq, int w, Seg& g) {
+  g.s = (int)(widx % wq); int64_t t = widx / wq;
+  g.y = (int)(t % h); g.img = (int)(t / h);
+  g.x0 = g.s * 32;
+  g.nvalid = w - g.x0 < 32 ? w - g.x0 : 32;
+  return true;
+}
+__device__ __forceinline__ unsigned valid_mask(int nvalid) { return nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u); }
+// lanes where a run (maximal stretch of equal class inside the segment) starts
+__device__ __forceinline__ unsigned run_starts(unsigned cur, int nvalid) {
+  unsigned st = (cur ^ (cur << 1)) | 1u;
+  if (nvalid < 32) st |= 1u << nvalid;     // sentinel: terminates the last valid run
+  return st;
+}
+
+// A: binarize (strict >), pack, write the byte bitmap, label every pixel with the first pixel of its segment run
 __global__ void __launch_bounds__(CCL_THREADS)
-ccl_init_kernel(const float* __restrict__ pred, int c, int h, int w, float thresh, uint8_t* __restrict__ bitmap, int* __restrict__ label) {
-  const int img = blockIdx.y;
+ccl_pack_init_kernel(const float* __restrict__ pred, int c, int n, int h, int w, int wq, float thresh, uint8_t* __restrict__ bitmap,
+                     unsigned* __restrict__ bits, int* __restrict__ label) {
   const int64_t hw = (int64_t)h * w;
-  const float* P = pred + (int64_t)img * c * hw;
-  uint8_t* bm = bitmap + img * hw;
-  int* L = label + img * (hw + 1);
-  for (int64_t i = (int64_t)blockIdx.x * CCL_THREADS + threadIdx.x; i <= hw; i += (int64_t)gridDim.x * CCL_THREADS) {
-    L[i] = (int)i;
-    if (i < hw) bm[i] = P[i] > thresh ? 1 : 0;
+  const int lane = threadIdx.x & 31;
+  const int64_t nseg = (int64_t)n * h * wq;
+  const int64_t wstride = (int64_t)gridDim.x * (CCL_THREADS / 32);
+  for (int64_t widx = (int64_t)blockIdx.x * (CCL_THREADS / 32) + (threadIdx.x >> 5); widx < nseg; widx += wstride) {
+    Seg g; seg_of(widx, h, wq, w, g);
+    const bool in = lane < g.nvalid;
+    const int64_t pix = (int64_t)g.y * w + g.x0 + lane;
+    const float p = in ? pred[(int64_t)g.img * c * hw + pix] : 0.f;
+    const unsigned cur = __ballot_sync(0xffffffffu, in && p > thresh);
+    if (lane == 0) bits[widx] = cur;
+    if (in) {
+      bitmap[g.img * hw + pix] = (cur >> lane) & 1u;
+      const unsigned st = run_starts(cur, g.nvalid) & ((2u << lane) - 1u);
+      label[g.img * (hw + 1) + pix] = (int)((int64_t)g.y * w + g.x0 + (31 - __clz(st)));
+    }
+    if (widx % ((int64_t)h * wq) == 0 && lane == 0) label[g.img * (hw + 1) + hw] = (int)hw;   // virtual outside node
   }
 }
 
+// B: unions between touching runs: across segment boundaries, with the row above (4-connectivity for background,
+// 8-connectivity for foreground), and background runs on the image frame with the virtual outside node
 __global__ void __launch_bounds__(CCL_THREADS)
-ccl_merge_kernel(const uint8_t* __restrict__ bitmap, int h, int w, int* __restrict__ label) {
-  const int img = blockIdx.y;
+ccl_link_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, int* __restrict__ label) {
   const int64_t hw = (int64_t)h * w;
-  const uint8_t* bm = bitmap + img * hw;
-  int* L = label + img * (hw + 1);
-  for (int64_t i = (int64_t)blockIdx.x * CCL_THREADS + threadIdx.x; i < hw; i += (int64_t)gridDim.x * CCL_THREADS) {
-    const int y = (int)(i / w), x = (int)(i - (int64_t)y * w);
-    const uint8_t v = bm[i];
-    if (v) {   // foreground: 8-connectivity
-      if (x > 0 && bm[i - 1]) uf_union(L, (int)i, (int)i - 1);
-      if (y > 0) {
-        if (bm[i - w]) uf_union(L, (int)i, (int)(i - w));
-        if (x > 0 && bm[i - w - 1]) uf_union(L, (int)i, (int)(i - w - 1));
-        if (x < w - 1 && bm[i - w + 1]) uf_union(L, (int)i, (int)(i - w + 1));
+  const int lane = threadIdx.x & 31;
+  const int64_t nseg = (int64_t)n * h * wq;
+  const int64_t wstride = (int64_t)gridDim.x * (CCL_THREADS / 32);
+  for (int64_t widx = (int64_t)blockIdx.x * (CCL_THREADS / 32) + (threadIdx.x >> 5); widx < nseg; widx += wstride) {
+    Seg g; seg_of(widx, h, wq, w, g);
+    if (lane >= g.nvalid) continue;
+    int* L = label + g.img * (hw + 1);
+    const unsigned cur = bits[widx];
+    const unsigned prv = g.s > 0 ? bits[widx - 1] : 0u, nxt = g.s < wq - 1 ? bits[widx + 1] : 0u;
+    const bool has_up = g.y > 0;
+    const unsigned up = has_up ? bits[widx - wq] : 0u;
+    const unsigned upp = (has_up && g.s > 0) ? bits[widx - wq - 1] : 0u, upn = (has_up && g.s < wq - 1) ? bits[widx - wq + 1] : 0u;
+    const unsigned vm = valid_mask(g.nvalid);
+    // neighbours shifted into lane position: L = pixel x-1, R = pixel x+1
+    const unsigned curL = (cur << 1) | (prv >> 31), curR = (cur >> 1) | (nxt << 31);
+    const unsigned upL = (up << 1) | (upp >> 31), upR = (up >> 1) | (upn << 31);
+    const unsigned hasL = g.s > 0 ? 0xffffffffu : 0xfffffffeu;                         // pixel x-1 exists
+    const int x = g.x0 + lane;
+    const int i = g.y * w + x;
+    const unsigned bit = 1u << lane;
+    const bool fg = cur & bit;
+    // horizontal link across the segment boundary (inside a segment the run label already encodes it)
+    if (lane == 0 && g.s > 0 && (((cur & 1u) != 0) == ((prv >> 31) != 0))) uf_union(L, i, i - 1);
+    if (fg) {
+      if (has_up) {
+        const unsigned V = cur & up & ~(curL & upL & hasL);            // first column of a vertical overlap
+        const unsigned DL = cur & ~up & upL & ~curL & hasL;             // diagonal up-left, not implied by a neighbour
+        const unsigned DR = cur & ~up & upR & ~curR;                    // diagonal up-right (upR is 0 beyond the row end)
+        if (V & bit) uf_union(L, i, i - w);
+        if (DL & bit) uf_union(L, i, i - w - 1);
+        if ((DR & bit) && x + 1 < w) uf_union(L, i, i - w + 1);
       }
-    } else {   // background: 4-connectivity; the image frame belongs to the outside region
-      if (x > 0 && !bm[i - 1]) uf_union(L, (int)i, (int)i - 1);
-      if (y > 0 && !bm[i - w]) uf_union(L, (int)i, (int)(i - w));
-      if (x == 0 || y == 0 || x == w - 1 || y == h - 1) uf_union(L, (int)hw, (int)i);
+    } else {
+      const unsigned ncur = ~cur & vm, nup = ~up;
+      if (has_up) {
+        const unsigned ncurL = ~curL, nupL = ~upL;
+        const unsigned V = ncur & nup & ~(ncurL & nupL & hasL);
+        if (V & bit) uf_union(L, i, i - w);
+      }
+      // frame pixels belong to the outside region: one union per run start on the frame
+      const bool frame = g.y == 0 || g.y == h - 1 || x == 0 || x == w - 1;
+      if (frame) {
+        const unsigned st = run_starts(cur, g.nvalid);
+        if ((st & bit) || x == w - 1 || ((g.y != 0 && g.y != h - 1) && x == 0)) uf_union(L, (int)hw, i);
+      }
     }
   }
 }
 
+// C: run-start pixels jump straight to their root; roots zero their statistics slot
 __global__ void __launch_bounds__(CCL_THREADS)
-ccl_compress_kernel(int h, int w, int* __restrict__ label, CompStat* __restrict__ stat) {
-  const int img = blockIdx.y;
+ccl_flatten_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, int* __restrict__ label, CompStat* __restrict__ stat) {
   const int64_t hw = (int64_t)h * w;
-  int* L = label + img * (hw + 1);
-  CompStat* S = stat + img * hw;
-  for (int64_t i = (int64_t)blockIdx.x * CCL_THREADS + threadIdx.x; i <= hw; i += (int64_t)gridDim.x * CCL_THREADS) {
-    const int r = uf_find(L, (int)i);
-    L[i] = r;       // benign race: concurrent finds still terminate at the same root
-    if (r == (int)i && i < hw) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nseg = (int64_t)n * h * wq;
+  const int64_t wstride = (int64_t)gridDim.x * (CCL_THREADS / 32);
+  for (int64_t widx = (int64_t)blockIdx.x * (CCL_THREADS / 32) + (threadIdx.x >> 5); widx < nseg; widx += wstride) {
+    Seg g; seg_of(widx, h, wq, w, g);
+    int* L = label + g.img * (hw + 1);
+    if (widx % ((int64_t)h * wq) == 0 && lane == 0) L[hw] = uf_find(L, (int)hw);
+    if (lane >= g.nvalid) continue;
+    const unsigned st = run_starts(bits[widx], g.nvalid);
+    if (!(st & (1u << lane))) continue;
+    const int i = g.y * w + g.x0 + lane;
+    const int r = uf_find(L, i);
+    L[i] = r;
+    if (r == i) {
       CompStat z;
       z.sum = 0.0; z.acc_sum = 0.0; z.count = 0; z.acc_count = 0;
       z.x0 = w; z.y0 = h; z.x1 = -1; z.y1 = -1;
-      S[i] = z;
+      stat[g.img * hw + i] = z;
     }
   }
 }
 
-// parent region of a root pixel r: the region containing the pixel north of it (outside for the first row)
-__device__ __forceinline__ int parent_of(const int* L, int r, int w, int r_out) { return r < w ? r_out : L[r - w]; }
+// parent region of a root pixel r: the region containing the pixel north of it (outside for the first row).
+// two-hop lookup: a label is either already the root or a run start whose label is the root.
+__device__ __forceinline__ int root2(const int* L, int i) { return L[L[i]]; }
+__device__ __forceinline__ int parent_of(const int* L, int r, int w, int r_out) { return r < w ? r_out : root2(L, r - w); }
 
+// D: final labels + per-component statistics.  One atomic set per (segment run) instead of per pixel: run sums come from
+// a warp prefix sum in float64; the outside region is skipped; foreground pixels that 4-touch an enclosed background
+// region add themselves to that hole's boundary ring.
 __global__ void __launch_bounds__(CCL_THREADS)
-ccl_stats_kernel(const float* __restrict__ pred, int c, const uint8_t* __restrict__ bitmap, int h, int w, const int* __restrict__ label,
-                 CompStat* __restrict__ stat) {
-  const int img = blockIdx.y;
+ccl_stats_kernel(const float* __restrict__ pred, int c, const unsigned* __restrict__ bits, int n, int h, int w, int wq,
+                 int* __restrict__ label, CompStat* __restrict__ stat) {
   const int64_t hw = (int64_t)h * w;
-  const float* P = pred + (int64_t)img * c * hw;
-  const uint8_t* bm = bitmap + img * hw;
-  const int* L = label + img * (hw + 1);
-  CompStat* S = stat + img * hw;
-  const int r_out = L[hw];
   const int lane = threadIdx.x & 31;
-  const int64_t stride = (int64_t)gridDim.x * CCL_THREADS;
-  const int64_t iters = (hw + stride - 1) / stride;
-  for (int64_t it = 0; it < iters; ++it) {
-    const int64_t i = (int64_t)blockIdx.x * CCL_THREADS + threadIdx.x + it * stride;
-    const bool valid = i < hw;
-    int r = -1, x = 0, y = 0;
-    float p = 0.f;
-    if (valid) {
-      r = L[i];
-      if (r == r_out) r = -1;      // the outside region is not a candidate
-      else { y = (int)(i / w); x = (int)(i - (int64_t)y * w); p = P[i]; }
-    }
-    // warp aggregation: lanes with the same root elect a leader that issues one set of atomics
-    const unsigned act = __ballot_sync(0xffffffffu, r >= 0);
-    if (r >= 0) {
-      const unsigned grp = __match_any_sync(act, r);
-      const int leader = __ffs(grp) - 1;
-      double gs; int gc, gx0, gx1, gy0, gy1;
-      if (grp == 0xffffffffu) {          // the common case inside a region: the whole warp is one run -> butterfly
-        gs = (double)p; gc = 32; gx0 = x; gx1 = x; gy0 = y; gy1 = y;
+  const int64_t nseg = (int64_t)n * h * wq;
+  const int64_t wstride = (int64_t)gridDim.x * (CCL_THREADS / 32);
+  for (int64_t widx = (int64_t)blockIdx.x * (CCL_THREADS / 32) + (threadIdx.x >> 5); widx < nseg; widx += wstride) {
+    Seg g; seg_of(widx, h, wq, w, g);
+    int* L = label + g.img * (hw + 1);
+    CompStat* S = stat + g.img * hw;
+    const int r_out = L[hw];
+    const bool in = lane < g.nvalid;
+    const int x = g.x0 + lane;
+    const int i = g.y * w + x;
+    const unsigned cur = bits[widx];
+    const unsigned st = run_starts(cur, g.nvalid);
+    // this lane's run: [a, b]
+    const int a = 31 - __clz(st & ((2u << lane) - 1u));
+    const unsigned later = (lane >= 31) ? 0u : (st & ~((2u << lane) - 1u));
+    const int b = later ? (__ffs(later) - 2) : 31;
+    int r = -1;
+    if (in) r = root2(L, g.y * w + g.x0 + a);            // every lane of a run reads the same word
+    const float p = in ? pred[(int64_t)g.img * c * hw + i] : 0.f;
+    // inclusive prefix sum over the warp in float64
+    double pre = (double)p;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          gs += __shfl_xor_sync(0xffffffffu, gs, o);
-          gx0 = min(gx0, __shfl_xor_sync(0xffffffffu, gx0, o)); gx1 = max(gx1, __shfl_xor_sync(0xffffffffu, gx1, o));
-          gy0 = min(gy0, __shfl_xor_sync(0xffffffffu, gy0, o)); gy1 = max(gy1, __shfl_xor_sync(0xffffffffu, gy1, o));
-        }
-      } else {                           // arbitrary lane subset: every member walks the member list
-        gs = 0.0; gc = 0; gx0 = w; gx1 = -1; gy0 = h; gy1 = -1;
-        for (unsigned m = grp; m; m &= m - 1) {
-          const int src = __ffs(m) - 1;
-          const double so = __shfl_sync(grp, (double)p, src);
-          const int ax = __shfl_sync(grp, x, src), ay = __shfl_sync(grp, y, src);
-          gs += so; gc += 1;
-          gx0 = min(gx0, ax); gx1 = max(gx1, ax); gy0 = min(gy0, ay); gy1 = max(gy1, ay);
-        }
-      }
-      if (lane == leader) {
-        CompStat* t = S + r;
-        atomicAdd(&t->sum, gs);
-        atomicAdd(&t->count, gc);
-        atomicMin(&t->x0, gx0); atomicMax(&t->x1, gx1); atomicMin(&t->y0, gy0); atomicMax(&t->y1, gy1);
-      }
-      // boundary ring of holes: a foreground pixel contributes once to every DISTINCT enclosed region it 4-touches
-      if (bm[i]) {
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += t;
+    }
+    const double pre_b = __shfl_sync(0xffffffffu, pre, b < g.nvalid ? b : g.nvalid - 1 < 0 ? 0 : (b > 31 ? 31 : b));
+    if (!in) continue;
+    if (r != i) L[i] = r;                                  // final label
+    if (r == r_out) continue;
+    if (lane == a) {
+      const int be = b < g.nvalid ? b : g.nvalid - 1;
+      const double run_sum = pre_b - pre + (double)p;
+      CompStat* t = S + r;
+      atomicAdd(&t->sum, run_sum);
+      atomicAdd(&t->count, be - a + 1);
+      atomicMin(&t->x0, g.x0 + a); atomicMax(&t->x1, g.x0 + be); atomicMin(&t->y0, g.y); atomicMax(&t->y1, g.y);
+    }
+    // boundary ring of holes: a foreground pixel contributes once to every DISTINCT enclosed region it 4-touches
+    if ((cur >> lane) & 1u) {
+      const unsigned prv = g.s > 0 ? bits[widx - 1] : 0xffffffffu, nxt = g.s < wq - 1 ? bits[widx + 1] : 0xffffffffu;
+      const bool bgL = x > 0 && !(lane > 0 ? (cur >> (lane - 1)) & 1u : (prv >> 31) & 1u);
+      const bool bgR = x < w - 1 && !(lane < 31 ? (cur >> (lane + 1)) & 1u : nxt & 1u);
+      const bool bgU = g.y > 0 && !((bits[widx - wq] >> lane) & 1u);
+      const bool bgD = g.y < h - 1 && !((bits[widx + wq] >> lane) & 1u);
+      if (bgL | bgR | bgU | bgD) {
         const int pr = parent_of(L, r, w, r_out);
-        int g[4] = {-1, -1, -1, -1};
-        if (x > 0 && !bm[i - 1]) g[0] = L[i - 1];
-        if (x < w - 1 && !bm[i + 1]) g[1] = L[i + 1];
-        if (y > 0 && !bm[i - w]) g[2] = L[i - w];
-        if (y < h - 1 && !bm[i + w]) g[3] = L[i + w];
+        int gq[4] = {-1, -1, -1, -1};
+        if (bgL) gq[0] = root2(L, i - 1);
+        if (bgR) gq[1] = root2(L, i + 1);
+        if (bgU) gq[2] = root2(L, i - w);
+        if (bgD) gq[3] = root2(L, i + w);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const int gk = g[k];
+          const int gk = gq[k];
           if (gk < 0 || gk == pr || gk == r_out) continue;
           bool dup = false;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) if (q < k && g[q] == gk) dup = true;
+          for (int q = 0; q < 4; ++q) if (q < k && gq[q] == gk) dup = true;
           if (dup) continue;
           atomicAdd(&S[gk].acc_sum, (double)p);
           atomicAdd(&S[gk].acc_count, 1);
@@ -311,9 +384,9 @@ ccl_emit_kernel(const uint8_t* __restrict__ bitmap, int h, int w, const int* __r
 using namespace dbb;
 
 extern "C" size_t dbb_postprocess_workspace(int64_t n, int64_t h, int64_t w) {
-  const int64_t hw = h * w;
-  return ccl_align(sizeof(int) * (size_t)n * (hw + 1)) + ccl_align(sizeof(CompStat) * (size_t)n * hw) +
-         2 * ccl_align(sizeof(int) * (size_t)n * ccl_nblk(hw)) + 256;
+  const int64_t hw = h * w, wq = (w + 31) / 32;
+  return ccl_align(sizeof(unsigned) * (size_t)n * h * wq) + ccl_align(sizeof(int) * (size_t)n * (hw + 1)) +
+         ccl_align(sizeof(CompStat) * (size_t)n * hw) + 2 * ccl_align(sizeof(int) * (size_t)n * ccl_nblk(hw)) + 256;
 }
 
 extern "C" int dbb_binarize_ccl_score(const float* pred, int64_t n, int c, int64_t h, int64_t w, float thresh, double box_thresh,
@@ -326,14 +399,18 @@ extern "C" int dbb_binarize_ccl_score(const float* pred, int64_t n, int c, int64
   if (!aligned16(workspace)) return set_error(DBB_EALIGN, "binarize_ccl_score: workspace not 16B aligned");
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t hw = h * w;
-  CclWs ws = ccl_carve(workspace, n, hw);
+  const int wq = (int)((w + 31) / 32);
+  CclWs ws = ccl_carve(workspace, n, hw, h, wq);
+  const int64_t nseg = n * h * wq;
+  int gseg = (int)((nseg + CCL_THREADS / 32 - 1) / (CCL_THREADS / 32));
+  if (gseg > DBB_NUM_SMS * 16) gseg = DBB_NUM_SMS * 16;
   const int nblk = ccl_nblk(hw);
   int gx = nblk < DBB_NUM_SMS * 8 ? nblk : DBB_NUM_SMS * 8;
   const dim3 grid((unsigned)gx, (unsigned)n), gridb((unsigned)nblk, (unsigned)n);
-  DBB_LAUNCH("ccl_init", s, ccl_init_kernel<<<grid, CCL_THREADS, 0, s>>>(pred, c, (int)h, (int)w, thresh, bitmap, ws.label));
-  DBB_LAUNCH("ccl_merge", s, ccl_merge_kernel<<<grid, CCL_THREADS, 0, s>>>(bitmap, (int)h, (int)w, ws.label));
-  DBB_LAUNCH("ccl_compress", s, ccl_compress_kernel<<<grid, CCL_THREADS, 0, s>>>((int)h, (int)w, ws.label, ws.stat));
-  DBB_LAUNCH("ccl_stats", s, ccl_stats_kernel<<<grid, CCL_THREADS, 0, s>>>(pred, c, bitmap, (int)h, (int)w, ws.label, ws.stat));
+  DBB_LAUNCH("ccl_pack_init", s, ccl_pack_init_kernel<<<gseg, CCL_THREADS, 0, s>>>(pred, c, (int)n, (int)h, (int)w, wq, thresh, bitmap, ws.bits, ws.label));
+  DBB_LAUNCH("ccl_link", s, ccl_link_kernel<<<gseg, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label));
+  DBB_LAUNCH("ccl_flatten", s, ccl_flatten_kernel<<<gseg, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat));
+  DBB_LAUNCH("ccl_stats", s, ccl_stats_kernel<<<gseg, CCL_THREADS, 0, s>>>(pred, c, ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat));
   DBB_LAUNCH("ccl_tree", s, ccl_tree_kernel<<<grid, CCL_THREADS, 0, s>>>(bitmap, (int)h, (int)w, ws.label, ws.stat));
   DBB_LAUNCH("ccl_count", s, ccl_count_kernel<<<gridb, CCL_THREADS, 0, s>>>((int)h, (int)w, ws.label, ws.blk_count, nblk));
   DBB_LAUNCH("ccl_scan", s, ccl_scan_kernel<<<(unsigned)n, 1024, 0, s>>>(ws.blk_count, ws.blk_off, nblk, n_cands));

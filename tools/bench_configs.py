@@ -26,7 +26,7 @@ def config4(n=64, s=1024):
     x = synth.images(n, s, s, 0).cuda()
     ms_model = timed(lambda: model(x), 5)
     # post-processing front on synthetic blob maps (random-init P sits near 0.5 everywhere: SURVEY section 8c)
-    maps = np.stack([(synth.prob_map(s, s, 100 + i) - 0.25).clip(0) / 0.75 for i in range(8)])
+    maps = np.stack([((synth.prob_map(s, s, 100 + i) - 0.45) * 8).clip(0, 1) for i in range(8)])
     P = torch.from_numpy(np.concatenate([maps] * (n // 8)))[:, None].cuda()
     rep = SegDetectorRepresenter(thresh=0.25, box_thresh=0.5, unclip_ratio=1.5)
     ms_front = timed(lambda: rep.front(P), 5)
