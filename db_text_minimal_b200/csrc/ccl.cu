@@ -11,15 +11,16 @@
 //   fill(hole border of G)  = G + everything below G + the pixels of G's parent component that are 4-adjacent to G
 //
 // Pipeline (all images in one grid; labels are pixel indices, root = smallest index of the component, so the root IS the
-// raster-first pixel = cv2's discovery point):
-//   1 init      bitmap, label[i] = i                                     read P 4 B, write 1 + 4 B per pixel
-//   2 merge     union-find over backward neighbours (fg: W,NW,N,NE; bg: W,N; border bg pixels join a virtual outside node)
-//   3 compress  label[i] = root(i); roots zero their statistics slot
-//   4 stats     per-component count / float64 sum / bbox with warp-aggregated atomics (match.any), plus the boundary
-//               ring of every hole; the outside region is skipped (it is no candidate and would serialise the atomics)
-//   5 tree      every node adds its own statistics to all its ancestors (parent = region north of the root pixel)
-//   6 rank/emit suffix count of roots in raster order = position in cv2's reverse-discovery order -> candidates are
-//               written already sorted, the first max_cands of them (src/postprocess.py:70,119)
+// raster-first pixel = cv2's discovery point).  A warp owns one 32-pixel row segment of a bit-packed bitmap:
+//   A pack_init  binarize (strict >), pack 32 px / word, byte bitmap, label = first pixel of the segment run   (4 B read, 5 B written / px)
+//   B link       one union per pair of touching runs (fg: vertical + the two diagonals, bg: vertical), segment seams,
+//                frame runs -> virtual outside node; two-level (32-row strips, then strip seams) to keep chains short
+//   C flatten    run starts -> root; roots zero their statistics slot
+//   D stats      final labels + per-run float64 sums (warp prefix sum) -> one atomic set per run; hole boundary rings;
+//                the outside region is skipped (it is no candidate and would serialise the atomics)
+//   E tree       every node adds its statistics to all its ancestors (parent = region north of the root pixel)
+//   F rank/emit  suffix count of roots in raster order = position in cv2's reverse-discovery order -> candidates are
+//                written already sorted, the first max_cands of them (src/postprocess.py:70,119)
 #include "common.cuh"
 
 namespace dbb {
@@ -121,7 +122,7 @@ ccl_pack_init_kernel(const float* __restrict__ pred, int c, int n, int h, int w,
 // B: unions between touching runs: across segment boundaries, with the row above (4-connectivity for background,
 // 8-connectivity for foreground), and background runs on the image frame with the virtual outside node
 __global__ void __launch_bounds__(CCL_THREADS)
-ccl_link_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, int* __restrict__ label) {
+ccl_link_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, int* __restrict__ label, int phase) {
   const int64_t hw = (int64_t)h * w;
   const int lane = threadIdx.x & 31;
   const int64_t nseg = (int64_t)n * h * wq;
@@ -129,10 +130,14 @@ ccl_link_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, 
   for (int64_t widx = (int64_t)blockIdx.x * (CCL_THREADS / 32) + (threadIdx.x >> 5); widx < nseg; widx += wstride) {
     Seg g; seg_of(widx, h, wq, w, g);
     if (lane >= g.nvalid) continue;
+    // two-level merge keeps union-find chains short: phase 0 links everything except across the boundaries of
+    // 32-row strips (chains <= 32), the strips are flattened, phase 1 links the strip boundaries (chains <= H/32)
+    const bool strip_edge = (g.y & 31) == 0;
+    if (phase == 1 && !(strip_edge && g.y > 0)) continue;
     int* L = label + g.img * (hw + 1);
     const unsigned cur = bits[widx];
     const unsigned prv = g.s > 0 ? bits[widx - 1] : 0u, nxt = g.s < wq - 1 ? bits[widx + 1] : 0u;
-    const bool has_up = g.y > 0;
+    const bool has_up = g.y > 0 && (phase == 1 || !strip_edge);
     const unsigned up = has_up ? bits[widx - wq] : 0u;
     const unsigned upp = (has_up && g.s > 0) ? bits[widx - wq - 1] : 0u, upn = (has_up && g.s < wq - 1) ? bits[widx - wq + 1] : 0u;
     const unsigned vm = valid_mask(g.nvalid);
@@ -145,7 +150,7 @@ ccl_link_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, 
     const unsigned bit = 1u << lane;
     const bool fg = cur & bit;
     // horizontal link across the segment boundary (inside a segment the run label already encodes it)
-    if (lane == 0 && g.s > 0 && (((cur & 1u) != 0) == ((prv >> 31) != 0))) uf_union(L, i, i - 1);
+    if (phase == 0 && lane == 0 && g.s > 0 && (((cur & 1u) != 0) == ((prv >> 31) != 0))) uf_union(L, i, i - 1);
     if (fg) {
       if (has_up) {
         const unsigned V = cur & up & ~(curL & upL & hasL);            // first column of a vertical overlap
@@ -164,7 +169,7 @@ ccl_link_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, 
       }
       // frame pixels belong to the outside region: one union per run start on the frame
       const bool frame = g.y == 0 || g.y == h - 1 || x == 0 || x == w - 1;
-      if (frame) {
+      if (frame && phase == 0) {
         const unsigned st = run_starts(cur, g.nvalid);
         if ((st & bit) || x == w - 1 || ((g.y != 0 && g.y != h - 1) && x == 0)) uf_union(L, (int)hw, i);
       }
@@ -174,7 +179,7 @@ ccl_link_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, 
 
 // C: run-start pixels jump straight to their root; roots zero their statistics slot
 __global__ void __launch_bounds__(CCL_THREADS)
-ccl_flatten_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, int* __restrict__ label, CompStat* __restrict__ stat) {
+ccl_flatten_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, int* __restrict__ label, CompStat* __restrict__ stat, int init_stats) {
   const int64_t hw = (int64_t)h * w;
   const int lane = threadIdx.x & 31;
   const int64_t nseg = (int64_t)n * h * wq;
@@ -189,7 +194,7 @@ ccl_flatten_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int w
     const int i = g.y * w + g.x0 + lane;
     const int r = uf_find(L, i);
     L[i] = r;
-    if (r == i) {
+    if (r == i && init_stats) {
       CompStat z;
       z.sum = 0.0; z.acc_sum = 0.0; z.count = 0; z.acc_count = 0;
       z.x0 = w; z.y0 = h; z.x1 = -1; z.y1 = -1;
@@ -408,8 +413,12 @@ extern "C" int dbb_binarize_ccl_score(const float* pred, int64_t n, int c, int64
   int gx = nblk < DBB_NUM_SMS * 8 ? nblk : DBB_NUM_SMS * 8;
   const dim3 grid((unsigned)gx, (unsigned)n), gridb((unsigned)nblk, (unsigned)n);
   DBB_LAUNCH("ccl_pack_init", s, ccl_pack_init_kernel<<<gseg, CCL_THREADS, 0, s>>>(pred, c, (int)n, (int)h, (int)w, wq, thresh, bitmap, ws.bits, ws.label));
-  DBB_LAUNCH("ccl_link", s, ccl_link_kernel<<<gseg, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label));
-  DBB_LAUNCH("ccl_flatten", s, ccl_flatten_kernel<<<gseg, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat));
+  DBB_LAUNCH("ccl_link", s, ccl_link_kernel<<<gseg, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, 0));
+  if (h > 32) {
+    DBB_LAUNCH("ccl_flatten", s, ccl_flatten_kernel<<<gseg, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, 0));
+    DBB_LAUNCH("ccl_link", s, ccl_link_kernel<<<gseg, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, 1));
+  }
+  DBB_LAUNCH("ccl_flatten", s, ccl_flatten_kernel<<<gseg, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, 1));
   DBB_LAUNCH("ccl_stats", s, ccl_stats_kernel<<<gseg, CCL_THREADS, 0, s>>>(pred, c, ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat));
   DBB_LAUNCH("ccl_tree", s, ccl_tree_kernel<<<grid, CCL_THREADS, 0, s>>>(bitmap, (int)h, (int)w, ws.label, ws.stat));
   DBB_LAUNCH("ccl_count", s, ccl_count_kernel<<<gridb, CCL_THREADS, 0, s>>>((int)h, (int)w, ws.label, ws.blk_count, nblk));
