@@ -79,6 +79,21 @@ int halo64_supported(int h, int w);
 int halo64_plan(HaloPlan* p, const bf16* x, int n, int h, int w, int x_ctotal, int x_coff, const bf16* wp, int dgrad);
 int halo64_launch(const HaloPlan& p, cudaStream_t s);
 
+// weight gradient of the 3x3 / stride 1 / 64 -> 64 layers: persistent CTAs walk down a strip of image rows keeping a ring
+// of activation rows in shared memory; every row of x and dy is fetched exactly once; the nine taps are descriptor start
+// offsets into the ring (two horizontally adjacent taps share one M = 128 MMA).
+struct WgradRowPlan {
+  CUtensorMap tmap_x;      // 4-D NHWC, box {64, KP + 2, 1, 1}
+  CUtensorMap tmap_dy;     // 4-D NHWC, box {64, KP, 1, 1}
+  int n, h, w, kp;         // kp = W rounded up to 16
+  int rows_per_chunk, chunks_per_image, nchunks;
+  float* ws;               // partials [chunk][tap][ci][co]
+  float* dw;               // OIHW fp32
+};
+int wgrad_row64_supported(int w);
+int wgrad_row64(const bf16* x, int x_ctotal, int x_coff, const bf16* dy, int dy_ctotal, int dy_coff, int n, int h, int w, float* dw,
+                float* scratch, size_t scratch_bytes, cudaStream_t s);
+
 // weight gradient:  dW[m][n][tap] (+)= sum_pixel A[pixel @ (a-side map)][m] * B[pixel @ tap][n]
 struct WgradPlan {
   CUtensorMap tmap_a;      // M-side operand (dy for Conv2d, x for ConvT): 4-D NHWC, box {64, bw*a_sw, bh*a_sh, bn}

@@ -187,6 +187,8 @@ int conv_wgrad(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const
                float* scratch, size_t scratch_bytes, cudaStream_t s) {
   // dW[co,ci,kh,kw] = sum_{n,i,j} dy[n,i,j,co] * x[n, i*s+kh-pad, j*s+kw-pad, ci]
   const int ho = g.out_h(), wo = g.out_w();
+  if (use_halo(g) && wgrad_row64_supported(g.w) && getenv("DBB_NO_ROW64") == nullptr)
+    return wgrad_row64(x, x_ctotal, x_coff, dy, dy_ctotal, dy_coff, g.n, g.h, g.w, dw, scratch, scratch_bytes, s);
   WgradPlan p;
   memset(&p, 0, sizeof(p));
   p.mn = g.n; p.mh = ho; p.mw = wo;

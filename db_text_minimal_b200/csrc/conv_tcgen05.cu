@@ -342,6 +342,165 @@ int halo64_launch(const HaloPlan& p, cudaStream_t s) {
   return DBB_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// wgrad_row64: dW[co][ci][kh][kw] = sum_{n,i,j} dy[n,i,j,co] * x[n,i+kh-1,j+kw-1,ci]   (3x3, stride 1, 64 -> 64)
+// ---------------------------------------------------------------------------------------------
+constexpr int WR_XSLOTS = 4, WR_DSLOTS = 2;
+
+__global__ void __launch_bounds__(IG_THREADS)
+wgrad_row64_kernel(const __grid_constant__ WgradRowPlan p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int xbytes = (p.kp + 2) * 128, xslot = (xbytes + 1023) & ~1023, dbytes = p.kp * 128;
+  uint8_t* sX = smem;
+  uint8_t* sD = smem + WR_XSLOTS * xslot;
+  uint64_t* xfull = reinterpret_cast<uint64_t*>(sD + WR_DSLOTS * dbytes + 1024);   // +1 KB guard: the junk half of the
+  uint64_t* dfull = xfull + WR_XSLOTS;                                              // single-tap groups reads one row past
+  uint64_t* step_done = dfull + WR_DSLOTS;
+  uint64_t* acc_full = step_done + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x;
+  const int img = chunk / p.chunks_per_image;
+  const int i0 = (chunk % p.chunks_per_image) * p.rows_per_chunk;
+  const int nrows = min(p.rows_per_chunk, p.h - i0);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmap_x);
+    prefetch_tmap(&p.tmap_dy);
+    for (int s = 0; s < WR_XSLOTS; ++s) mbar_init(&xfull[s], 1);
+    for (int s = 0; s < WR_DSLOTS; ++s) mbar_init(&dfull[s], 1);
+    for (int s = 0; s < 4; ++s) mbar_init(&step_done[s], 1);
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      auto load_x = [&](int q) {      // x row (i0 - 1 + q) -> slot q % 4
+        const int s = q % WR_XSLOTS;
+        mbar_arrive_expect_tx(&xfull[s], (uint32_t)xbytes);
+        tma_load_4d(sX + s * xslot, &p.tmap_x, &xfull[s], 0, -1, i0 - 1 + q, img);
+      };
+      auto load_d = [&](int j) {
+        const int s = j % WR_DSLOTS;
+        mbar_arrive_expect_tx(&dfull[s], (uint32_t)dbytes);
+        tma_load_4d(sD + s * dbytes, &p.tmap_dy, &dfull[s], 0, 0, i0 + j, img);
+      };
+      load_x(0); load_x(1); load_x(2); load_d(0);
+      for (int j = 1; j < nrows; ++j) {
+        if (j >= 2) mbar_wait(&step_done[(j - 2) & 3], (uint32_t)((j - 2) >> 2) & 1u);
+        load_x(j + 2);
+        load_d(j);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+      const int kslices = p.kp >> 4;
+      for (int j = 0; j < nrows; ++j) {
+        mbar_wait(&dfull[j % WR_DSLOTS], (uint32_t)(j / WR_DSLOTS) & 1u);
+        for (int q = j; q <= j + 2; ++q) mbar_wait(&xfull[q % WR_XSLOTS], (uint32_t)(q / WR_XSLOTS) & 1u);
+        tc_fence_after();
+        const uint32_t d0 = smem_u32(sD + (j % WR_DSLOTS) * dbytes);
+        for (int ks = 0; ks < kslices; ++ks) {
+          const uint64_t db = make_desc_sw128(d0 + (uint32_t)ks * 2048u, 16, 1024);
+#pragma unroll
+          for (int g = 0; g < 6; ++g) {
+            const int kh = g < 3 ? g : g - 3, kw = g < 3 ? 0 : 2;
+            const uint32_t a0 = smem_u32(sX + ((j + kh) % WR_XSLOTS) * xslot) + (uint32_t)(kw + 16 * ks) * 128u;
+            // M-major A: rows 0..63 = tap (kh,kw), rows 64..127 = tap (kh,kw+1) one pixel (128 B) further
+            mma_bf16_ss(tmem_d + (uint32_t)(g * 64), make_desc_sw128(a0, 128, 1024), db, idesc, (j | ks) != 0);
+          }
+        }
+        mma_commit(&step_done[j & 3]);
+      }
+      mma_commit(acc_full);
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int m = q4 * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_d + ((uint32_t)(q4 * 32) << 16);
+#pragma unroll 1
+    for (int g = 0; g < 6; ++g) {
+      const int kh = g < 3 ? g : g - 3;
+      const int kw = g < 3 ? (m >> 6) : 2;
+      const bool ok = g < 3 || m < 64;
+      float* dst = p.ws + (((int64_t)chunk * 9 + kh * 3 + kw) * 64 + (m & 63)) * 64;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[16];
+        tmem_ld_x16(taddr + (uint32_t)(g * 64 + c * 16), v);
+        tmem_ld_wait();
+        if (ok) {
+          float4* d4 = reinterpret_cast<float4*>(dst + c * 16);
+          d4[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+          d4[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+          d4[2] = make_float4(__uint_as_float(v[8]), __uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
+          d4[3] = make_float4(__uint_as_float(v[12]), __uint_as_float(v[13]), __uint_as_float(v[14]), __uint_as_float(v[15]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_d);
+}
+
+// dW[co][ci][tap] = sum_chunk ws[chunk][tap][ci][co]   (fixed order)
+__global__ void __launch_bounds__(256) wgrad_row64_reduce_kernel(const float* __restrict__ ws, int nchunks, float* __restrict__ dw) {
+  const int i = blockIdx.x * 256 + threadIdx.x;      // over [tap][ci][co]
+  if (i >= 9 * 64 * 64) return;
+  const int co = i & 63, ci = (i >> 6) & 63, tap = i >> 12;
+  float acc = 0.f;
+  for (int c = 0; c < nchunks; ++c) acc += ws[(int64_t)c * 36864 + i];
+  dw[(co * 64 + ci) * 9 + tap] = acc;
+}
+
+int wgrad_row64_supported(int w) { return w >= 1 && ((w + 15) / 16 * 16) + 2 <= 256; }
+
+int wgrad_row64(const bf16* x, int x_ctotal, int x_coff, const bf16* dy, int dy_ctotal, int dy_coff, int n, int h, int w, float* dw,
+                float* scratch, size_t scratch_bytes, cudaStream_t s) {
+  WgradRowPlan p;
+  memset(&p, 0, sizeof(p));
+  p.n = n; p.h = h; p.w = w; p.kp = (w + 15) / 16 * 16;
+  int cpi = DBB_NUM_SMS / n; if (cpi < 1) cpi = 1; if (cpi > h) cpi = h;
+  p.rows_per_chunk = (h + cpi - 1) / cpi;
+  p.chunks_per_image = (h + p.rows_per_chunk - 1) / p.rows_per_chunk;
+  p.nchunks = n * p.chunks_per_image;
+  if (!scratch || scratch_bytes < (size_t)p.nchunks * 36864 * sizeof(float)) return set_error(DBB_EWORKSPACE, "wgrad_row64: scratch too small");
+  p.ws = scratch; p.dw = dw;
+  int rc = encode_tmap_nhwc(&p.tmap_x, x, n, h, w, x_ctotal, x_coff, 64, 1, 1, p.kp + 2, 1, 1);
+  if (rc) return rc;
+  rc = encode_tmap_nhwc(&p.tmap_dy, dy, n, h, w, dy_ctotal, dy_coff, 64, 1, 1, p.kp, 1, 1);
+  if (rc) return rc;
+  const int xslot = ((p.kp + 2) * 128 + 1023) & ~1023;
+  const int smem = WR_XSLOTS * xslot + WR_DSLOTS * p.kp * 128 + 1024 + 256 + 1024;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    DBB_CUDA(cudaFuncSetAttribute(wgrad_row64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  const char* label = "wgrad_row64";
+  if (prof_enabled()) {
+    char tmp[96];
+    snprintf(tmp, sizeof(tmp), "wgrad_nt64_m64_n64_t9_k%lld_row", (long long)n * h * w);
+    label = prof_label(tmp);
+  }
+  DBB_LAUNCH(label, s, wgrad_row64_kernel<<<p.nchunks, IG_THREADS, smem, s>>>(p));
+  DBB_LAUNCH("wgrad_reduce", s, wgrad_row64_reduce_kernel<<<(36864 + 255) / 256, 256, 0, s>>>(p.ws, p.nchunks, dw));
+  return DBB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // weight gradient
 // ---------------------------------------------------------------------------------------------
