@@ -128,7 +128,8 @@ dbloss_reduce_kernel(const float* __restrict__ preds, const float* __restrict__ 
   for (int i = 0; i < 9; ++i) acc[i] = 0.f;
 
   for (int64_t v = (int64_t)blockIdx.x * LOSS_THREADS + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * LOSS_THREADS) {
-    const int64_t n = v / hwv, r = (v - n * hwv) * VEC;
+    const unsigned n32 = (unsigned)v / (unsigned)hwv;          // nvec < 2^32 (host check): 32-bit divide
+    const int64_t n = n32, r = (int64_t)((unsigned)v - n32 * (unsigned)hwv) * VEC;
     const float* pp = preds + (n * cch) * hw + r;
     const int64_t go = n * hw + r;
     Vec4 P = Loader<VEC>::ld(pp), T = Loader<VEC>::ld(pp + hw);
@@ -270,7 +271,8 @@ dbloss_select_pass2_kernel(const float* __restrict__ preds, const float* __restr
       float hit[4];
       int cnt = 0;
       if (v < nvec) {
-        const int64_t n = v / hwv, r = (v - n * hwv) * VEC;
+        const unsigned n32 = (unsigned)v / (unsigned)hwv;
+        const int64_t n = n32, r = (int64_t)((unsigned)v - n32 * (unsigned)hwv) * VEC;
         Vec4 P = Loader<VEC>::ld(preds + (n * cch) * hw + r);
         Vec4 G = Loader<VEC>::ld(gts + n * hw + r), M = Loader<VEC>::ld(gts + px + n * hw + r);
 #pragma unroll
@@ -446,7 +448,8 @@ dbloss_bwd_kernel(const float* __restrict__ preds, const float* __restrict__ gts
   const bool any_neg = st->n_neg > 0;
 
   for (int64_t v = (int64_t)blockIdx.x * LOSS_THREADS + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * LOSS_THREADS) {
-    const int64_t n = v / hwv, r = (v - n * hwv) * VEC;
+    const unsigned n32 = (unsigned)v / (unsigned)hwv;
+    const int64_t n = n32, r = (int64_t)((unsigned)v - n32 * (unsigned)hwv) * VEC;
     const int64_t po = (n * cch) * hw + r, go = n * hw + r;
     Vec4 P = Loader<VEC>::ld(preds + po), T = Loader<VEC>::ld(preds + po + hw);
     Vec4 G = Loader<VEC>::ld(gts + go), M = Loader<VEC>::ld(gts + px + go);
@@ -538,6 +541,7 @@ extern "C" int dbb_dbloss_fwd(const float* preds, const float* gts, int64_t n, i
   if (n <= 0 || h <= 0 || w <= 0 || (c != 2 && c != 3) || (reduction != 0 && reduction != 1))
     return set_error(DBB_EINVAL, "dbloss_fwd: bad shape or reduction");
   if (!aligned16(preds) || !aligned16(gts) || !aligned16(workspace)) return set_error(DBB_EALIGN, "dbloss_fwd: pointer not 16B aligned");
+  if (n * h * w >= ((int64_t)1 << 32)) return set_error(DBB_EUNSUPPORTED, "dbloss_fwd: more than 2^32 pixels");
   if (workspace_bytes < dbb_dbloss_workspace(n, c, h, w, reduction)) return set_error(DBB_EWORKSPACE, "dbloss_fwd: workspace too small");
   const int64_t hw = h * w;
   LossParams lp{alpha, beta, negative_ratio, eps, n * hw, c == 3};

@@ -187,9 +187,10 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const bf16* __rest
                                                               const bf16* __restrict__ res, int relu, bf16* __restrict__ out,
                                                               int out_ctotal, int out_coff) {
   const int groups = c / 8;
+  const int lg = 31 - __clz(groups);            // groups is a power of two (check_c): shifts instead of 64-bit divides
   const int64_t total = P * groups;
   for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
-    const int64_t p = i / groups; const int g = (int)(i - p * groups);
+    const int64_t p = i >> lg; const int g = (int)(i & (groups - 1));
     const F8 x = ld8s(z + p * c + g * 8);
     const F8 sc = ldf8(stats4 + g * 8), sh = ldf8(stats4 + c + g * 8);
     F8 y;
@@ -254,9 +255,10 @@ bn_bwd_apply_kernel(const bf16* __restrict__ dout, int dout_ctotal, int dout_cof
                     const float* __restrict__ stats4, const float* __restrict__ coef3, bf16* __restrict__ dz,
                     bf16* __restrict__ dsum) {
   const int groups = c / 8;
+  const int lg = 31 - __clz(groups);
   const int64_t total = P * groups;
   for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
-    const int64_t p = i / groups; const int g = (int)(i - p * groups);
+    const int64_t p = i >> lg; const int g = (int)(i & (groups - 1));
     F8 dy = ld8s(dout + p * dout_ctotal + dout_coff + g * 8);
     if (mask_src) {
       const F8 m = ld8s(mask_src + p * mask_ctotal + mask_coff + g * 8);
@@ -296,7 +298,7 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ partials, int n
   if ((threadIdx.x & 31) == 0) out[ch] = (float)s;
 }
 
-static int check_c(int c) { return (c % 8 == 0 && c >= 8 && c <= 2048 && EW_THREADS % (c / 8) == 0) ? 0 : 1; }
+static int check_c(int c) { return (c % 8 == 0 && c >= 8 && c <= 2048 && EW_THREADS % (c / 8) == 0 && ((c / 8) & (c / 8 - 1)) == 0) ? 0 : 1; }
 
 
 // ---------------------------------------------------------------------------------------------
@@ -488,8 +490,9 @@ __global__ void __launch_bounds__(EW_THREADS) maxpool_fwd_kernel(const bf16* __r
   const int groups = c / 8;
   const int64_t total = (int64_t)n * oh * ow * groups;
   for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
-    const int g = (int)(i % groups); int64_t t = i / groups;
-    const int x0 = (int)(t % ow); t /= ow; const int y0 = (int)(t % oh); const int b = (int)(t / oh);
+    const unsigned u = (unsigned)i;                       // total < 2^32 (checked on the host): 32-bit divides
+    const int g = (int)(u % (unsigned)groups); unsigned t = u / (unsigned)groups;
+    const int x0 = (int)(t % (unsigned)ow); t /= (unsigned)ow; const int y0 = (int)(t % (unsigned)oh); const int b = (int)(t / (unsigned)oh);
     F8 best; uint8_t bi[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { best.v[j] = -INFINITY; bi[j] = 0; }
@@ -521,8 +524,9 @@ __global__ void __launch_bounds__(EW_THREADS) maxpool_bwd_kernel(const bf16* __r
   const int groups = c / 8;
   const int64_t total = (int64_t)n * h * w * groups;
   for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
-    const int g = (int)(i % groups); int64_t t = i / groups;
-    const int xx = (int)(t % w); t /= w; const int yy = (int)(t % h); const int b = (int)(t / h);
+    const unsigned u = (unsigned)i;
+    const int g = (int)(u % (unsigned)groups); unsigned t = u / (unsigned)groups;
+    const int xx = (int)(t % (unsigned)w); t /= (unsigned)w; const int yy = (int)(t % (unsigned)h); const int b = (int)(t / (unsigned)h);
     F8 acc;
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
@@ -547,8 +551,11 @@ __global__ void __launch_bounds__(EW_THREADS) maxpool_bwd_kernel(const bf16* __r
     st8(dx + (((int64_t)b * h + yy) * w + xx) * c + g * 8, acc);
   }
 }
+static int fits32(int64_t total, const char* who) { return total < ((int64_t)1 << 32) ? 0 : set_error(DBB_EUNSUPPORTED, who); }
+
 int maxpool_fwd(const bf16* x, int n, int h, int w, int c, bf16* y, uint8_t* argmax, cudaStream_t s) {
   const int oh = (h + 2 - 3) / 2 + 1, ow = (w + 2 - 3) / 2 + 1;
+  if (fits32((int64_t)n * h * w * (c / 8), "maxpool: tensor too large for 32-bit indexing")) return DBB_EUNSUPPORTED;
   DBB_LAUNCH("maxpool_fwd", s, maxpool_fwd_kernel<<<stream_grid((int64_t)n * oh * ow * (c / 8)), EW_THREADS, 0, s>>>(x, n, h, w, c, oh, ow, y, argmax));
   return DBB_OK;
 }
@@ -571,8 +578,9 @@ __global__ void __launch_bounds__(EW_THREADS) upsample_fwd_kernel(const bf16* __
   const int groups = c / 8;
   const int64_t total = (int64_t)n * h * w * groups;
   for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
-    const int g = (int)(i % groups); int64_t t = i / groups;
-    const int xx = (int)(t % w); t /= w; const int yy = (int)(t % h); const int b = (int)(t / h);
+    const unsigned u = (unsigned)i;
+    const int g = (int)(u % (unsigned)groups); unsigned t = u / (unsigned)groups;
+    const int xx = (int)(t % (unsigned)w); t /= (unsigned)w; const int yy = (int)(t % (unsigned)h); const int b = (int)(t / (unsigned)h);
     const int sy = nearest_src(yy, sch, hs), sx = nearest_src(xx, scw, ws);
     F8 v = ld8(xs + (((int64_t)b * hs + sy) * ws + sx) * c + g * 8);
     const int64_t pix = ((int64_t)b * h + yy) * w + xx;
@@ -590,8 +598,9 @@ __global__ void __launch_bounds__(EW_THREADS) upsample_bwd_kernel(const bf16* __
   const int groups = c / 8;
   const int64_t total = (int64_t)n * hs * ws * groups;
   for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
-    const int g = (int)(i % groups); int64_t t = i / groups;
-    const int sx = (int)(t % ws); t /= ws; const int sy = (int)(t % hs); const int b = (int)(t / hs);
+    const unsigned u = (unsigned)i;
+    const int g = (int)(u % (unsigned)groups); unsigned t = u / (unsigned)groups;
+    const int sx = (int)(t % (unsigned)ws); t /= (unsigned)ws; const int sy = (int)(t % (unsigned)hs); const int b = (int)(t / (unsigned)hs);
     // destination rows/cols that read (sy, sx): a contiguous range (the map is monotone)
     int y0 = (int)ceilf((float)sy / sch) - 2; if (y0 < 0) y0 = 0;
     while (y0 < h && nearest_src(y0, sch, hs) < sy) ++y0;
@@ -640,7 +649,8 @@ __global__ void __launch_bounds__(EW_THREADS) image_to_s2d_kernel(const float* _
   const int ph = hs + 3, pw = ws + 3;
   const int64_t total = (int64_t)n * ph * pw;
   for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
-    const int q = (int)(i % pw); int64_t t = i / pw; const int r = (int)(t % ph); const int b = (int)(t / ph);
+    const unsigned u = (unsigned)i;
+    const int q = (int)(u % (unsigned)pw); const unsigned t = u / (unsigned)pw; const int r = (int)(t % (unsigned)ph); const int b = (int)(t / (unsigned)ph);
     const int si = r - 2, sj = q - 2;
     float v[16];
 #pragma unroll

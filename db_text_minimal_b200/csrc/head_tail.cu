@@ -35,9 +35,9 @@ struct HtRing {
   int tiles_per_row, h2, w2;
   int64_t ntiles;
   __device__ __forceinline__ void issue(int64_t tile, int stage) const {
-    const int tr = (int)(tile % tiles_per_row);
-    const int64_t row = tile / tiles_per_row;
-    const bf16* src = zt + (row * w2 + (int64_t)tr * 64) * 128;
+    const unsigned row = (unsigned)tile / (unsigned)tiles_per_row;
+    const unsigned tr = (unsigned)tile - row * (unsigned)tiles_per_row;
+    const bf16* src = zt + ((int64_t)row * w2 + (int64_t)tr * 64) * 128;
     mbar_arrive_expect_tx(&full[stage], HT_TILE_BYTES);
     bulk_load(buf + stage * HT_TILE_BYTES, src, HT_TILE_BYTES, &full[stage]);
   }
@@ -86,6 +86,9 @@ __device__ __forceinline__ HtF8 ht_lds8(const bf16* p) {
   return r;
 }
 
+// packed fp32x2 FMA (sm_100 FFMA2): two taps per instruction halve the FMA issue count of these issue-bound kernels
+__device__ __forceinline__ float2 fma2(float a, float2 w, float2 acc) { return __ffma2_rn(make_float2(a, a), w, acc); }
+
 // per-lane constants: lane l = (branch = l>>3, channel group = l&7) owns channels ch0 = branch*64 + 8*(l&7) ..
 struct LaneConst {
   float sc[8], sh[8], w[8][4];
@@ -103,10 +106,12 @@ __device__ __forceinline__ void load_lane_const(LaneConst& L, int l16, const flo
   }
 }
 
-__device__ __forceinline__ void tile_coords(int64_t tile, int tiles_per_row, int h2, int& n, int& i, int& j0) {
-  const int tr = (int)(tile % tiles_per_row);
-  const int64_t row = tile / tiles_per_row;
-  i = (int)(row % h2); n = (int)(row / h2); j0 = tr * HT_TILE;
+// 32-bit index math on purpose: a 64-bit divide is a ~100-instruction software loop and these kernels are issue-bound
+__device__ __forceinline__ void tile_coords(int64_t tile64, int tiles_per_row, int h2, int& n, int& i, int& j0) {
+  const unsigned tile = (unsigned)tile64;
+  const unsigned row = tile / (unsigned)tiles_per_row;
+  const unsigned tr = tile - row * (unsigned)tiles_per_row;
+  n = (int)(row / (unsigned)h2); i = (int)(row - (unsigned)n * (unsigned)h2); j0 = (int)tr * HT_TILE;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -142,12 +147,14 @@ head_tail_fwd_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w2, con
       if (j0 + px < w2) {
         const bf16* zp = zrow + (int64_t)(j0 + px) * 128 + l16 * 8;
         const HtF8 z = PIPE ? ht_lds8(zp) : ht_ld8(zp);
+        float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float a = fmaxf(fmaf(z.v[j], L.sc[j], L.sh[j]), 0.f);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) acc[t] = fmaf(a, L.w[j][t], acc[t]);
+          a01 = fma2(a, make_float2(L.w[j][0], L.w[j][1]), a01);
+          a23 = fma2(a, make_float2(L.w[j][2], L.w[j][3]), a23);
         }
+        acc[0] = a01.x; acc[1] = a01.y; acc[2] = a23.x; acc[3] = a23.y;
       }
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -256,9 +263,12 @@ head_tail_bwd_reduce_kernel(const bf16* __restrict__ zt, int n_img, int h2, int 
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float a = fmaxf(fmaf(z.v[j], L.sc[j], L.sh[j]), 0.f);
-          float da = 0.f;
-#pragma unroll
-          for (int t = 0; t < 4; ++t) { accW[j][t] = fmaf(a, dz[t], accW[j][t]); da = fmaf(dz[t], L.w[j][t], da); }
+          const float2 w01 = fma2(a, make_float2(dz[0], dz[1]), make_float2(accW[j][0], accW[j][1]));
+          const float2 w23 = fma2(a, make_float2(dz[2], dz[3]), make_float2(accW[j][2], accW[j][3]));
+          accW[j][0] = w01.x; accW[j][1] = w01.y; accW[j][2] = w23.x; accW[j][3] = w23.y;
+          const float2 d2 = __ffma2_rn(make_float2(dz[0], dz[1]), make_float2(L.w[j][0], L.w[j][1]),
+                                       __fmul2_rn(make_float2(dz[2], dz[3]), make_float2(L.w[j][2], L.w[j][3])));
+          const float da = d2.x + d2.y;
           const float dy = a > 0.f ? da : 0.f;
           accS[j] += dy;
           accQ[j] = fmaf(dy, (z.v[j] - mean[j]) * inv[j], accQ[j]);
@@ -384,9 +394,9 @@ head_tail_bwd_apply_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float a = fmaf(z.v[j], L.sc[j], L.sh[j]);
-          float da = 0.f;
-#pragma unroll
-          for (int t = 0; t < 4; ++t) da = fmaf(dz[t], L.w[j][t], da);
+          const float2 d2 = __ffma2_rn(make_float2(dz[0], dz[1]), make_float2(L.w[j][0], L.w[j][1]),
+                                       __fmul2_rn(make_float2(dz[2], dz[3]), make_float2(L.w[j][2], L.w[j][3])));
+          const float da = d2.x + d2.y;
           const float dy = a > 0.f ? da : 0.f;
           o[j] = ca[j] * (dy - c1[j] - (z.v[j] - mean[j]) * inv[j] * c2[j]);
         }

@@ -20,6 +20,12 @@ CONV_CASES = [
     (2, 18, 25, 128, 256, 3, 2, 1),
     (3, 5, 7, 512, 64, 1, 1, 0),        # tiny maps: tiles span several images
     (16, 20, 20, 512, 512, 3, 1, 1),
+    # 64 -> 64 3x3: shifted-window (halo64) fprop/dgrad and row-ring (wgrad_row64) kernels on awkward extents
+    (3, 7, 33, 64, 64, 3, 1, 1),
+    (1, 50, 240, 64, 64, 3, 1, 1),      # widest image the row-ring kernel takes (KP + 2 <= 256)
+    (1, 20, 250, 64, 64, 3, 1, 1),      # wider: falls back to the generic split-K wgrad
+    (20, 12, 16, 64, 64, 3, 1, 1),      # more images than row chunks per image
+    (2, 1, 40, 64, 64, 3, 1, 1),        # single-row images
 ]
 CONVT_CASES = [(2, 20, 24, 64, 64), (1, 9, 13, 64, 64), (2, 40, 40, 128, 64)]
 
