@@ -120,7 +120,9 @@ int convt_fprop(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, cons
   p.out_sh = p.out_sw = 2; p.out_oh = p.out_ow = 0;
   p.bias = bias;
   const int64_t m_tiles = ((int64_t)g.n * g.h * g.w + 127) / 128;
-  int rc = igemm_plan_init(&p, x, g.n, g.h, g.w, x_ctotal, x_coff, g.cin, wp_cls, g.cin, 4 * g.cout, pick_block_n(4 * g.cout, m_tiles));
+  (void)m_tiles;
+  // one k-iteration per tile and a store-bound pixel-shuffle epilogue: 128-wide tiles (4 CTAs/SM) measured fastest
+  int rc = igemm_plan_init(&p, x, g.n, g.h, g.w, x_ctotal, x_coff, g.cin, wp_cls, g.cin, 4 * g.cout, 128);
   if (rc) return rc;
   return igemm_launch(p, s);
 }

@@ -807,10 +807,25 @@ static int igemm_launch_t(const IgemmPlan& p, cudaStream_t s) {
 
 int igemm_launch(const IgemmPlan& p, cudaStream_t s) {
   if (p.cin % 64 != 0 || p.ntaps < 1 || p.ntaps > IGEMM_MAX_TAPS) return set_error(DBB_EUNSUPPORTED, "igemm: cin must be a multiple of 64, taps <= 16");
+  // The k-loop of a tile has ntaps*cin/64 iterations.  Short loops (1x1 convolutions, ConvTranspose, conv1) cannot use a
+  // deep ring anyway; giving them 1-2 stages shrinks shared memory so that more CTAs are resident per SM and their
+  // load / MMA / epilogue phases overlap across CTAs (TMEM allows 512 / BLOCK_N of them).
+  const int kiters = p.ntaps * (p.cin >> 6);
+  static const bool deep_only = getenv("DBB_DEEP_RING") != nullptr;      // A/B switch
+  const int depth = deep_only ? 4 : (kiters <= 1 ? 1 : (kiters <= 4 ? 2 : 4));
   switch (p.block_n) {
-    case 64: return igemm_launch_t<64, 4>(p, s);     // 24 KB/stage -> 96 KB, 2 CTAs/SM
-    case 128: return igemm_launch_t<128, 3>(p, s);   // 32 KB/stage -> 96 KB, 2 CTAs/SM
-    case 256: return igemm_launch_t<256, 4>(p, s);   // 48 KB/stage -> 192 KB, 1 CTA/SM
+    case 64:
+      if (depth == 1) return igemm_launch_t<64, 1>(p, s);     // 24 KB -> 8 CTAs/SM
+      if (depth == 2) return igemm_launch_t<64, 2>(p, s);     // 48 KB -> 4 CTAs/SM
+      return igemm_launch_t<64, 4>(p, s);                     // 96 KB -> 2 CTAs/SM
+    case 128:
+      if (depth == 1) return igemm_launch_t<128, 1>(p, s);    // 32 KB -> 4 CTAs/SM (TMEM)
+      if (depth == 2) return igemm_launch_t<128, 2>(p, s);    // 64 KB -> 3 CTAs/SM
+      return igemm_launch_t<128, 3>(p, s);                    // 96 KB -> 2 CTAs/SM
+    case 256:
+      if (depth == 1) return igemm_launch_t<256, 1>(p, s);    // 48 KB -> 2 CTAs/SM (TMEM)
+      if (depth == 2) return igemm_launch_t<256, 2>(p, s);    // 96 KB -> 2 CTAs/SM
+      return igemm_launch_t<256, 4>(p, s);                    // 192 KB -> 1 CTA/SM
     default: return set_error(DBB_EUNSUPPORTED, "igemm: block_n must be 64, 128 or 256");
   }
 }
