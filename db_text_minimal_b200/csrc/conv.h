@@ -11,6 +11,20 @@ typedef __nv_bfloat16 bf16;
 
 constexpr int IGEMM_MAX_TAPS = 16;
 
+// Training-mode BatchNorm statistics of a convolution output, fused into the convolution's epilogue: per-channel sum and
+// sum of squares of the bf16-rounded outputs -> fp64 atomics into gacc ([2][c] doubles, zero on entry, left zero) -> the
+// last CTA to arrive (ticket in `counter`, zero on entry, left zero) writes stats4 = [scale | shift | mean | invstd] and
+// the running statistics.  Up to two parameter segments (the two head branches share one 128-channel tensor).
+struct BnFinSeg { const float* gamma; const float* beta; float* rmean; float* rvar; int coff, cn; };
+struct BnFin { BnFinSeg seg[2]; int nseg; float momentum, eps; float* stats4; };
+struct ConvStats {
+  int enabled;
+  double count;            // pixels per channel of the normalised tensor (N*H*W of y)
+  double* gacc;
+  unsigned* counter;
+  BnFin fin;               // channel indices are positions in y's channel dimension (width out_c)
+};
+
 // One implicit-GEMM launch:  Y[pixel, co] = sum_{tap, ci} X[pixel @ tap, ci] * Wp[co, tap*cin + ci]  (+ bias[co])
 //
 // "pixel" runs over an M-space grid (mn, mh, mw); row (n,h,w) reads X at (n, h*in_sh + dh[tap], w*in_sw + dw[tap])
@@ -38,6 +52,7 @@ struct IgemmPlan {
   const float* bias;       // may be null
   int accumulate;          // 1: Y += result (gradient fan-in), 0: overwrite
   int cls_cols;            // > 0: pixel-shuffle epilogue, GEMM column = class*cls_cols + channel (ConvTranspose2d k2 s2)
+  ConvStats st;            // optional fused BatchNorm statistics of y
 };
 
 // weight packing: fp32 parameter -> bf16 GEMM B matrix [rows][K] (K-major)
@@ -74,6 +89,7 @@ struct HaloPlan {
   const float* bias;
   int accumulate;
   int base_offset_mode;    // descriptor base_offset: 1 = (addr >> 7) & 7, 0 = always 0 (tuning / bring-up)
+  ConvStats st;            // optional fused BatchNorm statistics of y
 };
 int halo64_supported(int h, int w);
 int halo64_plan(HaloPlan* p, const bf16* x, int n, int h, int w, int x_ctotal, int x_coff, const bf16* wp, int dgrad);

@@ -22,7 +22,7 @@ static bool use_halo(const ConvGeom& g) {
 }
 
 int conv_fprop(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const bf16* wp, const float* bias, bf16* y,
-               int y_ctotal, int y_coff, cudaStream_t s) {
+               int y_ctotal, int y_coff, cudaStream_t s, const ConvStats* st) {
   const int ho = g.out_h(), wo = g.out_w();
   if (use_halo(g)) {
     HaloPlan hp;
@@ -30,6 +30,7 @@ int conv_fprop(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const
     int rc = halo64_plan(&hp, x, g.n, g.h, g.w, x_ctotal, x_coff, wp, 0);
     if (rc) return rc;
     hp.y = y; hp.out_c = y_ctotal; hp.out_coff = y_coff; hp.bias = bias; hp.accumulate = 0;
+    if (st) { hp.st = *st; hp.st.enabled = 1; hp.st.count = (double)g.n * ho * wo; }
     return halo64_launch(hp, s);
   }
   IgemmPlan p;
@@ -46,6 +47,7 @@ int conv_fprop(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const
   p.y = y; p.out_h = ho; p.out_w = wo; p.out_c = y_ctotal; p.out_coff = y_coff;
   p.out_sh = p.out_sw = 1; p.out_oh = p.out_ow = 0;
   p.bias = bias;
+  if (st) { p.st = *st; p.st.enabled = 1; p.st.count = (double)g.n * ho * wo; }
   const int64_t m_tiles = ((int64_t)g.n * ho * wo + 127) / 128;
   int rc = igemm_plan_init(&p, x, g.n, g.h, g.w, x_ctotal, x_coff, g.cin, wp, p.ntaps * g.cin, g.cout, pick_block_n(g.cout, m_tiles));
   if (rc) return rc;
@@ -106,7 +108,7 @@ int conv_dgrad(const ConvGeom& g, const bf16* dy, const bf16* wp_t, bf16* dx, cu
 }
 
 int convt_fprop(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const bf16* wp_cls, const float* bias, bf16* y,
-                int y_ctotal, int y_coff, cudaStream_t s) {
+                int y_ctotal, int y_coff, cudaStream_t s, const ConvStats* st) {
   // ConvTranspose2d(k=2, s=2): y[n,2i+a,2j+b,co] = sum_ci x[n,i,j,ci] * W[ci,co,a,b] + bias[co].
   // ONE GEMM [pixels, cin] x [cin, 4*cout] (packed weights are [class][co][ci] = 4*cout rows) with a pixel-shuffle epilogue.
   IgemmPlan p;
@@ -119,8 +121,7 @@ int convt_fprop(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, cons
   p.y = y; p.out_h = 2 * g.h; p.out_w = 2 * g.w; p.out_c = y_ctotal; p.out_coff = y_coff;
   p.out_sh = p.out_sw = 2; p.out_oh = p.out_ow = 0;
   p.bias = bias;
-  const int64_t m_tiles = ((int64_t)g.n * g.h * g.w + 127) / 128;
-  (void)m_tiles;
+  if (st) { p.st = *st; p.st.enabled = 1; p.st.count = (double)g.n * g.h * g.w * 4.0; }
   // one k-iteration per tile and a store-bound pixel-shuffle epilogue: 128-wide tiles (4 CTAs/SM) measured fastest
   int rc = igemm_plan_init(&p, x, g.n, g.h, g.w, x_ctotal, x_coff, g.cin, wp_cls, g.cin, 4 * g.cout, 128);
   if (rc) return rc;
@@ -230,7 +231,7 @@ static int conv1_tmap(CUtensorMap* m, const bf16* s2d, int n, int hs, int ws, in
   return encode_tmap_raw4(m, s2d, dims, strides, box);
 }
 
-int conv1_fprop(int n, int h, int w, const bf16* s2d, const bf16* wp, bf16* y, cudaStream_t s) {
+int conv1_fprop(int n, int h, int w, const bf16* s2d, const bf16* wp, bf16* y, cudaStream_t s, const ConvStats* st) {
   const int hs = (h + 1) / 2, ws = (w + 1) / 2;
   IgemmPlan p;
   memset(&p, 0, sizeof(p));
@@ -242,6 +243,7 @@ int conv1_fprop(int n, int h, int w, const bf16* s2d, const bf16* wp, bf16* y, c
   p.y = y; p.out_h = hs; p.out_w = ws; p.out_c = 64; p.out_coff = 0;
   p.out_sh = p.out_sw = 1;
   p.cin = 64; p.block_n = 64;
+  if (st) { p.st = *st; p.st.enabled = 1; p.st.count = (double)n * hs * ws; }
   choose_box(128, p.mn, p.mh, p.mw, &p.bn, &p.bh, &p.bw);
   p.tiles_n = (p.mn + p.bn - 1) / p.bn; p.tiles_h = (p.mh + p.bh - 1) / p.bh; p.tiles_w = (p.mw + p.bw - 1) / p.bw;
   int rc = conv1_tmap(&p.tmap_x, s2d, n, hs, ws, p.bn, p.bh, p.bw);

@@ -13,8 +13,9 @@ struct ConvGeom {
 };
 
 // wp: packed by pack_weights mode 0 ; x may be a channel slice [x_coff, x_coff+cin) of a wider NHWC tensor
+// st (optional): fuse the training-mode BatchNorm statistics of y into the epilogue (conv.h: ConvStats; count is filled here)
 int conv_fprop(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const bf16* wp, const float* bias, bf16* y,
-               int y_ctotal, int y_coff, cudaStream_t s);
+               int y_ctotal, int y_coff, cudaStream_t s, const ConvStats* st = nullptr);
 // wp_t: packed by pack_weights mode 1
 // dy may be a channel slice [dy_coff, dy_coff+cout) of a dy_ctotal-wide tensor (0 = compact); accumulate: dx += result
 int conv_dgrad(const ConvGeom& g, const bf16* dy, const bf16* wp_t, bf16* dx, cudaStream_t s, int accumulate = 0);
@@ -22,13 +23,13 @@ int conv_wgrad(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const
                float* scratch, size_t scratch_bytes, cudaStream_t s);
 // ConvTranspose2d(k=2, s=2); wp_cls: mode 2, wp_t: mode 3
 int convt_fprop(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const bf16* wp_cls, const float* bias, bf16* y,
-                int y_ctotal, int y_coff, cudaStream_t s);
+                int y_ctotal, int y_coff, cudaStream_t s, const ConvStats* st = nullptr);
 int convt_dgrad(const ConvGeom& g, const bf16* dy, int dy_ctotal, int dy_coff, const bf16* wp_t, bf16* dx, int dx_ctotal,
                 int dx_coff, cudaStream_t s);
 int convt_wgrad(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const bf16* dy, int dy_ctotal, int dy_coff, float* dw,
                 float* scratch, size_t scratch_bytes, cudaStream_t s);
 // conv1 (7x7/2, 3->64) on the space-to-depth staging buffer (elementwise.h: image_to_s2d); wp: pack mode 4
-int conv1_fprop(int n, int h, int w, const bf16* s2d, const bf16* wp, bf16* y, cudaStream_t s);
+int conv1_fprop(int n, int h, int w, const bf16* s2d, const bf16* wp, bf16* y, cudaStream_t s, const ConvStats* st = nullptr);
 // dw_s2d: [64][64][4] fp32 scratch, unpacked by conv1_wgrad_unpack
 int conv1_wgrad(int n, int h, int w, const bf16* s2d, const bf16* dy, float* dw_s2d, float* scratch, size_t scratch_bytes, cudaStream_t s);
 

@@ -12,6 +12,7 @@
 // warps 2..5 = epilogue (one TMEM lane quadrant each).  smem ring of STAGES {A,B} tiles with full/empty mbarriers.
 #include "common.cuh"
 #include "conv.h"
+#include "bn_fin.cuh"
 #include "tcgen05.cuh"
 #include <mutex>
 #include <stdlib.h>
@@ -151,12 +152,218 @@ igemm_kernel(const __grid_constant__ IgemmPlan p) {
 
 
 // ---------------------------------------------------------------------------------------------
+// Fused BatchNorm statistics (epilogue side).  s_stat = [2][ncols] floats in shared memory, zeroed before the first tile.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+
+// o0/o1 = the 16 bf16 outputs this lane stores for its row (zeros when the row is outside the tensor).  w_sum / w_sq point at
+// this WARP's private 16-float slices (no atomics: the lane pair that ends up owning a column adds to it).
+__device__ __forceinline__ void stat_accumulate16(const uint4& o0, const uint4& o1, bool ok, int lane, float* w_sum, float* w_sq) {
+  float x[16], q[16];
+  x[0] = bf16lo(o0.x); x[1] = bf16hi(o0.x); x[2] = bf16lo(o0.y); x[3] = bf16hi(o0.y);
+  x[4] = bf16lo(o0.z); x[5] = bf16hi(o0.z); x[6] = bf16lo(o0.w); x[7] = bf16hi(o0.w);
+  x[8] = bf16lo(o1.x); x[9] = bf16hi(o1.x); x[10] = bf16lo(o1.y); x[11] = bf16hi(o1.y);
+  x[12] = bf16lo(o1.z); x[13] = bf16hi(o1.z); x[14] = bf16lo(o1.w); x[15] = bf16hi(o1.w);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { x[j] = ok ? x[j] : 0.f; q[j] = x[j] * x[j]; }
+  const float ts = column_total16(x, lane), tq = column_total16(q, lane);
+  // even lanes own the sum, odd lanes the sum of squares of column (lane >> 1) & 15
+  float* dst = ((lane & 1) ? w_sq : w_sum) + column_of_lane16(lane);
+  *dst += (lane & 1) ? tq : ts;
+}
+
+// After the CTA's last tile: shared partials -> global fp64 accumulators; the last CTA finalizes.  Called by the 128
+// epilogue threads (e = 0..127).  s_stat = [4 warps][2][ncols]; column j of this CTA is channel
+// out_coff + (cls_cols ? col % cls_cols : col) of y.
+__device__ __forceinline__ void stat_flush(const ConvStats& st, const float* s_stat, int ncols, int col0, int cout, int cls_cols,
+                                           int out_coff, int out_c, int e, uint32_t* s_flag) {
+  epi_bar_sync();
+  for (int j = e; j < ncols; j += 128) {
+    const int col = col0 + j;
+    if (col >= cout) break;
+    const int ch = out_coff + (cls_cols > 0 ? col % cls_cols : col);
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) { a += s_stat[w * 2 * ncols + j]; b += s_stat[w * 2 * ncols + ncols + j]; }
+    atomicAdd(&st.gacc[ch], (double)a);
+    atomicAdd(&st.gacc[out_c + ch], (double)b);
+  }
+  __threadfence();
+  epi_bar_sync();
+  if (e == 0) *s_flag = (atomicAdd(st.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  epi_bar_sync();
+  if (*s_flag) {
+    __threadfence();
+    bn_finalize_channels(st.fin, out_c, st.count, st.gacc, e, 128);
+    if (e == 0) *st.counter = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent implicit GEMM: one CTA per SM slot walks m-tiles (fixed n-block per CTA), the TMEM accumulator is double
+// buffered so the epilogue of tile j (tcgen05.ld, bias, bf16 store, BatchNorm statistics) overlaps the MMAs of tile j+1,
+// and the TMA ring keeps streaming across tile boundaries.
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N, int STAGES>
+struct IgemmPSmem {
+  static constexpr int B_TILE_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;                 // full[S], empty[S], t_full[2], t_empty[2], slot, flag
+  static constexpr int STAT_OFF = BAR_OFF + 256;
+  static constexpr int TOTAL = STAT_OFF + 4 * 2 * BLOCK_N * 4 + 1024;     // + [4 warps][2][BLOCK_N] statistics
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(IG_THREADS)
+igemm_persist_kernel(const __grid_constant__ IgemmPlan p) {
+  using SM = IgemmPSmem<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* t_full = empty_bar + STAGES;     // [2]
+  uint64_t* t_empty = t_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint32_t* s_flag = tmem_slot + 1;
+  float* s_stat = reinterpret_cast<float*>(smem + SM::STAT_OFF);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_blocks = (p.cout + BLOCK_N - 1) / BLOCK_N;
+  const int nblk = blockIdx.x % n_blocks;
+  const int mt0 = blockIdx.x / n_blocks, mt_step = gridDim.x / n_blocks;       // gridDim.x is a multiple of n_blocks
+  const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
+  const int cin_chunks = p.cin >> 6;
+  const int kiters = p.ntaps * cin_chunks;
+  const uint32_t a_bytes = (uint32_t)(p.bn * p.bh * p.bw) * 128u;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmap_x);
+    prefetch_tmap(&p.tmap_w);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 4); }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 8 * BLOCK_N; i += IG_THREADS) s_stat[i] = 0.f;
+  if (warp == 1) tmem_alloc<2 * BLOCK_N>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t g = 0;                       // ring position, runs on across tiles
+      for (int mt = mt0; mt < m_tiles; mt += mt_step) {
+        int t = mt;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h; const int tn = t / p.tiles_h;
+        const int n0 = tn * p.bn, h0 = th * p.bh, w0 = tw * p.bw;
+        for (int it = 0; it < kiters; ++it, ++g) {
+          const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          const int tap = it / cin_chunks, cc = it - tap * cin_chunks;
+          uint8_t* sa = smem + s * SM::STAGE_BYTES;
+          uint8_t* sb = sa + A_TILE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], a_bytes + (uint32_t)SM::B_TILE_BYTES);
+          tma_load_4d(sa, &p.tmap_x, &full_bar[s], cc * 64, w0 * p.in_sw + p.dw[tap], h0 * p.in_sh + p.dh[tap], n0);
+          tma_load_2d(sb, &p.tmap_w, &full_bar[s], (int)p.wtap[tap] * p.cin + cc * 64, nblk * BLOCK_N);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+      uint32_t g = 0, j = 0;
+      for (int mt = mt0; mt < m_tiles; mt += mt_step, ++j) {
+        const uint32_t buf = j & 1u;
+        mbar_wait(&t_empty[buf], ((j >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t dcol = tmem_d + buf * (uint32_t)BLOCK_N;
+        for (int it = 0; it < kiters; ++it, ++g) {
+          const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
+          const uint64_t da = make_desc_sw128(sa, 16, 1024);
+          const uint64_t db = make_desc_sw128(sa + A_TILE_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_bf16_ss(dcol, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
+          mma_commit(&empty_bar[s]);
+        }
+        mma_commit(&t_full[buf]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int dw_ = r % p.bw, dh_ = (r / p.bw) % p.bh, dn_ = r / (p.bw * p.bh);
+    const bool do_stats = p.st.enabled != 0;
+    uint32_t j = 0;
+    for (int mt = mt0; mt < m_tiles; mt += mt_step, ++j) {
+      const uint32_t buf = j & 1u;
+      int t = mt;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; const int tn = t / p.tiles_h;
+      const int n = tn * p.bn + dn_, h = th * p.bh + dh_, w = tw * p.bw + dw_;
+      const bool row_ok = (dn_ < p.bn) && n < p.mn && h < p.mh && w < p.mw;
+      mbar_wait(&t_full[buf], (j >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(taddr + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (c + 16 == BLOCK_N) {           // accumulator drained: the MMA warp may start tile j+2 in this buffer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[buf]);
+        }
+        const int col0 = nblk * BLOCK_N + c;
+        if (col0 >= p.cout) continue;      // warp-uniform
+        int ch0 = col0, oh = p.out_oh, ow = p.out_ow;
+        if (p.cls_cols > 0) { const int cls = col0 / p.cls_cols; ch0 = col0 - cls * p.cls_cols; oh = cls >> 1; ow = cls & 1; }
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] += __ldg(p.bias + ch0 + i);
+        }
+        uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
+        if (row_ok) {
+          const int64_t opix = ((int64_t)n * p.out_h + (h * p.out_sh + oh)) * p.out_w + (w * p.out_sw + ow);
+          uint4* dst = reinterpret_cast<uint4*>(p.y + opix * p.out_c + p.out_coff + ch0);
+          if (p.accumulate) {
+            const uint4 e0 = dst[0], e1 = dst[1];
+            f[0] += bf16lo(e0.x); f[1] += bf16hi(e0.x); f[2] += bf16lo(e0.y); f[3] += bf16hi(e0.y);
+            f[4] += bf16lo(e0.z); f[5] += bf16hi(e0.z); f[6] += bf16lo(e0.w); f[7] += bf16hi(e0.w);
+            f[8] += bf16lo(e1.x); f[9] += bf16hi(e1.x); f[10] += bf16lo(e1.y); f[11] += bf16hi(e1.y);
+            f[12] += bf16lo(e1.z); f[13] += bf16hi(e1.z); f[14] += bf16lo(e1.w); f[15] += bf16hi(e1.w);
+          }
+          o0.x = pack_bf16(f[0], f[1]);   o0.y = pack_bf16(f[2], f[3]);   o0.z = pack_bf16(f[4], f[5]);   o0.w = pack_bf16(f[6], f[7]);
+          o1.x = pack_bf16(f[8], f[9]);   o1.y = pack_bf16(f[10], f[11]); o1.z = pack_bf16(f[12], f[13]); o1.w = pack_bf16(f[14], f[15]);
+          dst[0] = o0; dst[1] = o1;
+        }
+        if (do_stats) stat_accumulate16(o0, o1, row_ok, lane, s_stat + q * 2 * BLOCK_N + c, s_stat + q * 2 * BLOCK_N + BLOCK_N + c);
+      }
+    }
+    if (do_stats) stat_flush(p.st, s_stat, BLOCK_N, nblk * BLOCK_N, p.cout, p.cls_cols, p.out_coff, p.out_c, r, s_flag);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<2 * BLOCK_N>(tmem_d);
+}
+
+
+// ---------------------------------------------------------------------------------------------
 // halo64: 3x3 stride-1 64->64 convolution (fprop and dgrad), persistent + weights-stationary + shifted windows
 // ---------------------------------------------------------------------------------------------
 constexpr int HALO_B_BYTES = 9 * 64 * 128;      // nine 64x64 bf16 weight tiles
 constexpr int HALO_A_STAGE = 224 * 128;         // up to 224 pixel rows of 128 B
 constexpr int HALO_STAGES = 3;
-constexpr int HALO_SMEM = HALO_B_BYTES + HALO_STAGES * HALO_A_STAGE + 256 + 1024;
+constexpr int HALO_SMEM = HALO_B_BYTES + HALO_STAGES * HALO_A_STAGE + 256 + 4 * 2 * 64 * 4 + 1024;
 
 // Shifted-window operands start at 128 B granularity, not on the 1024 B swizzle repeat.  Measured on B200: tcgen05 applies the
 // 128 B swizzle to the ABSOLUTE shared-memory address bits (the same function TMA used when writing the tile), so the
@@ -179,9 +386,12 @@ halo64_kernel(const __grid_constant__ HaloPlan p) {
   uint64_t* t_full = b_full + 1;       // [2]
   uint64_t* t_empty = t_full + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint32_t* s_flag = tmem_slot + 1;
+  float* s_stat = reinterpret_cast<float*>(sA + HALO_STAGES * HALO_A_STAGE + 256);   // [4 warps][2][64]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_bytes = (uint32_t)((p.R + 2) * p.pitch) * 128u;
+  for (int i = threadIdx.x; i < 512; i += IG_THREADS) s_stat[i] = 0.f;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmap_x);
@@ -260,10 +470,11 @@ halo64_kernel(const __grid_constant__ HaloPlan p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[buf]);       // accumulator drained: the MMA warp may reuse this buffer
-      if (ok) {
-        bf16* yrow = p.y + (((int64_t)n * p.h + hh) * p.w + ww) * p.out_c + p.out_coff;
+      bf16* yrow = p.y + (((int64_t)n * p.h + hh) * p.w + ww) * p.out_c + p.out_coff;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 4; ++c) {
+        uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
+        if (ok) {
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[c][j]);
@@ -279,13 +490,14 @@ halo64_kernel(const __grid_constant__ HaloPlan p) {
             f[8] += bf16lo(e1.x); f[9] += bf16hi(e1.x); f[10] += bf16lo(e1.y); f[11] += bf16hi(e1.y);
             f[12] += bf16lo(e1.z); f[13] += bf16hi(e1.z); f[14] += bf16lo(e1.w); f[15] += bf16hi(e1.w);
           }
-          uint4 o0, o1;
           o0.x = pack_bf16(f[0], f[1]);   o0.y = pack_bf16(f[2], f[3]);   o0.z = pack_bf16(f[4], f[5]);   o0.w = pack_bf16(f[6], f[7]);
           o1.x = pack_bf16(f[8], f[9]);   o1.y = pack_bf16(f[10], f[11]); o1.z = pack_bf16(f[12], f[13]); o1.w = pack_bf16(f[14], f[15]);
           dst[0] = o0; dst[1] = o1;
         }
+        if (p.st.enabled) stat_accumulate16(o0, o1, ok, lane, s_stat + q * 128 + c * 16, s_stat + q * 128 + 64 + c * 16);
       }
     }
+    if (p.st.enabled) stat_flush(p.st, s_stat, 64, 0, 64, 0, p.out_coff, p.out_c, r, s_flag);
   }
   tc_fence_before();
   __syncthreads();
@@ -805,14 +1017,56 @@ static int igemm_launch_t(const IgemmPlan& p, cudaStream_t s) {
   return DBB_OK;
 }
 
+template <int BLOCK_N, int STAGES>
+static int igemm_launch_p(const IgemmPlan& p, cudaStream_t s) {
+  using SM = IgemmPSmem<BLOCK_N, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DBB_CUDA(cudaFuncSetAttribute(igemm_persist_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    attr_done = true;
+  }
+  const int n_blocks = (p.cout + BLOCK_N - 1) / BLOCK_N;
+  const int64_t total = (int64_t)p.tiles_n * p.tiles_h * p.tiles_w * n_blocks;
+  if (total <= 0 || total > 0x7fffffff) return set_error(DBB_EINVAL, "igemm: bad grid");
+  // resident CTAs per SM: shared memory (227 KB, 1 KB reserved per CTA) and TMEM (512 columns, 2*BLOCK_N per CTA)
+  int occ = (227 * 1024) / (SM::TOTAL + 1024);
+  if (occ > 512 / (2 * BLOCK_N)) occ = 512 / (2 * BLOCK_N);
+  if (occ < 1) occ = 1;
+  int64_t grid = (int64_t)DBB_NUM_SMS * occ;
+  grid -= grid % n_blocks;
+  if (grid > total) grid = total;             // total is a multiple of n_blocks
+  const char* label = "igemm";
+  if (prof_enabled()) {
+    char tmp[96];
+    snprintf(tmp, sizeof(tmp), "igemm_bn%d_m%lld_n%d_k%d%s", BLOCK_N, (long long)p.mn * p.mh * p.mw, p.cout, p.ntaps * p.cin, p.st.enabled ? "_st" : "");
+    label = prof_label(tmp);
+  }
+  DBB_LAUNCH(label, s, igemm_persist_kernel<BLOCK_N, STAGES><<<(unsigned)grid, IG_THREADS, SM::TOTAL, s>>>(p));
+  return DBB_OK;
+}
+
 int igemm_launch(const IgemmPlan& p, cudaStream_t s) {
   if (p.cin % 64 != 0 || p.ntaps < 1 || p.ntaps > IGEMM_MAX_TAPS) return set_error(DBB_EUNSUPPORTED, "igemm: cin must be a multiple of 64, taps <= 16");
-  // The k-loop of a tile has ntaps*cin/64 iterations.  Short loops (1x1 convolutions, ConvTranspose, conv1) cannot use a
-  // deep ring anyway; giving them 1-2 stages shrinks shared memory so that more CTAs are resident per SM and their
-  // load / MMA / epilogue phases overlap across CTAs (TMEM allows 512 / BLOCK_N of them).
+  // The k-loop of a tile has ntaps*cin/64 iterations; short loops (1x1 convolutions, ConvTranspose, conv1) get a
+  // shallow ring so that more CTAs (= more epilogue warps) are resident per SM.
   const int kiters = p.ntaps * (p.cin >> 6);
-  static const bool deep_only = getenv("DBB_DEEP_RING") != nullptr;      // A/B switch
+  static const bool deep_only = getenv("DBB_DEEP_RING") != nullptr;      // A/B switches
+  static const bool no_persist = getenv("DBB_NO_PERSIST") != nullptr;
   const int depth = deep_only ? 4 : (kiters <= 1 ? 1 : (kiters <= 4 ? 2 : 4));
+  if (!no_persist || p.st.enabled) {
+    switch (p.block_n) {
+      case 64:
+        if (depth <= 2) return igemm_launch_p<64, 2>(p, s);     // 48 KB -> 4 CTAs/SM
+        return igemm_launch_p<64, 4>(p, s);                     // 96 KB -> 2 CTAs/SM
+      case 128:
+        if (depth <= 2) return igemm_launch_p<128, 2>(p, s);    // 64 KB -> 2 CTAs/SM (TMEM)
+        return igemm_launch_p<128, 3>(p, s);                    // 96 KB -> 2 CTAs/SM
+      case 256:
+        if (depth <= 2) return igemm_launch_p<256, 2>(p, s);    // 96 KB -> 1 CTA/SM (TMEM)
+        return igemm_launch_p<256, 4>(p, s);                    // 192 KB -> 1 CTA/SM
+      default: return set_error(DBB_EUNSUPPORTED, "igemm: block_n must be 64, 128 or 256");
+    }
+  }
   switch (p.block_n) {
     case 64:
       if (depth == 1) return igemm_launch_t<64, 1>(p, s);     // 24 KB -> 8 CTAs/SM
@@ -870,7 +1124,13 @@ static int wgrad_launch_t(const WgradPlan& p, cudaStream_t s) {
   const int64_t total = (int64_t)p.ntaps * p.m_total * p.n_total;
   int rgrid = (int)((total + 255) / 256);
   if (rgrid > DBB_NUM_SMS * 8) rgrid = DBB_NUM_SMS * 8;
-  DBB_LAUNCH("wgrad_reduce", s, wgrad_reduce_kernel<<<rgrid, 256, 0, s>>>(p.ws, p.split_k, p.ntaps, p.m_pad, p.n_pad, p.m_total, p.n_total, p.tap_stride, p.dw));
+  const char* rlabel = "wgrad_reduce";
+  if (prof_enabled()) {
+    char tmp[96];
+    snprintf(tmp, sizeof(tmp), "wgrad_reduce_s%d_t%d_m%d_n%d", p.split_k, p.ntaps, p.m_total, p.n_total);
+    rlabel = prof_label(tmp);
+  }
+  DBB_LAUNCH(rlabel, s, wgrad_reduce_kernel<<<rgrid, 256, 0, s>>>(p.ws, p.split_k, p.ntaps, p.m_pad, p.n_pad, p.m_total, p.n_total, p.tap_stride, p.dw));
   return DBB_OK;
 }
 

@@ -502,9 +502,44 @@ __global__ void __launch_bounds__(256) step_bwd_kernel(const float* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// per-step pixel metric (SURVEY f-3): 2x2 confusion matrix of (P*mask > thresh) vs int(gt*mask)
+// replaces src/text_metrics.py:63-82 (cal_text_score) + RunningScore._fast_hist (:14-23), which copy the full P map to
+// the host every training step (src/train.py:176-181).  12 B/px read, 4 integers out.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LOSS_THREADS)
+text_score_hist_kernel(const float* __restrict__ p, int64_t p_img_stride, const float* __restrict__ gt, const float* __restrict__ mask,
+                       int64_t n_img, int64_t hw, float thresh, unsigned long long* __restrict__ hist4) {
+  unsigned c[4] = {0u, 0u, 0u, 0u};
+  const int64_t total = n_img * hw;
+  for (int64_t i = (int64_t)blockIdx.x * LOSS_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * LOSS_THREADS) {
+    const unsigned n32 = (unsigned)i / (unsigned)hw;
+    const int64_t r = (int64_t)((unsigned)i - n32 * (unsigned)hw);
+    const float m = mask[i];
+    const float pv = p[(int64_t)n32 * p_img_stride + r] * m;
+    const int g = (int)(gt[i] * m);                 // .astype(np.int32): truncation
+    if (g >= 0 && g < 2) c[g * 2 + (pv > thresh ? 1 : 0)] += 1u;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int s = warp_sum((int)c[k]);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(&hist4[k], (unsigned long long)s);
+  }
+}
+
 }  // namespace dbb
 
 using namespace dbb;
+
+// hist4 (device, 4 x uint64, row-major [gt][pred]) is ACCUMULATED into (zero it to start a new RunningScore)
+extern "C" int dbb_text_score_hist(const float* p, int64_t p_img_stride, const float* gt, const float* mask, int64_t n, int64_t h,
+                                   int64_t w, float thresh, unsigned long long* hist4, void* stream) {
+  if (!p || !gt || !mask || !hist4 || n <= 0 || h <= 0 || w <= 0) return set_error(DBB_EINVAL, "text_score_hist: bad argument");
+  if (n * h * w >= ((int64_t)1 << 32)) return set_error(DBB_EUNSUPPORTED, "text_score_hist: more than 2^32 pixels");
+  const int grid = loss_grid(n * h * w);
+  DBB_LAUNCH("text_score_hist", (cudaStream_t)stream, text_score_hist_kernel<<<grid, LOSS_THREADS, 0, (cudaStream_t)stream>>>(p, p_img_stride, gt, mask, n, h * w, thresh, hist4));
+  return DBB_OK;
+}
 
 extern "C" size_t dbb_dbloss_workspace(int64_t n, int c, int64_t h, int64_t w, int reduction) {
   (void)c;

@@ -3,6 +3,8 @@
 // count a multiple of 8, so every thread moves 16-byte vectors (8 channels) and a warp covers contiguous memory.
 #include "common.cuh"
 #include "elementwise.h"
+#include "bn_fin.cuh"
+#include <stdio.h>
 
 namespace dbb {
 
@@ -189,23 +191,39 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const bf16* __rest
   const int groups = c / 8;
   const int lg = 31 - __clz(groups);            // groups is a power of two (check_c): shifts instead of 64-bit divides
   const int64_t total = P * groups;
-  for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
-    const int64_t p = i >> lg; const int g = (int)(i & (groups - 1));
-    const F8 x = ld8s(z + p * c + g * 8);
-    const F8 sc = ldf8(stats4 + g * 8), sh = ldf8(stats4 + c + g * 8);
+  const int g = threadIdx.x & (groups - 1);     // the grid stride is a multiple of groups: one channel group per thread
+  const F8 sc = ldf8(stats4 + g * 8), sh = ldf8(stats4 + c + g * 8);
+  const int64_t step = (int64_t)gridDim.x * EW_THREADS;
+  auto one = [&](const F8& x, const F8* r, int64_t p) {
     F8 y;
 #pragma unroll
     for (int j = 0; j < 8; ++j) y.v[j] = fmaf(x.v[j], sc.v[j], sh.v[j]);
-    if (res) {
-      const F8 r = ld8s(res + p * c + g * 8);
+    if (r) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) y.v[j] += r.v[j];
+      for (int j = 0; j < 8; ++j) y.v[j] += r->v[j];
     }
     if (relu) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) y.v[j] = fmaxf(y.v[j], 0.f);
     }
     st8(out + p * out_ctotal + out_coff + g * 8, y);
+  };
+  int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x;
+  for (; i + step < total; i += 2 * step) {      // two items in flight per thread
+    const int64_t p0 = i >> lg, p1 = (i + step) >> lg;
+    const F8 x0 = ld8s(z + p0 * c + g * 8), x1 = ld8s(z + p1 * c + g * 8);
+    if (res) {
+      const F8 r0 = ld8s(res + p0 * c + g * 8), r1 = ld8s(res + p1 * c + g * 8);
+      one(x0, &r0, p0); one(x1, &r1, p1);
+    } else {
+      one(x0, nullptr, p0); one(x1, nullptr, p1);
+    }
+  }
+  if (i < total) {
+    const int64_t p0 = i >> lg;
+    const F8 x0 = ld8s(z + p0 * c + g * 8);
+    if (res) { const F8 r0 = ld8s(res + p0 * c + g * 8); one(x0, &r0, p0); }
+    else one(x0, nullptr, p0);
   }
 }
 
@@ -249,6 +267,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n
   coef3[2 * c + ch] = (float)(q / count);
 }
 
+template <int MASK>
 __global__ void __launch_bounds__(EW_THREADS)
 bn_bwd_apply_kernel(const bf16* __restrict__ dout, int dout_ctotal, int dout_coff, const bf16* __restrict__ mask_src,
                     int mask_ctotal, int mask_coff, const bf16* __restrict__ z, int64_t P, int c,
@@ -257,20 +276,25 @@ bn_bwd_apply_kernel(const bf16* __restrict__ dout, int dout_ctotal, int dout_cof
   const int groups = c / 8;
   const int lg = 31 - __clz(groups);
   const int64_t total = P * groups;
+  // groups is a power of two dividing the grid stride: a thread stays on one channel group -> per-channel constants hoisted
+  const int g = threadIdx.x & (groups - 1);
+  const F8 mean = ldf8(stats4 + 2 * c + g * 8), inv = ldf8(stats4 + 3 * c + g * 8);
+  const F8 a = ldf8(coef3 + g * 8), c1 = ldf8(coef3 + c + g * 8), c2 = ldf8(coef3 + 2 * c + g * 8);
+  F8 sc, sh;
+  if (MASK == 2) { sc = ldf8(stats4 + g * 8); sh = ldf8(stats4 + c + g * 8); }
   for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
-    const int64_t p = i >> lg; const int g = (int)(i & (groups - 1));
+    const int64_t p = i >> lg;
     F8 dy = ld8s(dout + p * dout_ctotal + dout_coff + g * 8);
-    if (mask_src) {
-      const F8 m = ld8s(mask_src + p * mask_ctotal + mask_coff + g * 8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dy.v[j] = m.v[j] > 0.f ? dy.v[j] : 0.f;
-    }
+    F8 m;
+    if (MASK == 1) m = ld8s(mask_src + p * mask_ctotal + mask_coff + g * 8);
     const F8 x = ld8s(z + p * c + g * 8);
-    const F8 mean = ldf8(stats4 + 2 * c + g * 8), inv = ldf8(stats4 + 3 * c + g * 8);
-    const F8 a = ldf8(coef3 + g * 8), c1 = ldf8(coef3 + c + g * 8), c2 = ldf8(coef3 + 2 * c + g * 8);
     F8 o;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o.v[j] = a.v[j] * (dy.v[j] - c1.v[j] - (x.v[j] - mean.v[j]) * inv.v[j] * c2.v[j]);
+    for (int j = 0; j < 8; ++j) {
+      if (MASK == 1) dy.v[j] = m.v[j] > 0.f ? dy.v[j] : 0.f;
+      if (MASK == 2) dy.v[j] = fmaf(x.v[j], sc.v[j], sh.v[j]) > 0.f ? dy.v[j] : 0.f;
+      o.v[j] = a.v[j] * (dy.v[j] - c1.v[j] - (x.v[j] - mean.v[j]) * inv.v[j] * c2.v[j]);
+    }
     st8(dz + p * c + g * 8, o);
     if (dsum) st8(dsum + p * c + g * 8, dy);
   }
@@ -298,6 +322,13 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ partials, int n
   if ((threadIdx.x & 31) == 0) out[ch] = (float)s;
 }
 
+static const char* shaped(const char* base, int64_t P, int c, int extra = -1) {
+  if (!prof_enabled()) return base;
+  char tmp[96];
+  if (extra >= 0) snprintf(tmp, sizeof(tmp), "%s_p%lld_c%d_m%d", base, (long long)P, c, extra);
+  else snprintf(tmp, sizeof(tmp), "%s_p%lld_c%d", base, (long long)P, c);
+  return prof_label(tmp);
+}
 static int check_c(int c) { return (c % 8 == 0 && c >= 8 && c <= 2048 && EW_THREADS % (c / 8) == 0 && ((c / 8) & (c / 8 - 1)) == 0) ? 0 : 1; }
 
 
@@ -350,31 +381,13 @@ bn_stats_fin_kernel(const bf16* __restrict__ z, int64_t P, int c, double* __rest
   }
   reduce_groups_atomic<2>(acc, c, gacc);
   if (!last_block_arrives(counter)) return;
-  const double count = (double)P;
-  for (int sg = 0; sg < fin.nseg; ++sg) {
-    const BnFinSeg& S = fin.seg[sg];
-    for (int i = threadIdx.x; i < S.cn; i += EW_THREADS) {
-      const int ch = S.coff + i;
-      const double s = __ldcg(&gacc[ch]), q = __ldcg(&gacc[c + ch]);
-      gacc[ch] = 0.0; gacc[c + ch] = 0.0;
-      const double mean = s / count;
-      double var = q / count - mean * mean;
-      if (var < 0.0) var = 0.0;
-      const double invstd = 1.0 / sqrt(var + (double)fin.eps);
-      fin.stats4[ch] = (float)((double)S.gamma[i] * invstd);
-      fin.stats4[c + ch] = (float)((double)S.beta[i] - mean * (double)S.gamma[i] * invstd);
-      fin.stats4[2 * c + ch] = (float)mean;
-      fin.stats4[3 * c + ch] = (float)invstd;
-      if (S.rmean) {   // running stats: unbiased variance, momentum 0.1 (torch.nn.BatchNorm2d)
-        const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
-        S.rmean[i] = (float)((1.0 - fin.momentum) * (double)S.rmean[i] + fin.momentum * mean);
-        S.rvar[i] = (float)((1.0 - fin.momentum) * (double)S.rvar[i] + fin.momentum * unb);
-      }
-    }
-  }
+  bn_finalize_channels(fin, c, (double)P, gacc, threadIdx.x, EW_THREADS);
   if (threadIdx.x == 0) *counter = 0u;
 }
 
+// MASK: 0 = dy = dout, 1 = dy = dout * (mask_src > 0), 2 = dy = dout * (z*scale + shift > 0)  (the layer's own ReLU output
+// re-derived from z: saves reading the activation tensor)
+template <int MASK>
 __global__ void __launch_bounds__(EW_THREADS)
 bn_bwd_reduce_fin_kernel(const bf16* __restrict__ dout, int dout_ctotal, int dout_coff, const bf16* __restrict__ mask_src,
                          int mask_ctotal, int mask_coff, const bf16* __restrict__ z, int64_t P, int c,
@@ -382,19 +395,35 @@ bn_bwd_reduce_fin_kernel(const bf16* __restrict__ dout, int dout_ctotal, int dou
   const int groups = c / 8;
   const int g = threadIdx.x % groups, pl = threadIdx.x / groups, lanes = EW_THREADS / groups;
   const F8 mean = ldf8(stats4 + 2 * c + g * 8), inv = ldf8(stats4 + 3 * c + g * 8);
+  F8 sc, sh;
+  if (MASK == 2) { sc = ldf8(stats4 + g * 8); sh = ldf8(stats4 + c + g * 8); }
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
-  for (int64_t p = (int64_t)blockIdx.x * lanes + pl; p < P; p += (int64_t)gridDim.x * lanes) {
-    F8 dy = ld8(dout + p * dout_ctotal + dout_coff + g * 8);
-    if (mask_src) {
-      const F8 m = ld8(mask_src + p * mask_ctotal + mask_coff + g * 8);
+  const int64_t step = (int64_t)gridDim.x * lanes;
+  auto body = [&](F8 dy, const F8& m, const F8& x) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dy.v[j] = m.v[j] > 0.f ? dy.v[j] : 0.f;
+    for (int j = 0; j < 8; ++j) {
+      if (MASK == 1) dy.v[j] = m.v[j] > 0.f ? dy.v[j] : 0.f;
+      if (MASK == 2) dy.v[j] = fmaf(x.v[j], sc.v[j], sh.v[j]) > 0.f ? dy.v[j] : 0.f;
+      acc[0][j] += dy.v[j]; acc[1][j] += dy.v[j] * (x.v[j] - mean.v[j]) * inv.v[j];
     }
-    const F8 x = ld8(z + p * c + g * 8);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { acc[0][j] += dy.v[j]; acc[1][j] += dy.v[j] * (x.v[j] - mean.v[j]) * inv.v[j]; }
+  };
+  int64_t p = (int64_t)blockIdx.x * lanes + pl;
+  for (; p + step < P; p += 2 * step) {      // two pixels in flight per thread
+    const int64_t p2 = p + step;
+    const F8 dy0 = ld8(dout + p * dout_ctotal + dout_coff + g * 8), dy1 = ld8(dout + p2 * dout_ctotal + dout_coff + g * 8);
+    F8 m0, m1;
+    if (MASK == 1) { m0 = ld8(mask_src + p * mask_ctotal + mask_coff + g * 8); m1 = ld8(mask_src + p2 * mask_ctotal + mask_coff + g * 8); }
+    const F8 x0 = ld8(z + p * c + g * 8), x1 = ld8(z + p2 * c + g * 8);
+    body(dy0, m0, x0); body(dy1, m1, x1);
+  }
+  if (p < P) {
+    const F8 dy0 = ld8(dout + p * dout_ctotal + dout_coff + g * 8);
+    F8 m0;
+    if (MASK == 1) m0 = ld8(mask_src + p * mask_ctotal + mask_coff + g * 8);
+    const F8 x0 = ld8(z + p * c + g * 8);
+    body(dy0, m0, x0);
   }
   reduce_groups_atomic<2>(acc, c, gacc);
   if (!last_block_arrives(counter)) return;
@@ -417,14 +446,17 @@ bn_bwd_reduce_fin_kernel(const bf16* __restrict__ dout, int dout_ctotal, int dou
 
 int bn_stats_finalize(const bf16* z, int64_t P, int c, const BnFin& fin, double* gacc, unsigned* counter, cudaStream_t s) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_stats: channel count");
-  DBB_LAUNCH("bn_stats_fin", s, bn_stats_fin_kernel<<<ew_blocks(P, c), EW_THREADS, 0, s>>>(z, P, c, gacc, counter, fin));
+  DBB_LAUNCH(shaped("bn_stats_fin", P, c), s, bn_stats_fin_kernel<<<ew_blocks(P, c), EW_THREADS, 0, s>>>(z, P, c, gacc, counter, fin));
   return DBB_OK;
 }
 int bn_bwd_reduce_finalize(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
                            const bf16* z, int64_t P, int c, const float* stats4, const BnBwdFin& fin, double* gacc,
-                           unsigned* counter, cudaStream_t s) {
+                           unsigned* counter, cudaStream_t s, int mask_self) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_bwd_reduce: channel count");
-  DBB_LAUNCH("bn_bwd_reduce_fin", s, bn_bwd_reduce_fin_kernel<<<ew_blocks(P, c), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, gacc, counter, fin));
+  const int grid = ew_blocks(P, c);
+  if (mask_self) DBB_LAUNCH(shaped("bn_bwd_reduce_fin", P, c, 2), s, bn_bwd_reduce_fin_kernel<2><<<grid, EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, gacc, counter, fin));
+  else if (mask_src) DBB_LAUNCH(shaped("bn_bwd_reduce_fin", P, c, 1), s, bn_bwd_reduce_fin_kernel<1><<<grid, EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, gacc, counter, fin));
+  else DBB_LAUNCH(shaped("bn_bwd_reduce_fin", P, c, 0), s, bn_bwd_reduce_fin_kernel<0><<<grid, EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, gacc, counter, fin));
   return DBB_OK;
 }
 
@@ -452,7 +484,7 @@ static int stream_grid(int64_t total) {
 int bn_apply(const bf16* z, int64_t P, int c, const float* stats4, const bf16* res, int relu, bf16* out, int out_ctotal,
              int out_coff, cudaStream_t s) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_apply: channel count");
-  DBB_LAUNCH("bn_apply", s, bn_apply_kernel<<<stream_grid(P * (c / 8)), EW_THREADS, 0, s>>>(z, P, c, stats4, res, relu, out, out_ctotal, out_coff));
+  DBB_LAUNCH(shaped("bn_apply", P, c, res ? 1 : 0), s, bn_apply_kernel<<<stream_grid(P * (c / 8)), EW_THREADS, 0, s>>>(z, P, c, stats4, res, relu, out, out_ctotal, out_coff));
   return DBB_OK;
 }
 int bn_bwd_reduce(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
@@ -469,9 +501,12 @@ int bn_bwd_finalize(const float* partials, int nblk, int c, int coff, int cn, in
 }
 int bn_bwd_apply(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
                  const bf16* z, int64_t P, int c, const float* stats4, const float* coef3, bf16* dz, bf16* dsum,
-                 cudaStream_t s) {
+                 cudaStream_t s, int mask_self) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_bwd_apply: channel count");
-  DBB_LAUNCH("bn_bwd_apply", s, bn_bwd_apply_kernel<<<stream_grid(P * (c / 8)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, coef3, dz, dsum));
+  const int grid = stream_grid(P * (c / 8));
+  if (mask_self) DBB_LAUNCH(shaped("bn_bwd_apply", P, c, 2), s, bn_bwd_apply_kernel<2><<<grid, EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, coef3, dz, dsum));
+  else if (mask_src) DBB_LAUNCH(shaped("bn_bwd_apply", P, c, dsum ? 11 : 1), s, bn_bwd_apply_kernel<1><<<grid, EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, coef3, dz, dsum));
+  else DBB_LAUNCH(shaped("bn_bwd_apply", P, c, 0), s, bn_bwd_apply_kernel<0><<<grid, EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, coef3, dz, dsum));
   return DBB_OK;
 }
 int bias_grad(const bf16* dz, int64_t P, int c, float* partials, float* dbias, cudaStream_t s) {

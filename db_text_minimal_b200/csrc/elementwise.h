@@ -22,19 +22,19 @@ int bn_finalize_eval(int c, int coff, int cn, const float* gamma, const float* b
                      float eps, float* stats4, cudaStream_t s);
 // fused statistics + finalize (one launch): fp64 atomics into `gacc` ([2][c] doubles, zero on entry, left zero) and a
 // last-block-done ticket in `counter` (zero on entry, left zero).  Up to two parameter segments (the two head branches).
-struct BnFinSeg { const float* gamma; const float* beta; float* rmean; float* rvar; int coff, cn; };
-struct BnFin { BnFinSeg seg[2]; int nseg; float momentum, eps; float* stats4; };
+// (BnFinSeg / BnFin live in conv.h: the convolution epilogues fuse the same statistics + finalize step)
 struct BnBwdFinSeg { const float* gamma; float* dgamma; float* dbeta; int coff, cn; };
 struct BnBwdFin { BnBwdFinSeg seg[2]; int nseg; float* coef3; };
 constexpr size_t BN_ACC_BYTES = 2 * 2048 * sizeof(double) + 256;
 int bn_stats_finalize(const bf16* z, int64_t P, int c, const BnFin& fin, double* gacc, unsigned* counter, cudaStream_t s);
 int bn_bwd_reduce_finalize(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
                            const bf16* z, int64_t P, int c, const float* stats4, const BnBwdFin& fin, double* gacc,
-                           unsigned* counter, cudaStream_t s);
+                           unsigned* counter, cudaStream_t s, int mask_self = 0);
 // out = [relu](z*scale + shift [+ res])
 int bn_apply(const bf16* z, int64_t P, int c, const float* stats4, const bf16* res, int relu, bf16* out, int out_ctotal,
              int out_coff, cudaStream_t s);
-// backward.  dy = dout * (mask_src > 0) if mask_src else dout.
+// backward.  dy = dout * (mask_src > 0) if mask_src else dout;  mask_self = 1: dy = dout * (z*scale + shift > 0), i.e. the
+// layer's own ReLU output re-derived from z (mask_src ignored; one tensor read less).
 int bn_bwd_reduce(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
                   const bf16* z, int64_t P, int c, const float* stats4, float* partials, int* nblk, cudaStream_t s);
 // dgamma, dbeta: fp32 parameter gradients (overwritten); coef3: [a = gamma*invstd | c1 = dbeta/M | c2 = dgamma/M]
@@ -43,7 +43,7 @@ int bn_bwd_finalize(const float* partials, int nblk, int c, int coff, int cn, in
 // dz = a*(dy - c1 - xhat*c2);  dsum (optional) receives dy (the ReLU-masked gradient, for the residual path)
 int bn_bwd_apply(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
                  const bf16* z, int64_t P, int c, const float* stats4, const float* coef3, bf16* dz, bf16* dsum,
-                 cudaStream_t s);
+                 cudaStream_t s, int mask_self = 0);
 // conv bias gradient: dbias[c] = sum_px dz[px, c]  (re-uses the bn partial buffers)
 int bias_grad(const bf16* dz, int64_t P, int c, float* partials, float* dbias, cudaStream_t s);
 

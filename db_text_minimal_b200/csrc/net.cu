@@ -329,6 +329,19 @@ int bn_prepare(const Ctx& c, const bf16* z, int64_t Pn, int ch, int nseg, const 
   }
   return 0;
 }
+// Training mode: the statistics ride in the producing convolution's epilogue (ConvStats) and no separate pass is
+// launched.  Returns the descriptor to hand to conv_fprop, or nullptr (eval mode / DBB_NO_FUSED_STATS) in which case
+// the caller runs bn_prepare after the convolution.  Segment i covers channels [coff0 + i*cn, +cn) of the y tensor.
+const ConvStats* bn_fused(const Ctx& c, ConvStats& st, int cn, int nseg, const BnIdx* ix, float* stats4, int coff0 = 0) {
+  static const bool off = getenv("DBB_NO_FUSED_STATS") != nullptr;     // A/B switch
+  if (!c.net->training || off) return nullptr;
+  memset(&st, 0, sizeof(st));
+  st.enabled = 1; st.gacc = c.acc(); st.counter = c.ticket();
+  st.fin.nseg = nseg; st.fin.momentum = BN_MOM; st.fin.eps = BN_EPS; st.fin.stats4 = stats4;
+  for (int i = 0; i < nseg; ++i)
+    st.fin.seg[i] = BnFinSeg{c.par(ix[i].gamma), c.par(ix[i].beta), c.buf(ix[i].rm), c.buf(ix[i].rv), coff0 + i * cn, cn};
+  return &st;
+}
 int bn_prepare(const Ctx& c, const bf16* z, int64_t Pn, int ch, int gamma, int beta, int rm, int rv, float* stats4) {
   const BnIdx ix{gamma, beta, rm, rv};
   return bn_prepare(c, z, Pn, ch, 1, &ix, stats4);
@@ -372,21 +385,28 @@ int pack_all(const Ctx& c) {
 }
 
 int convbn_fwd(const Ctx& c, ConvBN& L, const bf16* x, int x_ctotal, int x_coff) {
-  RC(conv_fprop(L.g, x, x_ctotal, x_coff, c.p(L.wp), c.par(L.b), c.p(L.z), L.g.cout, 0, c.s));
-  RC(bn_prepare(c, c.p(L.z), L.P(), L.g.cout, L.gamma, L.beta, L.rm, L.rv, c.p<float>(L.stats)));
+  const BnIdx ix{L.gamma, L.beta, L.rm, L.rv};
+  ConvStats st;
+  const ConvStats* fused = bn_fused(c, st, L.g.cout, 1, &ix, c.p<float>(L.stats));
+  RC(conv_fprop(L.g, x, x_ctotal, x_coff, c.p(L.wp), c.par(L.b), c.p(L.z), L.g.cout, 0, c.s, fused));
+  if (!fused) RC(bn_prepare(c, c.p(L.z), L.P(), L.g.cout, 1, &ix, c.p<float>(L.stats)));
   return 0;
 }
 
 // backward through BN (+ReLU mask) and the conv: dout -> dz -> (dW, dbias, dx)
+static int self_mask() { static const int v = getenv("DBB_NO_SELF_MASK") ? 0 : 1; return v; }    // A/B switch
+
+// mask_self: the ReLU mask is this layer's own output (no residual in between) -> re-derived from z instead of read
 int convbn_bwd(const Ctx& c, ConvBN& L, const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask, int mask_ctotal,
-               int mask_coff, const bf16* x, int x_ctotal, int x_coff, bf16* dx, int dx_accumulate, bf16* dsum) {
+               int mask_coff, const bf16* x, int x_ctotal, int x_coff, bf16* dx, int dx_accumulate, bf16* dsum, int mask_self = 0) {
+  mask_self = mask_self && self_mask();
   const int64_t Pn = L.P();
   const int ch = L.g.cout;
   BnBwdFin fin;
   fin.nseg = 1; fin.coef3 = c.p<float>(L.coef);
   fin.seg[0] = BnBwdFinSeg{c.par(L.gamma), c.grad(L.gamma), c.grad(L.beta), 0, ch};
-  RC(bn_bwd_reduce_finalize(dout, dout_ctotal, dout_coff, mask, mask_ctotal, mask_coff, c.p(L.z), Pn, ch, c.p<float>(L.stats), fin, c.acc(), c.ticket(), c.s));
-  RC(bn_bwd_apply(dout, dout_ctotal, dout_coff, mask, mask_ctotal, mask_coff, c.p(L.z), Pn, ch, c.p<float>(L.stats), c.p<float>(L.coef), c.p(L.dz), dsum, c.s));
+  RC(bn_bwd_reduce_finalize(dout, dout_ctotal, dout_coff, mask, mask_ctotal, mask_coff, c.p(L.z), Pn, ch, c.p<float>(L.stats), fin, c.acc(), c.ticket(), c.s, mask_self));
+  RC(bn_bwd_apply(dout, dout_ctotal, dout_coff, mask, mask_ctotal, mask_coff, c.p(L.z), Pn, ch, c.p<float>(L.stats), c.p<float>(L.coef), c.p(L.dz), dsum, c.s, mask_self));
   RC(conv_wgrad(L.g, x, x_ctotal, x_coff, c.p(L.dz), ch, 0, c.grad(L.w), c.wgs(), WGRAD_SCRATCH_BYTES, c.s));
   // the bias of a convolution that feeds a training-mode BatchNorm has an identically zero gradient
   // (sum_px dz = 0); the reference's value is float rounding noise.  Written as exact zeros.
@@ -428,7 +448,7 @@ int block_bwd(const Ctx& c, Block& bk, const bf16* x, bf16* dx, int dx_has_conte
     RC(convbn_bwd(c, bk.ds, dout, pl, 0, out, pl, 0, x, bk.c_in, 0, dx, acc, nullptr));
     acc = 1;
   }
-  RC(convbn_bwd(c, bk.c1, c.p(bk.d_a1), pl, 0, c.p(bk.a1), pl, 0, x, bk.c_in, 0, dx, acc, nullptr));
+  RC(convbn_bwd(c, bk.c1, c.p(bk.d_a1), pl, 0, c.p(bk.a1), pl, 0, x, bk.c_in, 0, dx, acc, nullptr, 1));
   return 0;
 }
 
@@ -445,10 +465,14 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
   // ---- stem: conv 7x7/2 (space-to-depth form) -> BN -> ReLU -> maxpool
   RC(image_to_s2d(x, N, net->h, net->w, c.p(net->s2d), c.s));
   RC(pack_all(c));
-  RC(conv1_fprop(N, net->h, net->w, c.p(net->s2d), c.p(net->wp_conv1), c.p(net->z0), c.s));
   const int64_t P0 = (int64_t)N * net->h1 * net->w1;
-  RC(bn_prepare(c, c.p(net->z0), P0, 64, P("backbone.bn1.weight"), P("backbone.bn1.bias"), B("backbone.bn1.running_mean"),
-                B("backbone.bn1.running_var"), c.p<float>(net->stats0)));
+  {
+    const BnIdx ix{P("backbone.bn1.weight"), P("backbone.bn1.bias"), B("backbone.bn1.running_mean"), B("backbone.bn1.running_var")};
+    ConvStats st;
+    const ConvStats* fused = bn_fused(c, st, 64, 1, &ix, c.p<float>(net->stats0));
+    RC(conv1_fprop(N, net->h, net->w, c.p(net->s2d), c.p(net->wp_conv1), c.p(net->z0), c.s, fused));
+    if (!fused) RC(bn_prepare(c, c.p(net->z0), P0, 64, 1, &ix, c.p<float>(net->stats0)));
+  }
   RC(bn_apply(c.p(net->z0), P0, 64, c.p<float>(net->stats0), nullptr, 1, c.p(net->a0), 64, 0, c.s));
   RC(maxpool_fwd(c.p(net->a0), N, net->h1, net->w1, 64, c.p(net->x1), net->training ? c.p<uint8_t>(net->argmax) : nullptr, c.s));
   // ---- residual stages
@@ -483,7 +507,6 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
   // ---- head (segmentation_head.py:35-45)
   DBB_CUDA(cudaMemsetAsync(c.p<float>(net->bias_h), 0, 128 * sizeof(float), c.s));
   DBB_CUDA(cudaMemcpyAsync(c.p<float>(net->bias_h), c.par(P("segmentation_head.binarize.0.bias")), 64 * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
-  RC(conv_fprop(net->hconv_g, c.p(net->af), 256, 0, c.p(net->wp_h), c.p<float>(net->bias_h), c.p(net->zh), 128, 0, c.s));
   const int64_t Ph = (int64_t)N * hf * wf;
   auto head_bn = [&](const char* idx) {
     std::vector<BnIdx> v;
@@ -495,17 +518,24 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
   };
   {
     const std::vector<BnIdx> ix = head_bn("1");
-    RC(bn_prepare(c, c.p(net->zh), Ph, 128, 2, ix.data(), c.p<float>(net->stats_h)));
+    ConvStats st;
+    const ConvStats* fused = bn_fused(c, st, 64, 2, ix.data(), c.p<float>(net->stats_h));
+    RC(conv_fprop(net->hconv_g, c.p(net->af), 256, 0, c.p(net->wp_h), c.p<float>(net->bias_h), c.p(net->zh), 128, 0, c.s, fused));
+    if (!fused) RC(bn_prepare(c, c.p(net->zh), Ph, 128, 2, ix.data(), c.p<float>(net->stats_h)));
   }
   RC(bn_apply(c.p(net->zh), Ph, 128, c.p<float>(net->stats_h), nullptr, 1, c.p(net->ah), 128, 0, c.s));
-  for (int br = 0; br < 2; ++br) {
-    const std::string pre = std::string("segmentation_head.") + (br ? "thresh" : "binarize");
-    RC(convt_fprop(net->tconv_g, c.p(net->ah), 128, br * 64, c.p(net->wp_t[br]), c.par(P(pre + ".3.bias")), c.p(net->zt), 128, br * 64, c.s));
-  }
   const int64_t Pt = Ph * 4;
   {
     const std::vector<BnIdx> ix = head_bn("4");
-    RC(bn_prepare(c, c.p(net->zt), Pt, 128, 2, ix.data(), c.p<float>(net->stats_t)));
+    bool all_fused = true;
+    for (int br = 0; br < 2; ++br) {       // each branch launch finalizes its own 64-channel half of the 128-wide tensor
+      const std::string pre = std::string("segmentation_head.") + (br ? "thresh" : "binarize");
+      ConvStats st;
+      const ConvStats* fused = bn_fused(c, st, 64, 1, &ix[br], c.p<float>(net->stats_t), br * 64);
+      all_fused = all_fused && fused;
+      RC(convt_fprop(net->tconv_g, c.p(net->ah), 128, br * 64, c.p(net->wp_t[br]), c.par(P(pre + ".3.bias")), c.p(net->zt), 128, br * 64, c.s, fused));
+    }
+    if (!all_fused) RC(bn_prepare(c, c.p(net->zt), Pt, 128, 2, ix.data(), c.p<float>(net->stats_t)));
   }
   float* hout = net->head_out.bytes ? c.p<float>(net->head_out) : out;
   RC(head_tail_fwd(c.p(net->zt), N, 2 * hf, 2 * wf, c.p<float>(net->stats_t), c.par(P("segmentation_head.binarize.6.weight")),
@@ -564,10 +594,10 @@ extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout
         const std::string pre = br ? ht : hb;
         fin.seg[br] = BnBwdFinSeg{c.par(P(pre + ".1.weight")), c.grad(P(pre + ".1.weight")), c.grad(P(pre + ".1.bias")), br * 64, 64};
       }
-      RC(bn_bwd_reduce_finalize(c.p(net->d_ah), 128, 0, c.p(net->ah), 128, 0, c.p(net->zh), Ph, 128, c.p<float>(net->stats_h), fin, c.acc(), c.ticket(), c.s));
+      RC(bn_bwd_reduce_finalize(c.p(net->d_ah), 128, 0, c.p(net->ah), 128, 0, c.p(net->zh), Ph, 128, c.p<float>(net->stats_h), fin, c.acc(), c.ticket(), c.s, self_mask()));
     }
     RC(bn_bwd_apply(c.p(net->d_ah), 128, 0, c.p(net->ah), 128, 0, c.p(net->zh), Ph, 128, c.p<float>(net->stats_h), c.p<float>(net->coef_h),
-                    c.p(net->d_zh), nullptr, c.s));
+                    c.p(net->d_zh), nullptr, c.s, self_mask()));
     RC(conv_wgrad(net->hconv_g, c.p(net->af), 256, 0, c.p(net->d_zh), 128, 0, c.p<float>(net->dw_h), c.wgs(), WGRAD_SCRATCH_BYTES, c.s));
     const size_t half = (size_t)64 * 256 * 9;
     DBB_CUDA(cudaMemcpyAsync(c.grad(P(hb + ".0.weight")), c.p<float>(net->dw_h), half * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
@@ -575,7 +605,7 @@ extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout
     DBB_CUDA(cudaMemsetAsync(c.grad(P(hb + ".0.bias")), 0, 64 * sizeof(float), c.s));
     RC(conv_dgrad(net->hconv_g, c.p(net->d_zh), c.p(net->wpt_h), c.p(net->d_af), c.s, 0));
     // ---- FPN output conv
-    RC(convbn_bwd(c, net->fconv, c.p(net->d_af), 256, 0, c.p(net->af), 256, 0, c.p(net->cat), 256, 0, c.p(net->d_cat), 0, nullptr));
+    RC(convbn_bwd(c, net->fconv, c.p(net->d_af), 256, 0, c.p(net->af), 256, 0, c.p(net->cat), 256, 0, c.p(net->d_cat), 0, nullptr, 1));
     // ---- top-down path, bottom level first: smooth_p2, p3, p4 then the c5 lateral
     //      d_p[k]: gradient of p5 (k=0), p4 (1), p3 (2); d_s[i]: gradient of the sum feeding smooth[i]
     const bf16* dlevel = c.p(net->d_cat);   // gradient w.r.t. p2 = channels 0..63 of d_cat
@@ -585,18 +615,18 @@ extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout
     for (int i = 2; i >= 0; --i) {
       const int lvl = 2 - i;               // smooth[2] -> level 0 (c2 resolution)
       const int up = lvl + 1;              // the level that was upsampled into this one
-      RC(convbn_bwd(c, net->smooth[i], dlevel, dl_ct, 0, mlevel, ml_ct, 0, c.p(net->s_sum[i]), 64, 0, c.p(net->d_s[i]), 0, nullptr));
+      RC(convbn_bwd(c, net->smooth[i], dlevel, dl_ct, 0, mlevel, ml_ct, 0, c.p(net->s_sum[i]), 64, 0, c.p(net->d_s[i]), 0, nullptr, 1));
       // gradient of the upsampled operand: concat slice (channels 64*up ..) + the upsample-add path
       bf16* dpu = c.p(net->d_p[3 - up]);   // up=1 -> d_p[2] (p3), up=2 -> d_p[1] (p4), up=3 -> d_p[0] (p5)
       RC(upsample_bwd(c.p(net->d_cat), 256, 64 * up, N, hf, wf, 64, dpu, net->hh[up], net->ww[up], 0, c.s));
       RC(upsample_bwd(c.p(net->d_s[i]), 64, 0, N, net->hh[lvl], net->ww[lvl], 64, dpu, net->hh[up], net->ww[up], 1, c.s));
       // lateral conv of this level: its output was the other operand of the sum
-      RC(convbn_bwd(c, net->lat[lvl], c.p(net->d_s[i]), 64, 0, c.p(net->l_act[lvl]), 64, 0, feat[lvl], planes[lvl], 0, c.p(net->d_c[lvl]), 0, nullptr));
+      RC(convbn_bwd(c, net->lat[lvl], c.p(net->d_s[i]), 64, 0, c.p(net->l_act[lvl]), 64, 0, feat[lvl], planes[lvl], 0, c.p(net->d_c[lvl]), 0, nullptr, 1));
       dlevel = dpu; dl_ct = 64;
       mlevel = (up < 3) ? c.p(net->p_act[2 - up]) : c.p(net->l_act[3]);   // p3 = p_act[1], p4 = p_act[0], p5 = l_act[3]
       ml_ct = 64;
     }
-    RC(convbn_bwd(c, net->lat[3], dlevel, 64, 0, mlevel, 64, 0, feat[3], 512, 0, c.p(net->d_c[3]), 0, nullptr));
+    RC(convbn_bwd(c, net->lat[3], dlevel, 64, 0, mlevel, 64, 0, feat[3], 512, 0, c.p(net->d_c[3]), 0, nullptr, 1));
   }
   auto run_block = [&](int i) -> int {
     const bf16* x = (i == 0) ? c.p(net->x1) : c.p(net->blocks[i - 1].out);
@@ -615,10 +645,10 @@ extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout
       BnBwdFin fin;
       fin.nseg = 1; fin.coef3 = c.p<float>(net->coef0);
       fin.seg[0] = BnBwdFinSeg{c.par(g1), c.grad(g1), c.grad(b1), 0, 64};
-      RC(bn_bwd_reduce_finalize(c.p(net->d_a0), 64, 0, c.p(net->a0), 64, 0, c.p(net->z0), P0, 64, c.p<float>(net->stats0), fin, c.acc(), c.ticket(), c.s));
+      RC(bn_bwd_reduce_finalize(c.p(net->d_a0), 64, 0, c.p(net->a0), 64, 0, c.p(net->z0), P0, 64, c.p<float>(net->stats0), fin, c.acc(), c.ticket(), c.s, self_mask()));
     }
     RC(bn_bwd_apply(c.p(net->d_a0), 64, 0, c.p(net->a0), 64, 0, c.p(net->z0), P0, 64, c.p<float>(net->stats0), c.p<float>(net->coef0),
-                    c.p(net->d_z0), nullptr, c.s));
+                    c.p(net->d_z0), nullptr, c.s, self_mask()));
     RC(conv1_wgrad(N, net->h, net->w, c.p(net->s2d), c.p(net->d_z0), c.p<float>(net->dw_s2d), c.wgs(), WGRAD_SCRATCH_BYTES, c.s));
     RC(conv1_wgrad_unpack(c.p<float>(net->dw_s2d), c.grad(P("backbone.conv1.weight")), c.s));
   }

@@ -78,6 +78,12 @@ int dbb_dbloss_bwd(const float* preds, const float* gts, int64_t n, int c, int64
                    float alpha, float beta, int reduction, float eps, const float* grad_out5,
                    DbbLossState* state, float* dpreds, void* stream);
 
+/* Per-step pixel metric (replaces src/text_metrics.py:63-82 cal_text_score + :14-23 _fast_hist): accumulates the 2x2
+ * confusion matrix hist4[gt*2 + pred] of pred = (P*mask > thresh) vs gt = int(gt*mask) into a device uint64[4].
+ * p may be a channel view of the (N,C,H,W) prediction: p_img_stride = C*H*W. */
+int dbb_text_score_hist(const float* p, int64_t p_img_stride, const float* gt, const float* mask, int64_t n, int64_t h,
+                        int64_t w, float thresh, unsigned long long* hist4, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Step function  B = 1/(1+exp(-k(P-T)))   (replaces src/modules/segmentation_head.py:106-108)
  * ------------------------------------------------------------------------------------------ */
