@@ -65,7 +65,9 @@ struct IgemmPlan {
 int pack_weights(int mode, const float* w, bf16* out, int co_n, int ci_n, int kh, int kw, cudaStream_t s, int co_total = 0, int co_off = 0);
 
 // batched packing: all weight tensors of the network in one or two launches
-struct PackJob { const float* w; bf16* out; int mode, co_n, ci_n, kh, kw, co_total, co_off; };
+//   mode 5 (batch only): Conv2d OIHW -> out in the mode 0 layout AND (if out2) out2 in the mode 1 layout, tiled through
+//           shared memory so that both the read and the two writes are coalesced (co_total / co_off apply to out2)
+struct PackJob { const float* w; bf16* out; int mode, co_n, ci_n, kh, kw, co_total, co_off; bf16* out2; };
 constexpr int PACK_BATCH = 48;
 struct PackBatch { int njobs; PackJob jobs[PACK_BATCH]; };
 int pack_weights_batch(const PackBatch& b, cudaStream_t s);

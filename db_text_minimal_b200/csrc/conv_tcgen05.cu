@@ -152,33 +152,58 @@ igemm_kernel(const __grid_constant__ IgemmPlan p) {
 
 
 // ---------------------------------------------------------------------------------------------
-// Fused BatchNorm statistics (epilogue side).  s_stat = [2][ncols] floats in shared memory, zeroed before the first tile.
+// Fused BatchNorm statistics (epilogue side).
+//   * register path (<= 64 columns per epilogue warp): every thread keeps sum / sum-of-squares of ITS row for each of its
+//     columns across all tiles of the CTA (2 FP ops per value per tile) and the warp-level column reduction
+//     (column_total16: 16 shuffles per 16 columns) runs ONCE per CTA;
+//   * butterfly path (BLOCK_N = 256): column reduction per chunk, added into warp-private shared-memory slices.
+// Either way the warp leaves its column totals in s_stat[quadrant][2][ncols]; stat_flush adds the four quadrants into the
+// global fp64 accumulators and the last CTA finalizes.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+template <int NTHREADS>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" :: "n"(NTHREADS) : "memory"); }   // epilogue warps only
 
-// o0/o1 = the 16 bf16 outputs this lane stores for its row (zeros when the row is outside the tensor).  w_sum / w_sq point at
-// this WARP's private 16-float slices (no atomics: the lane pair that ends up owning a column adds to it).
-__device__ __forceinline__ void stat_accumulate16(const uint4& o0, const uint4& o1, bool ok, int lane, float* w_sum, float* w_sq) {
-  float x[16], q[16];
+__device__ __forceinline__ void unpack16(const uint4& o0, const uint4& o1, float (&x)[16]) {
   x[0] = bf16lo(o0.x); x[1] = bf16hi(o0.x); x[2] = bf16lo(o0.y); x[3] = bf16hi(o0.y);
   x[4] = bf16lo(o0.z); x[5] = bf16hi(o0.z); x[6] = bf16lo(o0.w); x[7] = bf16hi(o0.w);
   x[8] = bf16lo(o1.x); x[9] = bf16hi(o1.x); x[10] = bf16lo(o1.y); x[11] = bf16hi(o1.y);
   x[12] = bf16lo(o1.z); x[13] = bf16hi(o1.z); x[14] = bf16lo(o1.w); x[15] = bf16hi(o1.w);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) { x[j] = ok ? x[j] : 0.f; q[j] = x[j] * x[j]; }
-  const float ts = column_total16(x, lane), tq = column_total16(q, lane);
-  // even lanes own the sum, odd lanes the sum of squares of column (lane >> 1) & 15
-  float* dst = ((lane & 1) ? w_sq : w_sum) + column_of_lane16(lane);
-  *dst += (lane & 1) ? tq : ts;
 }
 
-// After the CTA's last tile: shared partials -> global fp64 accumulators; the last CTA finalizes.  Called by the 128
-// epilogue threads (e = 0..127).  s_stat = [4 warps][2][ncols]; column j of this CTA is channel
+// o0/o1 = the 16 bf16 outputs this lane stored for its row (all-zero when the row is outside the tensor)
+__device__ __forceinline__ void stat_accumulate_regs(const uint4& o0, const uint4& o1, float (&acc_s)[16], float (&acc_q)[16]) {
+  float x[16];
+  unpack16(o0, o1, x);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { acc_s[j] += x[j]; acc_q[j] = fmaf(x[j], x[j], acc_q[j]); }
+}
+
+// warp-level column totals of 16 columns -> the warp's shared slices (ADD = accumulate across tiles, else overwrite)
+template <bool ADD>
+__device__ __forceinline__ void stat_reduce_store16(const float (&xs)[16], const float (&xq)[16], int lane, float* w_sum, float* w_sq) {
+  const float ts = column_total16(xs, lane), tq = column_total16(xq, lane);
+  // even lanes own the sum, odd lanes the sum of squares of column (lane >> 1) & 15
+  float* dst = ((lane & 1) ? w_sq : w_sum) + column_of_lane16(lane);
+  const float v = (lane & 1) ? tq : ts;
+  if (ADD) *dst += v; else *dst = v;
+}
+
+__device__ __forceinline__ void stat_accumulate_smem(const uint4& o0, const uint4& o1, int lane, float* w_sum, float* w_sq) {
+  float x[16], q[16];
+  unpack16(o0, o1, x);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) q[j] = x[j] * x[j];
+  stat_reduce_store16<true>(x, q, lane, w_sum, w_sq);
+}
+
+// After the CTA's last tile: shared partials -> global fp64 accumulators; the last CTA finalizes.  Called by all NTHREADS
+// epilogue threads (e = 0..NTHREADS-1).  s_stat = [4 quadrants][2][ncols]; column j of this CTA is channel
 // out_coff + (cls_cols ? col % cls_cols : col) of y.
+template <int NTHREADS>
 __device__ __forceinline__ void stat_flush(const ConvStats& st, const float* s_stat, int ncols, int col0, int cout, int cls_cols,
                                            int out_coff, int out_c, int e, uint32_t* s_flag) {
-  epi_bar_sync();
-  for (int j = e; j < ncols; j += 128) {
+  epi_bar_sync<NTHREADS>();
+  for (int j = e; j < ncols; j += NTHREADS) {
     const int col = col0 + j;
     if (col >= cout) break;
     const int ch = out_coff + (cls_cols > 0 ? col % cls_cols : col);
@@ -189,12 +214,12 @@ __device__ __forceinline__ void stat_flush(const ConvStats& st, const float* s_s
     atomicAdd(&st.gacc[out_c + ch], (double)b);
   }
   __threadfence();
-  epi_bar_sync();
+  epi_bar_sync<NTHREADS>();
   if (e == 0) *s_flag = (atomicAdd(st.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
-  epi_bar_sync();
+  epi_bar_sync<NTHREADS>();
   if (*s_flag) {
     __threadfence();
-    bn_finalize_channels(st.fin, out_c, st.count, st.gacc, e, 128);
+    bn_finalize_channels(st.fin, out_c, st.count, st.gacc, e, NTHREADS);
     if (e == 0) *st.counter = 0u;
   }
 }
@@ -202,21 +227,28 @@ __device__ __forceinline__ void stat_flush(const ConvStats& st, const float* s_s
 // ---------------------------------------------------------------------------------------------
 // Persistent implicit GEMM: one CTA per SM slot walks m-tiles (fixed n-block per CTA), the TMEM accumulator is double
 // buffered so the epilogue of tile j (tcgen05.ld, bias, bf16 store, BatchNorm statistics) overlaps the MMAs of tile j+1,
-// and the TMA ring keeps streaming across tile boundaries.
+// and the TMA ring keeps streaming across tile boundaries.  320 threads: warp 0 = TMA producer, warp 1 = MMA issuer,
+// warps 2..9 = epilogue; warp w drains TMEM lane quadrant w % 4 and column half (w - 2) / 4 of the tile.
 // ---------------------------------------------------------------------------------------------
+constexpr int IGP_THREADS = 320;
+constexpr int IGP_EPI_THREADS = 256;
+
 template <int BLOCK_N, int STAGES>
 struct IgemmPSmem {
   static constexpr int B_TILE_BYTES = BLOCK_N * 128;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;                 // full[S], empty[S], t_full[2], t_empty[2], slot, flag
   static constexpr int STAT_OFF = BAR_OFF + 256;
-  static constexpr int TOTAL = STAT_OFF + 4 * 2 * BLOCK_N * 4 + 1024;     // + [4 warps][2][BLOCK_N] statistics
+  static constexpr int TOTAL = STAT_OFF + 4 * 2 * BLOCK_N * 4 + 1024;     // + [4 quadrants][2][BLOCK_N] statistics
 };
 
-template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(IG_THREADS)
+template <int BLOCK_N, int STAGES, bool STATS>
+__global__ void __launch_bounds__(IGP_THREADS)
 igemm_persist_kernel(const __grid_constant__ IgemmPlan p) {
   using SM = IgemmPSmem<BLOCK_N, STAGES>;
+  constexpr int CW = BLOCK_N / 2;                  // columns per epilogue warp
+  constexpr int NCH = CW / 16;                     // 16-column chunks per epilogue warp
+  constexpr bool REG_STATS = STATS && CW <= 32;     // 64 accumulator registers; wider tiles would drop to 1 CTA/SM
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
@@ -240,10 +272,10 @@ igemm_persist_kernel(const __grid_constant__ IgemmPlan p) {
     prefetch_tmap(&p.tmap_x);
     prefetch_tmap(&p.tmap_w);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 8); }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < 8 * BLOCK_N; i += IG_THREADS) s_stat[i] = 0.f;
+  if (STATS) { for (int i = threadIdx.x; i < 8 * BLOCK_N; i += IGP_THREADS) s_stat[i] = 0.f; }
   if (warp == 1) tmem_alloc<2 * BLOCK_N>(tmem_slot);
   tc_fence_before();
   __syncthreads();
@@ -295,10 +327,19 @@ igemm_persist_kernel(const __grid_constant__ IgemmPlan p) {
       }
     }
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
+    const int cbase = half * CW;                    // first column (inside the BLOCK_N tile) of this warp
     const int dw_ = r % p.bw, dh_ = (r / p.bw) % p.bh, dn_ = r / (p.bw * p.bh);
-    const bool do_stats = p.st.enabled != 0;
+    float acc_s[REG_STATS ? NCH : 1][16], acc_q[REG_STATS ? NCH : 1][16];
+    if (REG_STATS) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { acc_s[c][i] = 0.f; acc_q[c][i] = 0.f; }
+    }
+    float* w_sum = s_stat + q * 2 * BLOCK_N + cbase;
+    float* w_sq = w_sum + BLOCK_N;
     uint32_t j = 0;
     for (int mt = mt0; mt < m_tiles; mt += mt_step, ++j) {
       const uint32_t buf = j & 1u;
@@ -307,20 +348,21 @@ igemm_persist_kernel(const __grid_constant__ IgemmPlan p) {
       const int th = t % p.tiles_h; const int tn = t / p.tiles_h;
       const int n = tn * p.bn + dn_, h = th * p.bh + dh_, w = tw * p.bw + dw_;
       const bool row_ok = (dn_ < p.bn) && n < p.mn && h < p.mh && w < p.mw;
-      mbar_wait(&t_full[buf], (j >> 1) & 1u);
+      mbar_wait_sleep(&t_full[buf], (j >> 1) & 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)BLOCK_N;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 16) {
+      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)BLOCK_N + (uint32_t)cbase;
+#pragma unroll
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int c = ci * 16;
         uint32_t v[16];
         tmem_ld_x16(taddr + (uint32_t)c, v);
         tmem_ld_wait();
-        if (c + 16 == BLOCK_N) {           // accumulator drained: the MMA warp may start tile j+2 in this buffer
+        if (ci == NCH - 1) {               // this warp's part of the accumulator is drained
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&t_empty[buf]);
         }
-        const int col0 = nblk * BLOCK_N + c;
+        const int col0 = nblk * BLOCK_N + cbase + c;
         if (col0 >= p.cout) continue;      // warp-uniform
         int ch0 = col0, oh = p.out_oh, ow = p.out_ow;
         if (p.cls_cols > 0) { const int cls = col0 / p.cls_cols; ch0 = col0 - cls * p.cls_cols; oh = cls >> 1; ow = cls & 1; }
@@ -346,10 +388,19 @@ igemm_persist_kernel(const __grid_constant__ IgemmPlan p) {
           o1.x = pack_bf16(f[8], f[9]);   o1.y = pack_bf16(f[10], f[11]); o1.z = pack_bf16(f[12], f[13]); o1.w = pack_bf16(f[14], f[15]);
           dst[0] = o0; dst[1] = o1;
         }
-        if (do_stats) stat_accumulate16(o0, o1, row_ok, lane, s_stat + q * 2 * BLOCK_N + c, s_stat + q * 2 * BLOCK_N + BLOCK_N + c);
+        if (REG_STATS) stat_accumulate_regs(o0, o1, acc_s[REG_STATS ? ci : 0], acc_q[REG_STATS ? ci : 0]);
+        else if (STATS) stat_accumulate_smem(o0, o1, lane, w_sum + c, w_sq + c);
       }
     }
-    if (do_stats) stat_flush(p.st, s_stat, BLOCK_N, nblk * BLOCK_N, p.cout, p.cls_cols, p.out_coff, p.out_c, r, s_flag);
+    if (STATS) {
+      if (REG_STATS) {
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci)
+          stat_reduce_store16<false>(acc_s[REG_STATS ? ci : 0], acc_q[REG_STATS ? ci : 0], lane, w_sum + ci * 16, w_sq + ci * 16);
+      }
+      stat_flush<IGP_EPI_THREADS>(p.st, s_stat, BLOCK_N, nblk * BLOCK_N, p.cout, p.cls_cols, p.out_coff, p.out_c,
+                                  (int)threadIdx.x - 64, s_flag);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -452,6 +503,11 @@ halo64_kernel(const __grid_constant__ HaloPlan p) {
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const int dr = r / p.pitch, dc = r - dr * p.pitch;
+    float acc_s[4][16], acc_q[4][16];      // fused BatchNorm statistics: this row's running sums for the 64 channels
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { acc_s[c][i] = 0.f; acc_q[c][i] = 0.f; }
     int k = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++k) {
       const int buf = k & 1;
@@ -460,7 +516,7 @@ halo64_kernel(const __grid_constant__ HaloPlan p) {
       const int th = t % p.tiles_h; const int n = t / p.tiles_h;
       const int hh = th * p.R + dr, ww = tw * p.bw + dc;
       const bool ok = dr < p.R && dc < p.bw && hh < p.h && ww < p.w;
-      mbar_wait(&t_full[buf], (uint32_t)(k >> 1) & 1u);
+      mbar_wait_sleep(&t_full[buf], (uint32_t)(k >> 1) & 1u);
       tc_fence_after();
       uint32_t v[4][16];
       const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 64);
@@ -494,10 +550,14 @@ halo64_kernel(const __grid_constant__ HaloPlan p) {
           o1.x = pack_bf16(f[8], f[9]);   o1.y = pack_bf16(f[10], f[11]); o1.z = pack_bf16(f[12], f[13]); o1.w = pack_bf16(f[14], f[15]);
           dst[0] = o0; dst[1] = o1;
         }
-        if (p.st.enabled) stat_accumulate16(o0, o1, ok, lane, s_stat + q * 128 + c * 16, s_stat + q * 128 + 64 + c * 16);
+        if (p.st.enabled) stat_accumulate_regs(o0, o1, acc_s[c], acc_q[c]);
       }
     }
-    if (p.st.enabled) stat_flush(p.st, s_stat, 64, 0, 64, 0, p.out_coff, p.out_c, r, s_flag);
+    if (p.st.enabled) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) stat_reduce_store16<false>(acc_s[c], acc_q[c], lane, s_stat + q * 128 + c * 16, s_stat + q * 128 + 64 + c * 16);
+      stat_flush<128>(p.st, s_stat, 64, 0, 64, 0, p.out_coff, p.out_c, r, s_flag);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -873,11 +933,45 @@ __global__ void pack_weights_kernel(int mode, const float* __restrict__ w, bf16*
                                     int co_total, int co_off) {
   pack_one(mode, w, out, co_n, ci_n, kh, kw, co_total, co_off, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
 }
+// mode 5: Conv2d OIHW -> BOTH GEMM layouts from one coalesced read: a block stages a 32(co) x 32(ci) x taps tile in shared
+// memory, then writes out[co][tap][ci] (mode 0 layout) and, if out2, out2[ci][tap][co_off + co] (mode 1 layout) in 64-byte runs.
+constexpr int PACK_TILE_MAX_TAPS = 9;
+__device__ __forceinline__ void pack_tiled(const PackJob& j, float* tile /* [32][32*taps + 1] */) {
+  const int taps = j.kh * j.kw;
+  const int row = 32 * taps + 1;
+  const int tiles_ci = j.ci_n / 32, ntiles = (j.co_n / 32) * tiles_ci;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int co0 = (t / tiles_ci) * 32, ci0 = (t % tiles_ci) * 32;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 32 * 32 * taps; idx += 256) {
+      const int co = idx / (32 * taps), rem = idx - co * 32 * taps;       // rem = ci * taps + tap: contiguous in w
+      tile[co * row + rem] = j.w[((int64_t)(co0 + co) * j.ci_n + ci0) * taps + rem];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 32 * 32 * taps; idx += 256) {
+      const int ci = idx & 31, r = idx >> 5;
+      const int tap = r % taps, co = r / taps;
+      j.out[((int64_t)(co0 + co) * taps + tap) * j.ci_n + ci0 + ci] = __float2bfloat16_rn(tile[co * row + ci * taps + tap]);
+    }
+    if (j.out2) {
+      for (int idx = threadIdx.x; idx < 32 * 32 * taps; idx += 256) {
+        const int co = idx & 31, r = idx >> 5;
+        const int tap = r % taps, ci = r / taps;
+        j.out2[((int64_t)(ci0 + ci) * taps + tap) * j.co_total + j.co_off + co0 + co] = __float2bfloat16_rn(tile[co * row + ci * taps + tap]);
+      }
+    }
+  }
+}
 __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const __grid_constant__ PackBatch b) {
+  __shared__ float tile[32 * (32 * PACK_TILE_MAX_TAPS + 1)];
   const PackJob& j = b.jobs[blockIdx.y];
+  if (j.mode == 5) { pack_tiled(j, tile); return; }
   pack_one(j.mode, j.w, j.out, j.co_n, j.ci_n, j.kh, j.kw, j.co_total, j.co_off, (int64_t)blockIdx.x * 256 + threadIdx.x, (int64_t)gridDim.x * 256);
 }
 int pack_weights_batch(const PackBatch& b, cudaStream_t s) {
+  for (int i = 0; i < b.njobs; ++i)
+    if (b.jobs[i].mode == 5 && (b.jobs[i].co_n % 32 || b.jobs[i].ci_n % 32 || b.jobs[i].kh * b.jobs[i].kw > PACK_TILE_MAX_TAPS))
+      return set_error(DBB_EUNSUPPORTED, "pack_weights: tiled mode needs channels % 32 == 0 and <= 9 taps");
   if (b.njobs <= 0) return DBB_OK;
   DBB_LAUNCH("pack_weights_batch", s, pack_weights_batch_kernel<<<dim3(64, (unsigned)b.njobs), 256, 0, s>>>(b));
   return DBB_OK;
@@ -1017,34 +1111,40 @@ static int igemm_launch_t(const IgemmPlan& p, cudaStream_t s) {
   return DBB_OK;
 }
 
-template <int BLOCK_N, int STAGES>
-static int igemm_launch_p(const IgemmPlan& p, cudaStream_t s) {
+template <int BLOCK_N, int STAGES, bool STATS>
+static int igemm_launch_p2(const IgemmPlan& p, cudaStream_t s) {
   using SM = IgemmPSmem<BLOCK_N, STAGES>;
   static bool attr_done = false;
+  static int occ = 1;
   if (!attr_done) {
-    DBB_CUDA(cudaFuncSetAttribute(igemm_persist_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    DBB_CUDA(cudaFuncSetAttribute(igemm_persist_kernel<BLOCK_N, STAGES, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    // resident CTAs per SM: registers + shared memory (runtime query) and TMEM (512 columns, 2*BLOCK_N per CTA)
+    // (the occupancy API answers for the default shared-memory carve-out, i.e. 1; computed from the limits instead)
+    cudaFuncAttributes fa;
+    DBB_CUDA(cudaFuncGetAttributes(&fa, igemm_persist_kernel<BLOCK_N, STAGES, STATS>));
+    const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * IGP_THREADS;
+    occ = (227 * 1024) / (SM::TOTAL + 1024);
+    if (occ > 65536 / regs_per_cta) occ = 65536 / regs_per_cta;
+    if (occ > 2048 / IGP_THREADS) occ = 2048 / IGP_THREADS;
+    if (occ > 512 / (2 * BLOCK_N)) occ = 512 / (2 * BLOCK_N);
+    if (occ < 1) occ = 1;
     attr_done = true;
   }
   const int n_blocks = (p.cout + BLOCK_N - 1) / BLOCK_N;
   const int64_t total = (int64_t)p.tiles_n * p.tiles_h * p.tiles_w * n_blocks;
   if (total <= 0 || total > 0x7fffffff) return set_error(DBB_EINVAL, "igemm: bad grid");
-  // resident CTAs per SM: shared memory (227 KB, 1 KB reserved per CTA) and TMEM (512 columns, 2*BLOCK_N per CTA)
-  int occ = (227 * 1024) / (SM::TOTAL + 1024);
-  if (occ > 512 / (2 * BLOCK_N)) occ = 512 / (2 * BLOCK_N);
-  if (occ < 1) occ = 1;
   int64_t grid = (int64_t)DBB_NUM_SMS * occ;
   grid -= grid % n_blocks;
   if (grid > total) grid = total;             // total is a multiple of n_blocks
   const char* label = "igemm";
   if (prof_enabled()) {
     char tmp[96];
-    snprintf(tmp, sizeof(tmp), "igemm_bn%d_m%lld_n%d_k%d%s", BLOCK_N, (long long)p.mn * p.mh * p.mw, p.cout, p.ntaps * p.cin, p.st.enabled ? "_st" : "");
+    snprintf(tmp, sizeof(tmp), "igemm_bn%d_m%lld_n%d_k%d%s", BLOCK_N, (long long)p.mn * p.mh * p.mw, p.cout, p.ntaps * p.cin, STATS ? "_st" : "");
     label = prof_label(tmp);
   }
-  DBB_LAUNCH(label, s, igemm_persist_kernel<BLOCK_N, STAGES><<<(unsigned)grid, IG_THREADS, SM::TOTAL, s>>>(p));
+  DBB_LAUNCH(label, s, igemm_persist_kernel<BLOCK_N, STAGES, STATS><<<(unsigned)grid, IGP_THREADS, SM::TOTAL, s>>>(p));
   return DBB_OK;
 }
-
 int igemm_launch(const IgemmPlan& p, cudaStream_t s) {
   if (p.cin % 64 != 0 || p.ntaps < 1 || p.ntaps > IGEMM_MAX_TAPS) return set_error(DBB_EUNSUPPORTED, "igemm: cin must be a multiple of 64, taps <= 16");
   // The k-loop of a tile has ntaps*cin/64 iterations; short loops (1x1 convolutions, ConvTranspose, conv1) get a
@@ -1054,16 +1154,19 @@ int igemm_launch(const IgemmPlan& p, cudaStream_t s) {
   static const bool no_persist = getenv("DBB_NO_PERSIST") != nullptr;
   const int depth = deep_only ? 4 : (kiters <= 1 ? 1 : (kiters <= 4 ? 2 : 4));
   if (!no_persist || p.st.enabled) {
+    const bool st = p.st.enabled != 0;
     switch (p.block_n) {
       case 64:
-        if (depth <= 2) return igemm_launch_p<64, 2>(p, s);     // 48 KB -> 4 CTAs/SM
-        return igemm_launch_p<64, 4>(p, s);                     // 96 KB -> 2 CTAs/SM
+        // statistics in registers (64 accumulators/thread) -> 1 CTA/SM, so that CTA gets a deep ring
+        if (st) return igemm_launch_p2<64, 6, true>(p, s);                                                   // 144 KB
+        if (depth <= 2) return igemm_launch_p2<64, 2, false>(p, s);                                          // 48 KB -> 4 CTAs/SM
+        return igemm_launch_p2<64, 4, false>(p, s);                                                          // 96 KB -> 2 CTAs/SM
       case 128:
-        if (depth <= 2) return igemm_launch_p<128, 2>(p, s);    // 64 KB -> 2 CTAs/SM (TMEM)
-        return igemm_launch_p<128, 3>(p, s);                    // 96 KB -> 2 CTAs/SM
+        if (depth <= 2) return st ? igemm_launch_p2<128, 2, true>(p, s) : igemm_launch_p2<128, 2, false>(p, s);   // 2 CTAs/SM (TMEM)
+        return st ? igemm_launch_p2<128, 3, true>(p, s) : igemm_launch_p2<128, 3, false>(p, s);
       case 256:
-        if (depth <= 2) return igemm_launch_p<256, 2>(p, s);    // 96 KB -> 1 CTA/SM (TMEM)
-        return igemm_launch_p<256, 4>(p, s);                    // 192 KB -> 1 CTA/SM
+        if (depth <= 2) return st ? igemm_launch_p2<256, 2, true>(p, s) : igemm_launch_p2<256, 2, false>(p, s);   // 1 CTA/SM (TMEM)
+        return st ? igemm_launch_p2<256, 4, true>(p, s) : igemm_launch_p2<256, 4, false>(p, s);
       default: return set_error(DBB_EUNSUPPORTED, "igemm: block_n must be 64, 128 or 256");
     }
   }
@@ -1099,6 +1202,29 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
+// few outputs, many splits (ConvTranspose / conv1 / 1x1 gradients): a block sums 32 consecutive outputs, warp w takes
+// splits w, w+8, ... and the eight partial sums are combined in a fixed order (still bitwise reproducible)
+__global__ void __launch_bounds__(256) wgrad_reduce_wide_kernel(const float* __restrict__ ws, int split_k, int ntaps, int m_pad, int n_pad,
+                                                                int m_total, int n_total, int tap_stride, float* __restrict__ dw) {
+  __shared__ float part[8][32];
+  const int64_t plane = (int64_t)ntaps * m_pad * n_pad;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + lane;            // n_total % 32 == 0: the 32 outputs share (tap, m)
+  const int n = (int)(i % n_total); const int64_t t = i / n_total;
+  const int m = (int)(t % m_total); const int tap = (int)(t / m_total);
+  const float* src = ws + ((int64_t)tap * m_pad + m) * n_pad + n;
+  float acc = 0.f;
+  for (int sp = wp; sp < split_k; sp += 8) acc += src[(int64_t)sp * plane];
+  part[wp][lane] = acc;
+  __syncthreads();
+  if (wp == 0) {
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += part[k][lane];
+    dw[((int64_t)m * n_total + n) * tap_stride + tap] = r;
+  }
+}
+
 size_t wgrad_scratch_bytes(const WgradPlan& p) {
   return (size_t)p.split_k * p.ntaps * p.m_pad * p.n_pad * sizeof(float);
 }
@@ -1129,6 +1255,10 @@ static int wgrad_launch_t(const WgradPlan& p, cudaStream_t s) {
     char tmp[96];
     snprintf(tmp, sizeof(tmp), "wgrad_reduce_s%d_t%d_m%d_n%d", p.split_k, p.ntaps, p.m_total, p.n_total);
     rlabel = prof_label(tmp);
+  }
+  if (p.split_k >= 16 && p.n_total % 32 == 0 && total / 32 <= 65535 * 16) {
+    DBB_LAUNCH(rlabel, s, wgrad_reduce_wide_kernel<<<(unsigned)(total / 32), 256, 0, s>>>(p.ws, p.split_k, p.ntaps, p.m_pad, p.n_pad, p.m_total, p.n_total, p.tap_stride, p.dw));
+    return DBB_OK;
   }
   DBB_LAUNCH(rlabel, s, wgrad_reduce_kernel<<<rgrid, 256, 0, s>>>(p.ws, p.split_k, p.ntaps, p.m_pad, p.n_pad, p.m_total, p.n_total, p.tap_stride, p.dw));
   return DBB_OK;

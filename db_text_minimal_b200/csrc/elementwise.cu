@@ -91,9 +91,10 @@ __device__ __forceinline__ F8 ldf8(const float* p) {
   return F8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
 }
 
+// Blocks of a per-channel reduction: every block ends with 2*c global fp64 atomics, so a block should own at least
+// ~64 KB of the tensor (small wide tensors were spending most of their time in those atomics).
 static int ew_blocks(int64_t P, int c) {
-  const int ppi = EW_THREADS / (c / 8);              // pixels per block iteration
-  int64_t want = (P + (int64_t)ppi * 4 - 1) / ((int64_t)ppi * 4);
+  int64_t want = (P * c * 2 + 65535) / 65536;
   if (want < 1) want = 1;
   if (want > BN_MAX_BLOCKS) want = BN_MAX_BLOCKS;
   return (int)want;
@@ -282,12 +283,7 @@ bn_bwd_apply_kernel(const bf16* __restrict__ dout, int dout_ctotal, int dout_cof
   const F8 a = ldf8(coef3 + g * 8), c1 = ldf8(coef3 + c + g * 8), c2 = ldf8(coef3 + 2 * c + g * 8);
   F8 sc, sh;
   if (MASK == 2) { sc = ldf8(stats4 + g * 8); sh = ldf8(stats4 + c + g * 8); }
-  for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
-    const int64_t p = i >> lg;
-    F8 dy = ld8s(dout + p * dout_ctotal + dout_coff + g * 8);
-    F8 m;
-    if (MASK == 1) m = ld8s(mask_src + p * mask_ctotal + mask_coff + g * 8);
-    const F8 x = ld8s(z + p * c + g * 8);
+  auto one = [&](F8 dy, const F8& m, const F8& x, int64_t p) {
     F8 o;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -297,6 +293,24 @@ bn_bwd_apply_kernel(const bf16* __restrict__ dout, int dout_ctotal, int dout_cof
     }
     st8(dz + p * c + g * 8, o);
     if (dsum) st8(dsum + p * c + g * 8, dy);
+  };
+  const int64_t step = (int64_t)gridDim.x * EW_THREADS;
+  int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x;
+  for (; i + step < total; i += 2 * step) {      // two items in flight per thread
+    const int64_t p0 = i >> lg, p1 = (i + step) >> lg;
+    const F8 dy0 = ld8s(dout + p0 * dout_ctotal + dout_coff + g * 8), dy1 = ld8s(dout + p1 * dout_ctotal + dout_coff + g * 8);
+    F8 m0, m1;
+    if (MASK == 1) { m0 = ld8s(mask_src + p0 * mask_ctotal + mask_coff + g * 8); m1 = ld8s(mask_src + p1 * mask_ctotal + mask_coff + g * 8); }
+    const F8 x0 = ld8s(z + p0 * c + g * 8), x1 = ld8s(z + p1 * c + g * 8);
+    one(dy0, m0, x0, p0); one(dy1, m1, x1, p1);
+  }
+  if (i < total) {
+    const int64_t p0 = i >> lg;
+    const F8 dy0 = ld8s(dout + p0 * dout_ctotal + dout_coff + g * 8);
+    F8 m0;
+    if (MASK == 1) m0 = ld8s(mask_src + p0 * mask_ctotal + mask_coff + g * 8);
+    const F8 x0 = ld8s(z + p0 * c + g * 8);
+    one(dy0, m0, x0, p0);
   }
 }
 
@@ -554,36 +568,55 @@ __global__ void __launch_bounds__(EW_THREADS) maxpool_fwd_kernel(const bf16* __r
     }
   }
 }
+// One thread per 2x2 block of dx pixels {2a, 2a+1} x {2b, 2b+1} and 8-channel group: the block is covered by exactly the
+// four pooling windows (a,b), (a,b+1), (a+1,b), (a+1,b+1), whose gradients and argmax bytes are loaded up front
+// (one window load per dx pixel instead of 2.25, all in flight together).
+__device__ __forceinline__ void mp_take(F8& acc, const F8& d, const uint2& pk, unsigned k) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const unsigned idx = ((j < 4 ? pk.x : pk.y) >> ((j & 3) * 8)) & 0xffu;
+    acc.v[j] += (idx == k) ? d.v[j] : 0.f;
+  }
+}
 __global__ void __launch_bounds__(EW_THREADS) maxpool_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* __restrict__ argmax, int n, int h,
                                                                  int w, int c, int oh, int ow, bf16* __restrict__ dx) {
   const int groups = c / 8;
-  const int64_t total = (int64_t)n * h * w * groups;
+  const int hb = (h + 1) / 2, wb = (w + 1) / 2;
+  const int64_t total = (int64_t)n * hb * wb * groups;
   for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
     const unsigned u = (unsigned)i;
     const int g = (int)(u % (unsigned)groups); unsigned t = u / (unsigned)groups;
-    const int xx = (int)(t % (unsigned)w); t /= (unsigned)w; const int yy = (int)(t % (unsigned)h); const int b = (int)(t / (unsigned)h);
-    F8 acc;
+    const int b = (int)(t % (unsigned)wb); t /= (unsigned)wb; const int a = (int)(t % (unsigned)hb); const int img = (int)(t / (unsigned)hb);
+    F8 d[4]; uint2 pk[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
-    // windows (y0, x0) with 2*y0-1 <= yy <= 2*y0+1
-    const int y_lo = yy / 2, y_hi = (yy + 1) / 2, x_lo = xx / 2, x_hi = (xx + 1) / 2;
-    for (int y0 = y_lo; y0 <= y_hi; ++y0) {
-      if (y0 >= oh) continue;
-      const int kh = yy - (2 * y0 - 1);
-      for (int x0 = x_lo; x0 <= x_hi; ++x0) {
-        if (x0 >= ow) continue;
-        const int k = kh * 3 + (xx - (2 * x0 - 1));
-        const int64_t o = (((int64_t)b * oh + y0) * ow + x0) * c + g * 8;
-        const uint2 pk = *reinterpret_cast<const uint2*>(argmax + o);
-        const F8 d = ld8(dy + o);
+    for (int q = 0; q < 4; ++q) {
+      const int y0 = a + (q >> 1), x0 = b + (q & 1);
+      if (y0 < oh && x0 < ow) {
+        const int64_t o = (((int64_t)img * oh + y0) * ow + x0) * c + g * 8;
+        pk[q] = *reinterpret_cast<const uint2*>(argmax + o);
+        d[q] = ld8(dy + o);
+      } else {
+        pk[q] = make_uint2(0xffffffffu, 0xffffffffu);     // matches no tap
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const unsigned idx = ((j < 4 ? pk.x : pk.y) >> ((j & 3) * 8)) & 0xffu;
-          if ((int)idx == k) acc.v[j] += d.v[j];
-        }
+        for (int j = 0; j < 8; ++j) d[q].v[j] = 0.f;
       }
     }
-    st8(dx + (((int64_t)b * h + yy) * w + xx) * c + g * 8, acc);
+    F8 o00, o01, o10, o11;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o00.v[j] = 0.f; o01.v[j] = 0.f; o10.v[j] = 0.f; o11.v[j] = 0.f; }
+    // tap index k = (yy - (2*y0 - 1)) * 3 + (xx - (2*x0 - 1)) of dx pixel (yy, xx) inside window (y0, x0)
+    mp_take(o00, d[0], pk[0], 4);
+    mp_take(o01, d[0], pk[0], 5); mp_take(o01, d[1], pk[1], 3);
+    mp_take(o10, d[0], pk[0], 7); mp_take(o10, d[2], pk[2], 1);
+    mp_take(o11, d[0], pk[0], 8); mp_take(o11, d[1], pk[1], 6); mp_take(o11, d[2], pk[2], 2); mp_take(o11, d[3], pk[3], 0);
+    const int yy = 2 * a, xx = 2 * b;
+    bf16* base = dx + (((int64_t)img * h + yy) * w + xx) * c + g * 8;
+    st8(base, o00);
+    if (xx + 1 < w) st8(base + c, o01);
+    if (yy + 1 < h) {
+      st8(base + (int64_t)w * c, o10);
+      if (xx + 1 < w) st8(base + (int64_t)w * c + c, o11);
+    }
   }
 }
 static int fits32(int64_t total, const char* who) { return total < ((int64_t)1 << 32) ? 0 : set_error(DBB_EUNSUPPORTED, who); }
@@ -596,7 +629,7 @@ int maxpool_fwd(const bf16* x, int n, int h, int w, int c, bf16* y, uint8_t* arg
 }
 int maxpool_bwd(const bf16* dy, const uint8_t* argmax, int n, int h, int w, int c, bf16* dx, cudaStream_t s) {
   const int oh = (h + 2 - 3) / 2 + 1, ow = (w + 2 - 3) / 2 + 1;
-  DBB_LAUNCH("maxpool_bwd", s, maxpool_bwd_kernel<<<stream_grid((int64_t)n * h * w * (c / 8)), EW_THREADS, 0, s>>>(dy, argmax, n, h, w, c, oh, ow, dx));
+  DBB_LAUNCH("maxpool_bwd", s, maxpool_bwd_kernel<<<stream_grid((int64_t)n * ((h + 1) / 2) * ((w + 1) / 2) * (c / 8)), EW_THREADS, 0, s>>>(dy, argmax, n, h, w, c, oh, ow, dx));
   return DBB_OK;
 }
 
@@ -661,6 +694,48 @@ __global__ void __launch_bounds__(EW_THREADS) upsample_bwd_kernel(const bf16* __
     st8(o, acc);
   }
 }
+// c == 64 and a large ratio (FPN p4 / p5 -> p2 resolution): one WARP per source pixel, lane = (row-split rs, channel group g);
+// every lane sums the window rows y0 + rs, y0 + rs + 4, ... (128 contiguous bytes per row across the 8 groups) and the four
+// row-splits are combined by a fixed shuffle tree.
+__global__ void __launch_bounds__(EW_THREADS) upsample_bwd_warp_kernel(const bf16* __restrict__ d_big, int big_ctotal, int big_coff, int n, int h,
+                                                                       int w, float sch, float scw, bf16* __restrict__ d_xs,
+                                                                       int hs, int ws, int accumulate) {
+  const int lane = threadIdx.x & 31, g = lane & 7, rs = lane >> 3;
+  const int total = n * hs * ws;
+  for (int i = blockIdx.x * (EW_THREADS / 32) + (threadIdx.x >> 5); i < total; i += gridDim.x * (EW_THREADS / 32)) {
+    unsigned t = (unsigned)i;
+    const int sx = (int)(t % (unsigned)ws); t /= (unsigned)ws; const int sy = (int)(t % (unsigned)hs); const int b = (int)(t / (unsigned)hs);
+    int y0 = (int)ceilf((float)sy / sch) - 2; if (y0 < 0) y0 = 0;
+    while (y0 < h && nearest_src(y0, sch, hs) < sy) ++y0;
+    int y1 = y0; while (y1 < h && nearest_src(y1, sch, hs) == sy) ++y1;
+    int x0 = (int)ceilf((float)sx / scw) - 2; if (x0 < 0) x0 = 0;
+    while (x0 < w && nearest_src(x0, scw, ws) < sx) ++x0;
+    int x1 = x0; while (x1 < w && nearest_src(x1, scw, ws) == sx) ++x1;
+    F8 acc;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
+    for (int yy = y0 + rs; yy < y1; yy += 4)
+      for (int xx = x0; xx < x1; ++xx) {
+        const F8 d = ld8(d_big + (((int64_t)b * h + yy) * w + xx) * big_ctotal + big_coff + g * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc.v[j] += d.v[j];
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc.v[j] += __shfl_xor_sync(0xffffffffu, acc.v[j], 8);
+      acc.v[j] += __shfl_xor_sync(0xffffffffu, acc.v[j], 16);
+    }
+    if (rs == 0) {
+      bf16* o = d_xs + (((int64_t)b * hs + sy) * ws + sx) * 64 + g * 8;
+      if (accumulate) {
+        const F8 old = ld8(o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc.v[j] += old.v[j];
+      }
+      st8(o, acc);
+    }
+  }
+}
 int upsample_add_fwd(const bf16* xs, int hs, int ws, const bf16* y, int n, int h, int w, int c, bf16* out, cudaStream_t s) {
   DBB_LAUNCH("upsample_add_fwd", s, upsample_fwd_kernel<<<stream_grid((int64_t)n * h * w * (c / 8)), EW_THREADS, 0, s>>>(xs, hs, ws, (float)hs / (float)h, (float)ws / (float)w, y, n, h, w, c, out, c, 0));
   return DBB_OK;
@@ -671,6 +746,12 @@ int upsample_into(const bf16* xs, int hs, int ws, int n, int h, int w, int c, bf
 }
 int upsample_bwd(const bf16* d_big, int big_ctotal, int big_coff, int n, int h, int w, int c, bf16* d_xs, int hs, int ws,
                  int accumulate, cudaStream_t s) {
+  if (c == 64 && h >= 4 * hs && (int64_t)n * hs * ws < (1 << 30)) {
+    int grid = (n * hs * ws + EW_THREADS / 32 - 1) / (EW_THREADS / 32);
+    if (grid > DBB_NUM_SMS * 16) grid = DBB_NUM_SMS * 16;
+    DBB_LAUNCH("upsample_bwd", s, upsample_bwd_warp_kernel<<<grid, EW_THREADS, 0, s>>>(d_big, big_ctotal, big_coff, n, h, w, (float)hs / (float)h, (float)ws / (float)w, d_xs, hs, ws, accumulate));
+    return DBB_OK;
+  }
   DBB_LAUNCH("upsample_bwd", s, upsample_bwd_kernel<<<stream_grid((int64_t)n * hs * ws * (c / 8)), EW_THREADS, 0, s>>>(d_big, big_ctotal, big_coff, n, h, w, c, (float)hs / (float)h, (float)ws / (float)w, d_xs, hs, ws, accumulate));
   return DBB_OK;
 }

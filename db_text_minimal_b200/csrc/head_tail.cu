@@ -195,20 +195,30 @@ head_tail_fwd_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w2, con
 // pass "reduce": per-channel sums for BN backward (sum dy, sum dy*xhat), dW2[c][tap] = sum a[c] dz[tap], db2 = sum dz
 // pass "apply" : d_zt = gamma*invstd*(dy - mean(dy) - xhat*mean(dy*xhat))  -> NHWC bf16
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bwd_phase_a(float (&dzs)[2][4][HT_TILE], const float* __restrict__ out, const float* __restrict__ dout,
-                                            int n, int i, int j0, int w2, int H, int W, float k) {
+// Phase A is software-pipelined: the six maps of tile k+1 are requested (registers) before the channel work of tile k, so
+// their global-memory latency hides behind it instead of stalling every tile.
+struct PhaseAIn { float P, T, B, dP, dT, dB; int valid; };
+__device__ __forceinline__ void bwd_phase_a_load(PhaseAIn& r, const float* __restrict__ out, const float* __restrict__ dout,
+                                                 int n, int i, int j0, int w2, int H, int W) {
+  const int a = threadIdx.x >> 7, col = threadIdx.x & 127;
+  const int px = col >> 1;
+  r.valid = (j0 + px < w2);
+  if (r.valid) {
+    const int64_t plane = (int64_t)H * W;
+    const int64_t o = ((int64_t)n * 3) * plane + (int64_t)(2 * i + a) * W + 2 * j0 + col;
+    r.P = __ldg(out + o); r.T = __ldg(out + o + plane); r.B = __ldg(out + o + 2 * plane);
+    r.dP = __ldg(dout + o); r.dT = __ldg(dout + o + plane); r.dB = __ldg(dout + o + 2 * plane);
+  }
+}
+__device__ __forceinline__ void bwd_phase_a_store(float (&dzs)[2][4][HT_TILE], const PhaseAIn& r, float k) {
   const int a = threadIdx.x >> 7, col = threadIdx.x & 127;
   const int px = col >> 1, tap = a * 2 + (col & 1);
   float dzb = 0.f, dzt = 0.f;
-  if (j0 + px < w2) {
-    const int64_t plane = (int64_t)H * W;
-    const int64_t o = ((int64_t)n * 3) * plane + (int64_t)(2 * i + a) * W + 2 * j0 + col;
-    const float P = __ldg(out + o), T = __ldg(out + o + plane), B = __ldg(out + o + 2 * plane);
-    const float dP = __ldg(dout + o), dT = __ldg(dout + o + plane), dB = __ldg(dout + o + 2 * plane);
-    const float e = expf(-k * (P - T));
-    const float s = dB * k * B * B * e;
-    dzb = (dP + s) * P * (1.f - P);
-    dzt = (dT - s) * T * (1.f - T);
+  if (r.valid) {
+    const float e = expf(-k * (r.P - r.T));
+    const float s = r.dB * k * r.B * r.B * e;
+    dzb = (r.dP + s) * r.P * (1.f - r.P);
+    dzt = (r.dT - s) * r.T * (1.f - r.T);
   }
   dzs[0][tap][px] = dzb;
   dzs[1][tap][px] = dzt;
@@ -243,10 +253,22 @@ head_tail_bwd_reduce_kernel(const bf16* __restrict__ zt, int n_img, int h2, int 
   const HtRing ring{ring_smem, full_bar, zt, tiles_per_row, h2, w2, ntiles};
   if (PIPE) ring.start();
   int64_t kk = 0;
+  PhaseAIn pa;
+  pa.valid = 0;
+  if ((int64_t)blockIdx.x < ntiles) {
+    int n, i, j0;
+    tile_coords(blockIdx.x, tiles_per_row, h2, n, i, j0);
+    bwd_phase_a_load(pa, out, dout, n, i, j0, w2, H, W);
+  }
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++kk) {
     int n, i, j0;
     tile_coords(tile, tiles_per_row, h2, n, i, j0);
-    bwd_phase_a(dzs, out, dout, n, i, j0, w2, H, W, k);
+    bwd_phase_a_store(dzs, pa, k);
+    if (tile + gridDim.x < ntiles) {       // request the next tile's maps now; consumed at the top of the next iteration
+      int n2, i2, j2;
+      tile_coords(tile + gridDim.x, tiles_per_row, h2, n2, i2, j2);
+      bwd_phase_a_load(pa, out, dout, n2, i2, j2, w2, H, W);
+    }
     __syncthreads();
     const bf16* zrow = PIPE ? ring.wait(kk) - (int64_t)j0 * 128 : zt + (((int64_t)n * h2 + i) * w2) * 128;
     const int br = l16 >> 3;
@@ -373,10 +395,22 @@ head_tail_bwd_apply_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w
   const HtRing ring{ring_smem, full_bar, zt, tiles_per_row, h2, w2, ntiles};
   if (PIPE) ring.start();
   int64_t kk = 0;
+  PhaseAIn pa;
+  pa.valid = 0;
+  if ((int64_t)blockIdx.x < ntiles) {
+    int n, i, j0;
+    tile_coords(blockIdx.x, tiles_per_row, h2, n, i, j0);
+    bwd_phase_a_load(pa, out, dout, n, i, j0, w2, H, W);
+  }
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++kk) {
     int n, i, j0;
     tile_coords(tile, tiles_per_row, h2, n, i, j0);
-    bwd_phase_a(dzs, out, dout, n, i, j0, w2, H, W, k);
+    bwd_phase_a_store(dzs, pa, k);
+    if (tile + gridDim.x < ntiles) {       // request the next tile's maps now; consumed at the top of the next iteration
+      int n2, i2, j2;
+      tile_coords(tile + gridDim.x, tiles_per_row, h2, n2, i2, j2);
+      bwd_phase_a_load(pa, out, dout, n2, i2, j2, w2, H, W);
+    }
     __syncthreads();
     const int64_t rowoff = (((int64_t)n * h2 + i) * w2) * 128;
     const bf16* ztile = PIPE ? ring.wait(kk) : nullptr;

@@ -354,15 +354,13 @@ int pack_all(const Ctx& c) {
   PackBatch b;
   b.njobs = 0;
   auto flush = [&]() -> int { int rc = pack_weights_batch(b, c.s); b.njobs = 0; return rc; };
-  auto add = [&](int mode, const float* w, bf16* out, int co, int ci, int ks, int co_total, int co_off) -> int {
+  auto add = [&](int mode, const float* w, bf16* out, int co, int ci, int ks, int co_total, int co_off, bf16* out2 = nullptr) -> int {
     if (b.njobs == PACK_BATCH) RC(flush());
-    b.jobs[b.njobs++] = PackJob{w, out, mode, co, ci, ks, ks, co_total > 0 ? co_total : co, co_off};
+    b.jobs[b.njobs++] = PackJob{w, out, mode, co, ci, ks, ks, co_total > 0 ? co_total : co, co_off, out2};
     return 0;
   };
-  auto unit = [&](ConvBN& L) -> int {
-    RC(add(0, c.par(L.w), c.p(L.wp), L.g.cout, L.g.cin, L.g.ks, 0, 0));
-    if (net->training && L.wpt.bytes) RC(add(1, c.par(L.w), c.p(L.wpt), L.g.cout, L.g.cin, L.g.ks, 0, 0));
-    return 0;
+  auto unit = [&](ConvBN& L) -> int {     // one tiled job writes the fprop layout and (training) the transposed dgrad layout
+    return add(5, c.par(L.w), c.p(L.wp), L.g.cout, L.g.cin, L.g.ks, 0, 0, (net->training && L.wpt.bytes) ? c.p(L.wpt) : nullptr);
   };
   RC(add(4, c.par(P("backbone.conv1.weight")), c.p(net->wp_conv1), 64, 3, 7, 0, 0));
   for (int i = 0; i < 8; ++i) {
@@ -374,12 +372,10 @@ int pack_all(const Ctx& c) {
   RC(unit(net->fconv));
   for (int br = 0; br < 2; ++br) {
     const std::string pre = std::string("segmentation_head.") + (br ? "thresh" : "binarize");
-    RC(add(0, c.par(P(pre + ".0.weight")), c.p(net->wp_h) + (size_t)br * 64 * 256 * 9, 64, 256, 3, 0, 0));
+    RC(add(5, c.par(P(pre + ".0.weight")), c.p(net->wp_h) + (size_t)br * 64 * 256 * 9, 64, 256, 3, 128, br * 64,
+           net->training ? c.p(net->wpt_h) : nullptr));
     RC(add(2, c.par(P(pre + ".3.weight")), c.p(net->wp_t[br]), 64, 64, 2, 0, 0));
-    if (net->training) {
-      RC(add(1, c.par(P(pre + ".0.weight")), c.p(net->wpt_h), 64, 256, 3, 128, br * 64));
-      RC(add(3, c.par(P(pre + ".3.weight")), c.p(net->wpt_t[br]), 64, 64, 2, 0, 0));
-    }
+    if (net->training) RC(add(3, c.par(P(pre + ".3.weight")), c.p(net->wpt_t[br]), 64, 64, 2, 0, 0));
   }
   return flush();
 }

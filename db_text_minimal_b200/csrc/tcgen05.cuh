@@ -55,6 +55,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// long waits (epilogue warps waiting for a whole k-loop): back off between polls so the spinning warps do not take issue
+// slots from the single MMA-issuing thread that shares their scheduler
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  for (uint32_t i = 0; !mbar_try_wait(bar, parity); ++i) {
+    __nanosleep(128);
+    if (i > (1u << 23)) {
+      printf("dbb: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(m)) : "memory");
