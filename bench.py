@@ -32,7 +32,8 @@ def parse():
     ap.add_argument("--reduction", default="none", choices=["none", "mean"],
                     help="'none' = true top-k OHEM (BASELINE config 2); 'mean' = the reference's shipped (degenerate) default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="do not replay the step as a CUDA graph (single GPU only)")
+    ap.add_argument("--no-graph", action="store_true", help="do not replay the step as a CUDA graph")
+    ap.add_argument("--no-graph-dp", action="store_true", help="multi-GPU: keep the step eager (the graph would contain the NCCL all-reduces)")
     ap.add_argument("--dump-kernels", default=None, help="write the full per-kernel timing table (JSON) to this path")
     ap.add_argument("--cpu-batch", type=int, default=2, help="images in the bounded CPU sample")
     return ap.parse_args()
@@ -173,7 +174,7 @@ def run_ours(args):
     torch.manual_seed(0)                       # identical replicas on every rank
     model = DBTextModel().to(dev).train()
     crit = DBLoss(alpha=1.0, beta=10.0, reduction=args.reduction, negative_ratio=3)
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph and (world == 1 or not args.no_graph_dp)
     opt = torch.optim.Adam(model.parameters(), lr=0.005, fused=True, capturable=use_graph)     # src/train.py:114-117
     sync = GradSync(model)
 
@@ -197,7 +198,13 @@ def run_ours(args):
     graphed = None
     if use_graph:
         from db_text_minimal_b200.graph import GraphedTrainStep
-        graphed = GraphedTrainStep(model, crit, opt, dev_batches[0][0].shape, dev_batches[0][1].shape, dev).capture(*dev_batches[0])
+        try:
+            graphed = GraphedTrainStep(model, crit, opt, dev_batches[0][0].shape, dev_batches[0][1].shape, dev,
+                                       capture_error_mode="thread_local" if world > 1 else "global").capture(*dev_batches[0])
+        except Exception as e:          # deterministic across ranks (same code path), so every rank falls back together
+            print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running the step eagerly", file=sys.stderr)
+            graphed = None
+            torch.cuda.synchronize()
 
     def step(img, gts):
         # same work either way; with the graph the ~280 launches of a step are replayed by one cudaGraphLaunch
@@ -371,6 +378,16 @@ def run_ours(args):
             out["cpu_baseline"] = None
         print(json.dumps(out), flush=True)
     if world > 1:
+        sys.stdout.flush()
+        if graphed is not None:
+            # the captured graph holds NCCL kernel nodes: release it before the communicator, and do not let a
+            # communicator teardown that waits on it keep a finished benchmark alive
+            graphed.graph.reset()
+            torch.cuda.synchronize()
+            guard = threading.Timer(15.0, lambda: os._exit(0))
+            guard.daemon = True
+            guard.start()
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -148,16 +148,24 @@ int convt_dgrad(const ConvGeom& g, const bf16* dy, int dy_ctotal, int dy_coff, c
   return igemm_launch(p, s);
 }
 
-// split-K policy: enough CTAs to fill the GPU, but at least 8 k-iterations per CTA and partials that fit the scratch
-static int pick_split_k(int64_t out_tiles, int total_pixel_tiles, size_t tile_bytes_all, size_t scratch_bytes) {
-  int64_t want = (2 * DBB_NUM_SMS + out_tiles - 1) / out_tiles;
-  const int64_t cap_k = total_pixel_tiles / 8 > 1 ? total_pixel_tiles / 8 : 1;
+// split-K policy: minimise (waves of CTAs) x (k-iterations per CTA).  A grid one CTA over a multiple of the resident slots
+// costs a whole extra wave (306 CTAs on 148 slots ran at 69 % efficiency), so the split is chosen wave-aware; at least
+// 8 k-iterations per CTA, partials must fit the scratch, ties go to the smaller split (less scratch traffic to reduce).
+static int pick_split_k(int64_t out_tiles, int total_pixel_tiles, size_t tile_bytes_all, size_t scratch_bytes, int slots) {
+  int64_t cap = total_pixel_tiles / 8 > 1 ? total_pixel_tiles / 8 : 1;
   const int64_t cap_ws = tile_bytes_all ? (int64_t)(scratch_bytes / tile_bytes_all) : 1;
-  if (want > cap_k) want = cap_k;
-  if (want > cap_ws) want = cap_ws;
-  if (want > total_pixel_tiles) want = total_pixel_tiles;
-  if (want < 1) want = 1;
-  return (int)want;
+  if (cap > cap_ws) cap = cap_ws;
+  if (cap > total_pixel_tiles) cap = total_pixel_tiles;
+  if (cap > 4096) cap = 4096;
+  if (cap < 1) cap = 1;
+  int64_t best = 1; double best_cost = 1e30;
+  for (int64_t sp = 1; sp <= cap; ++sp) {
+    const int64_t waves = (out_tiles * sp + slots - 1) / slots;
+    const int64_t kiters = (total_pixel_tiles + sp - 1) / sp;
+    const double cost = (double)waves * (double)(kiters + 6) + 0.05 * (double)sp;     // + pipeline fill/epilogue per CTA, + reduce
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = sp; }
+  }
+  return (int)best;
 }
 
 static int wgrad_finish_plan(WgradPlan& p, float* scratch, size_t scratch_bytes) {
@@ -165,7 +173,18 @@ static int wgrad_finish_plan(WgradPlan& p, float* scratch, size_t scratch_bytes)
   p.m_pad = m_tiles * 128; p.n_pad = n_tiles * p.n_tile;
   const size_t one = (size_t)p.ntaps * p.m_pad * p.n_pad * sizeof(float);
   if (!scratch || scratch_bytes < one) return set_error(DBB_EWORKSPACE, "wgrad: split-K scratch too small");
-  p.split_k = pick_split_k((int64_t)p.ntaps * m_tiles * n_tiles, p.tiles_n * p.tiles_h * p.tiles_w, one, scratch_bytes);
+  const int slots = DBB_NUM_SMS * (p.n_tile >= 256 ? 1 : 2);      // resident CTAs: 192 KB ring at N = 256, 96 KB below
+  static const bool legacy = getenv("DBB_LEGACY_SPLITK") != nullptr;    // A/B switch: the old "2 CTAs per SM worth" rule
+  if (legacy) {
+    const int64_t out_tiles = (int64_t)p.ntaps * m_tiles * n_tiles;
+    int64_t want = (2 * DBB_NUM_SMS + out_tiles - 1) / out_tiles;
+    const int64_t T = p.tiles_n * p.tiles_h * p.tiles_w;
+    if (want > (T / 8 > 1 ? T / 8 : 1)) want = (T / 8 > 1 ? T / 8 : 1);
+    if (want > (int64_t)(scratch_bytes / one)) want = (int64_t)(scratch_bytes / one);
+    p.split_k = (int)(want < 1 ? 1 : want);
+  } else {
+    p.split_k = pick_split_k((int64_t)p.ntaps * m_tiles * n_tiles, p.tiles_n * p.tiles_h * p.tiles_w, one, scratch_bytes, slots);
+  }
   p.ws = scratch;
   return DBB_OK;
 }

@@ -425,7 +425,7 @@ __device__ __forceinline__ uint64_t make_desc_sw128_off(uint32_t smem_addr, uint
   return d;
 }
 
-__global__ void __launch_bounds__(IG_THREADS)
+__global__ void __launch_bounds__(IGP_THREADS)
 halo64_kernel(const __grid_constant__ HaloPlan p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -442,14 +442,14 @@ halo64_kernel(const __grid_constant__ HaloPlan p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_bytes = (uint32_t)((p.R + 2) * p.pitch) * 128u;
-  for (int i = threadIdx.x; i < 512; i += IG_THREADS) s_stat[i] = 0.f;
+  for (int i = threadIdx.x; i < 512; i += IGP_THREADS) s_stat[i] = 0.f;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmap_x);
     prefetch_tmap(&p.tmap_w);
     for (int s = 0; s < HALO_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     mbar_init(b_full, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<128>(tmem_slot);
@@ -500,12 +500,13 @@ halo64_kernel(const __grid_constant__ HaloPlan p) {
       }
     }
   } else {
-    const int q = warp & 3;
+    // 8 epilogue warps: warp w drains TMEM lane quadrant w % 4, channels [32*half, 32*half + 32) with half = (w - 2) / 4
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int dr = r / p.pitch, dc = r - dr * p.pitch;
-    float acc_s[4][16], acc_q[4][16];      // fused BatchNorm statistics: this row's running sums for the 64 channels
+    float acc_s[2][16], acc_q[2][16];      // fused BatchNorm statistics: this row's running sums for its 32 channels
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < 2; ++c)
 #pragma unroll
       for (int i = 0; i < 16; ++i) { acc_s[c][i] = 0.f; acc_q[c][i] = 0.f; }
     int k = 0;
@@ -518,17 +519,17 @@ halo64_kernel(const __grid_constant__ HaloPlan p) {
       const bool ok = dr < p.R && dc < p.bw && hh < p.h && ww < p.w;
       mbar_wait_sleep(&t_full[buf], (uint32_t)(k >> 1) & 1u);
       tc_fence_after();
-      uint32_t v[4][16];
-      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 64);
+      uint32_t v[2][16];
+      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 64 + half * 32);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_x16(taddr + (uint32_t)(c * 16), v[c]);
+      for (int c = 0; c < 2; ++c) tmem_ld_x16(taddr + (uint32_t)(c * 16), v[c]);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[buf]);       // accumulator drained: the MMA warp may reuse this buffer
-      bf16* yrow = p.y + (((int64_t)n * p.h + hh) * p.w + ww) * p.out_c + p.out_coff;
+      if (lane == 0) mbar_arrive(&t_empty[buf]);       // this warp's part is drained (8 arrivals free the buffer)
+      bf16* yrow = p.y + (((int64_t)n * p.h + hh) * p.w + ww) * p.out_c + p.out_coff + half * 32;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
         if (ok) {
           float f[16];
@@ -536,7 +537,7 @@ halo64_kernel(const __grid_constant__ HaloPlan p) {
           for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[c][j]);
           if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + c * 16 + j);
+            for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + half * 32 + c * 16 + j);
           }
           uint4* dst = reinterpret_cast<uint4*>(yrow + c * 16);
           if (p.accumulate) {
@@ -554,9 +555,10 @@ halo64_kernel(const __grid_constant__ HaloPlan p) {
       }
     }
     if (p.st.enabled) {
+      float* w_sum = s_stat + q * 128 + half * 32;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) stat_reduce_store16<false>(acc_s[c], acc_q[c], lane, s_stat + q * 128 + c * 16, s_stat + q * 128 + 64 + c * 16);
-      stat_flush<128>(p.st, s_stat, 64, 0, 64, 0, p.out_coff, p.out_c, r, s_flag);
+      for (int c = 0; c < 2; ++c) stat_reduce_store16<false>(acc_s[c], acc_q[c], lane, w_sum + c * 16, w_sum + 64 + c * 16);
+      stat_flush<IGP_EPI_THREADS>(p.st, s_stat, 64, 0, 64, 0, p.out_coff, p.out_c, (int)threadIdx.x - 64, s_flag);
     }
   }
   tc_fence_before();
@@ -610,7 +612,7 @@ int halo64_launch(const HaloPlan& p, cudaStream_t s) {
     snprintf(tmp, sizeof(tmp), "igemm_bn64_m%lld_n64_k576_halo", (long long)p.n * p.h * p.w);
     label = prof_label(tmp);
   }
-  DBB_LAUNCH(label, s, halo64_kernel<<<grid, IG_THREADS, HALO_SMEM, s>>>(p));
+  DBB_LAUNCH(label, s, halo64_kernel<<<grid, IGP_THREADS, HALO_SMEM, s>>>(p));
   return DBB_OK;
 }
 

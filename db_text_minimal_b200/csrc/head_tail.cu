@@ -227,7 +227,7 @@ __device__ __forceinline__ void bwd_phase_a_store(float (&dzs)[2][4][HT_TILE], c
 constexpr int HT_NACC = 6;   // per channel: dW2[4 taps], sum dy, sum dy*xhat
 
 template <bool PIPE>
-__global__ void __launch_bounds__(HT_THREADS)
+__global__ void __launch_bounds__(HT_THREADS, 2)
 head_tail_bwd_reduce_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w2, const float* __restrict__ stats4,
                             const float* __restrict__ w2b, const float* __restrict__ w2t, const float* __restrict__ out,
                             const float* __restrict__ dout, float k, float* __restrict__ partials /* [grid][128*6 + 2] */) {
@@ -482,7 +482,7 @@ int head_tail_bwd_reduce(const bf16* zt, int n, int h2, int w2, const float* sta
   if (w2 % HT_TILE == 0) {
     static bool attr = false;
     if (!attr) { DBB_CUDA(cudaFuncSetAttribute(head_tail_bwd_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_RING_BYTES)); attr = true; }
-    const int g = ht_pipe_grid(n, h2, w2, 1);
+    const int g = ht_pipe_grid(n, h2, w2, 2);      // 2 CTAs/SM (launch bound caps the kernel at 128 registers)
     *nblk = g < *nblk ? g : *nblk;
     DBB_LAUNCH("head_tail_bwd_reduce", s, head_tail_bwd_reduce_kernel<true><<<*nblk, HT_THREADS, HT_RING_BYTES, s>>>(zt, n, h2, w2, stats4, w2b, w2t, out, dout, k, partials));
     return DBB_OK;

@@ -8,9 +8,14 @@ import torch
 
 
 class GraphedTrainStep:
-    """step(img, gts) -> loss tensor (static, overwritten by every replay).  Single-process use."""
+    """step(img, gts) -> loss tensor (static, overwritten by every replay).
 
-    def __init__(self, model, criterion, optimizer, img_shape, gts_shape, device, warmup=3):
+    Data-parallel use: the gradient all-reduces issued by dist.GradSync during backward are NCCL kernels on NCCL's own
+    stream, forked from / joined to the capturing stream by events, so they become nodes of the same graph; pass
+    capture_error_mode="thread_local" so that the process group's watchdog thread cannot invalidate the capture."""
+
+    def __init__(self, model, criterion, optimizer, img_shape, gts_shape, device, warmup=3, capture_error_mode="global"):
+        self.capture_error_mode = capture_error_mode
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
         self.img = torch.zeros(img_shape, dtype=torch.float32, device=device)
         self.gts = torch.zeros(gts_shape, dtype=torch.float32, device=device)
@@ -38,7 +43,7 @@ class GraphedTrainStep:
         L = _lib.lib()
         self.graph = torch.cuda.CUDAGraph()
         n0 = L.dbb_launch_count()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode=self.capture_error_mode):
             self.loss = self._eager()
         self.launches_per_replay = int(L.dbb_launch_count() - n0)     # kernel nodes of this library inside the graph
         return self
