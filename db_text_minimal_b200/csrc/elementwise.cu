@@ -336,6 +336,21 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ partials, int n
   if ((threadIdx.x & 31) == 0) out[ch] = (float)s;
 }
 
+// Grid of a grid-stride kernel = one resident wave: SMs x (blocks that fit per SM for THIS kernel's register use).  Launching
+// more (the old fixed 16 blocks/SM) meant several waves of short-lived blocks; launching a non-multiple (592 blocks on 444
+// slots) cost a second wave for a third of the work.
+template <typename K>
+static int resident_blocks(K kernel) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, EW_THREADS, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 2; }
+  return DBB_NUM_SMS * occ;
+}
+#define DBB_RESIDENT(kernel) ([]() -> int { static const int v = resident_blocks(kernel); return v; }())
+static int fit_grid(int64_t blocks_wanted, int resident) {
+  if (blocks_wanted < 1) blocks_wanted = 1;
+  return (int)(blocks_wanted < resident ? blocks_wanted : resident);
+}
+
 static const char* shaped(const char* base, int64_t P, int c, int extra = -1) {
   if (!prof_enabled()) return base;
   char tmp[96];
@@ -460,17 +475,17 @@ bn_bwd_reduce_fin_kernel(const bf16* __restrict__ dout, int dout_ctotal, int dou
 
 int bn_stats_finalize(const bf16* z, int64_t P, int c, const BnFin& fin, double* gacc, unsigned* counter, cudaStream_t s) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_stats: channel count");
-  DBB_LAUNCH(shaped("bn_stats_fin", P, c), s, bn_stats_fin_kernel<<<ew_blocks(P, c), EW_THREADS, 0, s>>>(z, P, c, gacc, counter, fin));
+  DBB_LAUNCH(shaped("bn_stats_fin", P, c), s, bn_stats_fin_kernel<<<fit_grid(ew_blocks(P, c), DBB_RESIDENT(bn_stats_fin_kernel)), EW_THREADS, 0, s>>>(z, P, c, gacc, counter, fin));
   return DBB_OK;
 }
 int bn_bwd_reduce_finalize(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
                            const bf16* z, int64_t P, int c, const float* stats4, const BnBwdFin& fin, double* gacc,
                            unsigned* counter, cudaStream_t s, int mask_self) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_bwd_reduce: channel count");
-  const int grid = ew_blocks(P, c);
-  if (mask_self) DBB_LAUNCH(shaped("bn_bwd_reduce_fin", P, c, 2), s, bn_bwd_reduce_fin_kernel<2><<<grid, EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, gacc, counter, fin));
-  else if (mask_src) DBB_LAUNCH(shaped("bn_bwd_reduce_fin", P, c, 1), s, bn_bwd_reduce_fin_kernel<1><<<grid, EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, gacc, counter, fin));
-  else DBB_LAUNCH(shaped("bn_bwd_reduce_fin", P, c, 0), s, bn_bwd_reduce_fin_kernel<0><<<grid, EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, gacc, counter, fin));
+  const int want = ew_blocks(P, c);
+  if (mask_self) DBB_LAUNCH(shaped("bn_bwd_reduce_fin", P, c, 2), s, bn_bwd_reduce_fin_kernel<2><<<fit_grid(want, DBB_RESIDENT(bn_bwd_reduce_fin_kernel<2>)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, gacc, counter, fin));
+  else if (mask_src) DBB_LAUNCH(shaped("bn_bwd_reduce_fin", P, c, 1), s, bn_bwd_reduce_fin_kernel<1><<<fit_grid(want, DBB_RESIDENT(bn_bwd_reduce_fin_kernel<1>)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, gacc, counter, fin));
+  else DBB_LAUNCH(shaped("bn_bwd_reduce_fin", P, c, 0), s, bn_bwd_reduce_fin_kernel<0><<<fit_grid(want, DBB_RESIDENT(bn_bwd_reduce_fin_kernel<0>)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, gacc, counter, fin));
   return DBB_OK;
 }
 
@@ -498,7 +513,7 @@ static int stream_grid(int64_t total) {
 int bn_apply(const bf16* z, int64_t P, int c, const float* stats4, const bf16* res, int relu, bf16* out, int out_ctotal,
              int out_coff, cudaStream_t s) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_apply: channel count");
-  DBB_LAUNCH(shaped("bn_apply", P, c, res ? 1 : 0), s, bn_apply_kernel<<<stream_grid(P * (c / 8)), EW_THREADS, 0, s>>>(z, P, c, stats4, res, relu, out, out_ctotal, out_coff));
+  DBB_LAUNCH(shaped("bn_apply", P, c, res ? 1 : 0), s, bn_apply_kernel<<<fit_grid((P * (c / 8) + 2 * EW_THREADS - 1) / (2 * EW_THREADS), DBB_RESIDENT(bn_apply_kernel)), EW_THREADS, 0, s>>>(z, P, c, stats4, res, relu, out, out_ctotal, out_coff));
   return DBB_OK;
 }
 int bn_bwd_reduce(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
@@ -517,10 +532,10 @@ int bn_bwd_apply(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* m
                  const bf16* z, int64_t P, int c, const float* stats4, const float* coef3, bf16* dz, bf16* dsum,
                  cudaStream_t s, int mask_self) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_bwd_apply: channel count");
-  const int grid = stream_grid(P * (c / 8));
-  if (mask_self) DBB_LAUNCH(shaped("bn_bwd_apply", P, c, 2), s, bn_bwd_apply_kernel<2><<<grid, EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, coef3, dz, dsum));
-  else if (mask_src) DBB_LAUNCH(shaped("bn_bwd_apply", P, c, dsum ? 11 : 1), s, bn_bwd_apply_kernel<1><<<grid, EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, coef3, dz, dsum));
-  else DBB_LAUNCH(shaped("bn_bwd_apply", P, c, 0), s, bn_bwd_apply_kernel<0><<<grid, EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, coef3, dz, dsum));
+  const int64_t want = (P * (c / 8) + 2 * EW_THREADS - 1) / (2 * EW_THREADS);
+  if (mask_self) DBB_LAUNCH(shaped("bn_bwd_apply", P, c, 2), s, bn_bwd_apply_kernel<2><<<fit_grid(want, DBB_RESIDENT(bn_bwd_apply_kernel<2>)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, coef3, dz, dsum));
+  else if (mask_src) DBB_LAUNCH(shaped("bn_bwd_apply", P, c, dsum ? 11 : 1), s, bn_bwd_apply_kernel<1><<<fit_grid(want, DBB_RESIDENT(bn_bwd_apply_kernel<1>)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, coef3, dz, dsum));
+  else DBB_LAUNCH(shaped("bn_bwd_apply", P, c, 0), s, bn_bwd_apply_kernel<0><<<fit_grid(want, DBB_RESIDENT(bn_bwd_apply_kernel<0>)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, coef3, dz, dsum));
   return DBB_OK;
 }
 int bias_grad(const bf16* dz, int64_t P, int c, float* partials, float* dbias, cudaStream_t s) {
@@ -624,12 +639,12 @@ static int fits32(int64_t total, const char* who) { return total < ((int64_t)1 <
 int maxpool_fwd(const bf16* x, int n, int h, int w, int c, bf16* y, uint8_t* argmax, cudaStream_t s) {
   const int oh = (h + 2 - 3) / 2 + 1, ow = (w + 2 - 3) / 2 + 1;
   if (fits32((int64_t)n * h * w * (c / 8), "maxpool: tensor too large for 32-bit indexing")) return DBB_EUNSUPPORTED;
-  DBB_LAUNCH("maxpool_fwd", s, maxpool_fwd_kernel<<<stream_grid((int64_t)n * oh * ow * (c / 8)), EW_THREADS, 0, s>>>(x, n, h, w, c, oh, ow, y, argmax));
+  DBB_LAUNCH("maxpool_fwd", s, maxpool_fwd_kernel<<<fit_grid(((int64_t)n * oh * ow * (c / 8) + EW_THREADS - 1) / EW_THREADS, DBB_RESIDENT(maxpool_fwd_kernel)), EW_THREADS, 0, s>>>(x, n, h, w, c, oh, ow, y, argmax));
   return DBB_OK;
 }
 int maxpool_bwd(const bf16* dy, const uint8_t* argmax, int n, int h, int w, int c, bf16* dx, cudaStream_t s) {
   const int oh = (h + 2 - 3) / 2 + 1, ow = (w + 2 - 3) / 2 + 1;
-  DBB_LAUNCH("maxpool_bwd", s, maxpool_bwd_kernel<<<stream_grid((int64_t)n * ((h + 1) / 2) * ((w + 1) / 2) * (c / 8)), EW_THREADS, 0, s>>>(dy, argmax, n, h, w, c, oh, ow, dx));
+  DBB_LAUNCH("maxpool_bwd", s, maxpool_bwd_kernel<<<fit_grid(((int64_t)n * ((h + 1) / 2) * ((w + 1) / 2) * (c / 8) + EW_THREADS - 1) / EW_THREADS, DBB_RESIDENT(maxpool_bwd_kernel)), EW_THREADS, 0, s>>>(dy, argmax, n, h, w, c, oh, ow, dx));
   return DBB_OK;
 }
 
@@ -737,11 +752,11 @@ __global__ void __launch_bounds__(EW_THREADS) upsample_bwd_warp_kernel(const bf1
   }
 }
 int upsample_add_fwd(const bf16* xs, int hs, int ws, const bf16* y, int n, int h, int w, int c, bf16* out, cudaStream_t s) {
-  DBB_LAUNCH("upsample_add_fwd", s, upsample_fwd_kernel<<<stream_grid((int64_t)n * h * w * (c / 8)), EW_THREADS, 0, s>>>(xs, hs, ws, (float)hs / (float)h, (float)ws / (float)w, y, n, h, w, c, out, c, 0));
+  DBB_LAUNCH("upsample_add_fwd", s, upsample_fwd_kernel<<<fit_grid(((int64_t)n * h * w * (c / 8) + EW_THREADS - 1) / EW_THREADS, DBB_RESIDENT(upsample_fwd_kernel)), EW_THREADS, 0, s>>>(xs, hs, ws, (float)hs / (float)h, (float)ws / (float)w, y, n, h, w, c, out, c, 0));
   return DBB_OK;
 }
 int upsample_into(const bf16* xs, int hs, int ws, int n, int h, int w, int c, bf16* dst, int dst_ctotal, int dst_coff, cudaStream_t s) {
-  DBB_LAUNCH("upsample_into", s, upsample_fwd_kernel<<<stream_grid((int64_t)n * h * w * (c / 8)), EW_THREADS, 0, s>>>(xs, hs, ws, (float)hs / (float)h, (float)ws / (float)w, nullptr, n, h, w, c, dst, dst_ctotal, dst_coff));
+  DBB_LAUNCH("upsample_into", s, upsample_fwd_kernel<<<fit_grid(((int64_t)n * h * w * (c / 8) + EW_THREADS - 1) / EW_THREADS, DBB_RESIDENT(upsample_fwd_kernel)), EW_THREADS, 0, s>>>(xs, hs, ws, (float)hs / (float)h, (float)ws / (float)w, nullptr, n, h, w, c, dst, dst_ctotal, dst_coff));
   return DBB_OK;
 }
 int upsample_bwd(const bf16* d_big, int big_ctotal, int big_coff, int n, int h, int w, int c, bf16* d_xs, int hs, int ws,

@@ -13,6 +13,7 @@
 // the P/T/B rows leave as fully coalesced 512-byte stores.
 #include "common.cuh"
 #include "head_tail.h"
+#include <stdlib.h>
 #include "tcgen05.cuh"
 
 namespace dbb {
@@ -465,12 +466,13 @@ static int ht_reduce_grid(int n, int h2, int w2) {
   return (int)(g < 1 ? 1 : g);
 }
 
+static int ht_fwd_ctas() { static const int v = getenv("DBB_HT_FWD_CTAS") ? atoi(getenv("DBB_HT_FWD_CTAS")) : 3; return v; }   // 80 regs, 66 KB: 3 fit
 int head_tail_fwd(const bf16* zt, int n, int h2, int w2, const float* stats4, const float* w2b, const float* w2t,
                   const float* b2b, const float* b2t, float k, int out_c, float* out, cudaStream_t s) {
   if (w2 % HT_TILE == 0) {
     static bool attr = false;
     if (!attr) { DBB_CUDA(cudaFuncSetAttribute(head_tail_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_RING_BYTES)); attr = true; }
-    DBB_LAUNCH("head_tail_fwd", s, head_tail_fwd_kernel<true><<<ht_pipe_grid(n, h2, w2, 2), HT_THREADS, HT_RING_BYTES, s>>>(zt, n, h2, w2, stats4, w2b, w2t, b2b, b2t, k, out_c, out));
+    DBB_LAUNCH("head_tail_fwd", s, head_tail_fwd_kernel<true><<<ht_pipe_grid(n, h2, w2, ht_fwd_ctas()), HT_THREADS, HT_RING_BYTES, s>>>(zt, n, h2, w2, stats4, w2b, w2t, b2b, b2t, k, out_c, out));
     return DBB_OK;
   }
   DBB_LAUNCH("head_tail_fwd", s, head_tail_fwd_kernel<false><<<ht_grid(n, h2, w2), HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, w2b, w2t, b2b, b2t, k, out_c, out));
