@@ -33,6 +33,7 @@ def parse():
                     help="'none' = true top-k OHEM (BASELINE config 2); 'mean' = the reference's shipped (degenerate) default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step as a CUDA graph")
+    ap.add_argument("--torch-adam", action="store_true", help="use torch.optim.Adam(fused=True) instead of db_text_minimal_b200.optim.FlatAdam")
     ap.add_argument("--no-graph-dp", action="store_true", help="multi-GPU: keep the step eager (the graph would contain the NCCL all-reduces)")
     ap.add_argument("--dump-kernels", default=None, help="write the full per-kernel timing table (JSON) to this path")
     ap.add_argument("--cpu-batch", type=int, default=2, help="images in the bounded CPU sample")
@@ -175,7 +176,11 @@ def run_ours(args):
     model = DBTextModel().to(dev).train()
     crit = DBLoss(alpha=1.0, beta=10.0, reduction=args.reduction, negative_ratio=3)
     use_graph = not args.no_graph and (world == 1 or not args.no_graph_dp)
-    opt = torch.optim.Adam(model.parameters(), lr=0.005, fused=True, capturable=use_graph)     # src/train.py:114-117
+    if args.torch_adam:
+        opt = torch.optim.Adam(model.parameters(), lr=0.005, fused=True, capturable=use_graph)     # src/train.py:114-117
+    else:       # same update rule, one launch over the executor's flat parameter / gradient buffers (SURVEY f-2)
+        from db_text_minimal_b200.optim import FlatAdam
+        opt = FlatAdam(model, lr=0.005)
     sync = GradSync(model)
 
     # synthetic batches: per-rank seeds; three distinct host batches rotate through pinned memory for the e2e loop
@@ -353,7 +358,7 @@ def run_ours(args):
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"resnet18-FPN-DBHead training step fwd+DBLoss(OHEM {args.reduction})+bwd+Adam, batch {N}x3x{S}x{S} per GPU (BASELINE config {'2' if world == 1 else '3'})",
                        "per_gpu_batch": N, "global_batch": N * world, "image": [S, S], "reduction": args.reduction,
-                       "parallelism": f"dp{world}", "optimizer": "torch.optim.Adam(fused=True) inside the timed region",
+                       "parallelism": f"dp{world}", "optimizer": ("torch.optim.Adam(fused=True)" if args.torch_adam else "FlatAdam (dbb_adam_step, one launch)") + " inside the timed region",
                        "cuda_graph": bool(graphed is not None),
                        "l2": f"inputs {h2d_bytes / 1e6:.0f} MB/step (3 rotating batches) + ~6 GB of activations per step stream through the 126 MB L2; no explicit flush"},
             "clocks": clocks,

@@ -69,7 +69,7 @@ int pack_weights(int mode, const float* w, bf16* out, int co_n, int ci_n, int kh
 //           shared memory so that both the read and the two writes are coalesced (co_total / co_off apply to out2)
 struct PackJob { const float* w; bf16* out; int mode, co_n, ci_n, kh, kw, co_total, co_off; bf16* out2; };
 constexpr int PACK_BATCH = 48;
-struct PackBatch { int njobs; PackJob jobs[PACK_BATCH]; };
+struct PackBatch { int njobs; PackJob jobs[PACK_BATCH]; int tile_start[PACK_BATCH + 1]; };   // tile_start: filled by pack_weights_batch
 int pack_weights_batch(const PackBatch& b, cudaStream_t s);
 
 int igemm_plan_init(IgemmPlan* p, const bf16* x, int n, int h, int w, int c_total, int c_off, int cin,

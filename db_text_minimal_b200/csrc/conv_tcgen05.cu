@@ -938,44 +938,60 @@ __global__ void pack_weights_kernel(int mode, const float* __restrict__ w, bf16*
 // mode 5: Conv2d OIHW -> BOTH GEMM layouts from one coalesced read: a block stages a 32(co) x 32(ci) x taps tile in shared
 // memory, then writes out[co][tap][ci] (mode 0 layout) and, if out2, out2[ci][tap][co_off + co] (mode 1 layout) in 64-byte runs.
 constexpr int PACK_TILE_MAX_TAPS = 9;
-__device__ __forceinline__ void pack_tiled(const PackJob& j, float* tile /* [32][32*taps + 1] */) {
+__device__ __forceinline__ void pack_tile(const PackJob& j, int t, float* tile /* [32][32*taps + 1] */) {
   const int taps = j.kh * j.kw;
   const int row = 32 * taps + 1;
-  const int tiles_ci = j.ci_n / 32, ntiles = (j.co_n / 32) * tiles_ci;
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int co0 = (t / tiles_ci) * 32, ci0 = (t % tiles_ci) * 32;
-    __syncthreads();
+  const int tiles_ci = j.ci_n / 32;
+  const int co0 = (t / tiles_ci) * 32, ci0 = (t % tiles_ci) * 32;
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 32 * 32 * taps; idx += 256) {
+    const int co = idx / (32 * taps), rem = idx - co * 32 * taps;       // rem = ci * taps + tap: contiguous in w
+    tile[co * row + rem] = j.w[((int64_t)(co0 + co) * j.ci_n + ci0) * taps + rem];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 32 * 32 * taps; idx += 256) {
+    const int ci = idx & 31, r = idx >> 5;
+    const int tap = r % taps, co = r / taps;
+    j.out[((int64_t)(co0 + co) * taps + tap) * j.ci_n + ci0 + ci] = __float2bfloat16_rn(tile[co * row + ci * taps + tap]);
+  }
+  if (j.out2) {
     for (int idx = threadIdx.x; idx < 32 * 32 * taps; idx += 256) {
-      const int co = idx / (32 * taps), rem = idx - co * 32 * taps;       // rem = ci * taps + tap: contiguous in w
-      tile[co * row + rem] = j.w[((int64_t)(co0 + co) * j.ci_n + ci0) * taps + rem];
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < 32 * 32 * taps; idx += 256) {
-      const int ci = idx & 31, r = idx >> 5;
-      const int tap = r % taps, co = r / taps;
-      j.out[((int64_t)(co0 + co) * taps + tap) * j.ci_n + ci0 + ci] = __float2bfloat16_rn(tile[co * row + ci * taps + tap]);
-    }
-    if (j.out2) {
-      for (int idx = threadIdx.x; idx < 32 * 32 * taps; idx += 256) {
-        const int co = idx & 31, r = idx >> 5;
-        const int tap = r % taps, ci = r / taps;
-        j.out2[((int64_t)(ci0 + ci) * taps + tap) * j.co_total + j.co_off + co0 + co] = __float2bfloat16_rn(tile[co * row + ci * taps + tap]);
-      }
+      const int co = idx & 31, r = idx >> 5;
+      const int tap = r % taps, ci = r / taps;
+      j.out2[((int64_t)(ci0 + ci) * taps + tap) * j.co_total + j.co_off + co0 + co] = __float2bfloat16_rn(tile[co * row + ci * taps + tap]);
     }
   }
 }
+// One flat list of work units over all jobs (tile_start = prefix sums): a tiled job contributes (co/32)*(ci/32) tiles, any
+// other job is one unit, so blocks are spread in proportion to the work instead of 64 per job.
 __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const __grid_constant__ PackBatch b) {
   __shared__ float tile[32 * (32 * PACK_TILE_MAX_TAPS + 1)];
-  const PackJob& j = b.jobs[blockIdx.y];
-  if (j.mode == 5) { pack_tiled(j, tile); return; }
-  pack_one(j.mode, j.w, j.out, j.co_n, j.ci_n, j.kh, j.kw, j.co_total, j.co_off, (int64_t)blockIdx.x * 256 + threadIdx.x, (int64_t)gridDim.x * 256);
+  const int total = b.tile_start[b.njobs];
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    int ji = 0;
+    while (t >= b.tile_start[ji + 1]) ++ji;
+    const PackJob& j = b.jobs[ji];
+    if (j.mode == 5) pack_tile(j, t - b.tile_start[ji], tile);
+    else pack_one(j.mode, j.w, j.out, j.co_n, j.ci_n, j.kh, j.kw, j.co_total, j.co_off, threadIdx.x, 256);
+  }
 }
-int pack_weights_batch(const PackBatch& b, cudaStream_t s) {
-  for (int i = 0; i < b.njobs; ++i)
-    if (b.jobs[i].mode == 5 && (b.jobs[i].co_n % 32 || b.jobs[i].ci_n % 32 || b.jobs[i].kh * b.jobs[i].kw > PACK_TILE_MAX_TAPS))
-      return set_error(DBB_EUNSUPPORTED, "pack_weights: tiled mode needs channels % 32 == 0 and <= 9 taps");
-  if (b.njobs <= 0) return DBB_OK;
-  DBB_LAUNCH("pack_weights_batch", s, pack_weights_batch_kernel<<<dim3(64, (unsigned)b.njobs), 256, 0, s>>>(b));
+int pack_weights_batch(const PackBatch& b_in, cudaStream_t s) {
+  if (b_in.njobs <= 0) return DBB_OK;
+  PackBatch b = b_in;
+  b.tile_start[0] = 0;
+  for (int i = 0; i < b.njobs; ++i) {
+    const PackJob& j = b.jobs[i];
+    int units = 1;
+    if (j.mode == 5) {
+      if (j.co_n % 32 || j.ci_n % 32 || j.kh * j.kw > PACK_TILE_MAX_TAPS)
+        return set_error(DBB_EUNSUPPORTED, "pack_weights: tiled mode needs channels % 32 == 0 and <= 9 taps");
+      units = (j.co_n / 32) * (j.ci_n / 32);
+    }
+    b.tile_start[i + 1] = b.tile_start[i] + units;
+  }
+  int grid = b.tile_start[b.njobs];
+  if (grid > DBB_NUM_SMS * 6) grid = DBB_NUM_SMS * 6;
+  DBB_LAUNCH("pack_weights_batch", s, pack_weights_batch_kernel<<<grid, 256, 0, s>>>(b));
   return DBB_OK;
 }
 
@@ -1160,7 +1176,7 @@ int igemm_launch(const IgemmPlan& p, cudaStream_t s) {
     switch (p.block_n) {
       case 64:
         // statistics in registers (64 accumulators/thread) -> 1 CTA/SM, so that CTA gets a deep ring
-        if (st) return igemm_launch_p2<64, 6, true>(p, s);                                                   // 144 KB
+        if (st) return igemm_launch_p2<64, 6, true>(p, s);                                                   // 144 KB (2 CTAs/SM at 96 registers + 3 stages measured slower)
         if (depth <= 2) return igemm_launch_p2<64, 2, false>(p, s);                                          // 48 KB -> 4 CTAs/SM
         return igemm_launch_p2<64, 4, false>(p, s);                                                          // 96 KB -> 2 CTAs/SM
       case 128:

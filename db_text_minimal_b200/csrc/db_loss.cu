@@ -527,9 +527,58 @@ text_score_hist_kernel(const float* __restrict__ p, int64_t p_img_stride, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// optimizer step (SURVEY f-2): Adam over the flat parameter / gradient buffers of the executor
+// replaces torch.optim.Adam(dbnet.parameters(), lr=0.005, amsgrad=False).step() (src/train.py:114-117,172): one launch over
+// 12.27 M elements (28 B/element) instead of one multi-tensor pass per chunk list.  The step counter lives on the device
+// so that the whole training step stays CUDA-graph capturable.
+//   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)   (+ L2 weight decay into g)
+// ---------------------------------------------------------------------------------------------
+__global__ void adam_tick_kernel(long long* step) { *step += 1; }
+
+__global__ void __launch_bounds__(256)
+adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n4,
+                 float lr, float b1, float b2, float eps, float wd, float grad_scale, const long long* __restrict__ step) {
+  const double t = (double)*step;
+  const float bc1 = (float)(1.0 - pow((double)b1, t));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
+  const float step_size = lr / bc1;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = ldg_stream(reinterpret_cast<const float4*>(g) + i);
+    float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    float* P = &pp.x; const float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gr = G[k] * grad_scale;
+      if (wd != 0.f) gr = fmaf(wd, P[k], gr);
+      M[k] = fmaf(1.f - b1, gr - M[k], M[k]);                 // lerp, as torch's fused kernel
+      V[k] = fmaf(b2, V[k], (1.f - b2) * gr * gr);
+      const float denom = sqrtf(V[k]) / bc2_sqrt + eps;
+      P[k] -= step_size * (M[k] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+}
+
 }  // namespace dbb
 
 using namespace dbb;
+
+// p, g, m, v: flat float32 device buffers of n elements (n % 4 == 0, 16-byte aligned); step: device int64, incremented first
+extern "C" int dbb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, float grad_scale, long long* step, void* stream) {
+  if (!p || !g || !m || !v || !step || n <= 0 || (n & 3)) return set_error(DBB_EINVAL, "adam_step: bad argument (n must be a multiple of 4)");
+  if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) return set_error(DBB_EALIGN, "adam_step: buffers need 16-byte alignment");
+  cudaStream_t s = (cudaStream_t)stream;
+  DBB_LAUNCH("adam_tick", s, adam_tick_kernel<<<1, 1, 0, s>>>(step));
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks > DBB_NUM_SMS * 8) blocks = DBB_NUM_SMS * 8;
+  DBB_LAUNCH("adam_flat", s, adam_flat_kernel<<<(int)blocks, 256, 0, s>>>(p, g, m, v, n / 4, lr, beta1, beta2, eps, weight_decay, grad_scale, step));
+  return DBB_OK;
+}
 
 // hist4 (device, 4 x uint64, row-major [gt][pred]) is ACCUMULATED into (zero it to start a new RunningScore)
 extern "C" int dbb_text_score_hist(const float* p, int64_t p_img_stride, const float* gt, const float* mask, int64_t n, int64_t h,

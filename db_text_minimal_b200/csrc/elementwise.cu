@@ -549,8 +549,13 @@ int bias_grad(const bf16* dz, int64_t P, int c, float* partials, float* dbias, c
 // ---------------------------------------------------------------------------------------------
 // MaxPool2d(kernel 3, stride 2, padding 1); argmax = first maximum in (kh, kw) scan order (ATen semantics)
 // ---------------------------------------------------------------------------------------------
+// bn_stats4 != nullptr: x is the RAW convolution output and the pooled operand is bf16(relu(x*scale + shift)) computed on the
+// fly -- the stem's BatchNorm-apply pass and its 210 MB activation tensor disappear (the backward re-derives the ReLU mask
+// from x, see bn_bwd_*_kernel<2>).  The values are rounded to bf16 before the comparison, so results are bit-identical
+// to pooling a materialised activation tensor.
 __global__ void __launch_bounds__(EW_THREADS) maxpool_fwd_kernel(const bf16* __restrict__ x, int n, int h, int w, int c, int oh, int ow,
-                                                                 bf16* __restrict__ y, uint8_t* __restrict__ argmax) {
+                                                                 bf16* __restrict__ y, uint8_t* __restrict__ argmax,
+                                                                 const float* __restrict__ bn_stats4) {
   const int groups = c / 8;
   const int64_t total = (int64_t)n * oh * ow * groups;
   for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
@@ -560,6 +565,8 @@ __global__ void __launch_bounds__(EW_THREADS) maxpool_fwd_kernel(const bf16* __r
     F8 best; uint8_t bi[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { best.v[j] = -INFINITY; bi[j] = 0; }
+    F8 bsc, bsh;
+    if (bn_stats4) { bsc = ldf8(bn_stats4 + g * 8); bsh = ldf8(bn_stats4 + c + g * 8); }
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int yy = 2 * y0 - 1 + kh;
@@ -568,7 +575,12 @@ __global__ void __launch_bounds__(EW_THREADS) maxpool_fwd_kernel(const bf16* __r
       for (int kw = 0; kw < 3; ++kw) {
         const int xx = 2 * x0 - 1 + kw;
         if (xx < 0 || xx >= w) continue;
-        const F8 v = ld8(x + (((int64_t)b * h + yy) * w + xx) * c + g * 8);
+        F8 v = ld8(x + (((int64_t)b * h + yy) * w + xx) * c + g * 8);
+        if (bn_stats4) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            v.v[j] = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(v.v[j], bsc.v[j], bsh.v[j]), 0.f)));
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) if (v.v[j] > best.v[j]) { best.v[j] = v.v[j]; bi[j] = (uint8_t)(kh * 3 + kw); }
       }
@@ -636,10 +648,10 @@ __global__ void __launch_bounds__(EW_THREADS) maxpool_bwd_kernel(const bf16* __r
 }
 static int fits32(int64_t total, const char* who) { return total < ((int64_t)1 << 32) ? 0 : set_error(DBB_EUNSUPPORTED, who); }
 
-int maxpool_fwd(const bf16* x, int n, int h, int w, int c, bf16* y, uint8_t* argmax, cudaStream_t s) {
+int maxpool_fwd(const bf16* x, int n, int h, int w, int c, bf16* y, uint8_t* argmax, cudaStream_t s, const float* bn_stats4) {
   const int oh = (h + 2 - 3) / 2 + 1, ow = (w + 2 - 3) / 2 + 1;
   if (fits32((int64_t)n * h * w * (c / 8), "maxpool: tensor too large for 32-bit indexing")) return DBB_EUNSUPPORTED;
-  DBB_LAUNCH("maxpool_fwd", s, maxpool_fwd_kernel<<<fit_grid(((int64_t)n * oh * ow * (c / 8) + EW_THREADS - 1) / EW_THREADS, DBB_RESIDENT(maxpool_fwd_kernel)), EW_THREADS, 0, s>>>(x, n, h, w, c, oh, ow, y, argmax));
+  DBB_LAUNCH("maxpool_fwd", s, maxpool_fwd_kernel<<<fit_grid(((int64_t)n * oh * ow * (c / 8) + EW_THREADS - 1) / EW_THREADS, DBB_RESIDENT(maxpool_fwd_kernel)), EW_THREADS, 0, s>>>(x, n, h, w, c, oh, ow, y, argmax, bn_stats4));
   return DBB_OK;
 }
 int maxpool_bwd(const bf16* dy, const uint8_t* argmax, int n, int h, int w, int c, bf16* dx, cudaStream_t s) {

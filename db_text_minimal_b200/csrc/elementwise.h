@@ -48,7 +48,8 @@ int bn_bwd_apply(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* m
 int bias_grad(const bf16* dz, int64_t P, int c, float* partials, float* dbias, cudaStream_t s);
 
 // ---- MaxPool2d(3, 2, 1)  (src/modules/resnet.py:175,235)
-int maxpool_fwd(const bf16* x, int n, int h, int w, int c, bf16* y, uint8_t* argmax, cudaStream_t s);
+// bn_stats4 (optional): x is a raw conv output, pool bf16(relu(x*scale + shift)) computed on the fly (fused BatchNorm apply)
+int maxpool_fwd(const bf16* x, int n, int h, int w, int c, bf16* y, uint8_t* argmax, cudaStream_t s, const float* bn_stats4 = nullptr);
 int maxpool_bwd(const bf16* dy, const uint8_t* argmax, int n, int h, int w, int c, bf16* dx, cudaStream_t s);
 
 // ---- FPN glue: F.interpolate(mode='nearest') (+ add / concat)  (src/modules/segmentation_body.py:79-87)

@@ -469,8 +469,9 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
     RC(conv1_fprop(N, net->h, net->w, c.p(net->s2d), c.p(net->wp_conv1), c.p(net->z0), c.s, fused));
     if (!fused) RC(bn_prepare(c, c.p(net->z0), P0, 64, 1, &ix, c.p<float>(net->stats0)));
   }
-  RC(bn_apply(c.p(net->z0), P0, 64, c.p<float>(net->stats0), nullptr, 1, c.p(net->a0), 64, 0, c.s));
-  RC(maxpool_fwd(c.p(net->a0), N, net->h1, net->w1, 64, c.p(net->x1), net->training ? c.p<uint8_t>(net->argmax) : nullptr, c.s));
+  // BN + ReLU are applied inside the pooling kernel: a0 is never written (debug reads materialise it on demand)
+  RC(maxpool_fwd(c.p(net->z0), N, net->h1, net->w1, 64, c.p(net->x1), net->training ? c.p<uint8_t>(net->argmax) : nullptr, c.s,
+                 c.p<float>(net->stats0)));
   // ---- residual stages
   const bf16* cur = c.p(net->x1);
   for (int i = 0; i < 8; ++i) { RC(block_fwd(c, net->blocks[i], cur)); cur = c.p(net->blocks[i].out); }
@@ -718,5 +719,11 @@ extern "C" int dbb_net_debug_shape(DbbNet* net, const char* name, int64_t* shape
 extern "C" int dbb_net_debug_read(DbbNet* net, const char* name, const void* workspace, float* out_nchw, void* stream) {
   Buf b; int h, w, ch;
   if (!net || !name || !find_tensor(net, name, &b, &h, &w, &ch)) return set_error(DBB_EINVAL, "net_debug: unknown tensor");
+  if (std::string(name) == "a0") {   // the stem activation is fused away (maxpool_fwd applies BN + ReLU): materialise it for the reader
+    char* base = (char*)const_cast<void*>(workspace);
+    RC(bn_apply(reinterpret_cast<const bf16*>(base + net->z0.off), (int64_t)net->n * net->h1 * net->w1, 64,
+                reinterpret_cast<const float*>(base + net->stats0.off), nullptr, 1, reinterpret_cast<bf16*>(base + b.off), 64, 0,
+                (cudaStream_t)stream));
+  }
   return nhwc_bf16_to_nchw_f32(reinterpret_cast<const bf16*>((const char*)workspace + b.off), out_nchw, net->n, ch, (int64_t)h * w, (cudaStream_t)stream);
 }

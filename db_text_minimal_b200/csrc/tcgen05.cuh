@@ -59,7 +59,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // slots from the single MMA-issuing thread that shares their scheduler
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
   for (uint32_t i = 0; !mbar_try_wait(bar, parity); ++i) {
-    __nanosleep(128);
+    if (i >= 4) __nanosleep(64);        // short waits (back-to-back small tiles) are not delayed
     if (i > (1u << 23)) {
       printf("dbb: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
       __trap();

@@ -80,6 +80,7 @@ class _DBNetFn(torch.autograd.Function):
         dev = out.device
         dout = dout.float().contiguous()
         flat, views = model._grad_views(dev)
+        model._last_flat_grad = flat          # optim.FlatAdam steps on this buffer directly
         pa = _ptr_array([p.data_ptr() for p in params])
         ga = _ptr_array([v.data_ptr() for v in views])
         hook = model._segment_hook
@@ -146,6 +147,11 @@ class DBTextModel(nn.Module):
             off += (named_p[self._pnames[i]].numel() + 3) // 4 * 4      # keep 16-byte alignment
             bounds[seg_of(self._pnames[i]) + 1] = off
         self._flat_numel = off
+        used = torch.zeros(off, dtype=torch.bool)
+        for i in order:
+            used[self._flat_offsets[i]:self._flat_offsets[i] + named_p[self._pnames[i]].numel()] = True
+        self._flat_pad = torch.nonzero(~used).flatten()
+        self._flat_pad_dev = {}
         self._segment_slices = [(bounds[s], bounds[s + 1]) for s in range(3)]
 
     def _param_list(self):
@@ -158,6 +164,11 @@ class DBTextModel(nn.Module):
 
     def _grad_views(self, device):
         flat = torch.empty(self._flat_numel, dtype=torch.float32, device=device)
+        if self._flat_pad.numel():            # alignment gaps (behind the two 1-element ConvTranspose biases): keep them finite
+            key = str(device)
+            if key not in self._flat_pad_dev:
+                self._flat_pad_dev[key] = self._flat_pad.to(device)
+            flat.index_fill_(0, self._flat_pad_dev[key], 0.0)
         plist = self._param_list()
         views = []
         for i, p in enumerate(plist):

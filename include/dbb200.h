@@ -78,6 +78,12 @@ int dbb_dbloss_bwd(const float* preds, const float* gts, int64_t n, int c, int64
                    float alpha, float beta, int reduction, float eps, const float* grad_out5,
                    DbbLossState* state, float* dpreds, void* stream);
 
+/* Optimizer step (replaces torch.optim.Adam(...).step() of src/train.py:114-117,172; amsgrad off): Adam over flat float32
+ * buffers of n elements (n % 4 == 0).  *step (device int64) is incremented, then used for the bias corrections, so the
+ * call is CUDA-graph capturable.  grad_scale multiplies g first (1/world for a SUM all-reduce, 1 otherwise). */
+int dbb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, float grad_scale, long long* step, void* stream);
+
 /* Per-step pixel metric (replaces src/text_metrics.py:63-82 cal_text_score + :14-23 _fast_hist): accumulates the 2x2
  * confusion matrix hist4[gt*2 + pred] of pred = (P*mask > thresh) vs gt = int(gt*mask) into a device uint64[4].
  * p may be a channel view of the (N,C,H,W) prediction: p_img_stride = C*H*W. */
