@@ -125,6 +125,10 @@ struct DbbNet {
   Buf wg_scratch;         // split-K partials of the weight-gradient GEMMs
   Buf bn_acc;             // fp64 accumulators + ticket of the fused reduce+finalize kernels (kept zero between uses)
   int out_c;
+  // side stream of the weight-gradient chain (backward): wgrad GEMMs are independent of the dgrad / BatchNorm chain of the
+  // same layer, so they run concurrently with the (memory-bound) BatchNorm-backward kernels of the following layers
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // bump allocator
   size_t cur = 0;
   Buf alloc(size_t bytes) {
@@ -277,7 +281,13 @@ extern "C" DbbNet* dbb_net_create(int64_t n, int64_t h, int64_t w, int training)
   return net;
 }
 
-extern "C" void dbb_net_destroy(DbbNet* net) { delete net; }
+extern "C" void dbb_net_destroy(DbbNet* net) {
+  if (!net) return;
+  if (net->ev_fork) cudaEventDestroy(net->ev_fork);
+  if (net->ev_join) cudaEventDestroy(net->ev_join);
+  if (net->s2) cudaStreamDestroy(net->s2);
+  delete net;
+}
 extern "C" size_t dbb_net_workspace_bytes(const DbbNet* net) { return net ? net->ws_bytes : 0; }
 extern "C" int64_t dbb_net_out_channels(const DbbNet* net) { return net ? net->out_c : 0; }
 extern "C" uint64_t dbb_net_flops_fwd(const DbbNet* net) { return net ? net->flops_fwd : 0; }
@@ -300,6 +310,7 @@ struct Ctx {
   float* const* buffers;
   float* const* grads;
   cudaStream_t s;
+  cudaStream_t sw;        // weight-gradient stream (== s when the side stream is disabled)
   template <typename T = bf16> T* p(const Buf& b) const { return reinterpret_cast<T*>(base + b.off); }
   const float* par(int i) const { return i >= 0 ? params[i] : nullptr; }
   float* buf(int i) const { return (i >= 0 && buffers) ? buffers[i] : nullptr; }
@@ -311,6 +322,20 @@ struct Ctx {
 };
 
 #define RC(call) do { int rc__ = (call); if (rc__) return rc__; } while (0)
+
+// fork: work enqueued on c.sw from here on sees everything enqueued on c.s so far; join: the reverse
+int fork_w(const Ctx& c) {
+  if (c.sw == c.s) return 0;
+  DBB_CUDA(cudaEventRecord(c.net->ev_fork, c.s));
+  DBB_CUDA(cudaStreamWaitEvent(c.sw, c.net->ev_fork, 0));
+  return 0;
+}
+int join_w(const Ctx& c) {
+  if (c.sw == c.s) return 0;
+  DBB_CUDA(cudaEventRecord(c.net->ev_join, c.sw));
+  DBB_CUDA(cudaStreamWaitEvent(c.s, c.net->ev_join, 0));
+  return 0;
+}
 
 // BatchNorm statistics of a raw conv output (training: one fused reduce+finalize launch) or running statistics (eval)
 // -> stats4.  nseg = 2 for the 128-channel head tensors that carry two BatchNorm layers side by side.
@@ -403,10 +428,11 @@ int convbn_bwd(const Ctx& c, ConvBN& L, const bf16* dout, int dout_ctotal, int d
   fin.seg[0] = BnBwdFinSeg{c.par(L.gamma), c.grad(L.gamma), c.grad(L.beta), 0, ch};
   RC(bn_bwd_reduce_finalize(dout, dout_ctotal, dout_coff, mask, mask_ctotal, mask_coff, c.p(L.z), Pn, ch, c.p<float>(L.stats), fin, c.acc(), c.ticket(), c.s, mask_self));
   RC(bn_bwd_apply(dout, dout_ctotal, dout_coff, mask, mask_ctotal, mask_coff, c.p(L.z), Pn, ch, c.p<float>(L.stats), c.p<float>(L.coef), c.p(L.dz), dsum, c.s, mask_self));
-  RC(conv_wgrad(L.g, x, x_ctotal, x_coff, c.p(L.dz), ch, 0, c.grad(L.w), c.wgs(), WGRAD_SCRATCH_BYTES, c.s));
+  RC(fork_w(c));          // dz is complete: the weight gradient goes to the side stream, the data gradient stays here
+  RC(conv_wgrad(L.g, x, x_ctotal, x_coff, c.p(L.dz), ch, 0, c.grad(L.w), c.wgs(), WGRAD_SCRATCH_BYTES, c.sw));
   // the bias of a convolution that feeds a training-mode BatchNorm has an identically zero gradient
   // (sum_px dz = 0); the reference's value is float rounding noise.  Written as exact zeros.
-  if (L.b >= 0) DBB_CUDA(cudaMemsetAsync(c.grad(L.b), 0, sizeof(float) * ch, c.s));
+  if (L.b >= 0) DBB_CUDA(cudaMemsetAsync(c.grad(L.b), 0, sizeof(float) * ch, c.sw));
   if (dx) {
     RC(conv_dgrad(L.g, c.p(L.dz), c.p(L.wpt), dx, c.s, dx_accumulate));
   }
@@ -455,7 +481,7 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
   if (!net || !x || !params || !out || !workspace) return set_error(DBB_EINVAL, "net_forward: null pointer");
   if (workspace_bytes < net->ws_bytes) return set_error(DBB_EWORKSPACE, "net_forward: workspace too small");
   if (!aligned16(x) || !aligned16(out) || (reinterpret_cast<uintptr_t>(workspace) & 1023)) return set_error(DBB_EALIGN, "net_forward: x/out need 16 B, workspace 1024 B alignment");
-  Ctx c{net, (char*)workspace, params, buffers, nullptr, (cudaStream_t)stream};
+  Ctx c{net, (char*)workspace, params, buffers, nullptr, (cudaStream_t)stream, (cudaStream_t)stream};
   const int N = net->n;
   DBB_CUDA(cudaMemsetAsync(c.p<uint8_t>(net->bn_acc), 0, BN_ACC_BYTES, c.s));
   // ---- stem: conv 7x7/2 (space-to-depth form) -> BN -> ReLU -> maxpool
@@ -548,7 +574,22 @@ extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout
   if (!net->training) return set_error(DBB_EINVAL, "net_backward: network was planned in eval mode");
   if (workspace_bytes < net->ws_bytes) return set_error(DBB_EWORKSPACE, "net_backward: workspace too small");
   if (segment < -1 || segment > 2) return set_error(DBB_EINVAL, "net_backward: segment must be -1..2");
-  Ctx c{net, (char*)workspace, params, nullptr, grads, (cudaStream_t)stream};
+  static const bool side = getenv("DBB_NO_WGRAD_STREAM") == nullptr;     // A/B switch
+  if (side && !net->s2) {      // first backward on this plan (not while the caller's stream is being captured): side stream + events
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing((cudaStream_t)stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+      if (cudaStreamCreateWithFlags(&net->s2, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        if (net->s2) { cudaStreamDestroy(net->s2); net->s2 = nullptr; }
+      }
+    } else {
+      cudaGetLastError();
+    }
+  }
+  Ctx c{net, (char*)workspace, params, nullptr, grads, (cudaStream_t)stream, (side && net->s2 && !prof_enabled()) ? net->s2 : (cudaStream_t)stream};
+  // (per-kernel profiling serialises the two chains: CUDA-event times of overlapping kernels would be inflated)
   const int N = net->n;
   const int hf = net->hh[0], wf = net->ww[0];
   const int planes[4] = {64, 128, 256, 512};
@@ -576,12 +617,13 @@ extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout
     RC(head_tail_bwd_apply(c.p(net->zt), N, 2 * hf, 2 * wf, c.p<float>(net->stats_t), c.p<float>(net->coef_t), c.par(P(hb + ".6.weight")),
                            c.par(P(ht + ".6.weight")), hout, dhout, STEP_K, c.p(net->d_zt), c.s));
     // ---- ConvTranspose2d(64,64,2,2) x 2
+    RC(fork_w(c));
     for (int br = 0; br < 2; ++br) {
       const std::string pre = br ? ht : hb;
       // biases in front of a training-mode BatchNorm: identically zero gradient (see convbn_bwd)
-      DBB_CUDA(cudaMemsetAsync(c.grad(P(pre + ".3.bias")), 0, 64 * sizeof(float), c.s));
+      DBB_CUDA(cudaMemsetAsync(c.grad(P(pre + ".3.bias")), 0, 64 * sizeof(float), c.sw));
       RC(convt_dgrad(net->tconv_g, c.p(net->d_zt), 128, br * 64, c.p(net->wpt_t[br]), c.p(net->d_ah), 128, br * 64, c.s));
-      RC(convt_wgrad(net->tconv_g, c.p(net->ah), 128, br * 64, c.p(net->d_zt), 128, br * 64, c.grad(P(pre + ".3.weight")), c.wgs(), WGRAD_SCRATCH_BYTES, c.s));
+      RC(convt_wgrad(net->tconv_g, c.p(net->ah), 128, br * 64, c.p(net->d_zt), 128, br * 64, c.grad(P(pre + ".3.weight")), c.wgs(), WGRAD_SCRATCH_BYTES, c.sw));
     }
     // ---- BN(2 x 64) + ReLU + the fused 256->128 3x3 conv of the two branches
     {
@@ -595,11 +637,12 @@ extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout
     }
     RC(bn_bwd_apply(c.p(net->d_ah), 128, 0, c.p(net->ah), 128, 0, c.p(net->zh), Ph, 128, c.p<float>(net->stats_h), c.p<float>(net->coef_h),
                     c.p(net->d_zh), nullptr, c.s, self_mask()));
-    RC(conv_wgrad(net->hconv_g, c.p(net->af), 256, 0, c.p(net->d_zh), 128, 0, c.p<float>(net->dw_h), c.wgs(), WGRAD_SCRATCH_BYTES, c.s));
+    RC(fork_w(c));
+    RC(conv_wgrad(net->hconv_g, c.p(net->af), 256, 0, c.p(net->d_zh), 128, 0, c.p<float>(net->dw_h), c.wgs(), WGRAD_SCRATCH_BYTES, c.sw));
     const size_t half = (size_t)64 * 256 * 9;
-    DBB_CUDA(cudaMemcpyAsync(c.grad(P(hb + ".0.weight")), c.p<float>(net->dw_h), half * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
-    DBB_CUDA(cudaMemcpyAsync(c.grad(P(ht + ".0.weight")), c.p<float>(net->dw_h) + half, half * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
-    DBB_CUDA(cudaMemsetAsync(c.grad(P(hb + ".0.bias")), 0, 64 * sizeof(float), c.s));
+    DBB_CUDA(cudaMemcpyAsync(c.grad(P(hb + ".0.weight")), c.p<float>(net->dw_h), half * sizeof(float), cudaMemcpyDeviceToDevice, c.sw));
+    DBB_CUDA(cudaMemcpyAsync(c.grad(P(ht + ".0.weight")), c.p<float>(net->dw_h) + half, half * sizeof(float), cudaMemcpyDeviceToDevice, c.sw));
+    DBB_CUDA(cudaMemsetAsync(c.grad(P(hb + ".0.bias")), 0, 64 * sizeof(float), c.sw));
     RC(conv_dgrad(net->hconv_g, c.p(net->d_zh), c.p(net->wpt_h), c.p(net->d_af), c.s, 0));
     // ---- FPN output conv
     RC(convbn_bwd(c, net->fconv, c.p(net->d_af), 256, 0, c.p(net->af), 256, 0, c.p(net->cat), 256, 0, c.p(net->d_cat), 0, nullptr, 1));
@@ -646,9 +689,11 @@ extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout
     }
     RC(bn_bwd_apply(c.p(net->d_a0), 64, 0, c.p(net->a0), 64, 0, c.p(net->z0), P0, 64, c.p<float>(net->stats0), c.p<float>(net->coef0),
                     c.p(net->d_z0), nullptr, c.s, self_mask()));
-    RC(conv1_wgrad(N, net->h, net->w, c.p(net->s2d), c.p(net->d_z0), c.p<float>(net->dw_s2d), c.wgs(), WGRAD_SCRATCH_BYTES, c.s));
-    RC(conv1_wgrad_unpack(c.p<float>(net->dw_s2d), c.grad(P("backbone.conv1.weight")), c.s));
+    RC(fork_w(c));
+    RC(conv1_wgrad(N, net->h, net->w, c.p(net->s2d), c.p(net->d_z0), c.p<float>(net->dw_s2d), c.wgs(), WGRAD_SCRATCH_BYTES, c.sw));
+    RC(conv1_wgrad_unpack(c.p<float>(net->dw_s2d), c.grad(P("backbone.conv1.weight")), c.sw));
   }
+  RC(join_w(c));          // every gradient of this call is complete on the caller's stream
   return DBB_OK;
 }
 
