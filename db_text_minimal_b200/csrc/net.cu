@@ -323,6 +323,28 @@ struct Ctx {
 
 #define RC(call) do { int rc__ = (call); if (rc__) return rc__; } while (0)
 
+// The side stream of a plan (created on first use, never while the caller's stream is being captured); the caller's own
+// stream when it is disabled (DBB_NO_WGRAD_STREAM) or while per-kernel profiling is on (CUDA-event times of overlapping
+// kernels would be inflated).
+cudaStream_t side_stream(DbbNet* net, cudaStream_t stream) {
+  static const bool side = getenv("DBB_NO_WGRAD_STREAM") == nullptr;     // A/B switch
+  if (!side) return stream;
+  if (!net->s2) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+      if (cudaStreamCreateWithFlags(&net->s2, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        if (net->s2) { cudaStreamDestroy(net->s2); net->s2 = nullptr; }
+      }
+    } else {
+      cudaGetLastError();
+    }
+  }
+  return (net->s2 && !prof_enabled()) ? net->s2 : stream;
+}
+
 // fork: work enqueued on c.sw from here on sees everything enqueued on c.s so far; join: the reverse
 int fork_w(const Ctx& c) {
   if (c.sw == c.s) return 0;
@@ -374,11 +396,14 @@ int bn_prepare(const Ctx& c, const bf16* z, int64_t Pn, int ch, int gamma, int b
 
 // every weight tensor -> its bf16 GEMM operand(s), in one or two launches at the start of the forward pass
 // (fprop layout always; the transposed dgrad layout too in training mode, so backward launches no packing at all)
-int pack_all(const Ctx& c) {
+// stage 0: the stem weights, on the caller's stream; stage 1: everything else, on the side stream (it runs next to
+// image_to_s2d / conv1 / max-pool and is joined before layer1)
+int pack_all(const Ctx& c, int stage) {
   DbbNet* net = c.net;
   PackBatch b;
   b.njobs = 0;
-  auto flush = [&]() -> int { int rc = pack_weights_batch(b, c.s); b.njobs = 0; return rc; };
+  cudaStream_t ps = stage == 0 ? c.s : c.sw;
+  auto flush = [&]() -> int { int rc = pack_weights_batch(b, ps); b.njobs = 0; return rc; };
   auto add = [&](int mode, const float* w, bf16* out, int co, int ci, int ks, int co_total, int co_off, bf16* out2 = nullptr) -> int {
     if (b.njobs == PACK_BATCH) RC(flush());
     b.jobs[b.njobs++] = PackJob{w, out, mode, co, ci, ks, ks, co_total > 0 ? co_total : co, co_off, out2};
@@ -387,7 +412,10 @@ int pack_all(const Ctx& c) {
   auto unit = [&](ConvBN& L) -> int {     // one tiled job writes the fprop layout and (training) the transposed dgrad layout
     return add(5, c.par(L.w), c.p(L.wp), L.g.cout, L.g.cin, L.g.ks, 0, 0, (net->training && L.wpt.bytes) ? c.p(L.wpt) : nullptr);
   };
-  RC(add(4, c.par(P("backbone.conv1.weight")), c.p(net->wp_conv1), 64, 3, 7, 0, 0));
+  if (stage == 0) {
+    RC(add(4, c.par(P("backbone.conv1.weight")), c.p(net->wp_conv1), 64, 3, 7, 0, 0));
+    return flush();
+  }
   for (int i = 0; i < 8; ++i) {
     RC(unit(net->blocks[i].c1)); RC(unit(net->blocks[i].c2));
     if (net->blocks[i].has_ds) RC(unit(net->blocks[i].ds));
@@ -486,12 +514,14 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
   if (!net || !x || !params || !out || !workspace) return set_error(DBB_EINVAL, "net_forward: null pointer");
   if (workspace_bytes < net->ws_bytes) return set_error(DBB_EWORKSPACE, "net_forward: workspace too small");
   if (!aligned16(x) || !aligned16(out) || (reinterpret_cast<uintptr_t>(workspace) & 1023)) return set_error(DBB_EALIGN, "net_forward: x/out need 16 B, workspace 1024 B alignment");
-  Ctx c{net, (char*)workspace, params, buffers, nullptr, (cudaStream_t)stream, (cudaStream_t)stream};
+  Ctx c{net, (char*)workspace, params, buffers, nullptr, (cudaStream_t)stream, side_stream(net, (cudaStream_t)stream)};
   const int N = net->n;
   DBB_CUDA(cudaMemsetAsync(c.p<uint8_t>(net->bn_acc), 0, BN_ACC_BYTES, c.s));
   // ---- stem: conv 7x7/2 (space-to-depth form) -> BN -> ReLU -> maxpool
+  RC(pack_all(c, 0));
+  RC(fork_w(c));
+  RC(pack_all(c, 1));
   RC(image_to_s2d(x, N, net->h, net->w, c.p(net->s2d), c.s));
-  RC(pack_all(c));
   const int64_t P0 = (int64_t)N * net->h1 * net->w1;
   {
     const BnIdx ix{P("backbone.bn1.weight"), P("backbone.bn1.bias"), B("backbone.bn1.running_mean"), B("backbone.bn1.running_var")};
@@ -503,6 +533,7 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
   // BN + ReLU are applied inside the pooling kernel: a0 is never written (debug reads materialise it on demand)
   RC(maxpool_fwd(c.p(net->z0), N, net->h1, net->w1, 64, c.p(net->x1), net->training ? c.p<uint8_t>(net->argmax) : nullptr, c.s,
                  c.p<float>(net->stats0)));
+  RC(join_w(c));          // packed weights of every later layer are ready
   // ---- residual stages
   const bf16* cur = c.p(net->x1);
   for (int i = 0; i < 8; ++i) { RC(block_fwd(c, net->blocks[i], cur)); cur = c.p(net->blocks[i].out); }
@@ -579,21 +610,7 @@ extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout
   if (!net->training) return set_error(DBB_EINVAL, "net_backward: network was planned in eval mode");
   if (workspace_bytes < net->ws_bytes) return set_error(DBB_EWORKSPACE, "net_backward: workspace too small");
   if (segment < -1 || segment > 2) return set_error(DBB_EINVAL, "net_backward: segment must be -1..2");
-  static const bool side = getenv("DBB_NO_WGRAD_STREAM") == nullptr;     // A/B switch
-  if (side && !net->s2) {      // first backward on this plan (not while the caller's stream is being captured): side stream + events
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing((cudaStream_t)stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
-      if (cudaStreamCreateWithFlags(&net->s2, cudaStreamNonBlocking) != cudaSuccess ||
-          cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-          cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming) != cudaSuccess) {
-        cudaGetLastError();
-        if (net->s2) { cudaStreamDestroy(net->s2); net->s2 = nullptr; }
-      }
-    } else {
-      cudaGetLastError();
-    }
-  }
-  Ctx c{net, (char*)workspace, params, nullptr, grads, (cudaStream_t)stream, (side && net->s2 && !prof_enabled()) ? net->s2 : (cudaStream_t)stream};
+  Ctx c{net, (char*)workspace, params, nullptr, grads, (cudaStream_t)stream, side_stream(net, (cudaStream_t)stream)};
   // (per-kernel profiling serialises the two chains: CUDA-event times of overlapping kernels would be inflated)
   const int N = net->n;
   const int hf = net->hh[0], wf = net->ww[0];
