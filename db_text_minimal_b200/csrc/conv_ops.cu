@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "conv.h"
 #include "conv_ops.h"
+#include "elementwise.h"
 #include <stdlib.h>
 
 namespace dbb {
@@ -359,4 +360,42 @@ extern "C" int dbb_conv2d_wgrad(int kind, const void* x, const void* dy, float* 
     return convt_wgrad(g, (const bf16*)x, cin, 0, (const bf16*)dy, cout, 0, dw, (float*)workspace, workspace_bytes, (cudaStream_t)stream);
   }
   return set_error(DBB_EINVAL, "conv2d_wgrad: kind must be 0 (Conv2d) or 2 (ConvTranspose2d)");
+}
+
+// ---- stem: Conv2d(3, 64, 7, stride 2, pad 3, bias=False) of src/modules/resnet.py:171 on the NCHW float32 image.
+// workspace = space-to-depth staging buffer + packed weights (+ weight-gradient scratch for the backward entry)
+static size_t conv1_s2d_bytes(int64_t n, int64_t h, int64_t w) {
+  const int64_t hs = (h + 1) / 2, ws = (w + 1) / 2;
+  return ((size_t)n * (hs + 3) * (ws + 3) * 16 * sizeof(bf16) + 1023) / 1024 * 1024;
+}
+extern "C" size_t dbb_conv1_workspace(int64_t n, int64_t h, int64_t w, int backward) {
+  return conv1_s2d_bytes(n, h, w) + (backward ? (size_t)(64 * 64 * 4 * sizeof(float) + 1024) + WGRAD_SCRATCH_BYTES : (size_t)(64 * 256 * sizeof(bf16) + 1024));
+}
+extern "C" int dbb_conv1_fwd(const float* img, const float* weight, void* y, int64_t n, int64_t h, int64_t w, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  if (!img || !weight || !y || !workspace) return set_error(DBB_EINVAL, "conv1_fwd: null pointer");
+  if (n <= 0 || h < 8 || w < 8) return set_error(DBB_EINVAL, "conv1_fwd: bad shape");
+  if (workspace_bytes < dbb_conv1_workspace(n, h, w, 0)) return set_error(DBB_EWORKSPACE, "conv1_fwd: workspace too small");
+  if (!aligned16(img) || !aligned16(y) || (reinterpret_cast<uintptr_t>(workspace) & 1023)) return set_error(DBB_EALIGN, "conv1_fwd: alignment (workspace 1024 B)");
+  cudaStream_t s = (cudaStream_t)stream;
+  bf16* s2d = (bf16*)workspace;
+  bf16* wp = (bf16*)((char*)workspace + conv1_s2d_bytes(n, h, w));
+  int rc;
+  if ((rc = image_to_s2d(img, (int)n, (int)h, (int)w, s2d, s))) return rc;
+  if ((rc = pack_weights(4, weight, wp, 64, 3, 7, 7, s))) return rc;
+  return conv1_fprop((int)n, (int)h, (int)w, s2d, wp, (bf16*)y, s);
+}
+extern "C" int dbb_conv1_wgrad(const float* img, const void* dy, float* dw, int64_t n, int64_t h, int64_t w, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  if (!img || !dy || !dw || !workspace) return set_error(DBB_EINVAL, "conv1_wgrad: null pointer");
+  if (workspace_bytes < dbb_conv1_workspace(n, h, w, 1)) return set_error(DBB_EWORKSPACE, "conv1_wgrad: workspace too small");
+  if (!aligned16(img) || !aligned16(dy) || (reinterpret_cast<uintptr_t>(workspace) & 1023)) return set_error(DBB_EALIGN, "conv1_wgrad: alignment (workspace 1024 B)");
+  cudaStream_t s = (cudaStream_t)stream;
+  bf16* s2d = (bf16*)workspace;
+  float* dw_s2d = (float*)((char*)workspace + conv1_s2d_bytes(n, h, w));
+  float* scratch = (float*)((char*)dw_s2d + 64 * 64 * 4 * sizeof(float) + 1024);
+  int rc;
+  if ((rc = image_to_s2d(img, (int)n, (int)h, (int)w, s2d, s))) return rc;
+  if ((rc = conv1_wgrad((int)n, (int)h, (int)w, s2d, (const bf16*)dy, dw_s2d, scratch, WGRAD_SCRATCH_BYTES, s))) return rc;
+  return conv1_wgrad_unpack(dw_s2d, dw, s);
 }

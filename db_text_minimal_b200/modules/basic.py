@@ -3,8 +3,9 @@ from torch import nn
 
 
 class ConvBnRelu(nn.Module):
-    """Holds ``conv`` and ``bn`` exactly like the reference so state_dict keys match.  The arithmetic of the
-    DB network runs in the fused executor (csrc/net.cu); calling this block on its own is not part of the hot path."""
+    """Holds ``conv`` and ``bn`` exactly like the reference so state_dict keys match.  Inside DBTextModel the arithmetic
+    runs in the fused executor (csrc/net.cu); called on its own the block runs conv -> BatchNorm -> ReLU through the
+    single-operator C ABI (``_autograd``), NCHW float32 in and out like the reference (src/modules/basic.py:31-36)."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
                  padding_mode='zeros', inplace=True):
@@ -15,6 +16,5 @@ class ConvBnRelu(nn.Module):
         self.relu = nn.ReLU(inplace=inplace)
 
     def forward(self, x):
-        from .._lib import DbbError
-        raise DbbError("ConvBnRelu is executed inside the fused DBTextModel graph (csrc/net.cu); "
-                       "there is no stand-alone eager path")
+        from .. import _autograd as A
+        return A.ToNCHW.apply(A.conv_bn(A.ToNHWC.apply(x), self.conv, self.bn, relu=True))

@@ -26,6 +26,17 @@ class BasicBlock(nn.Module):
         self.downsample = downsample
         self.stride = stride
 
+    def _forward_nhwc(self, x):
+        """src/modules/resnet.py:70-91 on NHWC bf16 tensors."""
+        from .. import _autograd as A
+        a1 = A.conv_bn(x, self.conv1, self.bn1, relu=True)
+        res = x if self.downsample is None else A.conv_bn(x, self.downsample[0], self.downsample[1], relu=False)
+        return A.conv_bn(a1, self.conv2, self.bn2, relu=True, residual=res)
+
+    def forward(self, x):
+        from .. import _autograd as A
+        return A.ToNCHW.apply(self._forward_nhwc(A.ToNHWC.apply(x)))
+
 
 class ResNet(nn.Module):
     def __init__(self, block, layers, num_classes=1000, dcn=None):
@@ -62,8 +73,17 @@ class ResNet(nn.Module):
         return nn.Sequential(*layers)
 
     def forward(self, x):
-        from .._lib import DbbError
-        raise DbbError("the backbone runs inside the fused DBTextModel graph (csrc/net.cu)")
+        """src/modules/resnet.py:231-242: returns (c2, c3, c4, c5), NCHW float32.  Stand-alone path (single-operator
+        C ABI); DBTextModel runs the same layers inside the fused executor."""
+        from .. import _autograd as A
+        a = A.batch_norm(A.Stem.apply(x, self.conv1.weight), self.bn1, relu=True)
+        a = A.MaxPool.apply(a)
+        feats = []
+        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+            for blk in layer:
+                a = blk._forward_nhwc(a)
+            feats.append(A.ToNCHW.apply(a))
+        return tuple(feats)
 
 
 def resnet18(pretrained=True, **kwargs):

@@ -21,5 +21,14 @@ class FPN(nn.Module):
         self.out_channels = self.conv_out
 
     def forward(self, x):
-        from .._lib import DbbError
-        raise DbbError("the FPN runs inside the fused DBTextModel graph (csrc/net.cu)")
+        """src/modules/segmentation_body.py:64-77: x = (c2, c3, c4, c5) NCHW float32 -> fused map (N, 256, H/4, W/4).
+        Stand-alone path (single-operator C ABI); DBTextModel runs the same layers inside the fused executor."""
+        from .. import _autograd as A
+        c2, c3, c4, c5 = (A.ToNHWC.apply(t) for t in x)
+        cbr = lambda m, t: A.conv_bn(t, m.conv, m.bn, relu=True)
+        p5 = cbr(self.reduce_conv_c5, c5)
+        p4 = cbr(self.smooth_p4, A.UpsampleAdd.apply(p5, cbr(self.reduce_conv_c4, c4)))
+        p3 = cbr(self.smooth_p3, A.UpsampleAdd.apply(p4, cbr(self.reduce_conv_c3, c3)))
+        p2 = cbr(self.smooth_p2, A.UpsampleAdd.apply(p3, cbr(self.reduce_conv_c2, c2)))
+        cat = A.UpsampleCat.apply(p2, p3, p4, p5)
+        return A.ToNCHW.apply(A.conv_bn(cat, self.conv[0], self.conv[1], relu=True))

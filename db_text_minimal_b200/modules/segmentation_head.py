@@ -60,4 +60,24 @@ class DBHead(nn.Module):
         return _StepFn.apply(x, y, self.k)
 
     def forward(self, x):
-        raise _lib.DbbError("the DB head runs inside the fused DBTextModel graph (csrc/net.cu)")
+        """src/modules/segmentation_head.py:35-45: x (N, 256, H/4, W/4) NCHW float32 -> cat(P, T, B) in training mode,
+        cat(P, T) in eval mode.  Stand-alone path (single-operator C ABI)."""
+        from .. import _autograd as A
+        a = A.ToNHWC.apply(x)
+        zs = []
+        for br in (self.binarize, self.thresh):
+            h = A.conv_bn(a, br[0], br[1], relu=True)
+            zs.append(A.ConvT.apply(h, br[3].weight, br[3].bias))
+        zt = torch.cat(zs, dim=-1).contiguous()             # (N, H/2, W/2, 128) = [binarize | thresh]
+        bnb, bnt = self.binarize[4], self.thresh[4]
+        gamma, beta = torch.cat([bnb.weight, bnt.weight]), torch.cat([bnb.bias, bnt.bias])
+        training = self.training
+        rm, rv = torch.cat([bnb.running_mean, bnt.running_mean]), torch.cat([bnb.running_var, bnt.running_var])
+        out = A.HeadTail.apply(zt, gamma, beta, rm, rv, training, self.binarize[6].weight, self.thresh[6].weight,
+                               self.binarize[6].bias, self.thresh[6].bias, float(self.k))
+        if training:        # the kernel updated the concatenated copies: write the running statistics back
+            with torch.no_grad():
+                bnb.running_mean.copy_(rm[:64]); bnt.running_mean.copy_(rm[64:])
+                bnb.running_var.copy_(rv[:64]); bnt.running_var.copy_(rv[64:])
+                bnb.num_batches_tracked += 1; bnt.num_batches_tracked += 1
+        return out

@@ -187,6 +187,16 @@ int dbb_conv2d_wgrad(int kind, const void* x_nhwc_bf16, const void* dy_nhwc_bf16
                      void* workspace, size_t workspace_bytes, void* stream);
 
 
+/* Stem convolution (replaces self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False), src/modules/resnet.py:171,
+ * 232): img is the NCHW float32 image, y the NHWC bf16 output (n, ceil(h/2), ceil(w/2), 64).  The workspace (1024-byte
+ * aligned) holds the space-to-depth staging buffer and the packed weights; backward != 0 sizes it for dbb_conv1_wgrad
+ * (dw: (64,3,7,7) float32; the image gets no gradient). */
+size_t dbb_conv1_workspace(int64_t n, int64_t h, int64_t w, int backward);
+int dbb_conv1_fwd(const float* img, const float* weight, void* y, int64_t n, int64_t h, int64_t w, void* workspace,
+                  size_t workspace_bytes, void* stream);
+int dbb_conv1_wgrad(const float* img, const void* dy, float* dw, int64_t n, int64_t h, int64_t w, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Memory-bound operators on NHWC bf16 activations (parity-tested in isolation; also the building blocks of the executor)
  * ------------------------------------------------------------------------------------------ */
