@@ -21,6 +21,20 @@ import torch
 from . import _lib
 
 
+_PYCLIPPER = []
+
+
+def _pyclipper():
+    """pyclipper if it is installed, else None -- looked up once (a failing import costs ~0.3 ms per call)."""
+    if not _PYCLIPPER:
+        try:
+            import pyclipper
+            _PYCLIPPER.append(pyclipper)
+        except ImportError:
+            _PYCLIPPER.append(None)
+    return _PYCLIPPER[0]
+
+
 def _clipper_round(v):
     # Clipper's Round(): (val < 0) ? (cInt)(val - 0.5) : (cInt)(val + 0.5)
     return int(v - 0.5) if v < 0 else int(v + 0.5)
@@ -100,6 +114,8 @@ class SegDetectorRepresenter():
         self.box_thresh = box_thresh
         self.max_candidates = max_candidates
         self.unclip_ratio = unclip_ratio
+        import os
+        self.host_threads = min(16, os.cpu_count() or 1)     # host back half (survivors only): one image per worker
 
     # ------------------------------------------------------------------ GPU front
     def binarize(self, pred):
@@ -183,17 +199,15 @@ class SegDetectorRepresenter():
     def unclip(self, box, unclip_ratio=1.5):
         """src/postprocess.py:150-156.  distance = area * ratio / perimeter (shapely Polygon.area / .length)."""
         pts = np.asarray(box, dtype=np.float64).reshape(-1, 2)
-        x, y = pts[:, 0], pts[:, 1]
-        area = 0.5 * abs(float(np.dot(x, np.roll(y, -1)) - np.dot(y, np.roll(x, -1))))
-        length = float(np.sqrt(((pts - np.roll(pts, -1, axis=0)) ** 2).sum(1)).sum())
+        nxt = np.concatenate([pts[1:], pts[:1]])            # (np.roll costs ~30 us per call on these 4-point arrays)
+        area = 0.5 * abs(float((pts[:, 0] * nxt[:, 1] - pts[:, 1] * nxt[:, 0]).sum()))
+        length = float(np.sqrt(((pts - nxt) ** 2).sum(1)).sum())
         distance = area * unclip_ratio / length
-        try:
-            import pyclipper
+        pyclipper = _pyclipper()
+        if pyclipper is not None:
             offset = pyclipper.PyclipperOffset()
             offset.AddPath(box, pyclipper.JT_ROUND, pyclipper.ET_CLOSEDPOLYGON)
             return np.array(offset.Execute(distance))
-        except ImportError:
-            pass
         import cv2
         hull = cv2.convexHull(pts.astype(np.float32)).reshape(-1, 2)
         if len(hull) != len(pts):
@@ -292,15 +306,21 @@ class SegDetectorRepresenter():
         """src/postprocess.py:19-49: returns (boxes_batch, scores_batch)."""
         bitmap, _, rec, nc = self.front(pred)
         bm = bitmap.cpu().numpy()
-        boxes_batch, scores_batch = [], []
-        for i in range(bm.shape[0]):
+        fn = self._polygons if is_output_polygon else self._boxes
+
+        def one(i):
             height, width = batch['shape'][i]
             k = int(min(nc[i], self.max_candidates))
-            fn = self._polygons if is_output_polygon else self._boxes
-            boxes, scores = fn(bm[i], rec[i, :k], width, height)
-            boxes_batch.append(boxes)
-            scores_batch.append(scores)
-        return boxes_batch, scores_batch
+            return fn(bm[i], rec[i, :k], width, height)
+
+        n = bm.shape[0]
+        if n > 1 and self.host_threads > 1:      # images are independent; the OpenCV calls release the GIL
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=min(self.host_threads, n)) as pool:
+                results = list(pool.map(one, range(n)))
+        else:
+            results = [one(i) for i in range(n)]
+        return [r[0] for r in results], [r[1] for r in results]
 
     def boxes_from_bitmap(self, pred, _bitmap, dest_width, dest_height):
         """src/postprocess.py:106-148 for one (H, W) map; ``_bitmap`` is recomputed on the device from ``pred``."""
