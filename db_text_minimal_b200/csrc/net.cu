@@ -710,10 +710,11 @@ extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout
       BnBwdFin fin;
       fin.nseg = 1; fin.coef3 = c.p<float>(net->coef0);
       fin.seg[0] = BnBwdFinSeg{c.par(g1), c.grad(g1), c.grad(b1), 0, 64};
-      RC(bn_bwd_reduce_finalize(c.p(net->d_a0), 64, 0, c.p(net->a0), 64, 0, c.p(net->z0), P0, 64, c.p<float>(net->stats0), fin, c.acc(), c.ticket(), c.s, self_mask()));
+      // (the stem activation a0 is fused away in the forward pass, so its ReLU mask always comes from z0)
+      RC(bn_bwd_reduce_finalize(c.p(net->d_a0), 64, 0, nullptr, 64, 0, c.p(net->z0), P0, 64, c.p<float>(net->stats0), fin, c.acc(), c.ticket(), c.s, 1));
     }
-    RC(bn_bwd_apply(c.p(net->d_a0), 64, 0, c.p(net->a0), 64, 0, c.p(net->z0), P0, 64, c.p<float>(net->stats0), c.p<float>(net->coef0),
-                    c.p(net->d_z0), nullptr, c.s, self_mask()));
+    RC(bn_bwd_apply(c.p(net->d_a0), 64, 0, nullptr, 64, 0, c.p(net->z0), P0, 64, c.p<float>(net->stats0), c.p<float>(net->coef0),
+                    c.p(net->d_z0), nullptr, c.s, 1));
     RC(fork_w(c));
     RC(conv1_wgrad(N, net->h, net->w, c.p(net->s2d), c.p(net->d_z0), c.p<float>(net->dw_s2d), c.wgs(), WGRAD_SCRATCH_BYTES, c.sw));
     RC(conv1_wgrad_unpack(c.p<float>(net->dw_s2d), c.grad(P("backbone.conv1.weight")), c.sw));
