@@ -5,6 +5,7 @@
 #include "elementwise.h"
 #include "bn_fin.cuh"
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace dbb {
 
@@ -188,7 +189,7 @@ __global__ void bn_finalize_eval_kernel(int c, int coff, int cn, const float* __
 
 __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const bf16* __restrict__ z, int64_t P, int c, const float* __restrict__ stats4,
                                                               const bf16* __restrict__ res, int relu, bf16* __restrict__ out,
-                                                              int out_ctotal, int out_coff) {
+                                                              int out_ctotal, int out_coff, int rev) {
   const int groups = c / 8;
   const int lg = 31 - __clz(groups);            // groups is a power of two (check_c): shifts instead of 64-bit divides
   const int64_t total = P * groups;
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const bf16* __rest
   };
   int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x;
   for (; i + step < total; i += 2 * step) {      // two items in flight per thread
-    const int64_t p0 = i >> lg, p1 = (i + step) >> lg;
+    const int64_t p0 = rev ? P - 1 - (i >> lg) : (i >> lg), p1 = rev ? P - 1 - ((i + step) >> lg) : ((i + step) >> lg);
     const F8 x0 = ld8s(z + p0 * c + g * 8), x1 = ld8s(z + p1 * c + g * 8);
     if (res) {
       const F8 r0 = ld8s(res + p0 * c + g * 8), r1 = ld8s(res + p1 * c + g * 8);
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const bf16* __rest
     }
   }
   if (i < total) {
-    const int64_t p0 = i >> lg;
+    const int64_t p0 = rev ? P - 1 - (i >> lg) : (i >> lg);
     const F8 x0 = ld8s(z + p0 * c + g * 8);
     if (res) { const F8 r0 = ld8s(res + p0 * c + g * 8); one(x0, &r0, p0); }
     else one(x0, nullptr, p0);
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 bn_bwd_apply_kernel(const bf16* __restrict__ dout, int dout_ctotal, int dout_coff, const bf16* __restrict__ mask_src,
                     int mask_ctotal, int mask_coff, const bf16* __restrict__ z, int64_t P, int c,
                     const float* __restrict__ stats4, const float* __restrict__ coef3, bf16* __restrict__ dz,
-                    bf16* __restrict__ dsum) {
+                    bf16* __restrict__ dsum, int rev) {
   const int groups = c / 8;
   const int lg = 31 - __clz(groups);
   const int64_t total = P * groups;
@@ -297,7 +298,7 @@ bn_bwd_apply_kernel(const bf16* __restrict__ dout, int dout_ctotal, int dout_cof
   const int64_t step = (int64_t)gridDim.x * EW_THREADS;
   int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x;
   for (; i + step < total; i += 2 * step) {      // two items in flight per thread
-    const int64_t p0 = i >> lg, p1 = (i + step) >> lg;
+    const int64_t p0 = rev ? P - 1 - (i >> lg) : (i >> lg), p1 = rev ? P - 1 - ((i + step) >> lg) : ((i + step) >> lg);
     const F8 dy0 = ld8s(dout + p0 * dout_ctotal + dout_coff + g * 8), dy1 = ld8s(dout + p1 * dout_ctotal + dout_coff + g * 8);
     F8 m0, m1;
     if (MASK == 1) { m0 = ld8s(mask_src + p0 * mask_ctotal + mask_coff + g * 8); m1 = ld8s(mask_src + p1 * mask_ctotal + mask_coff + g * 8); }
@@ -305,7 +306,7 @@ bn_bwd_apply_kernel(const bf16* __restrict__ dout, int dout_ctotal, int dout_cof
     one(dy0, m0, x0, p0); one(dy1, m1, x1, p1);
   }
   if (i < total) {
-    const int64_t p0 = i >> lg;
+    const int64_t p0 = rev ? P - 1 - (i >> lg) : (i >> lg);
     const F8 dy0 = ld8s(dout + p0 * dout_ctotal + dout_coff + g * 8);
     F8 m0;
     if (MASK == 1) m0 = ld8s(mask_src + p0 * mask_ctotal + mask_coff + g * 8);
@@ -346,6 +347,9 @@ static int resident_blocks(K kernel) {
   return DBB_NUM_SMS * occ;
 }
 #define DBB_RESIDENT(kernel) ([]() -> int { static const int v = resident_blocks(kernel); return v; }())
+// The apply passes walk their tensors from the END: the producer (the convolution that wrote z, the reduce pass that just read
+// dout and z) touched the end last, so that is the part still resident in the 126 MB L2.
+static int ew_reverse() { static const int v = getenv("DBB_NO_REVERSE") ? 0 : 1; return v; }
 static int fit_grid(int64_t blocks_wanted, int resident) {
   if (blocks_wanted < 1) blocks_wanted = 1;
   return (int)(blocks_wanted < resident ? blocks_wanted : resident);
@@ -513,7 +517,7 @@ static int stream_grid(int64_t total) {
 int bn_apply(const bf16* z, int64_t P, int c, const float* stats4, const bf16* res, int relu, bf16* out, int out_ctotal,
              int out_coff, cudaStream_t s) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_apply: channel count");
-  DBB_LAUNCH(shaped("bn_apply", P, c, res ? 1 : 0), s, bn_apply_kernel<<<fit_grid((P * (c / 8) + 2 * EW_THREADS - 1) / (2 * EW_THREADS), DBB_RESIDENT(bn_apply_kernel)), EW_THREADS, 0, s>>>(z, P, c, stats4, res, relu, out, out_ctotal, out_coff));
+  DBB_LAUNCH(shaped("bn_apply", P, c, res ? 1 : 0), s, bn_apply_kernel<<<fit_grid((P * (c / 8) + 2 * EW_THREADS - 1) / (2 * EW_THREADS), DBB_RESIDENT(bn_apply_kernel)), EW_THREADS, 0, s>>>(z, P, c, stats4, res, relu, out, out_ctotal, out_coff, ew_reverse()));
   return DBB_OK;
 }
 int bn_bwd_reduce(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
@@ -533,9 +537,9 @@ int bn_bwd_apply(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* m
                  cudaStream_t s, int mask_self) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_bwd_apply: channel count");
   const int64_t want = (P * (c / 8) + 2 * EW_THREADS - 1) / (2 * EW_THREADS);
-  if (mask_self) DBB_LAUNCH(shaped("bn_bwd_apply", P, c, 2), s, bn_bwd_apply_kernel<2><<<fit_grid(want, DBB_RESIDENT(bn_bwd_apply_kernel<2>)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, coef3, dz, dsum));
-  else if (mask_src) DBB_LAUNCH(shaped("bn_bwd_apply", P, c, dsum ? 11 : 1), s, bn_bwd_apply_kernel<1><<<fit_grid(want, DBB_RESIDENT(bn_bwd_apply_kernel<1>)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, coef3, dz, dsum));
-  else DBB_LAUNCH(shaped("bn_bwd_apply", P, c, 0), s, bn_bwd_apply_kernel<0><<<fit_grid(want, DBB_RESIDENT(bn_bwd_apply_kernel<0>)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, coef3, dz, dsum));
+  if (mask_self) DBB_LAUNCH(shaped("bn_bwd_apply", P, c, 2), s, bn_bwd_apply_kernel<2><<<fit_grid(want, DBB_RESIDENT(bn_bwd_apply_kernel<2>)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, coef3, dz, dsum, ew_reverse()));
+  else if (mask_src) DBB_LAUNCH(shaped("bn_bwd_apply", P, c, dsum ? 11 : 1), s, bn_bwd_apply_kernel<1><<<fit_grid(want, DBB_RESIDENT(bn_bwd_apply_kernel<1>)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, coef3, dz, dsum, ew_reverse()));
+  else DBB_LAUNCH(shaped("bn_bwd_apply", P, c, 0), s, bn_bwd_apply_kernel<0><<<fit_grid(want, DBB_RESIDENT(bn_bwd_apply_kernel<0>)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, coef3, dz, dsum, ew_reverse()));
   return DBB_OK;
 }
 int bias_grad(const bf16* dz, int64_t P, int c, float* partials, float* dbias, cudaStream_t s) {
