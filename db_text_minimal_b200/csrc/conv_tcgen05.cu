@@ -2,14 +2,17 @@
 //
 // Replaces the cuDNN/oneDNN calls under nn.Conv2d / nn.ConvTranspose2d on the reference's hot path
 // (src/modules/resnet.py:73-86,232; segmentation_body.py:67-76; segmentation_head.py:25-29,64-76):
-//   * igemm_kernel  : forward / data-gradient.  A = activation tile fetched by TMA straight from the NHWC tensor
-//                     (one 4-D box per filter tap; padding = TMA out-of-bounds zero fill; stride = TMA element
-//                     stride), B = packed bf16 weights (2-D TMA), 128-byte swizzle, tcgen05.mma kind::f16 with the
-//                     fp32 accumulator in TMEM, epilogue tcgen05.ld -> +bias -> bf16 NHWC store.  No im2col buffer.
-//   * wgrad_kernel  : weight gradient.  Both operands MN-major (pixels are the GEMM K), split-K over pixel tiles,
-//                     fp32 red.global.add into the OIHW gradient.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (one TMEM lane quadrant each).  smem ring of STAGES {A,B} tiles with full/empty mbarriers.
+//   * igemm_persist_kernel : forward / data-gradient, persistent.  A = activation tile fetched by TMA straight from the
+//                     NHWC tensor (one 4-D box per filter tap; padding = TMA out-of-bounds zero fill; stride = TMA
+//                     element stride), B = packed bf16 weights (2-D TMA), 128-byte swizzle, tcgen05.mma kind::f16 with a
+//                     DOUBLE-BUFFERED fp32 accumulator in TMEM, 8 epilogue warps: tcgen05.ld -> +bias -> bf16 NHWC store
+//                     (+ fused training-mode BatchNorm statistics of the output).  No im2col buffer.
+//   * igemm_kernel  : the first, one-tile-per-CTA version (kept behind DBB_NO_PERSIST for A/B measurements).
+//   * halo64_kernel : 3x3 / stride 1 / 64 -> 64 special case (weights stationary, one halo box per tile, shifted descriptors).
+//   * wgrad_kernel / wgrad_row64_kernel : weight gradient.  Both operands MN-major (pixels are the GEMM K), wave-aware
+//                     split-K over pixel tiles into fp32 scratch partials, reduced in a fixed order (deterministic).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, remaining warps = epilogue (one
+// TMEM lane quadrant each).  smem ring of STAGES {A,B} tiles with full/empty mbarriers.
 #include "common.cuh"
 #include "conv.h"
 #include "bn_fin.cuh"
