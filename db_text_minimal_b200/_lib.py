@@ -53,6 +53,7 @@ def lib():
     sig("dbb_conv1_workspace", sz, [i64, i64, i64, i32])
     sig("dbb_conv1_fwd", i32, [vp, vp, vp, i64, i64, i64, vp, sz, vp])
     sig("dbb_conv1_wgrad", i32, [vp, vp, vp, i64, i64, i64, vp, sz, vp])
+    sig("dbb_thresh_map", i32, [vp, i64, i64, i64, vp, vp, vp, vp, vp, i32, i32, vp])
     sig("dbb_adam_step", i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, vp, vp])
     sig("dbb_text_score_hist", i32, [vp, i64, vp, vp, i64, i64, i64, f32, vp, vp])
     sig("dbb_step_fwd", i32, [vp, vp, vp, i64, f32, vp])

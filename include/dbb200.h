@@ -78,6 +78,15 @@ int dbb_dbloss_bwd(const float* preds, const float* gts, int64_t n, int c, int64
                    float alpha, float beta, int reduction, float eps, const float* grad_out5,
                    DbbLossState* state, float* dpreds, void* stream);
 
+/* Ground-truth border map (replaces the distance field of draw_thresh_map, src/db_transforms.py:26-59 + compute_distance
+ * :62-78): for every polygon, canvas[image] = fmax(canvas, 1 - min_edges clip(dist(pixel, edge) / D, 0, 1)) over the
+ * bounding box (xmin, ymin, xmax, ymax) of the DILATED polygon (the Clipper dilation stays on the host and supplies bbox
+ * and D).  canvas: (n_images, h, w) float32, non-negative; pts: float64 xy pairs of all polygons back to back;
+ * poly_start[npoly + 1], poly_image[npoly], bbox[npoly][4], dist[npoly]; max_pts <= 64.  Device pointers.  float64,
+ * bit-identical to the reference's numpy arithmetic. */
+int dbb_thresh_map(float* canvas, int64_t n_images, int64_t h, int64_t w, const double* pts, const int* poly_start,
+                   const int* poly_image, const long long* bbox, const double* dist, int npoly, int max_pts, void* stream);
+
 /* Optimizer step (replaces torch.optim.Adam(...).step() of src/train.py:114-117,172; amsgrad off): Adam over flat float32
  * buffers of n elements (n % 4 == 0).  *step (device int64) is incremented, then used for the bias corrections, so the
  * call is CUDA-graph capturable.  grad_scale multiplies g first (1/world for a SUM all-reduce, 1 otherwise). */

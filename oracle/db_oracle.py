@@ -555,3 +555,56 @@ def synth_prob_map(h: int, w: int, seed: int = 0, sigma: float = 6.0) -> np.ndar
 def synth_images(n: int, h: int, w: int, seed: int = 0) -> torch.Tensor:
     g = torch.Generator().manual_seed(seed)
     return torch.randn((n, 3, h, w), generator=g) * 60.0
+
+
+# --------------------------------------------------------------------------------------
+# GT border map: the distance field of draw_thresh_map
+# --------------------------------------------------------------------------------------
+
+def polygon_area_length(poly: np.ndarray):
+    """shapely Polygon.area / .length of a simple polygon (shoelace, perimeter), as used at
+    src/db_transforms.py:13-17 and src/data_loaders.py:107-121."""
+    p = np.asarray(poly, dtype=np.float64)
+    q = np.concatenate([p[1:], p[:1]])
+    area = 0.5 * abs(float((p[:, 0] * q[:, 1] - p[:, 1] * q[:, 0]).sum()))
+    length = float(np.sqrt(((p - q) ** 2).sum(1)).sum())
+    return area, length
+
+
+def segment_distance(xs, ys, a, b):
+    """src/db_transforms.py:62-78 (compute_distance): distance of every grid point to segment a-b through the law of
+    cosines, float64, including its behaviour at the degenerate points (nan_to_num of 1 - cos^2, the cos < 0 branch)."""
+    d1 = (xs - a[0]) ** 2 + (ys - a[1]) ** 2
+    d2 = (xs - b[0]) ** 2 + (ys - b[1]) ** 2
+    d = float((a[0] - b[0]) ** 2 + (a[1] - b[1]) ** 2)
+    with np.errstate(all="ignore"):
+        cosin = (d - d1 - d2) / (2 * np.sqrt(d1 * d2))
+        sq_sin = np.nan_to_num(1 - cosin ** 2)
+        res = np.sqrt(d1 * d2 * sq_sin / d)
+        neg = cosin < 0
+        res[neg] = np.sqrt(np.fmin(d1, d2))[neg]
+    return res
+
+
+def thresh_map_accumulate(canvas: np.ndarray, polygon, padded_bbox, distance: float):
+    """src/db_transforms.py:26-59: canvas = fmax(canvas, 1 - min_edges clip(dist/distance, 0, 1)) over the bounding box
+    (xmin, ymin, xmax, ymax) of the dilated polygon.  The dilation itself (pyclipper) is an input here."""
+    poly = np.array(polygon).copy()
+    xmin, ymin, xmax, ymax = (int(v) for v in padded_bbox)
+    width, height = xmax - xmin + 1, ymax - ymin + 1
+    poly[:, 0] = poly[:, 0] - xmin
+    poly[:, 1] = poly[:, 1] - ymin
+    xs = np.broadcast_to(np.arange(width, dtype=np.float64).reshape(1, width), (height, width))
+    ys = np.broadcast_to(np.arange(height, dtype=np.float64).reshape(height, 1), (height, width))
+    dm = np.zeros((poly.shape[0], height, width), dtype=np.float32)
+    for i in range(poly.shape[0]):
+        j = (i + 1) % poly.shape[0]
+        with np.errstate(all="ignore"):
+            dm[i] = np.clip(segment_distance(xs, ys, poly[i], poly[j]) / distance, 0, 1)
+    dm = dm.min(axis=0)
+    H, W = canvas.shape
+    x0, x1 = min(max(0, xmin), W - 1), min(max(0, xmax), W - 1)
+    y0, y1 = min(max(0, ymin), H - 1), min(max(0, ymax), H - 1)
+    canvas[y0:y1 + 1, x0:x1 + 1] = np.fmax(1 - dm[y0 - ymin:y1 - ymax + height, x0 - xmin:x1 - xmax + width],
+                                           canvas[y0:y1 + 1, x0:x1 + 1])
+    return canvas

@@ -191,11 +191,68 @@ def make_post_cases():
     print("post cases", {k: int(out[k + ':ncontours'][0]) for k in maps})
 
 
+def make_thresh_map_cases():
+    """f-4: runs the reference's own draw_thresh_map (src/db_transforms.py:8-59) with the two absent geometry libraries
+    replaced by stand-ins: shapely's Polygon -> shoelace area / perimeter, pyclipper's offset -> a dilated polygon supplied
+    by the case (the arithmetic of Clipper is NOT what is pinned here; the distance field that follows it is)."""
+    import types
+    import sys
+    ref_import.load()
+    offsets = {}
+
+    class FakeOffset:
+        def AddPath(self, subject, jt, et):
+            self.subject = tuple(map(tuple, subject))
+        def Execute(self, distance):
+            return [offsets[self.subject]]
+
+    class FakePolygon:
+        def __init__(self, pts):
+            self.area, self.length = O.polygon_area_length(np.asarray(pts))
+
+    pc = sys.modules["pyclipper"]
+    pc.PyclipperOffset, pc.JT_ROUND, pc.ET_CLOSEDPOLYGON = FakeOffset, 0, 0
+    sys.modules["shapely.geometry"].Polygon = FakePolygon
+    sys.modules.setdefault("imgaug", types.ModuleType("imgaug"))
+    import db_transforms as T
+    from db_text_minimal_b200.postprocess import offset_convex_round
+    rng = np.random.RandomState(9)
+    polys = {
+        "quad": np.array([[30, 20], [150, 28], [146, 60], [26, 52]]),
+        "tall": np.array([[100, 70], [118, 72], [116, 125], [98, 122]]),
+        "edge": np.array([[-6, 90], [40, 88], [42, 110], [-4, 112]]),           # dilated box leaves the canvas
+        "corner": np.array([[140, 110], [170, 108], [172, 135], [138, 136]]),   # beyond the bottom-right corner
+        "hex": np.array([[60, 100], [80, 92], [100, 100], [100, 120], [80, 128], [60, 120]]),
+        "float": np.array([[10.5, 5.25], [60.75, 6.5], [59.5, 30.0], [9.25, 28.5]]),
+    }
+    H, W = 128, 160
+    out = {}
+    canvas = np.zeros((H, W), np.float32)
+    mask = np.zeros((H, W), np.float32)
+    names = list(polys)
+    for name in names:
+        poly = polys[name]
+        area, length = O.polygon_area_length(poly)
+        distance = area * (1 - 0.4 ** 2) / length
+        padded = np.round(offset_convex_round(poly.astype(np.float64), distance)).astype(np.int64)
+        offsets[tuple(map(tuple, poly))] = padded.tolist()
+        T.draw_thresh_map(poly.copy(), canvas, mask, shrink_ratio=0.4)
+        out[name + ":poly"] = poly.astype(np.float64)
+        out[name + ":bbox"] = np.array([padded[:, 0].min(), padded[:, 1].min(), padded[:, 0].max(), padded[:, 1].max()], np.int64)
+        out[name + ":distance"] = np.array([distance])
+        out[name + ":canvas_after"] = canvas.copy()          # cumulative, in `names` order
+    out["names"] = np.array(names)
+    out["mask"] = mask
+    np.savez_compressed(os.path.join(GOLD, "thresh_map_cases.npz"), **out)
+    print("thresh map cases", names, float(canvas.max()), int((canvas > 0).sum()))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
     make_loss_cases()
     make_post_cases()
+    make_thresh_map_cases()
     make_model_case("model_s0_64", 0, 2, 64, 64)
     make_model_case("model_s1_72x100", 1, 2, 72, 100)
     make_model_case("model_s2_54x70", 2, 1, 54, 70)

@@ -132,3 +132,13 @@ def test_contour_free_sets_match_reference(case):
     # scores: float64 mean of float32 values; cv2 accumulates in double too
     gs = sorted(g[2] for g in got); ws = sorted(w[2] for w in want)
     np.testing.assert_allclose(gs, ws, rtol=1e-12, atol=1e-15)
+
+
+def test_thresh_map_oracle_matches_reference_canvases():
+    """f-4: oracle restatement of src/db_transforms.py:26-78 vs canvases drawn by the reference's own draw_thresh_map."""
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "thresh_map_cases.npz"))
+    names = [str(n) for n in d["names"]]
+    canvas = np.zeros_like(d[names[0] + ":canvas_after"])
+    for n in names:
+        O.thresh_map_accumulate(canvas, d[n + ":poly"], d[n + ":bbox"], float(d[n + ":distance"][0]))
+        assert np.array_equal(canvas, d[n + ":canvas_after"]), n
