@@ -25,6 +25,11 @@ struct ConvStats {
   BnFin fin;               // channel indices are positions in y's channel dimension (width out_c)
 };
 
+// Inference-mode epilogue: y = [relu]((acc + bias) * scale[ch] + shift[ch] [+ res]) -- BatchNorm with fixed statistics (and
+// the residual add / ReLU that follow it) applied to the fp32 accumulator, so eval-mode forward passes write activations
+// directly and run no separate BatchNorm pass.  res: compact NHWC tensor of the output's shape (channel stride = cout).
+struct ConvEpi { const float* scale; const float* shift; const bf16* res; int relu; };
+
 // One implicit-GEMM launch:  Y[pixel, co] = sum_{tap, ci} X[pixel @ tap, ci] * Wp[co, tap*cin + ci]  (+ bias[co])
 //
 // "pixel" runs over an M-space grid (mn, mh, mw); row (n,h,w) reads X at (n, h*in_sh + dh[tap], w*in_sw + dw[tap])
@@ -53,6 +58,7 @@ struct IgemmPlan {
   int accumulate;          // 1: Y += result (gradient fan-in), 0: overwrite
   int cls_cols;            // > 0: pixel-shuffle epilogue, GEMM column = class*cls_cols + channel (ConvTranspose2d k2 s2)
   ConvStats st;            // optional fused BatchNorm statistics of y
+  ConvEpi epi;             // optional inference epilogue (scale != nullptr)
 };
 
 // weight packing: fp32 parameter -> bf16 GEMM B matrix [rows][K] (K-major)
@@ -92,6 +98,7 @@ struct HaloPlan {
   int accumulate;
   int base_offset_mode;    // descriptor base_offset: 1 = (addr >> 7) & 7, 0 = always 0 (tuning / bring-up)
   ConvStats st;            // optional fused BatchNorm statistics of y
+  ConvEpi epi;             // optional inference epilogue (scale != nullptr)
 };
 int halo64_supported(int h, int w);
 int halo64_plan(HaloPlan* p, const bf16* x, int n, int h, int w, int x_ctotal, int x_coff, const bf16* wp, int dgrad);

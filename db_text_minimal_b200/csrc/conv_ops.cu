@@ -23,7 +23,7 @@ static bool use_halo(const ConvGeom& g) {
 }
 
 int conv_fprop(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const bf16* wp, const float* bias, bf16* y,
-               int y_ctotal, int y_coff, cudaStream_t s, const ConvStats* st) {
+               int y_ctotal, int y_coff, cudaStream_t s, const ConvStats* st, const ConvEpi* epi) {
   const int ho = g.out_h(), wo = g.out_w();
   if (use_halo(g)) {
     HaloPlan hp;
@@ -32,6 +32,7 @@ int conv_fprop(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const
     if (rc) return rc;
     hp.y = y; hp.out_c = y_ctotal; hp.out_coff = y_coff; hp.bias = bias; hp.accumulate = 0;
     if (st) { hp.st = *st; hp.st.enabled = 1; hp.st.count = (double)g.n * ho * wo; }
+    if (epi) hp.epi = *epi;
     return halo64_launch(hp, s);
   }
   IgemmPlan p;
@@ -49,6 +50,7 @@ int conv_fprop(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const
   p.out_sh = p.out_sw = 1; p.out_oh = p.out_ow = 0;
   p.bias = bias;
   if (st) { p.st = *st; p.st.enabled = 1; p.st.count = (double)g.n * ho * wo; }
+  if (epi) p.epi = *epi;
   const int64_t m_tiles = ((int64_t)g.n * ho * wo + 127) / 128;
   int rc = igemm_plan_init(&p, x, g.n, g.h, g.w, x_ctotal, x_coff, g.cin, wp, p.ntaps * g.cin, g.cout, pick_block_n(g.cout, m_tiles));
   if (rc) return rc;

@@ -15,7 +15,7 @@ struct ConvGeom {
 // wp: packed by pack_weights mode 0 ; x may be a channel slice [x_coff, x_coff+cin) of a wider NHWC tensor
 // st (optional): fuse the training-mode BatchNorm statistics of y into the epilogue (conv.h: ConvStats; count is filled here)
 int conv_fprop(const ConvGeom& g, const bf16* x, int x_ctotal, int x_coff, const bf16* wp, const float* bias, bf16* y,
-               int y_ctotal, int y_coff, cudaStream_t s, const ConvStats* st = nullptr);
+               int y_ctotal, int y_coff, cudaStream_t s, const ConvStats* st = nullptr, const ConvEpi* epi = nullptr);
 // wp_t: packed by pack_weights mode 1
 // dy may be a channel slice [dy_coff, dy_coff+cout) of a dy_ctotal-wide tensor (0 = compact); accumulate: dx += result
 int conv_dgrad(const ConvGeom& g, const bf16* dy, const bf16* wp_t, bf16* dx, cudaStream_t s, int accumulate = 0);

@@ -163,6 +163,25 @@ igemm_kernel(const __grid_constant__ IgemmPlan p) {
 // Either way the warp leaves its column totals in s_stat[quadrant][2][ncols]; stat_flush adds the four quadrants into the
 // global fp64 accumulators and the last CTA finalizes.
 // ---------------------------------------------------------------------------------------------
+// inference epilogue on 16 consecutive channels of one output pixel (conv.h: ConvEpi); res_off = element offset of the
+// pixel's channel ch0 inside the compact residual tensor
+__device__ __forceinline__ void epi_apply16(float (&f)[16], const ConvEpi& e, int ch0, int64_t res_off) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) f[i] = fmaf(f[i], __ldg(e.scale + ch0 + i), __ldg(e.shift + ch0 + i));
+  if (e.res) {
+    const uint4* r = reinterpret_cast<const uint4*>(e.res + res_off);
+    const uint4 r0 = r[0], r1 = r[1];
+    f[0] += bf16lo(r0.x); f[1] += bf16hi(r0.x); f[2] += bf16lo(r0.y); f[3] += bf16hi(r0.y);
+    f[4] += bf16lo(r0.z); f[5] += bf16hi(r0.z); f[6] += bf16lo(r0.w); f[7] += bf16hi(r0.w);
+    f[8] += bf16lo(r1.x); f[9] += bf16hi(r1.x); f[10] += bf16lo(r1.y); f[11] += bf16hi(r1.y);
+    f[12] += bf16lo(r1.z); f[13] += bf16hi(r1.z); f[14] += bf16lo(r1.w); f[15] += bf16hi(r1.w);
+  }
+  if (e.relu) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+  }
+}
+
 template <int NTHREADS>
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" :: "n"(NTHREADS) : "memory"); }   // epilogue warps only
 
@@ -380,6 +399,7 @@ igemm_persist_kernel(const __grid_constant__ IgemmPlan p) {
         if (row_ok) {
           const int64_t opix = ((int64_t)n * p.out_h + (h * p.out_sh + oh)) * p.out_w + (w * p.out_sw + ow);
           uint4* dst = reinterpret_cast<uint4*>(p.y + opix * p.out_c + p.out_coff + ch0);
+          if (p.epi.scale) epi_apply16(f, p.epi, ch0, opix * p.cout + ch0);
           if (p.accumulate) {
             const uint4 e0 = dst[0], e1 = dst[1];
             f[0] += bf16lo(e0.x); f[1] += bf16hi(e0.x); f[2] += bf16lo(e0.y); f[3] += bf16hi(e0.y);
@@ -543,6 +563,8 @@ halo64_kernel(const __grid_constant__ HaloPlan p) {
             for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + half * 32 + c * 16 + j);
           }
           uint4* dst = reinterpret_cast<uint4*>(yrow + c * 16);
+          if (p.epi.scale)
+            epi_apply16(f, p.epi, half * 32 + c * 16, (((int64_t)n * p.h + hh) * p.w + ww) * 64 + half * 32 + c * 16);
           if (p.accumulate) {
             const uint4 e0 = dst[0], e1 = dst[1];
             f[0] += bf16lo(e0.x); f[1] += bf16hi(e0.x); f[2] += bf16lo(e0.y); f[3] += bf16hi(e0.y);
@@ -1174,7 +1196,7 @@ int igemm_launch(const IgemmPlan& p, cudaStream_t s) {
   static const bool deep_only = getenv("DBB_DEEP_RING") != nullptr;      // A/B switches
   static const bool no_persist = getenv("DBB_NO_PERSIST") != nullptr;
   const int depth = deep_only ? 4 : (kiters <= 1 ? 1 : (kiters <= 4 ? 2 : 4));
-  if (!no_persist || p.st.enabled) {
+  if (!no_persist || p.st.enabled || p.epi.scale) {
     const bool st = p.st.enabled != 0;
     switch (p.block_n) {
       case 64:

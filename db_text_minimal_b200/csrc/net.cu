@@ -442,6 +442,23 @@ int convbn_fwd(const Ctx& c, ConvBN& L, const bf16* x, int x_ctotal, int x_coff)
   return 0;
 }
 
+// conv -> BatchNorm -> [+ res] -> [ReLU] -> out.  Training: raw output z + fused statistics, then one apply pass.
+// Inference: the fixed-statistics BatchNorm, the residual add and the ReLU run in the convolution's epilogue on the fp32
+// accumulator (ConvEpi): no z tensor, no apply pass.
+int convbn_act_fwd(const Ctx& c, ConvBN& L, const bf16* x, int x_ctotal, int x_coff, const bf16* res, int relu, bf16* out,
+                   int out_ctotal, int out_coff) {
+  static const bool no_epi = getenv("DBB_NO_EVAL_EPILOGUE") != nullptr;     // A/B switch
+  const int ch = L.g.cout;
+  if (c.net->training || no_epi) {
+    RC(convbn_fwd(c, L, x, x_ctotal, x_coff));
+    return bn_apply(c.p(L.z), L.P(), ch, c.p<float>(L.stats), res, relu, out, out_ctotal, out_coff, c.s);
+  }
+  float* stats4 = c.p<float>(L.stats);
+  RC(bn_finalize_eval(ch, 0, ch, c.par(L.gamma), c.par(L.beta), c.buf(L.rm), c.buf(L.rv), BN_EPS, stats4, c.s));
+  const ConvEpi epi{stats4, stats4 + ch, res, relu};
+  return conv_fprop(L.g, x, x_ctotal, x_coff, c.p(L.wp), c.par(L.b), out, out_ctotal, out_coff, c.s, nullptr, &epi);
+}
+
 // backward through BN (+ReLU mask) and the conv: dout -> dz -> (dW, dbias, dx)
 static bool wgrad_fork_late() { static const bool v = getenv("DBB_WGRAD_FORK_LATE") != nullptr; return v; }   // A/B switch
 static int self_mask() { static const int v = getenv("DBB_NO_SELF_MASK") ? 0 : 1; return v; }    // A/B switch
@@ -473,16 +490,13 @@ int convbn_bwd(const Ctx& c, ConvBN& L, const bf16* dout, int dout_ctotal, int d
 }
 
 int block_fwd(const Ctx& c, Block& bk, const bf16* x) {
-  RC(convbn_fwd(c, bk.c1, x, bk.c_in, 0));
-  RC(bn_apply(c.p(bk.c1.z), bk.c1.P(), bk.c1.g.cout, c.p<float>(bk.c1.stats), nullptr, 1, c.p(bk.a1), bk.c1.g.cout, 0, c.s));
-  RC(convbn_fwd(c, bk.c2, c.p(bk.a1), bk.c1.g.cout, 0));
+  RC(convbn_act_fwd(c, bk.c1, x, bk.c_in, 0, nullptr, 1, c.p(bk.a1), bk.c1.g.cout, 0));
   const bf16* res = x;
   if (bk.has_ds) {
-    RC(convbn_fwd(c, bk.ds, x, bk.c_in, 0));
-    RC(bn_apply(c.p(bk.ds.z), bk.ds.P(), bk.ds.g.cout, c.p<float>(bk.ds.stats), nullptr, 0, c.p(bk.rd), bk.ds.g.cout, 0, c.s));
+    RC(convbn_act_fwd(c, bk.ds, x, bk.c_in, 0, nullptr, 0, c.p(bk.rd), bk.ds.g.cout, 0));
     res = c.p(bk.rd);
   }
-  RC(bn_apply(c.p(bk.c2.z), bk.c2.P(), bk.c2.g.cout, c.p<float>(bk.c2.stats), res, 1, c.p(bk.out), bk.c2.g.cout, 0, c.s));
+  RC(convbn_act_fwd(c, bk.c2, c.p(bk.a1), bk.c1.g.cout, 0, res, 1, c.p(bk.out), bk.c2.g.cout, 0));
   return 0;
 }
 
@@ -542,8 +556,7 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
   const int planes[4] = {64, 128, 256, 512};
   // ---- FPN top-down (segmentation_body.py:64-77)
   for (int i = 3; i >= 0; --i) {
-    RC(convbn_fwd(c, net->lat[i], feat[i], planes[i], 0));
-    RC(bn_apply(c.p(net->lat[i].z), net->lat[i].P(), 64, c.p<float>(net->lat[i].stats), nullptr, 1, c.p(net->l_act[i]), 64, 0, c.s));
+    RC(convbn_act_fwd(c, net->lat[i], feat[i], planes[i], 0, nullptr, 1, c.p(net->l_act[i]), 64, 0));
   }
   const int hf = net->hh[0], wf = net->ww[0];
   const bf16* upper = c.p(net->l_act[3]);   // p5
@@ -551,9 +564,8 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
   for (int i = 0; i < 3; ++i) {             // p4, p3, p2
     const int lvl = 2 - i;
     RC(upsample_add_fwd(upper, uh, uw, c.p(net->l_act[lvl]), N, net->hh[lvl], net->ww[lvl], 64, c.p(net->s_sum[i]), c.s));
-    RC(convbn_fwd(c, net->smooth[i], c.p(net->s_sum[i]), 64, 0));
     bf16* dst = (i < 2) ? c.p(net->p_act[i]) : c.p(net->cat);
-    RC(bn_apply(c.p(net->smooth[i].z), net->smooth[i].P(), 64, c.p<float>(net->smooth[i].stats), nullptr, 1, dst, i < 2 ? 64 : 256, 0, c.s));
+    RC(convbn_act_fwd(c, net->smooth[i], c.p(net->s_sum[i]), 64, 0, nullptr, 1, dst, i < 2 ? 64 : 256, 0));
     upper = dst; uh = net->hh[lvl]; uw = net->ww[lvl];
     if (i == 2) break;
   }
@@ -561,8 +573,7 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
   RC(upsample_into(c.p(net->p_act[1]), net->hh[1], net->ww[1], N, hf, wf, 64, c.p(net->cat), 256, 64, c.s));
   RC(upsample_into(c.p(net->p_act[0]), net->hh[2], net->ww[2], N, hf, wf, 64, c.p(net->cat), 256, 128, c.s));
   RC(upsample_into(c.p(net->l_act[3]), net->hh[3], net->ww[3], N, hf, wf, 64, c.p(net->cat), 256, 192, c.s));
-  RC(convbn_fwd(c, net->fconv, c.p(net->cat), 256, 0));
-  RC(bn_apply(c.p(net->fconv.z), net->fconv.P(), 256, c.p<float>(net->fconv.stats), nullptr, 1, c.p(net->af), 256, 0, c.s));
+  RC(convbn_act_fwd(c, net->fconv, c.p(net->cat), 256, 0, nullptr, 1, c.p(net->af), 256, 0));
   // ---- head (segmentation_head.py:35-45)
   DBB_CUDA(cudaMemsetAsync(c.p<float>(net->bias_h), 0, 128 * sizeof(float), c.s));
   DBB_CUDA(cudaMemcpyAsync(c.p<float>(net->bias_h), c.par(P("segmentation_head.binarize.0.bias")), 64 * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
@@ -577,12 +588,20 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
   };
   {
     const std::vector<BnIdx> ix = head_bn("1");
-    ConvStats st;
-    const ConvStats* fused = bn_fused(c, st, 64, 2, ix.data(), c.p<float>(net->stats_h));
-    RC(conv_fprop(net->hconv_g, c.p(net->af), 256, 0, c.p(net->wp_h), c.p<float>(net->bias_h), c.p(net->zh), 128, 0, c.s, fused));
-    if (!fused) RC(bn_prepare(c, c.p(net->zh), Ph, 128, 2, ix.data(), c.p<float>(net->stats_h)));
+    static const bool no_epi = getenv("DBB_NO_EVAL_EPILOGUE") != nullptr;     // A/B switch
+    if (!net->training && !no_epi) {     // inference: BatchNorm + ReLU in the convolution's epilogue (see convbn_act_fwd)
+      float* stats4 = c.p<float>(net->stats_h);
+      RC(bn_prepare(c, nullptr, Ph, 128, 2, ix.data(), stats4));
+      const ConvEpi epi{stats4, stats4 + 128, nullptr, 1};
+      RC(conv_fprop(net->hconv_g, c.p(net->af), 256, 0, c.p(net->wp_h), c.p<float>(net->bias_h), c.p(net->ah), 128, 0, c.s, nullptr, &epi));
+    } else {
+      ConvStats st;
+      const ConvStats* fused = bn_fused(c, st, 64, 2, ix.data(), c.p<float>(net->stats_h));
+      RC(conv_fprop(net->hconv_g, c.p(net->af), 256, 0, c.p(net->wp_h), c.p<float>(net->bias_h), c.p(net->zh), 128, 0, c.s, fused));
+      if (!fused) RC(bn_prepare(c, c.p(net->zh), Ph, 128, 2, ix.data(), c.p<float>(net->stats_h)));
+      RC(bn_apply(c.p(net->zh), Ph, 128, c.p<float>(net->stats_h), nullptr, 1, c.p(net->ah), 128, 0, c.s));
+    }
   }
-  RC(bn_apply(c.p(net->zh), Ph, 128, c.p<float>(net->stats_h), nullptr, 1, c.p(net->ah), 128, 0, c.s));
   const int64_t Pt = Ph * 4;
   {
     const std::vector<BnIdx> ix = head_bn("4");
