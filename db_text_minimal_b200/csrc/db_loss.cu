@@ -208,6 +208,51 @@ __device__ void write_losses(const double* S, double prob, const LossParams& lp,
   st->tie_ticket = 0;
 }
 
+// Walk a histogram (in shared memory) from the top until k entries are covered -- block-wide: every thread sums its slice
+// of bins, a suffix scan over the threads locates the slice in which the running count crosses k, and that one thread
+// finishes the walk inside its slice.  (The serial single-thread walk over 2048 bins cost 15-35 us per call.)
+//   found : some bin b has  count(bins > b) < k <= count(bins >= b)  -> bin = b, above = count(bins > b)
+//   k <= 0: bin = nbins - 1, above = 0 (found)          k > total: bin = 0, above = total (not found)
+// Must be called by all threads of the block (blockDim.x <= 512).
+struct PickRes { int bin; long long above; int found; };
+__device__ PickRes pick_bin_block(const unsigned* sh, int nbins, long long k) {
+  __shared__ long long part[512];
+  __shared__ int s_bin, s_found;
+  __shared__ long long s_above;
+  const int nt = blockDim.x, t = threadIdx.x;
+  const int per = (nbins + nt - 1) / nt;
+  long long local = 0;
+  for (int j = 0; j < per; ++j) { const int b = t * per + j; if (b < nbins) local += sh[b]; }
+  part[t] = local;
+  if (t == 0) { s_found = 0; s_bin = 0; s_above = 0; }
+  __syncthreads();
+  for (int off = 1; off < nt; off <<= 1) {            // part[t] <- sum of part[u], u >= t
+    const long long v = (t + off < nt) ? part[t + off] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  const long long incl = part[t], excl = incl - local;
+  if (k <= 0) {
+    if (t == 0) { s_found = 1; s_bin = nbins - 1; s_above = 0; }
+  } else if (excl < k && incl >= k) {                 // exactly one thread
+    long long acc = excl;
+    for (int j = per - 1; j >= 0; --j) {
+      const int b = t * per + j;
+      if (b >= nbins) continue;
+      const long long c = sh[b];
+      if (acc + c >= k) { s_found = 1; s_bin = b; s_above = acc; break; }
+      acc += c;
+    }
+  } else if (t == 0 && part[0] < k) {
+    s_above = part[0];                                // k exceeds the total
+  }
+  __syncthreads();
+  PickRes r{s_bin, s_above, s_found};
+  __syncthreads();                                    // the shared result may be reused by a later call
+  return r;
+}
+
 // finalize for 'mean', and level-1 bin search for 'none'
 template <bool SELECT>
 __global__ void __launch_bounds__(256)
@@ -220,12 +265,14 @@ dbloss_finalize1_kernel(const double* __restrict__ partials, int nblk, unsigned*
   sum_partials(partials, nblk, S, 0, 9);
   if (SELECT) for (int i = threadIdx.x; i < HIST1_BINS; i += blockDim.x) sh[i] = hist1[i];
   __syncthreads();
-  if (threadIdx.x != 0) return;
   const long long n_pos = (long long)S[S_POS];                       // int(positive.sum())
   long long n_neg = (long long)((double)n_pos * (double)lp.ratio);   // int(no_positive * ratio)
   const long long n_neg_cur = (long long)S[S_NEG];
   if (n_neg_cur < n_neg) n_neg = n_neg_cur;
   const double D = (double)n_pos + (double)n_neg + (double)lp.eps;
+  PickRes pick{0, 0, 0};
+  if (SELECT) pick = pick_bin_block(sh, HIST1_BINS, n_neg);          // level-1: block-wide walk from the top bin down
+  if (threadIdx.x != 0) return;
   st->n_pos = n_pos; st->n_neg = n_neg; st->reduction = SELECT ? 1 : 0;
   if (!SELECT) {
     const double mean_bce = S[S_BCE_ALL] / (double)lp.px;
@@ -235,15 +282,8 @@ dbloss_finalize1_kernel(const double* __restrict__ partials, int nblk, unsigned*
     write_losses(S, prob, lp, losses5, st, (S[S_POS] + (double)n_neg) / D / (double)lp.px);
     return;
   }
-  // level-1: walk the histogram from the top bin down until k entries are covered
   long long above = 0; int tb = -1;
-  if (n_neg > 0) {
-    for (int b = HIST1_BINS - 1; b >= 0; --b) {
-      const long long c = sh[b];
-      if (above + c >= n_neg) { tb = b; break; }
-      above += c;
-    }
-  }
+  if (n_neg > 0) { above = pick.above; tb = pick.found ? pick.bin : -1; }
   // tb == -1: k == 0, or k exceeds the number of strictly positive entries -> tau = 0
   cand_ctl[0] = 0u;
   cand_ctl[1] = (unsigned)tb;
@@ -325,30 +365,22 @@ dbloss_l2hist_kernel(const unsigned* __restrict__ cand_ctl, const float* __restr
   for (int i = threadIdx.x; i < HIST2_BINS; i += LOSS_THREADS) { const unsigned c = sh[i]; if (c) atomicAdd(&hist2[i], c); }
 }
 
-// walk a histogram (in shared memory) from the top until k entries are covered; one warp, 64-bin chunks per step
-__device__ void pick_bin(const unsigned* sh, int nbins, long long k, int& bin, long long& above) {
-  long long acc = 0; int b = nbins - 1;
-  for (; b >= 0; --b) {
-    const long long c = sh[b];
-    if (acc + c >= k) break;
-    acc += c;
-  }
-  bin = b < 0 ? 0 : b; above = acc;
-}
-
 __global__ void __launch_bounds__(256)
 dbloss_pick2_kernel(const unsigned* __restrict__ cand_ctl, const unsigned* __restrict__ hist2, const DbbLossState* __restrict__ st,
                     unsigned* __restrict__ sel_ctl) {
   __shared__ unsigned sh[HIST2_BINS];
   for (int i = threadIdx.x; i < HIST2_BINS; i += blockDim.x) sh[i] = hist2[i];
   __syncthreads();
-  if (threadIdx.x != 0) return;
   const int tb = (int)cand_ctl[1];
-  if (tb < 0) { sel_ctl[0] = 0; sel_ctl[1] = sel_ctl[2] = sel_ctl[3] = sel_ctl[4] = 0; return; }
+  if (tb < 0) {
+    if (threadIdx.x == 0) { sel_ctl[0] = 0; sel_ctl[1] = sel_ctl[2] = sel_ctl[3] = sel_ctl[4] = 0; }
+    return;
+  }
   const long long above1 = ((long long)cand_ctl[3] << 32) | cand_ctl[2];
   const long long krem = st->n_neg - above1;
-  int b2; long long a2;
-  pick_bin(sh, HIST2_BINS, krem, b2, a2);
+  const PickRes pk = pick_bin_block(sh, HIST2_BINS, krem);
+  if (threadIdx.x != 0) return;
+  const int b2 = pk.bin; const long long a2 = pk.above;
   const long long k3 = krem - a2, ab = above1 + a2;
   sel_ctl[0] = (unsigned)b2;
   sel_ctl[1] = (unsigned)(k3 & 0xffffffffll); sel_ctl[2] = (unsigned)(k3 >> 32);
@@ -396,10 +428,10 @@ dbloss_select_final_kernel(double* __restrict__ partials, int nblk, const unsign
   __syncthreads();
   sum_partials(partials, nblk, S, S_TOP_ABOVE, S_TOP_CAND + 1);
   __syncthreads();
-  if (tid != 0) return;
   const long long n_pos = st->n_pos, n_neg = st->n_neg;
   const double D = (double)n_pos + (double)n_neg + (double)lp.eps;
   if (tb < 0) {
+    if (tid != 0) return;
     // tau = 0: every strictly positive entry is taken, the rest of the picks are zeros
     const long long nz = ((long long)cand_ctl[3] << 32) | cand_ctl[2];
     st->tau = 0.f; st->tau_bits = 0u;
@@ -412,15 +444,24 @@ dbloss_select_final_kernel(double* __restrict__ partials, int nblk, const unsign
   const unsigned b2 = sel_ctl[0];
   const long long k3 = ((long long)sel_ctl[2] << 32) | sel_ctl[1];
   long long above = ((long long)sel_ctl[4] << 32) | sel_ctl[3];
-  int b3; long long a3;
-  pick_bin(sh, HIST3_BINS, k3, b3, a3);
-  above += a3;
+  const PickRes pk = pick_bin_block(sh, HIST3_BINS, k3);
+  const int b3 = pk.bin;
+  above += pk.above;
   const unsigned prefix = ((unsigned)tb << 20) | (b2 << 9);
   const unsigned tau_bits = prefix | (unsigned)b3;
   const float tau = __uint_as_float(tau_bits);
   // candidates sharing the 23-bit prefix and a larger low field are single values: count x value is exact
+  // (one bin per thread, warp sums combined in warp order: a fixed summation order)
+  __shared__ double wsum[16];
+  double term = 0.0;
+  for (int b = tid; b < HIST3_BINS; b += blockDim.x)
+    if (b > b3) term += (double)sh[b] * (double)__uint_as_float(prefix | (unsigned)b);
+  term = warp_sum(term);
+  if ((tid & 31) == 0) wsum[tid >> 5] = term;
+  __syncthreads();
+  if (tid != 0) return;
   double same_prefix = 0.0;
-  for (int b = HIST3_BINS - 1; b > b3; --b) same_prefix += (double)sh[b] * (double)__uint_as_float(prefix | (unsigned)b);
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) same_prefix += wsum[w];
   const long long n_tie = n_neg - above;
   st->tau = tau; st->tau_bits = tau_bits; st->n_above = above; st->n_tie = n_tie;
   S[S_TOP_CAND] += same_prefix;
