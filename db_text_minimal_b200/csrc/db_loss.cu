@@ -300,6 +300,8 @@ dbloss_select_pass2_kernel(const float* __restrict__ preds, const float* __restr
   const int tb = (int)cand_ctl[1];
   const int64_t px = n_img * hw;
   const int64_t hwv = hw / VEC, nvec = n_img * hwv;
+  __shared__ unsigned wtot[2][LOSS_THREADS / 32];      // double buffered by iteration parity
+  __shared__ unsigned blk_base[2];
   float acc = 0.f;
   if (tb >= 0) {
     const int lane = threadIdx.x & 31;
@@ -323,20 +325,25 @@ dbloss_select_pass2_kernel(const float* __restrict__ preds, const float* __restr
           if (bin == tb) hit[cnt++] = nl;
         }
       }
-      // warp exclusive scan of the hit counts -> one atomicAdd per warp
+      // warp exclusive scan of the hit counts, warp totals combined per block -> ONE atomicAdd per block iteration
+      // (the tau bin holds a large share of the negatives: one atomic per warp was ~50 k same-address atomics)
       int incl = cnt;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
       }
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      if (total) {
-        unsigned base = 0;
-        if (lane == 31) base = atomicAdd(&cand_ctl[0], (unsigned)total);
-        base = __shfl_sync(0xffffffffu, base, 31) + (unsigned)(incl - cnt);
-        for (int j = 0; j < cnt; ++j) cands[base + j] = hit[j];
+      const int par = (int)(it & 1);
+      if (lane == 31) wtot[par][threadIdx.x >> 5] = (unsigned)incl;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned sum = 0;
+        for (int w = 0; w < LOSS_THREADS / 32; ++w) { const unsigned t = wtot[par][w]; wtot[par][w] = sum; sum += t; }
+        blk_base[par] = sum ? atomicAdd(&cand_ctl[0], sum) : 0u;
       }
+      __syncthreads();
+      const unsigned base = blk_base[par] + wtot[par][threadIdx.x >> 5] + (unsigned)(incl - cnt);
+      for (int j = 0; j < cnt; ++j) cands[base + j] = hit[j];
     }
   }
   __shared__ float red[LOSS_THREADS / 32];
