@@ -68,6 +68,9 @@ def lib():
     sig("dbb_net_buffer_name", C.c_char_p, [i32])
     sig("dbb_net_buffer_numel", i32, [i32])
     sig("dbb_net_create", vp, [i64, i64, i64, i32])
+    sig("dbb_net_create_ex", vp, [i64, i64, i64, i32, i32])
+    sig("dbb_net_precision", i32, [vp])
+    sig("dbb_net_backward_ex", i32, [vp, vp, vp, vp, vp, vp, vp, sz, i32, vp])
     sig("dbb_net_destroy", None, [vp])
     sig("dbb_net_workspace_bytes", sz, [vp])
     sig("dbb_net_out_channels", i64, [vp])

@@ -12,6 +12,8 @@ namespace dbb {
 // ---------------------------------------------------------------------------------------------
 // NCHW float32 <-> NHWC bf16   (module boundaries keep the reference's NCHW float32 layout)
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act2f(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float act2f(float v) { return v; }
 // tile transpose through shared memory: 32 pixels x 32 channels per step
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, bf16* __restrict__ y, int c, int64_t hw) {
   __shared__ float tile[32][33];
@@ -31,16 +33,17 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
     if (pp < hw && cc < c) yb[pp * c + cc] = __float2bfloat16_rn(tile[tx][j]);
   }
 }
-__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const bf16* __restrict__ x, float* __restrict__ y, int c, int64_t hw) {
+template <typename T>
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int c, int64_t hw) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int64_t p0 = (int64_t)blockIdx.x * 32;
   const int c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const bf16* xb = x + (int64_t)n * hw * c;
+  const T* xb = x + (int64_t)n * hw * c;
   for (int j = ty; j < 32; j += 8) {
     const int64_t pp = p0 + j; const int cc = c0 + tx;
-    tile[j][tx] = (pp < hw && cc < c) ? __bfloat162float(xb[pp * c + cc]) : 0.f;
+    tile[j][tx] = (pp < hw && cc < c) ? act2f(xb[pp * c + cc]) : 0.f;
   }
   __syncthreads();
   float* yb = y + (int64_t)n * c * hw;
@@ -55,11 +58,15 @@ int nchw_f32_to_nhwc_bf16(const float* x, bf16* y, int n, int c, int64_t hw, cud
   DBB_LAUNCH("nchw_to_nhwc", s, nchw_to_nhwc_kernel<<<grid, 256, 0, s>>>(x, y, c, hw));
   return DBB_OK;
 }
-int nhwc_bf16_to_nchw_f32(const bf16* x, float* y, int n, int c, int64_t hw, cudaStream_t s) {
+template <typename T>
+int nhwc_to_nchw_f32(const T* x, float* y, int n, int c, int64_t hw, cudaStream_t s) {
   dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n);
-  DBB_LAUNCH("nhwc_to_nchw", s, nhwc_to_nchw_kernel<<<grid, 256, 0, s>>>(x, y, c, hw));
+  DBB_LAUNCH("nhwc_to_nchw", s, nhwc_to_nchw_kernel<T><<<grid, 256, 0, s>>>(x, y, c, hw));
   return DBB_OK;
 }
+template int nhwc_to_nchw_f32<bf16>(const bf16*, float*, int, int, int64_t, cudaStream_t);
+template int nhwc_to_nchw_f32<float>(const float*, float*, int, int, int64_t, cudaStream_t);
+int nhwc_bf16_to_nchw_f32(const bf16* x, float* y, int n, int c, int64_t hw, cudaStream_t s) { return nhwc_to_nchw_f32<bf16>(x, y, n, c, hw, s); }
 
 
 // ---------------------------------------------------------------------------------------------
@@ -87,6 +94,23 @@ __device__ __forceinline__ void st8(bf16* p, const F8& a) {
   u.x = pack_bf16(a.v[0], a.v[1]); u.y = pack_bf16(a.v[2], a.v[3]); u.z = pack_bf16(a.v[4], a.v[5]); u.w = pack_bf16(a.v[6], a.v[7]);
   *reinterpret_cast<uint4*>(p) = u;
 }
+// fp32-parity storage (DESIGN.md "fp32 mode"): the same kernels instantiated on float activations
+__device__ __forceinline__ F8 ld8(const float* p) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  return F8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+__device__ __forceinline__ F8 ld8s(const float* p) {
+  const float4 a = ldg_stream(reinterpret_cast<const float4*>(p)), b = ldg_stream(reinterpret_cast<const float4*>(p + 4));
+  return F8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+__device__ __forceinline__ void st8(float* p, const F8& a) {
+  *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+// value as it will be stored in an activation tensor of type T
+template <typename T> __device__ __forceinline__ float round_act(float v);
+template <> __device__ __forceinline__ float round_act<bf16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+template <> __device__ __forceinline__ float round_act<float>(float v) { return v; }
 __device__ __forceinline__ F8 ldf8(const float* p) {
   const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
   return F8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
@@ -187,8 +211,9 @@ __global__ void bn_finalize_eval_kernel(int c, int coff, int cn, const float* __
   stats4[3 * c + ch] = invstd;
 }
 
-__global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const bf16* __restrict__ z, int64_t P, int c, const float* __restrict__ stats4,
-                                                              const bf16* __restrict__ res, int relu, bf16* __restrict__ out,
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const T* __restrict__ z, int64_t P, int c, const float* __restrict__ stats4,
+                                                              const T* __restrict__ res, int relu, T* __restrict__ out,
                                                               int out_ctotal, int out_coff, int rev) {
   const int groups = c / 8;
   const int lg = 31 - __clz(groups);            // groups is a power of two (check_c): shifts instead of 64-bit divides
@@ -269,12 +294,12 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n
   coef3[2 * c + ch] = (float)(q / count);
 }
 
-template <int MASK>
+template <int MASK, typename T>
 __global__ void __launch_bounds__(EW_THREADS)
-bn_bwd_apply_kernel(const bf16* __restrict__ dout, int dout_ctotal, int dout_coff, const bf16* __restrict__ mask_src,
-                    int mask_ctotal, int mask_coff, const bf16* __restrict__ z, int64_t P, int c,
-                    const float* __restrict__ stats4, const float* __restrict__ coef3, bf16* __restrict__ dz,
-                    bf16* __restrict__ dsum, int rev) {
+bn_bwd_apply_kernel(const T* __restrict__ dout, int dout_ctotal, int dout_coff, const T* __restrict__ mask_src,
+                    int mask_ctotal, int mask_coff, const T* __restrict__ z, int64_t P, int c,
+                    const float* __restrict__ stats4, const float* __restrict__ coef3, T* __restrict__ dz,
+                    T* __restrict__ dsum, int rev) {
   const int groups = c / 8;
   const int lg = 31 - __clz(groups);
   const int64_t total = P * groups;
@@ -400,8 +425,9 @@ __device__ __forceinline__ void reduce_groups_atomic(float (&acc)[NACC][8], int 
   }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(EW_THREADS)
-bn_stats_fin_kernel(const bf16* __restrict__ z, int64_t P, int c, double* __restrict__ gacc, unsigned* __restrict__ counter, BnFin fin) {
+bn_stats_fin_kernel(const T* __restrict__ z, int64_t P, int c, double* __restrict__ gacc, unsigned* __restrict__ counter, BnFin fin) {
   const int groups = c / 8;
   const int g = threadIdx.x % groups, pl = threadIdx.x / groups, lanes = EW_THREADS / groups;
   float acc[2][8];
@@ -420,10 +446,10 @@ bn_stats_fin_kernel(const bf16* __restrict__ z, int64_t P, int c, double* __rest
 
 // MASK: 0 = dy = dout, 1 = dy = dout * (mask_src > 0), 2 = dy = dout * (z*scale + shift > 0)  (the layer's own ReLU output
 // re-derived from z: saves reading the activation tensor)
-template <int MASK>
+template <int MASK, typename T>
 __global__ void __launch_bounds__(EW_THREADS)
-bn_bwd_reduce_fin_kernel(const bf16* __restrict__ dout, int dout_ctotal, int dout_coff, const bf16* __restrict__ mask_src,
-                         int mask_ctotal, int mask_coff, const bf16* __restrict__ z, int64_t P, int c,
+bn_bwd_reduce_fin_kernel(const T* __restrict__ dout, int dout_ctotal, int dout_coff, const T* __restrict__ mask_src,
+                         int mask_ctotal, int mask_coff, const T* __restrict__ z, int64_t P, int c,
                          const float* __restrict__ stats4, double* __restrict__ gacc, unsigned* __restrict__ counter, BnBwdFin fin) {
   const int groups = c / 8;
   const int g = threadIdx.x % groups, pl = threadIdx.x / groups, lanes = EW_THREADS / groups;
@@ -477,21 +503,27 @@ bn_bwd_reduce_fin_kernel(const bf16* __restrict__ dout, int dout_ctotal, int dou
   if (threadIdx.x == 0) *counter = 0u;
 }
 
-int bn_stats_finalize(const bf16* z, int64_t P, int c, const BnFin& fin, double* gacc, unsigned* counter, cudaStream_t s) {
+template <typename T>
+int bn_stats_finalize(const T* z, int64_t P, int c, const BnFin& fin, double* gacc, unsigned* counter, cudaStream_t s) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_stats: channel count");
-  DBB_LAUNCH(shaped("bn_stats_fin", P, c), s, bn_stats_fin_kernel<<<fit_grid(ew_blocks(P, c), DBB_RESIDENT(bn_stats_fin_kernel)), EW_THREADS, 0, s>>>(z, P, c, gacc, counter, fin));
+  DBB_LAUNCH(shaped("bn_stats_fin", P, c), s, bn_stats_fin_kernel<T><<<fit_grid(ew_blocks(P, c), DBB_RESIDENT(bn_stats_fin_kernel<T>)), EW_THREADS, 0, s>>>(z, P, c, gacc, counter, fin));
   return DBB_OK;
 }
-int bn_bwd_reduce_finalize(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
-                           const bf16* z, int64_t P, int c, const float* stats4, const BnBwdFin& fin, double* gacc,
+template int bn_stats_finalize<bf16>(const bf16*, int64_t, int, const BnFin&, double*, unsigned*, cudaStream_t);
+template int bn_stats_finalize<float>(const float*, int64_t, int, const BnFin&, double*, unsigned*, cudaStream_t);
+template <typename T>
+int bn_bwd_reduce_finalize(const T* dout, int dout_ctotal, int dout_coff, const ND<T>* mask_src, int mask_ctotal, int mask_coff,
+                           const ND<T>* z, int64_t P, int c, const float* stats4, const BnBwdFin& fin, double* gacc,
                            unsigned* counter, cudaStream_t s, int mask_self) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_bwd_reduce: channel count");
   const int want = ew_blocks(P, c);
-  if (mask_self) DBB_LAUNCH(shaped("bn_bwd_reduce_fin", P, c, 2), s, bn_bwd_reduce_fin_kernel<2><<<fit_grid(want, DBB_RESIDENT(bn_bwd_reduce_fin_kernel<2>)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, gacc, counter, fin));
-  else if (mask_src) DBB_LAUNCH(shaped("bn_bwd_reduce_fin", P, c, 1), s, bn_bwd_reduce_fin_kernel<1><<<fit_grid(want, DBB_RESIDENT(bn_bwd_reduce_fin_kernel<1>)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, gacc, counter, fin));
-  else DBB_LAUNCH(shaped("bn_bwd_reduce_fin", P, c, 0), s, bn_bwd_reduce_fin_kernel<0><<<fit_grid(want, DBB_RESIDENT(bn_bwd_reduce_fin_kernel<0>)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, gacc, counter, fin));
+  if (mask_self) DBB_LAUNCH(shaped("bn_bwd_reduce_fin", P, c, 2), s, bn_bwd_reduce_fin_kernel<2, T><<<fit_grid(want, DBB_RESIDENT((bn_bwd_reduce_fin_kernel<2, T>))), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, gacc, counter, fin));
+  else if (mask_src) DBB_LAUNCH(shaped("bn_bwd_reduce_fin", P, c, 1), s, bn_bwd_reduce_fin_kernel<1, T><<<fit_grid(want, DBB_RESIDENT((bn_bwd_reduce_fin_kernel<1, T>))), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, gacc, counter, fin));
+  else DBB_LAUNCH(shaped("bn_bwd_reduce_fin", P, c, 0), s, bn_bwd_reduce_fin_kernel<0, T><<<fit_grid(want, DBB_RESIDENT((bn_bwd_reduce_fin_kernel<0, T>))), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, gacc, counter, fin));
   return DBB_OK;
 }
+template int bn_bwd_reduce_finalize<bf16>(const bf16*, int, int, const bf16*, int, int, const bf16*, int64_t, int, const float*, const BnBwdFin&, double*, unsigned*, cudaStream_t, int);
+template int bn_bwd_reduce_finalize<float>(const float*, int, int, const float*, int, int, const float*, int64_t, int, const float*, const BnBwdFin&, double*, unsigned*, cudaStream_t, int);
 
 int bn_stats(const bf16* z, int64_t P, int c, float* partials, int* nblk, cudaStream_t s) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_stats: channel count");
@@ -514,12 +546,15 @@ static int stream_grid(int64_t total) {
   if (g > DBB_NUM_SMS * 16) g = DBB_NUM_SMS * 16;
   return (int)(g < 1 ? 1 : g);
 }
-int bn_apply(const bf16* z, int64_t P, int c, const float* stats4, const bf16* res, int relu, bf16* out, int out_ctotal,
+template <typename T>
+int bn_apply(const T* z, int64_t P, int c, const float* stats4, const ND<T>* res, int relu, ND<T>* out, int out_ctotal,
              int out_coff, cudaStream_t s) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_apply: channel count");
-  DBB_LAUNCH(shaped("bn_apply", P, c, res ? 1 : 0), s, bn_apply_kernel<<<fit_grid((P * (c / 8) + 2 * EW_THREADS - 1) / (2 * EW_THREADS), DBB_RESIDENT(bn_apply_kernel)), EW_THREADS, 0, s>>>(z, P, c, stats4, res, relu, out, out_ctotal, out_coff, ew_reverse()));
+  DBB_LAUNCH(shaped("bn_apply", P, c, res ? 1 : 0), s, bn_apply_kernel<T><<<fit_grid((P * (c / 8) + 2 * EW_THREADS - 1) / (2 * EW_THREADS), DBB_RESIDENT(bn_apply_kernel<T>)), EW_THREADS, 0, s>>>(z, P, c, stats4, res, relu, out, out_ctotal, out_coff, ew_reverse()));
   return DBB_OK;
 }
+template int bn_apply<bf16>(const bf16*, int64_t, int, const float*, const bf16*, int, bf16*, int, int, cudaStream_t);
+template int bn_apply<float>(const float*, int64_t, int, const float*, const float*, int, float*, int, int, cudaStream_t);
 int bn_bwd_reduce(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
                   const bf16* z, int64_t P, int c, const float* stats4, float* partials, int* nblk, cudaStream_t s) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_bwd_reduce: channel count");
@@ -532,16 +567,19 @@ int bn_bwd_finalize(const float* partials, int nblk, int c, int coff, int cn, in
   DBB_LAUNCH("bn_bwd_finalize", s, bn_bwd_finalize_kernel<<<(cn + 7) / 8, 256, 0, s>>>(partials, nblk, c, coff, cn, (double)count, gamma, stats4, dgamma, dbeta, coef3));
   return DBB_OK;
 }
-int bn_bwd_apply(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
-                 const bf16* z, int64_t P, int c, const float* stats4, const float* coef3, bf16* dz, bf16* dsum,
+template <typename T>
+int bn_bwd_apply(const T* dout, int dout_ctotal, int dout_coff, const ND<T>* mask_src, int mask_ctotal, int mask_coff,
+                 const ND<T>* z, int64_t P, int c, const float* stats4, const float* coef3, ND<T>* dz, ND<T>* dsum,
                  cudaStream_t s, int mask_self) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bn_bwd_apply: channel count");
   const int64_t want = (P * (c / 8) + 2 * EW_THREADS - 1) / (2 * EW_THREADS);
-  if (mask_self) DBB_LAUNCH(shaped("bn_bwd_apply", P, c, 2), s, bn_bwd_apply_kernel<2><<<fit_grid(want, DBB_RESIDENT(bn_bwd_apply_kernel<2>)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, coef3, dz, dsum, ew_reverse()));
-  else if (mask_src) DBB_LAUNCH(shaped("bn_bwd_apply", P, c, dsum ? 11 : 1), s, bn_bwd_apply_kernel<1><<<fit_grid(want, DBB_RESIDENT(bn_bwd_apply_kernel<1>)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, coef3, dz, dsum, ew_reverse()));
-  else DBB_LAUNCH(shaped("bn_bwd_apply", P, c, 0), s, bn_bwd_apply_kernel<0><<<fit_grid(want, DBB_RESIDENT(bn_bwd_apply_kernel<0>)), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, coef3, dz, dsum, ew_reverse()));
+  if (mask_self) DBB_LAUNCH(shaped("bn_bwd_apply", P, c, 2), s, bn_bwd_apply_kernel<2, T><<<fit_grid(want, DBB_RESIDENT((bn_bwd_apply_kernel<2, T>))), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, coef3, dz, dsum, ew_reverse()));
+  else if (mask_src) DBB_LAUNCH(shaped("bn_bwd_apply", P, c, dsum ? 11 : 1), s, bn_bwd_apply_kernel<1, T><<<fit_grid(want, DBB_RESIDENT((bn_bwd_apply_kernel<1, T>))), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, mask_src, mask_ctotal, mask_coff, z, P, c, stats4, coef3, dz, dsum, ew_reverse()));
+  else DBB_LAUNCH(shaped("bn_bwd_apply", P, c, 0), s, bn_bwd_apply_kernel<0, T><<<fit_grid(want, DBB_RESIDENT((bn_bwd_apply_kernel<0, T>))), EW_THREADS, 0, s>>>(dout, dout_ctotal, dout_coff, nullptr, 0, 0, z, P, c, stats4, coef3, dz, dsum, ew_reverse()));
   return DBB_OK;
 }
+template int bn_bwd_apply<bf16>(const bf16*, int, int, const bf16*, int, int, const bf16*, int64_t, int, const float*, const float*, bf16*, bf16*, cudaStream_t, int);
+template int bn_bwd_apply<float>(const float*, int, int, const float*, int, int, const float*, int64_t, int, const float*, const float*, float*, float*, cudaStream_t, int);
 int bias_grad(const bf16* dz, int64_t P, int c, float* partials, float* dbias, cudaStream_t s) {
   if (check_c(c)) return set_error(DBB_EUNSUPPORTED, "bias_grad: channel count");
   const int nblk = ew_blocks(P, c);
@@ -557,8 +595,9 @@ int bias_grad(const bf16* dz, int64_t P, int c, float* partials, float* dbias, c
 // fly -- the stem's BatchNorm-apply pass and its 210 MB activation tensor disappear (the backward re-derives the ReLU mask
 // from x, see bn_bwd_*_kernel<2>).  The values are rounded to bf16 before the comparison, so results are bit-identical
 // to pooling a materialised activation tensor.
-__global__ void __launch_bounds__(EW_THREADS) maxpool_fwd_kernel(const bf16* __restrict__ x, int n, int h, int w, int c, int oh, int ow,
-                                                                 bf16* __restrict__ y, uint8_t* __restrict__ argmax,
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) maxpool_fwd_kernel(const T* __restrict__ x, int n, int h, int w, int c, int oh, int ow,
+                                                                 T* __restrict__ y, uint8_t* __restrict__ argmax,
                                                                  const float* __restrict__ bn_stats4) {
   const int groups = c / 8;
   const int64_t total = (int64_t)n * oh * ow * groups;
@@ -583,7 +622,7 @@ __global__ void __launch_bounds__(EW_THREADS) maxpool_fwd_kernel(const bf16* __r
         if (bn_stats4) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            v.v[j] = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(v.v[j], bsc.v[j], bsh.v[j]), 0.f)));
+            v.v[j] = round_act<T>(fmaxf(fmaf(v.v[j], bsc.v[j], bsh.v[j]), 0.f));
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) if (v.v[j] > best.v[j]) { best.v[j] = v.v[j]; bi[j] = (uint8_t)(kh * 3 + kw); }
@@ -609,8 +648,9 @@ __device__ __forceinline__ void mp_take(F8& acc, const F8& d, const uint2& pk, u
     acc.v[j] += (idx == k) ? d.v[j] : 0.f;
   }
 }
-__global__ void __launch_bounds__(EW_THREADS) maxpool_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* __restrict__ argmax, int n, int h,
-                                                                 int w, int c, int oh, int ow, bf16* __restrict__ dx) {
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ argmax, int n, int h,
+                                                                 int w, int c, int oh, int ow, T* __restrict__ dx) {
   const int groups = c / 8;
   const int hb = (h + 1) / 2, wb = (w + 1) / 2;
   const int64_t total = (int64_t)n * hb * wb * groups;
@@ -641,7 +681,7 @@ __global__ void __launch_bounds__(EW_THREADS) maxpool_bwd_kernel(const bf16* __r
     mp_take(o10, d[0], pk[0], 7); mp_take(o10, d[2], pk[2], 1);
     mp_take(o11, d[0], pk[0], 8); mp_take(o11, d[1], pk[1], 6); mp_take(o11, d[2], pk[2], 2); mp_take(o11, d[3], pk[3], 0);
     const int yy = 2 * a, xx = 2 * b;
-    bf16* base = dx + (((int64_t)img * h + yy) * w + xx) * c + g * 8;
+    T* base = dx + (((int64_t)img * h + yy) * w + xx) * c + g * 8;
     st8(base, o00);
     if (xx + 1 < w) st8(base + c, o01);
     if (yy + 1 < h) {
@@ -652,17 +692,23 @@ __global__ void __launch_bounds__(EW_THREADS) maxpool_bwd_kernel(const bf16* __r
 }
 static int fits32(int64_t total, const char* who) { return total < ((int64_t)1 << 32) ? 0 : set_error(DBB_EUNSUPPORTED, who); }
 
-int maxpool_fwd(const bf16* x, int n, int h, int w, int c, bf16* y, uint8_t* argmax, cudaStream_t s, const float* bn_stats4) {
+template <typename T>
+int maxpool_fwd(const T* x, int n, int h, int w, int c, ND<T>* y, uint8_t* argmax, cudaStream_t s, const float* bn_stats4) {
   const int oh = (h + 2 - 3) / 2 + 1, ow = (w + 2 - 3) / 2 + 1;
   if (fits32((int64_t)n * h * w * (c / 8), "maxpool: tensor too large for 32-bit indexing")) return DBB_EUNSUPPORTED;
-  DBB_LAUNCH("maxpool_fwd", s, maxpool_fwd_kernel<<<fit_grid(((int64_t)n * oh * ow * (c / 8) + EW_THREADS - 1) / EW_THREADS, DBB_RESIDENT(maxpool_fwd_kernel)), EW_THREADS, 0, s>>>(x, n, h, w, c, oh, ow, y, argmax, bn_stats4));
+  DBB_LAUNCH("maxpool_fwd", s, maxpool_fwd_kernel<T><<<fit_grid(((int64_t)n * oh * ow * (c / 8) + EW_THREADS - 1) / EW_THREADS, DBB_RESIDENT(maxpool_fwd_kernel<T>)), EW_THREADS, 0, s>>>(x, n, h, w, c, oh, ow, y, argmax, bn_stats4));
   return DBB_OK;
 }
-int maxpool_bwd(const bf16* dy, const uint8_t* argmax, int n, int h, int w, int c, bf16* dx, cudaStream_t s) {
+template int maxpool_fwd<bf16>(const bf16*, int, int, int, int, bf16*, uint8_t*, cudaStream_t, const float*);
+template int maxpool_fwd<float>(const float*, int, int, int, int, float*, uint8_t*, cudaStream_t, const float*);
+template <typename T>
+int maxpool_bwd(const T* dy, const uint8_t* argmax, int n, int h, int w, int c, ND<T>* dx, cudaStream_t s) {
   const int oh = (h + 2 - 3) / 2 + 1, ow = (w + 2 - 3) / 2 + 1;
-  DBB_LAUNCH("maxpool_bwd", s, maxpool_bwd_kernel<<<fit_grid(((int64_t)n * ((h + 1) / 2) * ((w + 1) / 2) * (c / 8) + EW_THREADS - 1) / EW_THREADS, DBB_RESIDENT(maxpool_bwd_kernel)), EW_THREADS, 0, s>>>(dy, argmax, n, h, w, c, oh, ow, dx));
+  DBB_LAUNCH("maxpool_bwd", s, maxpool_bwd_kernel<T><<<fit_grid(((int64_t)n * ((h + 1) / 2) * ((w + 1) / 2) * (c / 8) + EW_THREADS - 1) / EW_THREADS, DBB_RESIDENT(maxpool_bwd_kernel<T>)), EW_THREADS, 0, s>>>(dy, argmax, n, h, w, c, oh, ow, dx));
   return DBB_OK;
 }
+template int maxpool_bwd<bf16>(const bf16*, const uint8_t*, int, int, int, int, bf16*, cudaStream_t);
+template int maxpool_bwd<float>(const float*, const uint8_t*, int, int, int, int, float*, cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------
 // nearest-neighbour upsampling, F.interpolate(mode='nearest'): src = min(floor(dst * fp32(in/out)), in-1)
@@ -671,9 +717,10 @@ __device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
   const int s = (int)floorf((float)dst * scale);
   return s < in_size - 1 ? s : in_size - 1;
 }
-__global__ void __launch_bounds__(EW_THREADS) upsample_fwd_kernel(const bf16* __restrict__ xs, int hs, int ws, float sch, float scw,
-                                                                  const bf16* __restrict__ addend, int n, int h, int w, int c,
-                                                                  bf16* __restrict__ dst, int dst_ctotal, int dst_coff) {
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) upsample_fwd_kernel(const T* __restrict__ xs, int hs, int ws, float sch, float scw,
+                                                                  const T* __restrict__ addend, int n, int h, int w, int c,
+                                                                  T* __restrict__ dst, int dst_ctotal, int dst_coff) {
   const int groups = c / 8;
   const int64_t total = (int64_t)n * h * w * groups;
   for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * EW_THREADS) {
@@ -691,8 +738,9 @@ __global__ void __launch_bounds__(EW_THREADS) upsample_fwd_kernel(const bf16* __
     st8(dst + pix * dst_ctotal + dst_coff + g * 8, v);
   }
 }
-__global__ void __launch_bounds__(EW_THREADS) upsample_bwd_kernel(const bf16* __restrict__ d_big, int big_ctotal, int big_coff, int n, int h,
-                                                                  int w, int c, float sch, float scw, bf16* __restrict__ d_xs,
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) upsample_bwd_kernel(const T* __restrict__ d_big, int big_ctotal, int big_coff, int n, int h,
+                                                                  int w, int c, float sch, float scw, T* __restrict__ d_xs,
                                                                   int hs, int ws, int accumulate) {
   const int groups = c / 8;
   const int64_t total = (int64_t)n * hs * ws * groups;
@@ -716,7 +764,7 @@ __global__ void __launch_bounds__(EW_THREADS) upsample_bwd_kernel(const bf16* __
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc.v[j] += d.v[j];
       }
-    bf16* o = d_xs + (((int64_t)b * hs + sy) * ws + sx) * c + g * 8;
+    T* o = d_xs + (((int64_t)b * hs + sy) * ws + sx) * c + g * 8;
     if (accumulate) {
       const F8 old = ld8(o);
 #pragma unroll
@@ -728,8 +776,9 @@ __global__ void __launch_bounds__(EW_THREADS) upsample_bwd_kernel(const bf16* __
 // c == 64 and a large ratio (FPN p4 / p5 -> p2 resolution): one WARP per source pixel, lane = (row-split rs, channel group g);
 // every lane sums the window rows y0 + rs, y0 + rs + 4, ... (128 contiguous bytes per row across the 8 groups) and the four
 // row-splits are combined by a fixed shuffle tree.
-__global__ void __launch_bounds__(EW_THREADS) upsample_bwd_warp_kernel(const bf16* __restrict__ d_big, int big_ctotal, int big_coff, int n, int h,
-                                                                       int w, float sch, float scw, bf16* __restrict__ d_xs,
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) upsample_bwd_warp_kernel(const T* __restrict__ d_big, int big_ctotal, int big_coff, int n, int h,
+                                                                       int w, float sch, float scw, T* __restrict__ d_xs,
                                                                        int hs, int ws, int accumulate) {
   const int lane = threadIdx.x & 31, g = lane & 7, rs = lane >> 3;
   const int total = n * hs * ws;
@@ -757,7 +806,7 @@ __global__ void __launch_bounds__(EW_THREADS) upsample_bwd_warp_kernel(const bf1
       acc.v[j] += __shfl_xor_sync(0xffffffffu, acc.v[j], 16);
     }
     if (rs == 0) {
-      bf16* o = d_xs + (((int64_t)b * hs + sy) * ws + sx) * 64 + g * 8;
+      T* o = d_xs + (((int64_t)b * hs + sy) * ws + sx) * 64 + g * 8;
       if (accumulate) {
         const F8 old = ld8(o);
 #pragma unroll
@@ -767,25 +816,34 @@ __global__ void __launch_bounds__(EW_THREADS) upsample_bwd_warp_kernel(const bf1
     }
   }
 }
-int upsample_add_fwd(const bf16* xs, int hs, int ws, const bf16* y, int n, int h, int w, int c, bf16* out, cudaStream_t s) {
-  DBB_LAUNCH("upsample_add_fwd", s, upsample_fwd_kernel<<<fit_grid(((int64_t)n * h * w * (c / 8) + EW_THREADS - 1) / EW_THREADS, DBB_RESIDENT(upsample_fwd_kernel)), EW_THREADS, 0, s>>>(xs, hs, ws, (float)hs / (float)h, (float)ws / (float)w, y, n, h, w, c, out, c, 0));
+template <typename T>
+int upsample_add_fwd(const T* xs, int hs, int ws, const ND<T>* y, int n, int h, int w, int c, ND<T>* out, cudaStream_t s) {
+  DBB_LAUNCH("upsample_add_fwd", s, upsample_fwd_kernel<T><<<fit_grid(((int64_t)n * h * w * (c / 8) + EW_THREADS - 1) / EW_THREADS, DBB_RESIDENT(upsample_fwd_kernel<T>)), EW_THREADS, 0, s>>>(xs, hs, ws, (float)hs / (float)h, (float)ws / (float)w, y, n, h, w, c, out, c, 0));
   return DBB_OK;
 }
-int upsample_into(const bf16* xs, int hs, int ws, int n, int h, int w, int c, bf16* dst, int dst_ctotal, int dst_coff, cudaStream_t s) {
-  DBB_LAUNCH("upsample_into", s, upsample_fwd_kernel<<<fit_grid(((int64_t)n * h * w * (c / 8) + EW_THREADS - 1) / EW_THREADS, DBB_RESIDENT(upsample_fwd_kernel)), EW_THREADS, 0, s>>>(xs, hs, ws, (float)hs / (float)h, (float)ws / (float)w, nullptr, n, h, w, c, dst, dst_ctotal, dst_coff));
+template int upsample_add_fwd<bf16>(const bf16*, int, int, const bf16*, int, int, int, int, bf16*, cudaStream_t);
+template int upsample_add_fwd<float>(const float*, int, int, const float*, int, int, int, int, float*, cudaStream_t);
+template <typename T>
+int upsample_into(const T* xs, int hs, int ws, int n, int h, int w, int c, ND<T>* dst, int dst_ctotal, int dst_coff, cudaStream_t s) {
+  DBB_LAUNCH("upsample_into", s, upsample_fwd_kernel<T><<<fit_grid(((int64_t)n * h * w * (c / 8) + EW_THREADS - 1) / EW_THREADS, DBB_RESIDENT(upsample_fwd_kernel<T>)), EW_THREADS, 0, s>>>(xs, hs, ws, (float)hs / (float)h, (float)ws / (float)w, nullptr, n, h, w, c, dst, dst_ctotal, dst_coff));
   return DBB_OK;
 }
-int upsample_bwd(const bf16* d_big, int big_ctotal, int big_coff, int n, int h, int w, int c, bf16* d_xs, int hs, int ws,
+template int upsample_into<bf16>(const bf16*, int, int, int, int, int, int, bf16*, int, int, cudaStream_t);
+template int upsample_into<float>(const float*, int, int, int, int, int, int, float*, int, int, cudaStream_t);
+template <typename T>
+int upsample_bwd(const T* d_big, int big_ctotal, int big_coff, int n, int h, int w, int c, ND<T>* d_xs, int hs, int ws,
                  int accumulate, cudaStream_t s) {
   if (c == 64 && h >= 4 * hs && (int64_t)n * hs * ws < (1 << 30)) {
     int grid = (n * hs * ws + EW_THREADS / 32 - 1) / (EW_THREADS / 32);
     if (grid > DBB_NUM_SMS * 16) grid = DBB_NUM_SMS * 16;
-    DBB_LAUNCH("upsample_bwd", s, upsample_bwd_warp_kernel<<<grid, EW_THREADS, 0, s>>>(d_big, big_ctotal, big_coff, n, h, w, (float)hs / (float)h, (float)ws / (float)w, d_xs, hs, ws, accumulate));
+    DBB_LAUNCH("upsample_bwd", s, upsample_bwd_warp_kernel<T><<<grid, EW_THREADS, 0, s>>>(d_big, big_ctotal, big_coff, n, h, w, (float)hs / (float)h, (float)ws / (float)w, d_xs, hs, ws, accumulate));
     return DBB_OK;
   }
-  DBB_LAUNCH("upsample_bwd", s, upsample_bwd_kernel<<<stream_grid((int64_t)n * hs * ws * (c / 8)), EW_THREADS, 0, s>>>(d_big, big_ctotal, big_coff, n, h, w, c, (float)hs / (float)h, (float)ws / (float)w, d_xs, hs, ws, accumulate));
+  DBB_LAUNCH("upsample_bwd", s, upsample_bwd_kernel<T><<<stream_grid((int64_t)n * hs * ws * (c / 8)), EW_THREADS, 0, s>>>(d_big, big_ctotal, big_coff, n, h, w, c, (float)hs / (float)h, (float)ws / (float)w, d_xs, hs, ws, accumulate));
   return DBB_OK;
 }
+template int upsample_bwd<bf16>(const bf16*, int, int, int, int, int, int, bf16*, int, int, int, cudaStream_t);
+template int upsample_bwd<float>(const float*, int, int, int, int, int, int, float*, int, int, int, cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------
 // conv1 staging: NCHW float32 image -> zero-padded space-to-depth bf16 [n][hs+3][ws+3][16]

@@ -6,8 +6,14 @@
 
 namespace dbb {
 
+// ND<T>: non-deduced pointer parameters (the first activation pointer of a call fixes T; nullptr is allowed for the rest).
+// T is bf16 (product path) or float (fp32-parity mode of the executor: same kernels, float activations).
+template <typename T> struct NdId { typedef T type; };
+template <typename T> using ND = typename NdId<T>::type;
+
 int nchw_f32_to_nhwc_bf16(const float* x, bf16* y, int n, int c, int64_t hw, cudaStream_t s);
 int nhwc_bf16_to_nchw_f32(const bf16* x, float* y, int n, int c, int64_t hw, cudaStream_t s);
+template <typename T> int nhwc_to_nchw_f32(const T* x, float* y, int n, int c, int64_t hw, cudaStream_t s);
 
 // ---- BatchNorm2d (eps 1e-5, momentum 0.1; src/modules/basic.py:34, resnet.py:74,83, segmentation_head.py:26,28,68,74)
 constexpr int BN_MAX_BLOCKS = DBB_NUM_SMS * 4;
@@ -26,12 +32,14 @@ int bn_finalize_eval(int c, int coff, int cn, const float* gamma, const float* b
 struct BnBwdFinSeg { const float* gamma; float* dgamma; float* dbeta; int coff, cn; };
 struct BnBwdFin { BnBwdFinSeg seg[2]; int nseg; float* coef3; };
 constexpr size_t BN_ACC_BYTES = 2 * 2048 * sizeof(double) + 256;
-int bn_stats_finalize(const bf16* z, int64_t P, int c, const BnFin& fin, double* gacc, unsigned* counter, cudaStream_t s);
-int bn_bwd_reduce_finalize(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
-                           const bf16* z, int64_t P, int c, const float* stats4, const BnBwdFin& fin, double* gacc,
+template <typename T> int bn_stats_finalize(const T* z, int64_t P, int c, const BnFin& fin, double* gacc, unsigned* counter, cudaStream_t s);
+template <typename T>
+int bn_bwd_reduce_finalize(const T* dout, int dout_ctotal, int dout_coff, const ND<T>* mask_src, int mask_ctotal, int mask_coff,
+                           const ND<T>* z, int64_t P, int c, const float* stats4, const BnBwdFin& fin, double* gacc,
                            unsigned* counter, cudaStream_t s, int mask_self = 0);
 // out = [relu](z*scale + shift [+ res])
-int bn_apply(const bf16* z, int64_t P, int c, const float* stats4, const bf16* res, int relu, bf16* out, int out_ctotal,
+template <typename T>
+int bn_apply(const T* z, int64_t P, int c, const float* stats4, const ND<T>* res, int relu, ND<T>* out, int out_ctotal,
              int out_coff, cudaStream_t s);
 // backward.  dy = dout * (mask_src > 0) if mask_src else dout;  mask_self = 1: dy = dout * (z*scale + shift > 0), i.e. the
 // layer's own ReLU output re-derived from z (mask_src ignored; one tensor read less).
@@ -41,24 +49,25 @@ int bn_bwd_reduce(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* 
 int bn_bwd_finalize(const float* partials, int nblk, int c, int coff, int cn, int64_t count, const float* gamma, const float* stats4,
                     float* dgamma, float* dbeta, float* coef3, cudaStream_t s);
 // dz = a*(dy - c1 - xhat*c2);  dsum (optional) receives dy (the ReLU-masked gradient, for the residual path)
-int bn_bwd_apply(const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask_src, int mask_ctotal, int mask_coff,
-                 const bf16* z, int64_t P, int c, const float* stats4, const float* coef3, bf16* dz, bf16* dsum,
+template <typename T>
+int bn_bwd_apply(const T* dout, int dout_ctotal, int dout_coff, const ND<T>* mask_src, int mask_ctotal, int mask_coff,
+                 const ND<T>* z, int64_t P, int c, const float* stats4, const float* coef3, ND<T>* dz, ND<T>* dsum,
                  cudaStream_t s, int mask_self = 0);
 // conv bias gradient: dbias[c] = sum_px dz[px, c]  (re-uses the bn partial buffers)
 int bias_grad(const bf16* dz, int64_t P, int c, float* partials, float* dbias, cudaStream_t s);
 
 // ---- MaxPool2d(3, 2, 1)  (src/modules/resnet.py:175,235)
 // bn_stats4 (optional): x is a raw conv output, pool bf16(relu(x*scale + shift)) computed on the fly (fused BatchNorm apply)
-int maxpool_fwd(const bf16* x, int n, int h, int w, int c, bf16* y, uint8_t* argmax, cudaStream_t s, const float* bn_stats4 = nullptr);
-int maxpool_bwd(const bf16* dy, const uint8_t* argmax, int n, int h, int w, int c, bf16* dx, cudaStream_t s);
+template <typename T> int maxpool_fwd(const T* x, int n, int h, int w, int c, ND<T>* y, uint8_t* argmax, cudaStream_t s, const float* bn_stats4 = nullptr);
+template <typename T> int maxpool_bwd(const T* dy, const uint8_t* argmax, int n, int h, int w, int c, ND<T>* dx, cudaStream_t s);
 
 // ---- FPN glue: F.interpolate(mode='nearest') (+ add / concat)  (src/modules/segmentation_body.py:79-87)
 // out[n,h,w,:] = y[n,h,w,:] + xs[n, src(h), src(w), :]
-int upsample_add_fwd(const bf16* xs, int hs, int ws, const bf16* y, int n, int h, int w, int c, bf16* out, cudaStream_t s);
+template <typename T> int upsample_add_fwd(const T* xs, int hs, int ws, const ND<T>* y, int n, int h, int w, int c, ND<T>* out, cudaStream_t s);
 // dst[n,h,w, coff:coff+c] = xs[n, src(h), src(w), :]
-int upsample_into(const bf16* xs, int hs, int ws, int n, int h, int w, int c, bf16* dst, int dst_ctotal, int dst_coff, cudaStream_t s);
+template <typename T> int upsample_into(const T* xs, int hs, int ws, int n, int h, int w, int c, ND<T>* dst, int dst_ctotal, int dst_coff, cudaStream_t s);
 // d_xs[n,hs,ws,:] (+)= sum over the destination pixels that read it of d_big[n,h,w, coff:coff+c]
-int upsample_bwd(const bf16* d_big, int big_ctotal, int big_coff, int n, int h, int w, int c, bf16* d_xs, int hs, int ws,
+template <typename T> int upsample_bwd(const T* d_big, int big_ctotal, int big_coff, int n, int h, int w, int c, ND<T>* d_xs, int hs, int ws,
                  int accumulate, cudaStream_t s);
 
 // ---- conv1 (7x7/2, 3->64) helpers: space-to-depth staging of the NCHW float32 image

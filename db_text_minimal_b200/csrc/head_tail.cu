@@ -79,6 +79,21 @@ __device__ __forceinline__ HtF8 ht_ld8(const bf16* p) {
   return r;
 }
 
+// fp32-parity storage: the same kernels on float activations (never staged: PIPE = false)
+__device__ __forceinline__ HtF8 ht_ld8(const float* p) {
+  const float4 a = ldg_stream(reinterpret_cast<const float4*>(p)), b = ldg_stream(reinterpret_cast<const float4*>(p + 4));
+  return HtF8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+__device__ __forceinline__ HtF8 ht_lds8(const float* p) { return ht_ld8(p); }
+__device__ __forceinline__ void ht_st8(bf16* p, const float (&o)[8]) {
+  uint4 u;
+  u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+  stg_stream(reinterpret_cast<uint4*>(p), u);
+}
+__device__ __forceinline__ void ht_st8(float* p, const float (&o)[8]) {
+  stg_stream(reinterpret_cast<float4*>(p), make_float4(o[0], o[1], o[2], o[3]));
+  stg_stream(reinterpret_cast<float4*>(p + 4), make_float4(o[4], o[5], o[6], o[7]));
+}
 __device__ __forceinline__ HtF8 ht_lds8(const bf16* p) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
   HtF8 r;
@@ -118,9 +133,9 @@ __device__ __forceinline__ void tile_coords(int64_t tile64, int tiles_per_row, i
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <bool PIPE>
+template <bool PIPE, typename T>
 __global__ void __launch_bounds__(HT_THREADS)
-head_tail_fwd_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w2, const float* __restrict__ stats4,
+head_tail_fwd_kernel(const T* __restrict__ zt, int n_img, int h2, int w2, const float* __restrict__ stats4,
                      const float* __restrict__ w2b, const float* __restrict__ w2t, const float* __restrict__ b2b,
                      const float* __restrict__ b2t, float k, int out_c, float* __restrict__ out) {
   __shared__ float zs[2][4][HT_TILE];   // [branch][tap][pixel] pre-sigmoid logits
@@ -133,20 +148,20 @@ head_tail_fwd_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w2, con
   const int tiles_per_row = (w2 + HT_TILE - 1) / HT_TILE;
   const int64_t ntiles = (int64_t)n_img * h2 * tiles_per_row;
   const int H = 2 * h2, W = 2 * w2;
-  const HtRing ring{ring_smem, full_bar, zt, tiles_per_row, h2, w2, ntiles};
+  const HtRing ring{ring_smem, full_bar, reinterpret_cast<const bf16*>(zt), tiles_per_row, h2, w2, ntiles};
   if (PIPE) ring.start();
   int64_t kk = 0;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++kk) {
     int n, i, j0;
     tile_coords(tile, tiles_per_row, h2, n, i, j0);
-    const bf16* zrow = PIPE ? ring.wait(kk) - (int64_t)j0 * 128 : zt + (((int64_t)n * h2 + i) * w2) * 128;
+    const T* zrow = PIPE ? reinterpret_cast<const T*>(ring.wait(kk)) - (int64_t)j0 * 128 : zt + (((int64_t)n * h2 + i) * w2) * 128;
     // ---- phase 1: BN + ReLU + 4 dot products per branch
 #pragma unroll
     for (int pass = 0; pass < HT_TILE / 16; ++pass) {
       const int px = pass * 16 + pslot;
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       if (j0 + px < w2) {
-        const bf16* zp = zrow + (int64_t)(j0 + px) * 128 + l16 * 8;
+        const T* zp = zrow + (int64_t)(j0 + px) * 128 + l16 * 8;
         const HtF8 z = PIPE ? ht_lds8(zp) : ht_ld8(zp);
         float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -227,9 +242,9 @@ __device__ __forceinline__ void bwd_phase_a_store(float (&dzs)[2][4][HT_TILE], c
 
 constexpr int HT_NACC = 6;   // per channel: dW2[4 taps], sum dy, sum dy*xhat
 
-template <bool PIPE>
+template <bool PIPE, typename T>
 __global__ void __launch_bounds__(HT_THREADS, 2)
-head_tail_bwd_reduce_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w2, const float* __restrict__ stats4,
+head_tail_bwd_reduce_kernel(const T* __restrict__ zt, int n_img, int h2, int w2, const float* __restrict__ stats4,
                             const float* __restrict__ w2b, const float* __restrict__ w2t, const float* __restrict__ out,
                             const float* __restrict__ dout, float k, float* __restrict__ partials /* [grid][128*6 + 2] */) {
   __shared__ float dzs[2][4][HT_TILE];
@@ -251,7 +266,7 @@ head_tail_bwd_reduce_kernel(const bf16* __restrict__ zt, int n_img, int h2, int 
   const int tiles_per_row = (w2 + HT_TILE - 1) / HT_TILE;
   const int64_t ntiles = (int64_t)n_img * h2 * tiles_per_row;
   const int H = 2 * h2, W = 2 * w2;
-  const HtRing ring{ring_smem, full_bar, zt, tiles_per_row, h2, w2, ntiles};
+  const HtRing ring{ring_smem, full_bar, reinterpret_cast<const bf16*>(zt), tiles_per_row, h2, w2, ntiles};
   if (PIPE) ring.start();
   int64_t kk = 0;
   PhaseAIn pa;
@@ -271,13 +286,13 @@ head_tail_bwd_reduce_kernel(const bf16* __restrict__ zt, int n_img, int h2, int 
       bwd_phase_a_load(pa, out, dout, n2, i2, j2, w2, H, W);
     }
     __syncthreads();
-    const bf16* zrow = PIPE ? ring.wait(kk) - (int64_t)j0 * 128 : zt + (((int64_t)n * h2 + i) * w2) * 128;
+    const T* zrow = PIPE ? reinterpret_cast<const T*>(ring.wait(kk)) - (int64_t)j0 * 128 : zt + (((int64_t)n * h2 + i) * w2) * 128;
     const int br = l16 >> 3;
 #pragma unroll
     for (int pass = 0; pass < HT_TILE / 16; ++pass) {
       const int px = pass * 16 + pslot;
       if (j0 + px < w2) {
-        const bf16* zp = zrow + (int64_t)(j0 + px) * 128 + l16 * 8;
+        const T* zp = zrow + (int64_t)(j0 + px) * 128 + l16 * 8;
         const HtF8 z = PIPE ? ht_lds8(zp) : ht_ld8(zp);
         float dz[4];
 #pragma unroll
@@ -370,11 +385,11 @@ __global__ void head_tail_bwd_finalize_kernel(const float* __restrict__ partials
   coef3[256 + ch] = (float)(acc[5] / count);
 }
 
-template <bool PIPE>
+template <bool PIPE, typename T>
 __global__ void __launch_bounds__(HT_THREADS)
-head_tail_bwd_apply_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w2, const float* __restrict__ stats4,
+head_tail_bwd_apply_kernel(const T* __restrict__ zt, int n_img, int h2, int w2, const float* __restrict__ stats4,
                            const float* __restrict__ coef3, const float* __restrict__ w2b, const float* __restrict__ w2t,
-                           const float* __restrict__ out, const float* __restrict__ dout, float k, bf16* __restrict__ d_zt) {
+                           const float* __restrict__ out, const float* __restrict__ dout, float k, T* __restrict__ d_zt) {
   __shared__ float dzs[2][4][HT_TILE];
   __shared__ uint64_t full_bar[HT_STAGES];
   extern __shared__ __align__(128) uint8_t ring_smem[];
@@ -393,7 +408,7 @@ head_tail_bwd_apply_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w
   const int tiles_per_row = (w2 + HT_TILE - 1) / HT_TILE;
   const int64_t ntiles = (int64_t)n_img * h2 * tiles_per_row;
   const int H = 2 * h2, W = 2 * w2;
-  const HtRing ring{ring_smem, full_bar, zt, tiles_per_row, h2, w2, ntiles};
+  const HtRing ring{ring_smem, full_bar, reinterpret_cast<const bf16*>(zt), tiles_per_row, h2, w2, ntiles};
   if (PIPE) ring.start();
   int64_t kk = 0;
   PhaseAIn pa;
@@ -414,7 +429,7 @@ head_tail_bwd_apply_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w
     }
     __syncthreads();
     const int64_t rowoff = (((int64_t)n * h2 + i) * w2) * 128;
-    const bf16* ztile = PIPE ? ring.wait(kk) : nullptr;
+    const T* ztile = PIPE ? reinterpret_cast<const T*>(ring.wait(kk)) : nullptr;
     const int br = l16 >> 3;
 #pragma unroll
     for (int pass = 0; pass < HT_TILE / 16; ++pass) {
@@ -435,9 +450,7 @@ head_tail_bwd_apply_kernel(const bf16* __restrict__ zt, int n_img, int h2, int w
           const float dy = a > 0.f ? da : 0.f;
           o[j] = ca[j] * (dy - c1[j] - (z.v[j] - mean[j]) * inv[j] * c2[j]);
         }
-        uint4 u;
-        u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
-        stg_stream(reinterpret_cast<uint4*>(d_zt + off), u);
+        ht_st8(d_zt + off, o);
       }
     }
     __syncthreads();
@@ -467,29 +480,32 @@ static int ht_reduce_grid(int n, int h2, int w2) {
 }
 
 static int ht_fwd_ctas() { static const int v = getenv("DBB_HT_FWD_CTAS") ? atoi(getenv("DBB_HT_FWD_CTAS")) : 3; return v; }   // 80 regs, 66 KB: 3 fit
-int head_tail_fwd(const bf16* zt, int n, int h2, int w2, const float* stats4, const float* w2b, const float* w2t,
+template <typename T> constexpr bool ht_can_pipe() { return sizeof(T) == 2; }     // the bulk-copy ring stages 16 KB bf16 tiles
+template <typename T>
+int head_tail_fwd(const T* zt, int n, int h2, int w2, const float* stats4, const float* w2b, const float* w2t,
                   const float* b2b, const float* b2t, float k, int out_c, float* out, cudaStream_t s) {
-  if (w2 % HT_TILE == 0) {
+  if (ht_can_pipe<T>() && w2 % HT_TILE == 0) {
     static bool attr = false;
-    if (!attr) { DBB_CUDA(cudaFuncSetAttribute(head_tail_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_RING_BYTES)); attr = true; }
-    DBB_LAUNCH("head_tail_fwd", s, head_tail_fwd_kernel<true><<<ht_pipe_grid(n, h2, w2, ht_fwd_ctas()), HT_THREADS, HT_RING_BYTES, s>>>(zt, n, h2, w2, stats4, w2b, w2t, b2b, b2t, k, out_c, out));
+    if (!attr) { DBB_CUDA(cudaFuncSetAttribute(head_tail_fwd_kernel<true, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_RING_BYTES)); attr = true; }
+    DBB_LAUNCH("head_tail_fwd", s, head_tail_fwd_kernel<true, bf16><<<ht_pipe_grid(n, h2, w2, ht_fwd_ctas()), HT_THREADS, HT_RING_BYTES, s>>>(reinterpret_cast<const bf16*>(zt), n, h2, w2, stats4, w2b, w2t, b2b, b2t, k, out_c, out));
     return DBB_OK;
   }
-  DBB_LAUNCH("head_tail_fwd", s, head_tail_fwd_kernel<false><<<ht_grid(n, h2, w2), HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, w2b, w2t, b2b, b2t, k, out_c, out));
+  DBB_LAUNCH("head_tail_fwd", s, head_tail_fwd_kernel<false, T><<<ht_grid(n, h2, w2), HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, w2b, w2t, b2b, b2t, k, out_c, out));
   return DBB_OK;
 }
-int head_tail_bwd_reduce(const bf16* zt, int n, int h2, int w2, const float* stats4, const float* w2b, const float* w2t,
+template <typename T>
+int head_tail_bwd_reduce(const T* zt, int n, int h2, int w2, const float* stats4, const float* w2b, const float* w2t,
                          const float* out, const float* dout, float k, float* partials, int* nblk, cudaStream_t s) {
   *nblk = ht_reduce_grid(n, h2, w2);
-  if (w2 % HT_TILE == 0) {
+  if (ht_can_pipe<T>() && w2 % HT_TILE == 0) {
     static bool attr = false;
-    if (!attr) { DBB_CUDA(cudaFuncSetAttribute(head_tail_bwd_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_RING_BYTES)); attr = true; }
+    if (!attr) { DBB_CUDA(cudaFuncSetAttribute(head_tail_bwd_reduce_kernel<true, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_RING_BYTES)); attr = true; }
     const int g = ht_pipe_grid(n, h2, w2, 2);      // 2 CTAs/SM (launch bound caps the kernel at 128 registers)
     *nblk = g < *nblk ? g : *nblk;
-    DBB_LAUNCH("head_tail_bwd_reduce", s, head_tail_bwd_reduce_kernel<true><<<*nblk, HT_THREADS, HT_RING_BYTES, s>>>(zt, n, h2, w2, stats4, w2b, w2t, out, dout, k, partials));
+    DBB_LAUNCH("head_tail_bwd_reduce", s, head_tail_bwd_reduce_kernel<true, bf16><<<*nblk, HT_THREADS, HT_RING_BYTES, s>>>(reinterpret_cast<const bf16*>(zt), n, h2, w2, stats4, w2b, w2t, out, dout, k, partials));
     return DBB_OK;
   }
-  DBB_LAUNCH("head_tail_bwd_reduce", s, head_tail_bwd_reduce_kernel<false><<<*nblk, HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, w2b, w2t, out, dout, k, partials));
+  DBB_LAUNCH("head_tail_bwd_reduce", s, head_tail_bwd_reduce_kernel<false, T><<<*nblk, HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, w2b, w2t, out, dout, k, partials));
   return DBB_OK;
 }
 int head_tail_bwd_finalize(const float* partials, int nblk, int64_t count, const float* gamma_b, const float* gamma_t,
@@ -499,16 +515,23 @@ int head_tail_bwd_finalize(const float* partials, int nblk, int64_t count, const
                                                   dgamma_t, dbeta_t, coef3, dw2b, dw2t, db2b, db2t));
   return DBB_OK;
 }
-int head_tail_bwd_apply(const bf16* zt, int n, int h2, int w2, const float* stats4, const float* coef3, const float* w2b,
-                        const float* w2t, const float* out, const float* dout, float k, bf16* d_zt, cudaStream_t s) {
-  if (w2 % HT_TILE == 0) {
+template <typename T>
+int head_tail_bwd_apply(const T* zt, int n, int h2, int w2, const float* stats4, const float* coef3, const float* w2b,
+                        const float* w2t, const float* out, const float* dout, float k, ND<T>* d_zt, cudaStream_t s) {
+  if (ht_can_pipe<T>() && w2 % HT_TILE == 0) {
     static bool attr = false;
-    if (!attr) { DBB_CUDA(cudaFuncSetAttribute(head_tail_bwd_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_RING_BYTES)); attr = true; }
-    DBB_LAUNCH("head_tail_bwd_apply", s, head_tail_bwd_apply_kernel<true><<<ht_pipe_grid(n, h2, w2, 2), HT_THREADS, HT_RING_BYTES, s>>>(zt, n, h2, w2, stats4, coef3, w2b, w2t, out, dout, k, d_zt));
+    if (!attr) { DBB_CUDA(cudaFuncSetAttribute(head_tail_bwd_apply_kernel<true, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_RING_BYTES)); attr = true; }
+    DBB_LAUNCH("head_tail_bwd_apply", s, head_tail_bwd_apply_kernel<true, bf16><<<ht_pipe_grid(n, h2, w2, 2), HT_THREADS, HT_RING_BYTES, s>>>(reinterpret_cast<const bf16*>(zt), n, h2, w2, stats4, coef3, w2b, w2t, out, dout, k, reinterpret_cast<bf16*>(d_zt)));
     return DBB_OK;
   }
-  DBB_LAUNCH("head_tail_bwd_apply", s, head_tail_bwd_apply_kernel<false><<<ht_grid(n, h2, w2), HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, coef3, w2b, w2t, out, dout, k, d_zt));
+  DBB_LAUNCH("head_tail_bwd_apply", s, head_tail_bwd_apply_kernel<false, T><<<ht_grid(n, h2, w2), HT_THREADS, 0, s>>>(zt, n, h2, w2, stats4, coef3, w2b, w2t, out, dout, k, d_zt));
   return DBB_OK;
 }
+#define DBB_HT_INST(T) \
+  template int head_tail_fwd<T>(const T*, int, int, int, const float*, const float*, const float*, const float*, const float*, float, int, float*, cudaStream_t); \
+  template int head_tail_bwd_reduce<T>(const T*, int, int, int, const float*, const float*, const float*, const float*, const float*, float, float*, int*, cudaStream_t); \
+  template int head_tail_bwd_apply<T>(const T*, int, int, int, const float*, const float*, const float*, const float*, const float*, const float*, float, T*, cudaStream_t);
+DBB_HT_INST(bf16)
+DBB_HT_INST(float)
 
 }  // namespace dbb

@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <type_traits>
 
 namespace dbb {
 
@@ -96,6 +97,8 @@ using namespace dbb;
 
 struct DbbNet {
   int n, h, w, training;
+  int fp32 = 0;                          // DBB_PRECISION_FP32: float activations + CUDA-core convolutions (parity mode)
+  size_t esz = sizeof(bf16);             // bytes per activation element
   int h1, w1, h2, w2, hh[4], ww[4];      // conv1 out, pool out (= c2), c2..c5 extents
   int ho, wo;                            // head output extent (4*h2, 4*w2)
   size_t ws_bytes = 0;
@@ -158,24 +161,27 @@ static void setup_convbn(DbbNet* net, ConvBN& L, const std::string& conv, const 
   const size_t wbytes = (size_t)cin * cout * ks * ks * sizeof(bf16);
   L.wp = net->alloc(wbytes);
   if (net->training && need_dgrad) L.wpt = net->alloc(wbytes);
-  L.z = net->alloc((size_t)L.P() * cout * sizeof(bf16));
+  L.z = net->alloc((size_t)L.P() * cout * net->esz);
   L.stats = net->alloc(4 * cout * sizeof(float));
   if (net->training) {
     L.coef = net->alloc(3 * cout * sizeof(float));
-    L.dz = net->alloc((size_t)L.P() * cout * sizeof(bf16));
+    L.dz = net->alloc((size_t)L.P() * cout * net->esz);
   }
   net->flops_fwd += 2ull * (uint64_t)L.P() * cout * cin * ks * ks;
 }
 
-extern "C" DbbNet* dbb_net_create(int64_t n, int64_t h, int64_t w, int training) {
+extern "C" DbbNet* dbb_net_create_ex(int64_t n, int64_t h, int64_t w, int training, int precision) {
   build_tables();
   if (n <= 0 || h < 32 || w < 32) { set_error(DBB_EINVAL, "net_create: need n >= 1 and h, w >= 32"); return nullptr; }
+  if (precision != DBB_PRECISION_BF16 && precision != DBB_PRECISION_FP32) { set_error(DBB_EINVAL, "net_create: unknown precision"); return nullptr; }
   DbbNet* net = new DbbNet();
   net->n = (int)n; net->h = (int)h; net->w = (int)w; net->training = training ? 1 : 0;
+  net->fp32 = precision == DBB_PRECISION_FP32;
+  net->esz = net->fp32 ? sizeof(float) : sizeof(bf16);
   net->out_c = training ? 3 : 2;
   const int N = (int)n;
   const bool T = net->training;
-  auto act_bytes = [&](int hh, int ww, int c) { return (size_t)N * hh * ww * c * sizeof(bf16); };
+  auto act_bytes = [&](int hh, int ww, int c) { return (size_t)N * hh * ww * c * net->esz; };
   // ---- stem
   net->h1 = ((int)h + 1) / 2; net->w1 = ((int)w + 1) / 2;                 // conv 7x7/2 pad 3
   net->h2 = (net->h1 + 2 - 3) / 2 + 1; net->w2 = (net->w1 + 2 - 3) / 2 + 1;   // maxpool 3/2 pad 1
@@ -248,7 +254,7 @@ extern "C" DbbNet* dbb_net_create(int64_t n, int64_t h, int64_t w, int training)
   // ---- head: the two 3x3 convs share their input -> one 256->128 GEMM; the two ConvT(64,64,2,2) write one 128-wide tensor
   net->hconv_g = ConvGeom{N, hf, wf, 256, 128, 3, 1, 1};
   net->tconv_g = ConvGeom{N, hf, wf, 64, 64, 2, 2, 0};
-  net->wp_h = net->alloc(128 * 256 * 9 * sizeof(bf16));
+  net->wp_h = net->alloc(128 * 256 * 9 * net->esz);      // fp32 mode: the two OIHW tensors side by side
   net->bias_h = net->alloc(128 * sizeof(float));
   net->zh = net->alloc(act_bytes(hf, wf, 128));
   net->stats_h = net->alloc(4 * 128 * sizeof(float));
@@ -281,6 +287,11 @@ extern "C" DbbNet* dbb_net_create(int64_t n, int64_t h, int64_t w, int training)
   return net;
 }
 
+extern "C" DbbNet* dbb_net_create(int64_t n, int64_t h, int64_t w, int training) {
+  return dbb_net_create_ex(n, h, w, training, DBB_PRECISION_BF16);
+}
+extern "C" int dbb_net_precision(const DbbNet* net) { return net ? (net->fp32 ? DBB_PRECISION_FP32 : DBB_PRECISION_BF16) : -1; }
+
 extern "C" void dbb_net_destroy(DbbNet* net) {
   if (!net) return;
   if (net->ev_fork) cudaEventDestroy(net->ev_fork);
@@ -303,6 +314,7 @@ namespace {
 
 constexpr float BN_EPS = 1e-5f, BN_MOM = 0.1f, STEP_K = 50.f;
 
+template <typename T>
 struct Ctx {
   DbbNet* net;
   char* base;
@@ -311,13 +323,13 @@ struct Ctx {
   float* const* grads;
   cudaStream_t s;
   cudaStream_t sw;        // weight-gradient stream (== s when the side stream is disabled)
-  template <typename T = bf16> T* p(const Buf& b) const { return reinterpret_cast<T*>(base + b.off); }
+  template <typename U = T> U* p(const Buf& b) const { return reinterpret_cast<U*>(base + b.off); }
   const float* par(int i) const { return i >= 0 ? params[i] : nullptr; }
   float* buf(int i) const { return (i >= 0 && buffers) ? buffers[i] : nullptr; }
   float* grad(int i) const { return (i >= 0 && grads) ? grads[i] : nullptr; }
   float* partials() const { return p<float>(net->partials); }
   float* wgs() const { return p<float>(net->wg_scratch); }
-  double* acc() const { return p<double>(net->bn_acc); }
+  double* acc() const { return this->template p<double>(net->bn_acc); }
   unsigned* ticket() const { return reinterpret_cast<unsigned*>(base + net->bn_acc.off + 2 * 2048 * sizeof(double)); }
 };
 
@@ -346,13 +358,15 @@ cudaStream_t side_stream(DbbNet* net, cudaStream_t stream) {
 }
 
 // fork: work enqueued on c.sw from here on sees everything enqueued on c.s so far; join: the reverse
-int fork_w(const Ctx& c) {
+template <typename T>
+int fork_w(const Ctx<T>& c) {
   if (c.sw == c.s) return 0;
   DBB_CUDA(cudaEventRecord(c.net->ev_fork, c.s));
   DBB_CUDA(cudaStreamWaitEvent(c.sw, c.net->ev_fork, 0));
   return 0;
 }
-int join_w(const Ctx& c) {
+template <typename T>
+int join_w(const Ctx<T>& c) {
   if (c.sw == c.s) return 0;
   DBB_CUDA(cudaEventRecord(c.net->ev_join, c.sw));
   DBB_CUDA(cudaStreamWaitEvent(c.s, c.net->ev_join, 0));
@@ -362,7 +376,8 @@ int join_w(const Ctx& c) {
 // BatchNorm statistics of a raw conv output (training: one fused reduce+finalize launch) or running statistics (eval)
 // -> stats4.  nseg = 2 for the 128-channel head tensors that carry two BatchNorm layers side by side.
 struct BnIdx { int gamma, beta, rm, rv; };
-int bn_prepare(const Ctx& c, const bf16* z, int64_t Pn, int ch, int nseg, const BnIdx* ix, float* stats4) {
+template <typename T>
+int bn_prepare(const Ctx<T>& c, const ND<T>* z, int64_t Pn, int ch, int nseg, const BnIdx* ix, float* stats4) {
   const int cn = ch / nseg;
   if (c.net->training) {
     BnFin fin;
@@ -379,9 +394,10 @@ int bn_prepare(const Ctx& c, const bf16* z, int64_t Pn, int ch, int nseg, const 
 // Training mode: the statistics ride in the producing convolution's epilogue (ConvStats) and no separate pass is
 // launched.  Returns the descriptor to hand to conv_fprop, or nullptr (eval mode / DBB_NO_FUSED_STATS) in which case
 // the caller runs bn_prepare after the convolution.  Segment i covers channels [coff0 + i*cn, +cn) of the y tensor.
-const ConvStats* bn_fused(const Ctx& c, ConvStats& st, int cn, int nseg, const BnIdx* ix, float* stats4, int coff0 = 0) {
+template <typename T>
+const ConvStats* bn_fused(const Ctx<T>& c, ConvStats& st, int cn, int nseg, const BnIdx* ix, float* stats4, int coff0 = 0) {
   static const bool off = getenv("DBB_NO_FUSED_STATS") != nullptr;     // A/B switch
-  if (!c.net->training || off) return nullptr;
+  if (!c.net->training || off || c.net->fp32) return nullptr;
   memset(&st, 0, sizeof(st));
   st.enabled = 1; st.gacc = c.acc(); st.counter = c.ticket();
   st.fin.nseg = nseg; st.fin.momentum = BN_MOM; st.fin.eps = BN_EPS; st.fin.stats4 = stats4;
@@ -389,22 +405,39 @@ const ConvStats* bn_fused(const Ctx& c, ConvStats& st, int cn, int nseg, const B
     st.fin.seg[i] = BnFinSeg{c.par(ix[i].gamma), c.par(ix[i].beta), c.buf(ix[i].rm), c.buf(ix[i].rv), coff0 + i * cn, cn};
   return &st;
 }
-int bn_prepare(const Ctx& c, const bf16* z, int64_t Pn, int ch, int gamma, int beta, int rm, int rv, float* stats4) {
+template <typename T>
+int bn_prepare(const Ctx<T>& c, const ND<T>* z, int64_t Pn, int ch, int gamma, int beta, int rm, int rv, float* stats4) {
   const BnIdx ix{gamma, beta, rm, rv};
   return bn_prepare(c, z, Pn, ch, 1, &ix, stats4);
 }
 
-// every weight tensor -> its bf16 GEMM operand(s), in one or two launches at the start of the forward pass
+// every weight tensor -> its T GEMM operand(s), in one or two launches at the start of the forward pass
 // (fprop layout always; the transposed dgrad layout too in training mode, so backward launches no packing at all)
 // stage 0: the stem weights, on the caller's stream; stage 1: everything else, on the side stream (it runs next to
 // image_to_s2d / conv1 / max-pool and is joined before layer1)
-int pack_all(const Ctx& c, int stage) {
+// weight operand of a convolution: the packed bf16 GEMM matrix (product path) or the raw float32 parameter (fp32 mode)
+inline const bf16* wsel(const Ctx<bf16>& c, const Buf& packed, int) { return c.p(packed); }
+inline const float* wsel(const Ctx<float>& c, const Buf&, int param) { return c.par(param); }
+
+template <typename T>
+int pack_all(const Ctx<T>& c, int stage) {
   DbbNet* net = c.net;
+  if constexpr (std::is_same<T, float>::value) {
+    // fp32 mode: convolutions read the parameters directly; only the two head 3x3 weights are laid side by side
+    // (one 256 -> 128 convolution for both branches, as on the product path)
+    if (stage == 0) return 0;
+    const size_t half = (size_t)64 * 256 * 9;
+    for (int br = 0; br < 2; ++br) {
+      const std::string pre = std::string("segmentation_head.") + (br ? "thresh" : "binarize");
+      DBB_CUDA(cudaMemcpyAsync(c.p(net->wp_h) + br * half, c.par(P(pre + ".0.weight")), half * sizeof(float), cudaMemcpyDeviceToDevice, c.sw));
+    }
+    return 0;
+  } else {
   PackBatch b;
   b.njobs = 0;
   cudaStream_t ps = stage == 0 ? c.s : c.sw;
   auto flush = [&]() -> int { int rc = pack_weights_batch(b, ps); b.njobs = 0; return rc; };
-  auto add = [&](int mode, const float* w, bf16* out, int co, int ci, int ks, int co_total, int co_off, bf16* out2 = nullptr) -> int {
+  auto add = [&](int mode, const float* w, T* out, int co, int ci, int ks, int co_total, int co_off, T* out2 = nullptr) -> int {
     if (b.njobs == PACK_BATCH) RC(flush());
     b.jobs[b.njobs++] = PackJob{w, out, mode, co, ci, ks, ks, co_total > 0 ? co_total : co, co_off, out2};
     return 0;
@@ -431,32 +464,38 @@ int pack_all(const Ctx& c, int stage) {
     if (net->training) RC(add(3, c.par(P(pre + ".3.weight")), c.p(net->wpt_t[br]), 64, 64, 2, 0, 0));
   }
   return flush();
+  }
 }
 
-int convbn_fwd(const Ctx& c, ConvBN& L, const bf16* x, int x_ctotal, int x_coff) {
+template <typename T>
+int convbn_fwd(const Ctx<T>& c, ConvBN& L, const ND<T>* x, int x_ctotal, int x_coff) {
   const BnIdx ix{L.gamma, L.beta, L.rm, L.rv};
   ConvStats st;
-  const ConvStats* fused = bn_fused(c, st, L.g.cout, 1, &ix, c.p<float>(L.stats));
-  RC(conv_fprop(L.g, x, x_ctotal, x_coff, c.p(L.wp), c.par(L.b), c.p(L.z), L.g.cout, 0, c.s, fused));
-  if (!fused) RC(bn_prepare(c, c.p(L.z), L.P(), L.g.cout, 1, &ix, c.p<float>(L.stats)));
+  const ConvStats* fused = bn_fused(c, st, L.g.cout, 1, &ix, c.template p<float>(L.stats));
+  RC(conv_fprop(L.g, x, x_ctotal, x_coff, wsel(c, L.wp, L.w), c.par(L.b), c.p(L.z), L.g.cout, 0, c.s, fused));
+  if (!fused) RC(bn_prepare(c, c.p(L.z), L.P(), L.g.cout, 1, &ix, c.template p<float>(L.stats)));
   return 0;
 }
 
 // conv -> BatchNorm -> [+ res] -> [ReLU] -> out.  Training: raw output z + fused statistics, then one apply pass.
 // Inference: the fixed-statistics BatchNorm, the residual add and the ReLU run in the convolution's epilogue on the fp32
 // accumulator (ConvEpi): no z tensor, no apply pass.
-int convbn_act_fwd(const Ctx& c, ConvBN& L, const bf16* x, int x_ctotal, int x_coff, const bf16* res, int relu, bf16* out,
+template <typename T>
+int convbn_act_fwd(const Ctx<T>& c, ConvBN& L, const ND<T>* x, int x_ctotal, int x_coff, const ND<T>* res, int relu, ND<T>* out,
                    int out_ctotal, int out_coff) {
   static const bool no_epi = getenv("DBB_NO_EVAL_EPILOGUE") != nullptr;     // A/B switch
   const int ch = L.g.cout;
-  if (c.net->training || no_epi) {
+  if (c.net->training || no_epi || c.net->fp32) {
     RC(convbn_fwd(c, L, x, x_ctotal, x_coff));
-    return bn_apply(c.p(L.z), L.P(), ch, c.p<float>(L.stats), res, relu, out, out_ctotal, out_coff, c.s);
+    return bn_apply(c.p(L.z), L.P(), ch, c.template p<float>(L.stats), res, relu, out, out_ctotal, out_coff, c.s);
   }
-  float* stats4 = c.p<float>(L.stats);
-  RC(bn_finalize_eval(ch, 0, ch, c.par(L.gamma), c.par(L.beta), c.buf(L.rm), c.buf(L.rv), BN_EPS, stats4, c.s));
-  const ConvEpi epi{stats4, stats4 + ch, res, relu};
-  return conv_fprop(L.g, x, x_ctotal, x_coff, c.p(L.wp), c.par(L.b), out, out_ctotal, out_coff, c.s, nullptr, &epi);
+  if constexpr (std::is_same<T, bf16>::value) {
+    float* stats4 = c.template p<float>(L.stats);
+    RC(bn_finalize_eval(ch, 0, ch, c.par(L.gamma), c.par(L.beta), c.buf(L.rm), c.buf(L.rv), BN_EPS, stats4, c.s));
+    const ConvEpi epi{stats4, stats4 + ch, res, relu};
+    return conv_fprop(L.g, x, x_ctotal, x_coff, wsel(c, L.wp, L.w), c.par(L.b), out, out_ctotal, out_coff, c.s, nullptr, &epi);
+  }
+  return DBB_OK;
 }
 
 // backward through BN (+ReLU mask) and the conv: dout -> dz -> (dW, dbias, dx)
@@ -464,22 +503,23 @@ static bool wgrad_fork_late() { static const bool v = getenv("DBB_WGRAD_FORK_LAT
 static int self_mask() { static const int v = getenv("DBB_NO_SELF_MASK") ? 0 : 1; return v; }    // A/B switch
 
 // mask_self: the ReLU mask is this layer's own output (no residual in between) -> re-derived from z instead of read
-int convbn_bwd(const Ctx& c, ConvBN& L, const bf16* dout, int dout_ctotal, int dout_coff, const bf16* mask, int mask_ctotal,
-               int mask_coff, const bf16* x, int x_ctotal, int x_coff, bf16* dx, int dx_accumulate, bf16* dsum, int mask_self = 0) {
+template <typename T>
+int convbn_bwd(const Ctx<T>& c, ConvBN& L, const ND<T>* dout, int dout_ctotal, int dout_coff, const ND<T>* mask, int mask_ctotal,
+               int mask_coff, const ND<T>* x, int x_ctotal, int x_coff, ND<T>* dx, int dx_accumulate, ND<T>* dsum, int mask_self = 0) {
   mask_self = mask_self && self_mask();
   const int64_t Pn = L.P();
   const int ch = L.g.cout;
   BnBwdFin fin;
-  fin.nseg = 1; fin.coef3 = c.p<float>(L.coef);
+  fin.nseg = 1; fin.coef3 = c.template p<float>(L.coef);
   fin.seg[0] = BnBwdFinSeg{c.par(L.gamma), c.grad(L.gamma), c.grad(L.beta), 0, ch};
-  RC(bn_bwd_reduce_finalize(dout, dout_ctotal, dout_coff, mask, mask_ctotal, mask_coff, c.p(L.z), Pn, ch, c.p<float>(L.stats), fin, c.acc(), c.ticket(), c.s, mask_self));
-  RC(bn_bwd_apply(dout, dout_ctotal, dout_coff, mask, mask_ctotal, mask_coff, c.p(L.z), Pn, ch, c.p<float>(L.stats), c.p<float>(L.coef), c.p(L.dz), dsum, c.s, mask_self));
+  RC(bn_bwd_reduce_finalize(dout, dout_ctotal, dout_coff, mask, mask_ctotal, mask_coff, c.p(L.z), Pn, ch, c.template p<float>(L.stats), fin, c.acc(), c.ticket(), c.s, mask_self));
+  RC(bn_bwd_apply(dout, dout_ctotal, dout_coff, mask, mask_ctotal, mask_coff, c.p(L.z), Pn, ch, c.template p<float>(L.stats), c.template p<float>(L.coef), c.p(L.dz), dsum, c.s, mask_self));
   // The weight gradient goes to the side stream as soon as dz is complete (measured: forking before the data gradient,
   // 7.85-7.92 ms/step, beats forking after it, 8.03; without the side stream 8.31).
   const bool fork_late = wgrad_fork_late();
   if (!fork_late) RC(fork_w(c));
   if (dx) {
-    RC(conv_dgrad(L.g, c.p(L.dz), c.p(L.wpt), dx, c.s, dx_accumulate));
+    RC(conv_dgrad(L.g, c.p(L.dz), wsel(c, L.wpt, L.w), dx, c.s, dx_accumulate));
   }
   if (fork_late) RC(fork_w(c));
   RC(conv_wgrad(L.g, x, x_ctotal, x_coff, c.p(L.dz), ch, 0, c.grad(L.w), c.wgs(), WGRAD_SCRATCH_BYTES, c.sw));
@@ -489,9 +529,10 @@ int convbn_bwd(const Ctx& c, ConvBN& L, const bf16* dout, int dout_ctotal, int d
   return 0;
 }
 
-int block_fwd(const Ctx& c, Block& bk, const bf16* x) {
+template <typename T>
+int block_fwd(const Ctx<T>& c, Block& bk, const ND<T>* x) {
   RC(convbn_act_fwd(c, bk.c1, x, bk.c_in, 0, nullptr, 1, c.p(bk.a1), bk.c1.g.cout, 0));
-  const bf16* res = x;
+  const T* res = x;
   if (bk.has_ds) {
     RC(convbn_act_fwd(c, bk.ds, x, bk.c_in, 0, nullptr, 0, c.p(bk.rd), bk.ds.g.cout, 0));
     res = c.p(bk.rd);
@@ -501,12 +542,13 @@ int block_fwd(const Ctx& c, Block& bk, const bf16* x) {
 }
 
 // dx: gradient buffer of the block input; dx_has_content: it already holds another consumer's contribution
-int block_bwd(const Ctx& c, Block& bk, const bf16* x, bf16* dx, int dx_has_content) {
+template <typename T>
+int block_bwd(const Ctx<T>& c, Block& bk, const ND<T>* x, ND<T>* dx, int dx_has_content) {
   const int pl = bk.c2.g.cout;
-  const bf16* dout = c.p(bk.d_out);
-  const bf16* out = c.p(bk.out);
+  const T* dout = c.p(bk.d_out);
+  const T* out = c.p(bk.out);
   // bn2 + conv2 ; identity skip: the ReLU-masked gradient goes straight to dx
-  bf16* dsum = nullptr;
+  T* dsum = nullptr;
   if (!bk.has_ds) {
     if (dx_has_content) return set_error(DBB_EUNSUPPORTED, "block_bwd: identity-skip block with pre-filled dx");
     dsum = dx;
@@ -523,35 +565,35 @@ int block_bwd(const Ctx& c, Block& bk, const bf16* x, bf16* dx, int dx_has_conte
 
 }  // namespace
 
-extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* params, float* const* buffers, float* out,
-                               void* workspace, size_t workspace_bytes, void* stream) {
-  if (!net || !x || !params || !out || !workspace) return set_error(DBB_EINVAL, "net_forward: null pointer");
-  if (workspace_bytes < net->ws_bytes) return set_error(DBB_EWORKSPACE, "net_forward: workspace too small");
-  if (!aligned16(x) || !aligned16(out) || (reinterpret_cast<uintptr_t>(workspace) & 1023)) return set_error(DBB_EALIGN, "net_forward: x/out need 16 B, workspace 1024 B alignment");
-  Ctx c{net, (char*)workspace, params, buffers, nullptr, (cudaStream_t)stream, side_stream(net, (cudaStream_t)stream)};
+template <typename T>
+static int net_forward_t(DbbNet* net, const float* x, const float* const* params, float* const* buffers, float* out,
+                         void* workspace, void* stream) {
+  constexpr bool F32 = std::is_same<T, float>::value;
+  Ctx<T> c{net, (char*)workspace, params, buffers, nullptr, (cudaStream_t)stream, side_stream(net, (cudaStream_t)stream)};
   const int N = net->n;
-  DBB_CUDA(cudaMemsetAsync(c.p<uint8_t>(net->bn_acc), 0, BN_ACC_BYTES, c.s));
+  DBB_CUDA(cudaMemsetAsync(c.template p<uint8_t>(net->bn_acc), 0, BN_ACC_BYTES, c.s));
   // ---- stem: conv 7x7/2 (space-to-depth form) -> BN -> ReLU -> maxpool
   RC(pack_all(c, 0));
   RC(fork_w(c));
   RC(pack_all(c, 1));
-  RC(image_to_s2d(x, N, net->h, net->w, c.p(net->s2d), c.s));
+  if constexpr (!F32) RC(image_to_s2d(x, N, net->h, net->w, c.p(net->s2d), c.s));
   const int64_t P0 = (int64_t)N * net->h1 * net->w1;
   {
     const BnIdx ix{P("backbone.bn1.weight"), P("backbone.bn1.bias"), B("backbone.bn1.running_mean"), B("backbone.bn1.running_var")};
     ConvStats st;
-    const ConvStats* fused = bn_fused(c, st, 64, 1, &ix, c.p<float>(net->stats0));
-    RC(conv1_fprop(N, net->h, net->w, c.p(net->s2d), c.p(net->wp_conv1), c.p(net->z0), c.s, fused));
-    if (!fused) RC(bn_prepare(c, c.p(net->z0), P0, 64, 1, &ix, c.p<float>(net->stats0)));
+    const ConvStats* fused = bn_fused(c, st, 64, 1, &ix, c.template p<float>(net->stats0));
+    if constexpr (F32) RC(conv1_fprop_f32(N, net->h, net->w, x, c.par(P("backbone.conv1.weight")), c.p(net->z0), c.s));
+    else RC(conv1_fprop(N, net->h, net->w, c.p(net->s2d), c.p(net->wp_conv1), c.p(net->z0), c.s, fused));
+    if (!fused) RC(bn_prepare(c, c.p(net->z0), P0, 64, 1, &ix, c.template p<float>(net->stats0)));
   }
   // BN + ReLU are applied inside the pooling kernel: a0 is never written (debug reads materialise it on demand)
-  RC(maxpool_fwd(c.p(net->z0), N, net->h1, net->w1, 64, c.p(net->x1), net->training ? c.p<uint8_t>(net->argmax) : nullptr, c.s,
-                 c.p<float>(net->stats0)));
+  RC(maxpool_fwd(c.p(net->z0), N, net->h1, net->w1, 64, c.p(net->x1), net->training ? c.template p<uint8_t>(net->argmax) : nullptr, c.s,
+                 c.template p<float>(net->stats0)));
   RC(join_w(c));          // packed weights of every later layer are ready
   // ---- residual stages
-  const bf16* cur = c.p(net->x1);
+  const T* cur = c.p(net->x1);
   for (int i = 0; i < 8; ++i) { RC(block_fwd(c, net->blocks[i], cur)); cur = c.p(net->blocks[i].out); }
-  const bf16* feat[4];
+  const T* feat[4];
   for (int i = 0; i < 4; ++i) feat[i] = c.p(net->blocks[i * 2 + 1].out);
   const int planes[4] = {64, 128, 256, 512};
   // ---- FPN top-down (segmentation_body.py:64-77)
@@ -559,12 +601,12 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
     RC(convbn_act_fwd(c, net->lat[i], feat[i], planes[i], 0, nullptr, 1, c.p(net->l_act[i]), 64, 0));
   }
   const int hf = net->hh[0], wf = net->ww[0];
-  const bf16* upper = c.p(net->l_act[3]);   // p5
+  const T* upper = c.p(net->l_act[3]);   // p5
   int uh = net->hh[3], uw = net->ww[3];
   for (int i = 0; i < 3; ++i) {             // p4, p3, p2
     const int lvl = 2 - i;
     RC(upsample_add_fwd(upper, uh, uw, c.p(net->l_act[lvl]), N, net->hh[lvl], net->ww[lvl], 64, c.p(net->s_sum[i]), c.s));
-    bf16* dst = (i < 2) ? c.p(net->p_act[i]) : c.p(net->cat);
+    T* dst = (i < 2) ? c.p(net->p_act[i]) : c.p(net->cat);
     RC(convbn_act_fwd(c, net->smooth[i], c.p(net->s_sum[i]), 64, 0, nullptr, 1, dst, i < 2 ? 64 : 256, 0));
     upper = dst; uh = net->hh[lvl]; uw = net->ww[lvl];
     if (i == 2) break;
@@ -575,8 +617,8 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
   RC(upsample_into(c.p(net->l_act[3]), net->hh[3], net->ww[3], N, hf, wf, 64, c.p(net->cat), 256, 192, c.s));
   RC(convbn_act_fwd(c, net->fconv, c.p(net->cat), 256, 0, nullptr, 1, c.p(net->af), 256, 0));
   // ---- head (segmentation_head.py:35-45)
-  DBB_CUDA(cudaMemsetAsync(c.p<float>(net->bias_h), 0, 128 * sizeof(float), c.s));
-  DBB_CUDA(cudaMemcpyAsync(c.p<float>(net->bias_h), c.par(P("segmentation_head.binarize.0.bias")), 64 * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
+  DBB_CUDA(cudaMemsetAsync(c.template p<float>(net->bias_h), 0, 128 * sizeof(float), c.s));
+  DBB_CUDA(cudaMemcpyAsync(c.template p<float>(net->bias_h), c.par(P("segmentation_head.binarize.0.bias")), 64 * sizeof(float), cudaMemcpyDeviceToDevice, c.s));
   const int64_t Ph = (int64_t)N * hf * wf;
   auto head_bn = [&](const char* idx) {
     std::vector<BnIdx> v;
@@ -589,17 +631,17 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
   {
     const std::vector<BnIdx> ix = head_bn("1");
     static const bool no_epi = getenv("DBB_NO_EVAL_EPILOGUE") != nullptr;     // A/B switch
-    if (!net->training && !no_epi) {     // inference: BatchNorm + ReLU in the convolution's epilogue (see convbn_act_fwd)
-      float* stats4 = c.p<float>(net->stats_h);
-      RC(bn_prepare(c, nullptr, Ph, 128, 2, ix.data(), stats4));
+    if (!net->training && !no_epi && !F32) {     // inference: BatchNorm + ReLU in the convolution's epilogue (see convbn_act_fwd)
+      float* stats4 = c.template p<float>(net->stats_h);
+      RC(bn_prepare(c, (const T*)nullptr, Ph, 128, 2, ix.data(), stats4));
       const ConvEpi epi{stats4, stats4 + 128, nullptr, 1};
-      RC(conv_fprop(net->hconv_g, c.p(net->af), 256, 0, c.p(net->wp_h), c.p<float>(net->bias_h), c.p(net->ah), 128, 0, c.s, nullptr, &epi));
+      RC(conv_fprop(net->hconv_g, c.p(net->af), 256, 0, c.p(net->wp_h), c.template p<float>(net->bias_h), c.p(net->ah), 128, 0, c.s, nullptr, &epi));
     } else {
       ConvStats st;
-      const ConvStats* fused = bn_fused(c, st, 64, 2, ix.data(), c.p<float>(net->stats_h));
-      RC(conv_fprop(net->hconv_g, c.p(net->af), 256, 0, c.p(net->wp_h), c.p<float>(net->bias_h), c.p(net->zh), 128, 0, c.s, fused));
-      if (!fused) RC(bn_prepare(c, c.p(net->zh), Ph, 128, 2, ix.data(), c.p<float>(net->stats_h)));
-      RC(bn_apply(c.p(net->zh), Ph, 128, c.p<float>(net->stats_h), nullptr, 1, c.p(net->ah), 128, 0, c.s));
+      const ConvStats* fused = bn_fused(c, st, 64, 2, ix.data(), c.template p<float>(net->stats_h));
+      RC(conv_fprop(net->hconv_g, c.p(net->af), 256, 0, c.p(net->wp_h), c.template p<float>(net->bias_h), c.p(net->zh), 128, 0, c.s, fused));
+      if (!fused) RC(bn_prepare(c, c.p(net->zh), Ph, 128, 2, ix.data(), c.template p<float>(net->stats_h)));
+      RC(bn_apply(c.p(net->zh), Ph, 128, c.template p<float>(net->stats_h), nullptr, 1, c.p(net->ah), 128, 0, c.s));
     }
   }
   const int64_t Pt = Ph * 4;
@@ -609,32 +651,30 @@ extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* 
     for (int br = 0; br < 2; ++br) {       // each branch launch finalizes its own 64-channel half of the 128-wide tensor
       const std::string pre = std::string("segmentation_head.") + (br ? "thresh" : "binarize");
       ConvStats st;
-      const ConvStats* fused = bn_fused(c, st, 64, 1, &ix[br], c.p<float>(net->stats_t), br * 64);
+      const ConvStats* fused = bn_fused(c, st, 64, 1, &ix[br], c.template p<float>(net->stats_t), br * 64);
       all_fused = all_fused && fused;
-      RC(convt_fprop(net->tconv_g, c.p(net->ah), 128, br * 64, c.p(net->wp_t[br]), c.par(P(pre + ".3.bias")), c.p(net->zt), 128, br * 64, c.s, fused));
+      RC(convt_fprop(net->tconv_g, c.p(net->ah), 128, br * 64, wsel(c, net->wp_t[br], P(pre + ".3.weight")), c.par(P(pre + ".3.bias")), c.p(net->zt), 128, br * 64, c.s, fused));
     }
-    if (!all_fused) RC(bn_prepare(c, c.p(net->zt), Pt, 128, 2, ix.data(), c.p<float>(net->stats_t)));
+    if (!all_fused) RC(bn_prepare(c, c.p(net->zt), Pt, 128, 2, ix.data(), c.template p<float>(net->stats_t)));
   }
-  float* hout = net->head_out.bytes ? c.p<float>(net->head_out) : out;
-  RC(head_tail_fwd(c.p(net->zt), N, 2 * hf, 2 * wf, c.p<float>(net->stats_t), c.par(P("segmentation_head.binarize.6.weight")),
+  float* hout = net->head_out.bytes ? c.template p<float>(net->head_out) : out;
+  RC(head_tail_fwd(c.p(net->zt), N, 2 * hf, 2 * wf, c.template p<float>(net->stats_t), c.par(P("segmentation_head.binarize.6.weight")),
                    c.par(P("segmentation_head.thresh.6.weight")), c.par(P("segmentation_head.binarize.6.bias")),
                    c.par(P("segmentation_head.thresh.6.bias")), STEP_K, net->out_c, hout, c.s));
   if (net->head_out.bytes) RC(bilinear_fwd(hout, N * net->out_c, net->ho, net->wo, out, net->h, net->w, c.s));
   return DBB_OK;
 }
 
-extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout, const float* const* params,
-                                float* const* grads, void* workspace, size_t workspace_bytes, int segment, void* stream) {
-  if (!net || !out || !dout || !params || !grads || !workspace) return set_error(DBB_EINVAL, "net_backward: null pointer");
-  if (!net->training) return set_error(DBB_EINVAL, "net_backward: network was planned in eval mode");
-  if (workspace_bytes < net->ws_bytes) return set_error(DBB_EWORKSPACE, "net_backward: workspace too small");
-  if (segment < -1 || segment > 2) return set_error(DBB_EINVAL, "net_backward: segment must be -1..2");
-  Ctx c{net, (char*)workspace, params, nullptr, grads, (cudaStream_t)stream, side_stream(net, (cudaStream_t)stream)};
+template <typename T>
+static int net_backward_t(DbbNet* net, const float* x_img, const float* out, const float* dout, const float* const* params,
+                          float* const* grads, void* workspace, int segment, void* stream) {
+  constexpr bool F32 = std::is_same<T, float>::value;
+  Ctx<T> c{net, (char*)workspace, params, nullptr, grads, (cudaStream_t)stream, side_stream(net, (cudaStream_t)stream)};
   // (per-kernel profiling serialises the two chains: CUDA-event times of overlapping kernels would be inflated)
   const int N = net->n;
   const int hf = net->hh[0], wf = net->ww[0];
   const int planes[4] = {64, 128, 256, 512};
-  const bf16* feat[4];
+  const T* feat[4];
   for (int i = 0; i < 4; ++i) feat[i] = c.p(net->blocks[i * 2 + 1].out);
   const bool all = segment < 0;
   int nblk = 0;
@@ -644,23 +684,23 @@ extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout
     const float* hout = out;
     const float* dhout = dout;
     if (net->head_out.bytes) {
-      RC(bilinear_bwd(dout, N * 3, net->ho, net->wo, c.p<float>(net->d_head_out), net->h, net->w, c.s));
-      hout = c.p<float>(net->head_out); dhout = c.p<float>(net->d_head_out);
+      RC(bilinear_bwd(dout, N * 3, net->ho, net->wo, c.template p<float>(net->d_head_out), net->h, net->w, c.s));
+      hout = c.template p<float>(net->head_out); dhout = c.template p<float>(net->d_head_out);
     }
     const std::string hb = "segmentation_head.binarize", ht = "segmentation_head.thresh";
     const int64_t Ph = (int64_t)N * hf * wf, Pt = Ph * 4;
-    RC(head_tail_bwd_reduce(c.p(net->zt), N, 2 * hf, 2 * wf, c.p<float>(net->stats_t), c.par(P(hb + ".6.weight")), c.par(P(ht + ".6.weight")),
+    RC(head_tail_bwd_reduce(c.p(net->zt), N, 2 * hf, 2 * wf, c.template p<float>(net->stats_t), c.par(P(hb + ".6.weight")), c.par(P(ht + ".6.weight")),
                             hout, dhout, STEP_K, c.partials(), &nblk, c.s));
-    RC(head_tail_bwd_finalize(c.partials(), nblk, Pt, c.par(P(hb + ".4.weight")), c.par(P(ht + ".4.weight")), c.p<float>(net->stats_t),
+    RC(head_tail_bwd_finalize(c.partials(), nblk, Pt, c.par(P(hb + ".4.weight")), c.par(P(ht + ".4.weight")), c.template p<float>(net->stats_t),
                               c.grad(P(hb + ".4.weight")), c.grad(P(hb + ".4.bias")), c.grad(P(ht + ".4.weight")), c.grad(P(ht + ".4.bias")),
-                              c.p<float>(net->coef_t), c.grad(P(hb + ".6.weight")), c.grad(P(ht + ".6.weight")), c.grad(P(hb + ".6.bias")),
+                              c.template p<float>(net->coef_t), c.grad(P(hb + ".6.weight")), c.grad(P(ht + ".6.weight")), c.grad(P(hb + ".6.bias")),
                               c.grad(P(ht + ".6.bias")), c.s));
-    RC(head_tail_bwd_apply(c.p(net->zt), N, 2 * hf, 2 * wf, c.p<float>(net->stats_t), c.p<float>(net->coef_t), c.par(P(hb + ".6.weight")),
+    RC(head_tail_bwd_apply(c.p(net->zt), N, 2 * hf, 2 * wf, c.template p<float>(net->stats_t), c.template p<float>(net->coef_t), c.par(P(hb + ".6.weight")),
                            c.par(P(ht + ".6.weight")), hout, dhout, STEP_K, c.p(net->d_zt), c.s));
     // ---- ConvTranspose2d(64,64,2,2) x 2
     if (!wgrad_fork_late()) RC(fork_w(c));
     for (int br = 0; br < 2; ++br)
-      RC(convt_dgrad(net->tconv_g, c.p(net->d_zt), 128, br * 64, c.p(net->wpt_t[br]), c.p(net->d_ah), 128, br * 64, c.s));
+      RC(convt_dgrad(net->tconv_g, c.p(net->d_zt), 128, br * 64, wsel(c, net->wpt_t[br], P((br ? ht : hb) + ".3.weight")), c.p(net->d_ah), 128, br * 64, c.s));
     if (wgrad_fork_late()) RC(fork_w(c));
     for (int br = 0; br < 2; ++br) {
       const std::string pre = br ? ht : hb;
@@ -671,37 +711,37 @@ extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout
     // ---- BN(2 x 64) + ReLU + the fused 256->128 3x3 conv of the two branches
     {
       BnBwdFin fin;
-      fin.nseg = 2; fin.coef3 = c.p<float>(net->coef_h);
+      fin.nseg = 2; fin.coef3 = c.template p<float>(net->coef_h);
       for (int br = 0; br < 2; ++br) {
         const std::string pre = br ? ht : hb;
         fin.seg[br] = BnBwdFinSeg{c.par(P(pre + ".1.weight")), c.grad(P(pre + ".1.weight")), c.grad(P(pre + ".1.bias")), br * 64, 64};
       }
-      RC(bn_bwd_reduce_finalize(c.p(net->d_ah), 128, 0, c.p(net->ah), 128, 0, c.p(net->zh), Ph, 128, c.p<float>(net->stats_h), fin, c.acc(), c.ticket(), c.s, self_mask()));
+      RC(bn_bwd_reduce_finalize(c.p(net->d_ah), 128, 0, c.p(net->ah), 128, 0, c.p(net->zh), Ph, 128, c.template p<float>(net->stats_h), fin, c.acc(), c.ticket(), c.s, self_mask()));
     }
-    RC(bn_bwd_apply(c.p(net->d_ah), 128, 0, c.p(net->ah), 128, 0, c.p(net->zh), Ph, 128, c.p<float>(net->stats_h), c.p<float>(net->coef_h),
+    RC(bn_bwd_apply(c.p(net->d_ah), 128, 0, c.p(net->ah), 128, 0, c.p(net->zh), Ph, 128, c.template p<float>(net->stats_h), c.template p<float>(net->coef_h),
                     c.p(net->d_zh), nullptr, c.s, self_mask()));
     if (!wgrad_fork_late()) RC(fork_w(c));
-    RC(conv_dgrad(net->hconv_g, c.p(net->d_zh), c.p(net->wpt_h), c.p(net->d_af), c.s, 0));
+    RC(conv_dgrad(net->hconv_g, c.p(net->d_zh), F32 ? c.p(net->wp_h) : c.p(net->wpt_h), c.p(net->d_af), c.s, 0));
     if (wgrad_fork_late()) RC(fork_w(c));
-    RC(conv_wgrad(net->hconv_g, c.p(net->af), 256, 0, c.p(net->d_zh), 128, 0, c.p<float>(net->dw_h), c.wgs(), WGRAD_SCRATCH_BYTES, c.sw));
+    RC(conv_wgrad(net->hconv_g, c.p(net->af), 256, 0, c.p(net->d_zh), 128, 0, c.template p<float>(net->dw_h), c.wgs(), WGRAD_SCRATCH_BYTES, c.sw));
     const size_t half = (size_t)64 * 256 * 9;
-    DBB_CUDA(cudaMemcpyAsync(c.grad(P(hb + ".0.weight")), c.p<float>(net->dw_h), half * sizeof(float), cudaMemcpyDeviceToDevice, c.sw));
-    DBB_CUDA(cudaMemcpyAsync(c.grad(P(ht + ".0.weight")), c.p<float>(net->dw_h) + half, half * sizeof(float), cudaMemcpyDeviceToDevice, c.sw));
+    DBB_CUDA(cudaMemcpyAsync(c.grad(P(hb + ".0.weight")), c.template p<float>(net->dw_h), half * sizeof(float), cudaMemcpyDeviceToDevice, c.sw));
+    DBB_CUDA(cudaMemcpyAsync(c.grad(P(ht + ".0.weight")), c.template p<float>(net->dw_h) + half, half * sizeof(float), cudaMemcpyDeviceToDevice, c.sw));
     DBB_CUDA(cudaMemsetAsync(c.grad(P(hb + ".0.bias")), 0, 64 * sizeof(float), c.sw));
     // ---- FPN output conv
     RC(convbn_bwd(c, net->fconv, c.p(net->d_af), 256, 0, c.p(net->af), 256, 0, c.p(net->cat), 256, 0, c.p(net->d_cat), 0, nullptr, 1));
     // ---- top-down path, bottom level first: smooth_p2, p3, p4 then the c5 lateral
     //      d_p[k]: gradient of p5 (k=0), p4 (1), p3 (2); d_s[i]: gradient of the sum feeding smooth[i]
-    const bf16* dlevel = c.p(net->d_cat);   // gradient w.r.t. p2 = channels 0..63 of d_cat
+    const T* dlevel = c.p(net->d_cat);   // gradient w.r.t. p2 = channels 0..63 of d_cat
     int dl_ct = 256;
-    const bf16* mlevel = c.p(net->cat);     // p2 activation = channels 0..63 of cat
+    const T* mlevel = c.p(net->cat);     // p2 activation = channels 0..63 of cat
     int ml_ct = 256;
     for (int i = 2; i >= 0; --i) {
       const int lvl = 2 - i;               // smooth[2] -> level 0 (c2 resolution)
       const int up = lvl + 1;              // the level that was upsampled into this one
       RC(convbn_bwd(c, net->smooth[i], dlevel, dl_ct, 0, mlevel, ml_ct, 0, c.p(net->s_sum[i]), 64, 0, c.p(net->d_s[i]), 0, nullptr, 1));
       // gradient of the upsampled operand: concat slice (channels 64*up ..) + the upsample-add path
-      bf16* dpu = c.p(net->d_p[3 - up]);   // up=1 -> d_p[2] (p3), up=2 -> d_p[1] (p4), up=3 -> d_p[0] (p5)
+      T* dpu = c.p(net->d_p[3 - up]);   // up=1 -> d_p[2] (p3), up=2 -> d_p[1] (p4), up=3 -> d_p[0] (p5)
       RC(upsample_bwd(c.p(net->d_cat), 256, 64 * up, N, hf, wf, 64, dpu, net->hh[up], net->ww[up], 0, c.s));
       RC(upsample_bwd(c.p(net->d_s[i]), 64, 0, N, net->hh[lvl], net->ww[lvl], 64, dpu, net->hh[up], net->ww[up], 1, c.s));
       // lateral conv of this level: its output was the other operand of the sum
@@ -713,8 +753,8 @@ extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout
     RC(convbn_bwd(c, net->lat[3], dlevel, 64, 0, mlevel, 64, 0, feat[3], 512, 0, c.p(net->d_c[3]), 0, nullptr, 1));
   }
   auto run_block = [&](int i) -> int {
-    const bf16* x = (i == 0) ? c.p(net->x1) : c.p(net->blocks[i - 1].out);
-    bf16* dx = (i == 0) ? c.p(net->d_x1) : c.p(net->blocks[i - 1].d_out);
+    const T* x = (i == 0) ? c.p(net->x1) : c.p(net->blocks[i - 1].out);
+    T* dx = (i == 0) ? c.p(net->d_x1) : c.p(net->blocks[i - 1].d_out);
     const int has_content = (i >= 2 && (i % 2) == 0) ? 1 : 0;   // input is c2/c3/c4: the FPN lateral already wrote its share
     return block_bwd(c, net->blocks[i], x, dx, has_content);
   };
@@ -722,24 +762,54 @@ extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout
   if (all || segment == 2) {
     for (int i = 3; i >= 0; --i) RC(run_block(i));
     // ---- stem: maxpool -> ReLU/BN -> conv1 (no data gradient: the image needs none)
-    RC(maxpool_bwd(c.p(net->d_x1), c.p<uint8_t>(net->argmax), N, net->h1, net->w1, 64, c.p(net->d_a0), c.s));
+    RC(maxpool_bwd(c.p(net->d_x1), c.template p<uint8_t>(net->argmax), N, net->h1, net->w1, 64, c.p(net->d_a0), c.s));
     const int64_t P0 = (int64_t)N * net->h1 * net->w1;
     const int g1 = P("backbone.bn1.weight"), b1 = P("backbone.bn1.bias");
     {
       BnBwdFin fin;
-      fin.nseg = 1; fin.coef3 = c.p<float>(net->coef0);
+      fin.nseg = 1; fin.coef3 = c.template p<float>(net->coef0);
       fin.seg[0] = BnBwdFinSeg{c.par(g1), c.grad(g1), c.grad(b1), 0, 64};
       // (the stem activation a0 is fused away in the forward pass, so its ReLU mask always comes from z0)
-      RC(bn_bwd_reduce_finalize(c.p(net->d_a0), 64, 0, nullptr, 64, 0, c.p(net->z0), P0, 64, c.p<float>(net->stats0), fin, c.acc(), c.ticket(), c.s, 1));
+      RC(bn_bwd_reduce_finalize(c.p(net->d_a0), 64, 0, nullptr, 64, 0, c.p(net->z0), P0, 64, c.template p<float>(net->stats0), fin, c.acc(), c.ticket(), c.s, 1));
     }
-    RC(bn_bwd_apply(c.p(net->d_a0), 64, 0, nullptr, 64, 0, c.p(net->z0), P0, 64, c.p<float>(net->stats0), c.p<float>(net->coef0),
+    RC(bn_bwd_apply(c.p(net->d_a0), 64, 0, nullptr, 64, 0, c.p(net->z0), P0, 64, c.template p<float>(net->stats0), c.template p<float>(net->coef0),
                     c.p(net->d_z0), nullptr, c.s, 1));
     RC(fork_w(c));
-    RC(conv1_wgrad(N, net->h, net->w, c.p(net->s2d), c.p(net->d_z0), c.p<float>(net->dw_s2d), c.wgs(), WGRAD_SCRATCH_BYTES, c.sw));
-    RC(conv1_wgrad_unpack(c.p<float>(net->dw_s2d), c.grad(P("backbone.conv1.weight")), c.sw));
+    if constexpr (F32) {
+      if (!x_img) return set_error(DBB_EINVAL, "net_backward: the fp32 mode needs the input image (dbb_net_backward_ex)");
+      RC(conv1_wgrad_f32(N, net->h, net->w, x_img, c.p(net->d_z0), c.grad(P("backbone.conv1.weight")), c.sw));
+    } else {
+      RC(conv1_wgrad(N, net->h, net->w, c.p(net->s2d), c.p(net->d_z0), c.template p<float>(net->dw_s2d), c.wgs(), WGRAD_SCRATCH_BYTES, c.sw));
+      RC(conv1_wgrad_unpack(c.template p<float>(net->dw_s2d), c.grad(P("backbone.conv1.weight")), c.sw));
+    }
   }
   RC(join_w(c));          // every gradient of this call is complete on the caller's stream
   return DBB_OK;
+}
+
+extern "C" int dbb_net_forward(DbbNet* net, const float* x, const float* const* params, float* const* buffers, float* out,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  if (!net || !x || !params || !out || !workspace) return set_error(DBB_EINVAL, "net_forward: null pointer");
+  if (workspace_bytes < net->ws_bytes) return set_error(DBB_EWORKSPACE, "net_forward: workspace too small");
+  if (!aligned16(x) || !aligned16(out) || (reinterpret_cast<uintptr_t>(workspace) & 1023)) return set_error(DBB_EALIGN, "net_forward: x/out need 16 B, workspace 1024 B alignment");
+  return net->fp32 ? net_forward_t<float>(net, x, params, buffers, out, workspace, stream)
+                   : net_forward_t<bf16>(net, x, params, buffers, out, workspace, stream);
+}
+
+// x: the input image of the matching forward call.  The bf16 path keeps its own staged copy (space-to-depth buffer) and
+// ignores it; the fp32-parity mode reads it for conv1's weight gradient.
+extern "C" int dbb_net_backward_ex(DbbNet* net, const float* x, const float* out, const float* dout, const float* const* params,
+                                   float* const* grads, void* workspace, size_t workspace_bytes, int segment, void* stream) {
+  if (!net || !out || !dout || !params || !grads || !workspace) return set_error(DBB_EINVAL, "net_backward: null pointer");
+  if (!net->training) return set_error(DBB_EINVAL, "net_backward: network was planned in eval mode");
+  if (workspace_bytes < net->ws_bytes) return set_error(DBB_EWORKSPACE, "net_backward: workspace too small");
+  if (segment < -1 || segment > 2) return set_error(DBB_EINVAL, "net_backward: segment must be -1..2");
+  return net->fp32 ? net_backward_t<float>(net, x, out, dout, params, grads, workspace, segment, stream)
+                   : net_backward_t<bf16>(net, x, out, dout, params, grads, workspace, segment, stream);
+}
+extern "C" int dbb_net_backward(DbbNet* net, const float* out, const float* dout, const float* const* params,
+                                float* const* grads, void* workspace, size_t workspace_bytes, int segment, void* stream) {
+  return dbb_net_backward_ex(net, nullptr, out, dout, params, grads, workspace, workspace_bytes, segment, stream);
 }
 
 // ---- debugging / parity aid: copy a named internal NHWC bf16 tensor out as NCHW float32 (tests only)
@@ -811,9 +881,15 @@ extern "C" int dbb_net_debug_read(DbbNet* net, const char* name, const void* wor
   if (!net || !name || !find_tensor(net, name, &b, &h, &w, &ch)) return set_error(DBB_EINVAL, "net_debug: unknown tensor");
   if (std::string(name) == "a0") {   // the stem activation is fused away (maxpool_fwd applies BN + ReLU): materialise it for the reader
     char* base = (char*)const_cast<void*>(workspace);
+    if (net->fp32)
+      RC(bn_apply(reinterpret_cast<const float*>(base + net->z0.off), (int64_t)net->n * net->h1 * net->w1, 64,
+                  reinterpret_cast<const float*>(base + net->stats0.off), nullptr, 1, reinterpret_cast<float*>(base + b.off), 64, 0,
+                  (cudaStream_t)stream));
+    else
     RC(bn_apply(reinterpret_cast<const bf16*>(base + net->z0.off), (int64_t)net->n * net->h1 * net->w1, 64,
                 reinterpret_cast<const float*>(base + net->stats0.off), nullptr, 1, reinterpret_cast<bf16*>(base + b.off), 64, 0,
                 (cudaStream_t)stream));
   }
+  if (net->fp32) return nhwc_to_nchw_f32(reinterpret_cast<const float*>((const char*)workspace + b.off), out_nchw, net->n, ch, (int64_t)h * w, (cudaStream_t)stream);
   return nhwc_bf16_to_nchw_f32(reinterpret_cast<const bf16*>((const char*)workspace + b.off), out_nchw, net->n, ch, (int64_t)h * w, (cudaStream_t)stream);
 }

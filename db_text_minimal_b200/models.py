@@ -21,12 +21,12 @@ segmentation_head_dict = {'DBHead': DBHead}
 
 
 class _Plan:
-    """One (N, H, W, training) configuration of the native executor."""
+    """One (N, H, W, training, precision) configuration of the native executor."""
 
-    def __init__(self, n, h, w, training):
+    def __init__(self, n, h, w, training, precision=0):
         L = _lib.lib()
         self.key = (n, h, w, training)
-        self.handle = L.dbb_net_create(n, h, w, 1 if training else 0)
+        self.handle = L.dbb_net_create_ex(n, h, w, 1 if training else 0, precision)
         if not self.handle:
             raise _lib.DbbError("dbb_net_create failed: " + L.dbb_last_cuda_error().decode())
         self.ws_bytes = L.dbb_net_workspace_bytes(self.handle)
@@ -69,13 +69,13 @@ class _DBNetFn(torch.autograd.Function):
                                          _lib.stream_ptr()), "dbb_net_forward")
         if training:
             ctx.plan, ctx.ws_raw, ctx.ws_ptr, ctx.model = plan, ws_raw, ws_ptr, model
-            ctx.save_for_backward(out, *params)
+            ctx.save_for_backward(out, x, *params)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         L = _lib.lib()
-        out, *params = ctx.saved_tensors
+        out, x, *params = ctx.saved_tensors
         plan, model = ctx.plan, ctx.model
         dev = out.device
         dout = dout.float().contiguous()
@@ -87,8 +87,8 @@ class _DBNetFn(torch.autograd.Function):
         nseg = L.dbb_net_num_segments()
         with torch.cuda.device(dev):
             for seg in range(nseg):
-                _lib.check(L.dbb_net_backward(plan.handle, out.data_ptr(), dout.data_ptr(), pa, ga, ctx.ws_ptr, plan.ws_bytes,
-                                              seg, _lib.stream_ptr()), "dbb_net_backward")
+                _lib.check(L.dbb_net_backward_ex(plan.handle, x.data_ptr(), out.data_ptr(), dout.data_ptr(), pa, ga, ctx.ws_ptr,
+                                                 plan.ws_bytes, seg, _lib.stream_ptr()), "dbb_net_backward")
                 if hook is not None:
                     hook(seg, flat, model._segment_slices[seg])
         if hook is not None:
@@ -98,10 +98,22 @@ class _DBNetFn(torch.autograd.Function):
         return (None, None, None, *grads)
 
 
+PRECISIONS = {"bf16": 0, "fp32": 1}
+
+
 class DBTextModel(nn.Module):
-    def __init__(self):
+    """precision: 'bf16' (default; tcgen05 convolutions on bf16 activations, fp32 accumulate) or 'fp32' (parity mode: the
+    same executor graph on float32 activations with CUDA-core convolutions -- slow, matches the reference to fp32
+    round-off).  $DBB_PRECISION overrides the default.  pretrained: as the reference's hard-coded True
+    (src/models.py:17); see modules/resnet.py:resnet18 for where the ImageNet weights are looked up."""
+
+    def __init__(self, precision=None, pretrained=True):
         super().__init__()
-        pretrained = True      # as in the reference (src/models.py:17); nothing is downloaded here
+        import os
+        precision = precision or os.environ.get("DBB_PRECISION", "bf16")
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.precision = precision
         backbone_name = "resnet18"
         segmentation_body_name = "FPN"
         segmentation_head_name = "DBHead"
@@ -188,7 +200,7 @@ class DBTextModel(nn.Module):
     def _plan(self, n, h, w, training):
         key = (n, h, w, training)
         if key not in self._plans:
-            self._plans[key] = _Plan(n, h, w, training)
+            self._plans[key] = _Plan(n, h, w, training, PRECISIONS[self.precision])
         return self._plans[key]
 
     # ------------------------------------------------------------------ the reference's public surface

@@ -86,5 +86,48 @@ class ResNet(nn.Module):
         return tuple(feats)
 
 
+model_urls = {'resnet18': 'https://download.pytorch.org/models/resnet18-5c106cde.pth'}
+
+
+def _imagenet_state_dict():
+    """The reference (src/modules/resnet.py:245-255) fetches the ImageNet ResNet-18 through model_zoo.load_url.  Same
+    lookup here, in this order: $DBB_RESNET18_WEIGHTS (a local .pth), the torch hub checkpoint cache (where load_url
+    itself would have left the file), then load_url (needs network)."""
+    import os
+    import torch
+    cands = [os.environ.get("DBB_RESNET18_WEIGHTS")]
+    try:
+        cands.append(os.path.join(torch.hub.get_dir(), "checkpoints", os.path.basename(model_urls['resnet18'])))
+    except Exception:
+        pass
+    for c in cands:
+        if c and os.path.exists(c):
+            return torch.load(c, map_location="cpu")
+    import socket
+    from torch.utils import model_zoo
+    old = socket.getdefaulttimeout()
+    socket.setdefaulttimeout(float(os.environ.get("DBB_DOWNLOAD_TIMEOUT", "10")))     # an offline box must not hang here
+    try:
+        return model_zoo.load_url(model_urls['resnet18'], progress=False)
+    finally:
+        socket.setdefaulttimeout(old)
+
+
 def resnet18(pretrained=True, **kwargs):
-    return ResNet(BasicBlock, [2, 2, 2, 2], **kwargs)
+    """Constructs a ResNet-18 model (src/modules/resnet.py:245-255): ImageNet weights with strict=False when
+    pretrained.  When the weights cannot be obtained (no network, nothing cached) the backbone keeps its random
+    initialisation and a RuntimeWarning says so -- set DBB_RESNET18_WEIGHTS=<resnet18-5c106cde.pth> or load a
+    checkpoint afterwards."""
+    model = ResNet(BasicBlock, [2, 2, 2, 2], **kwargs)
+    if pretrained:
+        try:
+            sd = _imagenet_state_dict()
+        except Exception as e:        # offline box
+            import warnings
+            warnings.warn("resnet18(pretrained=True): ImageNet weights unavailable (%s: %s); the backbone is RANDOMLY "
+                          "initialised. Set DBB_RESNET18_WEIGHTS or load a checkpoint." % (type(e).__name__, e),
+                          RuntimeWarning, stacklevel=2)
+        else:
+            print('load from imagenet')
+            model.load_state_dict(sd, strict=False)
+    return model

@@ -158,6 +158,14 @@ int dbb_net_buffer_numel(int i);
 
 /* Plans one (N, H, W, training) configuration.  Returns NULL on error (see dbb_last_cuda_error). */
 DbbNet* dbb_net_create(int64_t n, int64_t h, int64_t w, int training);
+/* precision: DBB_PRECISION_BF16 (the product path: bf16 activations, tcgen05 convolutions, fp32 accumulate) or
+ * DBB_PRECISION_FP32 (parity mode: the same graph and the same elementwise / head kernels on float32 activations with
+ * CUDA-core float32 convolutions; slow, used to check the network against the reference at north_star's fp32 tolerance:
+ * P, T, B 1e-4, losses / gradients 1e-3). */
+#define DBB_PRECISION_BF16 0
+#define DBB_PRECISION_FP32 1
+DbbNet* dbb_net_create_ex(int64_t n, int64_t h, int64_t w, int training, int precision);
+int dbb_net_precision(const DbbNet* net);
 void dbb_net_destroy(DbbNet* net);
 size_t dbb_net_workspace_bytes(const DbbNet* net);
 int64_t dbb_net_out_channels(const DbbNet* net);   /* 3 train, 2 eval */
@@ -174,8 +182,12 @@ int dbb_net_forward(DbbNet* net, const float* x, const float* const* params, flo
 int dbb_net_num_segments(void);
 int dbb_net_backward(DbbNet* net, const float* out, const float* dout, const float* const* params, float* const* grads,
                      void* workspace, size_t workspace_bytes, int segment, void* stream);
+/* Same, with the input image x of the matching forward call.  The bf16 path keeps a staged copy of the image in its
+ * workspace and ignores x; the fp32 mode needs it for conv1's weight gradient (src/modules/resnet.py:171). */
+int dbb_net_backward_ex(DbbNet* net, const float* x, const float* out, const float* dout, const float* const* params,
+                        float* const* grads, void* workspace, size_t workspace_bytes, int segment, void* stream);
 
-/* parity aid (tests): shape of / NCHW float32 copy of a named internal NHWC bf16 activation or gradient, e.g. "af", "block3.out" */
+/* parity aid (tests): shape of / NCHW float32 copy of a named internal NHWC activation or gradient (bf16, or float32 in the fp32 mode), e.g. "af", "block3.out" */
 int dbb_net_debug_shape(DbbNet* net, const char* name, int64_t* shape4);
 int dbb_net_debug_read(DbbNet* net, const char* name, const void* workspace, float* out_nchw, void* stream);
 

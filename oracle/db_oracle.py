@@ -557,6 +557,58 @@ def synth_images(n: int, h: int, w: int, seed: int = 0) -> torch.Tensor:
     return torch.randn((n, 3, h, w), generator=g) * 60.0
 
 
+def synth_text_batch(n: int, h: int, w: int, seed: int = 0):
+    """Images that DEPICT their ground truth (for conditioning a network by a few training steps and for BASELINE-size
+    goldens): N(0, 25^2) noise + a per-channel offset inside the dilated text area + another inside the shrunk core.
+    Returns (x float32 (N,3,H,W) torch, gts float32 (4,N,H,W) numpy).  Value range ~ +-125 like mean-subtracted pixels
+    (src/utils.py:190-193)."""
+    gts = synth_gt_maps(n, h, w, seed)
+    g = torch.Generator().manual_seed(1000 + seed)
+    area = torch.from_numpy(gts[3]).unsqueeze(1)
+    core = torch.from_numpy(gts[0]).unsqueeze(1)
+    img = torch.randn((n, 3, h, w), generator=g) * 25.0
+    img = img + torch.tensor([70.0, -50.0, 60.0]).view(1, 3, 1, 1) * (area - 0.5)
+    img = img + torch.tensor([30.0, 40.0, -35.0]).view(1, 3, 1, 1) * core
+    return img.contiguous(), gts
+
+
+COND_SEED = 7          # init_params seed of the conditioned network (tests/golden/cond_params.npz)
+
+
+def cond_trainable(key: str, numel_dim: int) -> bool:
+    """The parameter subset the golden generator lets the REFERENCE train (everything else stays at init_params(7) so the
+    fixture stays small): the whole DBHead and every 1-D tensor (BatchNorm affine, conv biases) outside the unused
+    backbone.fc / backbone.smooth."""
+    if key.startswith("backbone.fc") or key.startswith("backbone.smooth"):
+        return False
+    return key.startswith("segmentation_head") or numel_dim == 1
+
+
+def cond_params(golden_dir: str) -> Dict[str, torch.Tensor]:
+    """init_params(COND_SEED) overlaid with the tensors the reference trained (oracle/make_golden.py:make_cond_params)."""
+    import os
+    z = np.load(os.path.join(golden_dir, "cond_params.npz"))
+    p = init_params(COND_SEED)
+    for k in z.files:
+        if k.startswith("p:"):
+            t = torch.from_numpy(z[k])
+            assert p[k[2:]].shape == t.shape, k
+            p[k[2:]] = t.to(p[k[2:]].dtype)
+    return p
+
+
+def strided_summary(a: np.ndarray, stride: int = 4, block: int = 16):
+    """(samples a[..., ::stride, ::stride], float64 block sums over block x block tiles) of a (..., H, W) map: every pixel
+    contributes to the fixture while the .npz stays small."""
+    a = np.asarray(a)
+    H, W = a.shape[-2:]
+    hb, wb = -(-H // block) * block, -(-W // block) * block
+    pad = np.zeros(a.shape[:-2] + (hb, wb), np.float64)
+    pad[..., :H, :W] = a
+    bs = pad.reshape(a.shape[:-2] + (hb // block, block, wb // block, block)).sum(axis=(-3, -1))
+    return np.ascontiguousarray(a[..., ::stride, ::stride]), bs
+
+
 # --------------------------------------------------------------------------------------
 # GT border map (SURVEY.md section 8 f-4): the distance field of draw_thresh_map
 # --------------------------------------------------------------------------------------

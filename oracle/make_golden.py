@@ -68,6 +68,133 @@ def make_model_case(name, seed, n, h, w):
     print(name, {k: getattr(v, "shape", None) for k, v in out.items() if k in ("eval", "train")}, out["losses_mean"])
 
 
+def make_cond_params(steps=100):
+    """Conditions a network with the UNMODIFIED reference: DBTextModel + DBLoss('mean') + torch.optim.Adam(lr 0.005), as
+    src/train.py:110-117,160-172 does, for `steps` steps on 4x3x128x128 synthetic text batches.  Only the subset
+    O.cond_trainable() is trained so that the fixture is ~1.3 MB; the rest stays at O.init_params(O.COND_SEED).
+    A randomly initialised DB network has saturated sigmoid logits (kaiming init of the 64->1 ConvTranspose) and is too
+    ill-conditioned to compare a bf16 pipeline against; this one produces text-like maps."""
+    _, losses, _ = ref_import.load()
+    torch.manual_seed(0)
+    params = O.init_params(O.COND_SEED)
+    m = ref_import.build_model(params)
+    train_p = []
+    for k, p in m.named_parameters():
+        ok = O.cond_trainable(k, p.dim())
+        p.requires_grad_(ok)
+        if ok:
+            train_p.append(p)
+    opt = torch.optim.Adam(train_p, lr=0.005)
+    crit = losses.DBLoss(alpha=1.0, beta=10.0, reduction="mean", negative_ratio=3)
+    m.train()
+    hist = []
+    for it in range(steps):
+        x, g = O.synth_text_batch(4, 128, 128, it)
+        ls = crit(m(x), torch.from_numpy(g))
+        opt.zero_grad()
+        ls[-1].backward()
+        opt.step()
+        hist.append(float(ls[-1]))
+    out = {}
+    ref = O.init_params(O.COND_SEED)
+    for k, v in m.state_dict().items():
+        if not torch.equal(v, ref[k]):
+            out["p:" + k] = v.detach().numpy().copy()
+    out["loss_history"] = np.array(hist)
+    np.savez_compressed(os.path.join(GOLD, "cond_params.npz"), **out)
+    print("cond params:", len(out) - 1, "tensors,", sum(v.size for k, v in out.items() if k.startswith("p:")), "values; loss",
+          hist[0], "->", hist[-1])
+
+
+def make_baseline_size_cases():
+    """BASELINE.json configs at their real sizes on the conditioned network: config 1 (1x3x640x640 eval + the
+    post-processing front's candidate rows), config 2 (2 of the 16 images of a 640x640 training step: P, T, B, losses,
+    gradient summaries), config 4 (one 1024x1024 eval image).  Maps are stored as stride-4 samples + 16x16 block sums."""
+    import cv2
+    _, losses, postprocess = ref_import.load()
+    params = O.cond_params(GOLD)
+    m = ref_import.build_model(params)
+
+    def put(out, key, arr):
+        out[key + ":samples"], out[key + ":blocks"] = O.strided_summary(arr)
+
+    # ---- config 1
+    out = {}
+    x, _ = O.synth_text_batch(1, 640, 640, 901)
+    m.eval()
+    with torch.no_grad():
+        y = m(x).numpy()
+    put(out, "eval", y)
+    out["meta"] = np.array([901, 1, 640, 640])
+    out["x_checksum"] = np.array([x.double().sum().item(), x.double().abs().sum().item()])
+    rep = postprocess.SegDetectorRepresenter(thresh=0.25, box_thresh=0.5, max_candidates=1000, unclip_ratio=1.5)
+    P = y[0, 0]
+    bitmap = rep.binarize(torch.from_numpy(P)).numpy()
+    contours, _ = cv2.findContours((bitmap * 255).astype(np.uint8), cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+    rows = []
+    for contour in contours[:rep.max_candidates]:
+        c = contour.squeeze(1)
+        pts, sside = rep.get_mini_boxes(c)
+        score = rep.box_score_fast(P, c)
+        x0, y0, x1, y1 = c[:, 0].min(), c[:, 1].min(), c[:, 0].max(), c[:, 1].max()
+        mk = np.zeros((y1 - y0 + 1, x1 - x0 + 1), np.uint8)
+        cv2.fillPoly(mk, (c - [x0, y0]).reshape(1, -1, 2).astype(np.int32), 1)
+        keep = (not (sside < rep.min_size)) and (not (rep.box_thresh > score))
+        rows.append([score, sside, float(keep), float(mk.sum()), x0, y0, x1, y1] + list(np.array(pts).reshape(-1)))
+    out["bitmap_packed"] = np.packbits(bitmap.astype(np.uint8))
+    out["ncontours"] = np.array([len(contours)])
+    out["cands"] = np.array(rows, dtype=np.float64).reshape(len(rows), 16)
+    np.savez_compressed(os.path.join(GOLD, "model_c1_640_eval.npz"), **out)
+    print("config 1:", len(contours), "contours,", int(sum(r[2] for r in rows)), "kept; P>0.25:", float(bitmap.mean()))
+
+    # ---- config 2 (2 images)
+    out = {}
+    x, gts = O.synth_text_batch(2, 640, 640, 905)
+    m.train()
+    for p in m.parameters():
+        p.requires_grad_(True)
+    y = m(x)
+    put(out, "train", y.detach().numpy())
+    for red in ("mean", "none"):
+        m.zero_grad()
+        crit = losses.DBLoss(alpha=1.0, beta=10.0, reduction=red, negative_ratio=3)
+        ls = crit(y, torch.from_numpy(gts))
+        ls[-1].backward(retain_graph=True)
+        out[f"losses_{red}"] = np.array([float(v) for v in ls])
+        keys, summ = [], []
+        for k, p in m.named_parameters():
+            if p.grad is None:
+                continue
+            keys.append(k)
+            summ.append(grad_summary(p.grad))
+        out[f"grad_keys_{red}"] = np.array(keys)
+        out[f"grad_summary_{red}"] = np.stack(summ)
+        for k, p in m.named_parameters():      # every 1-D gradient in full (BatchNorm affine, biases): 9.9 k values
+            if p.grad is not None and p.dim() == 1:
+                out[f"grad_{red}:{k}"] = p.grad.numpy().copy()
+        out[f"grad_{red}:backbone.conv1.weight"] = m.backbone.conv1.weight.grad.numpy().copy()
+        out[f"grad_{red}:segmentation_head.binarize.6.weight"] = m.segmentation_head.binarize[6].weight.grad.numpy().copy()
+        out[f"grad_{red}:segmentation_head.thresh.6.weight"] = m.segmentation_head.thresh[6].weight.grad.numpy().copy()
+        out[f"grad_{red}:segmentation_head.thresh.3.weight"] = m.segmentation_head.thresh[3].weight.grad.numpy().copy()
+    out["meta"] = np.array([905, 2, 640, 640])
+    out["x_checksum"] = np.array([x.double().sum().item(), x.double().abs().sum().item()])
+    np.savez_compressed(os.path.join(GOLD, "model_c2_640_train.npz"), **out)
+    print("config 2:", out["losses_mean"], out["losses_none"])
+
+    # ---- config 4 (one image); a fresh model: the training forward above moved the BatchNorm running statistics
+    out = {}
+    x, _ = O.synth_text_batch(1, 1024, 1024, 909)
+    m = ref_import.build_model(params)
+    m.eval()
+    with torch.no_grad():
+        y = m(x).numpy()
+    put(out, "eval", y)
+    out["meta"] = np.array([909, 1, 1024, 1024])
+    out["x_checksum"] = np.array([x.double().sum().item(), x.double().abs().sum().item()])
+    np.savez_compressed(os.path.join(GOLD, "model_c4_1024_eval.npz"), **out)
+    print("config 4: P>0.25:", float((y[0, 0] > 0.25).mean()))
+
+
 def make_loss_cases():
     _, losses, _ = ref_import.load()
     rng = np.random.RandomState(7)
@@ -256,3 +383,5 @@ if __name__ == "__main__":
     make_model_case("model_s0_64", 0, 2, 64, 64)
     make_model_case("model_s1_72x100", 1, 2, 72, 100)
     make_model_case("model_s2_54x70", 2, 1, 54, 70)
+    make_cond_params()
+    make_baseline_size_cases()

@@ -57,6 +57,52 @@ def test_model_backward_matches_reference(red):
                                rtol=1e-3, atol=1e-4 * np.abs(z[f"grad_head_b6w_{red}"]).max())
 
 
+# ------------------------------------------------------------------ BASELINE-size cases on the conditioned network
+def _l2rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-300))
+
+
+@pytest.mark.parametrize("fname,key,training", [("model_c1_640_eval.npz", "eval", False), ("model_c4_1024_eval.npz", "eval", False),
+                                                ("model_c2_640_train.npz", "train", True)])
+def test_baseline_size_forward_matches_reference(fname, key, training):
+    """BASELINE configs 1, 4 and 2 at their real spatial sizes, weights = the reference-trained conditioned network."""
+    z = np.load(os.path.join(GOLD, fname))
+    seed, n, h, w = [int(v) for v in z["meta"]]
+    x, _ = O.synth_text_batch(n, h, w, seed)
+    assert np.allclose([x.double().sum().item(), x.double().abs().sum().item()], z["x_checksum"], rtol=1e-12)
+    with torch.no_grad():
+        y = O.dbnet_forward(O.cond_params(GOLD), x, training=training).numpy()
+    samples, blocks = O.strided_summary(y)
+    for ch in range(2):
+        assert _l2rel(samples[:, ch], z[key + ":samples"][:, ch]) <= 1e-4
+        assert _l2rel(blocks[:, ch], z[key + ":blocks"][:, ch]) <= 1e-4
+
+
+def test_baseline_size_backward_matches_reference():
+    z = np.load(os.path.join(GOLD, "model_c2_640_train.npz"))
+    seed, n, h, w = [int(v) for v in z["meta"]]
+    x, gts = O.synth_text_batch(n, h, w, seed)
+    params = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in O.cond_params(GOLD).items()}
+    y = O.dbnet_forward(params, x, training=True)
+    red = "none"
+    res = O.db_loss(y.detach().numpy(), gts, reduction=red)
+    np.testing.assert_allclose(res["losses"], z[f"losses_{red}"], rtol=1e-4)
+    y.backward(torch.from_numpy(res["grad"]).float())
+    keys = [str(k) for k in z[f"grad_keys_{red}"]]
+    for k, s in zip(keys, z[f"grad_summary_{red}"]):
+        if k.endswith("conv.bias") or k.endswith(".0.bias") or k.endswith(".3.bias"):
+            continue      # true gradient is zero (feeds a training-mode BatchNorm); both sides are rounding noise
+        gnorm = params[k].grad.double().norm().item()
+        assert abs(gnorm - s[0]) <= 1e-3 * s[0] + 1e-9, (k, gnorm, s[0])
+    for zk in z.files:
+        if zk.startswith(f"grad_{red}:"):
+            k = zk.split(":", 1)[1]
+            if k.endswith("conv.bias") or k.endswith(".0.bias") or k.endswith(".3.bias"):
+                continue
+            assert _l2rel(params[k].grad.numpy(), z[zk]) <= 1e-3, k
+
+
 # ------------------------------------------------------------------ loss (a-7 .. a-10)
 LOSS_CASES = ["random", "eval2ch", "ragged", "nopos", "allmasked", "saturated", "kbig", "ties"]
 
