@@ -33,6 +33,7 @@ struct F32Conv {
   View y;                // FPROP: output; DGRAD: dx; WGRAD: dy (read)
   WView w;               // weights (FPROP/DGRAD: read; WGRAD: written through wout)
   float* out;            // FPROP: y base; DGRAD: dx base; WGRAD: dw base
+  double* acc64;         // WGRAD: split-K partial sums are added here in double (scratch), then rounded once into out
   const float* bias;
   int n, cin, cout, ks, stride, pad;
   int Ho, Wo;            // output extent of the forward convolution
@@ -66,11 +67,14 @@ __global__ void __launch_bounds__(TH) f32_conv_kernel(const F32Conv P) {
   if (MODE == 1) { const int64_t hw = (int64_t)P.y.H * P.y.W; a_n = (int)(am / hw); const int r = (int)(am % hw); a_y = r / P.y.W; a_x = r % P.y.W; }
   if (MODE == 2) { const int kk = P.ks * P.ks; b_ci = (int)(bn / kk); const int r = (int)(bn % kk); b_kh = r / P.ks; b_kw = r % P.ks; }
   const int tx = tid & 15, ty = tid >> 4;
-  float acc[4][4];
+  // double accumulators: exact products of float operands, so a convolution result carries ONE float rounding (when it
+  // is stored) -- the fp32 mode must not be noisier than the reference it is compared with (B200 runs FP64 FMA at half the
+  // FP32 rate; this is a verification mode)
+  double acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
   for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
 #pragma unroll
@@ -103,13 +107,13 @@ __global__ void __launch_bounds__(TH) f32_conv_kernel(const F32Conv P) {
     __syncthreads();
 #pragma unroll
     for (int kl = 0; kl < BK; ++kl) {
-      float a[4], b[4];
+      double a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = As[kl][ty * 4 + i]; b[i] = Bs[kl][tx * 4 + i]; }
+      for (int i = 0; i < 4; ++i) { a[i] = (double)As[kl][ty * 4 + i]; b[i] = (double)Bs[kl][tx * 4 + i]; }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
@@ -127,16 +131,30 @@ __global__ void __launch_bounds__(TH) f32_conv_kernel(const F32Conv P) {
       if (nn >= P.N) continue;
       if (MODE == 2) {
         const int kk = P.ks * P.ks; const int ci = (int)(nn / kk); const int r = (int)(nn % kk);
-        atomicAdd(P.out + m * P.w.so + ci * P.w.si + (r / P.ks) * P.w.skh + (r % P.ks) * P.w.skw, acc[i][j]);
+        atomicAdd(P.acc64 + m * P.w.so + ci * P.w.si + (r / P.ks) * P.w.skh + (r % P.ks) * P.w.skw, acc[i][j]);
       } else {
         float* o = P.out + on * P.y.sn + oy * P.y.sh + ox * P.y.sw + nn * P.y.sc;
-        float v = acc[i][j];
-        if (MODE == 0 && P.bias) v += P.bias[nn];
-        if (P.accumulate) v += *o;
-        *o = v;
+        double v = acc[i][j];
+        if (MODE == 0 && P.bias) v += (double)P.bias[nn];
+        if (P.accumulate) v += (double)*o;
+        *o = (float)v;
       }
     }
   }
+}
+
+__global__ void f32_round_kernel(const double* __restrict__ a, float* __restrict__ o, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) o[i] = (float)a[i];
+}
+// weight gradients: zero the double scratch, accumulate the split-K partials into it, round once
+int wgrad_finish(F32Conv& P, int64_t numel, float* scratch, size_t scratch_bytes, cudaStream_t s, int (*run)(int, F32Conv&, cudaStream_t)) {
+  if (!scratch || scratch_bytes < (size_t)numel * sizeof(double)) return set_error(DBB_EWORKSPACE, "fp32 wgrad: scratch too small");
+  P.acc64 = reinterpret_cast<double*>(scratch);
+  DBB_CUDA(cudaMemsetAsync(P.acc64, 0, sizeof(double) * (size_t)numel, s));
+  int rc = run(2, P, s);
+  if (rc) return rc;
+  DBB_LAUNCH("f32_round", s, f32_round_kernel<<<(unsigned)((numel + 255) / 256 > 1184 ? 1184 : (numel + 255) / 256), 256, 0, s>>>(P.acc64, P.out, numel));
+  return DBB_OK;
 }
 
 View nhwc(const float* p, int h, int w, int ctotal, int coff) {
@@ -192,7 +210,6 @@ int conv_dgrad(const ConvGeom& g, const float* dy, const float* w, float* dx, cu
 
 int conv_wgrad(const ConvGeom& g, const float* x, int x_ctotal, int x_coff, const float* dy, int dy_ctotal, int dy_coff, float* dw,
                float* scratch, size_t scratch_bytes, cudaStream_t s) {
-  (void)scratch; (void)scratch_bytes;
   F32Conv P{};
   P.x = nhwc(x, g.h, g.w, x_ctotal, x_coff);
   P.y = nhwc(dy, g.out_h(), g.out_w(), dy_ctotal, dy_coff);
@@ -201,8 +218,7 @@ int conv_wgrad(const ConvGeom& g, const float* x, int x_ctotal, int x_coff, cons
   P.n = g.n; P.cin = g.cin; P.cout = g.cout; P.ks = g.ks; P.stride = g.stride; P.pad = g.pad;
   P.Ho = g.out_h(); P.Wo = g.out_w();
   P.M = g.cout; P.N = (int64_t)g.cin * g.ks * g.ks; P.K = (int64_t)g.n * P.Ho * P.Wo;
-  DBB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g.cout * g.cin * g.ks * g.ks, s));
-  return launch(2, P, s);
+  return wgrad_finish(P, (int64_t)g.cout * g.cin * g.ks * g.ks, scratch, scratch_bytes, s, launch);
 }
 
 // ConvTranspose2d(k2, s2), weight (ci, co, 2, 2):  y[n,2i+a,2j+b,co] = sum_ci x[n,i,j,ci] W[ci,co,a,b] + bias[co]
@@ -245,7 +261,6 @@ int convt_dgrad(const ConvGeom& g, const float* dy, int dy_ctotal, int dy_coff, 
 // dW[ci,co,a,b] = sum_{n,i,j} x[n,i,j,ci] dy[n,2i+a,2j+b,co]: WGRAD with the roles swapped ("dy" := x, "x" := dy, k2 s2)
 int convt_wgrad(const ConvGeom& g, const float* x, int x_ctotal, int x_coff, const float* dy, int dy_ctotal, int dy_coff, float* dw,
                 float* scratch, size_t scratch_bytes, cudaStream_t s) {
-  (void)scratch; (void)scratch_bytes;
   F32Conv P{};
   P.x = nhwc(dy, 2 * g.h, 2 * g.w, dy_ctotal, dy_coff);
   P.y = nhwc(x, g.h, g.w, x_ctotal, x_coff);
@@ -254,8 +269,7 @@ int convt_wgrad(const ConvGeom& g, const float* x, int x_ctotal, int x_coff, con
   P.n = g.n; P.cin = g.cout; P.cout = g.cin; P.ks = 2; P.stride = 2; P.pad = 0;
   P.Ho = g.h; P.Wo = g.w;
   P.M = g.cin; P.N = (int64_t)g.cout * 4; P.K = (int64_t)g.n * g.h * g.w;
-  DBB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g.cin * g.cout * 4, s));
-  return launch(2, P, s);
+  return wgrad_finish(P, (int64_t)g.cin * g.cout * 4, scratch, scratch_bytes, s, launch);
 }
 
 // conv1: Conv2d(3, 64, 7, stride 2, pad 3, bias=False) straight from the NCHW float32 image (no space-to-depth staging)
@@ -271,7 +285,7 @@ int conv1_fprop_f32(int n, int h, int w, const float* img, const float* wt, floa
   P.M = (int64_t)n * ho * wo; P.N = 64; P.K = 147;
   return launch(0, P, s);
 }
-int conv1_wgrad_f32(int n, int h, int w, const float* img, const float* dy, float* dw, cudaStream_t s) {
+int conv1_wgrad_f32(int n, int h, int w, const float* img, const float* dy, float* dw, float* scratch, size_t scratch_bytes, cudaStream_t s) {
   const int ho = (h + 1) / 2, wo = (w + 1) / 2;
   F32Conv P{};
   P.x = View{img, 3 * (int64_t)h * w, w, 1, (int64_t)h * w, h, w};
@@ -281,8 +295,7 @@ int conv1_wgrad_f32(int n, int h, int w, const float* img, const float* dy, floa
   P.n = n; P.cin = 3; P.cout = 64; P.ks = 7; P.stride = 2; P.pad = 3;
   P.Ho = ho; P.Wo = wo;
   P.M = 64; P.N = 147; P.K = (int64_t)n * ho * wo;
-  DBB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 64 * 147, s));
-  return launch(2, P, s);
+  return wgrad_finish(P, 64 * 147, scratch, scratch_bytes, s, launch);
 }
 
 }  // namespace dbb

@@ -50,6 +50,6 @@ int convt_wgrad(const ConvGeom& g, const float* x, int x_ctotal, int x_coff, con
                 float* scratch, size_t scratch_bytes, cudaStream_t s);
 // conv1 (7x7/2, 3->64) straight from the NCHW float32 image; y / dy NHWC float32; wt / dw OIHW (64,3,7,7)
 int conv1_fprop_f32(int n, int h, int w, const float* img, const float* wt, float* y, cudaStream_t s);
-int conv1_wgrad_f32(int n, int h, int w, const float* img, const float* dy, float* dw, cudaStream_t s);
+int conv1_wgrad_f32(int n, int h, int w, const float* img, const float* dy, float* dw, float* scratch, size_t scratch_bytes, cudaStream_t s);
 
 }  // namespace dbb

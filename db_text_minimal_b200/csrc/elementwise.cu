@@ -404,9 +404,14 @@ __device__ __forceinline__ bool last_block_arrives(unsigned* counter) {
   return is_last;
 }
 
-template <int NACC>
-__device__ __forceinline__ void reduce_groups_atomic(float (&acc)[NACC][8], int c, double* gacc /* [NACC][c] */) {
-  __shared__ float sh[EW_THREADS * 8];
+// per-thread accumulator type of the per-channel reductions: float on the bf16 product path; double in the fp32-parity mode
+// (whose reductions must not add rounding noise of their own: its results are compared with the reference at 1e-4 / 1e-3)
+template <typename T> struct AccOf { typedef float type; };
+template <> struct AccOf<float> { typedef double type; };
+
+template <int NACC, typename A>
+__device__ __forceinline__ void reduce_groups_atomic(A (&acc)[NACC][8], int c, double* gacc /* [NACC][c] */) {
+  __shared__ A sh[EW_THREADS * 8];
   const int groups = c / 8;
   const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
   const int lanes = EW_THREADS / groups;
@@ -418,7 +423,7 @@ __device__ __forceinline__ void reduce_groups_atomic(float (&acc)[NACC][8], int 
     __syncthreads();
     for (int ch = threadIdx.x; ch < c; ch += EW_THREADS) {
       const int gg = ch / 8, jj = ch % 8;
-      float s = 0.f;
+      A s = 0;
       for (int l = 0; l < lanes; ++l) s += sh[(l * groups + gg) * 8 + jj];
       atomicAdd(&gacc[a * c + ch], (double)s);
     }
@@ -428,17 +433,18 @@ __device__ __forceinline__ void reduce_groups_atomic(float (&acc)[NACC][8], int 
 template <typename T>
 __global__ void __launch_bounds__(EW_THREADS)
 bn_stats_fin_kernel(const T* __restrict__ z, int64_t P, int c, double* __restrict__ gacc, unsigned* __restrict__ counter, BnFin fin) {
+  typedef typename AccOf<T>::type A;
   const int groups = c / 8;
   const int g = threadIdx.x % groups, pl = threadIdx.x / groups, lanes = EW_THREADS / groups;
-  float acc[2][8];
+  A acc[2][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+  for (int j = 0; j < 8; ++j) { acc[0][j] = 0; acc[1][j] = 0; }
   for (int64_t p = (int64_t)blockIdx.x * lanes + pl; p < P; p += (int64_t)gridDim.x * lanes) {
     const F8 x = ld8(z + p * c + g * 8);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc[0][j] += x.v[j]; acc[1][j] += x.v[j] * x.v[j]; }
+    for (int j = 0; j < 8; ++j) { acc[0][j] += (A)x.v[j]; acc[1][j] += (A)x.v[j] * (A)x.v[j]; }
   }
-  reduce_groups_atomic<2>(acc, c, gacc);
+  reduce_groups_atomic<2, A>(acc, c, gacc);
   if (!last_block_arrives(counter)) return;
   bn_finalize_channels(fin, c, (double)P, gacc, threadIdx.x, EW_THREADS);
   if (threadIdx.x == 0) *counter = 0u;
@@ -456,16 +462,17 @@ bn_bwd_reduce_fin_kernel(const T* __restrict__ dout, int dout_ctotal, int dout_c
   const F8 mean = ldf8(stats4 + 2 * c + g * 8), inv = ldf8(stats4 + 3 * c + g * 8);
   F8 sc, sh;
   if (MASK == 2) { sc = ldf8(stats4 + g * 8); sh = ldf8(stats4 + c + g * 8); }
-  float acc[2][8];
+  typedef typename AccOf<T>::type A;
+  A acc[2][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+  for (int j = 0; j < 8; ++j) { acc[0][j] = 0; acc[1][j] = 0; }
   const int64_t step = (int64_t)gridDim.x * lanes;
   auto body = [&](F8 dy, const F8& m, const F8& x) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (MASK == 1) dy.v[j] = m.v[j] > 0.f ? dy.v[j] : 0.f;
       if (MASK == 2) dy.v[j] = fmaf(x.v[j], sc.v[j], sh.v[j]) > 0.f ? dy.v[j] : 0.f;
-      acc[0][j] += dy.v[j]; acc[1][j] += dy.v[j] * (x.v[j] - mean.v[j]) * inv.v[j];
+      acc[0][j] += (A)dy.v[j]; acc[1][j] += (A)dy.v[j] * (A)((x.v[j] - mean.v[j]) * inv.v[j]);
     }
   };
   int64_t p = (int64_t)blockIdx.x * lanes + pl;
@@ -484,7 +491,7 @@ bn_bwd_reduce_fin_kernel(const T* __restrict__ dout, int dout_ctotal, int dout_c
     const F8 x0 = ld8(z + p * c + g * 8);
     body(dy0, m0, x0);
   }
-  reduce_groups_atomic<2>(acc, c, gacc);
+  reduce_groups_atomic<2, A>(acc, c, gacc);
   if (!last_block_arrives(counter)) return;
   const double count = (double)P;
   for (int sg = 0; sg < fin.nseg; ++sg) {

@@ -242,13 +242,15 @@ __device__ __forceinline__ void bwd_phase_a_store(float (&dzs)[2][4][HT_TILE], c
 
 constexpr int HT_NACC = 6;   // per channel: dW2[4 taps], sum dy, sum dy*xhat
 
+template <typename T> struct HtAcc { typedef float type; };
+template <> struct HtAcc<float> { typedef double type; };      // fp32-parity mode: reductions add no rounding noise of their own
 template <bool PIPE, typename T>
-__global__ void __launch_bounds__(HT_THREADS, 2)
+__global__ void __launch_bounds__(HT_THREADS, sizeof(T) == 2 ? 2 : 1)
 head_tail_bwd_reduce_kernel(const T* __restrict__ zt, int n_img, int h2, int w2, const float* __restrict__ stats4,
                             const float* __restrict__ w2b, const float* __restrict__ w2t, const float* __restrict__ out,
                             const float* __restrict__ dout, float k, float* __restrict__ partials /* [grid][128*6 + 2] */) {
   __shared__ float dzs[2][4][HT_TILE];
-  __shared__ float red[HT_THREADS][9];   // padded rows
+  __shared__ typename HtAcc<T>::type red[HT_THREADS][9];   // padded rows
   __shared__ uint64_t full_bar[HT_STAGES];
   extern __shared__ __align__(128) uint8_t ring_smem[];
   const int l16 = threadIdx.x & 15, pslot = threadIdx.x >> 4;
@@ -260,9 +262,11 @@ head_tail_bwd_reduce_kernel(const T* __restrict__ zt, int n_img, int h2, int w2,
 #pragma unroll
     for (int j = 0; j < 8; ++j) { mean[j] = stats4[256 + ch0 + j]; inv[j] = stats4[384 + ch0 + j]; }
   }
-  float accW[8][4], accS[8], accQ[8], accB = 0.f;
+  typedef typename HtAcc<T>::type A;
+  constexpr bool WIDE = sizeof(A) == 8;
+  A accW[8][4], accS[8], accQ[8], accB = 0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { accS[j] = 0.f; accQ[j] = 0.f; for (int t = 0; t < 4; ++t) accW[j][t] = 0.f; }
+  for (int j = 0; j < 8; ++j) { accS[j] = 0; accQ[j] = 0; for (int t = 0; t < 4; ++t) accW[j][t] = 0; }
   const int tiles_per_row = (w2 + HT_TILE - 1) / HT_TILE;
   const int64_t ntiles = (int64_t)n_img * h2 * tiles_per_row;
   const int H = 2 * h2, W = 2 * w2;
@@ -297,19 +301,25 @@ head_tail_bwd_reduce_kernel(const T* __restrict__ zt, int n_img, int h2, int w2,
         float dz[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) dz[t] = dzs[br][t][px];
-        if ((l16 & 7) == 0) accB += dz[0] + dz[1] + dz[2] + dz[3];
+        if ((l16 & 7) == 0) accB += (A)dz[0] + (A)dz[1] + (A)dz[2] + (A)dz[3];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float a = fmaxf(fmaf(z.v[j], L.sc[j], L.sh[j]), 0.f);
-          const float2 w01 = fma2(a, make_float2(dz[0], dz[1]), make_float2(accW[j][0], accW[j][1]));
-          const float2 w23 = fma2(a, make_float2(dz[2], dz[3]), make_float2(accW[j][2], accW[j][3]));
-          accW[j][0] = w01.x; accW[j][1] = w01.y; accW[j][2] = w23.x; accW[j][3] = w23.y;
+          if (WIDE) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) accW[j][t] += (A)a * (A)dz[t];
+          } else {
+            const float2 w01 = fma2(a, make_float2(dz[0], dz[1]), make_float2((float)accW[j][0], (float)accW[j][1]));
+            const float2 w23 = fma2(a, make_float2(dz[2], dz[3]), make_float2((float)accW[j][2], (float)accW[j][3]));
+            accW[j][0] = w01.x; accW[j][1] = w01.y; accW[j][2] = w23.x; accW[j][3] = w23.y;
+          }
           const float2 d2 = __ffma2_rn(make_float2(dz[0], dz[1]), make_float2(L.w[j][0], L.w[j][1]),
                                        __fmul2_rn(make_float2(dz[2], dz[3]), make_float2(L.w[j][2], L.w[j][3])));
           const float da = d2.x + d2.y;
           const float dy = a > 0.f ? da : 0.f;
-          accS[j] += dy;
-          accQ[j] = fmaf(dy, (z.v[j] - mean[j]) * inv[j], accQ[j]);
+          accS[j] += (A)dy;
+          if (WIDE) accQ[j] += (A)dy * (A)((z.v[j] - mean[j]) * inv[j]);
+          else accQ[j] = fmaf(dy, (z.v[j] - mean[j]) * inv[j], (float)accQ[j]);
         }
       }
     }
@@ -327,11 +337,11 @@ head_tail_bwd_reduce_kernel(const T* __restrict__ zt, int n_img, int h2, int w2,
     __syncthreads();
     if (threadIdx.x < 128) {      // thread -> channel (l = t/8, j = t%8)
       const int l = threadIdx.x >> 3, j = threadIdx.x & 7;
-      float s = 0.f;
+      A s = 0;
 #pragma unroll
       for (int ps = 0; ps < 16; ++ps) s += red[ps * 16 + l][j];
       const int ch = (l >> 3) * 64 + (l & 7) * 8 + j;
-      my[ch * HT_NACC + q] = s;
+      my[ch * HT_NACC + q] = (float)s;
     }
   }
   (void)ch0;
@@ -339,9 +349,9 @@ head_tail_bwd_reduce_kernel(const T* __restrict__ zt, int n_img, int h2, int w2,
   red[threadIdx.x][0] = accB;
   __syncthreads();
   if (threadIdx.x < 2) {
-    float s = 0.f;
+    A s = 0;
     for (int ps = 0; ps < 16; ++ps) s += red[ps * 16 + threadIdx.x * 8][0];
-    my[128 * HT_NACC + threadIdx.x] = s;
+    my[128 * HT_NACC + threadIdx.x] = (float)s;
   }
 }
 

@@ -777,7 +777,7 @@ static int net_backward_t(DbbNet* net, const float* x_img, const float* out, con
     RC(fork_w(c));
     if constexpr (F32) {
       if (!x_img) return set_error(DBB_EINVAL, "net_backward: the fp32 mode needs the input image (dbb_net_backward_ex)");
-      RC(conv1_wgrad_f32(N, net->h, net->w, x_img, c.p(net->d_z0), c.grad(P("backbone.conv1.weight")), c.sw));
+      RC(conv1_wgrad_f32(N, net->h, net->w, x_img, c.p(net->d_z0), c.grad(P("backbone.conv1.weight")), c.wgs(), WGRAD_SCRATCH_BYTES, c.sw));
     } else {
       RC(conv1_wgrad(N, net->h, net->w, c.p(net->s2d), c.p(net->d_z0), c.template p<float>(net->dw_s2d), c.wgs(), WGRAD_SCRATCH_BYTES, c.sw));
       RC(conv1_wgrad_unpack(c.template p<float>(net->dw_s2d), c.grad(P("backbone.conv1.weight")), c.sw));

@@ -114,8 +114,9 @@ def init_params(seed: int = 0) -> Dict[str, torch.Tensor]:
 class _Ctx:
     """Carries mode + collects updated BN buffers (functional restatement of nn.BatchNorm2d)."""
 
-    def __init__(self, params, training: bool, quant=None):
+    def __init__(self, params, training: bool, quant=None, taps=None):
         self.p = params
+        self.taps = taps          # optional dict: named intermediate activations (the executor's dbb_net_debug_read names)
         self.training = training
         self.new_buffers: Dict[str, torch.Tensor] = {}
         self.q = quant if quant is not None else (lambda t: t)
@@ -131,6 +132,11 @@ class _Ctx:
             self.new_buffers[prefix + ".running_var"] = rv
             self.new_buffers[prefix + ".num_batches_tracked"] = self.p[prefix + ".num_batches_tracked"] + 1
         return y
+
+    def tap(self, name, t):
+        if self.taps is not None:
+            self.taps[name] = t.detach()
+        return t
 
     def conv(self, x, prefix, stride=1, padding=0):
         w = self.q(self.p[prefix + ".weight"])
@@ -156,11 +162,11 @@ def _basic_block(c: _Ctx, x, pre: str, stride: int):
 def resnet18_forward(c: _Ctx, x):
     """src/modules/resnet.py:231-242 -> (c2, c3, c4, c5)."""
     x = F.relu(c.bn(c.conv(x, "backbone.conv1", 2, 3), "backbone.bn1"))
-    x = F.max_pool2d(x, 3, 2, 1)
+    x = c.tap("x1", F.max_pool2d(x, 3, 2, 1))
     feats = []
     for li in range(1, 5):
         for bi in range(2):
-            x = _basic_block(c, x, f"backbone.layer{li}.{bi}", 2 if (li > 1 and bi == 0) else 1)
+            x = c.tap(f"block{(li - 1) * 2 + bi}.out", _basic_block(c, x, f"backbone.layer{li}.{bi}", 2 if (li > 1 and bi == 0) else 1))
         feats.append(x)
     return tuple(feats)
 
@@ -188,7 +194,9 @@ def fpn_forward(c: _Ctx, feats):
     p2 = cbr(nearest_upsample(p3, l2.shape[2:]) + l2, "smooth_p2", 1)
     hw = p2.shape[2:]
     cat = torch.cat([p2, nearest_upsample(p3, hw), nearest_upsample(p4, hw), nearest_upsample(p5, hw)], 1)
-    return F.relu(c.bn(c.conv(cat, sb + "conv.0", 1, 1), sb + "conv.1"))
+    for nm, t in (("p5", p5), ("l4", l4), ("p4", p4), ("l3", l3), ("p3", p3), ("l2", l2), ("cat", cat)):
+        c.tap(nm, t)
+    return c.tap("af", F.relu(c.bn(c.conv(cat, sb + "conv.0", 1, 1), sb + "conv.1")))
 
 
 def step_function(p, t, k=50.0):
@@ -199,20 +207,23 @@ def step_function(p, t, k=50.0):
 def dbhead_forward(c: _Ctx, x, k=50.0):
     """src/modules/segmentation_head.py:35-45."""
     outs = []
+    ahs = []
     for br in ("binarize", "thresh"):
         pre = "segmentation_head." + br
         y = F.relu(c.bn(c.conv(x, pre + ".0", 1, 1), pre + ".1"))
+        ahs.append(y)
         y = F.relu(c.bn(c.q(c.convT(y, pre + ".3")), pre + ".4"))
         outs.append(torch.sigmoid(F.conv_transpose2d(y, c.p[pre + ".6.weight"], c.p[pre + ".6.bias"], stride=2)))
+    c.tap("ah", torch.cat(ahs, 1))
     if c.training:
         outs.append(step_function(outs[0], outs[1], k))
     return torch.cat(outs, 1)
 
 
-def dbnet_forward(params, x, training: bool, quant=None, return_buffers=False):
+def dbnet_forward(params, x, training: bool, quant=None, return_buffers=False, taps=None):
     """src/models.py:34-48.  ``quant`` (optional) is applied to conv inputs, weights and raw
     conv outputs -- used to emulate the product's bf16 rounding points."""
-    c = _Ctx(params, training, quant)
+    c = _Ctx(params, training, quant, taps)
     H, W = x.shape[2:]
     y = dbhead_forward(c, fpn_forward(c, resnet18_forward(c, x)))
     if tuple(y.shape[2:]) != (H, W):
