@@ -13,6 +13,10 @@ import sys
 import types
 
 REF_SRC = "/root/reference/src"
+if not os.path.isdir(REF_SRC):      # GPU box: the copy staged by oracle/stage_ref.py (bench.py's reference legs only)
+    _staged = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "src")
+    if os.path.isfile(os.path.join(_staged, "models.py")):
+        REF_SRC = _staged
 
 
 def available() -> bool:
