@@ -61,6 +61,11 @@ def lib():
     sig("dbb_postprocess_workspace", sz, [i64, i64, i64])
     sig("dbb_binarize", i32, [vp, i64, i32, i64, i64, f32, vp, vp])
     sig("dbb_binarize_ccl_score", i32, [vp, i64, i32, i64, i64, f32, f64, vp, vp, vp, vp, i32, vp, sz, vp])
+    sig("dbb_ccl_border_points", i32, [vp, sz, i64, i64, i64, vp, vp, i32, vp])
+    sig("dbb_boxes_from_border_points", i32, [vp, vp, vp, vp, i64, i32, i32, i64, i64, vp, f32, i32, vp, vp, vp, vp, i32])
+    sig("dbb_mini_box", i32, [vp, i32, vp, vp])
+    sig("dbb_clipper_offset", i32, [vp, i32, f64, f64, vp, i32, vp, i32])
+    sig("dbb_clipper_offset_raw", i32, [vp, i32, f64, f64, vp, i32])
     sig("dbb_net_num_params", i32, [])
     sig("dbb_net_param_name", C.c_char_p, [i32])
     sig("dbb_net_param_numel", i32, [i32])

@@ -344,14 +344,14 @@ ccl_scan_kernel(const int* __restrict__ blk_count, int* __restrict__ blk_off, in
   if (threadIdx.x == 0) n_cands[img] = carry;
 }
 __global__ void __launch_bounds__(CCL_THREADS)
-ccl_emit_kernel(const uint8_t* __restrict__ bitmap, int h, int w, const int* __restrict__ label, const CompStat* __restrict__ stat,
+ccl_emit_kernel(const uint8_t* __restrict__ bitmap, int h, int w, const int* __restrict__ label, CompStat* __restrict__ stat,
                 const int* __restrict__ blk_off, int nblk, double box_thresh, DbbCandidate* __restrict__ cands, int max_cands,
                 int32_t* __restrict__ labels_out) {
   const int img = blockIdx.y, b = blockIdx.x;
   const int64_t hw = (int64_t)h * w;
   const uint8_t* bm = bitmap + img * hw;
   const int* L = label + img * (hw + 1);
-  const CompStat* S = stat + img * hw;
+  CompStat* S = stat + img * hw;
   const int r_out = L[hw];
   const int64_t i = (int64_t)b * CCL_THREADS + threadIdx.x;
   const bool in = i < hw;
@@ -368,8 +368,14 @@ ccl_emit_kernel(const uint8_t* __restrict__ bitmap, int h, int w, const int* __r
   int rank = __popc(bal & ~((2u << lane) - 1u));      // lanes above me in my warp
   for (int k = wid + 1; k < CCL_THREADS / 32; ++k) rank += wcount[k];
   rank += blk_off[img * nblk + b];
-  if (rank >= max_cands) return;
   const CompStat s = S[i];
+  // (last reader of the statistics slot: acc_count now carries the candidate's output slot for ccl_points_kernel,
+  //  -1 = not an emitted, kept candidate)
+  {
+    const double sc = (s.sum + s.acc_sum) / (double)(s.count + s.acc_count);
+    S[i].acc_count = (rank < max_cands && !(box_thresh > sc)) ? rank : -1;
+  }
+  if (rank >= max_cands) return;
   DbbCandidate cd;
   const int y = (int)(i / w), x = (int)(i - (int64_t)y * w);
   cd.kind = bm[i] ? 0 : 1;
@@ -384,9 +390,91 @@ ccl_emit_kernel(const uint8_t* __restrict__ bitmap, int h, int w, const int* __r
   cands[(int64_t)img * max_cands + rank] = cd;
 }
 
+// G: border points of the KEPT candidates (src/postprocess.py:119-121: the contour handed to get_mini_boxes).  cv2.minAreaRect
+// only sees the convex hull of the contour, and hull(outer border of F) = hull(pixels of F) = hull(end pixels of F's runs),
+// hull(hole border of G) = hull(foreground pixels 4-adjacent to G) -- so the device emits, per kept candidate, the two end
+// pixels of each of its segment runs (holes: the foreground pixels left / right of each run and the first / last foreground
+// pixel above / below it).  A few thousand (slot, x, y) triples per image cross to the host instead of the bitmap.
+__global__ void __launch_bounds__(CCL_THREADS)
+ccl_points_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, const int* __restrict__ label,
+                  const CompStat* __restrict__ stat, int32_t* __restrict__ points, int32_t* __restrict__ n_points, int cap) {
+  const int64_t hw = (int64_t)h * w;
+  const int lane = threadIdx.x & 31;
+  const int64_t nseg = (int64_t)n * h * wq;
+  const int64_t wstride = (int64_t)gridDim.x * (CCL_THREADS / 32);
+  for (int64_t widx = (int64_t)blockIdx.x * (CCL_THREADS / 32) + (threadIdx.x >> 5); widx < nseg; widx += wstride) {
+    Seg g; seg_of(widx, h, wq, w, g);
+    if (lane >= g.nvalid) continue;
+    const unsigned cur = bits[widx];
+    const unsigned st = run_starts(cur, g.nvalid);
+    if (!(st & (1u << lane))) continue;                       // one lane per run
+    const int* L = label + g.img * (hw + 1);
+    const CompStat* S = stat + g.img * hw;
+    const int a = lane;
+    const unsigned later = (lane >= 31) ? 0u : (st & ~((2u << lane) - 1u));
+    int b = later ? (__ffs(later) - 2) : 31;
+    if (b > g.nvalid - 1) b = g.nvalid - 1;
+    const int i = g.y * w + g.x0 + a;
+    const int r = L[i];
+    if (r == L[hw]) continue;                                 // outside region
+    const int slot = S[r].acc_count;
+    if (slot < 0) continue;
+    int px[6], py[6], k = 0;
+    const int xs = g.x0 + a, xe = g.x0 + b;
+    // does the run really start / end here, or does it continue in the neighbouring 32-pixel word?
+    const bool same_class_left = a == 0 && g.s > 0 && (((bits[widx - 1] >> 31) & 1u) == ((cur >> a) & 1u));
+    const bool same_class_right = b == g.nvalid - 1 && g.s < wq - 1 && ((bits[widx + 1] & 1u) == ((cur >> b) & 1u));
+    if ((cur >> lane) & 1u) {
+      if (!same_class_left) { px[k] = xs; py[k++] = g.y; }
+      if (!same_class_right && (xe != xs || same_class_left)) { px[k] = xe; py[k++] = g.y; }
+    } else {
+      const unsigned runmask = ((b >= 31) ? 0xffffffffu : ((2u << b) - 1u)) & ~((1u << a) - 1u);
+      // left / right foreground neighbours (a hole never touches the frame, so they exist whenever the run really ends here)
+      if (!same_class_left && xs > 0) { px[k] = xs - 1; py[k++] = g.y; }
+      if (!same_class_right && xe < w - 1) { px[k] = xe + 1; py[k++] = g.y; }
+      if (g.y > 0) {
+        const unsigned m = bits[widx - wq] & runmask;
+        if (m) { px[k] = g.x0 + __ffs(m) - 1; py[k++] = g.y - 1; if (m & (m - 1)) { px[k] = g.x0 + 31 - __clz(m); py[k++] = g.y - 1; } }
+      }
+      if (g.y < h - 1) {
+        const unsigned m = bits[widx + wq] & runmask;
+        if (m) { px[k] = g.x0 + __ffs(m) - 1; py[k++] = g.y + 1; if (m & (m - 1)) { px[k] = g.x0 + 31 - __clz(m); py[k++] = g.y + 1; } }
+      }
+    }
+    if (k == 0) continue;
+    const int pos = atomicAdd(&n_points[g.img], k);
+    for (int j = 0; j < k; ++j) {
+      if (pos + j < cap) {
+        int32_t* o = points + ((int64_t)g.img * cap + pos + j) * 2;
+        o[0] = slot; o[1] = (py[j] << 16) | px[j];
+      }
+    }
+  }
+}
+
 }  // namespace dbb
 
 using namespace dbb;
+
+// Must follow dbb_binarize_ccl_score on the SAME workspace and stream (it reads the packed bitmap, the final labels and the
+// per-root candidate slots left there).  points: (N, cap, 2) int32 {candidate slot, (y << 16) | x}; n_points: (N) int32, the
+// number of points the image produced (> cap means the buffer was too small: call again with a larger one).
+extern "C" int dbb_ccl_border_points(const void* workspace, size_t workspace_bytes, int64_t n, int64_t h, int64_t w, int32_t* points,
+                                     int32_t* n_points, int cap, void* stream) {
+  if (!workspace || !points || !n_points || cap <= 0) return set_error(DBB_EINVAL, "ccl_border_points: bad argument");
+  if (h >= 32768 || w >= 65536) return set_error(DBB_EUNSUPPORTED, "ccl_border_points: points are packed as (y << 16) | x");
+  if (workspace_bytes < dbb_postprocess_workspace(n, h, w)) return set_error(DBB_EWORKSPACE, "ccl_border_points: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t hw = h * w;
+  const int wq = (int)((w + 31) / 32);
+  CclWs ws = ccl_carve(const_cast<void*>(workspace), n, hw, h, wq);
+  const int64_t nseg = n * h * wq;
+  int gseg = (int)((nseg + CCL_THREADS / 32 - 1) / (CCL_THREADS / 32));
+  if (gseg > DBB_NUM_SMS * 16) gseg = DBB_NUM_SMS * 16;
+  DBB_CUDA(cudaMemsetAsync(n_points, 0, sizeof(int32_t) * (size_t)n, s));
+  DBB_LAUNCH("ccl_points", s, ccl_points_kernel<<<gseg, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, points, n_points, cap));
+  return DBB_OK;
+}
 
 extern "C" size_t dbb_postprocess_workspace(int64_t n, int64_t h, int64_t w) {
   const int64_t hw = h * w, wq = (w + 31) / 32;

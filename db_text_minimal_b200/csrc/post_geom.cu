@@ -1,0 +1,405 @@
+// post_geom.cu -- host back half of SegDetectorRepresenter.boxes_from_bitmap (box mode), in C++ (no CUDA in this file).
+//
+// Replaces, for the candidates the device front kept (score filter) and on the border points it emitted
+// (ccl.cu: ccl_points_kernel), src/postprocess.py:119-147 of the reference:
+//   :121,158-184  get_mini_boxes  = cv2.minAreaRect(contour) -> cv2.boxPoints -> corner ordering, sside = min(w, h)
+//   :122          sside < min_size                                   -> dropped
+//   :132,150-156  unclip          = shapely Polygon(box).area * ratio / .length, pyclipper round-join offset by that distance
+//   :134-136      get_mini_boxes of the expanded polygon, sside < min_size + 2 -> dropped
+//   :142-147      rescale to the destination size in float32, round half to even, clip, int16
+// cv2.minAreaRect is restated from OpenCV's rotating calipers (imgproc/rotcalipers.cpp: same float32 arithmetic, same
+// tie-breaking "area <= minarea"), cv2.boxPoints from RotatedRect::points.  The offset is ClipperOffset (Clipper 6.4.2,
+// JT_ROUND, ET_CLOSEDPOLYGON, arc tolerance 0.25) for CONVEX input -- a min-area box always is; its arithmetic is pinned
+// by nothing (pyclipper is absent from the reference tree and from this image): "parity unpinned", see DESIGN.md.
+#include "common.cuh"
+#include "post_geom.h"
+#include <algorithm>
+#include <cmath>
+#include <cfloat>
+#include <climits>
+#include <thread>
+#include <vector>
+
+namespace dbb {
+
+// ---------------------------------------------------------------------------------------------- convex hull
+static inline int64_t cross(const IPt& o, const IPt& a, const IPt& b) {
+  return (int64_t)(a.x - o.x) * (b.y - o.y) - (int64_t)(a.y - o.y) * (b.x - o.x);
+}
+// Andrew's monotone chain on points sorted by (x, y) without duplicates: strictly convex vertices, counter-clockwise in a
+// y-up frame, starting at pts[0]
+static void hull_chain(const std::vector<IPt>& pts, std::vector<IPt>& hull) {
+  const int n = (int)pts.size();
+  hull.clear();
+  if (n < 3) { hull = pts; return; }
+  hull.resize(2 * n);
+  int k = 0;
+  for (int i = 0; i < n; ++i) {
+    while (k >= 2 && cross(hull[k - 2], hull[k - 1], pts[i]) <= 0) --k;
+    hull[k++] = pts[i];
+  }
+  for (int i = n - 2, t = k + 1; i >= 0; --i) {
+    while (k >= t && cross(hull[k - 2], hull[k - 1], pts[i]) <= 0) --k;
+    hull[k++] = pts[i];
+  }
+  hull.resize(k - 1);
+}
+// cv2.minAreaRect runs its calipers on convexHull(points, clockwise=True) (measured against cv2 4.13: the other orientation
+// never reproduces its angle / size assignment): the hull starts at the lexicographically smallest (x, then y) point and
+// runs clockwise in a y-up frame; two points come largest first.
+static void opencv_order(std::vector<IPt>& hull) {
+  const int n = (int)hull.size();
+  if (n == 2) { if (hull[0].x < hull[1].x || (hull[0].x == hull[1].x && hull[0].y < hull[1].y)) std::swap(hull[0], hull[1]); return; }
+  if (n < 3) return;
+  double a2 = 0;
+  int lo = 0;
+  for (int i = 0; i < n; ++i) {
+    const IPt &p = hull[i], &q = hull[(i + 1) % n];
+    a2 += (double)p.x * q.y - (double)q.x * p.y;
+    if (p.x < hull[lo].x || (p.x == hull[lo].x && p.y < hull[lo].y)) lo = i;
+  }
+  std::rotate(hull.begin(), hull.begin() + lo, hull.end());
+  if (a2 > 0) std::reverse(hull.begin() + 1, hull.end());
+}
+void convex_hull(std::vector<IPt>& pts, std::vector<IPt>& hull) {
+  std::sort(pts.begin(), pts.end(), [](const IPt& a, const IPt& b) { return a.x < b.x || (a.x == b.x && a.y < b.y); });
+  pts.erase(std::unique(pts.begin(), pts.end(), [](const IPt& a, const IPt& b) { return a.x == b.x && a.y == b.y; }), pts.end());
+  hull_chain(pts, hull);
+  opencv_order(hull);
+}
+// the same hull from per-row extremes (device border points bucketed by row): no sort -- rows are visited in order and the
+// chain runs on (y, x)-swapped coordinates
+void convex_hull_rows(const std::vector<int>& row_min, const std::vector<int>& row_max, int y0, std::vector<IPt>& scratch, std::vector<IPt>& hull) {
+  scratch.clear();
+  for (size_t r = 0; r < row_min.size(); ++r) {
+    if (row_min[r] > row_max[r]) continue;
+    scratch.push_back(IPt{y0 + (int)r, row_min[r]});                       // swapped: (x', y') = (y, x)
+    if (row_max[r] != row_min[r]) scratch.push_back(IPt{y0 + (int)r, row_max[r]});
+  }
+  hull_chain(scratch, hull);
+  for (IPt& p : hull) std::swap(p.x, p.y);
+  opencv_order(hull);
+}
+
+// ---------------------------------------------------------------------------------------------- cv2.minAreaRect
+// rotating calipers, float32, as OpenCV's rotatingCalipers(..., CALIPERS_MINAREARECT, out): out = {corner, vec1, vec2}
+static void rotating_calipers(const FPt* points, int n, float* out) {
+  float minarea = FLT_MAX;
+  std::vector<float> inv_len(n);
+  std::vector<FPt> vect(n);
+  int left = 0, bottom = 0, right = 0, top = 0;
+  int seq[4] = {-1, -1, -1, -1};
+  float orientation = 0, base_a, base_b = 0;
+  FPt pt0 = points[0];
+  float left_x = pt0.x, right_x = pt0.x, top_y = pt0.y, bottom_y = pt0.y;
+  for (int i = 0; i < n; ++i) {
+    if (pt0.x < left_x) left_x = pt0.x, left = i;
+    if (pt0.x > right_x) right_x = pt0.x, right = i;
+    if (pt0.y > top_y) top_y = pt0.y, top = i;
+    if (pt0.y < bottom_y) bottom_y = pt0.y, bottom = i;
+    const FPt pt = points[(i + 1 < n) ? i + 1 : 0];
+    const double dx = pt.x - pt0.x, dy = pt.y - pt0.y;
+    vect[i].x = (float)dx; vect[i].y = (float)dy;
+    inv_len[i] = (float)(1. / std::sqrt(dx * dx + dy * dy));
+    pt0 = pt;
+  }
+  {
+    double ax = vect[n - 1].x, ay = vect[n - 1].y;
+    for (int i = 0; i < n; ++i) {
+      const double bx = vect[i].x, by = vect[i].y;
+      const double convexity = ax * by - ay * bx;
+      if (convexity != 0) { orientation = (convexity > 0) ? 1.f : -1.f; break; }
+      ax = bx; ay = by;
+    }
+  }
+  base_a = orientation;
+  seq[0] = bottom; seq[1] = right; seq[2] = top; seq[3] = left;
+  int best_left = 0, best_bottom = 0;
+  float best_a = 1.f, best_b = 0.f, best_w = 0.f, best_h = 0.f;
+  for (int k = 0; k < n; ++k) {
+    const float dp[4] = {
+        +base_a * vect[seq[0]].x + base_b * vect[seq[0]].y,
+        -base_b * vect[seq[1]].x + base_a * vect[seq[1]].y,
+        -base_a * vect[seq[2]].x - base_b * vect[seq[2]].y,
+        +base_b * vect[seq[3]].x - base_a * vect[seq[3]].y,
+    };
+    float maxcos = dp[0] * inv_len[seq[0]];
+    int main_element = 0;
+    for (int i = 1; i < 4; ++i) {
+      const float cosalpha = dp[i] * inv_len[seq[i]];
+      if (cosalpha > maxcos) { main_element = i; maxcos = cosalpha; }
+    }
+    {
+      const int pindex = seq[main_element];
+      const float lead_x = vect[pindex].x * inv_len[pindex], lead_y = vect[pindex].y * inv_len[pindex];
+      switch (main_element) {
+        case 0: base_a = lead_x; base_b = lead_y; break;
+        case 1: base_a = lead_y; base_b = -lead_x; break;
+        case 2: base_a = -lead_x; base_b = -lead_y; break;
+        default: base_a = -lead_y; base_b = lead_x; break;
+      }
+    }
+    seq[main_element] += 1;
+    if (seq[main_element] == n) seq[main_element] = 0;
+    float dx = points[seq[1]].x - points[seq[3]].x, dy = points[seq[1]].y - points[seq[3]].y;
+    const float width = dx * base_a + dy * base_b;
+    dx = points[seq[2]].x - points[seq[0]].x; dy = points[seq[2]].y - points[seq[0]].y;
+    const float height = -dx * base_b + dy * base_a;
+    const float area = width * height;
+    if (area <= minarea) {
+      minarea = area;
+      best_left = seq[3]; best_a = base_a; best_w = width; best_b = base_b; best_h = height; best_bottom = seq[0];
+    }
+  }
+  const float A1 = best_a, B1 = best_b, A2 = -best_b, B2 = best_a;
+  const float C1 = A1 * points[best_left].x + points[best_left].y * B1;
+  const float C2 = A2 * points[best_bottom].x + points[best_bottom].y * B2;
+  const float idet = 1.f / (A1 * B2 - A2 * B1);
+  out[0] = (C1 * B2 - C2 * B1) * idet;
+  out[1] = (A1 * C2 - A2 * C1) * idet;
+  out[2] = A1 * best_w; out[3] = B1 * best_w;
+  out[4] = A2 * best_h; out[5] = B2 * best_h;
+}
+
+RotRect min_area_rect_hull(const std::vector<IPt>& hull) {
+  const int n = (int)hull.size();
+  RotRect box{0, 0, 0, 0, 0};
+  if (n > 2) {
+    std::vector<FPt> hp(n);
+    for (int i = 0; i < n; ++i) { hp[i].x = (float)hull[i].x; hp[i].y = (float)hull[i].y; }
+    float out[6];
+    rotating_calipers(hp.data(), n, out);
+    box.cx = out[0] + (out[2] + out[4]) * 0.5f;
+    box.cy = out[1] + (out[3] + out[5]) * 0.5f;
+    box.w = (float)std::sqrt((double)out[2] * out[2] + (double)out[3] * out[3]);
+    box.h = (float)std::sqrt((double)out[4] * out[4] + (double)out[5] * out[5]);
+    box.angle = (float)std::atan2((double)out[3], (double)out[2]);
+  } else if (n == 2) {
+    box.cx = ((float)hull[0].x + (float)hull[1].x) * 0.5f;
+    box.cy = ((float)hull[0].y + (float)hull[1].y) * 0.5f;
+    const double dx = (double)hull[1].x - hull[0].x, dy = (double)hull[1].y - hull[0].y;
+    box.w = (float)std::sqrt(dx * dx + dy * dy);
+    box.h = 0;
+    box.angle = (float)std::atan2(dy, dx);
+  } else if (n == 1) {
+    box.cx = (float)hull[0].x; box.cy = (float)hull[0].y;
+  }
+  box.angle = (float)(box.angle * 180 / 3.1415926535897932384626433832795);
+  return box;
+}
+RotRect min_area_rect(std::vector<IPt>& pts) {
+  std::vector<IPt> hull;
+  convex_hull(pts, hull);
+  return min_area_rect_hull(hull);
+}
+
+// cv2.boxPoints (RotatedRect::points)
+void box_points(const RotRect& r, FPt pt[4]) {
+  const double ang = r.angle * 3.1415926535897932384626433832795 / 180.;
+  const float b = (float)std::cos(ang) * 0.5f, a = (float)std::sin(ang) * 0.5f;
+  pt[0].x = r.cx - a * r.h - b * r.w;
+  pt[0].y = r.cy + b * r.h - a * r.w;
+  pt[1].x = r.cx + a * r.h - b * r.w;
+  pt[1].y = r.cy - b * r.h - a * r.w;
+  pt[2].x = 2 * r.cx - pt[0].x;
+  pt[2].y = 2 * r.cy - pt[0].y;
+  pt[3].x = 2 * r.cx - pt[1].x;
+  pt[3].y = 2 * r.cy - pt[1].y;
+}
+
+// src/postprocess.py:158-184: the four corners sorted by x (stable), then paired by y; returns sside = min(w, h)
+static float mini_box_rect(const RotRect& r, FPt box[4]);
+float mini_box(std::vector<IPt>& contour, FPt box[4]) { return mini_box_rect(min_area_rect(contour), box); }
+float mini_box_hull(const std::vector<IPt>& hull, FPt box[4]) { return mini_box_rect(min_area_rect_hull(hull), box); }
+static float mini_box_rect(const RotRect& r, FPt box[4]) {
+  FPt p[4];
+  box_points(r, p);
+  std::stable_sort(p, p + 4, [](const FPt& a, const FPt& b) { return a.x < b.x; });
+  int i1, i2, i3, i4;
+  if (p[1].y > p[0].y) { i1 = 0; i4 = 1; } else { i1 = 1; i4 = 0; }
+  if (p[3].y > p[2].y) { i2 = 2; i3 = 3; } else { i2 = 3; i3 = 2; }
+  box[0] = p[i1]; box[1] = p[i2]; box[2] = p[i3]; box[3] = p[i4];
+  return r.w < r.h ? r.w : r.h;
+}
+
+// ---------------------------------------------------------------------------------------------- unclip (convex)
+static inline int64_t clipper_round(double v) { return v < 0 ? (int64_t)(v - 0.5) : (int64_t)(v + 0.5); }
+
+// ClipperOffset::DoOffset / OffsetPoint / DoRound of Clipper 6.4.2 for ONE closed CONVEX path, JT_ROUND, positive delta.
+// For convex input the raw offset path is simple, so the union Clipper runs afterwards only drops collinear / duplicate
+// points -- which cannot change the min-area rectangle taken next.
+void offset_convex_round(const IPt* in, int n_in, double delta, std::vector<IPt>& out, double arc_tolerance) {
+  std::vector<IPt> pts(in, in + n_in);
+  double area = 0;
+  for (int i = 0; i < n_in; ++i) {
+    const IPt& a = pts[i]; const IPt& b = pts[(i + 1) % n_in];
+    area += ((double)a.x + b.x) * ((double)a.y - b.y);
+  }
+  area = -area * 0.5;
+  if (area < 0) std::reverse(pts.begin(), pts.end());
+  std::vector<IPt> clean;
+  for (const IPt& p : pts) if (clean.empty() || p.x != clean.back().x || p.y != clean.back().y) clean.push_back(p);
+  if (clean.size() > 1 && clean.front().x == clean.back().x && clean.front().y == clean.back().y) clean.pop_back();
+  pts.swap(clean);
+  const int n = (int)pts.size();
+  out.clear();
+  if (n < 3 || delta <= 0) { out = pts; return; }
+  double y = arc_tolerance > 0 ? arc_tolerance : 0.25;
+  if (y > std::fabs(delta) * 0.25) y = std::fabs(delta) * 0.25;
+  double steps = 3.14159265358979323846 / std::acos(1 - y / std::fabs(delta));
+  if (steps > std::fabs(delta) * 3.14159265358979323846) steps = std::fabs(delta) * 3.14159265358979323846;
+  const double m_sin = std::sin(2 * 3.14159265358979323846 / steps), m_cos = std::cos(2 * 3.14159265358979323846 / steps);
+  const double steps_per_rad = steps / (2 * 3.14159265358979323846);
+  std::vector<double> nx(n), ny(n);
+  for (int j = 0; j < n; ++j) {
+    const IPt& a = pts[j]; const IPt& b = pts[(j + 1) % n];
+    const double dx = (double)(b.x - a.x), dy = (double)(b.y - a.y);
+    const double f = 1.0 / std::sqrt(dx * dx + dy * dy);
+    nx[j] = dy * f; ny[j] = -dx * f;
+  }
+  auto push = [&](double x, double yv) { out.push_back(IPt{(int)clipper_round(x), (int)clipper_round(yv)}); };
+  int k = n - 1;
+  for (int j = 0; j < n; ++j) {
+    double sin_a = nx[k] * ny[j] - nx[j] * ny[k];
+    const double cos_a = nx[k] * nx[j] + ny[j] * ny[k];
+    if (std::fabs(sin_a * delta) < 1.0 && cos_a > 0) {
+      push(pts[j].x + nx[k] * delta, pts[j].y + ny[k] * delta);
+      k = j;
+      continue;
+    }
+    if (sin_a > 1.0) sin_a = 1.0; else if (sin_a < -1.0) sin_a = -1.0;
+    if (sin_a * delta < 0) {
+      push(pts[j].x + nx[k] * delta, pts[j].y + ny[k] * delta);
+      out.push_back(pts[j]);
+      push(pts[j].x + nx[j] * delta, pts[j].y + ny[j] * delta);
+    } else {
+      const double a = std::atan2(sin_a, cos_a);
+      int st = (int)clipper_round(steps_per_rad * std::fabs(a));
+      if (st < 1) st = 1;
+      double X = nx[k], Y = ny[k];
+      for (int q = 0; q < st; ++q) {
+        push(pts[j].x + X * delta, pts[j].y + Y * delta);
+        const double X2 = X;
+        X = X * m_cos - m_sin * Y;
+        Y = X2 * m_sin + Y * m_cos;
+      }
+      push(pts[j].x + nx[j] * delta, pts[j].y + ny[j] * delta);
+    }
+    k = j;
+  }
+}
+
+// one candidate: contour points -> final box; returns false when a size filter drops it
+bool box_from_hull(const std::vector<IPt>& hull, float unclip_ratio, int min_size, int src_w, int src_h, int dest_w, int dest_h,
+                   int16_t out_box[8], float* sside1, float mini1[8]) {
+  FPt b1[4];
+  const float s1 = mini_box_hull(hull, b1);
+  if (sside1) *sside1 = s1;
+  if (mini1) for (int i = 0; i < 4; ++i) { mini1[2 * i] = b1[i].x; mini1[2 * i + 1] = b1[i].y; }
+  if (s1 < (float)min_size) return false;
+  // shapely: area (shoelace, absolute) and length of the float32 corner ring, in double
+  double area = 0, length = 0;
+  for (int i = 0; i < 4; ++i) {
+    const FPt& a = b1[i]; const FPt& b = b1[(i + 1) & 3];
+    area += (double)a.x * (double)b.y - (double)a.y * (double)b.x;
+    const double dx = (double)a.x - (double)b.x, dy = (double)a.y - (double)b.y;
+    length += std::sqrt(dx * dx + dy * dy);
+  }
+  area = std::fabs(area) * 0.5;
+  const double distance = area * (double)unclip_ratio / length;
+  IPt ip[4];
+  for (int i = 0; i < 4; ++i) { ip[i].x = (int)b1[i].x; ip[i].y = (int)b1[i].y; }      // pyclipper: float -> cInt truncates
+  std::vector<IPt> expanded;
+  offset_convex_round(ip, 4, distance, expanded, 0.25);
+  FPt b2[4];
+  const float s2 = mini_box(expanded, b2);
+  if (s2 < (float)(min_size + 2)) return false;
+  for (int i = 0; i < 4; ++i) {
+    // numpy float32 arithmetic: x / width * dest_width, np.round (half to even), np.clip, astype(int16)
+    float fx = b2[i].x / (float)src_w * (float)dest_w, fy = b2[i].y / (float)src_h * (float)dest_h;
+    fx = std::nearbyintf(fx); fy = std::nearbyintf(fy);
+    fx = fx < 0.f ? 0.f : (fx > (float)dest_w ? (float)dest_w : fx);
+    fy = fy < 0.f ? 0.f : (fy > (float)dest_h ? (float)dest_h : fy);
+    out_box[2 * i] = (int16_t)fx; out_box[2 * i + 1] = (int16_t)fy;
+  }
+  return true;
+}
+
+}  // namespace dbb
+
+using namespace dbb;
+
+// Host function (no device work).  cands: (N, max_cands) records as copied back from dbb_binarize_ccl_score, n_cands (N);
+// points (N, cap, 2) {slot, (y << 16) | x} / n_points (N) as copied back from dbb_ccl_border_points (cap_stride = the stride actually copied);
+// dest_wh (N, 2) = (dest_width, dest_height) per image.  Outputs: boxes (N, max_cands, 4, 2) int16 and scores (N, max_cands)
+// float32, zero rows for dropped candidates (src/postprocess.py:119-148); optional debug outputs sside (N, max_cands) and
+// mini (N, max_cands, 4, 2) = the first get_mini_boxes result of every KEPT candidate.
+extern "C" int dbb_boxes_from_border_points(const DbbCandidate* cands, const int32_t* n_cands, const int32_t* points,
+                                            const int32_t* n_points, int64_t n, int max_cands, int cap_stride, int64_t h, int64_t w,
+                                            const int32_t* dest_wh, float unclip_ratio, int min_size, int16_t* boxes,
+                                            float* scores, float* sside_out, float* mini_out, int threads) {
+  if (!cands || !n_cands || !points || !n_points || !dest_wh || !boxes || !scores || n <= 0 || max_cands <= 0)
+    return set_error(DBB_EINVAL, "boxes_from_border_points: bad argument");
+  for (int64_t i = 0; i < n; ++i)
+    if (n_points[i] > cap_stride) return set_error(DBB_EWORKSPACE, "boxes_from_border_points: the border-point buffer overflowed (n_points > cap)");
+  auto work = [&](int64_t img) {
+    const int k = n_cands[img] < max_cands ? n_cands[img] : max_cands;
+    const DbbCandidate* C = cands + img * max_cands;
+    int16_t* B = boxes + img * max_cands * 8;
+    float* Sc = scores + img * max_cands;
+    std::fill(B, B + (size_t)max_cands * 8, (int16_t)0);
+    std::fill(Sc, Sc + max_cands, 0.f);
+    // bucket the points by candidate slot (counting sort)
+    const int np = n_points[img];
+    const int32_t* P = points + img * (int64_t)cap_stride * 2;
+    std::vector<int> start(k + 1, 0);
+    for (int q = 0; q < np; ++q) { const int s = P[2 * q]; if (s >= 0 && s < k) ++start[s + 1]; }
+    for (int s = 0; s < k; ++s) start[s + 1] += start[s];
+    std::vector<IPt> sorted(start[k]);
+    std::vector<int> fill(start.begin(), start.end() - 1);
+    for (int q = 0; q < np; ++q) {
+      const int s = P[2 * q];
+      if (s >= 0 && s < k) sorted[fill[s]++] = IPt{P[2 * q + 1] & 0xffff, (int)((uint32_t)P[2 * q + 1] >> 16)};
+    }
+    std::vector<IPt> scratch, hull;
+    std::vector<int> row_min, row_max;
+    for (int s = 0; s < k; ++s) {
+      if (!C[s].keep || start[s + 1] == start[s]) continue;
+      // per-row extremes inside the candidate's bounding box -> hull without sorting
+      const int y0 = C[s].y0, rows = C[s].y1 - C[s].y0 + 1;
+      row_min.assign(rows, INT32_MAX); row_max.assign(rows, INT32_MIN);
+      for (int q = start[s]; q < start[s + 1]; ++q) {
+        const int r = sorted[q].y - y0;
+        if (r < 0 || r >= rows) continue;
+        if (sorted[q].x < row_min[r]) row_min[r] = sorted[q].x;
+        if (sorted[q].x > row_max[r]) row_max[r] = sorted[q].x;
+      }
+      convex_hull_rows(row_min, row_max, y0, scratch, hull);
+      float ss = 0, mini[8];
+      const bool ok = box_from_hull(hull, unclip_ratio, min_size, (int)w, (int)h, dest_wh[2 * img], dest_wh[2 * img + 1],
+                                    B + (size_t)s * 8, &ss, mini);
+      if (sside_out) sside_out[img * max_cands + s] = ss;
+      if (mini_out) std::copy(mini, mini + 8, mini_out + ((size_t)img * max_cands + s) * 8);
+      if (!ok) { std::fill(B + (size_t)s * 8, B + (size_t)s * 8 + 8, (int16_t)0); continue; }
+      Sc[s] = (float)(C[s].sum / (double)C[s].count);
+    }
+  };
+  int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  if (nt > n) nt = (int)n;
+  if (nt <= 1) { for (int64_t i = 0; i < n; ++i) work(i); return DBB_OK; }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nt; ++t) pool.emplace_back([&, t]() { for (int64_t i = t; i < n; i += nt) work(i); });
+  for (auto& th : pool) th.join();
+  return DBB_OK;
+}
+
+// get_mini_boxes on an explicit integer contour (tests, polygon mode): box (4, 2) float32 out; returns sside through *sside
+extern "C" int dbb_mini_box(const int32_t* contour_xy, int npts, float* box8, float* sside) {
+  if (!contour_xy || npts <= 0 || !box8 || !sside) return set_error(DBB_EINVAL, "mini_box: bad argument");
+  std::vector<IPt> c(npts);
+  for (int i = 0; i < npts; ++i) c[i] = IPt{contour_xy[2 * i], contour_xy[2 * i + 1]};
+  FPt b[4];
+  *sside = mini_box(c, b);
+  for (int i = 0; i < 4; ++i) { box8[2 * i] = b[i].x; box8[2 * i + 1] = b[i].y; }
+  return DBB_OK;
+}

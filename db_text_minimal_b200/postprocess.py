@@ -6,11 +6,13 @@ region), float64 box score over the contour's fill set, score filter.  Only the 
 and, when boxes are requested, the 1-byte bitmap cross to the host -- not the two full float maps per image the
 reference copies (src/postprocess.py:61-62,113-114).
 
-Back half (host, survivors only): contour of the surviving component from the bitmap crop (cv2, same border follower
-as the reference), get_mini_boxes, unclip, rescale -- src/postprocess.py:70-103,122-147,150-184.
-``unclip`` needs Clipper (pyclipper 1.1.0.post3) which is neither in the reference tree nor in this image: when
-pyclipper is importable it is used; otherwise a restatement of ClipperOffset's round-join arithmetic for CONVEX
-input (box mode) is used and polygon mode raises.  That stage is unpinned (no pyclipper to generate goldens).
+Back half.  Box mode (src/postprocess.py:106-148): the device emits the border points of the kept candidates (run end
+pixels: their convex hull is the contour's), and C++ (csrc/post_geom.cu, csrc/clipper_offset.cu) does get_mini_boxes,
+unclip, the second get_mini_boxes and the rescale for the whole batch -- no bitmap crosses to the host, no Python per box.
+Polygon mode (src/postprocess.py:54-104) needs the ordered contour for cv2.approxPolyDP: contours of the survivors are
+traced by OpenCV on bitmap crops, the offset runs in C++.
+``unclip`` is Clipper (pyclipper 1.1.0.post3), which is neither in the reference tree nor in this image; it is restated in
+csrc/clipper_offset.cu for polygons of any shape.  That stage is unpinned (no pyclipper to generate goldens).
 """
 import ctypes as C
 import math
@@ -21,90 +23,52 @@ import torch
 from . import _lib
 
 
-_PYCLIPPER = []
+def _to_cint(points):
+    """pyclipper hands Clipper 64-bit integers: float coordinates are truncated toward zero."""
+    return np.ascontiguousarray(np.trunc(np.asarray(points, dtype=np.float64).reshape(-1, 2)).astype(np.int64))
 
 
-def _pyclipper():
-    """pyclipper if it is installed, else None -- looked up once (a failing import costs ~0.3 ms per call)."""
-    if not _PYCLIPPER:
-        try:
-            import pyclipper
-            _PYCLIPPER.append(pyclipper)
-        except ImportError:
-            _PYCLIPPER.append(None)
-    return _PYCLIPPER[0]
+def clipper_offset(points, delta, arc_tolerance=0.25):
+    """pyclipper.PyclipperOffset().AddPath(points, JT_ROUND, ET_CLOSEDPOLYGON); .Execute(delta) -> list of (k, 2) int64
+    arrays (one per result polygon; more than one when the offset region has holes or falls apart).  Runs in C++
+    (csrc/clipper_offset.cu: a restatement of Clipper 6.4.2's ClipperOffset -- parity unpinned, pyclipper is neither in
+    the reference tree nor installable here)."""
+    L = _lib.lib()
+    path = _to_cint(points)
+    cap = max(256, 64 * len(path) + int(8 * abs(delta)) + 64)
+    while True:
+        out = np.empty((cap, 2), np.int64)
+        counts = np.zeros(64, np.int32)
+        rc = L.dbb_clipper_offset(path.ctypes.data, len(path), float(delta), float(arc_tolerance), out.ctypes.data, cap,
+                                  counts.ctypes.data, len(counts))
+        if rc >= 0:
+            break
+        if cap > (1 << 22):
+            _lib.check(rc, "dbb_clipper_offset")
+        cap *= 4
+    res, o = [], 0
+    for i in range(rc):
+        res.append(out[o:o + counts[i]].copy())
+        o += counts[i]
+    return res
 
 
-def _clipper_round(v):
-    # Clipper's Round(): (val < 0) ? (cInt)(val - 0.5) : (cInt)(val + 0.5)
-    return int(v - 0.5) if v < 0 else int(v + 0.5)
+def clipper_offset_raw(points, delta, arc_tolerance=0.25):
+    """The raw offset path (before the union that removes its self-intersections); for tests."""
+    L = _lib.lib()
+    path = _to_cint(points)
+    cap = max(256, 64 * len(path) + int(8 * abs(delta)) + 64)
+    out = np.empty((cap, 2), np.int64)
+    rc = L.dbb_clipper_offset_raw(path.ctypes.data, len(path), float(delta), float(arc_tolerance), out.ctypes.data, cap)
+    if rc < 0:
+        _lib.check(rc, "dbb_clipper_offset_raw")
+    return out[:rc].copy()
 
 
 def offset_convex_round(points, delta, arc_tolerance=0.25):
-    """ClipperOffset(JT_ROUND, ET_CLOSEDPOLYGON).Execute(delta) for a CONVEX polygon, restated from Clipper 6.4.2
-    (ClipperOffset::DoOffset / OffsetPoint / DoRound).  Integer coordinates in, integer coordinates out.
-    For convex input the raw offset path is already simple, so the final union Clipper runs leaves the point set
-    unchanged up to start vertex and collinear points -- irrelevant to the min-area rectangle taken next."""
-    pts = [(int(p[0]), int(p[1])) for p in points]      # pyclipper truncates float input to cInt
-    # orientation: Clipper offsets outward for positive area; reverse if needed
-    area = 0.0
-    n = len(pts)
-    for i in range(n):
-        x0, y0 = pts[i]; x1, y1 = pts[(i + 1) % n]
-        area += (x0 + x1) * (y0 - y1)
-    area = -area * 0.5
-    if area < 0:
-        pts = pts[::-1]
-    # strip duplicate neighbours
-    clean = [pts[0]]
-    for p in pts[1:]:
-        if p != clean[-1]:
-            clean.append(p)
-    if len(clean) > 1 and clean[0] == clean[-1]:
-        clean.pop()
-    pts = clean
-    n = len(pts)
-    if n < 3 or delta <= 0:
-        return np.array(pts, dtype=np.int64).reshape(-1, 2)
-    y = arc_tolerance if arc_tolerance > 0 else 0.25
-    y = min(y, abs(delta) * 0.25) if y > abs(delta) * 0.25 else y
-    steps = math.pi / math.acos(1 - y / abs(delta))
-    if steps > abs(delta) * math.pi:
-        steps = abs(delta) * math.pi
-    m_sin, m_cos = math.sin(2 * math.pi / steps), math.cos(2 * math.pi / steps)
-    steps_per_rad = steps / (2 * math.pi)
-    normals = []
-    for j in range(n):
-        x0, y0 = pts[j]; x1, y1 = pts[(j + 1) % n]
-        dx, dy = float(x1 - x0), float(y1 - y0)
-        f = 1.0 / math.sqrt(dx * dx + dy * dy)
-        normals.append((dy * f, -dx * f))
-    out = []
-    k = n - 1
-    for j in range(n):
-        sin_a = normals[k][0] * normals[j][1] - normals[j][0] * normals[k][1]
-        cos_a = normals[k][0] * normals[j][0] + normals[j][1] * normals[k][1]
-        if abs(sin_a * delta) < 1.0 and cos_a > 0:
-            out.append((_clipper_round(pts[j][0] + normals[k][0] * delta), _clipper_round(pts[j][1] + normals[k][1] * delta)))
-            k = j
-            continue
-        sin_a = max(-1.0, min(1.0, sin_a))
-        if sin_a * delta < 0:      # concave vertex (does not occur for convex input)
-            out.append((_clipper_round(pts[j][0] + normals[k][0] * delta), _clipper_round(pts[j][1] + normals[k][1] * delta)))
-            out.append(pts[j])
-            out.append((_clipper_round(pts[j][0] + normals[j][0] * delta), _clipper_round(pts[j][1] + normals[j][1] * delta)))
-        else:                      # DoRound
-            a = math.atan2(sin_a, cos_a)
-            st = max(int(_clipper_round(steps_per_rad * abs(a))), 1)
-            X, Y = normals[k]
-            for _ in range(st):
-                out.append((_clipper_round(pts[j][0] + X * delta), _clipper_round(pts[j][1] + Y * delta)))
-                X2 = X
-                X = X * m_cos - m_sin * Y
-                Y = X2 * m_sin + Y * m_cos
-            out.append((_clipper_round(pts[j][0] + normals[j][0] * delta), _clipper_round(pts[j][1] + normals[j][1] * delta)))
-        k = j
-    return np.array(out, dtype=np.int64).reshape(-1, 2)
+    """Offset polygon of a CONVEX input as one (k, 2) int64 array (kept for the GT-map code and the golden generator)."""
+    res = clipper_offset(points, delta, arc_tolerance)
+    return res[0] if res else np.zeros((0, 2), np.int64)
 
 
 class SegDetectorRepresenter():
@@ -130,9 +94,8 @@ class SegDetectorRepresenter():
                                                out.data_ptr(), _lib.stream_ptr()), "dbb_binarize")
         return out.reshape(shape).bool()
 
-    def front(self, pred, want_labels=False):
-        """Device front on a (N, C, H, W) prediction (channel 0 = probability map, src/postprocess.py:33).
-        Returns (bitmap uint8 (N,H,W) on device, labels int32 or None, candidate records (numpy structured), n_cands)."""
+    def _front_device(self, pred, want_labels=False):
+        """Launches the device front; everything stays on the device.  Returns a dict of the tensors involved."""
         _lib.require_cuda(pred)
         L = _lib.lib()
         p = pred.detach().float().contiguous()
@@ -152,6 +115,13 @@ class SegDetectorRepresenter():
                                                 bitmap.data_ptr(), labels.data_ptr() if want_labels else None,
                                                 cands.data_ptr(), ncand.data_ptr(), self.max_candidates, ws.data_ptr(), wsb,
                                                 _lib.stream_ptr()), "dbb_binarize_ccl_score")
+        return dict(p=p, n=n, h=h, w=w, dev=dev, bitmap=bitmap, labels=labels, cands=cands, ncand=ncand, ws=ws, wsb=wsb, csize=csize)
+
+    def front(self, pred, want_labels=False):
+        """Device front on a (N, C, H, W) prediction (channel 0 = probability map, src/postprocess.py:33).
+        Returns (bitmap uint8 (N,H,W) on device, labels int32 or None, candidate records (numpy structured), n_cands)."""
+        f = self._front_device(pred, want_labels)
+        n, csize, bitmap, labels, cands, ncand = f["n"], f["csize"], f["bitmap"], f["labels"], f["cands"], f["ncand"]
         nc = ncand.cpu().numpy()
         kmax = int(min(nc.max(), self.max_candidates)) if n else 0
         raw = cands[:, :kmax].cpu().numpy() if kmax else np.zeros((n, 0, csize), np.uint8)
@@ -160,6 +130,53 @@ class SegDetectorRepresenter():
         assert dt.itemsize == csize
         rec = raw.reshape(n, kmax * csize).view(dt).reshape(n, kmax) if kmax else np.zeros((n, 0), dt)
         return bitmap, labels, rec, nc
+
+    # ------------------------------------------------------------------ box mode, whole batch: device front + C++ back half
+    def boxes_batch(self, pred, dest_wh, debug=False):
+        """src/postprocess.py:106-148 for a whole batch: the device front (binarize, candidates, scores, score filter), the
+        border points of the kept candidates (dbb_ccl_border_points) and the C++ back half (dbb_boxes_from_border_points:
+        get_mini_boxes, unclip, get_mini_boxes, rescale).  dest_wh: (N, 2) (dest_width, dest_height).
+        Returns (boxes (N, K, 4, 2) int16, scores (N, K) float32, n_cands (N,)) with K = the largest candidate count of
+        the batch (capped at max_candidates); rows of dropped candidates are zero, as in the reference."""
+        L = _lib.lib()
+        f = self._front_device(pred)
+        n, h, w, dev = f["n"], f["h"], f["w"], f["dev"]
+        cap = max(8192, (h * w) // 16)
+        npts_dev = torch.empty(n, dtype=torch.int32, device=dev)
+        while True:
+            pts_dev = torch.empty((n, cap, 2), dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(L.dbb_ccl_border_points(f["ws"].data_ptr(), f["wsb"], n, h, w, pts_dev.data_ptr(), npts_dev.data_ptr(), cap,
+                                                   _lib.stream_ptr()), "dbb_ccl_border_points")
+            counts = torch.stack([f["ncand"], npts_dev]).cpu().numpy()       # one synchronising copy
+            nc, npts = counts[0], counts[1]
+            if int(npts.max(initial=0)) <= cap:
+                break
+            cap = int(npts.max())                                             # rare: rerun with the exact size
+        k = int(min(max(int(nc.max(initial=0)), 1), self.max_candidates))
+        pmax = max(int(npts.max(initial=0)), 1)
+        # one pinned staging buffer for both device->host copies (pageable copies run at a fraction of the PCIe rate)
+        nb_c, nb_p = n * k * f["csize"], n * pmax * 8
+        stage = torch.empty(nb_c + nb_p, dtype=torch.uint8, pin_memory=True)
+        stage[:nb_c].view(n, k, f["csize"]).copy_(f["cands"][:, :k], non_blocking=True)
+        stage[nb_c:].view(torch.int32).view(n, pmax, 2).copy_(pts_dev[:, :pmax], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        host = stage.numpy()
+        cands, pts = host[:nb_c], host[nb_c:]
+        dest = np.ascontiguousarray(np.asarray(dest_wh, dtype=np.int32).reshape(n, 2))
+        boxes = np.empty((n, k, 4, 2), np.int16)
+        scores = np.empty((n, k), np.float32)
+        sside = np.zeros((n, k), np.float32) if debug else None
+        mini = np.zeros((n, k, 4, 2), np.float32) if debug else None
+        nc32, np32 = np.ascontiguousarray(nc.astype(np.int32)), np.ascontiguousarray(npts.astype(np.int32))
+        _lib.check(L.dbb_boxes_from_border_points(cands.ctypes.data, nc32.ctypes.data, pts.ctypes.data, np32.ctypes.data, n, k, pmax,
+                                                  h, w, dest.ctypes.data, float(self.unclip_ratio), int(self.min_size),
+                                                  boxes.ctypes.data, scores.ctypes.data,
+                                                  sside.ctypes.data if debug else None, mini.ctypes.data if debug else None,
+                                                  int(self.host_threads)), "dbb_boxes_from_border_points")
+        if debug:
+            return boxes, scores, nc, sside, mini, cands
+        return boxes, scores, nc
 
     def candidates(self, pred):
         """Per image: list of dicts (kind, score, count, bbox, first, keep) in the reference's contour order."""
@@ -197,23 +214,14 @@ class SegDetectorRepresenter():
         return c + np.array([[[x0, y0]]], dtype=c.dtype)
 
     def unclip(self, box, unclip_ratio=1.5):
-        """src/postprocess.py:150-156.  distance = area * ratio / perimeter (shapely Polygon.area / .length)."""
+        """src/postprocess.py:150-156.  distance = area * ratio / perimeter (shapely Polygon.area / .length); returns the list
+        of result polygons (the reference's np.array(offset.Execute(distance)); callers test len(...) > 1 and reshape)."""
         pts = np.asarray(box, dtype=np.float64).reshape(-1, 2)
-        nxt = np.concatenate([pts[1:], pts[:1]])            # (np.roll costs ~30 us per call on these 4-point arrays)
+        nxt = np.concatenate([pts[1:], pts[:1]])
         area = 0.5 * abs(float((pts[:, 0] * nxt[:, 1] - pts[:, 1] * nxt[:, 0]).sum()))
         length = float(np.sqrt(((pts - nxt) ** 2).sum(1)).sum())
         distance = area * unclip_ratio / length
-        pyclipper = _pyclipper()
-        if pyclipper is not None:
-            offset = pyclipper.PyclipperOffset()
-            offset.AddPath(box, pyclipper.JT_ROUND, pyclipper.ET_CLOSEDPOLYGON)
-            return np.array(offset.Execute(distance))
-        import cv2
-        hull = cv2.convexHull(pts.astype(np.float32)).reshape(-1, 2)
-        if len(hull) != len(pts):
-            raise _lib.DbbError("unclip of a non-convex polygon needs pyclipper (Clipper 6.4.2), which is not installed; "
-                                "box mode (convex input) uses the built-in restatement")
-        return offset_convex_round(pts, distance)[None]
+        return clipper_offset(box, distance)
 
     def get_mini_boxes(self, contour):
         """src/postprocess.py:158-184."""
@@ -243,34 +251,6 @@ class SegDetectorRepresenter():
         cv2.fillPoly(mask, box.reshape(1, -1, 2).astype(np.int32), 1)
         return cv2.mean(bitmap[ymin:ymax + 1, xmin:xmax + 1], mask)[0]
 
-    def _boxes(self, bitmap_np, rec, dest_width, dest_height):
-        """src/postprocess.py:119-147 on the device-scored candidates."""
-        height, width = bitmap_np.shape
-        num = len(rec)
-        boxes = np.zeros((num, 4, 2), dtype=np.int16)
-        scores = np.zeros((num,), dtype=np.float32)
-        for index, r in enumerate(rec):
-            if not r["keep"]:           # cheap test first; the reference applies sside first, the kept set is the same
-                continue
-            contour = self._contour_of(bitmap_np, r).squeeze(1)
-            points, sside = self.get_mini_boxes(contour)
-            if sside < self.min_size:
-                continue
-            points = np.array(points)
-            score = float(r["sum"]) / int(r["count"])
-            box = self.unclip(points, unclip_ratio=self.unclip_ratio).reshape(-1, 1, 2)
-            box, sside = self.get_mini_boxes(box.astype(np.float32) if box.dtype != np.int32 else box)
-            if sside < self.min_size + 2:
-                continue
-            box = np.array(box)
-            if not isinstance(dest_width, int):
-                dest_width, dest_height = dest_width.item(), dest_height.item()
-            box[:, 0] = np.clip(np.round(box[:, 0] / width * dest_width), 0, dest_width)
-            box[:, 1] = np.clip(np.round(box[:, 1] / height * dest_height), 0, dest_height)
-            boxes[index, :, :] = box.astype(np.int16)
-            scores[index] = score
-        return boxes, scores
-
     def _polygons(self, bitmap_np, rec, dest_width, dest_height):
         """src/postprocess.py:70-103."""
         import cv2
@@ -287,9 +267,9 @@ class SegDetectorRepresenter():
                 continue
             score = float(r["sum"]) / int(r["count"])
             box = self.unclip(points, unclip_ratio=self.unclip_ratio)
-            if len(box) > 1:
+            if len(box) != 1:          # the reference drops len(box) > 1; an empty result cannot be reshaped there either
                 continue
-            box = np.asarray(box).reshape(-1, 2)
+            box = np.asarray(box[0]).reshape(-1, 2)
             _, sside = self.get_mini_boxes(box.reshape((-1, 1, 2)).astype(np.int32))
             if sside < self.min_size + 2:
                 continue
@@ -304,9 +284,15 @@ class SegDetectorRepresenter():
 
     def __call__(self, batch, pred, is_output_polygon=False):
         """src/postprocess.py:19-49: returns (boxes_batch, scores_batch)."""
+        if not is_output_polygon:        # box mode: nothing but candidate records and border points leaves the device
+            n = pred.shape[0]
+            dest = [(int(batch['shape'][i][1]), int(batch['shape'][i][0])) for i in range(n)]
+            boxes, scores, nc = self.boxes_batch(pred, dest)
+            ks = [int(min(nc[i], self.max_candidates)) for i in range(n)]
+            return [boxes[i, :ks[i]] for i in range(n)], [scores[i, :ks[i]] for i in range(n)]
         bitmap, _, rec, nc = self.front(pred)
         bm = bitmap.cpu().numpy()
-        fn = self._polygons if is_output_polygon else self._boxes
+        fn = self._polygons
 
         def one(i):
             height, width = batch['shape'][i]
@@ -325,8 +311,11 @@ class SegDetectorRepresenter():
     def boxes_from_bitmap(self, pred, _bitmap, dest_width, dest_height):
         """src/postprocess.py:106-148 for one (H, W) map; ``_bitmap`` is recomputed on the device from ``pred``."""
         assert len(_bitmap.shape) == 2
-        bitmap, _, rec, nc = self.front(pred[None, None])
-        return self._boxes(bitmap[0].cpu().numpy(), rec[0, :int(min(nc[0], self.max_candidates))], dest_width, dest_height)
+        if not isinstance(dest_width, int):
+            dest_width, dest_height = dest_width.item(), dest_height.item()
+        boxes, scores, nc = self.boxes_batch(pred[None, None], [(int(dest_width), int(dest_height))])
+        k = int(min(nc[0], self.max_candidates))
+        return boxes[0, :k], scores[0, :k]
 
     def polygons_from_bitmap(self, pred, _bitmap, dest_width, dest_height):
         assert len(_bitmap.shape) == 2

@@ -135,6 +135,35 @@ int dbb_binarize_ccl_score(const float* pred, int64_t n, int c, int64_t h, int64
                            void* workspace, size_t workspace_bytes, void* stream);
 
 
+/* Border points of the KEPT candidates (replaces the contour handed to get_mini_boxes, src/postprocess.py:119-121: cv2.minAreaRect
+ * only sees the contour's convex hull, which equals the hull of the run end pixels of the component).  Must follow
+ * dbb_binarize_ccl_score on the same workspace and stream.  points: (N, cap, 2) int32 {candidate slot, (y << 16) | x} device out;
+ * n_points: (N) int32 device out (> cap: buffer too small, call again with a larger one). */
+int dbb_ccl_border_points(const void* workspace, size_t workspace_bytes, int64_t n, int64_t h, int64_t w, int32_t* points,
+                          int32_t* n_points, int cap, void* stream);
+/* HOST function: src/postprocess.py:119-147 (get_mini_boxes, sside filter, unclip, second get_mini_boxes, sside filter, rescale)
+ * for every kept candidate of a batch, on host copies of the candidate records and border points.  dest_wh: (N, 2) int32
+ * (dest_width, dest_height); boxes: (N, max_cands, 4, 2) int16 out, scores: (N, max_cands) float32 out (zero rows for dropped
+ * candidates, as the reference); sside_out / mini_out (optional): first get_mini_boxes result per kept candidate;
+ * threads: worker threads over images (0 = hardware concurrency). */
+int dbb_boxes_from_border_points(const DbbCandidate* cands, const int32_t* n_cands, const int32_t* points, const int32_t* n_points,
+                                 int64_t n, int max_cands, int cap_stride, int64_t h, int64_t w, const int32_t* dest_wh,
+                                 float unclip_ratio, int min_size, int16_t* boxes, float* scores, float* sside_out,
+                                 float* mini_out, int threads);
+/* HOST function: get_mini_boxes (src/postprocess.py:158-184 = cv2.minAreaRect + cv2.boxPoints + corner ordering) of an integer
+ * contour (npts, 2); box8: 4 x (x, y) float32 out. */
+int dbb_mini_box(const int32_t* contour_xy, int npts, float* box8, float* sside);
+
+/* HOST function: pyclipper.PyclipperOffset().AddPath(path, JT_ROUND, ET_CLOSEDPOLYGON); Execute(delta) for one closed polygon
+ * of any shape (src/postprocess.py:150-156 unclip; src/data_loaders.py:116-122 shrink with delta < 0; src/db_transforms.py:13-21).
+ * Restates Clipper 6.4.2's ClipperOffset arithmetic (third-party, not in the reference tree: PARITY UNPINNED, see
+ * csrc/clipper_offset.cu).  path_xy: (npts, 2) int64; result polygons are written back to back into out_xy (capacity
+ * cap_points points), out_counts[i] = points of polygon i.  Returns the number of polygons, or a negative DBB_E* code. */
+int dbb_clipper_offset(const int64_t* path_xy, int npts, double delta, double arc_tolerance, int64_t* out_xy, int cap_points,
+                       int32_t* out_counts, int max_paths);
+/* the raw offset path before the union step (tests) */
+int dbb_clipper_offset_raw(const int64_t* path_xy, int npts, double delta, double arc_tolerance, int64_t* out_xy, int cap_points);
+
 /* bitmap = pred[:, 0] > thresh on its own (src/postprocess.py:51-52) */
 int dbb_binarize(const float* pred, int64_t n, int c, int64_t h, int64_t w, float thresh, uint8_t* bitmap, void* stream);
 
