@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--torch-adam", action="store_true", help="use torch.optim.Adam(fused=True) instead of db_text_minimal_b200.optim.FlatAdam")
     ap.add_argument("--no-graph-dp", action="store_true", help="multi-GPU: keep the step eager (the graph would contain the NCCL all-reduces)")
     ap.add_argument("--dump-kernels", default=None, help="write the full per-kernel timing table (JSON) to this path")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the BASELINE config 4 / 5 summaries (single GPU only)")
     ap.add_argument("--cpu-batch", type=int, default=8, help="images in the bounded cpu_baseline sample of our arm's line")
     return ap.parse_args()
 
@@ -431,6 +432,18 @@ def run_ours(args):
             "top_kernels": table[:12],
         }
     barrier()
+    if rank == 0 and world == 1 and not args.no_extra_configs:
+        # BASELINE configs 4 and 5 (single GPU): batched 64 x 1024^2 inference + GPU post-processing, and the head + loss
+        # resolution sweep -- reported inside the same line so that they are driver-run numbers
+        graphed = None
+        torch.cuda.empty_cache()
+        try:
+            from tools import bench_configs
+            out["config4"] = bench_configs.config4()
+            torch.cuda.empty_cache()
+            out["config5"] = bench_configs.config5()
+        except Exception as e:
+            out["config4"] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             r = reference_rate(min(args.cpu_batch, N), S, args.reduction, 3, 1, budget_s=60.0)

@@ -40,6 +40,7 @@ struct CclWs {
   CompStat* stat;          // [n][hw]
   int* blk_count;          // [n][nblk]
   int* blk_off;            // [n][nblk]
+  unsigned* rootbits;      // [n][h][wq]    1 where the pixel is the root of its component (written by the final flatten)
 };
 
 __host__ __device__ inline size_t ccl_align(size_t v) { return (v + 255) / 256 * 256; }
@@ -53,7 +54,8 @@ static CclWs ccl_carve(void* ws, int64_t n, int64_t hw, int64_t h, int64_t wq) {
   w.label = (int*)p;        p += ccl_align(sizeof(int) * (size_t)n * (hw + 1));
   w.stat = (CompStat*)p;    p += ccl_align(sizeof(CompStat) * (size_t)n * hw);
   w.blk_count = (int*)p;    p += ccl_align(sizeof(int) * (size_t)n * ccl_nblk(hw));
-  w.blk_off = (int*)p;
+  w.blk_off = (int*)p;      p += ccl_align(sizeof(int) * (size_t)n * ccl_nblk(hw));
+  w.rootbits = (unsigned*)p;
   return w;
 }
 
@@ -80,9 +82,12 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
 // touching runs instead of once per pixel.
 // ---------------------------------------------------------------------------------------------
 struct Seg { int img, y, s, x0, nvalid; };
+// (32-bit arithmetic on purpose: the entry points check n*h*wq < 2^32, and a 64-bit divide is a ~100-instruction loop --
+//  ncu showed ccl_pack_init at 150 warp-instructions per word with 64-bit decodes)
 __device__ __forceinline__ bool seg_of(int64_t widx, int h, int wq, int w, Seg& g) {
-  g.s = (int)(widx % wq); int64_t t = widx / wq;
-  g.y = (int)(t % h); g.img = (int)(t / h);
+  const unsigned u = (unsigned)widx;
+  g.s = (int)(u % (unsigned)wq); const unsigned t = u / (unsigned)wq;
+  g.y = (int)(t % (unsigned)h); g.img = (int)(t / (unsigned)h);
   g.x0 = g.s * 32;
   g.nvalid = w - g.x0 < 32 ? w - g.x0 : 32;
   return true;
@@ -115,91 +120,103 @@ ccl_pack_init_kernel(const float* __restrict__ pred, int c, int n, int h, int w,
       const unsigned st = run_starts(cur, g.nvalid) & ((2u << lane) - 1u);
       label[g.img * (hw + 1) + pix] = (int)((int64_t)g.y * w + g.x0 + (31 - __clz(st)));
     }
-    if (widx % ((int64_t)h * wq) == 0 && lane == 0) label[g.img * (hw + 1) + hw] = (int)hw;   // virtual outside node
+    if (g.y == 0 && g.s == 0 && lane == 0) label[g.img * (hw + 1) + hw] = (int)hw;   // virtual outside node
   }
 }
 
 // B: unions between touching runs: across segment boundaries, with the row above (4-connectivity for background,
-// 8-connectivity for foreground), and background runs on the image frame with the virtual outside node
-__global__ void __launch_bounds__(CCL_THREADS)
-ccl_link_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, int* __restrict__ label, int phase) {
+// 8-connectivity for foreground), and background runs on the image frame with the virtual outside node.
+// ONE THREAD PER 32-PIXEL WORD: the neighbourhood masks are a dozen word operations computed once, and the thread then walks
+// the set bits (typically 0-2 unions per word).  The first version gave every pixel a lane that recomputed the same masks and
+// diverged on its own union: 30 warp-instructions per pixel at 5.7 active lanes (ncu, profiles/prof_ccl_r02.md) -- issue-bound.
+__device__ __forceinline__ void link_word(const unsigned* __restrict__ bits, int64_t widx, int h, int w, int wq, int* __restrict__ label, int phase) {
   const int64_t hw = (int64_t)h * w;
-  const int lane = threadIdx.x & 31;
-  const int64_t nseg = (int64_t)n * h * wq;
-  const int64_t wstride = (int64_t)gridDim.x * (CCL_THREADS / 32);
-  for (int64_t widx = (int64_t)blockIdx.x * (CCL_THREADS / 32) + (threadIdx.x >> 5); widx < nseg; widx += wstride) {
-    Seg g; seg_of(widx, h, wq, w, g);
-    if (lane >= g.nvalid) continue;
-    // two-level merge keeps union-find chains short: phase 0 links everything except across the boundaries of
-    // 32-row strips (chains <= 32), the strips are flattened, phase 1 links the strip boundaries (chains <= H/32)
-    const bool strip_edge = (g.y & 31) == 0;
-    if (phase == 1 && !(strip_edge && g.y > 0)) continue;
-    int* L = label + g.img * (hw + 1);
-    const unsigned cur = bits[widx];
-    const unsigned prv = g.s > 0 ? bits[widx - 1] : 0u, nxt = g.s < wq - 1 ? bits[widx + 1] : 0u;
-    const bool has_up = g.y > 0 && (phase == 1 || !strip_edge);
-    const unsigned up = has_up ? bits[widx - wq] : 0u;
-    const unsigned upp = (has_up && g.s > 0) ? bits[widx - wq - 1] : 0u, upn = (has_up && g.s < wq - 1) ? bits[widx - wq + 1] : 0u;
-    const unsigned vm = valid_mask(g.nvalid);
+  Seg g; seg_of(widx, h, wq, w, g);
+  // two-level merge keeps union-find chains short: phase 0 links everything except across the boundaries of
+  // 32-row strips (chains <= 32), the strips are flattened, phase 1 links the strip boundaries (chains <= H/32)
+  const bool strip_edge = (g.y & 31) == 0;
+  int* L = label + g.img * (hw + 1);
+  const unsigned cur = bits[widx];
+  const unsigned prv = g.s > 0 ? bits[widx - 1] : 0u, nxt = g.s < wq - 1 ? bits[widx + 1] : 0u;
+  const bool has_up = g.y > 0 && (phase == 1 || !strip_edge);
+  const unsigned vm = valid_mask(g.nvalid);
+  const int i0 = g.y * w + g.x0;
+  if (has_up) {
+    const unsigned up = bits[widx - wq];
+    const unsigned upp = g.s > 0 ? bits[widx - wq - 1] : 0u, upn = g.s < wq - 1 ? bits[widx - wq + 1] : 0u;
     // neighbours shifted into lane position: L = pixel x-1, R = pixel x+1
     const unsigned curL = (cur << 1) | (prv >> 31), curR = (cur >> 1) | (nxt << 31);
     const unsigned upL = (up << 1) | (upp >> 31), upR = (up >> 1) | (upn << 31);
     const unsigned hasL = g.s > 0 ? 0xffffffffu : 0xfffffffeu;                         // pixel x-1 exists
-    const int x = g.x0 + lane;
-    const int i = g.y * w + x;
-    const unsigned bit = 1u << lane;
-    const bool fg = cur & bit;
-    // horizontal link across the segment boundary (inside a segment the run label already encodes it)
-    if (phase == 0 && lane == 0 && g.s > 0 && (((cur & 1u) != 0) == ((prv >> 31) != 0))) uf_union(L, i, i - 1);
-    if (fg) {
-      if (has_up) {
-        const unsigned V = cur & up & ~(curL & upL & hasL);            // first column of a vertical overlap
-        const unsigned DL = cur & ~up & upL & ~curL & hasL;             // diagonal up-left, not implied by a neighbour
-        const unsigned DR = cur & ~up & upR & ~curR;                    // diagonal up-right (upR is 0 beyond the row end)
-        if (V & bit) uf_union(L, i, i - w);
-        if (DL & bit) uf_union(L, i, i - w - 1);
-        if ((DR & bit) && x + 1 < w) uf_union(L, i, i - w + 1);
-      }
-    } else {
-      const unsigned ncur = ~cur & vm, nup = ~up;
-      if (has_up) {
-        const unsigned ncurL = ~curL, nupL = ~upL;
-        const unsigned V = ncur & nup & ~(ncurL & nupL & hasL);
-        if (V & bit) uf_union(L, i, i - w);
-      }
-      // frame pixels belong to the outside region: one union per run start on the frame
-      const bool frame = g.y == 0 || g.y == h - 1 || x == 0 || x == w - 1;
-      if (frame && phase == 0) {
-        const unsigned st = run_starts(cur, g.nvalid);
-        if ((st & bit) || x == w - 1 || ((g.y != 0 && g.y != h - 1) && x == 0)) uf_union(L, (int)hw, i);
-      }
+    unsigned V = cur & up & ~(curL & upL & hasL);            // first column of a vertical overlap
+    unsigned DL = cur & ~up & upL & ~curL & hasL;            // diagonal up-left, not implied by a neighbour
+    unsigned DR = cur & ~up & upR & ~curR;                   // diagonal up-right (bits beyond the row end are 0)
+    if (g.s == wq - 1 && g.nvalid >= 1) DR &= ~(1u << (g.nvalid - 1));     // x + 1 < w
+    while (V) { const int b = __ffs(V) - 1; V &= V - 1; uf_union(L, i0 + b, i0 + b - w); }
+    while (DL) { const int b = __ffs(DL) - 1; DL &= DL - 1; uf_union(L, i0 + b, i0 + b - w - 1); }
+    while (DR) { const int b = __ffs(DR) - 1; DR &= DR - 1; uf_union(L, i0 + b, i0 + b - w + 1); }
+    const unsigned ncur = ~cur & vm;
+    unsigned VB = ncur & ~up & ~(~curL & ~upL & hasL);       // background: vertical links only (4-connectivity)
+    while (VB) { const int b = __ffs(VB) - 1; VB &= VB - 1; uf_union(L, i0 + b, i0 + b - w); }
+  }
+  if (phase != 0) return;
+  // horizontal link across the segment boundary (inside a segment the run label already encodes it)
+  if (g.s > 0 && (((cur & 1u) != 0) == ((prv >> 31) != 0))) uf_union(L, i0, i0 - 1);
+  // frame pixels of the background belong to the outside region: one union per background run start on the first / last
+  // row, the first / last pixel of every other row
+  const unsigned ncur = ~cur & vm;
+  if (g.y == 0 || g.y == h - 1) {
+    unsigned st = run_starts(cur, g.nvalid) & ncur;
+    while (st) { const int b = __ffs(st) - 1; st &= st - 1; uf_union(L, (int)hw, i0 + b); }
+  } else {
+    if (g.s == 0 && (ncur & 1u)) uf_union(L, (int)hw, i0);
+  }
+  if (g.s == wq - 1 && ((ncur >> (g.nvalid - 1)) & 1u)) uf_union(L, (int)hw, i0 + g.nvalid - 1);
+}
+__global__ void __launch_bounds__(CCL_THREADS)
+ccl_link_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, int* __restrict__ label, int phase) {
+  const int64_t stride = (int64_t)gridDim.x * CCL_THREADS;
+  if (phase == 0) {
+    const int64_t nseg = (int64_t)n * h * wq;
+    for (int64_t widx = (int64_t)blockIdx.x * CCL_THREADS + threadIdx.x; widx < nseg; widx += stride) link_word(bits, widx, h, w, wq, label, 0);
+  } else {
+    // only the first row of every 32-row strip (except row 0) takes part
+    const int nedge = (h - 1) / 32;                          // rows 32, 64, ...
+    const int64_t total = (int64_t)n * nedge * wq;
+    for (int64_t t = (int64_t)blockIdx.x * CCL_THREADS + threadIdx.x; t < total; t += stride) {
+      const int s = (int)(t % wq); const int64_t q = t / wq;
+      const int e = (int)(q % nedge), img = (int)(q / nedge);
+      link_word(bits, ((int64_t)img * h + (int64_t)(e + 1) * 32) * wq + s, h, w, wq, label, 1);
     }
   }
 }
 
-// C: run-start pixels jump straight to their root; roots zero their statistics slot
+// C: run-start pixels jump straight to their root; roots zero their statistics slot.  One thread per word (see B).
 __global__ void __launch_bounds__(CCL_THREADS)
-ccl_flatten_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, int* __restrict__ label, CompStat* __restrict__ stat, int init_stats) {
+ccl_flatten_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, int* __restrict__ label, CompStat* __restrict__ stat,
+                   int init_stats, unsigned* __restrict__ rootbits) {
   const int64_t hw = (int64_t)h * w;
-  const int lane = threadIdx.x & 31;
   const int64_t nseg = (int64_t)n * h * wq;
-  const int64_t wstride = (int64_t)gridDim.x * (CCL_THREADS / 32);
-  for (int64_t widx = (int64_t)blockIdx.x * (CCL_THREADS / 32) + (threadIdx.x >> 5); widx < nseg; widx += wstride) {
+  for (int64_t widx = (int64_t)blockIdx.x * CCL_THREADS + threadIdx.x; widx < nseg; widx += (int64_t)gridDim.x * CCL_THREADS) {
     Seg g; seg_of(widx, h, wq, w, g);
     int* L = label + g.img * (hw + 1);
-    if (widx % ((int64_t)h * wq) == 0 && lane == 0) L[hw] = uf_find(L, (int)hw);
-    if (lane >= g.nvalid) continue;
-    const unsigned st = run_starts(bits[widx], g.nvalid);
-    if (!(st & (1u << lane))) continue;
-    const int i = g.y * w + g.x0 + lane;
-    const int r = uf_find(L, i);
-    L[i] = r;
-    if (r == i && init_stats) {
-      CompStat z;
-      z.sum = 0.0; z.acc_sum = 0.0; z.count = 0; z.acc_count = 0;
-      z.x0 = w; z.y0 = h; z.x1 = -1; z.y1 = -1;
-      stat[g.img * hw + i] = z;
+    if (g.y == 0 && g.s == 0) L[hw] = uf_find(L, (int)hw);
+    unsigned st = run_starts(bits[widx], g.nvalid) & valid_mask(g.nvalid);
+    unsigned roots = 0;
+    while (st) {
+      const int b = __ffs(st) - 1; st &= st - 1;
+      const int i = g.y * w + g.x0 + b;
+      const int r = uf_find(L, i);
+      L[i] = r;
+      if (r == i && init_stats) {
+        CompStat z;
+        z.sum = 0.0; z.acc_sum = 0.0; z.count = 0; z.acc_count = 0;
+        z.x0 = w; z.y0 = h; z.x1 = -1; z.y1 = -1;
+        stat[g.img * hw + i] = z;
+        roots |= 1u << b;
+      }
     }
+    if (init_stats) rootbits[widx] = roots;
   }
 }
 
@@ -244,7 +261,6 @@ ccl_stats_kernel(const float* __restrict__ pred, int c, const unsigned* __restri
     }
     const double pre_b = __shfl_sync(0xffffffffu, pre, b < g.nvalid ? b : g.nvalid - 1 < 0 ? 0 : (b > 31 ? 31 : b));
     if (!in) continue;
-    if (r != i) L[i] = r;                                  // final label
     if (r == r_out) continue;
     if (lane == a) {
       const int be = b < g.nvalid ? b : g.nvalid - 1;
@@ -304,17 +320,32 @@ ccl_tree_kernel(const uint8_t* __restrict__ bitmap, int h, int w, const int* __r
   }
 }
 
-// ---- ranking: candidates in cv2 order = roots by DESCENDING pixel index
+// ---- ranking: candidates in cv2 order = roots by DESCENDING pixel index.  Roots are known as one bit per pixel
+// (ccl_flatten_kernel), so counting and ranking touch 1/32 of a word per pixel instead of the 4-byte label.
+// root bits of word wi of an image, the outside region's root removed
+__device__ __forceinline__ unsigned cand_bits(const unsigned* __restrict__ rootbits, int64_t base, int wi, int nw, int w, int wq, int r_out) {
+  if (wi >= nw) return 0u;
+  unsigned rb = rootbits[base + wi];
+  const int y = wi / wq, x0 = (wi - y * wq) * 32;
+  const int o = r_out - (y * w + x0);
+  if (o >= 0 && o < 32 && r_out < (y + 1) * w) rb &= ~(1u << o);
+  return rb;
+}
 __global__ void __launch_bounds__(CCL_THREADS)
-ccl_count_kernel(int h, int w, const int* __restrict__ label, int* __restrict__ blk_count, int nblk) {
+ccl_count_kernel(int h, int w, int wq, const int* __restrict__ label, const unsigned* __restrict__ rootbits, int* __restrict__ blk_count, int nblk) {
   const int img = blockIdx.y, b = blockIdx.x;
-  const int64_t hw = (int64_t)h * w;
-  const int* L = label + img * (hw + 1);
-  const int r_out = L[hw];
-  const int64_t i = (int64_t)b * CCL_THREADS + threadIdx.x;
-  const int flag = (i < hw && L[i] == (int)i && (int)i != r_out) ? 1 : 0;
-  const int c = __syncthreads_count(flag);
-  if (threadIdx.x == 0) blk_count[img * nblk + b] = c;
+  const int nw = h * wq;
+  const int r_out = label[img * ((int64_t)h * w + 1) + (int64_t)h * w];
+  const int c = __popc(cand_bits(rootbits, (int64_t)img * nw, b * CCL_THREADS + threadIdx.x, nw, w, wq, r_out));
+  __shared__ int wsum[CCL_THREADS / 32];
+  const int ws = warp_sum(c);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = ws;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int k = 0; k < CCL_THREADS / 32; ++k) t += wsum[k];
+    blk_count[img * nblk + b] = t;
+  }
 }
 __global__ void __launch_bounds__(1024)
 ccl_scan_kernel(const int* __restrict__ blk_count, int* __restrict__ blk_off, int nblk, int* __restrict__ n_cands) {
@@ -344,50 +375,69 @@ ccl_scan_kernel(const int* __restrict__ blk_count, int* __restrict__ blk_off, in
   if (threadIdx.x == 0) n_cands[img] = carry;
 }
 __global__ void __launch_bounds__(CCL_THREADS)
-ccl_emit_kernel(const uint8_t* __restrict__ bitmap, int h, int w, const int* __restrict__ label, CompStat* __restrict__ stat,
-                const int* __restrict__ blk_off, int nblk, double box_thresh, DbbCandidate* __restrict__ cands, int max_cands,
-                int32_t* __restrict__ labels_out) {
+ccl_emit_kernel(const uint8_t* __restrict__ bitmap, int h, int w, int wq, const int* __restrict__ label, CompStat* __restrict__ stat,
+                const unsigned* __restrict__ rootbits, const int* __restrict__ blk_off, int nblk, double box_thresh,
+                DbbCandidate* __restrict__ cands, int max_cands) {
   const int img = blockIdx.y, b = blockIdx.x;
   const int64_t hw = (int64_t)h * w;
+  const int nw = h * wq;
   const uint8_t* bm = bitmap + img * hw;
   const int* L = label + img * (hw + 1);
   CompStat* S = stat + img * hw;
   const int r_out = L[hw];
-  const int64_t i = (int64_t)b * CCL_THREADS + threadIdx.x;
-  const bool in = i < hw;
-  const int r = in ? L[i] : -1;
-  if (in && labels_out) labels_out[img * hw + i] = bm[i] ? (r + 1) : -(r + 1);
-  const int flag = (in && r == (int)i && (int)i != r_out) ? 1 : 0;
-  // rank inside the block among HIGHER thread indices (suffix), via warp ballots
+  const int wi = b * CCL_THREADS + threadIdx.x;
+  unsigned rb = cand_bits(rootbits, (int64_t)img * nw, wi, nw, w, wq, r_out);
+  const int c = __popc(rb);
+  // roots in LATER words of this block (suffix count): warp suffix by shuffles + totals of the later warps
   __shared__ int wcount[CCL_THREADS / 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const unsigned bal = __ballot_sync(0xffffffffu, flag);
-  if (lane == 0) wcount[wid] = __popc(bal);
+  int suf = c;                                   // inclusive suffix over the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_down_sync(0xffffffffu, suf, o);
+    if (lane + o < 32) suf += t;
+  }
+  if (lane == 0) wcount[wid] = suf;
   __syncthreads();
-  if (!flag) return;
-  int rank = __popc(bal & ~((2u << lane) - 1u));      // lanes above me in my warp
+  if (!rb) return;
+  int rank = suf - c;
   for (int k = wid + 1; k < CCL_THREADS / 32; ++k) rank += wcount[k];
   rank += blk_off[img * nblk + b];
-  const CompStat s = S[i];
-  // (last reader of the statistics slot: acc_count now carries the candidate's output slot for ccl_points_kernel,
-  //  -1 = not an emitted, kept candidate)
-  {
+  const int y = wi / wq, x0 = (wi - y * wq) * 32;
+  while (rb) {                                   // highest pixel index first
+    const int bit = 31 - __clz(rb);
+    rb &= ~(1u << bit);
+    const int i = y * w + x0 + bit;
+    const CompStat s = S[i];
+    // (last reader of the statistics slot: acc_count now carries the candidate's output slot for ccl_points_kernel,
+    //  -1 = not an emitted, kept candidate)
     const double sc = (s.sum + s.acc_sum) / (double)(s.count + s.acc_count);
-    S[i].acc_count = (rank < max_cands && !(box_thresh > sc)) ? rank : -1;
+    const int keep = (box_thresh > sc) ? 0 : 1;
+    S[i].acc_count = (rank < max_cands && keep) ? rank : -1;
+    if (rank < max_cands) {
+      DbbCandidate cd;
+      cd.kind = bm[i] ? 0 : 1;
+      cd.first_y = y; cd.first_x = x0 + bit;
+      if (cd.kind == 0) { cd.x0 = s.x0; cd.y0 = s.y0; cd.x1 = s.x1; cd.y1 = s.y1; }
+      else { cd.x0 = s.x0 - 1; cd.y0 = s.y0 - 1; cd.x1 = s.x1 + 1; cd.y1 = s.y1 + 1; }   // + the ring of parent pixels
+      cd.count = s.count + s.acc_count;
+      cd.sum = s.sum + s.acc_sum;
+      cd.keep = keep;
+      cd.pad_ = 0;
+      cands[(int64_t)img * max_cands + rank] = cd;
+    }
+    ++rank;
   }
-  if (rank >= max_cands) return;
-  DbbCandidate cd;
-  const int y = (int)(i / w), x = (int)(i - (int64_t)y * w);
-  cd.kind = bm[i] ? 0 : 1;
-  cd.first_y = y; cd.first_x = x;
-  if (cd.kind == 0) { cd.x0 = s.x0; cd.y0 = s.y0; cd.x1 = s.x1; cd.y1 = s.y1; }
-  else { cd.x0 = s.x0 - 1; cd.y0 = s.y0 - 1; cd.x1 = s.x1 + 1; cd.y1 = s.y1 + 1; }   // + the ring of parent pixels
-  cd.count = s.count + s.acc_count;
-  cd.sum = s.sum + s.acc_sum;
-  const double score = cd.sum / (double)cd.count;
-  cd.keep = (box_thresh > score) ? 0 : 1;
-  cd.pad_ = 0;
-  cands[(int64_t)img * max_cands + rank] = cd;
+}
+// optional per-pixel label map (tests / debugging): fg 1 + root index, bg -(1 + root index)
+__global__ void __launch_bounds__(CCL_THREADS)
+ccl_labels_kernel(const uint8_t* __restrict__ bitmap, int64_t hw, const int* __restrict__ label, int32_t* __restrict__ labels_out) {
+  const int img = blockIdx.y;
+  const int* L = label + img * (hw + 1);
+  for (int64_t i = (int64_t)blockIdx.x * CCL_THREADS + threadIdx.x; i < hw; i += (int64_t)gridDim.x * CCL_THREADS) {
+    const int rr = L[L[i]];                      // run starts carry their root; every other pixel points at its run start
+    labels_out[img * hw + i] = bitmap[img * hw + i] ? (rr + 1) : -(rr + 1);
+  }
 }
 
 // G: border points of the KEPT candidates (src/postprocess.py:119-121: the contour handed to get_mini_boxes).  cv2.minAreaRect
@@ -395,28 +445,22 @@ ccl_emit_kernel(const uint8_t* __restrict__ bitmap, int h, int w, const int* __r
 // hull(hole border of G) = hull(foreground pixels 4-adjacent to G) -- so the device emits, per kept candidate, the two end
 // pixels of each of its segment runs (holes: the foreground pixels left / right of each run and the first / last foreground
 // pixel above / below it).  A few thousand (slot, x, y) triples per image cross to the host instead of the bitmap.
-__global__ void __launch_bounds__(CCL_THREADS)
-ccl_points_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, const int* __restrict__ label,
-                  const CompStat* __restrict__ stat, int32_t* __restrict__ points, int32_t* __restrict__ n_points, int cap) {
-  const int64_t hw = (int64_t)h * w;
-  const int lane = threadIdx.x & 31;
-  const int64_t nseg = (int64_t)n * h * wq;
-  const int64_t wstride = (int64_t)gridDim.x * (CCL_THREADS / 32);
-  for (int64_t widx = (int64_t)blockIdx.x * (CCL_THREADS / 32) + (threadIdx.x >> 5); widx < nseg; widx += wstride) {
-    Seg g; seg_of(widx, h, wq, w, g);
-    if (lane >= g.nvalid) continue;
-    const unsigned cur = bits[widx];
-    const unsigned st = run_starts(cur, g.nvalid);
-    if (!(st & (1u << lane))) continue;                       // one lane per run
-    const int* L = label + g.img * (hw + 1);
-    const CompStat* S = stat + g.img * hw;
-    const int a = lane;
-    const unsigned later = (lane >= 31) ? 0u : (st & ~((2u << lane) - 1u));
+// points of one word; WRITE = false only counts them
+template <bool WRITE>
+__device__ __forceinline__ int word_points(const unsigned* __restrict__ bits, int64_t widx, const Seg& g, int h, int w, int wq, const int* __restrict__ L,
+                                           const CompStat* __restrict__ S, int r_out, int32_t* __restrict__ out, int base, int cap) {
+  const unsigned cur = bits[widx];
+  const unsigned vm = valid_mask(g.nvalid);
+  const unsigned st = run_starts(cur, g.nvalid);
+  unsigned todo = st & vm;
+  int total = 0;
+  while (todo) {
+    const int a = __ffs(todo) - 1; todo &= todo - 1;
+    const unsigned later = (a >= 31) ? 0u : (st & ~((2u << a) - 1u));
     int b = later ? (__ffs(later) - 2) : 31;
     if (b > g.nvalid - 1) b = g.nvalid - 1;
-    const int i = g.y * w + g.x0 + a;
-    const int r = L[i];
-    if (r == L[hw]) continue;                                 // outside region
+    const int r = L[g.y * w + g.x0 + a];                      // run starts carry their root (ccl_flatten_kernel)
+    if (r == r_out) continue;
     const int slot = S[r].acc_count;
     if (slot < 0) continue;
     int px[6], py[6], k = 0;
@@ -424,7 +468,7 @@ ccl_points_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq
     // does the run really start / end here, or does it continue in the neighbouring 32-pixel word?
     const bool same_class_left = a == 0 && g.s > 0 && (((bits[widx - 1] >> 31) & 1u) == ((cur >> a) & 1u));
     const bool same_class_right = b == g.nvalid - 1 && g.s < wq - 1 && ((bits[widx + 1] & 1u) == ((cur >> b) & 1u));
-    if ((cur >> lane) & 1u) {
+    if ((cur >> a) & 1u) {
       if (!same_class_left) { px[k] = xs; py[k++] = g.y; }
       if (!same_class_right && (xe != xs || same_class_left)) { px[k] = xe; py[k++] = g.y; }
     } else {
@@ -441,14 +485,47 @@ ccl_points_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq
         if (m) { px[k] = g.x0 + __ffs(m) - 1; py[k++] = g.y + 1; if (m & (m - 1)) { px[k] = g.x0 + 31 - __clz(m); py[k++] = g.y + 1; } }
       }
     }
-    if (k == 0) continue;
-    const int pos = atomicAdd(&n_points[g.img], k);
-    for (int j = 0; j < k; ++j) {
-      if (pos + j < cap) {
-        int32_t* o = points + ((int64_t)g.img * cap + pos + j) * 2;
-        o[0] = slot; o[1] = (py[j] << 16) | px[j];
+    if (WRITE) {
+      for (int j = 0; j < k; ++j) {
+        if (base + total + j < cap) { out[2 * (base + total + j)] = slot; out[2 * (base + total + j) + 1] = (py[j] << 16) | px[j]; }
       }
     }
+    total += k;
+  }
+  return total;
+}
+__global__ void __launch_bounds__(CCL_THREADS)
+ccl_points_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, const int* __restrict__ label,
+                  const CompStat* __restrict__ stat, int32_t* __restrict__ points, int32_t* __restrict__ n_points, int cap) {
+  const int64_t hw = (int64_t)h * w;
+  const int64_t nseg = (int64_t)n * h * wq;
+  const int lane = threadIdx.x & 31;
+  // one thread per 32-pixel word (see ccl_link_kernel); count, reserve with ONE atomic per warp and image, then write
+  const int64_t nround = (nseg + CCL_THREADS - 1) / CCL_THREADS * CCL_THREADS;
+  for (int64_t widx = (int64_t)blockIdx.x * CCL_THREADS + threadIdx.x; widx < nround; widx += (int64_t)gridDim.x * CCL_THREADS) {
+    const bool in = widx < nseg;
+    Seg g; g.img = -1;
+    int cnt = 0;
+    const int* L = nullptr; const CompStat* S = nullptr; int r_out = 0;
+    if (in) {
+      seg_of(widx, h, wq, w, g);
+      L = label + g.img * (hw + 1); S = stat + g.img * hw; r_out = L[hw];
+      cnt = word_points<false>(bits, widx, g, h, w, wq, L, S, r_out, nullptr, 0, 0);
+    }
+    // exclusive prefix of cnt among the lanes of the same image
+    const unsigned peers = __match_any_sync(0xffffffffu, g.img);
+    int pre = 0, tot = 0;
+    for (unsigned m = peers; m; m &= m - 1) {
+      const int src = __ffs(m) - 1;
+      const int v = __shfl_sync(peers, cnt, src);
+      if (src < lane) pre += v;
+      tot += v;
+    }
+    int base = 0;
+    const int leader = __ffs(peers) - 1;
+    if (lane == leader && tot > 0 && in) base = atomicAdd(&n_points[g.img], tot);
+    base = __shfl_sync(peers, base, leader);
+    if (in && cnt > 0) word_points<true>(bits, widx, g, h, w, wq, L, S, r_out, points + (int64_t)g.img * cap * 2, base + pre, cap);
   }
 }
 
@@ -469,8 +546,8 @@ extern "C" int dbb_ccl_border_points(const void* workspace, size_t workspace_byt
   const int wq = (int)((w + 31) / 32);
   CclWs ws = ccl_carve(const_cast<void*>(workspace), n, hw, h, wq);
   const int64_t nseg = n * h * wq;
-  int gseg = (int)((nseg + CCL_THREADS / 32 - 1) / (CCL_THREADS / 32));
-  if (gseg > DBB_NUM_SMS * 16) gseg = DBB_NUM_SMS * 16;
+  int gseg = (int)((nseg + CCL_THREADS - 1) / CCL_THREADS);
+  if (gseg > DBB_NUM_SMS * 8) gseg = DBB_NUM_SMS * 8;
   DBB_CUDA(cudaMemsetAsync(n_points, 0, sizeof(int32_t) * (size_t)n, s));
   DBB_LAUNCH("ccl_points", s, ccl_points_kernel<<<gseg, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, points, n_points, cap));
   return DBB_OK;
@@ -479,7 +556,8 @@ extern "C" int dbb_ccl_border_points(const void* workspace, size_t workspace_byt
 extern "C" size_t dbb_postprocess_workspace(int64_t n, int64_t h, int64_t w) {
   const int64_t hw = h * w, wq = (w + 31) / 32;
   return ccl_align(sizeof(unsigned) * (size_t)n * h * wq) + ccl_align(sizeof(int) * (size_t)n * (hw + 1)) +
-         ccl_align(sizeof(CompStat) * (size_t)n * hw) + 2 * ccl_align(sizeof(int) * (size_t)n * ccl_nblk(hw)) + 256;
+         ccl_align(sizeof(CompStat) * (size_t)n * hw) + 2 * ccl_align(sizeof(int) * (size_t)n * ccl_nblk(hw)) +
+         ccl_align(sizeof(unsigned) * (size_t)n * h * wq) + 256;
 }
 
 extern "C" int dbb_binarize_ccl_score(const float* pred, int64_t n, int c, int64_t h, int64_t w, float thresh, double box_thresh,
@@ -488,6 +566,7 @@ extern "C" int dbb_binarize_ccl_score(const float* pred, int64_t n, int c, int64
   if (!pred || !bitmap || !cands || !n_cands || !workspace) return set_error(DBB_EINVAL, "binarize_ccl_score: null pointer");
   if (n <= 0 || c <= 0 || h <= 0 || w <= 0 || max_cands <= 0 || n > 65535) return set_error(DBB_EINVAL, "binarize_ccl_score: bad shape");
   if (h * w >= (int64_t)1 << 31) return set_error(DBB_EUNSUPPORTED, "binarize_ccl_score: image too large for 32-bit labels");
+  if (n * h * ((w + 31) / 32) >= (int64_t)1 << 32) return set_error(DBB_EUNSUPPORTED, "binarize_ccl_score: batch too large for 32-bit word indices");
   if (workspace_bytes < dbb_postprocess_workspace(n, h, w)) return set_error(DBB_EWORKSPACE, "binarize_ccl_score: workspace too small");
   if (!aligned16(workspace)) return set_error(DBB_EALIGN, "binarize_ccl_score: workspace not 16B aligned");
   cudaStream_t s = (cudaStream_t)stream;
@@ -501,17 +580,27 @@ extern "C" int dbb_binarize_ccl_score(const float* pred, int64_t n, int c, int64
   int gx = nblk < DBB_NUM_SMS * 8 ? nblk : DBB_NUM_SMS * 8;
   const dim3 grid((unsigned)gx, (unsigned)n), gridb((unsigned)nblk, (unsigned)n);
   DBB_LAUNCH("ccl_pack_init", s, ccl_pack_init_kernel<<<gseg, CCL_THREADS, 0, s>>>(pred, c, (int)n, (int)h, (int)w, wq, thresh, bitmap, ws.bits, ws.label));
-  DBB_LAUNCH("ccl_link", s, ccl_link_kernel<<<gseg, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, 0));
+  // thread-per-word kernels
+  int gword = (int)((nseg + CCL_THREADS - 1) / CCL_THREADS);
+  if (gword > DBB_NUM_SMS * 8) gword = DBB_NUM_SMS * 8;
+  DBB_LAUNCH("ccl_link", s, ccl_link_kernel<<<gword, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, 0));
   if (h > 32) {
-    DBB_LAUNCH("ccl_flatten", s, ccl_flatten_kernel<<<gseg, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, 0));
-    DBB_LAUNCH("ccl_link", s, ccl_link_kernel<<<gseg, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, 1));
+    const int64_t nedge_words = n * ((h - 1) / 32) * wq;
+    int gedge = (int)((nedge_words + CCL_THREADS - 1) / CCL_THREADS);
+    if (gedge > DBB_NUM_SMS * 8) gedge = DBB_NUM_SMS * 8;
+    if (gedge < 1) gedge = 1;
+    DBB_LAUNCH("ccl_flatten", s, ccl_flatten_kernel<<<gword, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, 0, ws.rootbits));
+    DBB_LAUNCH("ccl_link", s, ccl_link_kernel<<<gedge, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, 1));
   }
-  DBB_LAUNCH("ccl_flatten", s, ccl_flatten_kernel<<<gseg, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, 1));
+  DBB_LAUNCH("ccl_flatten", s, ccl_flatten_kernel<<<gword, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, 1, ws.rootbits));
   DBB_LAUNCH("ccl_stats", s, ccl_stats_kernel<<<gseg, CCL_THREADS, 0, s>>>(pred, c, ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat));
   DBB_LAUNCH("ccl_tree", s, ccl_tree_kernel<<<grid, CCL_THREADS, 0, s>>>(bitmap, (int)h, (int)w, ws.label, ws.stat));
-  DBB_LAUNCH("ccl_count", s, ccl_count_kernel<<<gridb, CCL_THREADS, 0, s>>>((int)h, (int)w, ws.label, ws.blk_count, nblk));
-  DBB_LAUNCH("ccl_scan", s, ccl_scan_kernel<<<(unsigned)n, 1024, 0, s>>>(ws.blk_count, ws.blk_off, nblk, n_cands));
-  DBB_LAUNCH("ccl_emit", s, ccl_emit_kernel<<<gridb, CCL_THREADS, 0, s>>>(bitmap, (int)h, (int)w, ws.label, ws.stat, ws.blk_off, nblk, box_thresh, cands, max_cands, labels));
+  const int nwblk = (int)((h * wq + CCL_THREADS - 1) / CCL_THREADS);        // blocks of 256 words in raster order
+  const dim3 gridw((unsigned)nwblk, (unsigned)n);
+  DBB_LAUNCH("ccl_count", s, ccl_count_kernel<<<gridw, CCL_THREADS, 0, s>>>((int)h, (int)w, wq, ws.label, ws.rootbits, ws.blk_count, nwblk));
+  DBB_LAUNCH("ccl_scan", s, ccl_scan_kernel<<<(unsigned)n, 1024, 0, s>>>(ws.blk_count, ws.blk_off, nwblk, n_cands));
+  DBB_LAUNCH("ccl_emit", s, ccl_emit_kernel<<<gridw, CCL_THREADS, 0, s>>>(bitmap, (int)h, (int)w, wq, ws.label, ws.stat, ws.rootbits, ws.blk_off, nwblk, box_thresh, cands, max_cands));
+  if (labels) DBB_LAUNCH("ccl_labels", s, ccl_labels_kernel<<<grid, CCL_THREADS, 0, s>>>(bitmap, hw, ws.label, labels));
   return DBB_OK;
 }
 
