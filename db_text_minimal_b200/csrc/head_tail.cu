@@ -191,13 +191,13 @@ head_tail_fwd_kernel(const T* __restrict__ zt, int n_img, int h2, int w2, const 
       const int px = col >> 1, tap = a * 2 + (col & 1);
       if (j0 + px < w2) {
         const float zb = zs[0][tap][px] + bias_b, ztv = zs[1][tap][px] + bias_t;
-        const float P = 1.f / (1.f + expf(-zb));
-        const float T = 1.f / (1.f + expf(-ztv));
+        const float Pm = 1.f / (1.f + expf(-zb));
+        const float Tm = 1.f / (1.f + expf(-ztv));
         const int64_t plane = (int64_t)H * W;
         float* o = out + ((int64_t)n * out_c) * plane + (int64_t)(2 * i + a) * W + 2 * j0 + col;
-        o[0] = P;
-        o[plane] = T;
-        if (out_c == 3) o[2 * plane] = 1.f / (1.f + expf(-k * (P - T)));
+        o[0] = Pm;
+        o[plane] = Tm;
+        if (out_c == 3) o[2 * plane] = 1.f / (1.f + expf(-k * (Pm - Tm)));
       }
     }
     __syncthreads();
@@ -355,8 +355,195 @@ head_tail_bwd_reduce_kernel(const T* __restrict__ zt, int n_img, int h2, int w2,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// backward "reduce" on the tensor cores (bf16 activations, W2 a multiple of 64: the training shapes).
+//
+// The CUDA-core kernel above spends ~14 FMA-class instructions per (channel, input pixel) and is issue-bound at 0.30 of the
+// HBM roofline (ncu, profiles/prof_mem_r01.md).  All of its per-channel sums derive from TWO pixel reductions,
+//     M[c][t] = sum_px mask[c,px] dz[t,px]           Z[c][t] = sum_px mask[c,px] z[c,px] dz[t,px]
+// (mask = [z*scale + shift > 0], dz = the four tap gradients of the pixel):
+//     dW2[c][t] = scale_c Z + shift_c M      sum dy = sum_t w2[c][t] M      sum dy*xhat = invstd_c sum_t w2[c][t] (Z - mean_c M)
+// and M, Z are GEMMs over the pixel index: A = mask resp. mask*z (16 channels x 16 pixels, bf16: mask is 0/1 and z IS bf16, so
+// both are exact), B = dz (16 pixels x 8 columns = 4 taps x {hi, lo} bf16 split of the fp32 value: relative error 2^-17),
+// fp32 accumulate -- mma.sync.m16n8k16.  Per 64-pixel tile a warp owns 16 channels and issues 4 k-steps of
+// {ldmatrix.x4.trans from the 128B-swizzled TMA tile, 4 packed compare / and pairs, 2 MMAs}.  The ReLU mask is evaluated as
+// a packed bf16 comparison against the per-channel boundary zb = the largest bf16 value with fmaf(zb, scale, shift) <= 0
+// (found by bisection in the prologue; fmaf is monotone in z, so the mask equals the forward pass's for every bf16 z).
+// ---------------------------------------------------------------------------------------------
+constexpr int HT_MZ = 8;                 // per channel: M[4 taps], Z[4 taps]
+constexpr int HT_DZ_PITCH = 72;          // words per (branch, tap) row of the packed dz tile: conflict-free B-fragment reads
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// ordered index <-> bf16 bit pattern (monotone in the represented value; NaNs excluded by the range searched)
+__device__ __forceinline__ uint32_t bf16_from_ordered(int k) {      // k in [-0x7f80, 0x7f80]: -inf .. +inf
+  return k >= 0 ? (uint32_t)k : (0x8000u | (uint32_t)(-k));
+}
+// largest bf16 value zb (as ordered index) with fmaf(zb, sc, sh) <= 0, for sc > 0 (callers pass |sc| and flip z's sign otherwise)
+__device__ __forceinline__ int relu_boundary(float sc, float sh) {
+  int lo = -0x7f80, hi = 0x7f80;         // invariant: f(lo) <= 0 is assumed (f(-inf) = -inf), f(hi) > 0 (f(+inf) = +inf)
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    const float z = __uint_as_float(bf16_from_ordered(mid) << 16);
+    if (fmaf(z, sc, sh) > 0.f) hi = mid; else lo = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(HT_THREADS, 3)
+head_tail_bwd_reduce_mma_kernel(const __grid_constant__ CUtensorMap tmap, int n_img, int h2, int w2, const float* __restrict__ stats4,
+                                const float* __restrict__ out, const float* __restrict__ dout, float k,
+                                float* __restrict__ partials /* [grid][128*8 + 2] */) {
+  extern __shared__ uint8_t mma_smem_raw[];                               // HT_STAGES x {2 halves x [64 px][128 B], 128B swizzle}
+  uint8_t* ring_smem = mma_smem_raw + ((1024u - (smem_u32(mma_smem_raw) & 1023u)) & 1023u);      // swizzled TMA tiles: 1024 B
+  __shared__ uint32_t dzp[2][4][HT_DZ_PITCH];                             // packed (hi | lo << 16) bf16 split of dz
+  __shared__ uint64_t full_bar[HT_STAGES];
+  __shared__ float redB[HT_THREADS / 32][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int tiles_per_row = w2 / HT_TILE;
+  const int64_t ntiles = (int64_t)n_img * h2 * tiles_per_row;
+  const int H = 2 * h2, W = 2 * w2;
+  // ---- per-thread channel constants: rows g and g + 8 of this warp's 16-channel slab
+  uint32_t flip[2], zb2[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int ch = warp * 16 + g + 8 * r;
+    const float sc = stats4[ch], sh = stats4[128 + ch];
+    uint32_t f = 0, zb;
+    if (sc > 0.f) zb = bf16_from_ordered(relu_boundary(sc, sh));
+    else if (sc < 0.f) { f = 0x8000u; zb = bf16_from_ordered(relu_boundary(-sc, sh)); }   // mask = [-z > zb'] with f(-z') = (-sc) z' + sh
+    else zb = sh > 0.f ? 0xff80u /* -inf: every z passes */ : 0x7f80u /* +inf: none */;
+    flip[r] = f | (f << 16);
+    zb2[r] = zb | (zb << 16);
+  }
+  auto issue = [&](int64_t tile, int stage) {
+    int n, i, j0;
+    tile_coords(tile, tiles_per_row, h2, n, i, j0);
+    uint8_t* dst = ring_smem + stage * HT_TILE_BYTES;
+    mbar_arrive_expect_tx(&full_bar[stage], HT_TILE_BYTES);
+    ptx::tma_load_4d(dst, &tmap, &full_bar[stage], 0, j0, i, n);
+    ptx::tma_load_4d(dst + HT_TILE_BYTES / 2, &tmap, &full_bar[stage], 64, j0, i, n);
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < HT_STAGES; ++s) mbar_init(&full_bar[s], 1);
+    fence_barrier_init();
+    for (int s = 0; s < HT_STAGES; ++s) {
+      const int64_t tl = blockIdx.x + (int64_t)s * gridDim.x;
+      if (tl < ntiles) issue(tl, s);
+    }
+  }
+  __syncthreads();
+  float accM[4] = {0.f, 0.f, 0.f, 0.f}, accZ[4] = {0.f, 0.f, 0.f, 0.f};
+  float accBb = 0.f, accBt = 0.f;
+  PhaseAIn pa;
+  pa.valid = 0;
+  if ((int64_t)blockIdx.x < ntiles) {
+    int n, i, j0;
+    tile_coords(blockIdx.x, tiles_per_row, h2, n, i, j0);
+    bwd_phase_a_load(pa, out, dout, n, i, j0, w2, H, W);
+  }
+  const int br = warp >> 2;                                   // channels 0..63 = binarize branch, 64..127 = thresh
+  // ldmatrix row address of this lane inside a half tile: matrix mi = lane / 8 -> (pixel block, channel chunk)
+  const int mi = lane >> 3, mr = lane & 7;
+  const int chunk = (warp & 3) * 2 + (mi & 1);                // 16-byte chunk (8 channels) inside the 128-byte row
+  const int prow = (mi >> 1) * 8 + mr;                        // pixel row inside the 16-pixel k-step
+  int64_t kk = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++kk) {
+    // ---- phase A: dz of this tile's 256 output pixels -> packed hi/lo bf16 in shared memory
+    {
+      const int a = threadIdx.x >> 7, col = threadIdx.x & 127;
+      const int px = col >> 1, tap = a * 2 + (col & 1);
+      float dzb = 0.f, dzt = 0.f;
+      if (pa.valid) {
+        const float e = expf(-k * (pa.P - pa.T));
+        const float sgrad = pa.dB * k * pa.B * pa.B * e;
+        dzb = (pa.dP + sgrad) * pa.P * (1.f - pa.P);
+        dzt = (pa.dT - sgrad) * pa.T * (1.f - pa.T);
+      }
+      accBb += dzb; accBt += dzt;
+      const __nv_bfloat16 hb = __float2bfloat16_rn(dzb), ht = __float2bfloat16_rn(dzt);
+      const __nv_bfloat16 lb = __float2bfloat16_rn(dzb - __bfloat162float(hb)), lt = __float2bfloat16_rn(dzt - __bfloat162float(ht));
+      dzp[0][tap][px] = (uint32_t)__bfloat16_as_ushort(hb) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+      dzp[1][tap][px] = (uint32_t)__bfloat16_as_ushort(ht) | ((uint32_t)__bfloat16_as_ushort(lt) << 16);
+    }
+    if (tile + gridDim.x < ntiles) {       // request the next tile's maps now; consumed at the top of the next iteration
+      int n2, i2, j2;
+      tile_coords(tile + gridDim.x, tiles_per_row, h2, n2, i2, j2);
+      bwd_phase_a_load(pa, out, dout, n2, i2, j2, w2, H, W);
+    }
+    __syncthreads();
+    const int stage = (int)(kk % HT_STAGES);
+    mbar_wait(&full_bar[stage], (uint32_t)((kk / HT_STAGES) & 1));
+    const uint32_t half_base = smem_u32(ring_smem + stage * HT_TILE_BYTES + br * (HT_TILE_BYTES / 2));
+    const uint32_t* dzrow = &dzp[br][g & 3][0];
+    const uint32_t sel = (g & 4) ? 0x7632u : 0x5410u;         // PRMT selector: lo halves (bytes 2,3 of each word) or hi halves (0,1)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int p = ks * 16 + prow;
+      uint32_t a[4];
+      ldmatrix_x4_trans(a, half_base + p * 128 + ((chunk ^ (p & 7)) << 4));
+      // B fragment: column n = g -> (tap g & 3, part g >> 2), rows k = 2t, 2t+1 | 2t+8, 2t+9
+      const int kx = ks * 16 + 2 * t;
+      const uint32_t b0 = __byte_perm(dzrow[kx], dzrow[kx + 1], sel), b1 = __byte_perm(dzrow[kx + 8], dzrow[kx + 9], sel);
+      uint32_t am[4], az[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = q & 1;                                  // a0, a2: channel row g; a1, a3: row g + 8
+        const uint32_t zf = a[q] ^ flip[r];
+        const __nv_bfloat162 zz = *reinterpret_cast<const __nv_bfloat162*>(&zf), bb = *reinterpret_cast<const __nv_bfloat162*>(&zb2[r]);
+        const uint32_t m = __hgt2_mask(zz, bb);               // 0xffff per element where z (sign-adjusted) > boundary
+        am[q] = m & 0x3f803f80u;                              // 1.0 / 0.0
+        az[q] = a[q] & m;                                     // z / 0.0
+      }
+      mma_bf16_16816(accM, am, b0, b1);
+      mma_bf16_16816(accZ, az, b0, b1);
+    }
+    __syncthreads();                                          // every warp is done with this stage and with dzp
+    if (threadIdx.x == 0) {
+      const int64_t nxt = tile + (int64_t)HT_STAGES * gridDim.x;
+      if (nxt < ntiles) issue(nxt, stage);
+    }
+  }
+  // ---- per-CTA partials.  D fragment: c0, c1 = (row g, cols 2t, 2t+1); c2, c3 = (row g + 8, ...); cols 0..3 = hi parts of
+  // taps 0..3, cols 4..7 = lo parts: lanes t and t ^ 2 hold the two halves of the same taps
+  float* my = partials + (size_t)blockIdx.x * (128 * HT_MZ + 2);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    accM[q] += __shfl_xor_sync(0xffffffffu, accM[q], 2);
+    accZ[q] += __shfl_xor_sync(0xffffffffu, accZ[q], 2);
+  }
+  if (t < 2) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int ch = warp * 16 + g + 8 * r;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        my[ch * HT_MZ + 2 * t + e] = accM[2 * r + e];
+        my[ch * HT_MZ + 4 + 2 * t + e] = accZ[2 * r + e];
+      }
+    }
+  }
+  accBb = warp_sum(accBb); accBt = warp_sum(accBt);
+  if (lane == 0) { redB[warp][0] = accBb; redB[warp][1] = accBt; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float sB = 0.f;
+    for (int wv = 0; wv < HT_THREADS / 32; ++wv) sB += redB[wv][threadIdx.x];
+    my[128 * HT_MZ + threadIdx.x] = sB;
+  }
+}
+
 // one warp per channel (128 warps) + one warp per bias; lanes stride over the per-block partials in a fixed order
-__global__ void head_tail_bwd_finalize_kernel(const float* __restrict__ partials, int nblk, double count,
+// layout 0: per channel {dW2[4], sum dy, sum dy*xhat} (CUDA-core reduce); layout 1: per channel {M[4], Z[4]} (tensor-core reduce)
+__global__ void head_tail_bwd_finalize_kernel(const float* __restrict__ partials, int nblk, int layout, const float* __restrict__ w2b,
+                                              const float* __restrict__ w2t, double count,
                                               const float* __restrict__ gamma_b, const float* __restrict__ gamma_t,
                                               const float* __restrict__ stats4, float* __restrict__ dgamma_b,
                                               float* __restrict__ dbeta_b, float* __restrict__ dgamma_t,
@@ -365,26 +552,42 @@ __global__ void head_tail_bwd_finalize_kernel(const float* __restrict__ partials
                                               float* __restrict__ db2t) {
   const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // 0..129
   const int lane = threadIdx.x & 31;
-  const size_t stride = 128 * HT_NACC + 2;
+  const int per = layout ? HT_MZ : HT_NACC;
+  const size_t stride = 128 * per + 2;
   if (ch >= 130) return;
   if (ch >= 128) {
     double s = 0.0;
-    for (int b = lane; b < nblk; b += 32) s += (double)partials[(size_t)b * stride + 128 * HT_NACC + (ch - 128)];
+    for (int b = lane; b < nblk; b += 32) s += (double)partials[(size_t)b * stride + 128 * per + (ch - 128)];
     s = warp_sum(s);
     if (lane == 0) ((ch - 128) ? db2t : db2b)[0] = (float)s;
     return;
   }
-  double acc[HT_NACC];
+  double raw[HT_MZ];
 #pragma unroll
-  for (int q = 0; q < HT_NACC; ++q) acc[q] = 0.0;
+  for (int q = 0; q < HT_MZ; ++q) raw[q] = 0.0;
   for (int b = lane; b < nblk; b += 32) {
 #pragma unroll
-    for (int q = 0; q < HT_NACC; ++q) acc[q] += (double)partials[(size_t)b * stride + ch * HT_NACC + q];
+    for (int q = 0; q < HT_MZ; ++q) if (q < per) raw[q] += (double)partials[(size_t)b * stride + ch * per + q];
   }
 #pragma unroll
-  for (int q = 0; q < HT_NACC; ++q) acc[q] = warp_sum(acc[q]);
+  for (int q = 0; q < HT_MZ; ++q) raw[q] = warp_sum(raw[q]);
   if (lane != 0) return;
   const int br = ch >> 6, c = ch & 63;
+  double acc[HT_NACC];
+  if (layout) {        // dW2 = scale Z + shift M;  sum dy = sum_t w2 M;  sum dy*xhat = invstd sum_t w2 (Z - mean M)
+    const double sc = stats4[ch], sh = stats4[128 + ch], mean = stats4[256 + ch], inv = stats4[384 + ch];
+    const float* w2 = br ? w2t : w2b;
+    acc[4] = 0.0; acc[5] = 0.0;
+    for (int t = 0; t < 4; ++t) {
+      const double M = raw[t], Z = raw[4 + t], w = (double)w2[c * 4 + t];
+      acc[t] = sc * Z + sh * M;
+      acc[4] += w * M;
+      acc[5] += w * (Z - mean * M);
+    }
+    acc[5] *= inv;
+  } else {
+    for (int q = 0; q < HT_NACC; ++q) acc[q] = raw[q];
+  }
   float* dw2 = br ? dw2t : dw2b;
   for (int t = 0; t < 4; ++t) dw2[c * 4 + t] = (float)acc[t];
   (br ? dbeta_t : dbeta_b)[c] = (float)acc[4];
@@ -507,6 +710,19 @@ template <typename T>
 int head_tail_bwd_reduce(const T* zt, int n, int h2, int w2, const float* stats4, const float* w2b, const float* w2t,
                          const float* out, const float* dout, float k, float* partials, int* nblk, cudaStream_t s) {
   *nblk = ht_reduce_grid(n, h2, w2);
+  static const bool no_mma = getenv("DBB_HT_NO_MMA") != nullptr;      // A/B switch
+  if (ht_can_pipe<T>() && w2 % HT_TILE == 0 && !no_mma) {
+    // tensor-core reduce; *nblk < 0 tells head_tail_bwd_finalize that the partials are in the {M, Z} layout
+    static bool attr = false;
+    if (!attr) { DBB_CUDA(cudaFuncSetAttribute(head_tail_bwd_reduce_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_RING_BYTES + 1024)); attr = true; }
+    CUtensorMap tm;
+    int rc = encode_tmap_nhwc(&tm, reinterpret_cast<const bf16*>(zt), n, h2, w2, 128, 0, 128, 1, 1, HT_TILE, 1, 1);
+    if (rc) return rc;
+    const int g = ht_pipe_grid(n, h2, w2, 3);
+    DBB_LAUNCH("head_tail_bwd_reduce", s, head_tail_bwd_reduce_mma_kernel<<<g, HT_THREADS, HT_RING_BYTES + 1024, s>>>(tm, n, h2, w2, stats4, out, dout, k, partials));
+    *nblk = -g;
+    return DBB_OK;
+  }
   if (ht_can_pipe<T>() && w2 % HT_TILE == 0) {
     static bool attr = false;
     if (!attr) { DBB_CUDA(cudaFuncSetAttribute(head_tail_bwd_reduce_kernel<true, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_RING_BYTES)); attr = true; }
@@ -520,8 +736,11 @@ int head_tail_bwd_reduce(const T* zt, int n, int h2, int w2, const float* stats4
 }
 int head_tail_bwd_finalize(const float* partials, int nblk, int64_t count, const float* gamma_b, const float* gamma_t,
                            const float* stats4, float* dgamma_b, float* dbeta_b, float* dgamma_t, float* dbeta_t,
-                           float* coef3, float* dw2b, float* dw2t, float* db2b, float* db2t, cudaStream_t s) {
-  DBB_LAUNCH("head_tail_bwd_finalize", s, head_tail_bwd_finalize_kernel<<<(130 + 7) / 8, 256, 0, s>>>(partials, nblk, (double)count, gamma_b, gamma_t, stats4, dgamma_b, dbeta_b,
+                           float* coef3, float* dw2b, float* dw2t, float* db2b, float* db2t, const float* w2b, const float* w2t,
+                           cudaStream_t s) {
+  const int layout = nblk < 0 ? 1 : 0;
+  if (nblk < 0) nblk = -nblk;
+  DBB_LAUNCH("head_tail_bwd_finalize", s, head_tail_bwd_finalize_kernel<<<(130 + 7) / 8, 256, 0, s>>>(partials, nblk, layout, w2b, w2t, (double)count, gamma_b, gamma_t, stats4, dgamma_b, dbeta_b,
                                                   dgamma_t, dbeta_t, coef3, dw2b, dw2t, db2b, db2t));
   return DBB_OK;
 }

@@ -694,7 +694,7 @@ static int net_backward_t(DbbNet* net, const float* x_img, const float* out, con
     RC(head_tail_bwd_finalize(c.partials(), nblk, Pt, c.par(P(hb + ".4.weight")), c.par(P(ht + ".4.weight")), c.template p<float>(net->stats_t),
                               c.grad(P(hb + ".4.weight")), c.grad(P(hb + ".4.bias")), c.grad(P(ht + ".4.weight")), c.grad(P(ht + ".4.bias")),
                               c.template p<float>(net->coef_t), c.grad(P(hb + ".6.weight")), c.grad(P(ht + ".6.weight")), c.grad(P(hb + ".6.bias")),
-                              c.grad(P(ht + ".6.bias")), c.s));
+                              c.grad(P(ht + ".6.bias")), c.par(P(hb + ".6.weight")), c.par(P(ht + ".6.weight")), c.s));
     RC(head_tail_bwd_apply(c.p(net->zt), N, 2 * hf, 2 * wf, c.template p<float>(net->stats_t), c.template p<float>(net->coef_t), c.par(P(hb + ".6.weight")),
                            c.par(P(ht + ".6.weight")), hout, dhout, STEP_K, c.p(net->d_zt), c.s));
     // ---- ConvTranspose2d(64,64,2,2) x 2

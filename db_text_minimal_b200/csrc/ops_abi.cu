@@ -108,6 +108,6 @@ extern "C" int dbb_head_tail_bwd(const void* zt, int64_t n, int64_t h2, int64_t 
   int rc, nblk = 0;
   if ((rc = head_tail_bwd_reduce((const bf16*)zt, (int)n, (int)h2, (int)w2, stats4, w2b, w2t, out, dout, k, partials, &nblk, s))) return rc;
   if ((rc = head_tail_bwd_finalize(partials, nblk, n * h2 * w2, gamma, gamma + 64, stats4, dgamma, dbeta, dgamma + 64, dbeta + 64, coef3,
-                                   dw2b, dw2t, db2b, db2t, s))) return rc;
+                                   dw2b, dw2t, db2b, db2t, w2b, w2t, s))) return rc;
   return head_tail_bwd_apply((const bf16*)zt, (int)n, (int)h2, (int)w2, stats4, coef3, w2b, w2t, out, dout, k, (bf16*)d_zt, s);
 }

@@ -3,14 +3,14 @@
 
 The reference draws one polygon at a time into numpy canvases inside a single-worker DataLoader.  ``thresh_maps`` takes all
 text polygons of a batch and produces the (N, H, W) border map with one launch (csrc/gt_maps.cu, float64, bit-identical to
-the numpy arithmetic).  The polygon dilation that precedes the distance field is Clipper's (pyclipper) in the reference; it
-is used when installed, otherwise the convex round-join restatement of postprocess.offset_convex_round (parity of that
-stage is unpinned); the dilated polygon's fill (the ``mask`` canvas) stays a host cv2.fillPoly."""
+the numpy arithmetic).  The polygon dilation that precedes the distance field is Clipper's (pyclipper) in the reference; here
+it is the C++ ClipperOffset restatement behind postprocess.clipper_offset (csrc/clipper_offset.cu; parity of that stage is
+unpinned); the dilated polygon's fill (the ``mask`` canvas) stays a host cv2.fillPoly."""
 import numpy as np
 import torch
 
 from . import _lib
-from .postprocess import _pyclipper, offset_convex_round
+from .postprocess import clipper_offset
 
 
 def dilate_polygon(polygon, shrink_ratio=0.4):
@@ -22,14 +22,10 @@ def dilate_polygon(polygon, shrink_ratio=0.4):
     if area <= 0:
         return None, 0.0
     distance = area * (1 - np.power(shrink_ratio, 2)) / length
-    pc = _pyclipper()
-    if pc is not None:
-        off = pc.PyclipperOffset()
-        off.AddPath([tuple(pt) for pt in polygon], pc.JT_ROUND, pc.ET_CLOSEDPOLYGON)
-        padded = np.array(off.Execute(distance)[0])
-    else:
-        padded = np.round(offset_convex_round(p, distance)).astype(np.int64)
-    return padded, float(distance)
+    res = clipper_offset(p, distance)          # padded_polygon = np.array(padding.Execute(distance)[0])
+    if not res:
+        return None, 0.0
+    return res[0].astype(np.int64), float(distance)
 
 
 def thresh_maps(polygons_per_image, height, width, shrink_ratio=0.4, device="cuda", padded=None):
