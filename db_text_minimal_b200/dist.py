@@ -13,13 +13,37 @@ import torch.distributed as dist
 class GradSync:
     """Installs itself as ``model._segment_hook``; averages gradients across the process group."""
 
-    def __init__(self, model, group=None):
+    def __init__(self, model, group=None, broadcast=True):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.works = []
         self.pending = []
         model._segment_hook = self if self.world > 1 else None
         self.backend = dist.get_backend(group) if dist.is_initialized() else None
+        if broadcast and self.world > 1:
+            self.broadcast_state(model)
+
+    def broadcast_state(self, model, src=0):
+        """Every replica starts from rank `src`'s parameters AND buffers (as DistributedDataParallel does at construction):
+        replicas built without a common seed would otherwise diverge silently."""
+        with torch.no_grad():
+            for t in list(model.parameters()) + list(model.buffers()):
+                dist.broadcast(t.data, src=src, group=self.group)
+
+    def sync_buffers(self, model):
+        """Average the BatchNorm running statistics over the ranks (each rank normalises with its own shard's statistics, as
+        the single-device reference would; call this before evaluating or saving a checkpoint so that it does not carry
+        rank 0's statistics only)."""
+        if self.world == 1:
+            return
+        with torch.no_grad():
+            for name, b in model.named_buffers():
+                if b.is_floating_point():
+                    if self.backend == "nccl":
+                        dist.all_reduce(b.data, op=dist.ReduceOp.AVG, group=self.group)
+                    else:
+                        dist.all_reduce(b.data, op=dist.ReduceOp.SUM, group=self.group)
+                        b.data.div_(self.world)
 
     def __call__(self, seg, flat, bounds):
         if bounds is not None:

@@ -23,6 +23,8 @@ class FlatAdam(torch.optim.Optimizer):
         plist = model._param_list()
         used = [p for i, p in enumerate(plist) if not model._unused[i]]
         super().__init__(used, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        if len(self.param_groups) != 1:
+            raise ValueError("FlatAdam keeps one flat buffer: exactly one parameter group is supported")
         self.model = model
         dev = used[0].device
         _lib.require_cuda(used[0])
@@ -32,6 +34,7 @@ class FlatAdam(torch.optim.Optimizer):
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
         self._scratch_g = None
+        self._step_calls = 0
         with torch.no_grad():       # re-home every trained parameter into the flat buffer (state_dict is unaffected)
             for i, p in enumerate(plist):
                 if model._unused[i]:
@@ -40,6 +43,35 @@ class FlatAdam(torch.optim.Optimizer):
                 view = self.flat_p[o:o + p.numel()].view_as(p)
                 view.copy_(p)
                 p.data = view
+
+    # ------------------------------------------------------------------ checkpoint / resume (src/train.py:285-291 saves the model;
+    # a resumed run must also continue the Adam moments and the bias-correction step count)
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["flat"] = {"exp_avg": self.exp_avg.detach().clone(), "exp_avg_sq": self.exp_avg_sq.detach().clone(),
+                      "step": self.step_count.detach().clone(), "numel": int(self.flat_p.numel())}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        flat = state_dict.pop("flat", None)
+        super().load_state_dict(state_dict)
+        if flat is None:
+            raise ValueError("FlatAdam.load_state_dict: not a FlatAdam state (no flat moments)")
+        if int(flat["numel"]) != int(self.flat_p.numel()):
+            raise ValueError("FlatAdam.load_state_dict: flat layout mismatch")
+        self.exp_avg.copy_(flat["exp_avg"]); self.exp_avg_sq.copy_(flat["exp_avg_sq"]); self.step_count.copy_(flat["step"])
+
+    def _check_homes(self):
+        """Every trained parameter must still live inside flat_p (model.to() / .half() / a second FlatAdam re-home them)."""
+        model = self.model
+        base, end = self.flat_p.data_ptr(), self.flat_p.data_ptr() + 4 * self.flat_p.numel()
+        for i, p in enumerate(model._param_list()):
+            if model._unused[i]:
+                continue
+            if p.data_ptr() != base + 4 * model._flat_offsets[i] or not (base <= p.data_ptr() < end):
+                raise RuntimeError("FlatAdam: parameter %s no longer lives in the optimizer's flat buffer (the model was moved / "
+                                   "cast / re-wrapped after the optimizer was built); rebuild the optimizer" % model._pnames[i])
 
     def _flat_grad(self):
         """The flat gradient buffer of the last backward (zero-copy), or a gathered copy when the gradients were replaced."""
@@ -73,6 +105,9 @@ class FlatAdam(torch.optim.Optimizer):
         g = self._flat_grad()
         if g is None:
             return loss
+        if self._step_calls % 64 == 0:          # (a pointer walk over the 107 tensors: ~50 us, so not on every step)
+            self._check_homes()
+        self._step_calls += 1
         hp = self.param_groups[0]
         with torch.cuda.device(self.flat_p.device):
             _lib.check(_lib.lib().dbb_adam_step(self.flat_p.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr(),

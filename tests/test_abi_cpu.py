@@ -123,11 +123,20 @@ import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
 from db_text_minimal_b200.dist import GradSync
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
-class M:            # stands in for DBTextModel: GradSync only needs the hook slot
+class M(torch.nn.Module):            # stands in for DBTextModel: GradSync needs the hook slot, parameters and buffers
     _segment_hook = None
-m = M()
-sync = GradSync(m)
+    def __init__(self, rank):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.full((5,), float(rank + 1)))
+        self.register_buffer("running_mean", torch.full((3,), float(10 * (rank + 1))))
+rank = int(sys.argv[3])
+m = M(rank)
+sync = GradSync(m)                       # broadcasts rank 0's parameters and buffers (replicas built from different seeds)
 assert m._segment_hook is sync
+assert torch.equal(m.w.data, torch.full((5,), 1.0)) and torch.equal(m.running_mean, torch.full((3,), 10.0))
+m.running_mean.fill_(float(rank))
+sync.sync_buffers(m)                     # BatchNorm running statistics averaged over the ranks
+assert torch.allclose(m.running_mean, torch.full((3,), 0.5))
 rank = dist.get_rank()
 flat = torch.arange(100, dtype=torch.float32) * (rank + 1)
 slices = [(0, 30), (30, 80), (80, 100)]

@@ -68,3 +68,40 @@ def test_flat_adam_steps_on_the_backward_buffer_without_a_copy():
     # the model runs on the re-homed parameters
     out = model(img)
     assert torch.isfinite(out).all()
+
+
+def test_flat_adam_state_dict_resumes_moments_and_step():
+    """optimizer.state_dict() / load_state_dict() must carry the flat moments and the step count, and a model
+    that was moved after the optimizer was built must be detected."""
+    from db_text_minimal_b200.models import DBTextModel
+    from db_text_minimal_b200.optim import FlatAdam
+    torch.manual_seed(3)
+    g = torch.Generator(device="cuda").manual_seed(7)
+
+    def grads(model):
+        for p in _used(model):
+            p.grad = torch.randn(p.shape, device="cuda", generator=g) * 1e-2
+
+    a = DBTextModel().cuda().train()
+    oa = FlatAdam(a, lr=0.005)
+    for _ in range(3):
+        grads(a); oa.step()
+    sd_m, sd_o = {k: v.clone() for k, v in a.state_dict().items()}, oa.state_dict()
+    assert "flat" in sd_o and int(sd_o["flat"]["step"]) == 3
+    b = DBTextModel().cuda().train()
+    b.load_state_dict(sd_m)
+    ob = FlatAdam(b, lr=0.005)
+    ob.load_state_dict(sd_o)
+    gen_state = g.get_state()
+    grads(a); oa.step()
+    g.set_state(gen_state)
+    grads(b); ob.step()
+    for p, q in zip(_used(a), _used(b)):
+        assert torch.equal(p.detach(), q.detach())
+    assert int(ob.step_count.item()) == 4
+    # re-homing is checked: a parameter swapped out from under the optimizer raises instead of training a stale copy
+    first = _used(b)[0]
+    first.data = first.data.clone()
+    ob._step_calls = 0
+    with pytest.raises(RuntimeError):
+        grads(b); ob.step()
