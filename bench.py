@@ -36,6 +36,8 @@ def parse():
     ap.add_argument("--torch-adam", action="store_true", help="use torch.optim.Adam(fused=True) instead of db_text_minimal_b200.optim.FlatAdam")
     ap.add_argument("--no-graph-dp", action="store_true", help="multi-GPU: keep the step eager (the graph would contain the NCCL all-reduces)")
     ap.add_argument("--dump-kernels", default=None, help="write the full per-kernel timing table (JSON) to this path")
+    ap.add_argument("--e2e-float32", action="store_true", help="e2e: ship the batch as the reference's float32 tensors (184 MB) instead of "
+                    "uint8 image + uint8 maps + float32 threshold map (65.6 MB, lossless; expanded on the device by dbb_unpack_batch)")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the BASELINE config 4 / 5 summaries (single GPU only)")
     ap.add_argument("--cpu-batch", type=int, default=8, help="images in the bounded cpu_baseline sample of our arm's line")
     return ap.parse_args()
@@ -243,13 +245,20 @@ def run_ours(args):
     sync = GradSync(model)
 
     # synthetic batches: per-rank seeds; three distinct host batches rotate through pinned memory for the e2e loop
-    host = []
+    # images are 8-bit pixels minus the reference's per-channel mean (src/data_loaders.py:152-154), so that the batch can also
+    # travel in its compact form (uint8 image, uint8 {0,1} maps, float32 threshold map) and be expanded on the device
+    from db_text_minimal_b200 import data as dbdata
+    host, host_packed = [], []
+    mean = torch.tensor(dbdata.REFERENCE_MEAN, dtype=torch.float32).view(1, 3, 1, 1)
     for b in range(3):
-        img = synth.images(N, S, S, seed=100 * rank + b).pin_memory()
+        raw = (synth.images(N, S, S, seed=100 * rank + b) + mean).round().clamp(0, 255)
+        img = (raw - mean).pin_memory()
         gts = torch.from_numpy(synth.gt_maps(N, S, S, seed=100 * rank + b)).pin_memory()
         host.append((img, gts))
+        host_packed.append(tuple(t.pin_memory() for t in dbdata.pack_batch(img, gts)))
     dev_batches = [(i.to(dev), g.to(dev)) for i, g in host]
-    h2d_bytes = host[0][0].numel() * 4 + host[0][1].numel() * 4
+    compact = not args.e2e_float32
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_packed[0]) if compact else host[0][0].numel() * 4 + host[0][1].numel() * 4
 
     def eager_step(img, gts):
         opt.zero_grad(set_to_none=True)
@@ -306,17 +315,30 @@ def run_ours(args):
     # ---- end to end: host batches in pinned memory, H2D prefetch on a copy stream, loss read back every step
     copy_stream = torch.cuda.Stream()
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
-    bufs = [(torch.empty_like(dev_batches[0][0]), torch.empty_like(dev_batches[0][1])) for _ in range(2)]
+    if compact:
+        bufs = [tuple(torch.empty(t.shape, dtype=t.dtype, device=dev) for t in host_packed[0]) for _ in range(2)]
+        img_f = torch.empty_like(dev_batches[0][0]) if graphed is None else graphed.img
+        gts_f = torch.empty_like(dev_batches[0][1]) if graphed is None else graphed.gts
+    else:
+        bufs = [(torch.empty_like(dev_batches[0][0]), torch.empty_like(dev_batches[0][1])) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
 
     def prefetch(i):
         k = i % 2
+        src = host_packed[i % 3] if compact else host[i % 3]
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[k])
-            bufs[k][0].copy_(host[i % 3][0], non_blocking=True)
-            bufs[k][1].copy_(host[i % 3][1], non_blocking=True)
+            for d, t in zip(bufs[k], src):
+                d.copy_(t, non_blocking=True)
             ready[k].record(copy_stream)
+
+    def e2e_step(k):
+        if not compact:
+            return step(*bufs[k])
+        # expand straight into the step's input buffers (the CUDA graph's static tensors when the step is graphed)
+        dbdata.unpack_batch(*bufs[k], out_img=img_f, out_gts=gts_f)
+        return graphed.replay() if graphed is not None else eager_step(img_f, gts_f)
 
     def e2e_loop(nsteps):
         for k in range(2):
@@ -327,7 +349,7 @@ def run_ours(args):
                 prefetch(i + 1)
             k = i % 2
             torch.cuda.current_stream().wait_event(ready[k])
-            loss = step(*bufs[k])
+            loss = e2e_step(k)
             consumed[k].record()
             loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
             torch.cuda.current_stream().synchronize()          # the caller reads the loss every step (src/train.py:188-201)
@@ -421,7 +443,9 @@ def run_ours(args):
                            "l2": f"inputs {h2d_bytes / 1e6:.0f} MB/step (3 rotating batches) + ~6 GB of activations per step stream through the 126 MB L2; no explicit flush"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                    "note": "pinned host batches, H2D prefetch of step i+1 overlapped with step i, loss read back every step"},
+                    "note": ("pinned host batches, H2D prefetch of step i+1 overlapped with step i, loss read back every step; batch shipped as " +
+                             ("uint8 image + uint8 {0,1} maps + float32 threshold map and expanded on the device (dbb_unpack_batch, lossless)"
+                              if compact else "the reference loader's float32 tensors"))},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "conv_kernels": {"ms_per_step": conv_ms, "tflops": conv_fl / conv_ms / 1e9 if conv_ms else None,

@@ -59,6 +59,7 @@ struct IgemmPlan {
   int cls_cols;            // > 0: pixel-shuffle epilogue, GEMM column = class*cls_cols + channel (ConvTranspose2d k2 s2)
   ConvStats st;            // optional fused BatchNorm statistics of y
   ConvEpi epi;             // optional inference epilogue (scale != nullptr)
+  int no_staged_epilogue;  // A/B switch (DBB_NO_STAGED_EPI): direct per-thread stores in the 64-wide kernels
 };
 
 // weight packing: fp32 parameter -> bf16 GEMM B matrix [rows][K] (K-major)

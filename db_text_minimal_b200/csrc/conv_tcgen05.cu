@@ -261,7 +261,16 @@ struct IgemmPSmem {
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;                 // full[S], empty[S], t_full[2], t_empty[2], slot, flag
   static constexpr int STAT_OFF = BAR_OFF + 256;
-  static constexpr int TOTAL = STAT_OFF + 4 * 2 * BLOCK_N * 4 + 1024;     // + [4 quadrants][2][BLOCK_N] statistics
+  // Staged epilogue (64-wide tiles: the store-bound ConvTranspose / stem / 1x1 GEMMs).  Every epilogue warp owns a
+  // [32 rows][CW bf16 + 16 B pad] slab: rows are written as they come out of TMEM (one row per lane) and read back with
+  // consecutive lanes on consecutive 16-byte pieces of a row, so that a store instruction covers 8 half-lines of 64
+  // contiguous bytes (full 32-byte sectors) instead of 32 lines with a 16-byte partial-sector write each.  ncu on the
+  // ConvTranspose GEMM (profiles/prof_convt_r02.md): 13.1 M partial-sector writes for 6.55 M sectors of output, 119 us.
+  static constexpr bool STAGED = BLOCK_N == 64;
+  static constexpr int EPI_PITCH = (BLOCK_N / 2) * 2 + 16;
+  static constexpr int EPI_OFF = STAT_OFF + 4 * 2 * BLOCK_N * 4;          // + [4 quadrants][2][BLOCK_N] statistics
+  static constexpr int EPI_BYTES = STAGED ? 8 * 32 * EPI_PITCH : 0;
+  static constexpr int TOTAL = EPI_OFF + EPI_BYTES + 1024;
 };
 
 template <int BLOCK_N, int STAGES, bool STATS>
@@ -362,6 +371,20 @@ igemm_persist_kernel(const __grid_constant__ IgemmPlan p) {
     }
     float* w_sum = s_stat + q * 2 * BLOCK_N + cbase;
     float* w_sq = w_sum + BLOCK_N;
+    // staged write-out (see IgemmPSmem): lane -> (row i*RPI + lane/PP, 16-byte piece lane%PP) for i = 0..PP-1
+    constexpr int PP = CW / 8, RPI = 32 / PP;
+    // (not with fused statistics: that variant runs one CTA per SM and is bound by the per-tile epilogue latency chain --
+    //  measured 0.279 -> 0.375 ms for the two training-mode ConvTranspose launches with the extra shared-memory round trip)
+    const bool staged = SM::STAGED && !STATS && !p.accumulate && !p.no_staged_epilogue && (p.cls_cols == 0 || p.cls_cols % CW == 0);
+    uint8_t* slab = smem + SM::EPI_OFF + (warp - 2) * 32 * SM::EPI_PITCH;
+    int s_dn[SM::STAGED ? PP : 1], s_dh[SM::STAGED ? PP : 1], s_dw[SM::STAGED ? PP : 1];
+    if (SM::STAGED) {
+#pragma unroll
+      for (int i = 0; i < PP; ++i) {
+        const int rr = q * 32 + i * RPI + lane / PP;
+        s_dw[i] = rr % p.bw; s_dh[i] = (rr / p.bw) % p.bh; s_dn[i] = rr / (p.bw * p.bh);
+      }
+    }
     uint32_t j = 0;
     for (int mt = mt0; mt < m_tiles; mt += mt_step, ++j) {
       const uint32_t buf = j & 1u;
@@ -409,10 +432,34 @@ igemm_persist_kernel(const __grid_constant__ IgemmPlan p) {
           }
           o0.x = pack_bf16(f[0], f[1]);   o0.y = pack_bf16(f[2], f[3]);   o0.z = pack_bf16(f[4], f[5]);   o0.w = pack_bf16(f[6], f[7]);
           o1.x = pack_bf16(f[8], f[9]);   o1.y = pack_bf16(f[10], f[11]); o1.z = pack_bf16(f[12], f[13]); o1.w = pack_bf16(f[14], f[15]);
-          dst[0] = o0; dst[1] = o1;
+          if (!staged) { dst[0] = o0; dst[1] = o1; }
+        }
+        if (SM::STAGED && staged) {
+          uint4* sl = reinterpret_cast<uint4*>(slab + lane * SM::EPI_PITCH + ci * 32);
+          sl[0] = o0; sl[1] = o1;
         }
         if (REG_STATS) stat_accumulate_regs(o0, o1, acc_s[REG_STATS ? ci : 0], acc_q[REG_STATS ? ci : 0]);
         else if (STATS) stat_accumulate_smem(o0, o1, lane, w_sum + c, w_sq + c);
+      }
+      if (SM::STAGED && staged) {
+        // columns of this warp that exist (cout may end inside the tile), and their place in y
+        const int colw = nblk * BLOCK_N + cbase;
+        int valid_cols = p.cout - colw; valid_cols = valid_cols < 0 ? 0 : (valid_cols > CW ? CW : valid_cols);
+        int chw = colw, oh = p.out_oh, ow = p.out_ow;
+        if (p.cls_cols > 0) { const int cls = colw / p.cls_cols; chw = colw - cls * p.cls_cols; oh = cls >> 1; ow = cls & 1; }
+        __syncwarp();
+        const int piece = lane % PP;
+#pragma unroll
+        for (int i = 0; i < PP; ++i) {
+          const int n2 = tn * p.bn + s_dn[i], h2 = th * p.bh + s_dh[i], w2 = tw * p.bw + s_dw[i];
+          const bool ok = (s_dn[i] < p.bn) && n2 < p.mn && h2 < p.mh && w2 < p.mw && piece * 8 < valid_cols;
+          if (ok) {
+            const uint4 v = *reinterpret_cast<const uint4*>(slab + (i * RPI + lane / PP) * SM::EPI_PITCH + piece * 16);
+            const int64_t opix = ((int64_t)n2 * p.out_h + (h2 * p.out_sh + oh)) * p.out_w + (w2 * p.out_sw + ow);
+            *reinterpret_cast<uint4*>(p.y + opix * p.out_c + p.out_coff + chw + piece * 8) = v;
+          }
+        }
+        __syncwarp();
       }
     }
     if (STATS) {
@@ -1188,7 +1235,10 @@ static int igemm_launch_p2(const IgemmPlan& p, cudaStream_t s) {
   DBB_LAUNCH(label, s, igemm_persist_kernel<BLOCK_N, STAGES, STATS><<<(unsigned)grid, IGP_THREADS, SM::TOTAL, s>>>(p));
   return DBB_OK;
 }
-int igemm_launch(const IgemmPlan& p, cudaStream_t s) {
+int igemm_launch(const IgemmPlan& p_in, cudaStream_t s) {
+  IgemmPlan p = p_in;
+  static const bool no_staged = getenv("DBB_NO_STAGED_EPI") != nullptr;      // A/B switch
+  p.no_staged_epilogue = no_staged ? 1 : 0;
   if (p.cin % 64 != 0 || p.ntaps < 1 || p.ntaps > IGEMM_MAX_TAPS) return set_error(DBB_EUNSUPPORTED, "igemm: cin must be a multiple of 64, taps <= 16");
   // The k-loop of a tile has ntaps*cin/64 iterations; short loops (1x1 convolutions, ConvTranspose, conv1) get a
   // shallow ring so that more CTAs (= more epilogue warps) are resident per SM.

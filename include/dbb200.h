@@ -164,6 +164,13 @@ int dbb_clipper_offset(const int64_t* path_xy, int npts, double delta, double ar
 /* the raw offset path before the union step (tests) */
 int dbb_clipper_offset_raw(const int64_t* path_xy, int npts, double delta, double arc_tolerance, int64_t* out_xy, int cap_points);
 
+/* Loader -> device boundary (src/data_loaders.py:152-166, src/train.py:163-166): expands a batch shipped as uint8 image (N,3,H,W),
+ * uint8 {0,1} prob / supervision-mask / text-area maps (N,H,W) and the float32 threshold map into the float32 tensors the
+ * reference's loader produces: img_out (N,3,H,W) = uint8 - mean[c], gts_out (4,N,H,W).  H*W must be a multiple of 16. */
+int dbb_unpack_batch(const uint8_t* img_u8, float mean0, float mean1, float mean2, const uint8_t* prob_u8, const uint8_t* mask_u8,
+                     const float* thresh_f32, const uint8_t* area_u8, int64_t n, int64_t h, int64_t w, float* img_out,
+                     float* gts_out, void* stream);
+
 /* bitmap = pred[:, 0] > thresh on its own (src/postprocess.py:51-52) */
 int dbb_binarize(const float* pred, int64_t n, int c, int64_t h, int64_t w, float thresh, uint8_t* bitmap, void* stream);
 
