@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdbb200.so")
-SOURCES = ["api.cu", "db_loss.cu", "head_tail.cu", "ccl.cu", "elementwise.cu", "conv_tcgen05.cu", "conv_ops.cu", "conv_f32.cu", "net.cu", "ops_abi.cu", "gt_maps.cu", "post_geom.cu", "clipper_offset.cu", "data.cu"]
+SOURCES = ["api.cu", "db_loss.cu", "head_tail.cu", "ccl.cu", "elementwise.cu", "conv_tcgen05.cu", "conv_ops.cu", "conv_f32.cu", "net.cu", "ops_abi.cu", "gt_maps.cu", "post_geom.cu", "clipper_offset.cu", "data.cu", "poly_fill.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]

@@ -75,3 +75,85 @@ def draw_thresh_map(polygon, canvas, mask, shrink_ratio=0.4):
     cv2.fillPoly(mask, [padded.astype(np.int32)], 1.0)
     dev_canvas, _ = thresh_maps([[polygon]], canvas.shape[0], canvas.shape[1], shrink_ratio, padded=[[(padded, distance)]])
     np.fmax(canvas, dev_canvas[0].cpu().numpy(), out=canvas)
+
+
+def fill_polygons(maps, polygons, planes, values):
+    """cv2.fillPoly(maps[plane], [polygon.astype(int32)], value) for a list of polygons, on the device, bit-exact with OpenCV
+    (csrc/poly_fill.cu).  maps: (P, H, W) float32 CUDA tensor, filled in place."""
+    if not polygons:
+        return maps
+    _lib.require_cuda(maps)
+    assert maps.dtype == torch.float32 and maps.dim() == 3 and maps.is_contiguous()
+    verts = [np.asarray(p).astype(np.int32).reshape(-1, 2) for p in polygons]      # (poly.astype(np.int32): truncation)
+    if max(len(v) for v in verts) > 512:
+        raise _lib.DbbError("fill_polygons: more than 512 vertices in one polygon")
+    start = np.zeros(len(verts) + 1, np.int32)
+    start[1:] = np.cumsum([len(v) for v in verts])
+    dev = maps.device
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+    d_v, d_s, d_p, d_val = t(np.concatenate(verts), np.int32), t(start, np.int32), t(planes, np.int32), t(values, np.float32)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dbb_fill_polygons(d_v.data_ptr(), d_s.data_ptr(), d_p.data_ptr(), d_val.data_ptr(), len(verts),
+                                                maps.data_ptr(), maps.shape[1], maps.shape[2], _lib.stream_ptr()), "dbb_fill_polygons")
+    return maps
+
+
+def gt_maps(anns_per_image, image_size, shrink_ratio=0.4, thresh_min=0.3, thresh_max=0.7, min_text_size=8,
+            ignore_tags=("*", "###"), device="cuda"):
+    """The four ground-truth maps of a batch, src/data_loaders.py:86-149 (after augmentation / resize), built on the device:
+    shrink map `prob_map`, `supervision_mask`, border `thresh_map` (scaled to [thresh_min, thresh_max]) and `text_area_map`
+    (the reference's thresh_mask).  anns_per_image: per image a list of {'poly': (K, 2) array, 'text': str}.
+    Returns a dict of (N, S, S) float32 CUDA tensors plus 'ignore_tags' (per image list of bools, data_loaders.py:102-137).
+
+    Host side: per polygon the area / perimeter, the two Clipper offsets (C++, csrc/clipper_offset.cu -- unpinned) and the
+    ignore logic; device side: every cv2.fillPoly (csrc/poly_fill.cu, bit-exact with OpenCV) and the border distance field
+    (csrc/gt_maps.cu, bit-exact with the numpy arithmetic).  The reference's shapely validity tests
+    (`Polygon(...).buffer(0).is_valid`, data_loaders.py:85,128) are taken as true: shapely is not a dependency."""
+    from .postprocess import clipper_offset
+    n, S = len(anns_per_image), int(image_size)
+    dev = torch.device(device)
+    # planes: [0, N) prob_map, [N, 2N) supervision_mask, [2N, 3N) text_area_map
+    maps = torch.zeros((3 * n, S, S), dtype=torch.float32, device=dev)
+    maps[n:2 * n] = 1.0
+    fills, planes, values, thresh_polys, padded, ignore = [], [], [], [[] for _ in range(n)], [[] for _ in range(n)], [[] for _ in range(n)]
+    for i, anns in enumerate(anns_per_image):
+        for ann in anns:
+            poly = np.array(ann["poly"])
+            height = max(poly[:, 1]) - min(poly[:, 1])
+            width = max(poly[:, 0]) - min(poly[:, 0])
+            p = poly.astype(np.float64)
+            q = np.concatenate([p[1:], p[:1]])
+            area = 0.5 * abs(float((p[:, 0] * q[:, 1] - p[:, 1] * q[:, 0]).sum()))
+            length = float(np.sqrt(((p - q) ** 2).sum(1)).sum())
+
+            def ignore_it():
+                ignore[i].append(True)
+                fills.append(poly); planes.append(n + i); values.append(0.0)
+
+            if area < 1 or min(height, width) < min_text_size or ann.get("text") in ignore_tags:
+                ignore_it()
+                continue
+            distance = area * (1 - np.power(shrink_ratio, 2)) / length
+            shrinked = clipper_offset(poly, -distance)
+            if len(shrinked) == 0:
+                ignore_it()
+                continue
+            sh = np.array(shrinked[0]).reshape(-1, 2)
+            if sh.shape[0] > 2:
+                ignore[i].append(False)
+                fills.append(sh); planes.append(i); values.append(1.0)
+            else:
+                ignore_it()
+                continue
+            # draw_thresh_map (src/db_transforms.py:8-59): dilated polygon -> text-area fill + border distance field
+            pp, d = dilate_polygon(poly, shrink_ratio)
+            if pp is None:
+                continue
+            fills.append(pp); planes.append(2 * n + i); values.append(1.0)
+            thresh_polys[i].append(poly)
+            padded[i].append((pp, d))
+    fill_polygons(maps, fills, planes, values)
+    canvas, _ = thresh_maps(thresh_polys, S, S, shrink_ratio, device=dev, padded=padded)
+    thresh = canvas * (thresh_max - thresh_min) + thresh_min
+    return {"prob_map": maps[:n], "supervision_mask": maps[n:2 * n], "thresh_map": thresh, "text_area_map": maps[2 * n:],
+            "ignore_tags": ignore}

@@ -171,6 +171,12 @@ int dbb_unpack_batch(const uint8_t* img_u8, float mean0, float mean1, float mean
                      const float* thresh_f32, const uint8_t* area_u8, int64_t n, int64_t h, int64_t w, float* img_out,
                      float* gts_out, void* stream);
 
+/* cv2.fillPoly on the device for the ground-truth canvases of a batch (shrink map, supervision mask, text-area map:
+ * src/data_loaders.py:107,125,131,135, src/db_transforms.py:22), bit-exact with OpenCV for integer polygons.  verts (total, 2)
+ * int32, start (npolys + 1), plane (npolys) = canvas index into maps (planes, H, W) float32, value (npolys): all device. */
+int dbb_fill_polygons(const int32_t* verts, const int32_t* start, const int32_t* plane, const float* value, int npolys,
+                      float* maps, int64_t h, int64_t w, void* stream);
+
 /* bitmap = pred[:, 0] > thresh on its own (src/postprocess.py:51-52) */
 int dbb_binarize(const float* pred, int64_t n, int c, int64_t h, int64_t w, float thresh, uint8_t* bitmap, void* stream);
 

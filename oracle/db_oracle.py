@@ -671,3 +671,48 @@ def thresh_map_accumulate(canvas: np.ndarray, polygon, padded_bbox, distance: fl
     canvas[y0:y1 + 1, x0:x1 + 1] = np.fmax(1 - dm[y0 - ymin:y1 - ymax + height, x0 - xmin:x1 - xmax + width],
                                            canvas[y0:y1 + 1, x0:x1 + 1])
     return canvas
+
+
+def gt_maps_reference(anns, image_size, offset_fn, shrink_ratio=0.4, thresh_min=0.3, thresh_max=0.7, min_text_size=8,
+                      ignore_tags=("*", "###")):
+    """src/data_loaders.py:86-149 for ONE image with OpenCV / numpy exactly as the reference runs them; the two third-party
+    geometry calls are parameters: `offset_fn(poly, delta)` stands for pyclipper's Execute (list of int arrays), shapely's
+    Polygon area / length are the shoelace / perimeter formulas and its validity tests are taken as true.
+    Returns (gt, mask, thresh_map, thresh_mask, ignore_tags)."""
+    import cv2
+    S = image_size
+    gt = np.zeros((S, S), np.float32)
+    mask = np.ones((S, S), np.float32)
+    thresh_map = np.zeros((S, S), np.float32)
+    thresh_mask = np.zeros((S, S), np.float32)
+    tags = []
+    for ann in anns:
+        poly = np.array(ann["poly"])
+        height = max(poly[:, 1]) - min(poly[:, 1])
+        width = max(poly[:, 0]) - min(poly[:, 0])
+        area, length = polygon_area_length(poly)
+        if area < 1 or min(height, width) < min_text_size or ann.get("text") in ignore_tags:
+            tags.append(True)
+            cv2.fillPoly(mask, poly.astype(np.int32)[np.newaxis, :, :], 0)
+            continue
+        distance = area * (1 - np.power(shrink_ratio, 2)) / length
+        shrinked = offset_fn(poly, -distance)
+        if len(shrinked) == 0:
+            tags.append(True)
+            cv2.fillPoly(mask, poly.astype(np.int32)[np.newaxis, :, :], 0)
+            continue
+        sh = np.array(shrinked[0]).reshape(-1, 2)
+        if sh.shape[0] > 2:
+            tags.append(False)
+            cv2.fillPoly(gt, [sh.astype(np.int32)], 1)
+        else:
+            tags.append(True)
+            cv2.fillPoly(mask, poly.astype(np.int32)[np.newaxis, :, :], 0)
+            continue
+        # draw_thresh_map, src/db_transforms.py:8-59
+        padded = np.array(offset_fn(poly, distance)[0])
+        cv2.fillPoly(thresh_mask, [padded.astype(np.int32)], 1.0)
+        bbox = (padded[:, 0].min(), padded[:, 1].min(), padded[:, 0].max(), padded[:, 1].max())
+        thresh_map_accumulate(thresh_map, poly.astype(np.float64), bbox, distance)
+    thresh_map = thresh_map * (thresh_max - thresh_min) + thresh_min
+    return gt, mask, thresh_map, thresh_mask, tags
