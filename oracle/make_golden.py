@@ -374,6 +374,37 @@ def make_thresh_map_cases():
     print("thresh map cases", names, float(canvas.max()), int((canvas > 0).sum()))
 
 
+def make_metric_cases():
+    """f-3: the reference's own cal_text_score / RunningScore (src/text_metrics.py:9-82), imported unmodified (its two
+    unrelated imports -- iou (shapely) and utils (matplotlib) -- are stubbed), on seeded maps."""
+    import types
+    ref_import.load()
+    for name, attr in (("iou", "DetectionIoUEvaluator"), ("utils", "to_list_tuples_coords")):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            setattr(m, attr, object)
+            sys.modules[name] = m
+    import text_metrics as TM
+    out = {}
+    for ci, (n, h, w, seed) in enumerate([(2, 64, 64, 1), (3, 37, 53, 2), (4, 160, 160, 3)]):
+        rng = np.random.RandomState(seed)
+        P = rng.uniform(0, 1, (n, h, w)).astype(np.float32)
+        P[0, :4, :4] = 0.25                       # exactly on the threshold ('<=' -> 0)
+        gts = O.synth_gt_maps(n, h, w, seed)
+        rs = TM.RunningScore(2)
+        s1 = TM.cal_text_score(torch.from_numpy(P), torch.from_numpy(gts[0]), torch.from_numpy(gts[1]), rs, thresh=0.25)
+        h1 = rs.confusion_matrix.copy()
+        s2 = TM.cal_text_score(torch.from_numpy(P * 0.5), torch.from_numpy(gts[0]), torch.from_numpy(gts[1]), rs, thresh=0.25)
+        out[f"c{ci}:meta"] = np.array([n, h, w, seed])
+        out[f"c{ci}:hist1"] = h1
+        out[f"c{ci}:hist2"] = rs.confusion_matrix.copy()
+        keys = ["Overall Acc", "Mean Acc", "FreqW Acc", "Mean IoU"]
+        out[f"c{ci}:score1"] = np.array([s1[k] for k in keys])
+        out[f"c{ci}:score2"] = np.array([s2[k] for k in keys])
+    np.savez_compressed(os.path.join(GOLD, "metric_cases.npz"), **out)
+    print("metric cases", out["c0:hist1"].tolist(), out["c0:score1"].tolist())
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
@@ -385,3 +416,4 @@ if __name__ == "__main__":
     make_model_case("model_s2_54x70", 2, 1, 54, 70)
     make_cond_params()
     make_baseline_size_cases()
+    make_metric_cases()

@@ -41,3 +41,27 @@ def test_confusion_matrix_is_exact(shape):
     assert score['Overall Acc'] == acc and score['Mean IoU'] == np.nanmean(iu)
     cal_text_score(p[:, 0], g[0], g[1], rs, thresh=0.25)               # accumulates like RunningScore.update
     assert np.array_equal(rs.confusion_matrix, 2 * want)
+
+
+def test_matches_the_reference_function_golden():
+    """tests/golden/metric_cases.npz comes from the UNMODIFIED src/text_metrics.py (cal_text_score + RunningScore), two
+    accumulating calls per case: confusion matrices bit-exact, the four scores equal to the last bit of float64."""
+    import os
+    from db_text_minimal_b200.text_metrics import RunningScore, cal_text_score
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "metric_cases.npz"))
+    keys = ["Overall Acc", "Mean Acc", "FreqW Acc", "Mean IoU"]
+    for ci in range(3):
+        n, h, w, seed = [int(v) for v in z[f"c{ci}:meta"]]
+        rng = np.random.RandomState(seed)
+        P = rng.uniform(0, 1, (n, h, w)).astype(np.float32)
+        P[0, :4, :4] = 0.25
+        gts = O.synth_gt_maps(n, h, w, seed)
+        assert np.array_equal(ref_hist(P, gts[0], gts[1], 0.25), z[f"c{ci}:hist1"])      # the numpy restatement used above is pinned too
+        rs = RunningScore(2)
+        g = torch.from_numpy(gts).cuda()
+        s1 = cal_text_score(torch.from_numpy(P).cuda(), g[0], g[1], rs, thresh=0.25)
+        assert np.array_equal(rs.confusion_matrix, z[f"c{ci}:hist1"])
+        assert [s1[k] for k in keys] == z[f"c{ci}:score1"].tolist()
+        s2 = cal_text_score(torch.from_numpy(P * 0.5).cuda(), g[0], g[1], rs, thresh=0.25)
+        assert np.array_equal(rs.confusion_matrix, z[f"c{ci}:hist2"])
+        assert [s2[k] for k in keys] == z[f"c{ci}:score2"].tolist()
