@@ -64,6 +64,9 @@ def lib():
     sig("dbb_ccl_border_points", i32, [vp, sz, i64, i64, i64, vp, vp, i32, vp])
     sig("dbb_boxes_from_border_points", i32, [vp, vp, vp, vp, i64, i32, i32, i64, i64, vp, f32, i32, vp, vp, vp, vp, i32])
     sig("dbb_mini_box", i32, [vp, i32, vp, vp])
+    sig("dbb_polygons_from_bitmap", i32, [vp, vp, vp, i64, i32, i64, i64, vp, f32, i32, vp, vp, i32, vp, vp, i32])
+    sig("dbb_trace_contour", i32, [vp, i64, i64, i32, i32, i32, vp, i32])
+    sig("dbb_approx_poly_dp", i32, [vp, i32, f64, vp, i32, vp])
     sig("dbb_fill_polygons", i32, [vp, vp, vp, vp, i32, vp, i64, i64, vp])
     sig("dbb_unpack_batch", i32, [vp, f32, f32, f32, vp, vp, vp, vp, i64, i64, i64, vp, vp, vp])
     sig("dbb_clipper_offset", i32, [vp, i32, f64, f64, vp, i32, vp, i32])

@@ -28,14 +28,16 @@
 namespace dbb {
 
 typedef long long i64;
-struct LPt { i64 x, y; };
+struct LPt64 { long long x, y; };
+typedef LPt64 LPt;
 static inline bool operator==(const LPt& a, const LPt& b) { return a.x == b.x && a.y == b.y; }
 static inline bool operator!=(const LPt& a, const LPt& b) { return !(a == b); }
 static inline bool operator<(const LPt& a, const LPt& b) { return a.x < b.x || (a.x == b.x && a.y < b.y); }
 typedef std::vector<LPt> LPath;
 
 static inline i64 c_round(double v) { return v < 0 ? (i64)(v - 0.5) : (i64)(v + 0.5); }
-static inline __int128 crossv(i64 ax, i64 ay, i64 bx, i64 by) { return (__int128)ax * by - (__int128)ay * bx; }
+// coordinates are pixel positions (|v| < 2^30, checked on entry: Clipper's own "loRange"), so 64-bit products are exact
+static inline i64 crossv(i64 ax, i64 ay, i64 bx, i64 by) { return ax * by - ay * bx; }
 
 // Clipper's Area(): positive for counter-clockwise paths in a y-up frame
 static double clipper_area(const LPath& p) {
@@ -125,39 +127,55 @@ inline bool angle_less(i64 ax, i64 ay, i64 bx, i64 by) {
   return crossv(ax, ay, bx, by) > 0;
 }
 
+// Intersection points are snapped to a grid SUB times finer than the integer pixel grid of the input: snapping to the pixel grid
+// itself (what Clipper's IntersectPoint does) moves a sub-edge by up to half a pixel, which for the 1-2 pixel arc pieces of a
+// small offset creates crossings that were not there -- the arrangement stops being planar and faces / winding numbers go
+// wrong (observed on 119 of 876 approxPolyDP polygons at delta ~ 4 px).  Result vertices are rounded back to pixels at the end.
+constexpr i64 SUB = 1024;
 void positive_region(const LPath& path, std::vector<LPath>& result) {
   result.clear();
   // ---- segments (zero-length dropped)
   LPath P;
-  for (const LPt& p : path) if (P.empty() || P.back() != p) P.push_back(p);
+  for (const LPt& p0 : path) { const LPt p{p0.x * SUB, p0.y * SUB}; if (P.empty() || P.back() != p) P.push_back(p); }
   while (P.size() > 1 && P.front() == P.back()) P.pop_back();
   const int n = (int)P.size();
   if (n < 3) return;
   // ---- split points per segment
-  std::vector<std::vector<LPt>> cuts(n);
+  struct Cut { int seg; LPt p; };
+  std::vector<Cut> cuts;
+  cuts.reserve(64);
   auto seg_a = [&](int i) -> const LPt& { return P[i]; };
   auto seg_b = [&](int i) -> const LPt& { return P[(i + 1) % n]; };
   auto strictly_inside = [](const LPt& a, const LPt& b, const LPt& q) {      // q on segment ab (collinear assumed), not an end point
     if (q == a || q == b) return false;
     return std::min(a.x, b.x) <= q.x && q.x <= std::max(a.x, b.x) && std::min(a.y, b.y) <= q.y && q.y <= std::max(a.y, b.y);
   };
-  for (int i = 0; i < n; ++i) {
-    const LPt &a = seg_a(i), &b = seg_b(i);
-    const i64 d1x = b.x - a.x, d1y = b.y - a.y;
-    for (int j = i + 1; j < n; ++j) {
+  // sweep and prune on x: segments sorted by their smaller x; a pair is tested only while the x ranges overlap (the raw
+  // offset path consists of short arc pieces, so this is near-linear instead of the n^2 / 2 pair tests of the naive loop)
+  std::vector<int> order(n);
+  for (int i = 0; i < n; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int p, int q) { return std::min(seg_a(p).x, seg_b(p).x) < std::min(seg_a(q).x, seg_b(q).x); });
+  for (int oi = 0; oi < n; ++oi) {
+    const int i0 = order[oi];
+    const i64 maxx_i = std::max(seg_a(i0).x, seg_b(i0).x);
+    for (int oj = oi + 1; oj < n; ++oj) {
+      const int j0 = order[oj];
+      if (std::min(seg_a(j0).x, seg_b(j0).x) > maxx_i) break;
+      const int i = i0 < j0 ? i0 : j0, j = i0 < j0 ? j0 : i0;
+      const LPt &a = seg_a(i), &b = seg_b(i);
+      const i64 d1x = b.x - a.x, d1y = b.y - a.y;
       const LPt &c = seg_a(j), &d = seg_b(j);
-      if (std::max(a.x, b.x) < std::min(c.x, d.x) || std::max(c.x, d.x) < std::min(a.x, b.x) ||
-          std::max(a.y, b.y) < std::min(c.y, d.y) || std::max(c.y, d.y) < std::min(a.y, b.y)) continue;
+      if (std::max(a.y, b.y) < std::min(c.y, d.y) || std::max(c.y, d.y) < std::min(a.y, b.y)) continue;
       const i64 d2x = d.x - c.x, d2y = d.y - c.y;
-      const __int128 den = crossv(d1x, d1y, d2x, d2y);
-      const __int128 tn = crossv(c.x - a.x, c.y - a.y, d2x, d2y);      // t = tn / den along ab
-      const __int128 un = crossv(c.x - a.x, c.y - a.y, d1x, d1y);      // u = un / den along cd
+      const i64 den = crossv(d1x, d1y, d2x, d2y);
+      const i64 tn = crossv(c.x - a.x, c.y - a.y, d2x, d2y);      // t = tn / den along ab
+      const i64 un = crossv(c.x - a.x, c.y - a.y, d1x, d1y);      // u = un / den along cd
       if (den == 0) {
         if (un != 0) continue;                                            // parallel, not collinear
-        if (strictly_inside(a, b, c)) cuts[i].push_back(c);
-        if (strictly_inside(a, b, d)) cuts[i].push_back(d);
-        if (strictly_inside(c, d, a)) cuts[j].push_back(a);
-        if (strictly_inside(c, d, b)) cuts[j].push_back(b);
+        if (strictly_inside(a, b, c)) cuts.push_back(Cut{i, c});
+        if (strictly_inside(a, b, d)) cuts.push_back(Cut{i, d});
+        if (strictly_inside(c, d, a)) cuts.push_back(Cut{j, a});
+        if (strictly_inside(c, d, b)) cuts.push_back(Cut{j, b});
         continue;
       }
       const bool pos = den > 0;
@@ -171,53 +189,78 @@ void positive_region(const LPath& path, std::vector<LPath>& result) {
         ip.x = c_round((double)a.x + t * (double)d1x);
         ip.y = c_round((double)a.y + t * (double)d1y);
       }
-      if (ip != a && ip != b) cuts[i].push_back(ip);
-      if (ip != c && ip != d) cuts[j].push_back(ip);
+      if (ip != a && ip != b) cuts.push_back(Cut{i, ip});
+      if (ip != c && ip != d) cuts.push_back(Cut{j, ip});
     }
   }
-  // ---- sub-edges between integer vertices, net weight per undirected pair
-  std::map<LPt, int> vid;
-  std::vector<LPt> V;
-  auto vertex = [&](const LPt& p) { auto it = vid.find(p); if (it != vid.end()) return it->second; vid[p] = (int)V.size(); V.push_back(p); return (int)V.size() - 1; };
-  std::map<std::pair<int, int>, int> net;      // (min id, max id) -> forward count in the min -> max direction
-  for (int i = 0; i < n; ++i) {
-    const LPt a = seg_a(i), b = seg_b(i);
-    std::vector<LPt>& c = cuts[i];
+  // ---- sub-edges between integer vertices, net weight per undirected pair (flat sorted arrays: no node allocations)
+  std::sort(cuts.begin(), cuts.end(), [&](const Cut& p, const Cut& q) {
+    if (p.seg != q.seg) return p.seg < q.seg;
+    const LPt& a = seg_a(p.seg); const LPt& b = seg_b(p.seg);
     const i64 dx = b.x - a.x, dy = b.y - a.y;
-    std::sort(c.begin(), c.end(), [&](const LPt& p, const LPt& q) {
-      return (__int128)(p.x - a.x) * dx + (__int128)(p.y - a.y) * dy < (__int128)(q.x - a.x) * dx + (__int128)(q.y - a.y) * dy; });
-    LPt prev = a;
-    auto emit = [&](const LPt& q) {
-      if (q == prev) return;
-      const int u = vertex(prev), v = vertex(q);
-      if (u < v) net[{u, v}] += 1; else net[{v, u}] -= 1;
-      prev = q;
-    };
-    for (const LPt& q : c) emit(q);
-    emit(b);
+    return (p.p.x - a.x) * dx + (p.p.y - a.y) * dy < (q.p.x - a.x) * dx + (q.p.y - a.y) * dy; });
+  struct Sub { LPt a, b; };
+  std::vector<Sub> subs;
+  subs.reserve(n + cuts.size());
+  {
+    size_t ci = 0;
+    for (int i = 0; i < n; ++i) {
+      LPt prev = seg_a(i);
+      const LPt b = seg_b(i);
+      for (; ci < cuts.size() && cuts[ci].seg == i; ++ci) {
+        if (cuts[ci].p != prev) { subs.push_back(Sub{prev, cuts[ci].p}); prev = cuts[ci].p; }
+      }
+      if (b != prev) subs.push_back(Sub{prev, b});
+    }
   }
+  std::vector<LPt> V;
+  V.reserve(2 * subs.size());
+  for (const Sub& e : subs) { V.push_back(e.a); V.push_back(e.b); }
+  std::sort(V.begin(), V.end());
+  V.erase(std::unique(V.begin(), V.end()), V.end());
+  auto vertex = [&](const LPt& p) { return (int)(std::lower_bound(V.begin(), V.end(), p) - V.begin()); };
+  struct Net { int u, v, w; };
+  std::vector<Net> net;
+  net.reserve(subs.size());
+  for (const Sub& e : subs) {
+    const int u = vertex(e.a), v = vertex(e.b);
+    if (u < v) net.push_back(Net{u, v, 1}); else net.push_back(Net{v, u, -1});
+  }
+  std::sort(net.begin(), net.end(), [](const Net& p, const Net& q) { return p.u < q.u || (p.u == q.u && p.v < q.v); });
   // ---- half-edges, sorted around every vertex
   std::vector<HalfEdge> H;
-  for (const auto& kv : net) {
-    const int u = kv.first.first, v = kv.first.second, w = kv.second;
+  H.reserve(2 * net.size());
+  for (size_t e = 0; e < net.size();) {
+    size_t f = e;
+    int w = 0;
+    while (f < net.size() && net[f].u == net[e].u && net[f].v == net[e].v) { w += net[f].w; ++f; }
     const int h = (int)H.size();
-    H.push_back(HalfEdge{u, v, h + 1, w, -1, false});
-    H.push_back(HalfEdge{v, u, h, -w, -1, false});
+    H.push_back(HalfEdge{net[e].u, net[e].v, h + 1, w, -1, false});
+    H.push_back(HalfEdge{net[e].v, net[e].u, h, -w, -1, false});
+    e = f;
   }
   const int nv = (int)V.size();
-  std::vector<std::vector<int>> out_of(nv);
-  for (int h = 0; h < (int)H.size(); ++h) out_of[H[h].from].push_back(h);
-  std::vector<int> pos_in(H.size());
-  for (int v = 0; v < nv; ++v) {
-    std::sort(out_of[v].begin(), out_of[v].end(), [&](int h1, int h2) {
-      return angle_less(V[H[h1].to].x - V[v].x, V[H[h1].to].y - V[v].y, V[H[h2].to].x - V[v].x, V[H[h2].to].y - V[v].y); });
-    for (int q = 0; q < (int)out_of[v].size(); ++q) pos_in[out_of[v][q]] = q;
+  // CSR adjacency: out_of[v] = ostart[v] .. ostart[v + 1]
+  std::vector<int> ostart(nv + 1, 0), oidx(H.size()), pos_in(H.size());
+  for (const HalfEdge& he : H) ++ostart[he.from + 1];
+  for (int v = 0; v < nv; ++v) ostart[v + 1] += ostart[v];
+  {
+    std::vector<int> fillp(ostart.begin(), ostart.end() - 1);
+    for (int h = 0; h < (int)H.size(); ++h) oidx[fillp[H[h].from]++] = h;
   }
+  for (int v = 0; v < nv; ++v) {
+    std::sort(oidx.begin() + ostart[v], oidx.begin() + ostart[v + 1], [&](int h1, int h2) {
+      return angle_less(V[H[h1].to].x - V[v].x, V[H[h1].to].y - V[v].y, V[H[h2].to].x - V[v].x, V[H[h2].to].y - V[v].y); });
+    for (int q = ostart[v]; q < ostart[v + 1]; ++q) pos_in[oidx[q]] = q - ostart[v];
+  }
+  struct OutView { const int* p; int m; int operator[](int i) const { return p[i]; } int size() const { return m; } };
+  auto out_of_v = [&](int v) { return OutView{oidx.data() + ostart[v], ostart[v + 1] - ostart[v]}; };
   // next half-edge along the face to the LEFT of h: at h.to, the outgoing edge just clockwise of twin(h)
   auto next_of = [&](int h) {
     const int t = H[h].twin, v = H[t].from;
-    const int q = pos_in[t], m = (int)out_of[v].size();
-    return out_of[v][(q - 1 + m) % m];
+    const OutView ov = out_of_v(v);
+    const int q = pos_in[t], m = ov.size();
+    return ov[(q - 1 + m) % m];
   };
   // ---- faces
   int nfaces = 0;
@@ -242,18 +285,12 @@ void positive_region(const LPath& path, std::vector<LPath>& result) {
   // ---- winding numbers by propagation across edges: W(left of h) = W(right of h) + weight(h)
   std::vector<int> W(nfaces, 0);
   std::vector<char> seen(nfaces, 0);
-  std::vector<std::vector<int>> edges_of(nfaces);
-  for (int h = 0; h < (int)H.size(); ++h) edges_of[H[h].face].push_back(h);
-  std::vector<int> stack{outer};
+  // (faces are few and the graph is small: relax over all half-edges until every face is labelled)
   seen[outer] = 1;
-  while (!stack.empty()) {
-    const int f = stack.back(); stack.pop_back();
-    for (int h : edges_of[f]) {              // h has f on its left; twin(h) has the neighbour on its left
-      const int g = H[H[h].twin].face;
-      if (seen[g]) continue;
-      W[g] = W[f] - H[h].weight;             // W(f) = W(g) + weight(h)
-      seen[g] = 1;
-      stack.push_back(g);
+  for (int left = nfaces - 1, guard = 0; left > 0 && guard <= nfaces; ++guard) {
+    for (int h = 0; h < (int)H.size(); ++h) {
+      const int f = H[h].face, g = H[H[h].twin].face;      // h has f on its left; twin(h) has g on its left
+      if (seen[f] && !seen[g]) { W[g] = W[f] - H[h].weight; seen[g] = 1; --left; }      // W(f) = W(g) + weight(h)
     }
   }
   // ---- boundary half-edges: winding > 0 on the left, <= 0 on the right
@@ -266,16 +303,28 @@ void positive_region(const LPath& path, std::vector<LPath>& result) {
       H[h].used = true;
       loop.push_back(V[H[h].from]);
       // continue with the first selected outgoing edge clockwise of twin(h) (keeps the region on the left, splits at touching points)
-      const int t = H[h].twin, v = H[t].from, m = (int)out_of[v].size();
+      const int t = H[h].twin, v = H[t].from;
+      const OutView ov = out_of_v(v);
+      const int m = ov.size();
       int q = pos_in[t], nxt = -1;
       for (int s = 1; s <= m; ++s) {
-        const int cand = out_of[v][((q - s) % m + m) % m];
+        const int cand = ov[((q - s) % m + m) % m];
         if (selected(cand) && !H[cand].used) { nxt = cand; break; }
         if (cand == h0) { nxt = h0; break; }
       }
       if (nxt < 0) break;
       h = nxt;
     } while (h != h0);
+    // back to the pixel grid (Clipper's Round()), duplicates out
+    {
+      LPath px;
+      for (const LPt& q : loop) {
+        const LPt r{c_round((double)q.x / (double)SUB), c_round((double)q.y / (double)SUB)};
+        if (px.empty() || px.back() != r) px.push_back(r);
+      }
+      while (px.size() > 1 && px.front() == px.back()) px.pop_back();
+      loop.swap(px);
+    }
     // cleanup: collinear vertices out (Clipper's FixupOutPolygon without PreserveCollinear)
     bool changed = true;
     while (changed && loop.size() >= 3) {
@@ -296,6 +345,8 @@ void positive_region(const LPath& path, std::vector<LPath>& result) {
 void clipper_offset_round(const LPath& in, double delta, double arc_tolerance, std::vector<LPath>& out) {
   LPath raw;
   out.clear();
+  for (const LPt& p : in) if (p.x > (1ll << 18) || p.x < -(1ll << 18) || p.y > (1ll << 18) || p.y < -(1ll << 18)) return;   // outside the exact int64 range of the x 1024 sub-grid
+  if (!(std::fabs(delta) < (double)(1ll << 18))) return;
   if (!raw_offset(in, delta, arc_tolerance, raw)) return;
   positive_region(raw, out);
 }

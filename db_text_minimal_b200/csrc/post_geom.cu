@@ -403,3 +403,266 @@ extern "C" int dbb_mini_box(const int32_t* contour_xy, int npts, float* box8, fl
   for (int i = 0; i < 4; ++i) { box8[2 * i] = b[i].x; box8[2 * i + 1] = b[i].y; }
   return DBB_OK;
 }
+
+// =================================================================================================================
+// Polygon mode (src/postprocess.py:54-104): the ordered contour of a kept candidate, cv2.arcLength, cv2.approxPolyDP
+// =================================================================================================================
+namespace dbb {
+
+// packed bitmap accessor: 1 bit per pixel, 32 pixels per word, zero outside the image
+struct BitImage {
+  const uint32_t* bits; int h, w, wq;
+  inline int at(int y, int x) const {
+    if ((unsigned)y >= (unsigned)h || (unsigned)x >= (unsigned)w) return 0;
+    return (bits[(size_t)y * wq + (x >> 5)] >> (x & 31)) & 1u;
+  }
+};
+
+// Border following of ONE border, as OpenCV's icvFetchContour (Suzuki-Abe) with CHAIN_APPROX_SIMPLE: `start` is the border's
+// start pixel (the raster-first pixel of the component for an outer border; the foreground pixel left of the hole's
+// raster-first pixel for a hole border); a point is emitted whenever the chain direction changes.
+void trace_border(const BitImage& im, int sx, int sy, bool is_hole, std::vector<IPt>& out) {
+  static const int DX[8] = {1, 1, 0, -1, -1, -1, 0, 1}, DY[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+  out.clear();
+  int s_end = is_hole ? 0 : 4, s = s_end;
+  int i1x, i1y;
+  do {
+    s = (s - 1) & 7;
+    i1x = sx + DX[s]; i1y = sy + DY[s];
+  } while (im.at(i1y, i1x) == 0 && s != s_end);
+  if (s == s_end) { out.push_back(IPt{sx, sy}); return; }       // single-pixel domain
+  int i3x = sx, i3y = sy, i4x = sx, i4y = sy;
+  int prev_s = s ^ 4;
+  int px = sx, py = sy;
+  for (;;) {
+    s_end = s;
+    while (s < 15) {
+      ++s;
+      i4x = i3x + DX[s & 7]; i4y = i3y + DY[s & 7];
+      if (im.at(i4y, i4x) != 0) break;
+    }
+    s &= 7;
+    if (s != prev_s) { out.push_back(IPt{px, py}); prev_s = s; }
+    px += DX[s]; py += DY[s];
+    if (i4x == sx && i4y == sy && i3x == i1x && i3y == i1y) break;
+    i3x = i4x; i3y = i4y;
+    s = (s + 4) & 7;
+  }
+}
+
+// cv2.arcLength(contour, closed=True) for integer points: float differences, float squares, sqrt, double sum
+double arc_length_closed(const std::vector<IPt>& c) {
+  const int n = (int)c.size();
+  if (n <= 1) return 0.0;
+  double perimeter = 0;
+  float prevx = (float)c[n - 1].x, prevy = (float)c[n - 1].y;
+  for (int i = 0; i < n; ++i) {
+    const float x = (float)c[i].x, y = (float)c[i].y;
+    const float dx = x - prevx, dy = y - prevy;
+    perimeter += std::sqrt(dx * dx + dy * dy);
+    prevx = x; prevy = y;
+  }
+  return perimeter;
+}
+
+// cv2.approxPolyDP(contour, eps, closed=True) for integer points (imgproc/approx.cpp: approxPolyDP_<int>)
+void approx_poly_dp_closed(const std::vector<IPt>& src, double eps, std::vector<IPt>& dst) {
+  struct Range { int start, end; };
+  const int count0 = (int)src.size();
+  dst.clear();
+  if (count0 == 0) return;
+  int count = count0, new_count = 0, pos = 0, i, j;
+  std::vector<IPt> out(count0);
+  std::vector<Range> stack;
+  Range slice{0, 0}, right_slice{0, 0};
+  IPt start_pt{-1000000, -1000000}, end_pt{0, 0}, pt{0, 0};
+  bool le_eps = false;
+  auto read_pt = [&](IPt& p, int& ps) { p = src[ps]; if (++ps >= count) ps = 0; };
+  eps *= eps;
+  // 1. approximately the two farthest points of the contour
+  right_slice.start = 0;
+  for (i = 0; i < 3; ++i) {
+    double max_dist = 0;
+    pos = (pos + right_slice.start) % count;
+    read_pt(start_pt, pos);
+    for (j = 1; j < count; ++j) {
+      read_pt(pt, pos);
+      const double dx = pt.x - start_pt.x, dy = pt.y - start_pt.y;
+      const double dist = dx * dx + dy * dy;
+      if (dist > max_dist) { max_dist = dist; right_slice.start = j; }
+    }
+    le_eps = max_dist <= eps;
+  }
+  // 2. initialise the stack
+  if (!le_eps) {
+    right_slice.end = slice.start = pos % count;
+    slice.end = right_slice.start = (right_slice.start + slice.start) % count;
+    stack.push_back(right_slice);
+    stack.push_back(slice);
+  } else {
+    out[new_count++] = start_pt;
+  }
+  // 3. recursive subdivision
+  while (!stack.empty()) {
+    slice = stack.back(); stack.pop_back();
+    end_pt = src[slice.end];
+    pos = slice.start;
+    read_pt(start_pt, pos);
+    if (pos != slice.end) {
+      double max_dist = 0;
+      const double dx = end_pt.x - start_pt.x, dy = end_pt.y - start_pt.y;
+      while (pos != slice.end) {
+        read_pt(pt, pos);
+        const double dist = std::fabs((pt.y - start_pt.y) * dx - (pt.x - start_pt.x) * dy);
+        if (dist > max_dist) { max_dist = dist; right_slice.start = (pos + count - 1) % count; }
+      }
+      le_eps = max_dist * max_dist <= eps * (dx * dx + dy * dy);
+    } else {
+      le_eps = true;
+      start_pt = src[slice.start];
+    }
+    if (le_eps) {
+      out[new_count++] = start_pt;
+    } else {
+      right_slice.end = slice.end;
+      slice.end = right_slice.start;
+      stack.push_back(right_slice);
+      stack.push_back(slice);
+    }
+  }
+  // 4. clean-up: points on [almost] straight lines
+  count = new_count;
+  auto read_dst = [&](IPt& p, int& ps) { p = out[ps]; if (++ps >= count) ps = 0; };
+  pos = count - 1;
+  read_dst(start_pt, pos);
+  int wpos = pos;
+  read_dst(pt, pos);
+  for (i = 0; i < count && new_count > 2; ++i) {
+    read_dst(end_pt, pos);
+    const double dx = end_pt.x - start_pt.x, dy = end_pt.y - start_pt.y;
+    const double dist = std::fabs((pt.x - start_pt.x) * dy - (pt.y - start_pt.y) * dx);
+    const double sip = (double)(pt.x - start_pt.x) * (end_pt.x - pt.x) + (double)(pt.y - start_pt.y) * (end_pt.y - pt.y);
+    if (dist * dist <= 0.5 * eps * (dx * dx + dy * dy) && dx != 0 && dy != 0 && sip >= 0) {
+      --new_count;
+      out[wpos] = start_pt = end_pt;
+      if (++wpos >= count) wpos = 0;
+      read_dst(pt, pos);
+      ++i;
+      continue;
+    }
+    out[wpos] = start_pt = pt;
+    if (++wpos >= count) wpos = 0;
+    pt = end_pt;
+  }
+  dst.assign(out.begin(), out.begin() + new_count);
+}
+
+}  // namespace dbb
+
+// HOST test entries: one border of a byte bitmap / approxPolyDP of an integer contour
+extern "C" int dbb_trace_contour(const uint8_t* bitmap, int64_t h, int64_t w, int start_x, int start_y, int is_hole, int32_t* out_xy, int cap) {
+  if (!bitmap || !out_xy || h <= 0 || w <= 0) return dbb::set_error(DBB_EINVAL, "trace_contour: bad argument");
+  const int wq = (int)((w + 31) / 32);
+  std::vector<uint32_t> bits((size_t)h * wq, 0u);
+  for (int64_t y = 0; y < h; ++y)
+    for (int64_t x = 0; x < w; ++x)
+      if (bitmap[y * w + x]) bits[(size_t)y * wq + (x >> 5)] |= 1u << (x & 31);
+  dbb::BitImage im{bits.data(), (int)h, (int)w, wq};
+  std::vector<dbb::IPt> c;
+  dbb::trace_border(im, start_x, start_y, is_hole != 0, c);
+  if ((int)c.size() > cap) return dbb::set_error(DBB_EWORKSPACE, "trace_contour: output buffer too small");
+  for (size_t i = 0; i < c.size(); ++i) { out_xy[2 * i] = c[i].x; out_xy[2 * i + 1] = c[i].y; }
+  return (int)c.size();
+}
+extern "C" int dbb_approx_poly_dp(const int32_t* contour_xy, int npts, double eps_or_negative_ratio, int32_t* out_xy, int cap, double* arc_length) {
+  if (!contour_xy || npts < 0 || !out_xy) return dbb::set_error(DBB_EINVAL, "approx_poly_dp: bad argument");
+  std::vector<dbb::IPt> c(npts), d;
+  for (int i = 0; i < npts; ++i) c[i] = dbb::IPt{contour_xy[2 * i], contour_xy[2 * i + 1]};
+  const double len = dbb::arc_length_closed(c);
+  if (arc_length) *arc_length = len;
+  const double eps = eps_or_negative_ratio < 0 ? -eps_or_negative_ratio * len : eps_or_negative_ratio;   // negative: a ratio of the arc length
+  dbb::approx_poly_dp_closed(c, eps, d);
+  if ((int)d.size() > cap) return dbb::set_error(DBB_EWORKSPACE, "approx_poly_dp: output buffer too small");
+  for (size_t i = 0; i < d.size(); ++i) { out_xy[2 * i] = d[i].x; out_xy[2 * i + 1] = d[i].y; }
+  return (int)d.size();
+}
+
+// ---------------------------------------------------------------------------------------------- polygon mode, whole batch
+namespace dbb {
+struct LPt64 { long long x, y; };
+void clipper_offset_round(const std::vector<LPt64>& in, double delta, double arc_tolerance, std::vector<std::vector<LPt64>>& out);
+}
+
+// HOST function: src/postprocess.py:54-104 (polygons_from_bitmap) for every kept candidate of a batch.  bits: the packed bitmap
+// (N, H, ceil(W/32)) uint32 copied back from the device front's workspace; cands / n_cands as in dbb_boxes_from_border_points.
+// Outputs per image: counts (N, max_cands) int32 = number of points of candidate s's polygon (0 = dropped), points
+// (N, cap, 2) int32 = the polygons back to back in candidate order, scores (N, max_cands) float64, totals (N) int32 = points
+// the image produced (> cap: call again with a larger buffer).
+extern "C" int dbb_polygons_from_bitmap(const uint32_t* bits, const DbbCandidate* cands, const int32_t* n_cands, int64_t n, int max_cands,
+                                        int64_t h, int64_t w, const int32_t* dest_wh, float unclip_ratio, int min_size, int32_t* counts,
+                                        int32_t* points, int cap, double* scores, int32_t* totals, int threads) {
+  if (!bits || !cands || !n_cands || !dest_wh || !counts || !points || !scores || !totals || n <= 0 || max_cands <= 0 || cap <= 0)
+    return set_error(DBB_EINVAL, "polygons_from_bitmap: bad argument");
+  const int wq = (int)((w + 31) / 32);
+  auto work = [&](int64_t img) {
+    const int k = n_cands[img] < max_cands ? n_cands[img] : max_cands;
+    const DbbCandidate* C = cands + img * max_cands;
+    int32_t* cnt = counts + img * max_cands;
+    double* sc = scores + img * max_cands;
+    int32_t* P = points + img * (int64_t)cap * 2;
+    std::fill(cnt, cnt + max_cands, 0);
+    std::fill(sc, sc + max_cands, 0.0);
+    BitImage im{bits + (size_t)img * h * wq, (int)h, (int)w, wq};
+    std::vector<IPt> contour, approx, ring;
+    std::vector<LPt64> path;
+    std::vector<std::vector<LPt64>> res;
+    const double dw = (double)dest_wh[2 * img], dh = (double)dest_wh[2 * img + 1];
+    int total = 0;
+    for (int s = 0; s < k; ++s) {
+      if (!C[s].keep) continue;
+      trace_border(im, C[s].kind ? C[s].first_x - 1 : C[s].first_x, C[s].first_y, C[s].kind != 0, contour);
+      approx_poly_dp_closed(contour, 0.005 * arc_length_closed(contour), approx);
+      const int np_ = (int)approx.size();
+      if (np_ < 4) continue;
+      double area = 0, length = 0;
+      for (int i = 0; i < np_; ++i) {
+        const IPt& a = approx[i]; const IPt& b = approx[(i + 1) % np_];
+        area += (double)a.x * b.y - (double)a.y * b.x;
+        const double dx = (double)a.x - b.x, dy = (double)a.y - b.y;
+        length += std::sqrt(dx * dx + dy * dy);
+      }
+      area = std::fabs(area) * 0.5;
+      if (!(length > 0)) continue;
+      const double distance = area * (double)unclip_ratio / length;
+      path.resize(np_);
+      for (int i = 0; i < np_; ++i) path[i] = LPt64{approx[i].x, approx[i].y};
+      clipper_offset_round(path, distance, 0.25, res);
+      if (res.size() != 1) continue;                            // len(box) > 1 -> dropped (an empty result cannot be reshaped either)
+      ring.resize(res[0].size());
+      for (size_t i = 0; i < res[0].size(); ++i) ring[i] = IPt{(int)res[0][i].x, (int)res[0][i].y};
+      FPt bx[4];
+      std::vector<IPt> tmp(ring);
+      if (mini_box(tmp, bx) < (float)(min_size + 2)) continue;
+      const int m = (int)ring.size();
+      if (total + m <= cap) {
+        for (int i = 0; i < m; ++i) {
+          // box[:, 0] = np.clip(np.round(box[:, 0] / width * dest_width), 0, dest_width)   (float64, half to even, into an int array)
+          double fx = std::nearbyint((double)ring[i].x / (double)w * dw), fy = std::nearbyint((double)ring[i].y / (double)h * dh);
+          fx = fx < 0 ? 0 : (fx > dw ? dw : fx); fy = fy < 0 ? 0 : (fy > dh ? dh : fy);
+          P[2 * (total + i)] = (int32_t)fx; P[2 * (total + i) + 1] = (int32_t)fy;
+        }
+      }
+      total += m;
+      cnt[s] = m;
+      sc[s] = C[s].sum / (double)C[s].count;
+    }
+    totals[img] = total;
+  };
+  int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  if (nt > n) nt = (int)n;
+  if (nt <= 1) { for (int64_t i = 0; i < n; ++i) work(i); return DBB_OK; }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nt; ++t) pool.emplace_back([&, t]() { for (int64_t i = t; i < n; i += nt) work(i); });
+  for (auto& th : pool) th.join();
+  return DBB_OK;
+}

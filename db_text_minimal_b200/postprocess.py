@@ -9,8 +9,9 @@ reference copies (src/postprocess.py:61-62,113-114).
 Back half.  Box mode (src/postprocess.py:106-148): the device emits the border points of the kept candidates (run end
 pixels: their convex hull is the contour's), and C++ (csrc/post_geom.cu, csrc/clipper_offset.cu) does get_mini_boxes,
 unclip, the second get_mini_boxes and the rescale for the whole batch -- no bitmap crosses to the host, no Python per box.
-Polygon mode (src/postprocess.py:54-104) needs the ordered contour for cv2.approxPolyDP: contours of the survivors are
-traced by OpenCV on bitmap crops, the offset runs in C++.
+Polygon mode (src/postprocess.py:54-104) needs the ordered contour for cv2.approxPolyDP: the packed bitmap (1 bit / pixel)
+comes back from the device and C++ traces the border of every kept candidate as cv2.findContours(CHAIN_APPROX_SIMPLE) does
+(Suzuki-Abe border following), then cv2.arcLength / cv2.approxPolyDP restated, the offset, the filters and the rescale.
 ``unclip`` is Clipper (pyclipper 1.1.0.post3), which is neither in the reference tree nor in this image; it is restated in
 csrc/clipper_offset.cu for polygons of any shape.  That stage is unpinned (no pyclipper to generate goldens).
 """
@@ -180,6 +181,50 @@ class SegDetectorRepresenter():
             return boxes, scores, nc, sside, mini, cands
         return boxes, scores, nc
 
+    # ------------------------------------------------------------------ polygon mode, whole batch: device front + C++ back half
+    def polygons_batch(self, pred, dest_wh):
+        """src/postprocess.py:54-104 for a whole batch.  The device front supplies the candidates, their scores and the packed
+        bitmap (1 bit / pixel); C++ (dbb_polygons_from_bitmap) traces the border of every kept candidate exactly as
+        cv2.findContours(CHAIN_APPROX_SIMPLE) does, then cv2.arcLength / cv2.approxPolyDP (restated, bit-exact on the test
+        contours), unclip, the filters and the rescale.  Returns (list per image of (K_i, 2) int64 arrays, list per image of
+        float scores) in the reference's contour order."""
+        L = _lib.lib()
+        f = self._front_device(pred)
+        n, h, w, dev = f["n"], f["h"], f["w"], f["dev"]
+        wq = (w + 31) // 32
+        nc = f["ncand"].cpu().numpy()
+        k = int(min(max(int(nc.max(initial=0)), 1), self.max_candidates))
+        nb_c, nb_b = n * k * f["csize"], n * h * wq * 4
+        if getattr(self, "_stage", None) is None or self._stage.numel() < nb_c + nb_b:
+            self._stage = torch.empty(int(1.25 * (nb_c + nb_b)), dtype=torch.uint8, pin_memory=True)
+        stage = self._stage[:nb_c + nb_b]
+        stage[:nb_c].view(n, k, f["csize"]).copy_(f["cands"][:, :k], non_blocking=True)
+        stage[nb_c:].copy_(f["ws"][:nb_b], non_blocking=True)              # the packed bitmap sits at the start of the workspace
+        torch.cuda.current_stream(dev).synchronize()
+        host = stage.numpy()
+        cands, bits = host[:nb_c], host[nb_c:nb_c + nb_b]
+        dest = np.ascontiguousarray(np.asarray(dest_wh, dtype=np.int32).reshape(n, 2))
+        nc32 = np.ascontiguousarray(nc.astype(np.int32))
+        cap = 256 * max(16, min(k, 256))
+        while True:
+            counts = np.empty((n, k), np.int32)
+            pts = np.empty((n, cap, 2), np.int32)
+            scores = np.empty((n, k), np.float64)
+            totals = np.empty(n, np.int32)
+            _lib.check(L.dbb_polygons_from_bitmap(bits.ctypes.data, cands.ctypes.data, nc32.ctypes.data, n, k, h, w, dest.ctypes.data,
+                                                  float(self.unclip_ratio), int(self.min_size), counts.ctypes.data, pts.ctypes.data, cap,
+                                                  scores.ctypes.data, totals.ctypes.data, int(self.host_threads)), "dbb_polygons_from_bitmap")
+            if int(totals.max(initial=0)) <= cap:
+                break
+            cap = int(totals.max())
+        boxes_batch, scores_batch = [], []
+        for i in range(n):
+            kept = np.nonzero(counts[i])[0]
+            offs = np.concatenate([[0], np.cumsum(counts[i][kept])])
+            boxes_batch.append([pts[i, offs[j]:offs[j + 1]].astype(np.int64) for j in range(len(kept))])
+            scores_batch.append([float(v) for v in scores[i][kept]])
+        return boxes_batch, scores_batch
+
     def candidates(self, pred):
         """Per image: list of dicts (kind, score, count, bbox, first, keep) in the reference's contour order."""
         _, _, rec, nc = self.front(pred)
@@ -191,30 +236,7 @@ class SegDetectorRepresenter():
                              first=(int(r["first_y"]), int(r["first_x"])), keep=bool(r["keep"])) for r in rec[i, :k]])
         return out
 
-    # ------------------------------------------------------------------ host back half (survivors only)
-    @staticmethod
-    def _contour_of(bitmap_np, r):
-        """Border of one candidate, traced by OpenCV on the bitmap crop (same follower as the reference uses)."""
-        import cv2
-        h, w = bitmap_np.shape
-        x0, y0, x1, y1 = max(int(r["x0"]) - 1, 0), max(int(r["y0"]) - 1, 0), min(int(r["x1"]) + 1, w - 1), min(int(r["y1"]) + 1, h - 1)
-        crop = np.ascontiguousarray(bitmap_np[y0:y1 + 1, x0:x1 + 1])
-        fy, fx = int(r["first_y"]) - y0, int(r["first_x"]) - x0
-        mask = np.zeros((crop.shape[0] + 2, crop.shape[1] + 2), np.uint8)
-        if r["kind"] == 0:      # component containing the first pixel, 8-connected
-            cv2.floodFill(crop.copy(), mask, (fx, fy), 2, flags=8 | cv2.FLOODFILL_MASK_ONLY | (1 << 8))
-            comp = mask[1:-1, 1:-1]
-            cs, _ = cv2.findContours(comp * 255, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
-            c = cs[0]
-        else:                   # hole region containing the first pixel, 4-connected; its border lives on the parent
-            inv = (1 - crop).astype(np.uint8)
-            cv2.floodFill(inv.copy(), mask, (fx, fy), 2, flags=4 | cv2.FLOODFILL_MASK_ONLY | (1 << 8))
-            hole = mask[1:-1, 1:-1]
-            solid = (1 - hole).astype(np.uint8)          # everything but the hole is foreground -> one hole border
-            cs, hier = cv2.findContours(solid * 255, cv2.RETR_CCOMP, cv2.CHAIN_APPROX_SIMPLE)
-            c = next(cs[i] for i in range(len(cs)) if hier[0][i][3] >= 0)
-        return c + np.array([[[x0, y0]]], dtype=c.dtype)
-
+    # ------------------------------------------------------------------ the reference's helper methods (single contour / polygon)
     def unclip(self, box, unclip_ratio=1.5):
         """src/postprocess.py:150-156.  distance = area * ratio / perimeter (shapely Polygon.area / .length); returns the list
         of result polygons (the reference's np.array(offset.Execute(distance)); callers test len(...) > 1 and reshape)."""
@@ -253,37 +275,6 @@ class SegDetectorRepresenter():
         cv2.fillPoly(mask, box.reshape(1, -1, 2).astype(np.int32), 1)
         return cv2.mean(bitmap[ymin:ymax + 1, xmin:xmax + 1], mask)[0]
 
-    def _polygons(self, bitmap_np, rec, dest_width, dest_height):
-        """src/postprocess.py:70-103."""
-        import cv2
-        height, width = bitmap_np.shape
-        boxes, scores = [], []
-        for r in rec:
-            if not r["keep"]:
-                continue
-            contour = self._contour_of(bitmap_np, r)
-            epsilon = 0.005 * cv2.arcLength(contour, True)
-            approx = cv2.approxPolyDP(contour, epsilon, True)
-            points = approx.reshape((-1, 2))
-            if points.shape[0] < 4:
-                continue
-            score = float(r["sum"]) / int(r["count"])
-            box = self.unclip(points, unclip_ratio=self.unclip_ratio)
-            if len(box) != 1:          # the reference drops len(box) > 1; an empty result cannot be reshaped there either
-                continue
-            box = np.asarray(box[0]).reshape(-1, 2)
-            _, sside = self.get_mini_boxes(box.reshape((-1, 1, 2)).astype(np.int32))
-            if sside < self.min_size + 2:
-                continue
-            if not isinstance(dest_width, int):
-                dest_width, dest_height = dest_width.item(), dest_height.item()
-            box = box.astype(np.float64)
-            box[:, 0] = np.clip(np.round(box[:, 0] / width * dest_width), 0, dest_width)
-            box[:, 1] = np.clip(np.round(box[:, 1] / height * dest_height), 0, dest_height)
-            boxes.append(box)
-            scores.append(score)
-        return boxes, scores
-
     def __call__(self, batch, pred, is_output_polygon=False):
         """src/postprocess.py:19-49: returns (boxes_batch, scores_batch)."""
         if not is_output_polygon:        # box mode: nothing but candidate records and border points leaves the device
@@ -292,23 +283,9 @@ class SegDetectorRepresenter():
             boxes, scores, nc = self.boxes_batch(pred, dest)
             ks = [int(min(nc[i], self.max_candidates)) for i in range(n)]
             return [boxes[i, :ks[i]] for i in range(n)], [scores[i, :ks[i]] for i in range(n)]
-        bitmap, _, rec, nc = self.front(pred)
-        bm = bitmap.cpu().numpy()
-        fn = self._polygons
-
-        def one(i):
-            height, width = batch['shape'][i]
-            k = int(min(nc[i], self.max_candidates))
-            return fn(bm[i], rec[i, :k], width, height)
-
-        n = bm.shape[0]
-        if n > 1 and self.host_threads > 1:      # images are independent; the OpenCV calls release the GIL
-            from concurrent.futures import ThreadPoolExecutor
-            with ThreadPoolExecutor(max_workers=min(self.host_threads, n)) as pool:
-                results = list(pool.map(one, range(n)))
-        else:
-            results = [one(i) for i in range(n)]
-        return [r[0] for r in results], [r[1] for r in results]
+        n = pred.shape[0]
+        dest = [(int(batch['shape'][i][1]), int(batch['shape'][i][0])) for i in range(n)]
+        return self.polygons_batch(pred, dest)
 
     def boxes_from_bitmap(self, pred, _bitmap, dest_width, dest_height):
         """src/postprocess.py:106-148 for one (H, W) map; ``_bitmap`` is recomputed on the device from ``pred``."""
@@ -321,5 +298,7 @@ class SegDetectorRepresenter():
 
     def polygons_from_bitmap(self, pred, _bitmap, dest_width, dest_height):
         assert len(_bitmap.shape) == 2
-        bitmap, _, rec, nc = self.front(pred[None, None])
-        return self._polygons(bitmap[0].cpu().numpy(), rec[0, :int(min(nc[0], self.max_candidates))], dest_width, dest_height)
+        if not isinstance(dest_width, int):
+            dest_width, dest_height = dest_width.item(), dest_height.item()
+        boxes, scores = self.polygons_batch(pred[None, None], [(int(dest_width), int(dest_height))])
+        return boxes[0], scores[0]

@@ -154,6 +154,22 @@ int dbb_boxes_from_border_points(const DbbCandidate* cands, const int32_t* n_can
  * contour (npts, 2); box8: 4 x (x, y) float32 out. */
 int dbb_mini_box(const int32_t* contour_xy, int npts, float* box8, float* sside);
 
+/* HOST function: src/postprocess.py:54-104 (polygons_from_bitmap: contour, arcLength, approxPolyDP, < 4 points drop, unclip,
+ * len(box) > 1 drop, sside filter, rescale) for every kept candidate of a batch.  bits: the packed bitmap (N, H, ceil(W/32))
+ * uint32 = the first N*H*ceil(W/32) words of the dbb_binarize_ccl_score workspace, copied to the host.  counts (N, max_cands):
+ * points of candidate s's polygon (0 = dropped); points (N, cap, 2) int32: the polygons back to back; scores (N, max_cands)
+ * float64; totals (N): points produced per image (> cap: call again with a larger buffer). */
+int dbb_polygons_from_bitmap(const uint32_t* bits, const DbbCandidate* cands, const int32_t* n_cands, int64_t n, int max_cands,
+                             int64_t h, int64_t w, const int32_t* dest_wh, float unclip_ratio, int min_size, int32_t* counts,
+                             int32_t* points, int cap, double* scores, int32_t* totals, int threads);
+
+/* HOST functions (tests / single-contour use): one border of a byte bitmap traced as cv2.findContours(CHAIN_APPROX_SIMPLE) traces
+ * it (start = the border's start pixel; is_hole: hole border, start = the foreground pixel left of the hole's raster-first
+ * pixel), and cv2.approxPolyDP(contour, eps, closed=True) (+ cv2.arcLength; a negative eps is a ratio of the arc length:
+ * src/postprocess.py:71-72 uses 0.005).  Both return the number of points written. */
+int dbb_trace_contour(const uint8_t* bitmap, int64_t h, int64_t w, int start_x, int start_y, int is_hole, int32_t* out_xy, int cap);
+int dbb_approx_poly_dp(const int32_t* contour_xy, int npts, double eps_or_negative_ratio, int32_t* out_xy, int cap, double* arc_length);
+
 /* HOST function: pyclipper.PyclipperOffset().AddPath(path, JT_ROUND, ET_CLOSEDPOLYGON); Execute(delta) for one closed polygon
  * of any shape (src/postprocess.py:150-156 unclip; src/data_loaders.py:116-122 shrink with delta < 0; src/db_transforms.py:13-21).
  * Restates Clipper 6.4.2's ClipperOffset arithmetic (third-party, not in the reference tree: PARITY UNPINNED, see

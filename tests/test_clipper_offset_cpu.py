@@ -161,6 +161,57 @@ def test_unpinned_nonconvex_offset_region_is_positive_winding_of_raw_path(name, 
     assert d.max() <= delta + 1.0
 
 
+def _blob_polygons(seed, size=1024):
+    """approxPolyDP polygons of a synthetic probability map's components -- what polygons_from_bitmap hands to unclip
+    (reference src/postprocess.py:62-86): many vertices, 1-3 px edges, concavities narrower than the offset."""
+    ndimage = pytest.importorskip("scipy.ndimage")
+    from oracle import db_oracle as O
+    P = ((O.synth_prob_map(size, size, seed) - 0.45) * 8).clip(0, 1).astype(np.float32)
+    bm = np.ascontiguousarray(O.binarize(P, 0.25).astype(np.uint8))
+    lab, nl = ndimage.label(bm, structure=np.ones((3, 3), int))
+    out = np.zeros((bm.size // 4, 2), np.int32)
+    polys = []
+    for sl, k in zip(ndimage.find_objects(lab), range(1, nl + 1)):
+        ys, xs = np.nonzero(lab[sl] == k)
+        i = np.lexsort((xs, ys))[0]
+        n = lib().dbb_trace_contour(bm.ctypes.data, size, size, int(xs[i]) + sl[1].start, int(ys[i]) + sl[0].start, 0, out.ctypes.data, len(out))
+        assert n > 0
+        c = np.ascontiguousarray(out[:n])
+        ap = np.zeros((n + 4, 2), np.int32)
+        m = lib().dbb_approx_poly_dp(c.ctypes.data, n, -0.005, ap.ctypes.data, len(ap), None)
+        if m >= 4:
+            polys.append(ap[:m].copy())
+    return polys
+
+
+@pytest.mark.parametrize("seed", [100, 101, 102])
+def test_unpinned_offset_region_on_realistic_polygons(seed):
+    """The same positive-winding property at the unclip distance the detector uses, on the polygons it actually sees.  This is
+    the case that broke a version which snapped intersection points to whole pixels (119 of 876 polygons lost their outer
+    boundary): the raw path of a 4 px offset is made of 1-2 px arc pieces, so half-pixel snapping crosses neighbours."""
+    from db_text_minimal_b200.postprocess import clipper_offset, clipper_offset_raw
+    polys = _blob_polygons(seed)
+    assert len(polys) > 40
+    bad = []
+    for idx, p in enumerate(polys):
+        area, perim = poly_area_perimeter(p)
+        d = abs(area) * 1.5 / perim
+        raw, res = clipper_offset_raw(p, d), clipper_offset(p, d)
+        lo, hi = raw.min(0) - 3, raw.max(0) + 3
+        step = max(1.37, (hi - lo).max() / 60)
+        gx, gy = np.meshgrid(np.arange(lo[0], hi[0], step), np.arange(lo[1], hi[1], step))
+        pts = np.stack([gx.ravel() + 0.123, gy.ravel() + 0.456], 1)
+        near = dist_to_path(raw, pts) < 1.0
+        got = np.zeros(len(pts), np.int64)
+        for r in res:
+            near |= dist_to_path(r, pts) < 1.0
+            got += winding_number(r, pts)
+        want = winding_number(raw, pts) > 0
+        if not (np.array_equal(got[~near] > 0, want[~near]) and set(np.unique(got[~near])) <= {0, 1}):
+            bad.append((idx, len(p), round(d, 2), [len(r) for r in res]))
+    assert not bad, bad[:5]
+
+
 def test_unpinned_offset_with_hole_returns_two_paths():
     """A 'C' whose gap closes under the offset: the region has a hole, Execute returns 2 paths and the reference drops the
     candidate (src/postprocess.py:85-87 `if len(box) > 1: continue`)."""

@@ -1,0 +1,114 @@
+"""Polygon-mode host geometry (csrc/post_geom.cu): border following, arc length and Douglas-Peucker, PINNED against OpenCV
+itself (cv2.findContours / cv2.arcLength / cv2.approxPolyDP, the calls at reference src/postprocess.py:58-70) on the golden
+bitmaps and on blob maps dense enough to hold holes, touching components and one-pixel spurs.  Plain C++ behind the C ABI:
+runs without a GPU.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+cv2 = pytest.importorskip("cv2")
+ndimage = pytest.importorskip("scipy.ndimage")
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def lib():
+    from db_text_minimal_b200 import _lib
+    return _lib.lib()
+
+
+def trace(bm, sx, sy, hole):
+    bm = np.ascontiguousarray(bm.astype(np.uint8))
+    out = np.zeros((bm.size + 8, 2), np.int32)
+    n = lib().dbb_trace_contour(bm.ctypes.data, bm.shape[0], bm.shape[1], sx, sy, int(hole), out.ctypes.data, len(out))
+    assert n >= 0
+    return out[:n]
+
+
+def approx(c, ratio=0.005):
+    c = np.ascontiguousarray(np.asarray(c).astype(np.int32).reshape(-1, 2))
+    out, al = np.zeros((len(c) + 4, 2), np.int32), C.c_double()
+    n = lib().dbb_approx_poly_dp(c.ctypes.data, len(c), -ratio, out.ctypes.data, len(out), C.byref(al))
+    assert n >= 0
+    return out[:n], al.value
+
+
+def bitmaps():
+    from oracle import db_oracle as O
+    z = np.load(os.path.join(GOLD, "post_cases.npz"))
+    maps = {nm: z[nm + ":bitmap"].astype(np.uint8) for nm in sorted({k.split(":")[0] for k in z.files})}
+    for seed, (h, w) in [(11, (256, 320)), (13, (640, 640))]:
+        P = ((O.synth_prob_map(h, w, seed) - 0.45) * 8).clip(0, 1).astype(np.float32)
+        maps[f"kept{seed}"] = O.binarize(P, 0.25).astype(np.uint8)
+    rng = np.random.default_rng(5)
+    maps["noise"] = (rng.random((96, 128)) < 0.55).astype(np.uint8)       # spurs, diagonal touches, many small holes
+    return maps
+
+
+BITMAPS = bitmaps()
+
+
+def _same_set(got, want):
+    A = sorted((np.asarray(c, np.int32).tobytes() for c in got))
+    B = sorted((np.asarray(c, np.int32).reshape(-1, 2).tobytes() for c in want))
+    return A == B
+
+
+@pytest.mark.parametrize("name", sorted(BITMAPS))
+def test_trace_contour_matches_findcontours(name):
+    """Outer borders start at the raster-first pixel of an 8-connected component, hole borders at the foreground pixel left
+    of the raster-first pixel of an enclosed 4-connected background region (what cv2's raster scan finds); the point lists
+    (CHAIN_APPROX_SIMPLE) must be identical, order and start included."""
+    bm = BITMAPS[name]
+    contours, hier = cv2.findContours(bm * 255, cv2.RETR_CCOMP, cv2.CHAIN_APPROX_SIMPLE)
+    if hier is None:
+        pytest.skip("empty bitmap")
+    outer = [c for c, hh in zip(contours, hier[0]) if hh[3] < 0]
+    holes = [c for c, hh in zip(contours, hier[0]) if hh[3] >= 0]
+    lab, nl = ndimage.label(bm, structure=np.ones((3, 3), int))
+    got = []
+    for sl, k in zip(ndimage.find_objects(lab), range(1, nl + 1)):
+        ys, xs = np.nonzero(lab[sl] == k)
+        i = np.lexsort((xs, ys))[0]
+        got.append(trace(bm, int(xs[i]) + sl[1].start, int(ys[i]) + sl[0].start, False))
+    assert len(got) == len(outer) and _same_set(got, outer)
+    labb, nb = ndimage.label(1 - bm)
+    H, W = bm.shape
+    got = []
+    for sl, k in zip(ndimage.find_objects(labb), range(1, nb + 1)):
+        if sl[0].start == 0 or sl[1].start == 0 or sl[0].stop == H or sl[1].stop == W:
+            continue
+        ys, xs = np.nonzero(labb[sl] == k)
+        i = np.lexsort((xs, ys))[0]
+        got.append(trace(bm, int(xs[i]) + sl[1].start - 1, int(ys[i]) + sl[0].start, True))
+    assert len(got) == len(holes) and _same_set(got, holes)
+
+
+@pytest.mark.parametrize("name", sorted(BITMAPS))
+def test_arc_length_and_approx_poly_dp_match_cv2(name):
+    bm = BITMAPS[name]
+    contours, _ = cv2.findContours(bm * 255, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+    for c in contours:
+        al_ref = cv2.arcLength(c, True)
+        want = cv2.approxPolyDP(c, 0.005 * al_ref, True).reshape(-1, 2)
+        got, al = approx(c)
+        assert abs(al - al_ref) <= 1e-9 * max(1.0, al_ref)
+        assert np.array_equal(got, want), (name, len(c))
+
+
+def test_approx_poly_dp_absolute_epsilon_and_tiny_inputs():
+    sq = np.array([[0, 0], [10, 0], [10, 1], [10, 10], [0, 10]], np.int32)
+    for eps in (0.0, 0.5, 1.5, 20.0):
+        want = cv2.approxPolyDP(sq.reshape(-1, 1, 2), eps, True).reshape(-1, 2)
+        out = np.zeros((8, 2), np.int32)
+        n = lib().dbb_approx_poly_dp(sq.ctypes.data, len(sq), eps, out.ctypes.data, len(out), None)
+        assert np.array_equal(out[:n], want), eps
+    for pts in ([[3, 4]], [[3, 4], [9, 4]]):
+        p = np.array(pts, np.int32)
+        want = cv2.approxPolyDP(p.reshape(-1, 1, 2), 1.0, True).reshape(-1, 2)
+        out = np.zeros((8, 2), np.int32)
+        n = lib().dbb_approx_poly_dp(p.ctypes.data, len(p), 1.0, out.ctypes.data, len(out), None)
+        assert np.array_equal(out[:n], want), pts
