@@ -100,27 +100,92 @@ __device__ __forceinline__ unsigned run_starts(unsigned cur, int nvalid) {
   return st;
 }
 
-// A: binarize (strict >), pack, write the byte bitmap, label every pixel with the first pixel of its segment run
+// A: binarize (strict >), pack, write the byte bitmap, label every pixel with the first pixel of its ROW run.
+// One warp per image row, 32 words (1,024 pixels) per pass: the 32 coalesced 128-byte loads of a pass are all issued before
+// the first ballot (the first version had one load in flight per warp: 2.2 TB/s); then lane k owns word k and a max-scan over
+// the lanes carries run starts across word boundaries, so horizontal neighbours are linked by construction and ccl_link has
+// no seam unions left to do.  (A label that points into an earlier word is an ordinary union-find parent pointer: it is
+// smaller than the pixel index and is itself the start of a segment run.)
 __global__ void __launch_bounds__(CCL_THREADS)
 ccl_pack_init_kernel(const float* __restrict__ pred, int c, int n, int h, int w, int wq, float thresh, uint8_t* __restrict__ bitmap,
-                     unsigned* __restrict__ bits, int* __restrict__ label) {
+                     unsigned* __restrict__ bits, int* __restrict__ label, int word_stores) {
   const int64_t hw = (int64_t)h * w;
   const int lane = threadIdx.x & 31;
-  const int64_t nseg = (int64_t)n * h * wq;
-  const int64_t wstride = (int64_t)gridDim.x * (CCL_THREADS / 32);
-  for (int64_t widx = (int64_t)blockIdx.x * (CCL_THREADS / 32) + (threadIdx.x >> 5); widx < nseg; widx += wstride) {
-    Seg g; seg_of(widx, h, wq, w, g);
-    const bool in = lane < g.nvalid;
-    const int64_t pix = (int64_t)g.y * w + g.x0 + lane;
-    const float p = in ? pred[(int64_t)g.img * c * hw + pix] : 0.f;
-    const unsigned cur = __ballot_sync(0xffffffffu, in && p > thresh);
-    if (lane == 0) bits[widx] = cur;
-    if (in) {
-      bitmap[g.img * hw + pix] = (cur >> lane) & 1u;
-      const unsigned st = run_starts(cur, g.nvalid) & ((2u << lane) - 1u);
-      label[g.img * (hw + 1) + pix] = (int)((int64_t)g.y * w + g.x0 + (31 - __clz(st)));
+  const int nrows = n * h;
+  const int wstride = gridDim.x * (CCL_THREADS / 32);
+  for (int row = blockIdx.x * (CCL_THREADS / 32) + (threadIdx.x >> 5); row < nrows; row += wstride) {
+    const int img = row / h, y = row - img * h;
+    const float* P = pred + (int64_t)img * c * hw + (int64_t)y * w;
+    int* Lrow = label + img * (hw + 1) + (int64_t)y * w;
+    uint8_t* Brow = bitmap + img * hw + (int64_t)y * w;
+    unsigned* Wrow = bits + (int64_t)row * wq;
+    if (y == 0 && lane == 0) label[img * (hw + 1) + hw] = (int)hw;       // virtual outside node
+    int carry_start = -1;            // start (x) of the row run that reaches the end of the previous pass
+    unsigned carry_bit = 0;          // class of the last pixel of the previous pass
+    for (int s0 = 0; s0 < wq; s0 += 32) {
+      const int kk = wq - s0 < 32 ? wq - s0 : 32;
+      float v[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int x = (s0 + k) * 32 + lane;
+        v[k] = (k < kk && x < w) ? __ldg(P + x) : 0.f;
+      }
+      unsigned cw[32];
+      unsigned mine = 0;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        cw[k] = __ballot_sync(0xffffffffu, v[k] > thresh);               // lanes beyond the row hold 0 -> bit 0
+        if (lane == k) mine = cw[k];
+      }
+      // ---- lane k owns word s0 + k
+      const int x0 = (s0 + lane) * 32;
+      const int nvalid = lane < kk ? (w - x0 < 32 ? w - x0 : 32) : 0;
+      const unsigned vm = valid_mask(nvalid);
+      if (lane < kk) Wrow[s0 + lane] = mine;
+      unsigned prev_word = __shfl_up_sync(0xffffffffu, mine, 1);
+      const unsigned prev_bit = lane == 0 ? carry_bit : (prev_word >> 31);
+      const bool cont = (s0 + lane > 0) && nvalid > 0 && ((mine & 1u) == prev_bit);
+      const unsigned stv = run_starts(mine, nvalid) & vm;
+      const bool single = (stv & (stv - 1)) == 0;
+      int val = (nvalid == 0 || (single && cont)) ? -1 : x0 + (31 - __clz(stv));
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, val, o);
+        if (lane >= o && t > val) val = t;
+      }
+      if (val < carry_start) val = carry_start;                          // nothing defined up to here: the run comes from the previous pass
+      int before = __shfl_up_sync(0xffffffffu, val, 1);
+      if (lane == 0) before = carry_start;
+      const int first_start = cont ? before : x0;                        // start of the row run the word's FIRST segment run belongs to
+      // ---- labels (lane = pixel again) and the byte bitmap
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int fs = __shfl_sync(0xffffffffu, first_start, k);
+        if (k < kk) {
+          const int xk = (s0 + k) * 32;
+          const int nv = w - xk < 32 ? w - xk : 32;
+          if (lane < nv) {
+            const unsigned st = run_starts(cw[k], nv) & ((2u << lane) - 1u);
+            const int a = 31 - __clz(st);
+            Lrow[xk + lane] = y * w + (a == 0 ? fs : xk + a);
+            if (!word_stores) Brow[xk + lane] = (cw[k] >> lane) & 1u;
+          }
+        }
+      }
+      if (word_stores) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {                                    // 4 words = 128 pixels = one 128-byte store per warp
+          const unsigned wv = __shfl_sync(0xffffffffu, mine, 4 * q + (lane >> 3));
+          const int x = (s0 + 4 * q) * 32 + 4 * lane;
+          if (4 * q < kk && x < w) {
+            const unsigned nib = (wv >> ((lane & 7) * 4)) & 0xfu;
+            *reinterpret_cast<unsigned*>(Brow + x) = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+          }
+        }
+      }
+      carry_start = __shfl_sync(0xffffffffu, val, kk - 1);
+      carry_bit = __shfl_sync(0xffffffffu, mine, kk - 1) >> 31;
     }
-    if (g.y == 0 && g.s == 0 && lane == 0) label[g.img * (hw + 1) + hw] = (int)hw;   // virtual outside node
   }
 }
 
@@ -160,8 +225,7 @@ __device__ __forceinline__ void link_word(const unsigned* __restrict__ bits, int
     while (VB) { const int b = __ffs(VB) - 1; VB &= VB - 1; uf_union(L, i0 + b, i0 + b - w); }
   }
   if (phase != 0) return;
-  // horizontal link across the segment boundary (inside a segment the run label already encodes it)
-  if (g.s > 0 && (((cur & 1u) != 0) == ((prv >> 31) != 0))) uf_union(L, i0, i0 - 1);
+  // (no horizontal unions: ccl_pack_init labels every pixel with the start of its ROW run)
   // frame pixels of the background belong to the outside region: one union per background run start on the first / last
   // row, the first / last pixel of every other row
   const unsigned ncur = ~cur & vm;
@@ -211,7 +275,7 @@ ccl_flatten_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int w
       if (r == i && init_stats) {
         CompStat z;
         z.sum = 0.0; z.acc_sum = 0.0; z.count = 0; z.acc_count = 0;
-        z.x0 = w; z.y0 = h; z.x1 = -1; z.y1 = -1;
+        z.x0 = w; z.y0 = i / w; z.x1 = -1; z.y1 = -1;      // the root is the raster-first pixel: its row IS y0
         stat[g.img * hw + i] = z;
         roots |= 1u << b;
       }
@@ -225,97 +289,228 @@ ccl_flatten_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int w
 __device__ __forceinline__ int root2(const int* L, int i) { return L[L[i]]; }
 __device__ __forceinline__ int parent_of(const int* L, int r, int w, int r_out) { return r < w ? r_out : root2(L, r - w); }
 
-// D: final labels + per-component statistics.  One atomic set per (segment run) instead of per pixel: run sums come from
-// a warp prefix sum in float64; the outside region is skipped; foreground pixels that 4-touch an enclosed background
-// region add themselves to that hole's boundary ring.
+// D: per-component statistics.  ONE THREAD PER 32-PIXEL WORD (the warp-per-word version spent 313 warp-instructions per word
+// on a float64 warp scan and per-lane ring tests: issue-bound at 0.85 ms for 64 x 1024^2, profiles/prof_ccl_r02.md):
+//   * a word whose runs all belong to the outside region (most of a text map) is dropped after one label lookup -- its
+//     probabilities are never read;
+//   * the probabilities of the other words of a warp are staged through shared memory (coalesced 128-byte rows in, one
+//     row of 32 floats per thread out, pitch 33 -> conflict-free), summed per run in float64, one atomic set per run;
+//   * hole rings: foreground pixels that 4-touch an enclosed background region add themselves to that hole's boundary ring.
+//     Neighbouring background RUNS are classified first (one label lookup per run); only pixels that touch a run which is
+//     not the outside region take the per-pixel path (distinct regions, parent test).
+__device__ __forceinline__ unsigned run_mask(int a, int b) {      // bits a..b inclusive
+  return (b >= 31 ? 0xffffffffu : ((2u << b) - 1u)) & ~((1u << a) - 1u);
+}
+// bits of `word` (background = 0 bits, restricted to `touch`) that lie in a background run whose region is not r_out
+__device__ __forceinline__ unsigned inner_bg(unsigned word, unsigned touch, int nvalid, const int* L, int ibase, int r_out) {
+  unsigned out = 0;
+  unsigned cand = ~word & touch;
+  const unsigned st = run_starts(word, nvalid);
+  while (cand) {
+    const int b = __ffs(cand) - 1;
+    const int a = 31 - __clz(st & ((2u << b) - 1u));
+    const unsigned later = b >= 31 ? 0u : (st & ~((2u << b) - 1u));
+    const int e = later ? (__ffs(later) - 2) : 31;
+    const unsigned m = run_mask(a, e);
+    if (root2(L, ibase + a) != r_out) out |= m;
+    cand &= ~m;
+  }
+  return out;
+}
+// Per-block aggregation of the run statistics.  A block owns a CONTIGUOUS range of words (STATS_WORDS_PER_BLOCK: 64 rows of a
+// 1,024-pixel image), so the runs of one region that fall into the range are summed in a small shared-memory hash table
+// and reach the region's global slot as ONE atomic set per block instead of one per run.  (Direct atomics: 19 M RED requests
+// for 64 x 1024^2, the busiest L2 slice 32 % occupied by its atomic unit, 0.62 of the kernel's 0.97 ms.)
+constexpr int AGG_N = 256;
+constexpr int STATS_WORDS_PER_BLOCK = 2048;
+struct AggEntry { unsigned long long key; double sum; int count, x0, x1, y1; };
+constexpr unsigned long long AGG_EMPTY = ~0ull;
+__device__ __forceinline__ void stat_add_global(CompStat* t, double sum, int count, int xa, int xb, int y) {
+  atomicAdd(&t->sum, sum);
+  atomicAdd(&t->count, count);
+  atomicMin(&t->x0, xa); atomicMax(&t->x1, xb); atomicMax(&t->y1, y);
+}
+__device__ __forceinline__ void agg_add(AggEntry* agg, CompStat* stat, unsigned long long key, double sum, int count, int xa, int xb, int y) {
+  const unsigned hsh = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 40);
+#pragma unroll 1
+  for (int probe = 0; probe < 4; ++probe) {
+    AggEntry* e = agg + ((hsh + probe) & (AGG_N - 1));
+    const unsigned long long old = atomicCAS(&e->key, AGG_EMPTY, key);
+    if (old == AGG_EMPTY || old == key) {
+      atomicAdd(&e->sum, sum);
+      atomicAdd(&e->count, count);
+      atomicMin(&e->x0, xa); atomicMax(&e->x1, xb); atomicMax(&e->y1, y);
+      return;
+    }
+  }
+  stat_add_global(stat + key, sum, count, xa, xb, y);       // table full around this hash: straight to the slot
+}
 __global__ void __launch_bounds__(CCL_THREADS)
 ccl_stats_kernel(const float* __restrict__ pred, int c, const unsigned* __restrict__ bits, int n, int h, int w, int wq,
-                 int* __restrict__ label, CompStat* __restrict__ stat) {
+                 const int* __restrict__ label, CompStat* __restrict__ stat, int dbg) {
+  __shared__ float tile[CCL_THREADS / 32][32 * 33];
+  __shared__ AggEntry agg[AGG_N];
   const int64_t hw = (int64_t)h * w;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   const int64_t nseg = (int64_t)n * h * wq;
-  const int64_t wstride = (int64_t)gridDim.x * (CCL_THREADS / 32);
-  for (int64_t widx = (int64_t)blockIdx.x * (CCL_THREADS / 32) + (threadIdx.x >> 5); widx < nseg; widx += wstride) {
-    Seg g; seg_of(widx, h, wq, w, g);
-    int* L = label + g.img * (hw + 1);
+  float* T = tile[wrp];
+  for (int t = threadIdx.x; t < AGG_N; t += CCL_THREADS) { AggEntry z; z.key = AGG_EMPTY; z.sum = 0.0; z.count = 0; z.x0 = 0x7fffffff; z.x1 = -1; z.y1 = -1; agg[t] = z; }
+  __syncthreads();
+  const int64_t range0 = (int64_t)blockIdx.x * STATS_WORDS_PER_BLOCK;
+  const int64_t range1 = range0 + STATS_WORDS_PER_BLOCK < nseg ? range0 + STATS_WORDS_PER_BLOCK : nseg;
+  for (int64_t base = range0; base < range1; base += CCL_THREADS) {
+    const int64_t widx = base + threadIdx.x;
+    const bool live = widx < nseg;
+    Seg g; g.img = 0; g.y = 0; g.s = 0; g.x0 = 0; g.nvalid = 0;
+    if (live) seg_of(widx, h, wq, w, g);
+    const int* L = label + g.img * (hw + 1);
     CompStat* S = stat + g.img * hw;
-    const int r_out = L[hw];
-    const bool in = lane < g.nvalid;
-    const int x = g.x0 + lane;
-    const int i = g.y * w + x;
-    const unsigned cur = bits[widx];
-    const unsigned st = run_starts(cur, g.nvalid);
-    // this lane's run: [a, b]
-    const int a = 31 - __clz(st & ((2u << lane) - 1u));
-    const unsigned later = (lane >= 31) ? 0u : (st & ~((2u << lane) - 1u));
-    const int b = later ? (__ffs(later) - 2) : 31;
-    int r = -1;
-    if (in) r = root2(L, g.y * w + g.x0 + a);            // every lane of a run reads the same word
-    const float p = in ? pred[(int64_t)g.img * c * hw + i] : 0.f;
-    // inclusive prefix sum over the warp in float64
-    double pre = (double)p;
+    const int r_out = live ? L[hw] : 0;
+    const int i0 = g.y * w + g.x0;
+    const unsigned vm = valid_mask(g.nvalid);
+    const unsigned cur = live ? bits[widx] : 0u;
+    const unsigned st = run_starts(cur, g.nvalid) & vm;
+    // the four neighbour words (ring test below), fetched with the word itself
+    const bool has_fg = (cur & vm) != 0;
+    const unsigned prv = has_fg && g.s > 0 ? bits[widx - 1] : 0xffffffffu, nxt = has_fg && g.s < wq - 1 ? bits[widx + 1] : 0xffffffffu;
+    const unsigned up = has_fg && g.y > 0 ? (bits[widx - wq] | ~vm) : 0xffffffffu, dn = has_fg && g.y < h - 1 ? (bits[widx + wq] | ~vm) : 0xffffffffu;
+    // roots of the first four runs, looked up together (two dependent loads each; doing them one by one at the run ends
+    // made the whole warp wait 2 x L2 latency per run end: 82 % of the stall samples, profiles/prof_ccl_r02.md)
+    int ra[4], rr[4];
+    {
+      unsigned m = st;
+      int l1[4];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double t = __shfl_up_sync(0xffffffffu, pre, o);
-      if (lane >= o) pre += t;
+      for (int k = 0; k < 4; ++k) { ra[k] = m ? __ffs(m) - 1 : -1; m &= m - 1; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) l1[k] = (live && ra[k] >= 0) ? L[i0 + ra[k]] : -1;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rr[k] = l1[k] >= 0 ? L[l1[k]] : r_out;
     }
-    const double pre_b = __shfl_sync(0xffffffffu, pre, b < g.nvalid ? b : g.nvalid - 1 < 0 ? 0 : (b > 31 ? 31 : b));
-    if (!in) continue;
-    if (r == r_out) continue;
-    if (lane == a) {
-      const int be = b < g.nvalid ? b : g.nvalid - 1;
-      const double run_sum = pre_b - pre + (double)p;
-      CompStat* t = S + r;
-      atomicAdd(&t->sum, run_sum);
-      atomicAdd(&t->count, be - a + 1);
-      atomicMin(&t->x0, g.x0 + a); atomicMax(&t->x1, g.x0 + be); atomicMin(&t->y0, g.y); atomicMax(&t->y1, g.y);
+    const int nruns = __popc(st);
+    const bool need = live && (nruns > 4 || rr[0] != r_out || rr[1] != r_out || rr[2] != r_out || rr[3] != r_out);
+    // ---- stage the probabilities of the needed words of this warp (uniform per k)
+    const unsigned needm = __ballot_sync(0xffffffffu, need);
+    const int64_t pbase = (int64_t)g.img * c * hw + i0;
+    __syncwarp();                                   // the previous chunk's reads of T are done
+    if (needm) {
+      float v[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int64_t pb = __shfl_sync(0xffffffffu, pbase, k);
+        const int nv = __shfl_sync(0xffffffffu, g.nvalid, k);
+        v[k] = ((needm >> k) & 1u) && lane < nv ? __ldg(pred + pb + lane) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 32; ++k) T[k * 33 + lane] = v[k];
     }
-    // boundary ring of holes: a foreground pixel contributes once to every DISTINCT enclosed region it 4-touches
-    if ((cur >> lane) & 1u) {
-      const unsigned prv = g.s > 0 ? bits[widx - 1] : 0xffffffffu, nxt = g.s < wq - 1 ? bits[widx + 1] : 0xffffffffu;
-      const bool bgL = x > 0 && !(lane > 0 ? (cur >> (lane - 1)) & 1u : (prv >> 31) & 1u);
-      const bool bgR = x < w - 1 && !(lane < 31 ? (cur >> (lane + 1)) & 1u : nxt & 1u);
-      const bool bgU = g.y > 0 && !((bits[widx - wq] >> lane) & 1u);
-      const bool bgD = g.y < h - 1 && !((bits[widx + wq] >> lane) & 1u);
-      if (bgL | bgR | bgU | bgD) {
-        const int pr = parent_of(L, r, w, r_out);
-        int gq[4] = {-1, -1, -1, -1};
-        if (bgL) gq[0] = root2(L, i - 1);
-        if (bgR) gq[1] = root2(L, i + 1);
-        if (bgU) gq[2] = root2(L, i - w);
-        if (bgD) gq[3] = root2(L, i + w);
+    __syncwarp();
+    if (!need) continue;
+    const float* row = T + lane * 33;
+    // ---- per-run sums -> one atomic set per run that is not the outside region
+    unsigned inner_cur = 0;                          // background pixels of this word in enclosed regions (for the ring test)
+    {
+      double acc = 0.0, sums[4] = {0.0, 0.0, 0.0, 0.0};
+      int ends[4] = {0, 0, 0, 0};
+      int a = 0, k = 0;
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        acc += (double)row[j];
+        const bool last = j + 1 >= g.nvalid;
+        const bool ends_here = j < g.nvalid && (last || ((st >> (j + 1)) & 1u));
+        if (ends_here) {
+          if (k < 4) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int gk = gq[k];
-          if (gk < 0 || gk == pr || gk == r_out) continue;
-          bool dup = false;
+            for (int q = 0; q < 4; ++q) if (q == k) { sums[q] = acc; ends[q] = j; }
+          } else {                                   // fifth and later runs of a word (noise): looked up on the spot
+            const int r = root2(L, i0 + a);
+            if (r != r_out) {
+              agg_add(agg, stat, (unsigned long long)(g.img * hw + r), acc, j - a + 1, g.x0 + a, g.x0 + j, g.y);
+              if (!((cur >> a) & 1u)) inner_cur |= run_mask(a, j);
+            }
+          }
+          acc = 0.0; a = j + 1; ++k;
+        }
+      }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) if (q < k && gq[q] == gk) dup = true;
-          if (dup) continue;
-          atomicAdd(&S[gk].acc_sum, (double)p);
-          atomicAdd(&S[gk].acc_count, 1);
+      for (int q = 0; q < 4; ++q) {
+        if (q < nruns && rr[q] != r_out && !(dbg & 2)) {
+          agg_add(agg, stat, (unsigned long long)(g.img * hw + rr[q]), sums[q], ends[q] - ra[q] + 1, g.x0 + ra[q], g.x0 + ends[q], g.y);
+          if (!((cur >> ra[q]) & 1u)) inner_cur |= run_mask(ra[q], ends[q]);
         }
       }
     }
+    // ---- boundary rings of holes
+    const unsigned fg = cur & vm;
+    if (!fg || (dbg & 1)) continue;
+    const unsigned ones = 0xffffffffu;
+    const unsigned curx = cur | ~vm;                                          // beyond the row end: not background
+    const int nv_up = g.nvalid;                                               // same column range in the rows above / below
+    const unsigned curL = (curx << 1) | (prv >> 31), curR = (curx >> 1) | (nxt << 31);
+    if (!(fg & (~curL | ~curR | ~up | ~dn))) continue;                        // interior word
+    // background runs around the word that are NOT the outside region
+    unsigned innL = inner_cur << 1, innR = inner_cur >> 1;
+    if ((fg & 1u) && !(prv >> 31) && root2(L, i0 - 1) != r_out) innL |= 1u;
+    if ((fg >> 31) && !(nxt & 1u) && root2(L, i0 + 32) != r_out) innR |= 0x80000000u;
+    const unsigned innU = (fg & ~up) ? inner_bg(up, fg, nv_up, L, i0 - w, r_out) : 0u;
+    const unsigned innD = (fg & ~dn) ? inner_bg(dn, fg, nv_up, L, i0 + w, r_out) : 0u;
+    unsigned slow = fg & (innL | innR | innU | innD);
+    while (slow) {
+      const int b = __ffs(slow) - 1; slow &= slow - 1;
+      const int i = i0 + b;
+      const int r = root2(L, i);
+      const int pr = parent_of(L, r, w, r_out);
+      int gq[4] = {-1, -1, -1, -1};
+      if ((innL >> b) & 1u) gq[0] = root2(L, i - 1);
+      if ((innR >> b) & 1u) gq[1] = root2(L, i + 1);
+      if ((innU >> b) & 1u) gq[2] = root2(L, i - w);
+      if ((innD >> b) & 1u) gq[3] = root2(L, i + w);
+      const double p = (double)row[b];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int gk = gq[k];
+        if (gk < 0 || gk == pr || gk == r_out) continue;
+        bool dup = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (q < k && gq[q] == gk) dup = true;
+        if (dup) continue;
+        atomicAdd(&S[gk].acc_sum, p);
+        atomicAdd(&S[gk].acc_count, 1);
+      }
+    }
+  }
+  // ---- one atomic set per region and block
+  __syncthreads();
+  for (int t = threadIdx.x; t < AGG_N; t += CCL_THREADS) {
+    const AggEntry e = agg[t];
+    if (e.key != AGG_EMPTY) stat_add_global(stat + e.key, e.sum, e.count, e.x0, e.x1, e.y1);
   }
 }
 
+// E: every region adds its own statistics to all its ancestors.  Roots come from the root bitmap (1/32 word per pixel instead
+// of the 4-byte label: 8 MB instead of 268 MB for 64 x 1024^2).
 __global__ void __launch_bounds__(CCL_THREADS)
-ccl_tree_kernel(const uint8_t* __restrict__ bitmap, int h, int w, const int* __restrict__ label, CompStat* __restrict__ stat) {
+ccl_tree_kernel(int h, int w, int wq, const int* __restrict__ label, const unsigned* __restrict__ rootbits, CompStat* __restrict__ stat) {
   const int img = blockIdx.y;
   const int64_t hw = (int64_t)h * w;
   const int* L = label + img * (hw + 1);
   CompStat* S = stat + img * hw;
   const int r_out = L[hw];
-  for (int64_t i = (int64_t)blockIdx.x * CCL_THREADS + threadIdx.x; i < hw; i += (int64_t)gridDim.x * CCL_THREADS) {
-    if (L[i] != (int)i || (int)i == r_out) continue;
-    const double s = S[i].sum;
-    const int cnt = S[i].count;
-    int a = parent_of(L, (int)i, w, r_out);
-    while (a != r_out) {
-      atomicAdd(&S[a].acc_sum, s);
-      atomicAdd(&S[a].acc_count, cnt);
-      a = parent_of(L, a, w, r_out);
+  const int nw = h * wq;
+  for (int wi = blockIdx.x * CCL_THREADS + threadIdx.x; wi < nw; wi += gridDim.x * CCL_THREADS) {
+    unsigned rb = rootbits[(int64_t)img * nw + wi];
+    const int y = wi / wq, i0 = y * w + (wi - y * wq) * 32;
+    while (rb) {
+      const int i = i0 + __ffs(rb) - 1; rb &= rb - 1;
+      if (i == r_out) continue;
+      const double s = S[i].sum;
+      const int cnt = S[i].count;
+      int a = parent_of(L, i, w, r_out);
+      while (a != r_out) {
+        atomicAdd(&S[a].acc_sum, s);
+        atomicAdd(&S[a].acc_count, cnt);
+        a = parent_of(L, a, w, r_out);
+      }
     }
   }
 }
@@ -566,6 +761,7 @@ extern "C" int dbb_binarize_ccl_score(const float* pred, int64_t n, int c, int64
   if (!pred || !bitmap || !cands || !n_cands || !workspace) return set_error(DBB_EINVAL, "binarize_ccl_score: null pointer");
   if (n <= 0 || c <= 0 || h <= 0 || w <= 0 || max_cands <= 0 || n > 65535) return set_error(DBB_EINVAL, "binarize_ccl_score: bad shape");
   if (h * w >= (int64_t)1 << 31) return set_error(DBB_EUNSUPPORTED, "binarize_ccl_score: image too large for 32-bit labels");
+  if (n * h >= (int64_t)1 << 31) return set_error(DBB_EUNSUPPORTED, "binarize_ccl_score: too many rows for 32-bit row indices");
   if (n * h * ((w + 31) / 32) >= (int64_t)1 << 32) return set_error(DBB_EUNSUPPORTED, "binarize_ccl_score: batch too large for 32-bit word indices");
   if (workspace_bytes < dbb_postprocess_workspace(n, h, w)) return set_error(DBB_EWORKSPACE, "binarize_ccl_score: workspace too small");
   if (!aligned16(workspace)) return set_error(DBB_EALIGN, "binarize_ccl_score: workspace not 16B aligned");
@@ -574,12 +770,13 @@ extern "C" int dbb_binarize_ccl_score(const float* pred, int64_t n, int c, int64
   const int wq = (int)((w + 31) / 32);
   CclWs ws = ccl_carve(workspace, n, hw, h, wq);
   const int64_t nseg = n * h * wq;
-  int gseg = (int)((nseg + CCL_THREADS / 32 - 1) / (CCL_THREADS / 32));
-  if (gseg > DBB_NUM_SMS * 16) gseg = DBB_NUM_SMS * 16;
+  int grow = (int)((n * h + CCL_THREADS / 32 - 1) / (CCL_THREADS / 32));
+  if (grow > DBB_NUM_SMS * 8) grow = DBB_NUM_SMS * 8;
   const int nblk = ccl_nblk(hw);
   int gx = nblk < DBB_NUM_SMS * 8 ? nblk : DBB_NUM_SMS * 8;
   const dim3 grid((unsigned)gx, (unsigned)n), gridb((unsigned)nblk, (unsigned)n);
-  DBB_LAUNCH("ccl_pack_init", s, ccl_pack_init_kernel<<<gseg, CCL_THREADS, 0, s>>>(pred, c, (int)n, (int)h, (int)w, wq, thresh, bitmap, ws.bits, ws.label));
+  DBB_LAUNCH("ccl_pack_init", s, ccl_pack_init_kernel<<<grow, CCL_THREADS, 0, s>>>(pred, c, (int)n, (int)h, (int)w, wq, thresh, bitmap, ws.bits, ws.label,
+                                                                                          (w % 4 == 0 && ((uintptr_t)bitmap & 3) == 0) ? 1 : 0));
   // thread-per-word kernels
   int gword = (int)((nseg + CCL_THREADS - 1) / CCL_THREADS);
   if (gword > DBB_NUM_SMS * 8) gword = DBB_NUM_SMS * 8;
@@ -593,10 +790,11 @@ extern "C" int dbb_binarize_ccl_score(const float* pred, int64_t n, int c, int64
     DBB_LAUNCH("ccl_link", s, ccl_link_kernel<<<gedge, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, 1));
   }
   DBB_LAUNCH("ccl_flatten", s, ccl_flatten_kernel<<<gword, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, 1, ws.rootbits));
-  DBB_LAUNCH("ccl_stats", s, ccl_stats_kernel<<<gseg, CCL_THREADS, 0, s>>>(pred, c, ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat));
-  DBB_LAUNCH("ccl_tree", s, ccl_tree_kernel<<<grid, CCL_THREADS, 0, s>>>(bitmap, (int)h, (int)w, ws.label, ws.stat));
+  DBB_LAUNCH("ccl_stats", s, ccl_stats_kernel<<<(unsigned)((nseg + STATS_WORDS_PER_BLOCK - 1) / STATS_WORDS_PER_BLOCK), CCL_THREADS, 0, s>>>(pred, c, ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, getenv("DBB_CCL_DBG") ? atoi(getenv("DBB_CCL_DBG")) : 0));
+  
   const int nwblk = (int)((h * wq + CCL_THREADS - 1) / CCL_THREADS);        // blocks of 256 words in raster order
   const dim3 gridw((unsigned)nwblk, (unsigned)n);
+  DBB_LAUNCH("ccl_tree", s, ccl_tree_kernel<<<gridw, CCL_THREADS, 0, s>>>((int)h, (int)w, wq, ws.label, ws.rootbits, ws.stat));
   DBB_LAUNCH("ccl_count", s, ccl_count_kernel<<<gridw, CCL_THREADS, 0, s>>>((int)h, (int)w, wq, ws.label, ws.rootbits, ws.blk_count, nwblk));
   DBB_LAUNCH("ccl_scan", s, ccl_scan_kernel<<<(unsigned)n, 1024, 0, s>>>(ws.blk_count, ws.blk_off, nwblk, n_cands));
   DBB_LAUNCH("ccl_emit", s, ccl_emit_kernel<<<gridw, CCL_THREADS, 0, s>>>(bitmap, (int)h, (int)w, wq, ws.label, ws.stat, ws.rootbits, ws.blk_off, nwblk, box_thresh, cands, max_cands));
