@@ -106,6 +106,77 @@ __device__ __forceinline__ unsigned run_starts(unsigned cur, int nvalid) {
 // the lanes carries run starts across word boundaries, so horizontal neighbours are linked by construction and ccl_link has
 // no seam unions left to do.  (A label that points into an earlier word is an ordinary union-find parent pointer: it is
 // smaller than the pixel index and is itself the start of a segment run.)
+// One image row by one warp.  Lrow / Wrow2 may point to shared memory (the strip kernel keeps strip-local labels there);
+// label_base is the index of the row's first pixel in the index space of Lrow's array.
+__device__ __forceinline__ void pack_row(const float* __restrict__ P, int w, int wq, float thresh, int* Lrow, int label_base,
+                                         uint8_t* __restrict__ Brow, unsigned* __restrict__ Wrow, unsigned* Wrow2, int word_stores, int lane) {
+  int carry_start = -1;            // start (x) of the row run that reaches the end of the previous pass
+  unsigned carry_bit = 0;          // class of the last pixel of the previous pass
+  for (int s0 = 0; s0 < wq; s0 += 32) {
+    const int kk = wq - s0 < 32 ? wq - s0 : 32;
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int x = (s0 + k) * 32 + lane;
+      v[k] = (k < kk && x < w) ? __ldg(P + x) : 0.f;
+    }
+    unsigned cw[32];
+    unsigned mine = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      cw[k] = __ballot_sync(0xffffffffu, v[k] > thresh);               // lanes beyond the row hold 0 -> bit 0
+      if (lane == k) mine = cw[k];
+    }
+    // ---- lane k owns word s0 + k
+    const int x0 = (s0 + lane) * 32;
+    const int nvalid = lane < kk ? (w - x0 < 32 ? w - x0 : 32) : 0;
+    const unsigned vm = valid_mask(nvalid);
+    if (lane < kk) { Wrow[s0 + lane] = mine; if (Wrow2) Wrow2[s0 + lane] = mine; }
+    unsigned prev_word = __shfl_up_sync(0xffffffffu, mine, 1);
+    const unsigned prev_bit = lane == 0 ? carry_bit : (prev_word >> 31);
+    const bool cont = (s0 + lane > 0) && nvalid > 0 && ((mine & 1u) == prev_bit);
+    const unsigned stv = run_starts(mine, nvalid) & vm;
+    const bool single = (stv & (stv - 1)) == 0;
+    int val = (nvalid == 0 || (single && cont)) ? -1 : x0 + (31 - __clz(stv));
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, val, o);
+      if (lane >= o && t > val) val = t;
+    }
+    if (val < carry_start) val = carry_start;                          // nothing defined up to here: the run comes from the previous pass
+    int before = __shfl_up_sync(0xffffffffu, val, 1);
+    if (lane == 0) before = carry_start;
+    const int first_start = cont ? before : x0;                        // start of the row run the word's FIRST segment run belongs to
+    // ---- labels (lane = pixel again) and the byte bitmap
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int fs = __shfl_sync(0xffffffffu, first_start, k);
+      if (k < kk) {
+        const int xk = (s0 + k) * 32;
+        const int nv = w - xk < 32 ? w - xk : 32;
+        if (lane < nv) {
+          const unsigned st = run_starts(cw[k], nv) & ((2u << lane) - 1u);
+          const int a = 31 - __clz(st);
+          Lrow[xk + lane] = label_base + (a == 0 ? fs : xk + a);
+          if (!word_stores) Brow[xk + lane] = (cw[k] >> lane) & 1u;
+        }
+      }
+    }
+    if (word_stores) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {                                    // 4 words = 128 pixels = one 128-byte store per warp
+        const unsigned wv = __shfl_sync(0xffffffffu, mine, 4 * q + (lane >> 3));
+        const int x = (s0 + 4 * q) * 32 + 4 * lane;
+        if (4 * q < kk && x < w) {
+          const unsigned nib = (wv >> ((lane & 7) * 4)) & 0xfu;
+          *reinterpret_cast<unsigned*>(Brow + x) = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+        }
+      }
+    }
+    carry_start = __shfl_sync(0xffffffffu, val, kk - 1);
+    carry_bit = __shfl_sync(0xffffffffu, mine, kk - 1) >> 31;
+  }
+}
 __global__ void __launch_bounds__(CCL_THREADS)
 ccl_pack_init_kernel(const float* __restrict__ pred, int c, int n, int h, int w, int wq, float thresh, uint8_t* __restrict__ bitmap,
                      unsigned* __restrict__ bits, int* __restrict__ label, int word_stores) {
@@ -115,77 +186,9 @@ ccl_pack_init_kernel(const float* __restrict__ pred, int c, int n, int h, int w,
   const int wstride = gridDim.x * (CCL_THREADS / 32);
   for (int row = blockIdx.x * (CCL_THREADS / 32) + (threadIdx.x >> 5); row < nrows; row += wstride) {
     const int img = row / h, y = row - img * h;
-    const float* P = pred + (int64_t)img * c * hw + (int64_t)y * w;
-    int* Lrow = label + img * (hw + 1) + (int64_t)y * w;
-    uint8_t* Brow = bitmap + img * hw + (int64_t)y * w;
-    unsigned* Wrow = bits + (int64_t)row * wq;
     if (y == 0 && lane == 0) label[img * (hw + 1) + hw] = (int)hw;       // virtual outside node
-    int carry_start = -1;            // start (x) of the row run that reaches the end of the previous pass
-    unsigned carry_bit = 0;          // class of the last pixel of the previous pass
-    for (int s0 = 0; s0 < wq; s0 += 32) {
-      const int kk = wq - s0 < 32 ? wq - s0 : 32;
-      float v[32];
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const int x = (s0 + k) * 32 + lane;
-        v[k] = (k < kk && x < w) ? __ldg(P + x) : 0.f;
-      }
-      unsigned cw[32];
-      unsigned mine = 0;
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        cw[k] = __ballot_sync(0xffffffffu, v[k] > thresh);               // lanes beyond the row hold 0 -> bit 0
-        if (lane == k) mine = cw[k];
-      }
-      // ---- lane k owns word s0 + k
-      const int x0 = (s0 + lane) * 32;
-      const int nvalid = lane < kk ? (w - x0 < 32 ? w - x0 : 32) : 0;
-      const unsigned vm = valid_mask(nvalid);
-      if (lane < kk) Wrow[s0 + lane] = mine;
-      unsigned prev_word = __shfl_up_sync(0xffffffffu, mine, 1);
-      const unsigned prev_bit = lane == 0 ? carry_bit : (prev_word >> 31);
-      const bool cont = (s0 + lane > 0) && nvalid > 0 && ((mine & 1u) == prev_bit);
-      const unsigned stv = run_starts(mine, nvalid) & vm;
-      const bool single = (stv & (stv - 1)) == 0;
-      int val = (nvalid == 0 || (single && cont)) ? -1 : x0 + (31 - __clz(stv));
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, val, o);
-        if (lane >= o && t > val) val = t;
-      }
-      if (val < carry_start) val = carry_start;                          // nothing defined up to here: the run comes from the previous pass
-      int before = __shfl_up_sync(0xffffffffu, val, 1);
-      if (lane == 0) before = carry_start;
-      const int first_start = cont ? before : x0;                        // start of the row run the word's FIRST segment run belongs to
-      // ---- labels (lane = pixel again) and the byte bitmap
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const int fs = __shfl_sync(0xffffffffu, first_start, k);
-        if (k < kk) {
-          const int xk = (s0 + k) * 32;
-          const int nv = w - xk < 32 ? w - xk : 32;
-          if (lane < nv) {
-            const unsigned st = run_starts(cw[k], nv) & ((2u << lane) - 1u);
-            const int a = 31 - __clz(st);
-            Lrow[xk + lane] = y * w + (a == 0 ? fs : xk + a);
-            if (!word_stores) Brow[xk + lane] = (cw[k] >> lane) & 1u;
-          }
-        }
-      }
-      if (word_stores) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {                                    // 4 words = 128 pixels = one 128-byte store per warp
-          const unsigned wv = __shfl_sync(0xffffffffu, mine, 4 * q + (lane >> 3));
-          const int x = (s0 + 4 * q) * 32 + 4 * lane;
-          if (4 * q < kk && x < w) {
-            const unsigned nib = (wv >> ((lane & 7) * 4)) & 0xfu;
-            *reinterpret_cast<unsigned*>(Brow + x) = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
-          }
-        }
-      }
-      carry_start = __shfl_sync(0xffffffffu, val, kk - 1);
-      carry_bit = __shfl_sync(0xffffffffu, mine, kk - 1) >> 31;
-    }
+    pack_row(pred + (int64_t)img * c * hw + (int64_t)y * w, w, wq, thresh, label + img * (hw + 1) + (int64_t)y * w, y * w,
+             bitmap + img * hw + (int64_t)y * w, bits + (int64_t)row * wq, nullptr, word_stores, lane);
   }
 }
 
@@ -194,29 +197,25 @@ ccl_pack_init_kernel(const float* __restrict__ pred, int c, int n, int h, int w,
 // ONE THREAD PER 32-PIXEL WORD: the neighbourhood masks are a dozen word operations computed once, and the thread then walks
 // the set bits (typically 0-2 unions per word).  The first version gave every pixel a lane that recomputed the same masks and
 // diverged on its own union: 30 warp-instructions per pixel at 5.7 active lanes (ncu, profiles/prof_ccl_r02.md) -- issue-bound.
-__device__ __forceinline__ void link_word(const unsigned* __restrict__ bits, int64_t widx, int h, int w, int wq, int* __restrict__ label, int phase) {
-  const int64_t hw = (int64_t)h * w;
-  Seg g; seg_of(widx, h, wq, w, g);
-  // two-level merge keeps union-find chains short: phase 0 links everything except across the boundaries of
-  // 32-row strips (chains <= 32), the strips are flattened, phase 1 links the strip boundaries (chains <= H/32)
-  const bool strip_edge = (g.y & 31) == 0;
-  int* L = label + g.img * (hw + 1);
-  const unsigned cur = bits[widx];
-  const unsigned prv = g.s > 0 ? bits[widx - 1] : 0u, nxt = g.s < wq - 1 ? bits[widx + 1] : 0u;
-  const bool has_up = g.y > 0 && (phase == 1 || !strip_edge);
-  const unsigned vm = valid_mask(g.nvalid);
-  const int i0 = g.y * w + g.x0;
-  if (has_up) {
-    const unsigned up = bits[widx - wq];
-    const unsigned upp = g.s > 0 ? bits[widx - wq - 1] : 0u, upn = g.s < wq - 1 ? bits[widx - wq + 1] : 0u;
+// B points at the word itself: B[-1] / B[1] are its row neighbours, B[-wq] the word above (global bits and the strip kernel's
+// shared copy have the same layout).  i0 = index of the word's first pixel in L's index space (row pitch w), out_node = index
+// of the virtual outside node there.  vertical: link with the row above; frame: horizontal-frame / outside unions.
+__device__ __forceinline__ void link_core(const unsigned* B, int s, int wq, int w, int nvalid, bool vertical, bool frame, bool frame_row,
+                                          int* L, int i0, int out_node) {
+  const unsigned cur = B[0];
+  const unsigned prv = s > 0 ? B[-1] : 0u, nxt = s < wq - 1 ? B[1] : 0u;
+  const unsigned vm = valid_mask(nvalid);
+  if (vertical) {
+    const unsigned up = B[-wq];
+    const unsigned upp = s > 0 ? B[-wq - 1] : 0u, upn = s < wq - 1 ? B[-wq + 1] : 0u;
     // neighbours shifted into lane position: L = pixel x-1, R = pixel x+1
     const unsigned curL = (cur << 1) | (prv >> 31), curR = (cur >> 1) | (nxt << 31);
     const unsigned upL = (up << 1) | (upp >> 31), upR = (up >> 1) | (upn << 31);
-    const unsigned hasL = g.s > 0 ? 0xffffffffu : 0xfffffffeu;                         // pixel x-1 exists
+    const unsigned hasL = s > 0 ? 0xffffffffu : 0xfffffffeu;                         // pixel x-1 exists
     unsigned V = cur & up & ~(curL & upL & hasL);            // first column of a vertical overlap
     unsigned DL = cur & ~up & upL & ~curL & hasL;            // diagonal up-left, not implied by a neighbour
     unsigned DR = cur & ~up & upR & ~curR;                   // diagonal up-right (bits beyond the row end are 0)
-    if (g.s == wq - 1 && g.nvalid >= 1) DR &= ~(1u << (g.nvalid - 1));     // x + 1 < w
+    if (s == wq - 1 && nvalid >= 1) DR &= ~(1u << (nvalid - 1));     // x + 1 < w
     while (V) { const int b = __ffs(V) - 1; V &= V - 1; uf_union(L, i0 + b, i0 + b - w); }
     while (DL) { const int b = __ffs(DL) - 1; DL &= DL - 1; uf_union(L, i0 + b, i0 + b - w - 1); }
     while (DR) { const int b = __ffs(DR) - 1; DR &= DR - 1; uf_union(L, i0 + b, i0 + b - w + 1); }
@@ -224,34 +223,106 @@ __device__ __forceinline__ void link_word(const unsigned* __restrict__ bits, int
     unsigned VB = ncur & ~up & ~(~curL & ~upL & hasL);       // background: vertical links only (4-connectivity)
     while (VB) { const int b = __ffs(VB) - 1; VB &= VB - 1; uf_union(L, i0 + b, i0 + b - w); }
   }
-  if (phase != 0) return;
-  // (no horizontal unions: ccl_pack_init labels every pixel with the start of its ROW run)
+  if (!frame) return;
+  // (no horizontal unions: pack_row labels every pixel with the start of its ROW run)
   // frame pixels of the background belong to the outside region: one union per background run start on the first / last
   // row, the first / last pixel of every other row
   const unsigned ncur = ~cur & vm;
-  if (g.y == 0 || g.y == h - 1) {
-    unsigned st = run_starts(cur, g.nvalid) & ncur;
-    while (st) { const int b = __ffs(st) - 1; st &= st - 1; uf_union(L, (int)hw, i0 + b); }
+  if (frame_row) {
+    unsigned st = run_starts(cur, nvalid) & ncur;
+    while (st) { const int b = __ffs(st) - 1; st &= st - 1; uf_union(L, out_node, i0 + b); }
   } else {
-    if (g.s == 0 && (ncur & 1u)) uf_union(L, (int)hw, i0);
+    if (s == 0 && (ncur & 1u)) uf_union(L, out_node, i0);
   }
-  if (g.s == wq - 1 && ((ncur >> (g.nvalid - 1)) & 1u)) uf_union(L, (int)hw, i0 + g.nvalid - 1);
+  if (s == wq - 1 && ((ncur >> (nvalid - 1)) & 1u)) uf_union(L, out_node, i0 + nvalid - 1);
 }
+// two-level merge keeps union-find chains short: phase 0 links everything except across the boundaries of strips of `sh`
+// rows (chains <= sh), the strips are flattened, phase 1 links the strip boundaries (chains <= H / sh)
+__device__ __forceinline__ void link_word(const unsigned* __restrict__ bits, int64_t widx, int h, int w, int wq, int* __restrict__ label, int phase, int sh) {
+  const int64_t hw = (int64_t)h * w;
+  Seg g; seg_of(widx, h, wq, w, g);
+  const bool strip_edge = (g.y % sh) == 0;
+  link_core(bits + widx, g.s, wq, w, g.nvalid, g.y > 0 && (phase == 1 || !strip_edge), phase == 0, g.y == 0 || g.y == h - 1,
+            label + g.img * (hw + 1), g.y * w + g.x0, (int)hw);
+}
+// phase 0: every word.  phase 1: only the first row of every strip (except row 0); strip_out (strip kernel path): the root each
+// strip found for its frame background, to be joined with the image's outside node.
 __global__ void __launch_bounds__(CCL_THREADS)
-ccl_link_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, int* __restrict__ label, int phase) {
+ccl_link_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, int* __restrict__ label, int phase, int sh,
+                const int* __restrict__ strip_out) {
   const int64_t stride = (int64_t)gridDim.x * CCL_THREADS;
   if (phase == 0) {
     const int64_t nseg = (int64_t)n * h * wq;
-    for (int64_t widx = (int64_t)blockIdx.x * CCL_THREADS + threadIdx.x; widx < nseg; widx += stride) link_word(bits, widx, h, w, wq, label, 0);
+    for (int64_t widx = (int64_t)blockIdx.x * CCL_THREADS + threadIdx.x; widx < nseg; widx += stride) link_word(bits, widx, h, w, wq, label, 0, sh);
   } else {
-    // only the first row of every 32-row strip (except row 0) takes part
-    const int nedge = (h - 1) / 32;                          // rows 32, 64, ...
+    const int nedge = (h - 1) / sh;                          // rows sh, 2 sh, ...
     const int64_t total = (int64_t)n * nedge * wq;
     for (int64_t t = (int64_t)blockIdx.x * CCL_THREADS + threadIdx.x; t < total; t += stride) {
       const int s = (int)(t % wq); const int64_t q = t / wq;
       const int e = (int)(q % nedge), img = (int)(q / nedge);
-      link_word(bits, ((int64_t)img * h + (int64_t)(e + 1) * 32) * wq + s, h, w, wq, label, 1);
+      link_word(bits, ((int64_t)img * h + (int64_t)(e + 1) * sh) * wq + s, h, w, wq, label, 1, sh);
     }
+    if (strip_out) {
+      const int nstrips = (h + sh - 1) / sh;
+      const int64_t hw = (int64_t)h * w;
+      for (int64_t t = (int64_t)blockIdx.x * CCL_THREADS + threadIdx.x; t < (int64_t)n * nstrips; t += stride) {
+        const int r = strip_out[t];
+        if (r >= 0) uf_union(label + (t / nstrips) * (hw + 1), (int)hw, r);
+      }
+    }
+  }
+}
+
+// A+B+C for one strip of STRIP_ROWS rows in ONE kernel: the strip's labels live in shared memory while its runs are linked
+// (a union-find hop costs ~30 cycles there instead of an L2 / DRAM round trip), and leave the SM already flattened:
+// every pixel is written once, carrying the strip-local root.  Replaces pack_init + link (phase 0) + flatten (strips):
+// 0.55 ms -> see profiles/prof_ccl_r02.md for 64 x 1024^2.
+constexpr int STRIP_ROWS = 16;
+constexpr int STRIP_THREADS = 512;
+__global__ void __launch_bounds__(STRIP_THREADS)
+ccl_strip_kernel(const float* __restrict__ pred, int c, int n, int h, int w, int wq, float thresh, uint8_t* __restrict__ bitmap,
+                 unsigned* __restrict__ bits, int* __restrict__ label, int* __restrict__ strip_out, int word_stores) {
+  extern __shared__ int strip_smem[];
+  int* sl = strip_smem;                                             // [STRIP_ROWS * w + 1] strip-local labels
+  unsigned* sb = (unsigned*)(strip_smem + STRIP_ROWS * w + 1);      // [STRIP_ROWS * wq]    the strip's words
+  const int64_t hw = (int64_t)h * w;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int nstrips = (h + STRIP_ROWS - 1) / STRIP_ROWS;
+  for (int sid = blockIdx.x; sid < n * nstrips; sid += gridDim.x) {
+    const int img = sid / nstrips, y0 = (sid - img * nstrips) * STRIP_ROWS;
+    const int rows = h - y0 < STRIP_ROWS ? h - y0 : STRIP_ROWS;
+    const int out_node = rows * w;
+    int* Lg = label + img * (hw + 1);
+    // ---- A: binarize + pack + row-run labels
+    for (int r = wrp; r < rows; r += STRIP_THREADS / 32)
+      pack_row(pred + (int64_t)img * c * hw + (int64_t)(y0 + r) * w, w, wq, thresh, sl + r * w, r * w,
+               bitmap + img * hw + (int64_t)(y0 + r) * w, bits + ((int64_t)img * h + y0 + r) * wq, sb + r * wq, word_stores, lane);
+    if (threadIdx.x == 0) { sl[out_node] = out_node; if (y0 == 0) Lg[hw] = (int)hw; }
+    __syncthreads();
+    // ---- B: unions inside the strip
+    for (int t = threadIdx.x; t < rows * wq; t += STRIP_THREADS) {
+      const int r = t / wq, sw = t - r * wq;
+      const int x0 = sw * 32;
+      const int y = y0 + r;
+      link_core(sb + t, sw, wq, w, w - x0 < 32 ? w - x0 : 32, r > 0, true, y == 0 || y == h - 1, sl, r * w + x0, out_node);
+    }
+    __syncthreads();
+    // ---- C: segment run starts -> strip root, then every pixel -> root of its run start, written out once
+    for (int t = threadIdx.x; t < rows * wq; t += STRIP_THREADS) {
+      const int r = t / wq, sw = t - r * wq;
+      const int x0 = sw * 32;
+      const int nvalid = w - x0 < 32 ? w - x0 : 32;
+      unsigned st = run_starts(sb[t], nvalid) & valid_mask(nvalid);
+      while (st) { const int b = __ffs(st) - 1; st &= st - 1; const int i = r * w + x0 + b; sl[i] = uf_find(sl, i); }
+    }
+    __syncthreads();
+    const int base = y0 * w;
+    for (int i = threadIdx.x; i < rows * w; i += STRIP_THREADS) Lg[base + i] = base + sl[sl[i]];
+    if (threadIdx.x == 0) {
+      const int ro = uf_find(sl, out_node);
+      strip_out[sid] = ro != out_node ? base + ro : -1;
+    }
+    __syncthreads();                                                // the next strip reuses the arrays
   }
 }
 
@@ -312,7 +383,7 @@ __device__ __forceinline__ unsigned inner_bg(unsigned word, unsigned touch, int 
     const unsigned later = b >= 31 ? 0u : (st & ~((2u << b) - 1u));
     const int e = later ? (__ffs(later) - 2) : 31;
     const unsigned m = run_mask(a, e);
-    if (root2(L, ibase + a) != r_out) out |= m;
+    if (L[ibase + a] != r_out) out |= m;                  // a is the start of a segment run: one hop
     cand &= ~m;
   }
   return out;
@@ -323,7 +394,7 @@ __device__ __forceinline__ unsigned inner_bg(unsigned word, unsigned touch, int 
 // for 64 x 1024^2, the busiest L2 slice 32 % occupied by its atomic unit, 0.62 of the kernel's 0.97 ms.)
 constexpr int AGG_N = 256;
 constexpr int STATS_WORDS_PER_BLOCK = 2048;
-struct AggEntry { unsigned long long key; double sum; int count, x0, x1, y1; };
+struct AggEntry { unsigned long long key; double sum, acc_sum; int count, x0, x1, y1, acc_count, pad; };
 constexpr unsigned long long AGG_EMPTY = ~0ull;
 __device__ __forceinline__ void stat_add_global(CompStat* t, double sum, int count, int xa, int xb, int y) {
   atomicAdd(&t->sum, sum);
@@ -345,6 +416,22 @@ __device__ __forceinline__ void agg_add(AggEntry* agg, CompStat* stat, unsigned 
   }
   stat_add_global(stat + key, sum, count, xa, xb, y);       // table full around this hash: straight to the slot
 }
+// hole-ring contributions (acc_sum / acc_count of the hole's slot) through the same table
+__device__ __forceinline__ void agg_add_ring(AggEntry* agg, CompStat* stat, unsigned long long key, double sum, int count) {
+  const unsigned hsh = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 40);
+#pragma unroll 1
+  for (int probe = 0; probe < 4; ++probe) {
+    AggEntry* e = agg + ((hsh + probe) & (AGG_N - 1));
+    const unsigned long long old = atomicCAS(&e->key, AGG_EMPTY, key);
+    if (old == AGG_EMPTY || old == key) {
+      atomicAdd(&e->acc_sum, sum);
+      atomicAdd(&e->acc_count, count);
+      return;
+    }
+  }
+  atomicAdd(&stat[key].acc_sum, sum);
+  atomicAdd(&stat[key].acc_count, count);
+}
 __global__ void __launch_bounds__(CCL_THREADS)
 ccl_stats_kernel(const float* __restrict__ pred, int c, const unsigned* __restrict__ bits, int n, int h, int w, int wq,
                  const int* __restrict__ label, CompStat* __restrict__ stat, int dbg) {
@@ -354,7 +441,7 @@ ccl_stats_kernel(const float* __restrict__ pred, int c, const unsigned* __restri
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   const int64_t nseg = (int64_t)n * h * wq;
   float* T = tile[wrp];
-  for (int t = threadIdx.x; t < AGG_N; t += CCL_THREADS) { AggEntry z; z.key = AGG_EMPTY; z.sum = 0.0; z.count = 0; z.x0 = 0x7fffffff; z.x1 = -1; z.y1 = -1; agg[t] = z; }
+  for (int t = threadIdx.x; t < AGG_N; t += CCL_THREADS) { AggEntry z; z.key = AGG_EMPTY; z.sum = 0.0; z.acc_sum = 0.0; z.count = 0; z.x0 = 0x7fffffff; z.x1 = -1; z.y1 = -1; z.acc_count = 0; z.pad = 0; agg[t] = z; }
   __syncthreads();
   const int64_t range0 = (int64_t)blockIdx.x * STATS_WORDS_PER_BLOCK;
   const int64_t range1 = range0 + STATS_WORDS_PER_BLOCK < nseg ? range0 + STATS_WORDS_PER_BLOCK : nseg;
@@ -374,18 +461,14 @@ ccl_stats_kernel(const float* __restrict__ pred, int c, const unsigned* __restri
     const bool has_fg = (cur & vm) != 0;
     const unsigned prv = has_fg && g.s > 0 ? bits[widx - 1] : 0xffffffffu, nxt = has_fg && g.s < wq - 1 ? bits[widx + 1] : 0xffffffffu;
     const unsigned up = has_fg && g.y > 0 ? (bits[widx - wq] | ~vm) : 0xffffffffu, dn = has_fg && g.y < h - 1 ? (bits[widx + wq] | ~vm) : 0xffffffffu;
-    // roots of the first four runs, looked up together (two dependent loads each; doing them one by one at the run ends
-    // made the whole warp wait 2 x L2 latency per run end: 82 % of the stall samples, profiles/prof_ccl_r02.md)
+    // roots of the first four runs, looked up together
     int ra[4], rr[4];
     {
       unsigned m = st;
-      int l1[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) { ra[k] = m ? __ffs(m) - 1 : -1; m &= m - 1; }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) l1[k] = (live && ra[k] >= 0) ? L[i0 + ra[k]] : -1;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) rr[k] = l1[k] >= 0 ? L[l1[k]] : r_out;
+      for (int k = 0; k < 4; ++k) rr[k] = (live && ra[k] >= 0) ? L[i0 + ra[k]] : r_out;      // a segment run start holds its root (final flatten)
     }
     const int nruns = __popc(st);
     const bool need = live && (nruns > 4 || rr[0] != r_out || rr[1] != r_out || rr[2] != r_out || rr[3] != r_out);
@@ -423,7 +506,7 @@ ccl_stats_kernel(const float* __restrict__ pred, int c, const unsigned* __restri
 #pragma unroll
             for (int q = 0; q < 4; ++q) if (q == k) { sums[q] = acc; ends[q] = j; }
           } else {                                   // fifth and later runs of a word (noise): looked up on the spot
-            const int r = root2(L, i0 + a);
+            const int r = L[i0 + a];
             if (r != r_out) {
               agg_add(agg, stat, (unsigned long long)(g.img * hw + r), acc, j - a + 1, g.x0 + a, g.x0 + j, g.y);
               if (!((cur >> a) & 1u)) inner_cur |= run_mask(a, j);
@@ -450,21 +533,28 @@ ccl_stats_kernel(const float* __restrict__ pred, int c, const unsigned* __restri
     if (!(fg & (~curL | ~curR | ~up | ~dn))) continue;                        // interior word
     // background runs around the word that are NOT the outside region
     unsigned innL = inner_cur << 1, innR = inner_cur >> 1;
-    if ((fg & 1u) && !(prv >> 31) && root2(L, i0 - 1) != r_out) innL |= 1u;
-    if ((fg >> 31) && !(nxt & 1u) && root2(L, i0 + 32) != r_out) innR |= 0x80000000u;
+    const int prv_start = 31 - __clz(run_starts(prv, 32));                    // start of the run that ends the previous word
+    if ((fg & 1u) && !(prv >> 31) && L[i0 - 32 + prv_start] != r_out) innL |= 1u;
+    if ((fg >> 31) && !(nxt & 1u) && L[i0 + 32] != r_out) innR |= 0x80000000u;
     const unsigned innU = (fg & ~up) ? inner_bg(up, fg, nv_up, L, i0 - w, r_out) : 0u;
     const unsigned innD = (fg & ~dn) ? inner_bg(dn, fg, nv_up, L, i0 + w, r_out) : 0u;
     unsigned slow = fg & (innL | innR | innU | innD);
+    if (!slow) continue;
+    const unsigned stU = run_starts(up, nv_up), stD = run_starts(dn, nv_up);
+    // consecutive ring pixels mostly feed the same hole: keep one pending (region, sum, count) per thread
+    long long pend_key = -1; double pend_sum = 0.0; int pend_cnt = 0;
+    int last_r = -1, last_pr = -1;
     while (slow) {
       const int b = __ffs(slow) - 1; slow &= slow - 1;
-      const int i = i0 + b;
-      const int r = root2(L, i);
-      const int pr = parent_of(L, r, w, r_out);
+      const unsigned upto = (2u << b) - 1u;
+      const int r = L[i0 + 31 - __clz(st & upto)];
+      if (r != last_r) { last_r = r; last_pr = parent_of(L, r, w, r_out); }
+      const int pr = last_pr;
       int gq[4] = {-1, -1, -1, -1};
-      if ((innL >> b) & 1u) gq[0] = root2(L, i - 1);
-      if ((innR >> b) & 1u) gq[1] = root2(L, i + 1);
-      if ((innU >> b) & 1u) gq[2] = root2(L, i - w);
-      if ((innD >> b) & 1u) gq[3] = root2(L, i + w);
+      if ((innL >> b) & 1u) gq[0] = b > 0 ? L[i0 + 31 - __clz(st & (upto >> 1))] : L[i0 - 32 + prv_start];
+      if ((innR >> b) & 1u) gq[1] = L[i0 + b + 1];                       // the right neighbour of a run end starts a run
+      if ((innU >> b) & 1u) gq[2] = L[i0 - w + 31 - __clz(stU & upto)];
+      if ((innD >> b) & 1u) gq[3] = L[i0 + w + 31 - __clz(stD & upto)];
       const double p = (double)row[b];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -474,16 +564,23 @@ ccl_stats_kernel(const float* __restrict__ pred, int c, const unsigned* __restri
 #pragma unroll
         for (int q = 0; q < 4; ++q) if (q < k && gq[q] == gk) dup = true;
         if (dup) continue;
-        atomicAdd(&S[gk].acc_sum, p);
-        atomicAdd(&S[gk].acc_count, 1);
+        const long long key = (long long)(g.img * hw + gk);
+        if (key != pend_key) {
+          if (pend_cnt) agg_add_ring(agg, stat, (unsigned long long)pend_key, pend_sum, pend_cnt);
+          pend_key = key; pend_sum = 0.0; pend_cnt = 0;
+        }
+        pend_sum += p; ++pend_cnt;
       }
     }
+    if (pend_cnt) agg_add_ring(agg, stat, (unsigned long long)pend_key, pend_sum, pend_cnt);
   }
   // ---- one atomic set per region and block
   __syncthreads();
   for (int t = threadIdx.x; t < AGG_N; t += CCL_THREADS) {
     const AggEntry e = agg[t];
-    if (e.key != AGG_EMPTY) stat_add_global(stat + e.key, e.sum, e.count, e.x0, e.x1, e.y1);
+    if (e.key == AGG_EMPTY) continue;
+    if (e.count) stat_add_global(stat + e.key, e.sum, e.count, e.x0, e.x1, e.y1);
+    if (e.acc_count) { atomicAdd(&stat[e.key].acc_sum, e.acc_sum); atomicAdd(&stat[e.key].acc_count, e.acc_count); }
   }
 }
 
@@ -775,19 +872,35 @@ extern "C" int dbb_binarize_ccl_score(const float* pred, int64_t n, int c, int64
   const int nblk = ccl_nblk(hw);
   int gx = nblk < DBB_NUM_SMS * 8 ? nblk : DBB_NUM_SMS * 8;
   const dim3 grid((unsigned)gx, (unsigned)n), gridb((unsigned)nblk, (unsigned)n);
-  DBB_LAUNCH("ccl_pack_init", s, ccl_pack_init_kernel<<<grow, CCL_THREADS, 0, s>>>(pred, c, (int)n, (int)h, (int)w, wq, thresh, bitmap, ws.bits, ws.label,
-                                                                                          (w % 4 == 0 && ((uintptr_t)bitmap & 3) == 0) ? 1 : 0));
   // thread-per-word kernels
   int gword = (int)((nseg + CCL_THREADS - 1) / CCL_THREADS);
   if (gword > DBB_NUM_SMS * 8) gword = DBB_NUM_SMS * 8;
-  DBB_LAUNCH("ccl_link", s, ccl_link_kernel<<<gword, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, 0));
-  if (h > 32) {
-    const int64_t nedge_words = n * ((h - 1) / 32) * wq;
+  const int word_stores = (w % 4 == 0 && ((uintptr_t)bitmap & 3) == 0) ? 1 : 0;
+  const size_t strip_smem = sizeof(int) * ((size_t)STRIP_ROWS * w + 1 + (size_t)STRIP_ROWS * wq);
+  const bool fused = w >= 16 && strip_smem <= 200 * 1024 && !getenv("DBB_CCL_NO_STRIP");
+  const int sh = fused ? STRIP_ROWS : 32;                    // strip height of the two-level merge
+  if (fused) {
+    // strips labelled in shared memory (pack + link + flatten in one pass over the probabilities)
+    static size_t attr_set = 0;
+    if (strip_smem > attr_set) {
+      DBB_CUDA(cudaFuncSetAttribute(ccl_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)strip_smem));
+      attr_set = strip_smem;
+    }
+    const int64_t nstrips = n * ((h + STRIP_ROWS - 1) / STRIP_ROWS);
+    const int gstrip = (int)(nstrips < (int64_t)DBB_NUM_SMS * 64 ? nstrips : (int64_t)DBB_NUM_SMS * 64);
+    DBB_LAUNCH("ccl_strip", s, ccl_strip_kernel<<<gstrip, STRIP_THREADS, strip_smem, s>>>(pred, c, (int)n, (int)h, (int)w, wq, thresh, bitmap, ws.bits, ws.label,
+                                                                                      ws.blk_count, word_stores));
+  } else {
+    DBB_LAUNCH("ccl_pack_init", s, ccl_pack_init_kernel<<<grow, CCL_THREADS, 0, s>>>(pred, c, (int)n, (int)h, (int)w, wq, thresh, bitmap, ws.bits, ws.label, word_stores));
+    DBB_LAUNCH("ccl_link", s, ccl_link_kernel<<<gword, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, 0, sh, nullptr));
+    if (h > sh) DBB_LAUNCH("ccl_flatten_strips", s, ccl_flatten_kernel<<<gword, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, 0, ws.rootbits));
+  }
+  if (h > sh || fused) {
+    const int64_t nedge_words = n * ((h - 1) / sh) * wq;
     int gedge = (int)((nedge_words + CCL_THREADS - 1) / CCL_THREADS);
     if (gedge > DBB_NUM_SMS * 8) gedge = DBB_NUM_SMS * 8;
     if (gedge < 1) gedge = 1;
-    DBB_LAUNCH("ccl_flatten", s, ccl_flatten_kernel<<<gword, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, 0, ws.rootbits));
-    DBB_LAUNCH("ccl_link", s, ccl_link_kernel<<<gedge, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, 1));
+    DBB_LAUNCH("ccl_link_seams", s, ccl_link_kernel<<<gedge, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, 1, sh, fused ? ws.blk_count : nullptr));
   }
   DBB_LAUNCH("ccl_flatten", s, ccl_flatten_kernel<<<gword, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, 1, ws.rootbits));
   DBB_LAUNCH("ccl_stats", s, ccl_stats_kernel<<<(unsigned)((nseg + STATS_WORDS_PER_BLOCK - 1) / STATS_WORDS_PER_BLOCK), CCL_THREADS, 0, s>>>(pred, c, ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, getenv("DBB_CCL_DBG") ? atoi(getenv("DBB_CCL_DBG")) : 0));
