@@ -31,7 +31,8 @@ struct CompStat {          // one slot per pixel index, touched only at roots
   double sum;              // own pixels
   double acc_sum;          // descendants (+ boundary ring for holes)
   int count, acc_count;
-  int x0, y0, x1, y1;
+  int x0, parent, x1, y1;  // bounding box without y0 (the root is the raster-first pixel: its row IS y0); parent = root of
+                           // the region north of the root pixel (written by the final flatten)
 };
 
 struct CclWs {
@@ -346,7 +347,8 @@ ccl_flatten_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int w
       if (r == i && init_stats) {
         CompStat z;
         z.sum = 0.0; z.acc_sum = 0.0; z.count = 0; z.acc_count = 0;
-        z.x0 = w; z.y0 = i / w; z.x1 = -1; z.y1 = -1;      // the root is the raster-first pixel: its row IS y0
+        z.x0 = w; z.x1 = -1; z.y1 = -1;
+        z.parent = uf_find(L, i < w ? (int)hw : i - w);   // all unions are done: uf_find is final whatever the flatten has reached
         stat[g.img * hw + i] = z;
         roots |= 1u << b;
       }
@@ -392,8 +394,8 @@ __device__ __forceinline__ unsigned inner_bg(unsigned word, unsigned touch, int 
 // 1,024-pixel image), so the runs of one region that fall into the range are summed in a small shared-memory hash table
 // and reach the region's global slot as ONE atomic set per block instead of one per run.  (Direct atomics: 19 M RED requests
 // for 64 x 1024^2, the busiest L2 slice 32 % occupied by its atomic unit, 0.62 of the kernel's 0.97 ms.)
-constexpr int AGG_N = 256;
-constexpr int STATS_WORDS_PER_BLOCK = 2048;
+constexpr int AGG_N = 128;
+constexpr int STATS_WORDS_PER_BLOCK = 1024;
 struct AggEntry { unsigned long long key; double sum, acc_sum; int count, x0, x1, y1, acc_count, pad; };
 constexpr unsigned long long AGG_EMPTY = ~0ull;
 __device__ __forceinline__ void stat_add_global(CompStat* t, double sum, int count, int xa, int xb, int y) {
@@ -432,7 +434,7 @@ __device__ __forceinline__ void agg_add_ring(AggEntry* agg, CompStat* stat, unsi
   atomicAdd(&stat[key].acc_sum, sum);
   atomicAdd(&stat[key].acc_count, count);
 }
-__global__ void __launch_bounds__(CCL_THREADS)
+__global__ void __launch_bounds__(CCL_THREADS, 4)
 ccl_stats_kernel(const float* __restrict__ pred, int c, const unsigned* __restrict__ bits, int n, int h, int w, int wq,
                  const int* __restrict__ label, CompStat* __restrict__ stat, int dbg) {
   __shared__ float tile[CCL_THREADS / 32][32 * 33];
@@ -548,7 +550,7 @@ ccl_stats_kernel(const float* __restrict__ pred, int c, const unsigned* __restri
       const int b = __ffs(slow) - 1; slow &= slow - 1;
       const unsigned upto = (2u << b) - 1u;
       const int r = L[i0 + 31 - __clz(st & upto)];
-      if (r != last_r) { last_r = r; last_pr = parent_of(L, r, w, r_out); }
+      if (r != last_r) { last_r = r; last_pr = S[r].parent; }
       const int pr = last_pr;
       int gq[4] = {-1, -1, -1, -1};
       if ((innL >> b) & 1u) gq[0] = b > 0 ? L[i0 + 31 - __clz(st & (upto >> 1))] : L[i0 - 32 + prv_start];
@@ -602,11 +604,11 @@ ccl_tree_kernel(int h, int w, int wq, const int* __restrict__ label, const unsig
       if (i == r_out) continue;
       const double s = S[i].sum;
       const int cnt = S[i].count;
-      int a = parent_of(L, i, w, r_out);
+      int a = S[i].parent;
       while (a != r_out) {
         atomicAdd(&S[a].acc_sum, s);
         atomicAdd(&S[a].acc_count, cnt);
-        a = parent_of(L, a, w, r_out);
+        a = S[a].parent;
       }
     }
   }
@@ -710,8 +712,8 @@ ccl_emit_kernel(const uint8_t* __restrict__ bitmap, int h, int w, int wq, const 
       DbbCandidate cd;
       cd.kind = bm[i] ? 0 : 1;
       cd.first_y = y; cd.first_x = x0 + bit;
-      if (cd.kind == 0) { cd.x0 = s.x0; cd.y0 = s.y0; cd.x1 = s.x1; cd.y1 = s.y1; }
-      else { cd.x0 = s.x0 - 1; cd.y0 = s.y0 - 1; cd.x1 = s.x1 + 1; cd.y1 = s.y1 + 1; }   // + the ring of parent pixels
+      if (cd.kind == 0) { cd.x0 = s.x0; cd.y0 = y; cd.x1 = s.x1; cd.y1 = s.y1; }
+      else { cd.x0 = s.x0 - 1; cd.y0 = y - 1; cd.x1 = s.x1 + 1; cd.y1 = s.y1 + 1; }   // + the ring of parent pixels
       cd.count = s.count + s.acc_count;
       cd.sum = s.sum + s.acc_sum;
       cd.keep = keep;
