@@ -37,7 +37,7 @@ struct CompStat {          // one slot per pixel index, touched only at roots
 
 struct CclWs {
   unsigned* bits;          // [n][h][wq]    packed bitmap, 32 pixels per word
-  int* label;              // [n][hw + 1]   (+1: virtual outside node)
+  int* label;              // [n][lab_stride(hw)]   (hw pixels + the virtual outside node at index hw, padded to 16 bytes)
   CompStat* stat;          // [n][hw]
   int* blk_count;          // [n][nblk]
   int* blk_off;            // [n][nblk]
@@ -45,6 +45,7 @@ struct CclWs {
 };
 
 __host__ __device__ inline size_t ccl_align(size_t v) { return (v + 255) / 256 * 256; }
+__host__ __device__ inline int64_t lab_stride(int64_t hw) { return (hw + 4) & ~(int64_t)3; }
 
 static int ccl_nblk(int64_t hw) { return (int)((hw + CCL_THREADS - 1) / CCL_THREADS); }
 
@@ -52,7 +53,7 @@ static CclWs ccl_carve(void* ws, int64_t n, int64_t hw, int64_t h, int64_t wq) {
   CclWs w;
   char* p = (char*)ws;
   w.bits = (unsigned*)p;    p += ccl_align(sizeof(unsigned) * (size_t)n * h * wq);
-  w.label = (int*)p;        p += ccl_align(sizeof(int) * (size_t)n * (hw + 1));
+  w.label = (int*)p;        p += ccl_align(sizeof(int) * (size_t)n * lab_stride(hw));
   w.stat = (CompStat*)p;    p += ccl_align(sizeof(CompStat) * (size_t)n * hw);
   w.blk_count = (int*)p;    p += ccl_align(sizeof(int) * (size_t)n * ccl_nblk(hw));
   w.blk_off = (int*)p;      p += ccl_align(sizeof(int) * (size_t)n * ccl_nblk(hw));
@@ -115,11 +116,18 @@ __device__ __forceinline__ void pack_row(const float* __restrict__ P, int w, int
   unsigned carry_bit = 0;          // class of the last pixel of the previous pass
   for (int s0 = 0; s0 < wq; s0 += 32) {
     const int kk = wq - s0 < 32 ? wq - s0 : 32;
+    const bool full = (s0 + 32) * 32 <= w;         // all 32 words of the pass are whole: constant offsets, no bounds tests
     float v[32];
+    if (full) {
+      const float* Pl = P + s0 * 32 + lane;
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const int x = (s0 + k) * 32 + lane;
-      v[k] = (k < kk && x < w) ? __ldg(P + x) : 0.f;
+      for (int k = 0; k < 32; ++k) v[k] = __ldg(Pl + k * 32);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int x = (s0 + k) * 32 + lane;
+        v[k] = (k < kk && x < w) ? __ldg(P + x) : 0.f;
+      }
     }
     unsigned cw[32];
     unsigned mine = 0;
@@ -149,6 +157,19 @@ __device__ __forceinline__ void pack_row(const float* __restrict__ P, int w, int
     if (lane == 0) before = carry_start;
     const int first_start = cont ? before : x0;                        // start of the row run the word's FIRST segment run belongs to
     // ---- labels (lane = pixel again) and the byte bitmap
+    if (full) {
+      int* Ll = Lrow + s0 * 32 + lane;
+      const unsigned upto = (2u << lane) - 1u;
+      const int xl = label_base + s0 * 32;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int fs = __shfl_sync(0xffffffffu, first_start, k);
+        const unsigned st = (((cw[k] ^ (cw[k] << 1)) | 1u)) & upto;
+        const int a = 31 - __clz(st);
+        Ll[k * 32] = a == 0 ? label_base + fs : xl + k * 32 + a;
+        if (!word_stores) Brow[(s0 + k) * 32 + lane] = (cw[k] >> lane) & 1u;
+      }
+    } else
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
       const int fs = __shfl_sync(0xffffffffu, first_start, k);
@@ -187,8 +208,8 @@ ccl_pack_init_kernel(const float* __restrict__ pred, int c, int n, int h, int w,
   const int wstride = gridDim.x * (CCL_THREADS / 32);
   for (int row = blockIdx.x * (CCL_THREADS / 32) + (threadIdx.x >> 5); row < nrows; row += wstride) {
     const int img = row / h, y = row - img * h;
-    if (y == 0 && lane == 0) label[img * (hw + 1) + hw] = (int)hw;       // virtual outside node
-    pack_row(pred + (int64_t)img * c * hw + (int64_t)y * w, w, wq, thresh, label + img * (hw + 1) + (int64_t)y * w, y * w,
+    if (y == 0 && lane == 0) label[img * lab_stride(hw) + hw] = (int)hw;       // virtual outside node
+    pack_row(pred + (int64_t)img * c * hw + (int64_t)y * w, w, wq, thresh, label + img * lab_stride(hw) + (int64_t)y * w, y * w,
              bitmap + img * hw + (int64_t)y * w, bits + (int64_t)row * wq, nullptr, word_stores, lane);
   }
 }
@@ -244,7 +265,7 @@ __device__ __forceinline__ void link_word(const unsigned* __restrict__ bits, int
   Seg g; seg_of(widx, h, wq, w, g);
   const bool strip_edge = (g.y % sh) == 0;
   link_core(bits + widx, g.s, wq, w, g.nvalid, g.y > 0 && (phase == 1 || !strip_edge), phase == 0, g.y == 0 || g.y == h - 1,
-            label + g.img * (hw + 1), g.y * w + g.x0, (int)hw);
+            label + g.img * lab_stride(hw), g.y * w + g.x0, (int)hw);
 }
 // phase 0: every word.  phase 1: only the first row of every strip (except row 0); strip_out (strip kernel path): the root each
 // strip found for its frame background, to be joined with the image's outside node.
@@ -268,7 +289,7 @@ ccl_link_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, 
       const int64_t hw = (int64_t)h * w;
       for (int64_t t = (int64_t)blockIdx.x * CCL_THREADS + threadIdx.x; t < (int64_t)n * nstrips; t += stride) {
         const int r = strip_out[t];
-        if (r >= 0) uf_union(label + (t / nstrips) * (hw + 1), (int)hw, r);
+        if (r >= 0) uf_union(label + (t / nstrips) * lab_stride(hw), (int)hw, r);
       }
     }
   }
@@ -282,7 +303,7 @@ constexpr int STRIP_ROWS = 16;
 constexpr int STRIP_THREADS = 512;
 __global__ void __launch_bounds__(STRIP_THREADS)
 ccl_strip_kernel(const float* __restrict__ pred, int c, int n, int h, int w, int wq, float thresh, uint8_t* __restrict__ bitmap,
-                 unsigned* __restrict__ bits, int* __restrict__ label, int* __restrict__ strip_out, int word_stores) {
+                 unsigned* __restrict__ bits, int* __restrict__ label, int* __restrict__ strip_out, unsigned* __restrict__ rootbits, int word_stores) {
   extern __shared__ int strip_smem[];
   int* sl = strip_smem;                                             // [STRIP_ROWS * w + 1] strip-local labels
   unsigned* sb = (unsigned*)(strip_smem + STRIP_ROWS * w + 1);      // [STRIP_ROWS * wq]    the strip's words
@@ -293,7 +314,7 @@ ccl_strip_kernel(const float* __restrict__ pred, int c, int n, int h, int w, int
     const int img = sid / nstrips, y0 = (sid - img * nstrips) * STRIP_ROWS;
     const int rows = h - y0 < STRIP_ROWS ? h - y0 : STRIP_ROWS;
     const int out_node = rows * w;
-    int* Lg = label + img * (hw + 1);
+    int* Lg = label + img * lab_stride(hw);
     // ---- A: binarize + pack + row-run labels
     for (int r = wrp; r < rows; r += STRIP_THREADS / 32)
       pack_row(pred + (int64_t)img * c * hw + (int64_t)(y0 + r) * w, w, wq, thresh, sl + r * w, r * w,
@@ -314,11 +335,28 @@ ccl_strip_kernel(const float* __restrict__ pred, int c, int n, int h, int w, int
       const int x0 = sw * 32;
       const int nvalid = w - x0 < 32 ? w - x0 : 32;
       unsigned st = run_starts(sb[t], nvalid) & valid_mask(nvalid);
-      while (st) { const int b = __ffs(st) - 1; st &= st - 1; const int i = r * w + x0 + b; sl[i] = uf_find(sl, i); }
+      unsigned roots = 0;
+      while (st) {
+        const int b = __ffs(st) - 1; st &= st - 1;
+        const int i = r * w + x0 + b;
+        const int rt = uf_find(sl, i);
+        sl[i] = rt;
+        if (rt == i) roots |= 1u << b;
+      }
+      rootbits[((int64_t)img * h + y0 + r) * wq + sw] = roots;      // strip roots: the only pixels the final flatten has to visit
     }
     __syncthreads();
     const int base = y0 * w;
-    for (int i = threadIdx.x; i < rows * w; i += STRIP_THREADS) Lg[base + i] = base + sl[sl[i]];
+    if ((w & 3) == 0) {                                             // label rows are 16-byte aligned (lab_stride)
+      for (int i = threadIdx.x * 4; i < rows * w; i += STRIP_THREADS * 4) {
+        const int4 l = *reinterpret_cast<const int4*>(sl + i);
+        int4 o;
+        o.x = base + sl[l.x]; o.y = base + sl[l.y]; o.z = base + sl[l.z]; o.w = base + sl[l.w];
+        *reinterpret_cast<int4*>(Lg + base + i) = o;
+      }
+    } else {
+      for (int i = threadIdx.x; i < rows * w; i += STRIP_THREADS) Lg[base + i] = base + sl[sl[i]];
+    }
     if (threadIdx.x == 0) {
       const int ro = uf_find(sl, out_node);
       strip_out[sid] = ro != out_node ? base + ro : -1;
@@ -330,20 +368,22 @@ ccl_strip_kernel(const float* __restrict__ pred, int c, int n, int h, int w, int
 // C: run-start pixels jump straight to their root; roots zero their statistics slot.  One thread per word (see B).
 __global__ void __launch_bounds__(CCL_THREADS)
 ccl_flatten_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq, int* __restrict__ label, CompStat* __restrict__ stat,
-                   int init_stats, unsigned* __restrict__ rootbits) {
+                   int init_stats, unsigned* __restrict__ rootbits, int from_roots) {
   const int64_t hw = (int64_t)h * w;
   const int64_t nseg = (int64_t)n * h * wq;
   for (int64_t widx = (int64_t)blockIdx.x * CCL_THREADS + threadIdx.x; widx < nseg; widx += (int64_t)gridDim.x * CCL_THREADS) {
     Seg g; seg_of(widx, h, wq, w, g);
-    int* L = label + g.img * (hw + 1);
+    int* L = label + g.img * lab_stride(hw);
     if (g.y == 0 && g.s == 0) L[hw] = uf_find(L, (int)hw);
-    unsigned st = run_starts(bits[widx], g.nvalid) & valid_mask(g.nvalid);
+    // strip-kernel path (from_roots): every pixel already carries its strip root, so only the strip roots move
+    unsigned st = from_roots ? rootbits[widx] : (run_starts(bits[widx], g.nvalid) & valid_mask(g.nvalid));
     unsigned roots = 0;
     while (st) {
       const int b = __ffs(st) - 1; st &= st - 1;
       const int i = g.y * w + g.x0 + b;
-      const int r = uf_find(L, i);
-      L[i] = r;
+      const int p0 = L[i];
+      const int r = uf_find(L, p0);
+      if (p0 != r) L[i] = r;                        // (after the strip kernel most run starts already hold their final root)
       if (r == i && init_stats) {
         CompStat z;
         z.sum = 0.0; z.acc_sum = 0.0; z.count = 0; z.acc_count = 0;
@@ -385,7 +425,7 @@ __device__ __forceinline__ unsigned inner_bg(unsigned word, unsigned touch, int 
     const unsigned later = b >= 31 ? 0u : (st & ~((2u << b) - 1u));
     const int e = later ? (__ffs(later) - 2) : 31;
     const unsigned m = run_mask(a, e);
-    if (L[ibase + a] != r_out) out |= m;                  // a is the start of a segment run: one hop
+    if (root2(L, ibase + a) != r_out) out |= m;
     cand &= ~m;
   }
   return out;
@@ -452,7 +492,7 @@ ccl_stats_kernel(const float* __restrict__ pred, int c, const unsigned* __restri
     const bool live = widx < nseg;
     Seg g; g.img = 0; g.y = 0; g.s = 0; g.x0 = 0; g.nvalid = 0;
     if (live) seg_of(widx, h, wq, w, g);
-    const int* L = label + g.img * (hw + 1);
+    const int* L = label + g.img * lab_stride(hw);
     CompStat* S = stat + g.img * hw;
     const int r_out = live ? L[hw] : 0;
     const int i0 = g.y * w + g.x0;
@@ -470,7 +510,11 @@ ccl_stats_kernel(const float* __restrict__ pred, int c, const unsigned* __restri
 #pragma unroll
       for (int k = 0; k < 4; ++k) { ra[k] = m ? __ffs(m) - 1 : -1; m &= m - 1; }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) rr[k] = (live && ra[k] >= 0) ? L[i0 + ra[k]] : r_out;      // a segment run start holds its root (final flatten)
+      int l1[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) l1[k] = (live && ra[k] >= 0) ? L[i0 + ra[k]] : -1;          // run start -> (strip) root -> root
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rr[k] = l1[k] >= 0 ? L[l1[k]] : r_out;
     }
     const int nruns = __popc(st);
     const bool need = live && (nruns > 4 || rr[0] != r_out || rr[1] != r_out || rr[2] != r_out || rr[3] != r_out);
@@ -508,7 +552,7 @@ ccl_stats_kernel(const float* __restrict__ pred, int c, const unsigned* __restri
 #pragma unroll
             for (int q = 0; q < 4; ++q) if (q == k) { sums[q] = acc; ends[q] = j; }
           } else {                                   // fifth and later runs of a word (noise): looked up on the spot
-            const int r = L[i0 + a];
+            const int r = root2(L, i0 + a);
             if (r != r_out) {
               agg_add(agg, stat, (unsigned long long)(g.img * hw + r), acc, j - a + 1, g.x0 + a, g.x0 + j, g.y);
               if (!((cur >> a) & 1u)) inner_cur |= run_mask(a, j);
@@ -536,8 +580,8 @@ ccl_stats_kernel(const float* __restrict__ pred, int c, const unsigned* __restri
     // background runs around the word that are NOT the outside region
     unsigned innL = inner_cur << 1, innR = inner_cur >> 1;
     const int prv_start = 31 - __clz(run_starts(prv, 32));                    // start of the run that ends the previous word
-    if ((fg & 1u) && !(prv >> 31) && L[i0 - 32 + prv_start] != r_out) innL |= 1u;
-    if ((fg >> 31) && !(nxt & 1u) && L[i0 + 32] != r_out) innR |= 0x80000000u;
+    if ((fg & 1u) && !(prv >> 31) && root2(L, i0 - 32 + prv_start) != r_out) innL |= 1u;
+    if ((fg >> 31) && !(nxt & 1u) && root2(L, i0 + 32) != r_out) innR |= 0x80000000u;
     const unsigned innU = (fg & ~up) ? inner_bg(up, fg, nv_up, L, i0 - w, r_out) : 0u;
     const unsigned innD = (fg & ~dn) ? inner_bg(dn, fg, nv_up, L, i0 + w, r_out) : 0u;
     unsigned slow = fg & (innL | innR | innU | innD);
@@ -549,14 +593,14 @@ ccl_stats_kernel(const float* __restrict__ pred, int c, const unsigned* __restri
     while (slow) {
       const int b = __ffs(slow) - 1; slow &= slow - 1;
       const unsigned upto = (2u << b) - 1u;
-      const int r = L[i0 + 31 - __clz(st & upto)];
+      const int r = root2(L, i0 + 31 - __clz(st & upto));
       if (r != last_r) { last_r = r; last_pr = S[r].parent; }
       const int pr = last_pr;
       int gq[4] = {-1, -1, -1, -1};
-      if ((innL >> b) & 1u) gq[0] = b > 0 ? L[i0 + 31 - __clz(st & (upto >> 1))] : L[i0 - 32 + prv_start];
-      if ((innR >> b) & 1u) gq[1] = L[i0 + b + 1];                       // the right neighbour of a run end starts a run
-      if ((innU >> b) & 1u) gq[2] = L[i0 - w + 31 - __clz(stU & upto)];
-      if ((innD >> b) & 1u) gq[3] = L[i0 + w + 31 - __clz(stD & upto)];
+      if ((innL >> b) & 1u) gq[0] = b > 0 ? root2(L, i0 + 31 - __clz(st & (upto >> 1))) : root2(L, i0 - 32 + prv_start);
+      if ((innR >> b) & 1u) gq[1] = root2(L, i0 + b + 1);
+      if ((innU >> b) & 1u) gq[2] = root2(L, i0 - w + 31 - __clz(stU & upto));
+      if ((innD >> b) & 1u) gq[3] = root2(L, i0 + w + 31 - __clz(stD & upto));
       const double p = (double)row[b];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -592,7 +636,7 @@ __global__ void __launch_bounds__(CCL_THREADS)
 ccl_tree_kernel(int h, int w, int wq, const int* __restrict__ label, const unsigned* __restrict__ rootbits, CompStat* __restrict__ stat) {
   const int img = blockIdx.y;
   const int64_t hw = (int64_t)h * w;
-  const int* L = label + img * (hw + 1);
+  const int* L = label + img * lab_stride(hw);
   CompStat* S = stat + img * hw;
   const int r_out = L[hw];
   const int nw = h * wq;
@@ -629,7 +673,7 @@ __global__ void __launch_bounds__(CCL_THREADS)
 ccl_count_kernel(int h, int w, int wq, const int* __restrict__ label, const unsigned* __restrict__ rootbits, int* __restrict__ blk_count, int nblk) {
   const int img = blockIdx.y, b = blockIdx.x;
   const int nw = h * wq;
-  const int r_out = label[img * ((int64_t)h * w + 1) + (int64_t)h * w];
+  const int r_out = label[img * lab_stride((int64_t)h * w) + (int64_t)h * w];
   const int c = __popc(cand_bits(rootbits, (int64_t)img * nw, b * CCL_THREADS + threadIdx.x, nw, w, wq, r_out));
   __shared__ int wsum[CCL_THREADS / 32];
   const int ws = warp_sum(c);
@@ -676,7 +720,7 @@ ccl_emit_kernel(const uint8_t* __restrict__ bitmap, int h, int w, int wq, const 
   const int64_t hw = (int64_t)h * w;
   const int nw = h * wq;
   const uint8_t* bm = bitmap + img * hw;
-  const int* L = label + img * (hw + 1);
+  const int* L = label + img * lab_stride(hw);
   CompStat* S = stat + img * hw;
   const int r_out = L[hw];
   const int wi = b * CCL_THREADS + threadIdx.x;
@@ -727,7 +771,7 @@ ccl_emit_kernel(const uint8_t* __restrict__ bitmap, int h, int w, int wq, const 
 __global__ void __launch_bounds__(CCL_THREADS)
 ccl_labels_kernel(const uint8_t* __restrict__ bitmap, int64_t hw, const int* __restrict__ label, int32_t* __restrict__ labels_out) {
   const int img = blockIdx.y;
-  const int* L = label + img * (hw + 1);
+  const int* L = label + img * lab_stride(hw);
   for (int64_t i = (int64_t)blockIdx.x * CCL_THREADS + threadIdx.x; i < hw; i += (int64_t)gridDim.x * CCL_THREADS) {
     const int rr = L[L[i]];                      // run starts carry their root; every other pixel points at its run start
     labels_out[img * hw + i] = bitmap[img * hw + i] ? (rr + 1) : -(rr + 1);
@@ -753,7 +797,7 @@ __device__ __forceinline__ int word_points(const unsigned* __restrict__ bits, in
     const unsigned later = (a >= 31) ? 0u : (st & ~((2u << a) - 1u));
     int b = later ? (__ffs(later) - 2) : 31;
     if (b > g.nvalid - 1) b = g.nvalid - 1;
-    const int r = L[g.y * w + g.x0 + a];                      // run starts carry their root (ccl_flatten_kernel)
+    const int r = root2(L, g.y * w + g.x0 + a);               // pixel -> run start or strip root -> root
     if (r == r_out) continue;
     const int slot = S[r].acc_count;
     if (slot < 0) continue;
@@ -803,7 +847,7 @@ ccl_points_kernel(const unsigned* __restrict__ bits, int n, int h, int w, int wq
     const int* L = nullptr; const CompStat* S = nullptr; int r_out = 0;
     if (in) {
       seg_of(widx, h, wq, w, g);
-      L = label + g.img * (hw + 1); S = stat + g.img * hw; r_out = L[hw];
+      L = label + g.img * lab_stride(hw); S = stat + g.img * hw; r_out = L[hw];
       cnt = word_points<false>(bits, widx, g, h, w, wq, L, S, r_out, nullptr, 0, 0);
     }
     // exclusive prefix of cnt among the lanes of the same image
@@ -849,7 +893,7 @@ extern "C" int dbb_ccl_border_points(const void* workspace, size_t workspace_byt
 
 extern "C" size_t dbb_postprocess_workspace(int64_t n, int64_t h, int64_t w) {
   const int64_t hw = h * w, wq = (w + 31) / 32;
-  return ccl_align(sizeof(unsigned) * (size_t)n * h * wq) + ccl_align(sizeof(int) * (size_t)n * (hw + 1)) +
+  return ccl_align(sizeof(unsigned) * (size_t)n * h * wq) + ccl_align(sizeof(int) * (size_t)n * lab_stride(hw)) +
          ccl_align(sizeof(CompStat) * (size_t)n * hw) + 2 * ccl_align(sizeof(int) * (size_t)n * ccl_nblk(hw)) +
          ccl_align(sizeof(unsigned) * (size_t)n * h * wq) + 256;
 }
@@ -891,11 +935,11 @@ extern "C" int dbb_binarize_ccl_score(const float* pred, int64_t n, int c, int64
     const int64_t nstrips = n * ((h + STRIP_ROWS - 1) / STRIP_ROWS);
     const int gstrip = (int)(nstrips < (int64_t)DBB_NUM_SMS * 64 ? nstrips : (int64_t)DBB_NUM_SMS * 64);
     DBB_LAUNCH("ccl_strip", s, ccl_strip_kernel<<<gstrip, STRIP_THREADS, strip_smem, s>>>(pred, c, (int)n, (int)h, (int)w, wq, thresh, bitmap, ws.bits, ws.label,
-                                                                                      ws.blk_count, word_stores));
+                                                                                      ws.blk_count, ws.rootbits, word_stores));
   } else {
     DBB_LAUNCH("ccl_pack_init", s, ccl_pack_init_kernel<<<grow, CCL_THREADS, 0, s>>>(pred, c, (int)n, (int)h, (int)w, wq, thresh, bitmap, ws.bits, ws.label, word_stores));
     DBB_LAUNCH("ccl_link", s, ccl_link_kernel<<<gword, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, 0, sh, nullptr));
-    if (h > sh) DBB_LAUNCH("ccl_flatten_strips", s, ccl_flatten_kernel<<<gword, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, 0, ws.rootbits));
+    if (h > sh) DBB_LAUNCH("ccl_flatten_strips", s, ccl_flatten_kernel<<<gword, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, 0, ws.rootbits, 0));
   }
   if (h > sh || fused) {
     const int64_t nedge_words = n * ((h - 1) / sh) * wq;
@@ -904,7 +948,7 @@ extern "C" int dbb_binarize_ccl_score(const float* pred, int64_t n, int c, int64
     if (gedge < 1) gedge = 1;
     DBB_LAUNCH("ccl_link_seams", s, ccl_link_kernel<<<gedge, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, 1, sh, fused ? ws.blk_count : nullptr));
   }
-  DBB_LAUNCH("ccl_flatten", s, ccl_flatten_kernel<<<gword, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, 1, ws.rootbits));
+  DBB_LAUNCH("ccl_flatten", s, ccl_flatten_kernel<<<gword, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, 1, ws.rootbits, fused ? 1 : 0));
   DBB_LAUNCH("ccl_stats", s, ccl_stats_kernel<<<(unsigned)((nseg + STATS_WORDS_PER_BLOCK - 1) / STATS_WORDS_PER_BLOCK), CCL_THREADS, 0, s>>>(pred, c, ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, getenv("DBB_CCL_DBG") ? atoi(getenv("DBB_CCL_DBG")) : 0));
   
   const int nwblk = (int)((h * wq + CCL_THREADS - 1) / CCL_THREADS);        // blocks of 256 words in raster order
