@@ -11,16 +11,18 @@
 //   fill(hole border of G)  = G + everything below G + the pixels of G's parent component that are 4-adjacent to G
 //
 // Pipeline (all images in one grid; labels are pixel indices, root = smallest index of the component, so the root IS the
-// raster-first pixel = cv2's discovery point).  A warp owns one 32-pixel row segment of a bit-packed bitmap:
-//   A pack_init  binarize (strict >), pack 32 px / word, byte bitmap, label = first pixel of the segment run   (4 B read, 5 B written / px)
-//   B link       one union per pair of touching runs (fg: vertical + the two diagonals, bg: vertical), segment seams,
-//                frame runs -> virtual outside node; two-level (32-row strips, then strip seams) to keep chains short
-//   C flatten    run starts -> root; roots zero their statistics slot
-//   D stats      final labels + per-run float64 sums (warp prefix sum) -> one atomic set per run; hole boundary rings;
-//                the outside region is skipped (it is no candidate and would serialise the atomics)
-//   E tree       every node adds its statistics to all its ancestors (parent = region north of the root pixel)
-//   F rank/emit  suffix count of roots in raster order = position in cv2's reverse-discovery order -> candidates are
-//                written already sorted, the first max_cands of them (src/postprocess.py:70,119)
+// raster-first pixel = cv2's discovery point).  Everything works on a bit-packed bitmap, 32 pixels per word:
+//   strip    16-row strips in SHARED memory: binarize (strict >), pack, byte bitmap, row-run labels, unions between touching
+//            runs (fg: vertical + the two diagonals, bg: vertical; frame runs -> virtual outside node), flatten; every pixel
+//            leaves the SM once, carrying its strip root                                     (4 B read, ~9 B written / px)
+//            (rows too wide for shared memory: pack_init + link + flatten as three kernels on global memory)
+//   seams    unions across the strip boundaries + each strip's outside root with the image's outside node
+//   flatten  strip roots -> root; roots zero their statistics slot, store their parent region, publish the root bitmap
+//   stats    one thread per word: per-run float64 sums -> shared-memory table per block -> one atomic set per region and
+//            block; hole boundary rings; words of the outside region are skipped before their probabilities are read
+//   tree     every region adds its statistics to all its ancestors (parent = region north of the root pixel)
+//   rank/emit  suffix count of roots in raster order = position in cv2's reverse-discovery order -> candidates are
+//            written already sorted, the first max_cands of them (src/postprocess.py:70,119)
 #include "common.cuh"
 
 namespace dbb {
@@ -435,7 +437,7 @@ __device__ __forceinline__ unsigned inner_bg(unsigned word, unsigned touch, int 
 // and reach the region's global slot as ONE atomic set per block instead of one per run.  (Direct atomics: 19 M RED requests
 // for 64 x 1024^2, the busiest L2 slice 32 % occupied by its atomic unit, 0.62 of the kernel's 0.97 ms.)
 constexpr int AGG_N = 128;
-constexpr int STATS_WORDS_PER_BLOCK = 1024;
+constexpr int STATS_WORDS_PER_BLOCK = 256;
 struct AggEntry { unsigned long long key; double sum, acc_sum; int count, x0, x1, y1, acc_count, pad; };
 constexpr unsigned long long AGG_EMPTY = ~0ull;
 __device__ __forceinline__ void stat_add_global(CompStat* t, double sum, int count, int xa, int xb, int y) {
