@@ -478,7 +478,7 @@ __device__ __forceinline__ void agg_add_ring(AggEntry* agg, CompStat* stat, unsi
 }
 __global__ void __launch_bounds__(CCL_THREADS, 4)
 ccl_stats_kernel(const float* __restrict__ pred, int c, const unsigned* __restrict__ bits, int n, int h, int w, int wq,
-                 const int* __restrict__ label, CompStat* __restrict__ stat, int dbg) {
+                 const int* __restrict__ label, CompStat* __restrict__ stat) {
   __shared__ float tile[CCL_THREADS / 32][32 * 33];
   __shared__ AggEntry agg[AGG_N];
   const int64_t hw = (int64_t)h * w;
@@ -565,7 +565,7 @@ ccl_stats_kernel(const float* __restrict__ pred, int c, const unsigned* __restri
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        if (q < nruns && rr[q] != r_out && !(dbg & 2)) {
+        if (q < nruns && rr[q] != r_out) {
           agg_add(agg, stat, (unsigned long long)(g.img * hw + rr[q]), sums[q], ends[q] - ra[q] + 1, g.x0 + ra[q], g.x0 + ends[q], g.y);
           if (!((cur >> ra[q]) & 1u)) inner_cur |= run_mask(ra[q], ends[q]);
         }
@@ -573,7 +573,7 @@ ccl_stats_kernel(const float* __restrict__ pred, int c, const unsigned* __restri
     }
     // ---- boundary rings of holes
     const unsigned fg = cur & vm;
-    if (!fg || (dbg & 1)) continue;
+    if (!fg) continue;
     const unsigned ones = 0xffffffffu;
     const unsigned curx = cur | ~vm;                                          // beyond the row end: not background
     const int nv_up = g.nvalid;                                               // same column range in the rows above / below
@@ -951,7 +951,7 @@ extern "C" int dbb_binarize_ccl_score(const float* pred, int64_t n, int c, int64
     DBB_LAUNCH("ccl_link_seams", s, ccl_link_kernel<<<gedge, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, 1, sh, fused ? ws.blk_count : nullptr));
   }
   DBB_LAUNCH("ccl_flatten", s, ccl_flatten_kernel<<<gword, CCL_THREADS, 0, s>>>(ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, 1, ws.rootbits, fused ? 1 : 0));
-  DBB_LAUNCH("ccl_stats", s, ccl_stats_kernel<<<(unsigned)((nseg + STATS_WORDS_PER_BLOCK - 1) / STATS_WORDS_PER_BLOCK), CCL_THREADS, 0, s>>>(pred, c, ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat, getenv("DBB_CCL_DBG") ? atoi(getenv("DBB_CCL_DBG")) : 0));
+  DBB_LAUNCH("ccl_stats", s, ccl_stats_kernel<<<(unsigned)((nseg + STATS_WORDS_PER_BLOCK - 1) / STATS_WORDS_PER_BLOCK), CCL_THREADS, 0, s>>>(pred, c, ws.bits, (int)n, (int)h, (int)w, wq, ws.label, ws.stat));
   
   const int nwblk = (int)((h * wq + CCL_THREADS - 1) / CCL_THREADS);        // blocks of 256 words in raster order
   const dim3 gridw((unsigned)nwblk, (unsigned)n);

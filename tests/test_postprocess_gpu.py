@@ -72,6 +72,44 @@ def test_front_matches_oracle_on_batch_and_sizes():
         np.testing.assert_allclose(gs, ws, rtol=1e-12)
 
 
+@pytest.mark.parametrize("shape", [(70, 130), (33, 97), (16, 64), (17, 31), (48, 1030)])
+def test_front_paths_agree_with_the_oracle_on_odd_shapes(shape, monkeypatch):
+    """Both labelling paths -- strips in shared memory (default) and the three global-memory kernels (rows too wide for
+    shared memory; forced here with DBB_CCL_NO_STRIP) -- against the contour-free oracle, on widths that are not multiples
+    of 4 / 32 and heights that are not multiples of the strip height."""
+    h, w = shape
+    maps = [O.synth_prob_map(h, w, 40 + s) for s in range(3)]
+    P = torch.from_numpy(np.stack(maps))[:, None].cuda()
+    want = [O.candidates_ccl(m, 0.25)[1] for m in maps]
+    for no_strip in (False, True):
+        if no_strip:
+            monkeypatch.setenv("DBB_CCL_NO_STRIP", "1")
+        got = rep(max_candidates=5000).candidates(P)
+        for i in range(len(maps)):
+            g = sorted((c["kind"], c["count"], c["bbox"], c["first"]) for c in got[i])
+            wv = sorted((c["kind"], c["count"], c["bbox"], c["first"]) for c in want[i])
+            assert g == wv, (shape, no_strip, i)
+            np.testing.assert_allclose(sorted(c["sum"] for c in got[i]), sorted(c["sum"] for c in want[i]), rtol=1e-12)
+
+
+def test_front_on_rows_too_wide_for_the_strip_kernel():
+    """w = 4,000: 16 rows of labels do not fit in shared memory, the front takes the three-kernel path by itself; it must
+    agree with the strip path run on the same content (two halves side by side never touch: a blank column band between)."""
+    h, w = 40, 4000
+    m = np.zeros((h, w), np.float32)
+    a = O.synth_prob_map(h, 1900, 7)
+    m[:, :1900] = a
+    m[:, 2100:] = a
+    got = rep(max_candidates=20000).candidates(torch.from_numpy(m)[None, None].cuda())[0]
+    half = rep(max_candidates=20000).candidates(torch.from_numpy(np.pad(a, ((0, 0), (0, 100))))[None, None].cuda())[0]
+    # the outer frame background is one region in both; every other region of the half map appears twice in the wide map
+    key = lambda c, dx=0: (c["kind"], c["count"], (c["bbox"][0] - dx, c["bbox"][1], c["bbox"][2] - dx, c["bbox"][3]))
+    left = sorted(key(c) for c in got if c["bbox"][2] < 2000)
+    right = sorted(key(c, 2100) for c in got if c["bbox"][0] >= 2100)
+    ref = sorted(key(c) for c in half if c["bbox"][2] < 1900)
+    assert left == ref and right == ref and len(ref) > 10
+
+
 def test_binarize_is_strict_and_exact():
     r = rep()
     p = torch.tensor([[0.25, 0.2500001, 0.24999999, 0.3, 0.0, 1.0]]).cuda()
