@@ -269,7 +269,8 @@ struct IgemmPSmem {
   static constexpr bool STAGED = BLOCK_N == 64;
   static constexpr int EPI_PITCH = (BLOCK_N / 2) * 2 + 16;
   static constexpr int EPI_OFF = STAT_OFF + 4 * 2 * BLOCK_N * 4;          // + [4 quadrants][2][BLOCK_N] statistics
-  static constexpr int EPI_BYTES = STAGED ? 8 * 32 * EPI_PITCH : 0;
+  static constexpr int EPI_PITCH_F32 = (BLOCK_N / 2) * 4 + 16;           // lean epilogue: raw fp32 accumulators are staged
+  static constexpr int EPI_BYTES = STAGED ? 8 * 32 * EPI_PITCH_F32 : 0;
   static constexpr int TOTAL = EPI_OFF + EPI_BYTES + 1024;
 };
 
@@ -279,7 +280,10 @@ igemm_persist_kernel(const __grid_constant__ IgemmPlan p) {
   using SM = IgemmPSmem<BLOCK_N, STAGES>;
   constexpr int CW = BLOCK_N / 2;                  // columns per epilogue warp
   constexpr int NCH = CW / 16;                     // 16-column chunks per epilogue warp
-  constexpr bool REG_STATS = STATS && CW <= 32;     // 64 accumulator registers; wider tiles would drop to 1 CTA/SM
+  // register statistics (64 accumulators per thread) only with a deep ring, i.e. one CTA per SM: the shallow-ring variant is
+  // for the store-bound launches (conv1, ConvTranspose 64->64, 1x1 laterals), where resident epilogue warps matter more than
+  // the shuffles of the shared-memory reduction
+  constexpr bool REG_STATS = STATS && CW <= 32 && STAGES > 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
@@ -375,7 +379,7 @@ igemm_persist_kernel(const __grid_constant__ IgemmPlan p) {
     constexpr int PP = CW / 8, RPI = 32 / PP;
     // (not with fused statistics: that variant runs one CTA per SM and is bound by the per-tile epilogue latency chain --
     //  measured 0.279 -> 0.375 ms for the two training-mode ConvTranspose launches with the extra shared-memory round trip)
-    const bool staged = SM::STAGED && !STATS && !p.accumulate && !p.no_staged_epilogue && (p.cls_cols == 0 || p.cls_cols % CW == 0);
+    const bool staged = SM::STAGED && !REG_STATS && !p.accumulate && !p.no_staged_epilogue && (p.cls_cols == 0 || p.cls_cols % CW == 0);
     uint8_t* slab = smem + SM::EPI_OFF + (warp - 2) * 32 * SM::EPI_PITCH;
     int s_dn[SM::STAGED ? PP : 1], s_dh[SM::STAGED ? PP : 1], s_dw[SM::STAGED ? PP : 1];
     if (SM::STAGED) {
@@ -385,6 +389,88 @@ igemm_persist_kernel(const __grid_constant__ IgemmPlan p) {
         s_dw[i] = rr % p.bw; s_dh[i] = (rr / p.bw) % p.bh; s_dn[i] = rr / (p.bw * p.bh);
       }
     }
+    // ---- lean epilogue of the 64-wide tiles (conv1, ConvTranspose 64->64, 1x1 laterals: store-bound launches whose epilogue
+    // was ISSUE-bound -- ncu, profiles/prof_convt_r02.md: 550 warp instructions per warp and tile with register statistics,
+    // 966 with the shuffle reduction, for 1,024 outputs).  The raw fp32 accumulators of the warp's 32 x 32 block go to its
+    // shared-memory slab straight from TMEM (both 16-column loads in flight, one wait); they are read back with consecutive
+    // lanes on consecutive 32-byte pieces of a row, so each lane always owns the SAME 8 columns: their bias lives in 8
+    // registers, their BatchNorm statistics in 16 (combined across lanes once per CTA), and a store instruction writes
+    // 8 x 64 contiguous bytes.
+    const bool lean = SM::STAGED && !p.accumulate && !p.epi.scale && !p.no_staged_epilogue && (p.cls_cols == 0 || p.cls_cols % CW == 0);
+    if (SM::STAGED && lean) {
+      const int piece = lane % PP;
+      const int colw = nblk * BLOCK_N + cbase;
+      int valid_cols = p.cout - colw; valid_cols = valid_cols < 0 ? 0 : (valid_cols > CW ? CW : valid_cols);
+      int chw = colw, oh = p.out_oh, ow = p.out_ow;
+      if (p.cls_cols > 0) { const int cls = colw / p.cls_cols; chw = colw - cls * p.cls_cols; oh = cls >> 1; ow = cls & 1; }
+      const bool piece_ok = piece * 8 < valid_cols;
+      float bias8[8], ssum[8], ssq[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { bias8[i] = (p.bias && piece_ok) ? __ldg(p.bias + chw + piece * 8 + i) : 0.f; ssum[i] = 0.f; ssq[i] = 0.f; }
+      uint8_t* fslab = smem + SM::EPI_OFF + (warp - 2) * 32 * SM::EPI_PITCH_F32;
+      bf16* ybase = p.y + p.out_coff + chw + piece * 8;
+      uint32_t j = 0;
+      for (int mt = mt0; mt < m_tiles; mt += mt_step, ++j) {
+        const uint32_t buf = j & 1u;
+        int t = mt;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h; const int tn = t / p.tiles_h;
+        mbar_wait_sleep(&t_full[buf], (j >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)BLOCK_N + (uint32_t)cbase;
+        uint32_t v0[16], v1[16];
+        tmem_ld_x16(taddr, v0);
+        tmem_ld_x16(taddr + 16u, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[buf]);                 // the accumulator buffer is free for tile j + 2
+        uint4* sl = reinterpret_cast<uint4*>(fslab + lane * SM::EPI_PITCH_F32);
+        sl[0] = make_uint4(v0[0], v0[1], v0[2], v0[3]);   sl[1] = make_uint4(v0[4], v0[5], v0[6], v0[7]);
+        sl[2] = make_uint4(v0[8], v0[9], v0[10], v0[11]); sl[3] = make_uint4(v0[12], v0[13], v0[14], v0[15]);
+        sl[4] = make_uint4(v1[0], v1[1], v1[2], v1[3]);   sl[5] = make_uint4(v1[4], v1[5], v1[6], v1[7]);
+        sl[6] = make_uint4(v1[8], v1[9], v1[10], v1[11]); sl[7] = make_uint4(v1[12], v1[13], v1[14], v1[15]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < PP; ++i) {
+          const int n2 = tn * p.bn + s_dn[i], h2 = th * p.bh + s_dh[i], w2 = tw * p.bw + s_dw[i];
+          const bool ok = (s_dn[i] < p.bn) && n2 < p.mn && h2 < p.mh && w2 < p.mw && piece_ok;
+          if (ok) {
+            const float4* src = reinterpret_cast<const float4*>(fslab + (i * RPI + lane / PP) * SM::EPI_PITCH_F32 + piece * 32);
+            const float4 a = src[0], b = src[1];
+            uint4 o;
+            o.x = pack_bf16(a.x + bias8[0], a.y + bias8[1]); o.y = pack_bf16(a.z + bias8[2], a.w + bias8[3]);
+            o.z = pack_bf16(b.x + bias8[4], b.y + bias8[5]); o.w = pack_bf16(b.z + bias8[6], b.w + bias8[7]);
+            const int64_t opix = ((int64_t)n2 * p.out_h + (h2 * p.out_sh + oh)) * p.out_w + (w2 * p.out_sw + ow);
+            *reinterpret_cast<uint4*>(ybase + opix * p.out_c) = o;
+            if (STATS) {                                           // on the bf16-rounded values, as the next layer sees them
+              const float x0 = bf16lo(o.x), x1 = bf16hi(o.x), x2 = bf16lo(o.y), x3 = bf16hi(o.y);
+              const float x4 = bf16lo(o.z), x5 = bf16hi(o.z), x6 = bf16lo(o.w), x7 = bf16hi(o.w);
+              ssum[0] += x0; ssum[1] += x1; ssum[2] += x2; ssum[3] += x3; ssum[4] += x4; ssum[5] += x5; ssum[6] += x6; ssum[7] += x7;
+              ssq[0] = fmaf(x0, x0, ssq[0]); ssq[1] = fmaf(x1, x1, ssq[1]); ssq[2] = fmaf(x2, x2, ssq[2]); ssq[3] = fmaf(x3, x3, ssq[3]);
+              ssq[4] = fmaf(x4, x4, ssq[4]); ssq[5] = fmaf(x5, x5, ssq[5]); ssq[6] = fmaf(x6, x6, ssq[6]); ssq[7] = fmaf(x7, x7, ssq[7]);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (STATS) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+          for (int off = PP; off < 32; off <<= 1) {                // lanes with the same piece
+            ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], off);
+            ssq[i] += __shfl_xor_sync(0xffffffffu, ssq[i], off);
+          }
+        }
+        if (lane < PP) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { w_sum[lane * 8 + i] = ssum[i]; w_sq[lane * 8 + i] = ssq[i]; }
+        }
+        stat_flush<IGP_EPI_THREADS>(p.st, s_stat, BLOCK_N, nblk * BLOCK_N, p.cout, p.cls_cols, p.out_coff, p.out_c,
+                                    (int)threadIdx.x - 64, s_flag);
+      }
+    } else {
     uint32_t j = 0;
     for (int mt = mt0; mt < m_tiles; mt += mt_step, ++j) {
       const uint32_t buf = j & 1u;
@@ -470,6 +556,7 @@ igemm_persist_kernel(const __grid_constant__ IgemmPlan p) {
       }
       stat_flush<IGP_EPI_THREADS>(p.st, s_stat, BLOCK_N, nblk * BLOCK_N, p.cout, p.cls_cols, p.out_coff, p.out_c,
                                   (int)threadIdx.x - 64, s_flag);
+    }
     }
   }
   tc_fence_before();
@@ -1251,7 +1338,11 @@ int igemm_launch(const IgemmPlan& p_in, cudaStream_t s) {
     switch (p.block_n) {
       case 64:
         // statistics in registers (64 accumulators/thread) -> 1 CTA/SM, so that CTA gets a deep ring
-        if (st) return igemm_launch_p2<64, 6, true>(p, s);                                                   // 144 KB (2 CTAs/SM at 96 registers + 3 stages measured slower)
+        if (st) {
+          static const bool deep_st = getenv("DBB_ST64_DEEP") != nullptr;                                    // A/B switch
+          if (!deep_st && depth <= 2) return igemm_launch_p2<64, 2, true>(p, s);                             // lean epilogue, 2 CTAs/SM (a 3-stage ring measured slower for conv1: 0.178 vs 0.132 ms)
+          return igemm_launch_p2<64, 6, true>(p, s);                                                         // 144 KB (2 CTAs/SM at 96 registers + 3 stages measured slower)
+        }
         if (depth <= 2) return igemm_launch_p2<64, 2, false>(p, s);                                          // 48 KB -> 4 CTAs/SM
         return igemm_launch_p2<64, 4, false>(p, s);                                                          // 96 KB -> 2 CTAs/SM
       case 128:
