@@ -234,7 +234,7 @@ def run_ours(args):
     N, S = args.batch, args.size
 
     torch.manual_seed(0)                       # identical replicas on every rank
-    model = DBTextModel().to(dev).train()
+    model = DBTextModel(pretrained=False).to(dev).train()
     crit = DBLoss(alpha=1.0, beta=10.0, reduction=args.reduction, negative_ratio=3)
     use_graph = not args.no_graph and (world == 1 or not args.no_graph_dp)
     if args.torch_adam:

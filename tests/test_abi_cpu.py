@@ -55,7 +55,7 @@ def test_no_compute_metadata_calls(lib):
 
 def test_model_tree_matches_executor_tables(lib):
     from db_text_minimal_b200.models import DBTextModel
-    m = DBTextModel()
+    m = DBTextModel(pretrained=False)
     assert len(m.state_dict()) == 211
     assert m._flat_numel >= 12269378 and m._segment_slices[0][0] == 0 and m._segment_slices[2][1] == m._flat_numel
     used = sum(p.numel() for k, p in m.named_parameters() if not (k.startswith("backbone.fc") or k.startswith("backbone.smooth")))
@@ -161,3 +161,25 @@ def test_gloo_two_rank_gradient_average(tmp_path):
         out, err = p.communicate(timeout=180)
         assert p.returncode == 0, err[-2000:]
         assert "ok" in out
+
+
+def test_pretrained_backbone_is_loaded_from_a_local_file_or_warns(tmp_path, monkeypatch):
+    """resnet18(pretrained=True) (src/modules/resnet.py:245-255): $DBB_RESNET18_WEIGHTS is loaded with strict=False; when
+    nothing can be obtained the backbone stays random AND a RuntimeWarning says so (never silently)."""
+    import warnings
+    from db_text_minimal_b200.modules import resnet as R
+    donor = R.resnet18(pretrained=False)
+    sd = {k: torch.full_like(v, 0.25) if v.dtype.is_floating_point else v for k, v in donor.state_dict().items()}
+    f = tmp_path / "resnet18.pth"
+    torch.save(sd, f)
+    monkeypatch.setenv("DBB_RESNET18_WEIGHTS", str(f))
+    m = R.resnet18(pretrained=True)
+    assert float(m.conv1.weight.min()) == 0.25 and float(m.layer4[1].conv2.weight.max()) == 0.25
+    # nothing local, no network: warn
+    monkeypatch.delenv("DBB_RESNET18_WEIGHTS")
+    monkeypatch.setattr(R, "_imagenet_state_dict", lambda: (_ for _ in ()).throw(OSError("offline")))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m = R.resnet18(pretrained=True)
+    assert any(issubclass(x.category, RuntimeWarning) and "RANDOMLY" in str(x.message) for x in w)
+    assert float(m.conv1.weight.min()) != 0.25

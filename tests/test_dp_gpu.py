@@ -20,7 +20,7 @@ rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
 torch.manual_seed(100 + rank)                      # DIFFERENT seeds on purpose: GradSync must broadcast rank 0's replica
-model = DBTextModel().cuda().train()
+model = DBTextModel(pretrained=False).cuda().train()
 sync = GradSync(model)
 ref = [p.detach().clone() for p in model.parameters()]
 gathered = [torch.empty_like(ref[0]) for _ in range(world)]

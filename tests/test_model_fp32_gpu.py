@@ -36,7 +36,7 @@ def l2rel(a, b):
 
 def build(params, precision):
     from db_text_minimal_b200.models import DBTextModel
-    m = DBTextModel(precision=precision)
+    m = DBTextModel(precision=precision, pretrained=False)
     m.load_state_dict(params, strict=True)
     return m.cuda()
 

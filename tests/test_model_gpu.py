@@ -33,7 +33,7 @@ def bf(t):
 def build(seed, device="cuda"):
     from db_text_minimal_b200.models import DBTextModel
     params = O.init_params(seed)
-    m = DBTextModel()
+    m = DBTextModel(pretrained=False)
     m.load_state_dict(params, strict=True)
     return m.to(device), params
 

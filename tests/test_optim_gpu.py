@@ -16,7 +16,7 @@ def test_flat_adam_matches_torch_adam_on_given_gradients(wd):
     from db_text_minimal_b200.models import DBTextModel
     from db_text_minimal_b200.optim import FlatAdam
     torch.manual_seed(3)
-    model = DBTextModel().cuda().train()
+    model = DBTextModel(pretrained=False).cuda().train()
     ref_params = [p.detach().clone().requires_grad_(True) for p in _used(model)]
     ref = torch.optim.Adam(ref_params, lr=0.005, weight_decay=wd)
     opt = FlatAdam(model, lr=0.005, weight_decay=wd)
@@ -49,7 +49,7 @@ def test_flat_adam_steps_on_the_backward_buffer_without_a_copy():
     from db_text_minimal_b200.optim import FlatAdam
     from db_text_minimal_b200 import synth
     torch.manual_seed(0)
-    model = DBTextModel().cuda().train()
+    model = DBTextModel(pretrained=False).cuda().train()
     opt = FlatAdam(model, lr=0.005)
     crit = DBLoss(alpha=1.0, beta=10.0, reduction="mean", negative_ratio=3)
     img = synth.images(2, 64, 64, seed=1).cuda()
@@ -82,13 +82,13 @@ def test_flat_adam_state_dict_resumes_moments_and_step():
         for p in _used(model):
             p.grad = torch.randn(p.shape, device="cuda", generator=g) * 1e-2
 
-    a = DBTextModel().cuda().train()
+    a = DBTextModel(pretrained=False).cuda().train()
     oa = FlatAdam(a, lr=0.005)
     for _ in range(3):
         grads(a); oa.step()
     sd_m, sd_o = {k: v.clone() for k, v in a.state_dict().items()}, oa.state_dict()
     assert "flat" in sd_o and int(sd_o["flat"]["step"]) == 3
-    b = DBTextModel().cuda().train()
+    b = DBTextModel(pretrained=False).cuda().train()
     b.load_state_dict(sd_m)
     ob = FlatAdam(b, lr=0.005)
     ob.load_state_dict(sd_o)

@@ -69,7 +69,7 @@ def test_submodule_chain_matches_fused_model(training):
     from db_text_minimal_b200.models import DBTextModel
     from db_text_minimal_b200 import synth
     torch.manual_seed(2)
-    model = DBTextModel().cuda()
+    model = DBTextModel(pretrained=False).cuda()
     model.train(training)
     img = synth.images(2, 96, 128, seed=3).cuda()
     with torch.no_grad():
@@ -95,7 +95,7 @@ def test_submodule_chain_backward_reaches_every_parameter():
     from db_text_minimal_b200.losses import DBLoss
     from db_text_minimal_b200 import synth
     torch.manual_seed(4)
-    model = DBTextModel().cuda().train()
+    model = DBTextModel(pretrained=False).cuda().train()
     img = synth.images(2, 64, 64, seed=5).cuda()
     gts = torch.from_numpy(synth.gt_maps(2, 64, 64, seed=5)).cuda()
     out = model.segmentation_head(model.segmentation_body(model.backbone(img)))

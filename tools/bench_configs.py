@@ -25,7 +25,7 @@ def config4(n=64, s=1024):
     (0.5) + unclip ratio 1.5.  Model and post-processing are timed separately and together; the post-processing input is a
     synthetic blob map (a randomly initialised network's P sits near 0.5 everywhere: SURVEY section 8c)."""
     torch.manual_seed(0)
-    model = DBTextModel().cuda().eval()
+    model = DBTextModel(pretrained=False).cuda().eval()
     x = synth.images(n, s, s, 0).cuda()
     ms_model = timed(lambda: model(x), 5)
     maps = np.stack([((synth.prob_map(s, s, 100 + i) - 0.45) * 8).clip(0, 1) for i in range(8)])

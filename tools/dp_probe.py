@@ -15,7 +15,7 @@ dist.all_reduce(x); torch.cuda.synchronize(); log("allreduce ok", x.tolist())
 from db_text_minimal_b200 import DBLoss, DBTextModel, synth
 from db_text_minimal_b200.dist import GradSync
 torch.manual_seed(0)
-model = DBTextModel().cuda().train()
+model = DBTextModel(pretrained=False).cuda().train()
 sync = GradSync(model)
 crit = DBLoss(reduction="none")
 opt = torch.optim.Adam(model.parameters(), lr=0.005, fused=True)

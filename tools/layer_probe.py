@@ -41,7 +41,7 @@ def read_taps(m, x, training, names):
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 150
     params = O.init_params(O.COND_SEED)
-    m = DBTextModel(precision="bf16")
+    m = DBTextModel(precision="bf16", pretrained=False)
     m.load_state_dict(params)
     m = m.cuda().train()
     opt = FlatAdam(m, lr=0.005)
@@ -52,7 +52,7 @@ def main():
         opt.zero_grad(); ls[-1].backward(); opt.step()
     print("trained; loss", float(ls[-1]))
     sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
-    m32 = DBTextModel(precision="fp32")
+    m32 = DBTextModel(precision="fp32", pretrained=False)
     m32.load_state_dict(sd)
     m32 = m32.cuda()
     names = ["x1"] + [f"block{i}.out" for i in range(8)] + ["p5", "l4", "p4", "l3", "p3", "l2", "cat", "af", "ah"]
