@@ -152,6 +152,49 @@ def reference_rate(batch, size, reduction, steps, warmup, budget_s):
             "sample": sample, "images": ref.batch, "median_sec": sorted(times)[len(times) // 2]}
 
 
+def reference_gpu_rate(batch, size, reduction, steps=10, warmup=3):
+    """Secondary baseline: the SAME unmodified reference step (oracle/_ref) as torch eager + cuDNN on this GPU, so that the
+    comparison is not only GPU-vs-CPU.  Two variants: the reference as it is (fp32; cuDNN may use TF32, torch's default)
+    and its forward under bf16 autocast (loss in fp32: binary_cross_entropy refuses autocast).  Returns None when the
+    reference files are not staged."""
+    import torch
+    from oracle import db_oracle as O
+    from oracle import ref_import
+    if not ref_import.available() or not torch.cuda.is_available():
+        return None
+    _, losses, _ = ref_import.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    x = O.synth_images(batch, size, size, 0).to(dev)
+    gts = torch.from_numpy(O.synth_gt_maps(batch, size, size, 0)).to(dev)
+    out = {"impl": "unmodified reference (oracle/_ref), torch eager + cuDNN on the same GPU, batch %d, fwd+DBLoss(%s)+bwd+Adam" % (batch, reduction)}
+    for name, autocast in (("fp32", False), ("bf16_autocast_forward", True)):
+        model = ref_import.build_model(O.init_params(0)).to(dev).train()
+        crit = losses.DBLoss(alpha=1.0, beta=10.0, reduction=reduction, negative_ratio=3)
+        opt = torch.optim.Adam(model.parameters(), lr=0.005, weight_decay=0.0, amsgrad=False)
+
+        def step():
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                preds = model(x)
+            total = crit(preds.float(), gts)[-1]
+            opt.zero_grad()
+            total.backward()
+            opt.step()
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[name] = {"value": batch / ms * 1e3, "unit": "img/s", "ms_per_step": ms}
+        del model, opt
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -472,6 +515,11 @@ def run_ours(args):
         if not args.no_cpu_baseline and world == 1:
             r = reference_rate(min(args.cpu_batch, N), S, args.reduction, 3, 1, budget_s=60.0)
             out["cpu_baseline"] = {"value": r["rate"], "unit": "img/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+            try:                      # secondary, same-device baseline (never the thing measured as `value`)
+                torch.cuda.empty_cache()
+                out["reference_on_gpu"] = reference_gpu_rate(N, S, args.reduction)
+            except Exception as e:
+                out["reference_on_gpu"] = {"error": f"{type(e).__name__}: {e}"}
         else:
             out["cpu_baseline"] = None
         print(json.dumps(out), flush=True)
