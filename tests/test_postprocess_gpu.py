@@ -110,6 +110,24 @@ def test_front_on_rows_too_wide_for_the_strip_kernel():
     assert left == ref and right == ref and len(ref) > 10
 
 
+def test_front_with_more_strips_than_resident_blocks():
+    """640 maps of 256 x 32: 10,240 strips of 16 rows, more than the strip kernel's grid cap (148 x 64 blocks), so its
+    blocks loop over several strips and reuse their shared-memory arrays; every image must come out as when run alone."""
+    base = [O.synth_prob_map(256, 32, 60 + s) for s in range(8)]
+    n = 640
+    P = torch.from_numpy(np.stack([base[i % 8] for i in range(n)]))[:, None].cuda()
+    r = rep(max_candidates=5000)
+    _, _, rec, nc = r.front(P)
+    single = [r.front(torch.from_numpy(b)[None, None].cuda()) for b in base]
+    for i in list(range(16)) + [n // 2, n - 9, n - 1]:
+        _, _, rec1, nc1 = single[i % 8]
+        assert int(nc[i]) == int(nc1[0])
+        a, b = rec[i][:int(nc[i])], rec1[0][:int(nc1[0])]
+        for f in ("kind", "first_y", "first_x", "x0", "y0", "x1", "y1", "count", "keep"):
+            assert np.array_equal(a[f], b[f]), (i, f)
+        np.testing.assert_allclose(a["sum"], b["sum"], rtol=1e-12)
+
+
 def test_binarize_is_strict_and_exact():
     r = rep()
     p = torch.tensor([[0.25, 0.2500001, 0.24999999, 0.3, 0.0, 1.0]]).cuda()
