@@ -72,7 +72,7 @@ def test_front_matches_oracle_on_batch_and_sizes():
         np.testing.assert_allclose(gs, ws, rtol=1e-12)
 
 
-@pytest.mark.parametrize("shape", [(70, 130), (33, 97), (16, 64), (17, 31), (48, 1030)])
+@pytest.mark.parametrize("shape", [(70, 130), (33, 97), (16, 64), (17, 31), (48, 1030), (9, 2100)])
 def test_front_paths_agree_with_the_oracle_on_odd_shapes(shape, monkeypatch):
     """Both labelling paths -- strips in shared memory (default) and the three global-memory kernels (rows too wide for
     shared memory; forced here with DBB_CCL_NO_STRIP) -- against the contour-free oracle, on widths that are not multiples
