@@ -506,6 +506,8 @@ def run_ours(args):
         torch.cuda.empty_cache()
         try:
             from tools import bench_configs
+            out["config1"] = bench_configs.config1()
+            torch.cuda.empty_cache()
             out["config4"] = bench_configs.config4()
             torch.cuda.empty_cache()
             out["config5"] = bench_configs.config5()

@@ -20,6 +20,39 @@ def timed(fn, iters, warm=2):
     return e0.elapsed_time(e1) / iters
 
 
+def config1(s=640):
+    """BASELINE config 1: the reference's own CPU-runnable case, 1 x 3 x 640 x 640 eval forward + post-processing (thresh
+    0.25, box_thresh 0.5, unclip 1.5), here on the GPU: latency of the model, of `SegDetectorRepresenter.__call__` in both
+    modes on a synthetic probability map of that size, and of the two back to back (wall clock, host included)."""
+    torch.manual_seed(0)
+    model = DBTextModel(pretrained=False).cuda().eval()
+    x = synth.images(1, s, s, 0).cuda()
+    with torch.no_grad():
+        ms_model = timed(lambda: model(x), 20, warm=5)
+    P = torch.from_numpy(((synth.prob_map(s, s, 100) - 0.45) * 8).clip(0, 1))[None, None].cuda()
+    rep = SegDetectorRepresenter(thresh=0.25, box_thresh=0.5, unclip_ratio=1.5)
+    shape = {"shape": [(s, s)]}
+    out = {"workload": f"eval forward 1x3x{s}x{s} + post-processing (BASELINE config 1)", "model_ms": ms_model}
+    for mode, key in ((False, "post_box_ms"), (True, "post_polygon_ms")):
+        for _ in range(3):
+            rep(shape, P, is_output_polygon=mode)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            boxes, _ = rep(shape, P, is_output_polygon=mode)
+        torch.cuda.synchronize()
+        out[key] = (time.perf_counter() - t0) * 1e3 / 20
+    t0 = time.perf_counter()
+    for _ in range(20):
+        with torch.no_grad():
+            model(x)
+        rep(shape, P, is_output_polygon=False)
+    torch.cuda.synchronize()
+    out["model_plus_post_box_ms"] = (time.perf_counter() - t0) * 1e3 / 20
+    out["img_s"] = 1e3 / out["model_plus_post_box_ms"]
+    return out
+
+
 def config4(n=64, s=1024):
     """BASELINE config 4: batched inference 64 x 1024 x 1024 with GPU binarize (0.25) + connected components + box score
     (0.5) + unclip ratio 1.5.  Model and post-processing are timed separately and together; the post-processing input is a
