@@ -510,14 +510,23 @@ void approx_poly_dp_closed(const std::vector<IPt>& src, double eps, std::vector<
     pos = slice.start;
     read_pt(start_pt, pos);
     if (pos != slice.end) {
+      // Squared distance to the SEGMENT start..end (a point that projects beyond an end is measured to that end), not to
+      // the infinite line: this is what OpenCV 4.13 does.  The line version agrees on ~99.8 % of contours; on long contours a
+      // farthest point that lies beyond the chord's end differs (2 of 1,275 contours in a soak; with this rule 0 of 54,844
+      // contour / epsilon pairs differ from cv2.approxPolyDP).
       double max_dist = 0;
-      const double dx = end_pt.x - start_pt.x, dy = end_pt.y - start_pt.y;
+      const double dx = end_pt.x - start_pt.x, dy = end_pt.y - start_pt.y, len2 = dx * dx + dy * dy;
       while (pos != slice.end) {
         read_pt(pt, pos);
-        const double dist = std::fabs((pt.y - start_pt.y) * dx - (pt.x - start_pt.x) * dy);
+        const double px = pt.x - start_pt.x, py = pt.y - start_pt.y;
+        const double t = px * dx + py * dy;
+        double dist;
+        if (t < 0 || len2 == 0) dist = px * px + py * py;
+        else if (t > len2) { const double qx = pt.x - end_pt.x, qy = pt.y - end_pt.y; dist = qx * qx + qy * qy; }
+        else { const double cr = py * dx - px * dy; dist = cr * cr / len2; }
         if (dist > max_dist) { max_dist = dist; right_slice.start = (pos + count - 1) % count; }
       }
-      le_eps = max_dist * max_dist <= eps * (dx * dx + dy * dy);
+      le_eps = max_dist <= eps;                       // eps is squared (above)
     } else {
       le_eps = true;
       start_pt = src[slice.start];

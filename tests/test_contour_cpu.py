@@ -40,7 +40,9 @@ def bitmaps():
     from oracle import db_oracle as O
     z = np.load(os.path.join(GOLD, "post_cases.npz"))
     maps = {nm: z[nm + ":bitmap"].astype(np.uint8) for nm in sorted({k.split(":")[0] for k in z.files})}
-    for seed, (h, w) in [(11, (256, 320)), (13, (640, 640))]:
+    # (2022 / 2035: maps whose long contours have a farthest point BEYOND the end of a chord -- OpenCV measures the distance to
+    #  the segment there, not to the line; the line version returned one different vertex on each)
+    for seed, (h, w) in [(11, (256, 320)), (13, (640, 640)), (2022, (314, 627)), (2035, (414, 292))]:
         P = ((O.synth_prob_map(h, w, seed) - 0.45) * 8).clip(0, 1).astype(np.float32)
         maps[f"kept{seed}"] = O.binarize(P, 0.25).astype(np.uint8)
     rng = np.random.default_rng(5)
@@ -97,6 +99,11 @@ def test_arc_length_and_approx_poly_dp_match_cv2(name):
         got, al = approx(c)
         assert abs(al - al_ref) <= 1e-9 * max(1.0, al_ref)
         assert np.array_equal(got, want), (name, len(c))
+        for eps in (0.02 * al_ref, 1.0, 2.5):                      # other tolerances: more chords whose far point lies beyond an end
+            cc = np.ascontiguousarray(c.reshape(-1, 2).astype(np.int32))
+            out = np.zeros((len(cc) + 4, 2), np.int32)
+            n = lib().dbb_approx_poly_dp(cc.ctypes.data, len(cc), float(eps), out.ctypes.data, len(out), None)
+            assert np.array_equal(out[:n], cv2.approxPolyDP(c, eps, True).reshape(-1, 2)), (name, len(c), eps)
 
 
 def test_approx_poly_dp_absolute_epsilon_and_tiny_inputs():
